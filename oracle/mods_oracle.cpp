@@ -1,0 +1,649 @@
+/*
+ * mods_oracle.cpp -- CPU restatement of the MODS hot path.  TEST INFRASTRUCTURE ONLY
+ * (see mods_oracle.h).  Build: oracle/Makefile (g++ -O2 -ffp-contract=off -mfma).
+ *
+ * All float arithmetic is written with explicit fmaf() where the reference's
+ * third-party back end (OpenCV 4.13 SIMD kernels) fuses, and plain ops elsewhere;
+ * the file MUST be compiled with -ffp-contract=off so the compiler adds no fusion.
+ *
+ * Citations are file:line in the upstream tree (ducha-aiki/mods-light-zmq @ 33c9ba2).
+ */
+#include "mods_oracle.h"
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+/* ========================================================================== */
+/* image primitives                                                           */
+/* ========================================================================== */
+
+/* synth-detection.cpp:344-351: convertTo(CV_32FC3); split; (p0+p1+p2)/3.0.
+ * The MatExpr "/3.0" is evaluated by cv::Mat::convertTo(alpha = 1.0/3.0) whose
+ * 32f->32f kernel multiplies by (float)alpha. */
+extern "C" void orc_gray_from_bgr(const uint8_t* bgr, int w, int h, float* gray) {
+  const float third = (float)(1.0 / 3.0);
+  for (long i = 0; i < (long)w * h; i++) {
+    float s = ((float)bgr[3 * i] + (float)bgr[3 * i + 1]) + (float)bgr[3 * i + 2];
+    gray[i] = s * third;
+  }
+}
+
+/* cv::getGaussianKernel(ksize, sigma, CV_32F) as called by cv::GaussianBlur from
+ * helpers.cpp:717-731: ksize = (int)(2*3*sigma+1), forced odd. */
+extern "C" int orc_gaussian_kernel(float sigmaf, float* taps) {
+  double sigma = (double)sigmaf;
+  int ks = (int)(2.0 * 3.0 * sigma + 1.0);
+  if (ks % 2 == 0) ks++;
+  int r = ks / 2;
+  std::vector<double> kd(ks);
+  double sum = 0;
+  for (int i = 0; i < ks; i++) {
+    double x = i - r;
+    kd[i] = std::exp(-x * x / (2.0 * sigma * sigma));
+    sum += kd[i];
+  }
+  for (int i = 0; i < ks; i++) taps[i] = (float)(kd[i] / sum);
+  return ks;
+}
+
+/* helpers.cpp:717-731 gaussianBlur()/gaussianBlurInplace(): cv::GaussianBlur with
+ * BORDER_REPLICATE.  Arithmetic order = OpenCV 4.13 sepFilter2D for CV_32F as shipped
+ * in the cv2 wheel of this image (AVX2/AVX-512 dispatch), established empirically and
+ * pinned bit-exactly by tests/test_oracle_cv2_pin.py:
+ *   row pass, ksize>=7 : x <  w&~3 : s=0; s=fma(src[x-r+t],k[t],s) for t=0..ks-1
+ *                        x >= w&~3 : s=src[x-r]*k[0]; s+=src*k[t] unfused, except the
+ *                                    last (ks-1)%4 taps which are fused (scalar tail as
+ *                                    compiled in the wheel)
+ *   row pass, ksize==5 : x <  w&~1 : s=(x[+1]+x[-1])*k1; s=fma(x0,k0,s); s=fma(x[+2]+x[-2],k2,s)
+ *                        else      : s=(x0*k0+(x[+1]+x[-1])*k1)+(x[+2]+x[-2])*k2  (unfused)
+ *   col pass           : s=c*k0; for t=1..r: s (+)= (up_t+down_t)*k[t], fused iff x < w&~7
+ */
+extern "C" void orc_gaussian_blur(const float* in, float* out, int w, int h, float sigma) {
+  std::vector<float> k(4096);
+  int ks = orc_gaussian_kernel(sigma, k.data());
+  int r = ks / 2;
+  std::vector<float> tmp((size_t)w * h);
+  const int wv = w & ~3, wc = w & ~7;
+  auto PX = [&](int y, int xx) -> float {
+    xx = xx < 0 ? 0 : (xx >= w ? w - 1 : xx);
+    return in[(size_t)y * w + xx];
+  };
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) {
+      float s;
+      if (ks == 5) {
+        float p1 = PX(y, x + 1) + PX(y, x - 1), p2 = PX(y, x + 2) + PX(y, x - 2), x0 = PX(y, x);
+        if (x < (w & ~1)) {
+          s = p1 * k[3];
+          s = fmaf(x0, k[2], s);
+          s = fmaf(p2, k[4], s);
+        } else {
+          s = x0 * k[2] + p1 * k[3];
+          s = s + p2 * k[4];
+        }
+      } else if (ks < 5) { /* not reachable from the hot path (sigma >= 0.75); plain symmetric sum */
+        s = PX(y, x) * k[r];
+        for (int t = 1; t <= r; t++) s = s + (PX(y, x + t) + PX(y, x - t)) * k[r + t];
+      } else if (x < wv) {
+        s = 0;
+        for (int t = 0; t < ks; t++) s = fmaf(PX(y, x + t - r), k[t], s);
+      } else {
+        int nf = (ks - 1) % 4;
+        s = PX(y, x - r) * k[0];
+        for (int t = 1; t < ks; t++) {
+          if (t >= ks - nf) s = fmaf(PX(y, x + t - r), k[t], s);
+          else s = s + PX(y, x + t - r) * k[t];
+        }
+      }
+      tmp[(size_t)y * w + x] = s;
+    }
+  auto TY = [&](int yy, int x) -> float {
+    yy = yy < 0 ? 0 : (yy >= h ? h - 1 : yy);
+    return tmp[(size_t)yy * w + x];
+  };
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) {
+      float s = tmp[(size_t)y * w + x] * k[r];
+      if (x < wc)
+        for (int t = 1; t <= r; t++) s = fmaf(TY(y - t, x) + TY(y + t, x), k[r + t], s);
+      else
+        for (int t = 1; t <= r; t++) s = s + (TY(y - t, x) + TY(y + t, x)) * k[r + t];
+      out[(size_t)y * w + x] = s;
+    }
+}
+
+/* pyramid.cpp:196-254 HessianResponse: 3x3 stencil, interior only.  The reference
+ * leaves the 1-px frame uninitialised (Mat without zeroing, :203); the oracle defines it
+ * as 0 -- it is never read with border >= 2. */
+extern "C" void orc_hessian_response(const float* in, float* out, int w, int h, float norm) {
+  const float norm2 = norm * norm;
+  std::memset(out, 0, sizeof(float) * (size_t)w * h);
+  for (int r = 1; r < h - 1; r++)
+    for (int c = 1; c < w - 1; c++) {
+      const float* p = in + (size_t)r * w + c;
+      float v11 = p[-w - 1], v12 = p[-w], v13 = p[-w + 1];
+      float v21 = p[-1], v22 = p[0], v23 = p[1];
+      float v31 = p[w - 1], v32 = p[w], v33 = p[w + 1];
+      float Lxx = (v21 - 2 * v22 + v23);
+      float Lyy = (v12 - 2 * v22 + v32);
+      float Lxy = (v13 - v11 + v31 - v33) / 4.0f;
+      out[(size_t)r * w + c] = (Lxx * Lyy - Lxy * Lxy) * norm2;
+    }
+}
+
+/* pyramid.cpp:476 cv::resize(nextBlur, next, Size(0,0), 0.5, 0.5, INTER_LINEAR).
+ * dsize = cvRound(w*0.5) (round-half-even).  Sample position 2*d+0.5 -> weights (.5,.5).
+ * cv2 4.13 of this image routes 32F INTER_LINEAR through its IPP HAL, whose arithmetic is
+ * the lerp form a+(b-a)*0.5 horizontally then vertically (pinned bit-exactly by
+ * tests/test_oracle_cv2_pin.py for even sizes; odd sizes clamp the +1 neighbour). */
+extern "C" void orc_half_size(int w, int h, int* ow, int* oh) {
+  *ow = (int)std::nearbyint(w * 0.5);
+  *oh = (int)std::nearbyint(h * 0.5);
+}
+extern "C" void orc_half_image(const float* in, int w, int h, float* out) {
+  int ow, oh;
+  orc_half_size(w, h, &ow, &oh);
+  for (int y = 0; y < oh; y++) {
+    int y0 = std::min(2 * y, h - 1), y1 = std::min(2 * y + 1, h - 1);
+    for (int x = 0; x < ow; x++) {
+      int x0 = std::min(2 * x, w - 1), x1 = std::min(2 * x + 1, w - 1);
+      float a = in[(size_t)y0 * w + x0], b = in[(size_t)y0 * w + x1];
+      float c = in[(size_t)y1 * w + x0], d = in[(size_t)y1 * w + x1];
+      float r0 = a + (b - a) * 0.5f;
+      float r1 = c + (d - c) * 0.5f;
+      out[(size_t)y * ow + x] = r0 + (r1 - r0) * 0.5f;
+    }
+  }
+}
+
+/* ========================================================================== */
+/* detector                                                                   */
+/* ========================================================================== */
+
+/* helpers.cpp:309-368 solveLinear3x3 (pivoted Gauss, float) */
+static void solveLinear3x3(float* A, float* b) {
+  int i = 0;
+  float* pr = A;
+  float vp = std::fabs(A[0]);
+  float tmp = std::fabs(A[3]);
+  if (tmp > vp) { pr = A + 3; i = 1; vp = tmp; }
+  if (std::fabs(A[6]) > vp) { pr = A + 6; i = 2; }
+  if (pr != A) {
+    std::swap(pr[0], A[0]); std::swap(pr[1], A[1]); std::swap(pr[2], A[2]);
+    std::swap(b[i], b[0]);
+  }
+  vp = A[3] / A[0]; A[4] -= vp * A[1]; A[5] -= vp * A[2]; b[1] -= vp * b[0];
+  vp = A[6] / A[0]; A[7] -= vp * A[1]; A[8] -= vp * A[2]; b[2] -= vp * b[0];
+  if (std::fabs(A[4]) < std::fabs(A[7])) {
+    std::swap(A[7], A[4]); std::swap(A[8], A[5]); std::swap(b[2], b[1]);
+  }
+  vp = A[7] / A[4]; A[8] -= vp * A[5]; b[2] -= vp * b[1];
+  b[2] = (b[2]) / A[8];
+  b[1] = (b[1] - A[5] * b[2]) / A[4];
+  b[0] = (b[0] - A[2] * b[2] - A[1] * b[1]) / A[0];
+}
+
+namespace {
+struct Detector {
+  orc_pyr_params P;
+  /* pyramid.h:46-66 derived constants */
+  double edgeScoreThreshold;
+  float finalThreshold, positiveThreshold, negativeThreshold;
+  int w = 0, h = 0;
+  std::vector<float> low, cur, high, blur, prevBlur;
+  std::vector<unsigned char> octaveMap;
+  std::vector<orc_keypoint> keys;
+  int octave = 0, level = 0;
+
+  explicit Detector(const orc_pyr_params& p) : P(p) {
+    edgeScoreThreshold = (p.edgeEigenValueRatio + 1.0f) * (p.edgeEigenValueRatio + 1.0f) / p.edgeEigenValueRatio;
+    finalThreshold = p.threshold;
+    positiveThreshold = (float)(0.8 * finalThreshold);
+    negativeThreshold = -positiveThreshold;
+    finalThreshold = p.threshold * p.threshold; /* DET_HESSIAN, FIXED_TH */
+  }
+
+  /* pyramid.cpp:41-63 */
+  bool isMax(float val, const std::vector<float>& pix, int row, int col) const {
+    for (int r = row - 1; r <= row + 1; r++)
+      for (int c = col - 1; c <= col + 1; c++)
+        if (pix[(size_t)r * w + c] > val) return false;
+    return true;
+  }
+  bool isMin(float val, const std::vector<float>& pix, int row, int col) const {
+    for (int r = row - 1; r <= row + 1; r++)
+      for (int c = col - 1; c <= col + 1; c++)
+        if (pix[(size_t)r * w + c] < val) return false;
+    return true;
+  }
+
+  /* pyramid.cpp:281-403 */
+  void localizeKeypoint(int r, int c, float curScale, float pixelDistance) {
+    const int cols = w, rows = h;
+    const int r0 = r, c0 = c;
+    float b[3] = {};
+    float val = 0;
+    int nr = r, nc = c;
+    for (int iter = 0; iter < 5; iter++) {
+      r = nr; c = nc;
+      const float* cur0 = &cur[(size_t)(r - 1) * w]; const float* cur1 = &cur[(size_t)r * w]; const float* cur2 = &cur[(size_t)(r + 1) * w];
+      const float* low0 = &low[(size_t)(r - 1) * w]; const float* low1 = &low[(size_t)r * w]; const float* low2 = &low[(size_t)(r + 1) * w];
+      const float* high0 = &high[(size_t)(r - 1) * w]; const float* high1 = &high[(size_t)r * w]; const float* high2 = &high[(size_t)(r + 1) * w];
+      float dxx = cur1[c - 1] - 2.0f * cur1[c] + cur1[c + 1];
+      float dyy = cur0[c] - 2.0f * cur1[c] + cur2[c];
+      float dss = low1[c] - 2.0f * cur1[c] + high1[c];
+      float dxy = 0.25f * (cur2[c + 1] - cur2[c - 1] - cur0[c + 1] + cur0[c - 1]);
+      if (0 == iter) {
+        float edgeScore = (dxx + dyy) * (dxx + dyy) / (dxx * dyy - dxy * dxy);
+        if (edgeScore >= edgeScoreThreshold || edgeScore < 0) return;
+      }
+      float dxs = 0.25f * (high1[c + 1] - high1[c - 1] - low1[c + 1] + low1[c - 1]);
+      float dys = 0.25f * (high2[c] - high0[c] - low2[c] + low0[c]);
+      float A[9] = {dxx, dxy, dxs, dxy, dyy, dys, dxs, dys, dss};
+      float dx = 0.5f * (cur1[c + 1] - cur1[c - 1]);
+      float dy = 0.5f * (cur2[c] - cur0[c]);
+      float ds = 0.5f * (high1[c] - low1[c]);
+      b[0] = -dx; b[1] = -dy; b[2] = -ds;
+      solveLinear3x3(A, b);
+      if (std::isnan(b[0]) || std::isnan(b[1]) || std::isnan(b[2])) return;
+      val = cur1[c] + 0.5f * (dx * b[0] + dy * b[1] + ds * b[2]);
+      /* MAX_SUBPIXEL_SHIFT 0.6 is a double literal (pyramid.cpp:25): float promoted */
+      if (b[0] > 0.6) { if (c < cols - 3) nc++; else return; }
+      if (b[1] > 0.6) { if (r < rows - 3) nr++; else return; }
+      if (b[0] < -0.6) { if (c > 3) nc--; else return; }
+      if (b[1] < -0.6) { if (r > 3) nr--; else return; }
+      if (nr == r && nc == c) break;
+    }
+    if (std::fabs(b[0]) > 1.5 || std::fabs(b[1]) > 1.5 || std::fabs(b[2]) > 1.5 ||
+        std::fabs(val) < finalThreshold || octaveMap[(size_t)r * w + c] > 0)
+      return;
+    octaveMap[(size_t)r * w + c] = 1;
+    /* pyramid.cpp:392: curScale * pow(2.0f, b[2]/numberOfScales)  -- powf in the reference;
+     * the oracle (and the kernel) evaluate 2^e in double and round once. */
+    float e = b[2] / P.numberOfScales;
+    float scale = curScale * (float)std::exp2((double)e);
+    /* pyramid.cpp:65-124 getPointType on `blur` (the image of `cur`) */
+    int type;
+    if (val < 0) type = 2;
+    else {
+      const float* ptr = &blur[(size_t)r * w + c];
+      float Lxx = (ptr[-1] - 2 * ptr[0] + ptr[1]);
+      type = (Lxx < 0) ? 0 : 1;
+    }
+    orc_keypoint k;
+    k.x = pixelDistance * (c + b[0]);
+    k.y = pixelDistance * (r + b[1]);
+    k.s = pixelDistance * scale;
+    k.response = val;
+    k.type = type;
+    k.octave = octave; k.level = level;
+    k.r0 = r0; k.c0 = c0; k.r = r; k.c = c;
+    k.seq = (int)keys.size();
+    keys.push_back(k);
+  }
+
+  /* pyramid.cpp:405-425 */
+  void findLevelKeypoints(float curScale, float pixelDistance) {
+    for (int r = P.border; r < (h - P.border); r++)
+      for (int c = P.border; c < (w - P.border); c++) {
+        const float val = cur[(size_t)r * w + c];
+        if ((val > positiveThreshold && (isMax(val, cur, r, c) && isMax(val, low, r, c) && isMax(val, high, r, c))) ||
+            (val < negativeThreshold && (isMin(val, cur, r, c) && isMin(val, low, r, c) && isMin(val, high, r, c))))
+          localizeKeypoint(r, c, curScale, pixelDistance);
+      }
+  }
+
+  /* pyramid.cpp:428-494 */
+  void detectOctave(const std::vector<float>& firstLevel, int W, int H, float pixelDistance,
+                    std::vector<float>& nextFirst, int& nW, int& nH) {
+    w = W; h = H;
+    octaveMap.assign((size_t)w * h, 0);
+    float sigmaStep = std::pow(2.0f, 1.0f / (float)P.numberOfScales);
+    float curSigma = P.initialSigma;
+    int numLevels = 1;
+    blur = firstLevel;
+    cur.resize((size_t)w * h); high.resize((size_t)w * h);
+    orc_hessian_response(blur.data(), cur.data(), w, h, curSigma * curSigma);
+    level = 0;
+    for (int i = 1; i < P.numberOfScales + 2; i++) {
+      float sigma = curSigma * std::sqrt(sigmaStep * sigmaStep - 1.0f);
+      std::vector<float> nextBlur((size_t)w * h);
+      orc_gaussian_blur(blur.data(), nextBlur.data(), w, h, sigma);
+      sigma = curSigma * sigmaStep;
+      orc_hessian_response(nextBlur.data(), high.data(), w, h, sigma * sigma);
+      numLevels++;
+      if (numLevels == 3) {
+        level = i - 1;
+        findLevelKeypoints(curSigma, pixelDistance);
+        numLevels--;
+      }
+      if (i == P.numberOfScales) {
+        orc_half_size(w, h, &nW, &nH);
+        nextFirst.resize((size_t)nW * nH);
+        orc_half_image(nextBlur.data(), w, h, nextFirst.data());
+      }
+      prevBlur.swap(blur);
+      blur.swap(nextBlur);
+      low.swap(cur);
+      cur.swap(high);
+      high.resize((size_t)w * h);
+      curSigma *= sigmaStep;
+    }
+  }
+};
+}  // namespace
+
+/* pyramid.cpp:496-529 detectPyramidKeypoints + scale-space-detector.hpp:120-131 sortKeys.
+ * std::sort in the reference is unstable; the oracle fixes the total order
+ * (|response| desc, push order asc) == what a stable sort yields. */
+extern "C" int orc_detect_hessian(const float* gray, int w, int h, const orc_pyr_params* p,
+                                  orc_keypoint* out, int cap) {
+  Detector D(*p);
+  float curSigma = 0.5f;
+  float pixelDistance = 1.0f;
+  std::vector<float> first(gray, gray + (size_t)w * h);
+  if (p->initialSigma > curSigma) {
+    float sigma = std::sqrt(p->initialSigma * p->initialSigma - curSigma * curSigma);
+    std::vector<float> t((size_t)w * h);
+    orc_gaussian_blur(first.data(), t.data(), w, h, sigma);
+    first.swap(t);
+  }
+  int minSize = 2 * p->border + 2;
+  int W = w, H = h;
+  D.octave = 0;
+  while (H > minSize && W > minSize) {
+    std::vector<float> next;
+    int nW = 0, nH = 0;
+    D.detectOctave(first, W, H, pixelDistance, next, nW, nH);
+    pixelDistance *= 2.0;
+    first.swap(next);
+    W = nW; H = nH;
+    D.octave++;
+  }
+  std::stable_sort(D.keys.begin(), D.keys.end(), [](const orc_keypoint& a, const orc_keypoint& b) {
+    return std::fabs(a.response) > std::fabs(b.response);
+  });
+  int n = (int)D.keys.size();
+  for (int i = 0; i < n && i < cap; i++) out[i] = D.keys[i];
+  return n;
+}
+
+/* ========================================================================== */
+/* patch sampler                                                              */
+/* ========================================================================== */
+
+/* helpers.cpp:524-549 */
+extern "C" int orc_interpolate_check_borders(int orig_img_w, int orig_img_h, float ofsx, float ofsy,
+                                             float a11, float a12, float a21, float a22, int res_w, int res_h) {
+  const int width = orig_img_w - 2;
+  const int height = orig_img_h - 2;
+  const float halfWidth = std::ceil((float)res_w / 2.0);
+  const float halfHeight = std::ceil((float)res_h / 2.0);
+  float x[4] = {-halfWidth, -halfWidth, +halfWidth, +halfWidth};
+  float y[4] = {-halfHeight, +halfHeight, -halfHeight, +halfHeight};
+  for (int i = 0; i < 4; i++) {
+    float imx = ofsx + x[i] * a11 + y[i] * a12;
+    float imy = ofsy + x[i] * a21 + y[i] * a22;
+    if (std::floor(imx) <= 0 || std::floor(imy) <= 0 || std::ceil(imx) >= width || std::ceil(imy) >= height) return 1;
+  }
+  return 0;
+}
+
+/* helpers.cpp:551-626 interpolate(): bilinear affine resample; sample coordinates are
+ * accumulated incrementally in float (WX += a11), which fixes the rounding. */
+extern "C" int orc_interpolate(const float* im, int w, int h, float ofsx, float ofsy, float a11, float a12,
+                               float a21, float a22, float* res, int res_w, int res_h) {
+  bool ret = false;
+  const int width = w - 1, height = h - 1;
+  const int halfWidth = res_w / 2, halfHeight = res_h / 2;
+  float* out = res;
+  float rx = ofsx - (float)halfHeight * a12;
+  float ry = ofsy - (float)halfHeight * a22;
+  bool touch = orc_interpolate_check_borders(w, h, ofsx, ofsy, a11, a12, a21, a22, res_w, res_h);
+  for (int j = -halfHeight; j < res_h - halfHeight; ++j) {
+    float WX = rx - (float)halfWidth * a11;
+    float WY = ry - (float)halfWidth * a21;
+    for (int i = -halfWidth; i < res_w - halfWidth; ++i) {
+      int x, y;
+      bool inside;
+      if (!touch) { x = (int)WX; y = (int)WY; inside = true; }
+      else {
+        x = (int)std::floor(WX); y = (int)std::floor(WY);
+        inside = (WX >= 0 && WY >= 0 && x < width && y < height);
+      }
+      if (inside) {
+        const float wx = WX - (float)x;
+        const float* Row0 = im + (size_t)y * w;
+        const float* Row1 = im + (size_t)(y + 1) * w;
+        const float I1 = wx * (Row0[x + 1] - Row0[x]) + Row0[x];
+        *out++ = (WY - y) * (wx * (Row1[x + 1] - Row1[x]) + Row1[x] - I1) + I1;
+      } else {
+        *out++ = 0;
+        ret = true;
+      }
+      WX += a11;
+      WY += a21;
+    }
+    rx += a12;
+    ry += a22;
+  }
+  return ret;
+}
+
+/* synth-detection.cpp:38-132 ExtractPatchesColumn, fast_extraction=false, photoNorm=false */
+extern "C" void orc_extract_patches(const float* img, int w, int h, const orc_region* regs, int n,
+                                    double mrSize, int patchSize, float* outp) {
+  std::vector<float> smoothed, blurred;
+  for (int i = 0; i < n; i++) {
+    float* roi = outp + (size_t)i * patchSize * patchSize;
+    const orc_region& k = regs[i];
+    float mrScale = std::ceil(k.s * mrSize); /* double product, ceil, -> float */
+    int patchImageSize = patchSize % 2 != 0 ? 2 * int(mrScale) + 1 : 2 * int(mrScale);
+    float imageToPatchScale = float(patchImageSize) / float(patchSize);
+    if (imageToPatchScale > 0.4) {
+      patchImageSize += 2;
+      size_t np = (size_t)patchImageSize * patchImageSize;
+      smoothed.resize(np); blurred.resize(np);
+      orc_interpolate(img, w, h, (float)k.x, (float)k.y, (float)k.a11, (float)k.a12, (float)k.a21, (float)k.a22,
+                      smoothed.data(), patchImageSize, patchImageSize);
+      orc_gaussian_blur(smoothed.data(), blurred.data(), patchImageSize, patchImageSize, 1.5f * imageToPatchScale);
+      orc_interpolate(blurred.data(), patchImageSize, patchImageSize, (float)(patchImageSize / 2), (float)(patchImageSize / 2),
+                      imageToPatchScale, 0, 0, imageToPatchScale, roi, patchSize, patchSize);
+    } else {
+      orc_interpolate(img, w, h, (float)k.x, (float)k.y, (float)k.a11 * imageToPatchScale, (float)k.a12 * imageToPatchScale,
+                      (float)k.a21 * imageToPatchScale, (float)k.a22 * imageToPatchScale, roi, patchSize, patchSize);
+    }
+  }
+}
+
+/* imagerepresentation.cpp:45 cv::imencode(".png", CV_32F Mat): OpenCV converts to 8 bit with
+ * saturate_cast<uchar>(float) = cvRound (round-half-even) + clamp. */
+extern "C" void orc_quantize_u8(const float* in, uint8_t* out, long n) {
+  for (long i = 0; i < n; i++) {
+    long v = std::lrintf(in[i]);
+    out[i] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+  }
+}
+
+/* ========================================================================== */
+/* region filters                                                             */
+/* ========================================================================== */
+
+/* helpers.cpp:378-387 rectifyAffineTransformationUpIsUp(double&...) */
+static void rectifyUpIsUp(double& a11, double& a12, double& a21, double& a22) {
+  double a = a11, b = a12, c = a21, d = a22;
+  double det = std::sqrt(std::fabs(a * d - b * c));
+  double b2a2 = std::sqrt(b * b + a * a);
+  a11 = b2a2 / det;
+  a12 = 0;
+  a21 = (d * b + c * a) / (b2a2 * det);
+  a22 = det / b2a2;
+}
+/* helpers.cpp:504-515 getEigenvalues (float) */
+static bool getEigenvalues(float a, float b, float c, float d, float& l1, float& l2) {
+  float trace = a + d;
+  float delta1 = (trace * trace - 4 * (a * d - b * c));
+  if (delta1 < 0) return false;
+  float delta = std::sqrt(delta1);
+  l1 = (trace + delta) / 2.0f;
+  l2 = (trace - delta) / 2.0f;
+  return true;
+}
+
+/* imagerepresentation.cpp:803-845 */
+extern "C" int orc_affnet_postprocess(const orc_region* in, const float* aff3, int n, int w, int h,
+                                      double mrSize, orc_region* out, int* src_index) {
+  int m = 0;
+  for (int i = 0; i < n; i++) {
+    orc_region t = in[i];
+    t.a11 = aff3[3 * i + 0]; t.a12 = 0; t.a21 = aff3[3 * i + 1]; t.a22 = aff3[3 * i + 2];
+    rectifyUpIsUp(t.a11, t.a12, t.a21, t.a22);
+    float l1 = 1.0f, l2 = 1.0f;
+    if (!getEigenvalues((float)t.a11, (float)t.a12, (float)t.a21, (float)t.a22, l1, l2)) continue;
+    if ((l1 / l2 > 6) || (l2 / l1 > 6)) continue;
+    /* double mrSize*s is passed into `const int res_w, res_h` (truncation) */
+    if (orc_interpolate_check_borders(w, h, (float)t.x, (float)t.y, (float)t.a11, (float)t.a12, (float)t.a21, (float)t.a22,
+                                      (int)(mrSize * t.s), (int)(mrSize * t.s)))
+      continue;
+    if (src_index) src_index[m] = i;
+    out[m++] = t;
+  }
+  return m;
+}
+
+/* imagerepresentation.cpp:881-899 */
+extern "C" void orc_orinet_postprocess(const orc_region* in, const float* ori2, int n, orc_region* out) {
+  for (int i = 0; i < n; i++) {
+    const orc_region& c = in[i];
+    double angle = std::atan2((double)ori2[2 * i + 0], (double)ori2[2 * i + 1]);
+    double ci = std::cos(angle), si = std::sin(angle);
+    orc_region t = c;
+    t.a11 = c.a11 * ci - c.a12 * si;
+    t.a12 = c.a11 * si + c.a12 * ci;
+    t.a21 = c.a21 * ci - c.a22 * si;
+    t.a22 = c.a21 * si + c.a22 * ci;
+    out[i] = t;
+  }
+}
+
+/* synth-detection.cpp:631-706 ReprojectRegions for the identity view (H = I): keep when the
+ * centre is strictly inside and the k_sigma*s frame (k_sigma = 2*3*sqrt(3), :21) does not
+ * touch the border. */
+extern "C" int orc_reproject_filter(const orc_region* in, int n, int w, int h, orc_region* out, int* src_index) {
+  const double k_sigma = 2 * 3.0 * std::sqrt(3.0);
+  int m = 0;
+  for (int i = 0; i < n; i++) {
+    const orc_region& p = in[i];
+    if ((p.x < w) && (p.y < h) && (p.x > 0) && (p.y > 0)) {
+      if (!orc_interpolate_check_borders(w, h, (float)p.x, (float)p.y, (float)p.a11, (float)p.a12, (float)p.a21, (float)p.a22,
+                                         (int)(k_sigma * p.s), (int)(k_sigma * p.s))) {
+        if (src_index) src_index[m] = i;
+        out[m++] = p;
+      }
+    }
+  }
+  return m;
+}
+
+/* ========================================================================== */
+/* matching                                                                   */
+/* ========================================================================== */
+
+/* cvflann::L2<float>::operator() (OpenCV flann/dist.h, third-party; version unpinned by the
+ * reference): float accumulation of squared differences in blocks of 4.  With the integer-
+ * valued HardNet descriptors (0..255, dim 128) every partial sum is exactly representable,
+ * so any summation order gives the same value. */
+static float l2sq(const float* a, const float* b, int dim) {
+  float result = 0;
+  int i = 0;
+  for (; i + 3 < dim; i += 4) {
+    float d0 = a[i] - b[i], d1 = a[i + 1] - b[i + 1], d2 = a[i + 2] - b[i + 2], d3 = a[i + 3] - b[i + 3];
+    result += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+  }
+  for (; i < dim; i++) { float d0 = a[i] - b[i]; result += d0 * d0; }
+  return result;
+}
+
+/* cvflann::LinearIndex::findNeighbors + KNNSimpleResultSet::addPoint: visit train points in
+ * index order; insert when dist < worst; equal distances keep insertion (index) order. */
+extern "C" void orc_knn_linear(const float* q, int nq, const float* t, int nt, int dim, int nn, int* idx, float* dist) {
+  for (int i = 0; i < nq; i++) {
+    int* I = idx + (size_t)i * nn;
+    float* Dd = dist + (size_t)i * nn;
+    int count = 0;
+    for (int j = 0; j < nn; j++) { I[j] = -1; Dd[j] = INFINITY; }
+    float worst = INFINITY;
+    for (int j = 0; j < nt; j++) {
+      float d = l2sq(q + (size_t)i * dim, t + (size_t)j * dim, dim);
+      if (d >= worst) continue;
+      int k;
+      for (k = count; k > 0; --k) {
+        if (Dd[k - 1] > d) { if (k < nn) { Dd[k] = Dd[k - 1]; I[k] = I[k - 1]; } }
+        else break;
+      }
+      if (count < nn) ++count;
+      Dd[k] = d; I[k] = j;
+      worst = Dd[nn - 1];
+    }
+  }
+}
+
+/* matching.cpp:356-460 MatchFlannFGINN, sqminratio < 1 branch (:430-457) */
+extern "C" int orc_match_fginn(const float* q, const double* qxy, int nq, const float* t, const double* txy,
+                               int nt, int dim, double ratio_thr, double contrad_dist, int nn, orc_match* out) {
+  (void)qxy;
+  if (nq == 0 || nt == 0) return 0;
+  double sqminratio = ratio_thr * ratio_thr;
+  double contrDistSq = contrad_dist * contrad_dist;
+  std::vector<int> idx((size_t)nq * nn);
+  std::vector<float> dist((size_t)nq * nn);
+  orc_knn_linear(q, nq, t, nt, dim, nn, idx.data(), dist.data());
+  int m = 0;
+  for (int i = 0; i < nq; i++) {
+    const int* I = &idx[(size_t)i * nn];
+    const float* Dd = &dist[(size_t)i * nn];
+    for (int j = 1; j < nn; j++) {
+      if (I[j] < 0) break; /* fewer than nn train points (defined as "stop") */
+      double ratio = Dd[0] / Dd[j]; /* float division, widened */
+      if (ratio <= sqminratio) {
+        orc_match mt;
+        mt.qi = i; mt.ti = I[0]; mt.tj_bad = I[j]; mt.d1 = Dd[0]; mt.d2 = Dd[j];
+        mt.ratio = std::sqrt(ratio);
+        out[m++] = mt;
+        break;
+      }
+      double dx = txy[2 * I[0]] - txy[2 * I[j]], dy = txy[2 * I[0] + 1] - txy[2 * I[j] + 1];
+      if (dx * dx + dy * dy > contrDistSq) break;
+    }
+  }
+  return m;
+}
+
+/* matching.cpp:2615-2679 DuplicateFiltering, mode MODE_FGINN (bestFGINN).  The reference's
+ * std::sort is unstable; the oracle uses a stable sort by |ratio| (ties keep query order). */
+extern "C" int orc_duplicate_filter(const double* xy1, const double* xy2, const double* ratio, int T,
+                                    double r, int* order_out) {
+  std::vector<int> ord(T);
+  for (int i = 0; i < T; i++) ord[i] = i;
+  if (r <= 0) { for (int i = 0; i < T; i++) order_out[i] = i; return T; }
+  std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return std::fabs(ratio[a]) < std::fabs(ratio[b]); });
+  double r_sq = r * r;
+  std::vector<char> uniq(T, 1);
+  for (int i = 0; i < T; i++) {
+    if (!uniq[i]) continue;
+    int a = ord[i];
+    for (int j = i + 1; j < T; j++) {
+      if (!uniq[j]) continue;
+      int b = ord[j];
+      double dx = xy1[2 * a] - xy1[2 * b], dy = xy1[2 * a + 1] - xy1[2 * b + 1];
+      if (dx * dx + dy * dy > r_sq) continue;
+      dx = xy2[2 * a] - xy2[2 * b]; dy = xy2[2 * a + 1] - xy2[2 * b + 1];
+      if (dx * dx + dy * dy <= r_sq) uniq[j] = 0;
+    }
+  }
+  int m = 0;
+  for (int i = 0; i < T; i++) if (uniq[i]) order_out[m++] = ord[i];
+  return m;
+}

@@ -1,0 +1,266 @@
+"""ctypes front end of the CPU oracle (TEST INFRASTRUCTURE ONLY).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+may import this module.  The product (libmodsgpu.so + its Python binding) never does.
+
+liboracle.so      : our restatement (oracle/mods_oracle.cpp)
+_ref/libdegensac_ref.so : the reference's own degensac C code (oracle/Makefile `ref`)
+"""
+import ctypes as C
+import glob
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class PyrParams(C.Structure):
+    _fields_ = [("numberOfScales", C.c_int), ("initialSigma", C.c_float), ("threshold", C.c_float),
+                ("edgeEigenValueRatio", C.c_double), ("border", C.c_int)]
+
+
+class Keypoint(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("s", C.c_float), ("response", C.c_float),
+                ("type", C.c_int), ("octave", C.c_int), ("level", C.c_int), ("r0", C.c_int), ("c0", C.c_int),
+                ("r", C.c_int), ("c", C.c_int), ("seq", C.c_int)]
+
+
+KP_DTYPE = np.dtype([("x", "f4"), ("y", "f4"), ("s", "f4"), ("response", "f4"), ("type", "i4"), ("octave", "i4"),
+                     ("level", "i4"), ("r0", "i4"), ("c0", "i4"), ("r", "i4"), ("c", "i4"), ("seq", "i4")])
+REGION_DTYPE = np.dtype([("x", "f8"), ("y", "f8"), ("s", "f8"), ("a11", "f8"), ("a12", "f8"), ("a21", "f8"), ("a22", "f8")])
+MATCH_DTYPE = np.dtype([("qi", "i4"), ("ti", "i4"), ("tj_bad", "i4"), ("d1", "f4"), ("d2", "f4"), ("_pad", "i4"), ("ratio", "f8")])
+
+_lib = None
+
+
+def default_params():
+    """[HessianAffine] section of build/config_aff_ori_desc_zeromq.ini:41-55."""
+    return PyrParams(3, 1.6, 5.33, 10.0, 5)
+
+
+def build():
+    subprocess.check_call(["make", "-C", HERE, "-s", "all"])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        _lib = C.CDLL(path)
+        assert MATCH_DTYPE.itemsize == 32
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def gray_from_bgr(bgr):
+    bgr = np.ascontiguousarray(bgr, np.uint8)
+    h, w, _ = bgr.shape
+    out = np.empty((h, w), np.float32)
+    lib().orc_gray_from_bgr(_p(bgr), w, h, _p(out))
+    return out
+
+
+def gaussian_blur(img, sigma):
+    img = np.ascontiguousarray(img, np.float32)
+    h, w = img.shape
+    out = np.empty_like(img)
+    lib().orc_gaussian_blur(_p(img), _p(out), w, h, C.c_float(sigma))
+    return out
+
+
+def gaussian_kernel(sigma):
+    k = np.zeros(4096, np.float32)
+    n = lib().orc_gaussian_kernel(C.c_float(sigma), _p(k))
+    return k[:n].copy()
+
+
+def hessian_response(img, norm):
+    img = np.ascontiguousarray(img, np.float32)
+    h, w = img.shape
+    out = np.empty_like(img)
+    lib().orc_hessian_response(_p(img), _p(out), w, h, C.c_float(norm))
+    return out
+
+
+def half_image(img):
+    img = np.ascontiguousarray(img, np.float32)
+    h, w = img.shape
+    ow, oh = C.c_int(), C.c_int()
+    lib().orc_half_size(w, h, C.byref(ow), C.byref(oh))
+    out = np.empty((oh.value, ow.value), np.float32)
+    lib().orc_half_image(_p(img), w, h, _p(out))
+    return out
+
+
+def detect_hessian(gray, params=None, cap=200000):
+    gray = np.ascontiguousarray(gray, np.float32)
+    h, w = gray.shape
+    params = params or default_params()
+    out = np.zeros(cap, KP_DTYPE)
+    n = lib().orc_detect_hessian(_p(gray), w, h, C.byref(params), _p(out), cap)
+    assert n <= cap
+    return out[:n].copy()
+
+
+def regions_from_keypoints(kps):
+    """synth-detection.hpp:79-112 with doBaumberg=0: A = I, s unchanged (sqrt|det I| = 1)."""
+    r = np.zeros(len(kps), REGION_DTYPE)
+    r["x"], r["y"], r["s"] = kps["x"], kps["y"], kps["s"]
+    r["a11"] = 1.0
+    r["a22"] = 1.0
+    return r
+
+
+def interpolate(img, ofsx, ofsy, a11, a12, a21, a22, res_w, res_h):
+    img = np.ascontiguousarray(img, np.float32)
+    h, w = img.shape
+    out = np.empty((res_h, res_w), np.float32)
+    f = C.c_float
+    t = lib().orc_interpolate(_p(img), w, h, f(ofsx), f(ofsy), f(a11), f(a12), f(a21), f(a22), _p(out), res_w, res_h)
+    return out, bool(t)
+
+
+def extract_patches(img, regions, mrSize=5.1962, patchSize=32):
+    img = np.ascontiguousarray(img, np.float32)
+    regions = np.ascontiguousarray(regions, REGION_DTYPE)
+    h, w = img.shape
+    out = np.empty((len(regions), patchSize, patchSize), np.float32)
+    lib().orc_extract_patches(_p(img), w, h, _p(regions), len(regions), C.c_double(mrSize), patchSize, _p(out))
+    return out
+
+
+def quantize_u8(a):
+    a = np.ascontiguousarray(a, np.float32)
+    out = np.empty(a.shape, np.uint8)
+    lib().orc_quantize_u8(_p(a), _p(out), C.c_long(a.size))
+    return out
+
+
+def affnet_postprocess(regions, aff3, w, h, mrSize=5.1962):
+    regions = np.ascontiguousarray(regions, REGION_DTYPE)
+    aff3 = np.ascontiguousarray(aff3, np.float32)
+    out = np.zeros(len(regions), REGION_DTYPE)
+    src = np.zeros(len(regions), np.int32)
+    m = lib().orc_affnet_postprocess(_p(regions), _p(aff3), len(regions), w, h, C.c_double(mrSize), _p(out), _p(src))
+    return out[:m].copy(), src[:m].copy()
+
+
+def orinet_postprocess(regions, ori2):
+    regions = np.ascontiguousarray(regions, REGION_DTYPE)
+    ori2 = np.ascontiguousarray(ori2, np.float32)
+    out = np.zeros(len(regions), REGION_DTYPE)
+    lib().orc_orinet_postprocess(_p(regions), _p(ori2), len(regions), _p(out))
+    return out
+
+
+def reproject_filter(regions, w, h):
+    regions = np.ascontiguousarray(regions, REGION_DTYPE)
+    out = np.zeros(len(regions), REGION_DTYPE)
+    src = np.zeros(len(regions), np.int32)
+    m = lib().orc_reproject_filter(_p(regions), len(regions), w, h, _p(out), _p(src))
+    return out[:m].copy(), src[:m].copy()
+
+
+def knn_linear(q, t, nn=50):
+    q = np.ascontiguousarray(q, np.float32)
+    t = np.ascontiguousarray(t, np.float32)
+    idx = np.empty((len(q), nn), np.int32)
+    dist = np.empty((len(q), nn), np.float32)
+    lib().orc_knn_linear(_p(q), len(q), _p(t), len(t), q.shape[1], nn, _p(idx), _p(dist))
+    return idx, dist
+
+
+def match_fginn(q, qxy, t, txy, ratio=0.8, contrad=10.0, nn=50):
+    q = np.ascontiguousarray(q, np.float32)
+    t = np.ascontiguousarray(t, np.float32)
+    qxy = np.ascontiguousarray(qxy, np.float64)
+    txy = np.ascontiguousarray(txy, np.float64)
+    out = np.zeros(max(len(q), 1), MATCH_DTYPE)
+    m = lib().orc_match_fginn(_p(q), _p(qxy), len(q), _p(t), _p(txy), len(t), q.shape[1] if len(q) else 128,
+                              C.c_double(ratio), C.c_double(contrad), nn, _p(out))
+    return out[:m].copy()
+
+
+def duplicate_filter(xy1, xy2, ratio, r=2.0):
+    xy1 = np.ascontiguousarray(xy1, np.float64)
+    xy2 = np.ascontiguousarray(xy2, np.float64)
+    ratio = np.ascontiguousarray(ratio, np.float64)
+    T = len(ratio)
+    order = np.zeros(max(T, 1), np.int32)
+    m = lib().orc_duplicate_filter(_p(xy1), _p(xy2), _p(ratio), T, C.c_double(r), _p(order))
+    return order[:m].copy()
+
+
+# --------------------------------------------------------------------------- reference degensac
+_ref = None
+
+
+class Score(C.Structure):
+    _fields_ = [("I", C.c_uint), ("J", C.c_double)]
+
+
+def _load_lapack():
+    """dsyev_/dgesvd_ come from the OpenBLAS bundled with the cv2 wheel of this image
+    (SURVEY §8c.1).  Loaded RTLD_GLOBAL so libdegensac_ref.so resolves against it."""
+    import importlib.util
+    spec = importlib.util.find_spec("cv2")
+    base = os.path.dirname(os.path.dirname(spec.origin))
+    cands = glob.glob(os.path.join(base, "opencv_python_headless.libs", "libopenblas*.so*")) + \
+        glob.glob(os.path.join(base, "opencv_python.libs", "libopenblas*.so*")) + \
+        glob.glob(os.path.join(base, "scipy.libs", "libscipy_openblas*.so*"))
+    # gfortran runtime deps of that OpenBLAS live in the same directory
+    for c in cands:
+        d = os.path.dirname(c)
+        for dep in sorted(glob.glob(os.path.join(d, "libgfortran*.so*")) + glob.glob(os.path.join(d, "libquadmath*.so*"))):
+            try:
+                C.CDLL(dep, mode=C.RTLD_GLOBAL)
+            except OSError:
+                pass
+        try:
+            return C.CDLL(c, mode=C.RTLD_GLOBAL)
+        except OSError:
+            continue
+    raise OSError("no LAPACK (OpenBLAS) found for the reference degensac")
+
+
+def ref_available():
+    return os.path.exists(os.path.join(HERE, "_ref", "libdegensac_ref.so"))
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        _load_lapack()
+        _ref = C.CDLL(os.path.join(HERE, "_ref", "libdegensac_ref.so"))
+        _ref.exp_ransacHcustom.restype = Score
+    return _ref
+
+
+def ref_ransac_H(u, th=16.0, conf=0.99, max_sam=1000000, seed_time=12345, sym_check=1, error="sampson"):
+    """Calls the reference's exp_ransacHcustom exactly as matching.cpp:731 does.
+    u: T x 6 doubles (x1,y1,1,x2,y2,1).  Returns dict(H, inl, samples, lo_count, oc_rejects, I, J)."""
+    L = ref()
+    u = np.ascontiguousarray(u, np.float64)
+    T = len(u)
+    H = np.zeros(9, np.float64)
+    inl = np.zeros(T, np.uint8)
+    data_out = np.zeros(T * 18 + 8, np.int32)
+    resids = C.c_void_p()
+    L.orc_ref_set_time(C.c_long(seed_time))
+    names = {"sampson": ("HDs", "HDsi", "HDsidx"), "symm_sum": ("HDsSym", "HDsiSym", "HDsSymidx"),
+             "symm_max": ("HDsSymMax", "HDsiSymMax", "HDsSymidxMax")}[error]
+    f = [C.cast(getattr(L, n), C.c_void_p) for n in names]
+    if T <= 20:
+        max_sam = 1000  # matching.cpp:644-645
+    S = L.exp_ransacHcustom(_p(u), T, C.c_double(th), C.c_double(conf), max_sam, _p(H), _p(inl), 4, _p(data_out),
+                            1, C.c_uint(0), C.byref(resids), f[0], f[1], f[2], sym_check)
+    C.CDLL(None).free(resids)
+    return dict(H=H, inl=inl, samples=int(data_out[0]), lo_count=int(data_out[1]), oc_rejects=int(data_out[2]),
+                I=int(S.I), J=float(S.J))

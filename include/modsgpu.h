@@ -1,0 +1,164 @@
+/*
+ * modsgpu.h -- C ABI of libmodsgpu.so: the B200 (sm_100a) implementation of the MODS
+ * per-view hot path  detect -> (AffNet) -> orient (OriNet) -> describe (HardNet++) ->
+ * match (FGINN) -> LO-RANSAC.
+ *
+ * Plain C: pointers and sizes only.  Every entry point names the reference interface it
+ * replaces (file:line in ducha-aiki/mods-light-zmq @ 33c9ba2).  INTEGRATION.md shows the
+ * C++ stubs a maintainer adds on the reference side to bind them.
+ *
+ * Conventions (mirroring the reference: integer returns, no exceptions):
+ *   return 0 on success, a negative MODSGPU_E* code on failure; modsgpu_last_error() gives
+ *   the message.  Host pointers unless a parameter is called "device".  A modsgpu_ctx owns
+ *   one CUDA stream and its workspaces and is NOT thread-safe: use one ctx per calling
+ *   thread (the reference calls the per-image pipeline from one OpenMP task per image,
+ *   mods.cpp:234-251).  The library never falls back to a CPU path: if no sm_100 device is
+ *   present modsgpu_create() fails with MODSGPU_ENODEV.
+ */
+#ifndef MODSGPU_H
+#define MODSGPU_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MODSGPU_OK        0
+#define MODSGPU_ENODEV   -1  /* no CUDA device / not sm_100                        */
+#define MODSGPU_ECUDA    -2  /* CUDA runtime error (message in modsgpu_last_error) */
+#define MODSGPU_EINVAL   -3  /* bad argument                                       */
+#define MODSGPU_EIO      -4  /* weight file unreadable / malformed                 */
+#define MODSGPU_ESTATE   -5  /* e.g. describe before modsgpu_load_weights          */
+
+typedef struct modsgpu_ctx modsgpu_ctx;
+typedef struct modsgpu_image modsgpu_image;   /* device-resident fp32 gray image */
+
+/* ---- context ------------------------------------------------------------------------- */
+int  modsgpu_create(int device, modsgpu_ctx** out);
+void modsgpu_destroy(modsgpu_ctx* ctx);
+const char* modsgpu_last_error(const modsgpu_ctx* ctx);
+const char* modsgpu_version(void);
+/* device-side time (ms, CUDA events on the ctx stream) of the last entry point called */
+float modsgpu_last_device_ms(const modsgpu_ctx* ctx);
+/* number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
+long long modsgpu_launch_count(const modsgpu_ctx* ctx);
+/* raw stream handle (cudaStream_t) so callers can record their own events */
+void* modsgpu_stream(const modsgpu_ctx* ctx);
+
+/* ---- image (replaces ImageRepresentation::ImageRepresentation imagerepresentation.cpp:293-302
+ *      + the gray conversion of GenerateSynthImageCorr synth-detection.cpp:344-354) -------- */
+/* 8-bit interleaved BGR (cv::imread layout) -> fp32 gray = (B+G+R)/3 on the device */
+int  modsgpu_image_from_bgr8(modsgpu_ctx* ctx, const uint8_t* bgr, int w, int h, modsgpu_image** out);
+/* fp32 gray, `stride` in floats */
+int  modsgpu_image_from_gray32f(modsgpu_ctx* ctx, const float* gray, int w, int h, int stride, modsgpu_image** out);
+int  modsgpu_image_download(modsgpu_ctx* ctx, const modsgpu_image* img, float* gray /* w*h */);
+void modsgpu_image_size(const modsgpu_image* img, int* w, int* h);
+void modsgpu_image_free(modsgpu_ctx* ctx, modsgpu_image* img);
+
+/* ---- S1 detector (replaces DetectAffineKeypoints scale-space-detector.cpp:13-32 ->
+ *      ScaleSpaceDetector::detectPyramidKeypoints pyramid.cpp:496-529, for DET_HESSIAN,
+ *      FIXED_TH, doBaumberg = 0) ------------------------------------------------------------ */
+typedef struct {            /* PyramidParams, structures.hpp:114-151 */
+  int    numberOfScales;        /* 3    */
+  float  initialSigma;          /* 1.6  */
+  float  threshold;             /* 5.33 ([HessianAffine] threshold in the ini) */
+  double edgeEigenValueRatio;   /* 10   */
+  int    border;                /* 5    */
+} modsgpu_pyr_params;
+
+typedef struct {            /* AffineKeypoint structures.hpp:185-194 + provenance for parity tests */
+  float x, y, s;                /* pyramid.cpp:392-402 */
+  float response;
+  int   type;                   /* 0 dark blob, 1 bright blob, 2 saddle (pyramid.cpp:65-124) */
+  int   octave;                 /* 0,1,..  (pixelDistance = 2^octave)                        */
+  int   level;                  /* 1..numberOfScales                                          */
+  int   r0, c0;                 /* raster position of the NMS candidate (findLevelKeypoints)  */
+  int   r, c;                   /* integer position after localizeKeypoint                    */
+  int   seq;                    /* reserved (0)                                               */
+} modsgpu_keypoint;
+
+void modsgpu_default_pyr_params(modsgpu_pyr_params* p);
+/* Output order = the reference's export order: |response| descending
+ * (scale-space-detector.hpp:120-131), ties by (octave, level, r0, c0).
+ * *out is malloc()ed by the library; release with modsgpu_free(). */
+int  modsgpu_detect(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_pyr_params* p,
+                    modsgpu_keypoint** out, int* n);
+void modsgpu_free(void* p);
+
+/* pyramid internals exposed for the parity tests only (helpers.cpp:717-731 gaussianBlur,
+ * pyramid.cpp:196-254 HessianResponse, pyramid.cpp:476 cv::resize 0.5) */
+int  modsgpu_gaussian_blur(modsgpu_ctx* ctx, const float* in, float* out, int w, int h, float sigma);
+int  modsgpu_hessian_response(modsgpu_ctx* ctx, const float* in, float* out, int w, int h, float norm);
+int  modsgpu_half_image(modsgpu_ctx* ctx, const float* in, int w, int h, float* out /* round(w/2)*round(h/2) */);
+
+/* ---- regions ---------------------------------------------------------------------------- */
+typedef struct {            /* the AffineKeypoint fields the sampler reads, structures.hpp:185-194 */
+  double x, y, s;
+  double a11, a12, a21, a22;
+} modsgpu_region;
+
+/* ---- S5 patch sampler (replaces ExtractPatchesColumn synth-detection.cpp:38-132 with
+ *      fast_extraction=false, photoNorm=false, followed by the float->u8 conversion of
+ *      cv::imencode(".png") imagerepresentation.cpp:45).  out: n * patchSize*patchSize bytes. */
+int  modsgpu_extract_patches(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_region* regs, int n,
+                             double mrSize, int patchSize, uint8_t* out);
+
+/* ---- S2 CNNs (replace DescribeWithZmq imagerepresentation.cpp:21-103 and the three daemons
+ *      build/affnet_server.py, orinet_server.py, desc_server.py) ------------------------------ */
+typedef enum { MODSGPU_AFFNET = 0, MODSGPU_ORINET = 1, MODSGPU_HARDNET = 2 } modsgpu_net;
+/* output floats per region: 3 (AffNet: a11, a21, a22 with +1 on a11,a22), 2 (OriNet: sin-like,
+ * cos-like), 128 (HardNet++: uint8-valued floats, desc_server.py:42) */
+int  modsgpu_net_out_dim(modsgpu_net net);
+/* .npz written by tools/export_weights.py from build/{AffNet,OriNet,HardNet++}.pth */
+int  modsgpu_load_weights(modsgpu_ctx* ctx, modsgpu_net net, const char* npz_path);
+/* patches -> net, no 2000-region batching limit.  out: n * out_dim floats. */
+int  modsgpu_describe(modsgpu_ctx* ctx, modsgpu_net net, const modsgpu_image* img, const modsgpu_region* regs,
+                      int n, double mrSize, int patchSize, float* out);
+/* the net alone on caller-supplied 32x32 u8 patches (what the daemons receive as PNG) */
+int  modsgpu_net_forward_u8(modsgpu_ctx* ctx, modsgpu_net net, const uint8_t* patches, int n, float* out);
+
+/* ---- S3 matcher (replaces MatchFlannFGINN matching.cpp:356-460 with vector_matcher=linear:
+ *      exact 50-NN + first-geometrically-inconsistent ratio test) ----------------------------- */
+typedef struct {            /* TentativeCorrespExt fields filled at matching.cpp:437-449 */
+  int    qi, ti, tj_bad;        /* query idx, 1st NN, the ratio-passing (geometrically inconsistent) NN */
+  float  d1, d2;                /* squared L2 distances to ti and tj_bad */
+  int    _pad;
+  double ratio;                 /* sqrt(d1/d2) */
+} modsgpu_match;
+/* q: nq x dim, t: nt x dim row-major floats holding integers in [0,255] (both reference descriptors
+ * do); txy: nt x 2 doubles (train keypoint positions).  out: capacity nq.
+ * knn_idx/knn_dist (nq x nn, may be NULL) receive the ordered neighbour lists (dist asc, idx asc). */
+int  modsgpu_match_fginn(modsgpu_ctx* ctx, const float* q, int nq, const float* t, const double* txy, int nt,
+                         int dim, double ratio_thr, double contrad_dist, int nn,
+                         modsgpu_match* out, int* nout, int* knn_idx, float* knn_dist);
+
+/* ---- duplicate filter (replaces DuplicateFiltering matching.cpp:2615-2679, mode bestFGINN;
+ *      stable order on ties).  order_out: indices of the survivors in sorted order. ---------- */
+int  modsgpu_duplicate_filter(modsgpu_ctx* ctx, const double* xy1, const double* xy2, const double* ratio,
+                              int T, double r, int* order_out, int* nout);
+
+/* ---- S4 LO-RANSAC (replaces exp_ransacHcustom degensac/exp_ranH.h:53-57 as called from
+ *      LORANSACFiltering matching.cpp:731).  Batched, counter-based RNG -> reproducible. ------- */
+typedef struct {
+  double th;                    /* squared pixel threshold (matching.cpp:731 passes err_threshold^2) */
+  double conf;                  /* 0.99 */
+  int    max_samples;           /* 1e6; matching.cpp:644-645 clamps to 1000 when T <= 20 */
+  int    do_sym_check;          /* matching.cpp:652-681 */
+  uint64_t seed;                /* the reference seeds with time(NULL), exp_ranH.c:823 */
+} modsgpu_ransac_params;
+typedef struct {
+  int    n_inliers;             /* Score.I */
+  double J;                     /* Score.J (MSAC cost) */
+  int    samples;               /* data_out[0] */
+  int    lo_runs;               /* data_out[1] */
+  int    oc_rejects;            /* data_out[2] */
+} modsgpu_ransac_result;
+/* u: T x 6 doubles (x1,y1,1,x2,y2,1) as packed at matching.cpp:695-713.  H: 9 doubles in the
+ * degensac convention (column-major / transposed, maps image 2 -> image 1).
+ * inl: T bytes. */
+int  modsgpu_ransac_H(modsgpu_ctx* ctx, const double* u, int T, const modsgpu_ransac_params* p,
+                      double* H, unsigned char* inl, modsgpu_ransac_result* res);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,250 @@
+"""mods_light_zmq_b200 -- ctypes binding of libmodsgpu.so (include/modsgpu.h).
+
+The library is the product; this module only marshals numpy arrays across the C ABI so that
+tests/ and bench.py can call it.  There is no CPU fallback: importing works without a GPU (the
+not-gpu tests check the exported symbols), but `ModsGpu()` raises unless an sm_100 device and the
+built library are present.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmodsgpu.so")
+WEIGHTS_DIR = os.path.join(os.path.dirname(HERE), "weights")
+
+KP_DTYPE = np.dtype([("x", "f4"), ("y", "f4"), ("s", "f4"), ("response", "f4"), ("type", "i4"), ("octave", "i4"),
+                     ("level", "i4"), ("r0", "i4"), ("c0", "i4"), ("r", "i4"), ("c", "i4"), ("seq", "i4")])
+REGION_DTYPE = np.dtype([("x", "f8"), ("y", "f8"), ("s", "f8"), ("a11", "f8"), ("a12", "f8"), ("a21", "f8"), ("a22", "f8")])
+MATCH_DTYPE = np.dtype([("qi", "i4"), ("ti", "i4"), ("tj_bad", "i4"), ("d1", "f4"), ("d2", "f4"), ("_pad", "i4"), ("ratio", "f8")])
+
+AFFNET, ORINET, HARDNET = 0, 1, 2
+NET_FILES = {AFFNET: "affnet.npz", ORINET: "orinet.npz", HARDNET: "hardnet.npz"}
+NET_DIM = {AFFNET: 3, ORINET: 2, HARDNET: 128}
+
+
+class PyrParams(C.Structure):
+    _fields_ = [("numberOfScales", C.c_int), ("initialSigma", C.c_float), ("threshold", C.c_float),
+                ("edgeEigenValueRatio", C.c_double), ("border", C.c_int)]
+
+
+class RansacParams(C.Structure):
+    _fields_ = [("th", C.c_double), ("conf", C.c_double), ("max_samples", C.c_int), ("do_sym_check", C.c_int),
+                ("seed", C.c_uint64)]
+
+
+class RansacResult(C.Structure):
+    _fields_ = [("n_inliers", C.c_int), ("J", C.c_double), ("samples", C.c_int), ("lo_runs", C.c_int),
+                ("oc_rejects", C.c_int)]
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen libmodsgpu.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libmodsgpu.so is not built: run `make` (or __graft_entry__.build()) first")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.modsgpu_last_error.restype = C.c_char_p
+        _lib.modsgpu_version.restype = C.c_char_p
+        _lib.modsgpu_last_device_ms.restype = C.c_float
+        _lib.modsgpu_launch_count.restype = C.c_longlong
+        _lib.modsgpu_stream.restype = C.c_void_p
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class ModsGpuError(RuntimeError):
+    pass
+
+
+class Image:
+    def __init__(self, owner, handle, w, h):
+        self.owner, self.handle, self.w, self.h = owner, handle, w, h
+
+    def free(self):
+        if self.handle:
+            self.owner.lib.modsgpu_image_free(self.owner.ctx, self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class ModsGpu:
+    """One modsgpu_ctx (one CUDA stream).  Method names follow the C ABI."""
+
+    def __init__(self, device=0, load_nets=False):
+        self.lib = load_library()
+        self.ctx = C.c_void_p()
+        rc = self.lib.modsgpu_create(int(device), C.byref(self.ctx))
+        if rc != 0:
+            raise ModsGpuError("modsgpu_create failed (%d): no sm_100 CUDA device -- there is no CPU path" % rc)
+        if load_nets:
+            for net in (AFFNET, ORINET, HARDNET):
+                self.load_weights(net)
+
+    def close(self):
+        if self.ctx:
+            self.lib.modsgpu_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise ModsGpuError("modsgpu error %d: %s" % (rc, self.lib.modsgpu_last_error(self.ctx).decode()))
+
+    @property
+    def last_device_ms(self):
+        return float(self.lib.modsgpu_last_device_ms(self.ctx))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.modsgpu_launch_count(self.ctx))
+
+    # ---- images
+    def image_from_bgr8(self, bgr):
+        bgr = np.ascontiguousarray(bgr, np.uint8)
+        h, w, _ = bgr.shape
+        hd = C.c_void_p()
+        self._check(self.lib.modsgpu_image_from_bgr8(self.ctx, _p(bgr), w, h, C.byref(hd)))
+        return Image(self, hd, w, h)
+
+    def image_from_gray32f(self, gray):
+        gray = np.ascontiguousarray(gray, np.float32)
+        h, w = gray.shape
+        hd = C.c_void_p()
+        self._check(self.lib.modsgpu_image_from_gray32f(self.ctx, _p(gray), w, h, w, C.byref(hd)))
+        return Image(self, hd, w, h)
+
+    def image_download(self, img):
+        out = np.empty((img.h, img.w), np.float32)
+        self._check(self.lib.modsgpu_image_download(self.ctx, img.handle, _p(out)))
+        return out
+
+    # ---- detector
+    def detect(self, img, params=None):
+        if params is None:
+            params = PyrParams()
+            self.lib.modsgpu_default_pyr_params(C.byref(params))
+        out = C.c_void_p()
+        n = C.c_int()
+        self._check(self.lib.modsgpu_detect(self.ctx, img.handle, C.byref(params), C.byref(out), C.byref(n)))
+        try:
+            if n.value == 0:
+                return np.zeros(0, KP_DTYPE)
+            buf = (C.c_char * (n.value * KP_DTYPE.itemsize)).from_address(out.value)
+            return np.frombuffer(buf, KP_DTYPE).copy()
+        finally:
+            self.lib.modsgpu_free(out)
+
+    def gaussian_blur(self, img, sigma):
+        img = np.ascontiguousarray(img, np.float32)
+        h, w = img.shape
+        out = np.empty_like(img)
+        self._check(self.lib.modsgpu_gaussian_blur(self.ctx, _p(img), _p(out), w, h, C.c_float(sigma)))
+        return out
+
+    def hessian_response(self, img, norm):
+        img = np.ascontiguousarray(img, np.float32)
+        h, w = img.shape
+        out = np.empty_like(img)
+        self._check(self.lib.modsgpu_hessian_response(self.ctx, _p(img), _p(out), w, h, C.c_float(norm)))
+        return out
+
+    def half_image(self, img):
+        img = np.ascontiguousarray(img, np.float32)
+        h, w = img.shape
+        ow, oh = int(np.rint(w * 0.5)), int(np.rint(h * 0.5))
+        out = np.empty((oh, ow), np.float32)
+        self._check(self.lib.modsgpu_half_image(self.ctx, _p(img), w, h, _p(out)))
+        return out
+
+    # ---- sampler / nets
+    def extract_patches(self, img, regions, mrSize=5.1962, patchSize=32):
+        regions = np.ascontiguousarray(regions, REGION_DTYPE)
+        out = np.empty((len(regions), patchSize, patchSize), np.uint8)
+        self._check(self.lib.modsgpu_extract_patches(self.ctx, img.handle, _p(regions), len(regions), C.c_double(mrSize),
+                                                     patchSize, _p(out)))
+        return out
+
+    def load_weights(self, net, path=None):
+        path = path or os.path.join(WEIGHTS_DIR, NET_FILES[net])
+        self._check(self.lib.modsgpu_load_weights(self.ctx, net, path.encode()))
+
+    def describe(self, net, img, regions, mrSize=5.1962, patchSize=32):
+        regions = np.ascontiguousarray(regions, REGION_DTYPE)
+        out = np.empty((len(regions), NET_DIM[net]), np.float32)
+        self._check(self.lib.modsgpu_describe(self.ctx, net, img.handle, _p(regions), len(regions), C.c_double(mrSize),
+                                              patchSize, _p(out)))
+        return out
+
+    def net_forward_u8(self, net, patches):
+        patches = np.ascontiguousarray(patches, np.uint8).reshape(-1, 32, 32)
+        out = np.empty((len(patches), NET_DIM[net]), np.float32)
+        self._check(self.lib.modsgpu_net_forward_u8(self.ctx, net, _p(patches), len(patches), _p(out)))
+        return out
+
+    def debug_umma_probe(self, A, B, swap=0):
+        A = np.ascontiguousarray(A, np.float32)
+        B = np.ascontiguousarray(B, np.float32)
+        D = np.empty((128, 32), np.float32)
+        self._check(self.lib.modsgpu_debug_umma_probe(self.ctx, _p(A), _p(B), _p(D), int(swap)))
+        return D
+
+    # ---- matching
+    def match_fginn(self, q, t, txy, ratio=0.8, contrad=10.0, nn=50, want_knn=False):
+        q = np.ascontiguousarray(q, np.float32)
+        t = np.ascontiguousarray(t, np.float32)
+        txy = np.ascontiguousarray(txy, np.float64)
+        nq, nt = len(q), len(t)
+        dim = q.shape[1] if q.ndim == 2 and nq else (t.shape[1] if t.ndim == 2 and nt else 128)
+        out = np.zeros(max(nq, 1), MATCH_DTYPE)
+        n = C.c_int()
+        ki = np.empty((nq, nn), np.int32) if want_knn else None
+        kd = np.empty((nq, nn), np.float32) if want_knn else None
+        self._check(self.lib.modsgpu_match_fginn(self.ctx, _p(q), nq, _p(t), _p(txy), nt, dim, C.c_double(ratio),
+                                                 C.c_double(contrad), nn, _p(out), C.byref(n),
+                                                 _p(ki) if want_knn else None, _p(kd) if want_knn else None))
+        m = out[:n.value].copy()
+        return (m, ki, kd) if want_knn else m
+
+    def duplicate_filter(self, xy1, xy2, ratio, r=2.0):
+        xy1 = np.ascontiguousarray(xy1, np.float64)
+        xy2 = np.ascontiguousarray(xy2, np.float64)
+        ratio = np.ascontiguousarray(ratio, np.float64)
+        T = len(ratio)
+        order = np.zeros(max(T, 1), np.int32)
+        n = C.c_int()
+        self._check(self.lib.modsgpu_duplicate_filter(self.ctx, _p(xy1), _p(xy2), _p(ratio), T, C.c_double(r), _p(order),
+                                                      C.byref(n)))
+        return order[:n.value].copy()
+
+    def ransac_H(self, u, th=16.0, conf=0.99, max_samples=1000000, sym_check=1, seed=12345):
+        u = np.ascontiguousarray(u, np.float64)
+        T = len(u)
+        p = RansacParams(th, conf, 1000 if T <= 20 else max_samples, sym_check, seed)
+        H = np.zeros(9, np.float64)
+        inl = np.zeros(max(T, 1), np.uint8)
+        res = RansacResult()
+        self._check(self.lib.modsgpu_ransac_H(self.ctx, _p(u), T, C.byref(p), _p(H), _p(inl), C.byref(res)))
+        return dict(H=H, inl=inl[:T], I=res.n_inliers, J=res.J, samples=res.samples, lo_count=res.lo_runs,
+                    oc_rejects=res.oc_rejects)
+
+
+def regions_from_keypoints(kps):
+    """DetectAffineRegions glue (synth-detection.hpp:79-112) for doBaumberg=0: A = I."""
+    r = np.zeros(len(kps), REGION_DTYPE)
+    r["x"], r["y"], r["s"] = kps["x"], kps["y"], kps["s"]
+    r["a11"] = 1.0
+    r["a22"] = 1.0
+    return r

@@ -1,0 +1,703 @@
+// cnn.cu -- AffNet / OriNet / HardNet++ as fused sm_100a kernels (seam S2).
+// Replaces the three ZeroMQ/PyTorch daemons (build/affnet_server.py:45-84, orinet_server.py:45-82,
+// desc_server.py:58-92).  BatchNorm is folded into the convolutions by tools/export_weights.py.
+//
+// Data layout in HBM (all activations fp16, accumulation fp32):
+//   An activation tensor with C channels over S x S maps is stored as C/8 "planes"; a plane is a flat
+//   array of 16-byte slots (8 channels of one pixel).  Pixels of all patches of a chunk share one
+//   linear slot index  g = patch*(S+1)^2 + (y+1)*(S+1) + x  : every row carries ONE trailing pad
+//   slot and every patch ONE leading pad row, so a 3x3 tap (dy,dx) is the constant slot shift
+//   dy*(S+1)+dx and all out-of-image reads land on pad slots (zero, never written).
+//   => a 128-pixel M tile of the implicit GEMM is 128 consecutive slots, its im2col operand for one
+//   tap is the SAME shared-memory tile read at a shifted start address -- expressed directly in the
+//   tcgen05 shared-memory descriptor (K-major, no swizzle: rows 16 B apart).  No im2col copy exists.
+//   Stride-2 layers read four parity planes (space-to-depth) written by the previous layer's epilogue,
+//   which turns them into unit-stride shifts as well.
+//
+// Kernels:
+//   k_conv1     CUDA cores: per-patch mean/std normalisation + conv1 (1->C1) + bias + ReLU
+//   k_conv_umma tcgen05 implicit GEMM for conv2..conv6: warp-specialised (bulk-copy producer, single
+//               thread MMA issuer, 4 epilogue warps), weights resident in smem, A tiles double buffered
+//               by cp.async.bulk + mbarrier, accumulators double buffered in TMEM
+//   k_head_gemm HardNet 8x8 conv (K = 8192 GEMM) + BN + L2 norm + uint8 quantisation epilogue
+//   k_head_aff / k_head_ori  the tiny 8x8 heads (+tanh) on CUDA cores
+#include "common.cuh"
+#include "umma.cuh"
+#include "npz.h"
+#include <map>
+
+using namespace umma;
+
+namespace {
+
+constexpr int FS = 64;  // zero slots in front of every plane (covers the negative tap shifts)
+enum { OUT_NORMAL = 0, OUT_PARITY = 1, OUT_GEMM = 2 };
+
+struct ConvW { __half* w = nullptr; float* b = nullptr; };
+
+}  // namespace
+
+struct NetWeights {
+  int net = 0, C1 = 0, out_dim = 0;
+  float* c1_w = nullptr; float* c1_b = nullptr;
+  ConvW conv[5];                 // conv2..conv6 in UMMA block order
+  __half* head_w16 = nullptr;    // HardNet head, UMMA block order
+  float* head_w32 = nullptr;     // AffNet / OriNet head [Cout][8][8][64]
+  float* head_b = nullptr;
+  int cap = 0;                   // patches per chunk the activation buffers hold
+  __half* act[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t slots[6] = {0, 0, 0, 0, 0, 0};
+};
+
+namespace {
+
+__host__ __device__ constexpr int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// =================================================================================================
+// conv1 (+ input normalisation) on CUDA cores
+// =================================================================================================
+template <int C1>
+__global__ void __launch_bounds__(256)
+k_conv1(const uint8_t* __restrict__ patches, int np, const float* __restrict__ w, const float* __restrict__ b,
+        __half* __restrict__ out, size_t out_slots) {
+  __shared__ float P[34][36];
+  __shared__ float ws[C1 * 9], bs[C1];
+  __shared__ unsigned red[2][8];
+  __shared__ float s_mean, s_inv;
+  const int patch = blockIdx.x, tid = threadIdx.x;
+  const uint8_t* src = patches + (size_t)patch * 1024;
+  for (int i = tid; i < 34 * 36; i += 256) (&P[0][0])[i] = 0.f;
+  for (int i = tid; i < C1 * 9; i += 256) ws[i] = w[i];
+  if (tid < C1) bs[tid] = b[tid];
+  uchar4 px = reinterpret_cast<const uchar4*>(src)[tid];
+  unsigned s1 = px.x + px.y + px.z + px.w;
+  unsigned s2 = px.x * px.x + px.y * px.y + px.z * px.z + px.w * px.w;
+  for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+  if ((tid & 31) == 0) { red[0][tid >> 5] = s1; red[1][tid >> 5] = s2; }
+  __syncthreads();
+  if (tid == 0) {
+    unsigned a = 0, q = 0;
+    for (int i = 0; i < 8; i++) { a += red[0][i]; q += red[1][i]; }
+    // torch.mean / torch.std (unbiased) of the 1024 pixels; (x-mean)/(std+1e-7) (desc_server.py:83-87)
+    double mean = (double)a / 1024.0;
+    double var = ((double)q - (double)a * mean) / 1023.0;
+    if (var < 0) var = 0;
+    s_mean = (float)mean;
+    s_inv = (float)sqrt(var) + 1e-7f;
+  }
+  __syncthreads();
+  {
+    const float mean = s_mean, sd = s_inv;
+    int y = tid >> 3, x = (tid & 7) * 4;
+    P[y + 1][x + 1] = ((float)px.x - mean) / sd;
+    P[y + 1][x + 2] = ((float)px.y - mean) / sd;
+    P[y + 1][x + 3] = ((float)px.z - mean) / sd;
+    P[y + 1][x + 4] = ((float)px.w - mean) / sd;
+  }
+  __syncthreads();
+  constexpr int C8 = C1 / 8;
+  for (int it = tid; it < 1024 * C8; it += 256) {
+    const int c8 = it >> 10, p = it & 1023, y = p >> 5, x = p & 31;
+    float v[9];
+#pragma unroll
+    for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+      for (int dx = 0; dx < 3; dx++) v[dy * 3 + dx] = P[y + dy][x + dx];
+    __align__(16) __half h[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+      const int c = c8 * 8 + e;
+      float acc = bs[c];
+#pragma unroll
+      for (int t = 0; t < 9; t++) acc = fmaf(ws[c * 9 + t], v[t], acc);
+      h[e] = __float2half_rn(fmaxf(acc, 0.f));
+    }
+    const size_t slot = (size_t)FS + (size_t)patch * 1089 + (size_t)(y + 1) * 33 + x;
+    *reinterpret_cast<uint4*>(out + ((size_t)c8 * out_slots + slot) * 8) = *reinterpret_cast<const uint4*>(h);
+  }
+}
+
+// =================================================================================================
+// conv2..conv6: tcgen05 implicit GEMM
+// =================================================================================================
+template <int CIN, int COUT_T, int NSPLIT, int S, int NGRP, int OUT_MODE>
+struct ConvCfg {
+  static constexpr int PT = S + 1, PP = PT * PT;
+  static constexpr int C8 = CIN / 8, KSTEPS = CIN / 16;
+  static constexpr int COUT = COUT_T * NSPLIT;
+  static constexpr int HALO_LO = PT + 1, HALO_HI = (NGRP == 1) ? PT + 1 : 0;
+  static constexpr int TP = 128 + HALO_LO + HALO_HI;
+  static constexpr int NPL = NGRP * C8;
+  static constexpr int A_BYTES = NPL * TP * 16;
+  static constexpr int W_BYTES = 9 * KSTEPS * 2 * COUT_T * 16;
+  static constexpr int TMEM_COLS = (2 * COUT_T <= 32) ? 32 : (2 * COUT_T <= 64 ? 64 : (2 * COUT_T <= 128 ? 128 : 256));
+  static constexpr int SMEM_BYTES = W_BYTES + 2 * A_BYTES + 128;
+  static_assert(CIN % 16 == 0 && COUT_T % 16 == 0, "UMMA shape");
+};
+
+template <int CIN, int COUT_T, int NSPLIT, int S, int NGRP, int OUT_MODE>
+__global__ void __launch_bounds__(192, 1)
+k_conv_umma(const __half* __restrict__ in, size_t in_slots, const __half* __restrict__ wts,
+            const float* __restrict__ bias, __half* __restrict__ out, size_t out_slots, int np, int ntiles) {
+  using Cfg = ConvCfg<CIN, COUT_T, NSPLIT, S, NGRP, OUT_MODE>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* w_s = smem;
+  uint8_t* a_s = smem + Cfg::W_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::W_BYTES + 2 * Cfg::A_BYTES);
+  uint64_t* w_full = bars;         // weights landed
+  uint64_t* a_full = bars + 1;     // [2]
+  uint64_t* a_empty = bars + 3;    // [2]
+  uint64_t* t_full = bars + 5;     // [2]
+  uint64_t* t_empty = bars + 7;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nsp = blockIdx.y;  // which COUT_T slice of the output channels
+
+  if (threadIdx.x == 0) {
+    mbar_init(w_full, 1);
+    for (int i = 0; i < 2; i++) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); mbar_init(t_full + i, 1); mbar_init(t_empty + i, 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---- producer: weights once, then one A tile (NPL planes) per M tile
+      mbar_expect_tx(w_full, Cfg::W_BYTES);
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(wts) + (size_t)nsp * Cfg::W_BYTES;
+      for (int off = 0; off < Cfg::W_BYTES; off += 32768) {
+        int bytes = Cfg::W_BYTES - off < 32768 ? Cfg::W_BYTES - off : 32768;
+        bulk_g2s(w_s + off, wsrc + off, bytes, w_full);
+      }
+      int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+        const int s = it & 1, ph = (it >> 1) & 1;
+        mbar_wait(a_empty + s, ph ^ 1);
+        mbar_expect_tx(a_full + s, Cfg::A_BYTES);
+        const size_t slot0 = (size_t)FS + (size_t)tile * 128 - Cfg::HALO_LO;
+        uint8_t* dst = a_s + s * Cfg::A_BYTES;
+#pragma unroll 1
+        for (int pl = 0; pl < Cfg::NPL; pl++)
+          bulk_g2s(dst + pl * Cfg::TP * 16, in + ((size_t)pl * in_slots + slot0) * 8, Cfg::TP * 16, a_full + s);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---- MMA issuer
+      constexpr uint32_t idesc = instr_desc_f16(COUT_T);
+      mbar_wait(w_full, 0);
+      const uint32_t w_addr = smem_u32(w_s);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+        const int s = it & 1, ph = (it >> 1) & 1;
+        mbar_wait(t_empty + s, ph ^ 1);
+        mbar_wait(a_full + s, ph);
+        fence_after_sync();
+        const uint32_t a_addr = smem_u32(a_s + s * Cfg::A_BYTES);
+        const uint32_t d_tmem = tmem_base + s * COUT_T;
+#pragma unroll
+        for (int t = 0; t < 9; t++) {
+          const int dy = t / 3, dx = t % 3;
+          int grp, shift;
+          if (NGRP == 1) { grp = 0; shift = (dy - 1) * Cfg::PT + (dx - 1); }
+          else {
+            grp = ((dy == 1) ? 0 : 2) + ((dx == 1) ? 0 : 1);
+            shift = ((dy == 0) ? -Cfg::PT : 0) + ((dx == 0) ? -1 : 0);
+          }
+#pragma unroll
+          for (int ks = 0; ks < Cfg::KSTEPS; ks++) {
+            const uint32_t a = a_addr + ((grp * Cfg::C8 + 2 * ks) * Cfg::TP + Cfg::HALO_LO + shift) * 16;
+            const uint32_t b = w_addr + ((t * Cfg::KSTEPS + ks) * 2 * COUT_T) * 16;
+            mma_f16(d_tmem, smem_desc(a, Cfg::TP * 16, 128), smem_desc(b, COUT_T * 16, 128), idesc, (t | ks) != 0);
+          }
+        }
+        mma_commit(a_empty + s);   // smem tile may be refilled once these MMAs retire
+        mma_commit(t_full + s);    // accumulator ready for the epilogue
+      }
+    }
+  } else {
+    // ---- epilogue warps 2..5: TMEM -> bias + ReLU -> fp16 -> next layer's layout
+    const int q = warp & 3;               // TMEM lane quarter this warp may touch
+    const int m = q * 32 + lane;          // row of the M tile
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+      const int s = it & 1, ph = (it >> 1) & 1;
+      const int g = tile * 128 + m;
+      const int patch = g / Cfg::PP;
+      const int idx = g - patch * Cfg::PP;
+      const int yy = idx / Cfg::PT, x = idx - yy * Cfg::PT, y = yy - 1;
+      const bool valid = patch < np && yy >= 1 && x < S;
+      size_t oslot; int oplane0;
+      if (OUT_MODE == OUT_NORMAL) { oslot = (size_t)FS + g; oplane0 = 0; }
+      else if (OUT_MODE == OUT_PARITY) {
+        constexpr int PT2 = S / 2 + 1, PP2 = PT2 * PT2;
+        oslot = (size_t)FS + (size_t)patch * PP2 + ((y >> 1) + 1) * PT2 + (x >> 1);
+        oplane0 = (((y & 1) << 1) | (x & 1)) * (Cfg::COUT / 8);
+      } else {
+        oslot = (size_t)patch;
+        oplane0 = (y * S + x) * (Cfg::COUT / 8);
+      }
+      oplane0 += nsp * (COUT_T / 8);
+      mbar_wait(t_full + s, ph);
+      fence_after_sync();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + s * COUT_T;
+#pragma unroll
+      for (int cc = 0; cc < COUT_T / 16; cc++) {
+        float v[16];
+        tmem_ld16(taddr + cc * 16, v);
+        if (valid) {
+          __align__(16) __half h[16];
+#pragma unroll
+          for (int e = 0; e < 16; e++) h[e] = __float2half_rn(fmaxf(v[e] + __ldg(bias + nsp * COUT_T + cc * 16 + e), 0.f));
+          __half* o = out + ((size_t)(oplane0 + cc * 2) * out_slots + oslot) * 8;
+          *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(h);
+          *reinterpret_cast<uint4*>(o + out_slots * 8) = *reinterpret_cast<const uint4*>(h + 8);
+        }
+      }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty + s);
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// =================================================================================================
+// HardNet head: 8x8 valid conv == GEMM  [patches x 8192] * [8192 x 128]  + BN + L2 norm + quantise
+// =================================================================================================
+constexpr int HG_STAGES = 3, HG_STAGE_BYTES = 65536;
+constexpr int HG_SMEM = HG_STAGES * HG_STAGE_BYTES + 128;
+
+__global__ void __launch_bounds__(192, 1)
+k_head_gemm(const __half* __restrict__ act, size_t slots, const __half* __restrict__ wts,
+            const float* __restrict__ bias, float* __restrict__ out, int np) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + HG_STAGES * HG_STAGE_BYTES);
+  uint64_t* full = bars;                 // [3]
+  uint64_t* empty = bars + HG_STAGES;    // [3]
+  uint64_t* t_full = bars + 2 * HG_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * HG_STAGES + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 128;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < HG_STAGES; i++) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+    mbar_init(t_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<128>(tmem_slot);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr int NKB = 64;  // K blocks of 128
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < NKB; kb++) {
+        const int s = kb % HG_STAGES, ph = (kb / HG_STAGES) & 1;
+        mbar_wait(empty + s, ph ^ 1);
+        mbar_expect_tx(full + s, HG_STAGE_BYTES);
+        uint8_t* dst = smem + s * HG_STAGE_BYTES;
+#pragma unroll 1
+        for (int pl = 0; pl < 16; pl++)
+          bulk_g2s(dst + pl * 2048, act + ((size_t)(kb * 16 + pl) * slots + m0) * 8, 2048, full + s);
+        bulk_g2s(dst + 32768, wts + (size_t)kb * 16384, 32768, full + s);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = instr_desc_f16(128);
+      for (int kb = 0; kb < NKB; kb++) {
+        const int s = kb % HG_STAGES, ph = (kb / HG_STAGES) & 1;
+        mbar_wait(full + s, ph);
+        fence_after_sync();
+        const uint32_t a_addr = smem_u32(smem + s * HG_STAGE_BYTES), b_addr = a_addr + 32768;
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          mma_f16(tmem_base, smem_desc(a_addr + j * 4096, 2048, 128), smem_desc(b_addr + j * 4096, 2048, 128), idesc, (kb | j) != 0);
+        mma_commit(empty + s);
+      }
+      mma_commit(t_full);
+    }
+  } else {
+    const int q = warp & 3, m = q * 32 + lane, patch = m0 + m;
+    mbar_wait(t_full, 0);
+    fence_after_sync();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    float ss = 0.f;
+#pragma unroll 1
+    for (int cc = 0; cc < 8; cc++) {
+      float v[16];
+      tmem_ld16(taddr + cc * 16, v);
+#pragma unroll
+      for (int e = 0; e < 16; e++) { float t = v[e] + __ldg(bias + cc * 16 + e); ss = fmaf(t, t, ss); }
+    }
+    // L2Norm (desc_server.py:49-52) then uint8(clip(210*(d+0.45),0,255)) (desc_server.py:42)
+    const float norm = sqrtf(ss + 1e-10f);
+#pragma unroll 1
+    for (int cc = 0; cc < 8; cc++) {
+      float v[16];
+      tmem_ld16(taddr + cc * 16, v);
+      if (patch < np) {
+        float o[16];
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+          float d = (v[e] + __ldg(bias + cc * 16 + e)) / norm;
+          double qd = 210.0 * ((double)d + 0.45);
+          qd = qd < 0.0 ? 0.0 : (qd > 255.0 ? 255.0 : qd);
+          o[e] = (float)(int)qd;
+        }
+        float4* dst = reinterpret_cast<float4*>(out + (size_t)patch * 128 + cc * 16);
+#pragma unroll
+        for (int e = 0; e < 4; e++) dst[e] = make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<128>(tmem_base);
+}
+
+// =================================================================================================
+// AffNet / OriNet heads on CUDA cores (input: conv6 output, S = 8, 64 channels, NORMAL layout)
+// =================================================================================================
+__device__ __forceinline__ float warp_sum(float v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ void load8(const __half* p, float* f) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; i++) { float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+
+// conv 8x8 (64->3, bias) -> tanh -> +1 on outputs 0 and 2 (affnet_server.py:64-66,:80-84)
+__global__ void k_head_aff(const __half* __restrict__ act, size_t slots, const float* __restrict__ w,
+                           const float* __restrict__ b, float* __restrict__ out, int np) {
+  const int patch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (patch >= np) return;
+  float acc[3] = {0.f, 0.f, 0.f};
+  for (int it = lane; it < 512; it += 32) {
+    const int pix = it >> 3, c8 = it & 7, y = pix >> 3, x = pix & 7;
+    float a[8];
+    load8(act + ((size_t)c8 * slots + FS + (size_t)patch * 81 + (y + 1) * 9 + x) * 8, a);
+#pragma unroll
+    for (int o = 0; o < 3; o++) {
+      const float* wp = w + ((size_t)o * 64 + pix) * 64 + c8 * 8;
+#pragma unroll
+      for (int e = 0; e < 8; e++) acc[o] = fmaf(a[e], __ldg(wp + e), acc[o]);
+    }
+  }
+  for (int o = 0; o < 3; o++) acc[o] = warp_sum(acc[o]);
+  if (lane == 0) {
+    out[patch * 3 + 0] = tanhf(acc[0] + b[0]) + 1.f;
+    out[patch * 3 + 1] = tanhf(acc[1] + b[1]);
+    out[patch * 3 + 2] = tanhf(acc[2] + b[2]) + 1.f;
+  }
+}
+
+// conv 8x8 pad 1 (64->2, bias) -> 3x3 map -> tanh -> mean (orinet_server.py:64-70)
+__global__ void k_head_ori(const __half* __restrict__ act, size_t slots, const float* __restrict__ w,
+                           const float* __restrict__ b, float* __restrict__ out, int np) {
+  const int patch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (patch >= np) return;
+  float res[2] = {0.f, 0.f};
+  for (int pos = 0; pos < 9; pos++) {
+    const int oy = pos / 3, ox = pos % 3;
+    float acc[2] = {0.f, 0.f};
+    for (int it = lane; it < 512; it += 32) {
+      const int pix = it >> 3, c8 = it & 7, y = pix >> 3, x = pix & 7;
+      const int ky = y - oy + 1, kx = x - ox + 1;
+      if (ky < 0 || ky > 7 || kx < 0 || kx > 7) continue;
+      float a[8];
+      load8(act + ((size_t)c8 * slots + FS + (size_t)patch * 81 + (y + 1) * 9 + x) * 8, a);
+#pragma unroll
+      for (int o = 0; o < 2; o++) {
+        const float* wp = w + ((size_t)o * 64 + ky * 8 + kx) * 64 + c8 * 8;
+#pragma unroll
+        for (int e = 0; e < 8; e++) acc[o] = fmaf(a[e], __ldg(wp + e), acc[o]);
+      }
+    }
+    for (int o = 0; o < 2; o++) res[o] += tanhf(warp_sum(acc[o]) + b[o]);
+  }
+  if (lane == 0) {
+    out[patch * 2 + 0] = res[0] / 9.f;
+    out[patch * 2 + 1] = res[1] / 9.f;
+  }
+}
+
+// =================================================================================================
+// debug probe: one 128 x N x 64 GEMM through the same descriptor conventions (tests only)
+// =================================================================================================
+__global__ void __launch_bounds__(128, 1)
+k_umma_probe(const __half* __restrict__ A, const __half* __restrict__ B, float* __restrict__ D, int swap_lbo_sbo) {
+  // A: [8 planes][128 rows][8], B: [8 planes][32 rows][8]  (K = 64, N = 32)
+  __shared__ __align__(1024) uint8_t sa[8 * 128 * 16];
+  __shared__ __align__(1024) uint8_t sb[8 * 32 * 16];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tslot;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 8 * 128; i += 128) reinterpret_cast<uint4*>(sa)[i] = reinterpret_cast<const uint4*>(A)[i];
+  for (int i = threadIdx.x; i < 8 * 32; i += 128) reinterpret_cast<uint4*>(sb)[i] = reinterpret_cast<const uint4*>(B)[i];
+  fence_proxy_async();
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc<32>(&tslot);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tb = tslot;
+  if (threadIdx.x == 0) {
+    constexpr uint32_t idesc = instr_desc_f16(32);
+    for (int ks = 0; ks < 4; ks++) {
+      uint32_t a = smem_u32(sa) + (2 * ks) * 128 * 16, b = smem_u32(sb) + (2 * ks) * 32 * 16;
+      uint64_t da = swap_lbo_sbo ? smem_desc(a, 128, 128 * 16) : smem_desc(a, 128 * 16, 128);
+      uint64_t db = swap_lbo_sbo ? smem_desc(b, 128, 32 * 16) : smem_desc(b, 32 * 16, 128);
+      mma_f16(tb, da, db, idesc, ks != 0);
+    }
+    mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  fence_after_sync();
+  const int m = threadIdx.x;
+  for (int cc = 0; cc < 2; cc++) {
+    float v[16];
+    tmem_ld16(tb + ((uint32_t)(warp * 32) << 16) + cc * 16, v);
+    for (int e = 0; e < 16; e++) D[m * 32 + cc * 16 + e] = v[e];
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<32>(tb);
+}
+
+// =================================================================================================
+// host side
+// =================================================================================================
+size_t plane_slots(int cap, int S) { return (size_t)FS + (size_t)round_up(cap * (S + 1) * (S + 1), 128) + 128; }
+
+// [Cout][3][3][Cin] fp32 -> per output slice nsp: [tap][k16][2][COUT_T][8] fp16
+std::vector<__half> pack_conv(const NpzArray& w, int cin, int cout, int nsplit) {
+  const int cout_t = cout / nsplit, ksteps = cin / 16;
+  std::vector<__half> r((size_t)9 * cin * cout);
+  size_t o = 0;
+  for (int ns = 0; ns < nsplit; ns++)
+    for (int t = 0; t < 9; t++)
+      for (int ks = 0; ks < ksteps; ks++)
+        for (int j = 0; j < 2; j++)
+          for (int n = 0; n < cout_t; n++)
+            for (int e = 0; e < 8; e++)
+              r[o++] = __float2half_rn(w.data[((size_t)(ns * cout_t + n) * 9 + t) * cin + ks * 16 + j * 8 + e]);
+  return r;
+}
+
+template <class T>
+cudaError_t upload(T** dst, const void* src, size_t bytes) {
+  cudaError_t e = cudaMalloc((void**)dst, bytes);
+  if (e != cudaSuccess) return e;
+  return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+}
+
+int cnn_chunk_cap() {
+  const char* e = getenv("MODSGPU_CNN_CHUNK");
+  int v = e ? atoi(e) : 512;
+  if (v < 128) v = 128;
+  return round_up(v, 128);
+}
+
+template <int CIN, int COUT_T, int NSPLIT, int S, int NGRP, int OUT_MODE>
+int launch_conv(modsgpu_ctx* ctx, const __half* in, size_t in_slots, const ConvW& w, __half* out, size_t out_slots, int np) {
+  using Cfg = ConvCfg<CIN, COUT_T, NSPLIT, S, NGRP, OUT_MODE>;
+  auto kern = k_conv_umma<CIN, COUT_T, NSPLIT, S, NGRP, OUT_MODE>;
+  static bool attr = false;
+  if (!attr) {
+    MG_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr = true;
+  }
+  const int ntiles = ceil_div(np * Cfg::PP, 128);
+  int gx = std::min(ntiles, std::max(1, ctx->num_sms / NSPLIT));
+  dim3 grid(gx, NSPLIT);
+  kern<<<grid, 192, Cfg::SMEM_BYTES, ctx->stream>>>(in, in_slots, w.w, w.b, out, out_slots, np, ntiles);
+  MG_LAUNCHED(ctx);
+  return 0;
+}
+
+}  // namespace
+
+static void free_net(NetWeights* nw) {
+  if (!nw) return;
+  cudaFree(nw->c1_w); cudaFree(nw->c1_b);
+  for (auto& c : nw->conv) { cudaFree(c.w); cudaFree(c.b); }
+  cudaFree(nw->head_w16); cudaFree(nw->head_w32); cudaFree(nw->head_b);
+  for (auto a : nw->act) cudaFree(a);
+  delete nw;
+}
+
+void mg_free_nets(modsgpu_ctx* ctx) {
+  for (int i = 0; i < 3; i++) { free_net(ctx->nets[i]); ctx->nets[i] = nullptr; }
+}
+
+extern "C" int modsgpu_net_out_dim(modsgpu_net net) { return net == MODSGPU_AFFNET ? 3 : (net == MODSGPU_ORINET ? 2 : 128); }
+
+extern "C" int modsgpu_load_weights(modsgpu_ctx* ctx, modsgpu_net net, const char* path) {
+  if (!ctx || !path || (int)net < 0 || (int)net > 2) return MODSGPU_EINVAL;
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::map<std::string, NpzArray> z;
+  std::string err;
+  if (!npz_load(path, z, err)) MG_FAIL(ctx, MODSGPU_EIO, "weights: " + err);
+  const int C1 = net == MODSGPU_HARDNET ? 32 : 16;
+  const int cins[5] = {C1, C1, 2 * C1, 2 * C1, 4 * C1}, couts[5] = {C1, 2 * C1, 2 * C1, 4 * C1, 4 * C1};
+  const int nsplit[5] = {1, 1, 1, net == MODSGPU_HARDNET ? 2 : 1, net == MODSGPU_HARDNET ? 2 : 1};
+  auto need = [&](const char* k, std::vector<int> shape) -> const NpzArray* {
+    auto it = z.find(k);
+    if (it == z.end() || it->second.shape != shape) return nullptr;
+    return &it->second;
+  };
+  if (ctx->nets[net]) { free_net(ctx->nets[net]); ctx->nets[net] = nullptr; }
+  NetWeights* nw = new NetWeights();
+  nw->net = net; nw->C1 = C1; nw->out_dim = modsgpu_net_out_dim(net);
+  const NpzArray* w1 = need("c1_w", {C1, 3, 3, 1});
+  const NpzArray* b1 = need("c1_b", {C1});
+  if (!w1 || !b1) { delete nw; MG_FAIL(ctx, MODSGPU_EIO, "weights: c1_w/c1_b missing or wrong shape"); }
+  MG_CUDA(ctx, upload(&nw->c1_w, w1->data.data(), w1->data.size() * 4));
+  MG_CUDA(ctx, upload(&nw->c1_b, b1->data.data(), b1->data.size() * 4));
+  for (int l = 0; l < 5; l++) {
+    std::string wn = "c" + std::to_string(l + 2) + "_w", bn = "c" + std::to_string(l + 2) + "_b";
+    const NpzArray* w = need(wn.c_str(), {couts[l], 3, 3, cins[l]});
+    const NpzArray* b = need(bn.c_str(), {couts[l]});
+    if (!w || !b) { delete nw; MG_FAIL(ctx, MODSGPU_EIO, "weights: " + wn + " missing or wrong shape"); }
+    std::vector<__half> pk = pack_conv(*w, cins[l], couts[l], nsplit[l]);
+    MG_CUDA(ctx, upload(&nw->conv[l].w, pk.data(), pk.size() * 2));
+    MG_CUDA(ctx, upload(&nw->conv[l].b, b->data.data(), b->data.size() * 4));
+  }
+  const NpzArray* hw = need("h_w", {nw->out_dim, 8, 8, 4 * C1});
+  const NpzArray* hb = need("h_b", {nw->out_dim});
+  if (!hw || !hb) { delete nw; MG_FAIL(ctx, MODSGPU_EIO, "weights: h_w/h_b missing or wrong shape"); }
+  MG_CUDA(ctx, upload(&nw->head_b, hb->data.data(), hb->data.size() * 4));
+  if (net == MODSGPU_HARDNET) {
+    // K = (y*8+x)*128 + c ; blocks of k16: [2][128 n][8]
+    std::vector<__half> pk((size_t)128 * 8192);
+    size_t o = 0;
+    for (int kk = 0; kk < 512; kk++)
+      for (int j = 0; j < 2; j++)
+        for (int n = 0; n < 128; n++)
+          for (int e = 0; e < 8; e++) pk[o++] = __float2half_rn(hw->data[(size_t)n * 8192 + kk * 16 + j * 8 + e]);
+    MG_CUDA(ctx, upload(&nw->head_w16, pk.data(), pk.size() * 2));
+  } else {
+    MG_CUDA(ctx, upload(&nw->head_w32, hw->data.data(), hw->data.size() * 4));
+  }
+  // activation buffers, zeroed once: pad slots are never written afterwards
+  const int cap = cnn_chunk_cap();
+  nw->cap = cap;
+  const int S_of[6] = {32, 16, 16, 8, 8, 8};
+  const int planes[6] = {C1 / 8, 4 * C1 / 8, 2 * C1 / 8, 4 * 2 * C1 / 8, 4 * C1 / 8, 4 * C1 / 8};
+  for (int i = 0; i < 6; i++) {
+    size_t slots = plane_slots(cap, S_of[i]);
+    int npl = planes[i];
+    if (i == 5 && net == MODSGPU_HARDNET) { slots = (size_t)cap; npl = 64 * 16; }
+    nw->slots[i] = slots;
+    size_t bytes = slots * npl * 16;
+    MG_CUDA(ctx, cudaMalloc((void**)&nw->act[i], bytes));
+    MG_CUDA(ctx, cudaMemset(nw->act[i], 0, bytes));
+  }
+  ctx->nets[net] = nw;
+  return 0;
+}
+
+// Enqueue the forward pass of `net` on n device-resident 32x32 u8 patches; d_out: n x out_dim floats.
+int mg_net_forward_enqueue(modsgpu_ctx* ctx, modsgpu_net net, const uint8_t* d_patches, int n, float* d_out) {
+  NetWeights* nw = ctx->nets[net];
+  if (!nw) MG_FAIL(ctx, MODSGPU_ESTATE, "modsgpu_load_weights has not been called for this net");
+  for (int p0 = 0; p0 < n; p0 += nw->cap) {
+    const int np = std::min(nw->cap, n - p0);
+    const uint8_t* pin = d_patches + (size_t)p0 * 1024;
+    float* pout = d_out + (size_t)p0 * nw->out_dim;
+    int rc = 0;
+    if (net == MODSGPU_HARDNET) {
+      k_conv1<32><<<np, 256, 0, ctx->stream>>>(pin, np, nw->c1_w, nw->c1_b, nw->act[0], nw->slots[0]);
+      MG_LAUNCHED(ctx);
+      if ((rc = launch_conv<32, 32, 1, 32, 1, OUT_PARITY>(ctx, nw->act[0], nw->slots[0], nw->conv[0], nw->act[1], nw->slots[1], np))) return rc;
+      if ((rc = launch_conv<32, 64, 1, 16, 4, OUT_NORMAL>(ctx, nw->act[1], nw->slots[1], nw->conv[1], nw->act[2], nw->slots[2], np))) return rc;
+      if ((rc = launch_conv<64, 64, 1, 16, 1, OUT_PARITY>(ctx, nw->act[2], nw->slots[2], nw->conv[2], nw->act[3], nw->slots[3], np))) return rc;
+      if ((rc = launch_conv<64, 64, 2, 8, 4, OUT_NORMAL>(ctx, nw->act[3], nw->slots[3], nw->conv[3], nw->act[4], nw->slots[4], np))) return rc;
+      if ((rc = launch_conv<128, 64, 2, 8, 1, OUT_GEMM>(ctx, nw->act[4], nw->slots[4], nw->conv[4], nw->act[5], nw->slots[5], np))) return rc;
+      static bool attr = false;
+      if (!attr) { MG_CUDA(ctx, cudaFuncSetAttribute(k_head_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, HG_SMEM)); attr = true; }
+      k_head_gemm<<<ceil_div(np, 128), 192, HG_SMEM, ctx->stream>>>(nw->act[5], nw->slots[5], nw->head_w16, nw->head_b, pout, np);
+      MG_LAUNCHED(ctx);
+    } else {
+      k_conv1<16><<<np, 256, 0, ctx->stream>>>(pin, np, nw->c1_w, nw->c1_b, nw->act[0], nw->slots[0]);
+      MG_LAUNCHED(ctx);
+      if ((rc = launch_conv<16, 16, 1, 32, 1, OUT_PARITY>(ctx, nw->act[0], nw->slots[0], nw->conv[0], nw->act[1], nw->slots[1], np))) return rc;
+      if ((rc = launch_conv<16, 32, 1, 16, 4, OUT_NORMAL>(ctx, nw->act[1], nw->slots[1], nw->conv[1], nw->act[2], nw->slots[2], np))) return rc;
+      if ((rc = launch_conv<32, 32, 1, 16, 1, OUT_PARITY>(ctx, nw->act[2], nw->slots[2], nw->conv[2], nw->act[3], nw->slots[3], np))) return rc;
+      if ((rc = launch_conv<32, 64, 1, 8, 4, OUT_NORMAL>(ctx, nw->act[3], nw->slots[3], nw->conv[3], nw->act[4], nw->slots[4], np))) return rc;
+      if ((rc = launch_conv<64, 64, 1, 8, 1, OUT_NORMAL>(ctx, nw->act[4], nw->slots[4], nw->conv[4], nw->act[5], nw->slots[5], np))) return rc;
+      if (net == MODSGPU_AFFNET)
+        k_head_aff<<<ceil_div(np, 8), 256, 0, ctx->stream>>>(nw->act[5], nw->slots[5], nw->head_w32, nw->head_b, pout, np);
+      else
+        k_head_ori<<<ceil_div(np, 8), 256, 0, ctx->stream>>>(nw->act[5], nw->slots[5], nw->head_w32, nw->head_b, pout, np);
+      MG_LAUNCHED(ctx);
+    }
+  }
+  return 0;
+}
+
+extern "C" int modsgpu_net_forward_u8(modsgpu_ctx* ctx, modsgpu_net net, const uint8_t* patches, int n, float* out) {
+  if (!ctx || (n > 0 && (!patches || !out)) || n < 0 || (int)net < 0 || (int)net > 2) return MODSGPU_EINVAL;
+  if (mg_begin(ctx)) return MODSGPU_ECUDA;
+  if (n == 0) return mg_end(ctx) ? MODSGPU_ECUDA : 0;
+  const int D = modsgpu_net_out_dim(net);
+  MG_CUDA(ctx, ctx->smp_out.ensure((size_t)n * 1024));
+  MG_CUDA(ctx, ctx->cnn_out.ensure((size_t)n * D * 4));
+  MG_CUDA(ctx, cudaMemcpyAsync(ctx->smp_out.p, patches, (size_t)n * 1024, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = mg_net_forward_enqueue(ctx, net, ctx->smp_out.as<uint8_t>(), n, ctx->cnn_out.as<float>());
+  if (rc) return rc;
+  MG_CUDA(ctx, cudaMemcpyAsync(out, ctx->cnn_out.p, (size_t)n * D * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  return mg_end(ctx) ? MODSGPU_ECUDA : 0;
+}
+
+int mg_sample_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_region* regs, int n,
+                      double mrSize, int ps, uint8_t* d_out);
+
+extern "C" int modsgpu_describe(modsgpu_ctx* ctx, modsgpu_net net, const modsgpu_image* img, const modsgpu_region* regs,
+                                int n, double mrSize, int patchSize, float* out) {
+  if (!ctx || !img || (n > 0 && (!regs || !out)) || n < 0 || (int)net < 0 || (int)net > 2) return MODSGPU_EINVAL;
+  if (patchSize != 32) MG_FAIL(ctx, MODSGPU_EINVAL, "the networks take 32x32 patches");
+  if (mg_begin(ctx)) return MODSGPU_ECUDA;
+  if (n == 0) return mg_end(ctx) ? MODSGPU_ECUDA : 0;
+  const int D = modsgpu_net_out_dim(net);
+  MG_CUDA(ctx, ctx->smp_out.ensure((size_t)n * 1024));
+  MG_CUDA(ctx, ctx->cnn_out.ensure((size_t)n * D * 4));
+  int rc = mg_sample_enqueue(ctx, img, regs, n, mrSize, patchSize, ctx->smp_out.as<uint8_t>());
+  if (rc) return rc;
+  rc = mg_net_forward_enqueue(ctx, net, ctx->smp_out.as<uint8_t>(), n, ctx->cnn_out.as<float>());
+  if (rc) return rc;
+  MG_CUDA(ctx, cudaMemcpyAsync(out, ctx->cnn_out.p, (size_t)n * D * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  return mg_end(ctx) ? MODSGPU_ECUDA : 0;
+}
+
+// test-only: D[128 x 32] = A[128 x 64] * B[32 x 64]^T through the tcgen05 path; A/B given row-major fp32
+extern "C" int modsgpu_debug_umma_probe(modsgpu_ctx* ctx, const float* A, const float* B, float* D, int swap_lbo_sbo) {
+  if (!ctx || !A || !B || !D) return MODSGPU_EINVAL;
+  if (mg_begin(ctx)) return MODSGPU_ECUDA;
+  std::vector<__half> ha(8 * 128 * 8), hb(8 * 32 * 8);
+  for (int c8 = 0; c8 < 8; c8++) {
+    for (int r = 0; r < 128; r++) for (int e = 0; e < 8; e++) ha[((size_t)c8 * 128 + r) * 8 + e] = __float2half_rn(A[r * 64 + c8 * 8 + e]);
+    for (int r = 0; r < 32; r++) for (int e = 0; e < 8; e++) hb[((size_t)c8 * 32 + r) * 8 + e] = __float2half_rn(B[r * 64 + c8 * 8 + e]);
+  }
+  MG_CUDA(ctx, ctx->io_a.ensure(ha.size() * 2));
+  MG_CUDA(ctx, ctx->io_b.ensure(hb.size() * 2));
+  MG_CUDA(ctx, ctx->io_c.ensure(128 * 32 * 4));
+  MG_CUDA(ctx, cudaMemcpyAsync(ctx->io_a.p, ha.data(), ha.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
+  MG_CUDA(ctx, cudaMemcpyAsync(ctx->io_b.p, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
+  k_umma_probe<<<1, 128, 0, ctx->stream>>>(ctx->io_a.as<__half>(), ctx->io_b.as<__half>(), ctx->io_c.as<float>(), swap_lbo_sbo);
+  MG_LAUNCHED(ctx);
+  MG_CUDA(ctx, cudaMemcpyAsync(D, ctx->io_c.p, 128 * 32 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  return mg_end(ctx) ? MODSGPU_ECUDA : 0;
+}

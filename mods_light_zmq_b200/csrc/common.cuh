@@ -1,0 +1,109 @@
+// common.cuh -- context, workspace buffers and error plumbing shared by the kernels of libmodsgpu.so
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/modsgpu.h"
+
+// A grow-only device buffer: cudaMalloc is far too slow to sit on the per-image path.
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// Pinned host staging buffer (grow-only).
+struct HostBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct modsgpu_image {
+  float* d = nullptr;  // device, w*h, dense
+  int w = 0, h = 0;
+};
+
+struct NetWeights;  // cnn.cu
+
+struct modsgpu_ctx {
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  float last_ms = 0.f;
+  long long launches = 0;
+  std::string err;
+  // workspaces (named by their user)
+  DevBuf det_pyr, det_cand, det_map, det_out, det_misc;
+  HostBuf h_stage, h_stage2;
+  DevBuf io_a, io_b, io_c;            // generic staging for the test-only entry points
+  DevBuf smp_regs, smp_meta, smp_taps, smp_scratch, smp_out;
+  DevBuf cnn_act0, cnn_act1, cnn_out;
+  DevBuf mt_q, mt_t, mt_d, mt_aux, mt_out;
+  DevBuf rs_buf;
+  NetWeights* nets[3] = {nullptr, nullptr, nullptr};
+};
+
+#define MG_CUDA(ctx, call)                                                                  \
+  do {                                                                                      \
+    cudaError_t e__ = (call);                                                               \
+    if (e__ != cudaSuccess) {                                                               \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" + \
+                   std::to_string(__LINE__) + ")";                                          \
+      return MODSGPU_ECUDA;                                                                 \
+    }                                                                                       \
+  } while (0)
+
+#define MG_FAIL(ctx, code, msg) \
+  do { (ctx)->err = (msg); return (code); } while (0)
+
+// after every kernel launch
+#define MG_LAUNCHED(ctx)                         \
+  do {                                           \
+    (ctx)->launches++;                           \
+    MG_CUDA(ctx, cudaGetLastError());            \
+  } while (0)
+
+static inline int mg_begin(modsgpu_ctx* ctx) {
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  MG_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  return 0;
+}
+static inline int mg_end(modsgpu_ctx* ctx) {
+  MG_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  MG_CUDA(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+  return 0;
+}
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Gaussian taps exactly as cv::getGaussianKernel(ksize,(double)sigma,CV_32F) produces them for the
+// ksize rule of helpers.cpp:717-731: ksize=(int)(2*3*sigma+1), forced odd.  Returns ksize.
+int mg_gaussian_taps(float sigma, std::vector<float>& taps);

@@ -1,0 +1,640 @@
+// detect.cu -- Hessian scale-space detector on the device.
+//
+// Compiled with --fmad=false: every float expression below is evaluated exactly as written
+// (no contraction); fused multiply-adds appear only as explicit fmaf().  That is what makes the
+// keypoint list bit-identical to the CPU oracle (oracle/mods_oracle.cpp), which restates
+// pyramid.cpp:196-529 and the arithmetic order of cv::GaussianBlur / cv::resize.
+//
+// Data layout in HBM: one workspace holds, per octave o (w_o x h_o, dense row-major fp32),
+// five blur levels L[0..4] and five responses R[0..4]; an int32 "octave map" (w_o x h_o)
+// resolves the reference's sequential octaveMap de-duplication (pyramid.cpp:387-391)
+// deterministically: the candidate with the smallest (level, r0, c0) visiting key wins.
+#include "common.cuh"
+#include <cmath>
+#include <algorithm>
+
+namespace {
+
+constexpr int BT_X = 64, BT_Y = 32, BT_THREADS = 256;
+constexpr int MAX_KS = 63;
+
+struct Taps {
+  float k[MAX_KS + 1];
+  int ks;
+};
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// Row pass of cv::GaussianBlur for one output pixel; p points at the tap-0 sample (x - r).
+// `vec` = x < (w & ~3): the SIMD body of OpenCV's row filter (fused), else its scalar tail.
+__device__ __forceinline__ float row_pass(const float* p, const float* k, int ks, bool vec, bool vec2) {
+  const int r = ks >> 1;
+  float s;
+  if (ks == 5) {
+    float p1 = p[r + 1] + p[r - 1], p2 = p[r + 2] + p[r - 2], x0 = p[r];
+    if (vec2) {
+      s = p1 * k[3];
+      s = fmaf(x0, k[2], s);
+      s = fmaf(p2, k[4], s);
+    } else {
+      s = x0 * k[2] + p1 * k[3];
+      s = s + p2 * k[4];
+    }
+  } else if (ks < 5) {
+    s = p[r] * k[r];
+    for (int t = 1; t <= r; t++) s = s + (p[r + t] + p[r - t]) * k[r + t];
+  } else if (vec) {
+    s = 0.f;
+    for (int t = 0; t < ks; t++) s = fmaf(p[t], k[t], s);
+  } else {
+    const int nf = (ks - 1) % 4;
+    s = p[0] * k[0];
+    for (int t = 1; t < ks; t++) {
+      if (t >= ks - nf) s = fmaf(p[t], k[t], s);
+      else s = s + p[t] * k[t];
+    }
+  }
+  return s;
+}
+
+// Column pass; p points at the centre sample, `pitch` floats between rows. `vec` = x < (w & ~7).
+__device__ __forceinline__ float col_pass(const float* p, int pitch, const float* k, int ks, bool vec) {
+  const int r = ks >> 1;
+  float s = p[0] * k[r];
+  if (vec) {
+    for (int t = 1; t <= r; t++) s = fmaf(p[-t * pitch] + p[t * pitch], k[r + t], s);
+  } else {
+    for (int t = 1; t <= r; t++) s = s + (p[-t * pitch] + p[t * pitch]) * k[r + t];
+  }
+  return s;
+}
+
+// pyramid.cpp:196-254
+__device__ __forceinline__ float hessian_at(const float* c, int pitch, float norm2) {
+  float v11 = c[-pitch - 1], v12 = c[-pitch], v13 = c[-pitch + 1];
+  float v21 = c[-1], v22 = c[0], v23 = c[1];
+  float v31 = c[pitch - 1], v32 = c[pitch], v33 = c[pitch + 1];
+  float Lxx = (v21 - 2 * v22 + v23);
+  float Lyy = (v12 - 2 * v22 + v32);
+  float Lxy = (v13 - v11 + v31 - v33) / 4.0f;
+  return (Lxx * Lyy - Lxy * Lxy) * norm2;
+}
+
+// Fused separable Gaussian blur (+ optional Hessian response of the blurred image).
+// One CTA -> a BT_X x BT_Y output tile.  Shared memory: A = source tile with (r+1) halo,
+// B = row-filtered, C = blurred tile with 1-px halo (for the 3x3 Hessian stencil).
+__global__ void __launch_bounds__(BT_THREADS)
+k_blur_resp(const float* __restrict__ src, float* __restrict__ dst, float* __restrict__ resp,
+            int w, int h, Taps taps, float norm2) {
+  extern __shared__ float sm[];
+  const int ks = taps.ks, r = ks >> 1;
+  const int AW = BT_X + 2 + 2 * r, AH = BT_Y + 2 + 2 * r;
+  const int BW = BT_X + 2, CW = BT_X + 2, CH = BT_Y + 2;
+  float* A = sm;
+  float* B = A + AW * AH;
+  float* C = B + BW * AH;
+  __shared__ float k[MAX_KS + 1];
+  const int tid = threadIdx.x;
+  if (tid < ks) k[tid] = taps.k[tid];
+  const int x0 = blockIdx.x * BT_X, y0 = blockIdx.y * BT_Y;
+  for (int i = tid; i < AW * AH; i += BT_THREADS) {
+    int ly = i / AW, lx = i - ly * AW;
+    int gy = clampi(y0 - 1 - r + ly, 0, h - 1), gx = clampi(x0 - 1 - r + lx, 0, w - 1);
+    A[i] = src[(size_t)gy * w + gx];
+  }
+  __syncthreads();
+  const int wv = w & ~3, wv2 = w & ~1, wc = w & ~7;
+  for (int i = tid; i < BW * AH; i += BT_THREADS) {
+    int ly = i / BW, lx = i - ly * BW;
+    int gx = x0 - 1 + lx;
+    float v = 0.f;
+    if (gx >= 0 && gx < w) v = row_pass(A + ly * AW + lx, k, ks, gx < wv, gx < wv2);
+    B[i] = v;
+  }
+  __syncthreads();
+  for (int i = tid; i < CW * CH; i += BT_THREADS) {
+    int ly = i / CW, lx = i - ly * CW;
+    int gx = x0 - 1 + lx, gy = y0 - 1 + ly;
+    float v = 0.f;
+    if (gx >= 0 && gx < w && gy >= 0 && gy < h) {
+      v = col_pass(B + (ly + r) * BW + lx, BW, k, ks, gx < wc);
+      if (lx >= 1 && lx <= BT_X && ly >= 1 && ly <= BT_Y) dst[(size_t)gy * w + gx] = v;
+    }
+    C[i] = v;
+  }
+  if (!resp) return;
+  __syncthreads();
+  for (int i = tid; i < BT_X * BT_Y; i += BT_THREADS) {
+    int ly = i / BT_X, lx = i - ly * BT_X;
+    int gx = x0 + lx, gy = y0 + ly;
+    if (gx >= w || gy >= h) continue;
+    float v = 0.f;
+    if (gx >= 1 && gx < w - 1 && gy >= 1 && gy < h - 1) v = hessian_at(C + (ly + 1) * CW + lx + 1, CW, norm2);
+    resp[(size_t)gy * w + gx] = v;
+  }
+}
+
+// Hessian response of an image already in HBM (first level of octaves >= 1).
+__global__ void k_response(const float* __restrict__ src, float* __restrict__ resp, int w, int h, float norm2) {
+  int gx = blockIdx.x * blockDim.x + threadIdx.x, gy = blockIdx.y * blockDim.y + threadIdx.y;
+  if (gx >= w || gy >= h) return;
+  float v = 0.f;
+  if (gx >= 1 && gx < w - 1 && gy >= 1 && gy < h - 1) v = hessian_at(src + (size_t)gy * w + gx, w, norm2);
+  resp[(size_t)gy * w + gx] = v;
+}
+
+// pyramid.cpp:476 cv::resize(.., 0.5, 0.5, INTER_LINEAR): lerp form a+(b-a)*0.5, x then y.
+__global__ void k_half(const float* __restrict__ in, int w, int h, float* __restrict__ out, int ow, int oh) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= ow || y >= oh) return;
+  int y0 = min(2 * y, h - 1), y1 = min(2 * y + 1, h - 1);
+  int xa = min(2 * x, w - 1), xb = min(2 * x + 1, w - 1);
+  float a = in[(size_t)y0 * w + xa], b = in[(size_t)y0 * w + xb];
+  float c = in[(size_t)y1 * w + xa], d = in[(size_t)y1 * w + xb];
+  float r0 = a + (b - a) * 0.5f;
+  float r1 = c + (d - c) * 0.5f;
+  out[(size_t)y * ow + x] = r0 + (r1 - r0) * 0.5f;
+}
+
+// synth-detection.cpp:344-351: (B+G+R)/3.0 evaluated as convertTo(alpha = 1/3)
+__global__ void k_gray_from_bgr(const uint8_t* __restrict__ bgr, float* __restrict__ gray, long n) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float third = (float)(1.0 / 3.0);
+  float s = ((float)bgr[3 * i] + (float)bgr[3 * i + 1]) + (float)bgr[3 * i + 2];
+  gray[i] = s * third;
+}
+
+__global__ void k_fill_i32(int* p, long n, int v) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// ---- NMS + localisation -------------------------------------------------------------------
+
+struct Cand {           // one localised keypoint awaiting octave-map resolution
+  float x, y, s, response;
+  int type, octave, level, r0, c0, r, c;
+  unsigned order;       // global visiting order: octave_base + (level-1)*w*h + r0*w + c0
+  int map_key;          // (level-1)*w*h + r0*w + c0  (per-octave)
+  int map_off;          // offset of (r,c) inside the octave-map workspace
+};
+
+// helpers.cpp:309-368 solveLinear3x3 (pivoted Gauss, float)
+__device__ __forceinline__ void swapf(float& a, float& b) { float t = a; a = b; b = t; }
+__device__ void solveLinear3x3(float* A, float* b) {
+  int i = 0, prow = 0;
+  float vp = fabsf(A[0]);
+  float tmp = fabsf(A[3]);
+  if (tmp > vp) { prow = 3; i = 1; vp = tmp; }
+  if (fabsf(A[6]) > vp) { prow = 6; i = 2; }
+  if (prow != 0) {
+    swapf(A[prow], A[0]); swapf(A[prow + 1], A[1]); swapf(A[prow + 2], A[2]);
+    swapf(b[i], b[0]);
+  }
+  vp = A[3] / A[0]; A[4] -= vp * A[1]; A[5] -= vp * A[2]; b[1] -= vp * b[0];
+  vp = A[6] / A[0]; A[7] -= vp * A[1]; A[8] -= vp * A[2]; b[2] -= vp * b[0];
+  if (fabsf(A[4]) < fabsf(A[7])) {
+    swapf(A[7], A[4]); swapf(A[8], A[5]); swapf(b[2], b[1]);
+  }
+  vp = A[7] / A[4]; A[8] -= vp * A[5]; b[2] -= vp * b[1];
+  b[2] = (b[2]) / A[8];
+  b[1] = (b[1] - A[5] * b[2]) / A[4];
+  b[0] = (b[0] - A[2] * b[2] - A[1] * b[1]) / A[0];
+}
+
+struct LevelArgs {
+  const float* low; const float* cur; const float* high; const float* blur;
+  float curScale; int level;
+};
+struct NmsArgs {
+  LevelArgs lv[8];
+  int nlev;
+  int w, h, border, octave;
+  float pixelDistance;
+  float posThr, negThr, finalThr;
+  double edgeThr;
+  int numberOfScales;
+  unsigned octave_base;
+  int map_base;
+};
+
+// pyramid.cpp:281-403 localizeKeypoint + :65-124 getPointType
+__device__ void localize(const NmsArgs& a, const LevelArgs& L, int li, int r, int c, int* map, Cand* cands,
+                         int* ncand, int cap) {
+  const int w = a.w, cols = a.w, rows = a.h;
+  const int r0 = r, c0 = c;
+  float b[3] = {0.f, 0.f, 0.f};
+  float val = 0.f;
+  int nr = r, nc = c;
+  for (int iter = 0; iter < 5; iter++) {
+    r = nr; c = nc;
+    const float* cur0 = L.cur + (size_t)(r - 1) * w; const float* cur1 = L.cur + (size_t)r * w; const float* cur2 = L.cur + (size_t)(r + 1) * w;
+    const float* low0 = L.low + (size_t)(r - 1) * w; const float* low1 = L.low + (size_t)r * w; const float* low2 = L.low + (size_t)(r + 1) * w;
+    const float* high0 = L.high + (size_t)(r - 1) * w; const float* high1 = L.high + (size_t)r * w; const float* high2 = L.high + (size_t)(r + 1) * w;
+    float dxx = cur1[c - 1] - 2.0f * cur1[c] + cur1[c + 1];
+    float dyy = cur0[c] - 2.0f * cur1[c] + cur2[c];
+    float dss = low1[c] - 2.0f * cur1[c] + high1[c];
+    float dxy = 0.25f * (cur2[c + 1] - cur2[c - 1] - cur0[c + 1] + cur0[c - 1]);
+    if (0 == iter) {
+      float edgeScore = (dxx + dyy) * (dxx + dyy) / (dxx * dyy - dxy * dxy);
+      if ((double)edgeScore >= a.edgeThr || edgeScore < 0) return;
+    }
+    float dxs = 0.25f * (high1[c + 1] - high1[c - 1] - low1[c + 1] + low1[c - 1]);
+    float dys = 0.25f * (high2[c] - high0[c] - low2[c] + low0[c]);
+    float A[9] = {dxx, dxy, dxs, dxy, dyy, dys, dxs, dys, dss};
+    float dx = 0.5f * (cur1[c + 1] - cur1[c - 1]);
+    float dy = 0.5f * (cur2[c] - cur0[c]);
+    float ds = 0.5f * (high1[c] - low1[c]);
+    b[0] = -dx; b[1] = -dy; b[2] = -ds;
+    solveLinear3x3(A, b);
+    if (isnan(b[0]) || isnan(b[1]) || isnan(b[2])) return;
+    val = cur1[c] + 0.5f * (dx * b[0] + dy * b[1] + ds * b[2]);
+    if ((double)b[0] > 0.6) { if (c < cols - 3) nc++; else return; }
+    if ((double)b[1] > 0.6) { if (r < rows - 3) nr++; else return; }
+    if ((double)b[0] < -0.6) { if (c > 3) nc--; else return; }
+    if ((double)b[1] < -0.6) { if (r > 3) nr--; else return; }
+    if (nr == r && nc == c) break;
+  }
+  if (fabsf(b[0]) > 1.5f || fabsf(b[1]) > 1.5f || fabsf(b[2]) > 1.5f || fabsf(val) < a.finalThr) return;
+  float e = b[2] / (float)a.numberOfScales;
+  float scale = L.curScale * (float)exp2((double)e);
+  int type;
+  if (val < 0) type = 2;
+  else {
+    const float* ptr = L.blur + (size_t)r * w + c;
+    float Lxx = (ptr[-1] - 2 * ptr[0] + ptr[1]);
+    type = (Lxx < 0) ? 0 : 1;
+  }
+  int slot = atomicAdd(ncand, 1);
+  if (slot >= cap) return;
+  Cand k;
+  k.x = a.pixelDistance * ((float)c + b[0]);
+  k.y = a.pixelDistance * ((float)r + b[1]);
+  k.s = a.pixelDistance * scale;
+  k.response = val;
+  k.type = type; k.octave = a.octave; k.level = L.level;
+  k.r0 = r0; k.c0 = c0; k.r = r; k.c = c;
+  k.map_key = li * (a.w * a.h) + r0 * a.w + c0;
+  k.order = a.octave_base + (unsigned)k.map_key;
+  k.map_off = a.map_base + r * a.w + c;
+  cands[slot] = k;
+  atomicMin(map + k.map_off, k.map_key);
+}
+
+// pyramid.cpp:405-425 findLevelKeypoints (+ isMax/isMin :41-63), all NMS levels of one octave
+// in one launch (blockIdx.z = level index).
+__global__ void k_nms_localize(NmsArgs a, int* map, Cand* cands, int* ncand, int cap) {
+  const int li = blockIdx.z;
+  const LevelArgs& L = a.lv[li];
+  int c = a.border + blockIdx.x * blockDim.x + threadIdx.x;
+  int r = a.border + blockIdx.y * blockDim.y + threadIdx.y;
+  if (c >= a.w - a.border || r >= a.h - a.border) return;
+  const int w = a.w;
+  const float val = L.cur[(size_t)r * w + c];
+  bool pos = val > a.posThr, neg = val < a.negThr;
+  if (!pos && !neg) return;
+  const float* planes[3] = {L.cur, L.low, L.high};
+  bool ok = true;
+  for (int p = 0; p < 3 && ok; p++) {
+    const float* q = planes[p] + (size_t)(r - 1) * w + (c - 1);
+    for (int j = 0; j < 3 && ok; j++)
+      for (int i = 0; i < 3; i++) {
+        float v = q[j * w + i];
+        if (pos ? (v > val) : (v < val)) { ok = false; break; }
+      }
+  }
+  if (!ok) return;
+  localize(a, L, li, r, c, map, cands, ncand, cap);
+}
+
+// Octave-map resolution + export order: a candidate survives iff it holds the minimum visiting key
+// at its final (r,c); survivors are ranked by (|response| desc, visiting order asc) -- the order a
+// stable sort by |response| gives the reference's push order (scale-space-detector.hpp:120-131).
+__device__ __forceinline__ unsigned long long sort_key(const Cand& k) {
+  unsigned ab = __float_as_uint(fabsf(k.response));
+  return ((unsigned long long)(~ab) << 32) | (unsigned long long)k.order;
+}
+__global__ void k_resolve(const Cand* cands, const int* ncand_p, int cap, const int* map,
+                          unsigned long long* keys, int* nkept) {
+  int n = min(*ncand_p, cap);
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Cand& k = cands[i];
+  bool keep = map[k.map_off] == k.map_key;
+  keys[i] = keep ? sort_key(k) : ~0ull;
+  if (keep) atomicAdd(nkept, 1);
+}
+__global__ void k_rank_export(const Cand* cands, const int* ncand_p, int cap, const unsigned long long* keys,
+                              modsgpu_keypoint* out) {
+  __shared__ unsigned long long tile[256];
+  int n = min(*ncand_p, cap);
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long mine = i < n ? keys[i] : ~0ull;
+  int rank = 0;
+  for (int base = 0; base < n; base += 256) {
+    int j = base + threadIdx.x;
+    tile[threadIdx.x] = j < n ? keys[j] : ~0ull;
+    __syncthreads();
+    int lim = min(256, n - base);
+    for (int t = 0; t < lim; t++) rank += tile[t] < mine;
+    __syncthreads();
+  }
+  if (i < n && mine != ~0ull) {
+    const Cand& k = cands[i];
+    modsgpu_keypoint o;
+    o.x = k.x; o.y = k.y; o.s = k.s; o.response = k.response; o.type = k.type; o.octave = k.octave;
+    o.level = k.level; o.r0 = k.r0; o.c0 = k.c0; o.r = k.r; o.c = k.c; o.seq = 0;
+    out[rank] = o;
+  }
+}
+
+int blur_smem_bytes(int ks) {
+  int r = ks >> 1;
+  int AW = BT_X + 2 + 2 * r, AH = BT_Y + 2 + 2 * r;
+  return (AW * AH + (BT_X + 2) * AH + (BT_X + 2) * (BT_Y + 2)) * (int)sizeof(float);
+}
+
+int launch_blur(modsgpu_ctx* ctx, const float* src, float* dst, float* resp, int w, int h, float sigma, float norm2) {
+  std::vector<float> t;
+  int ks = mg_gaussian_taps(sigma, t);
+  if (ks > MAX_KS) MG_FAIL(ctx, MODSGPU_EINVAL, "gaussian kernel too wide for the pyramid blur (ksize > 63)");
+  Taps taps;
+  memset(&taps, 0, sizeof(taps));
+  taps.ks = ks;
+  for (int i = 0; i < ks; i++) taps.k[i] = t[i];
+  int smem = blur_smem_bytes(ks);
+  static bool attr_set = false;
+  if (!attr_set) {
+    MG_CUDA(ctx, cudaFuncSetAttribute(k_blur_resp, cudaFuncAttributeMaxDynamicSharedMemorySize, blur_smem_bytes(MAX_KS)));
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(w, BT_X), ceil_div(h, BT_Y));
+  k_blur_resp<<<grid, BT_THREADS, smem, ctx->stream>>>(src, dst, resp, w, h, taps, norm2);
+  MG_LAUNCHED(ctx);
+  return 0;
+}
+
+}  // namespace
+
+int mg_gaussian_taps(float sigmaf, std::vector<float>& taps) {
+  double sigma = (double)sigmaf;
+  int ks = (int)(2.0 * 3.0 * sigma + 1.0);
+  if (ks % 2 == 0) ks++;
+  if (ks < 1) ks = 1;
+  int r = ks / 2;
+  std::vector<double> kd(ks);
+  double sum = 0;
+  for (int i = 0; i < ks; i++) {
+    double x = i - r;
+    kd[i] = std::exp(-x * x / (2.0 * sigma * sigma));
+    sum += kd[i];
+  }
+  taps.resize(ks);
+  for (int i = 0; i < ks; i++) taps[i] = (float)(kd[i] / sum);
+  return ks;
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" void modsgpu_default_pyr_params(modsgpu_pyr_params* p) {
+  p->numberOfScales = 3; p->initialSigma = 1.6f; p->threshold = 5.33f; p->edgeEigenValueRatio = 10.0; p->border = 5;
+}
+
+extern "C" int modsgpu_image_from_bgr8(modsgpu_ctx* ctx, const uint8_t* bgr, int w, int h, modsgpu_image** out) {
+  if (!ctx || !bgr || w <= 0 || h <= 0 || !out) return MODSGPU_EINVAL;
+  if (mg_begin(ctx)) return MODSGPU_ECUDA;
+  size_t n = (size_t)w * h;
+  MG_CUDA(ctx, ctx->io_a.ensure(n * 3));
+  modsgpu_image* img = new modsgpu_image();
+  img->w = w; img->h = h;
+  MG_CUDA(ctx, cudaMalloc(&img->d, n * sizeof(float)));
+  MG_CUDA(ctx, cudaMemcpyAsync(ctx->io_a.p, bgr, n * 3, cudaMemcpyHostToDevice, ctx->stream));
+  k_gray_from_bgr<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->io_a.as<uint8_t>(), img->d, (long)n);
+  MG_LAUNCHED(ctx);
+  if (mg_end(ctx)) return MODSGPU_ECUDA;
+  *out = img;
+  return 0;
+}
+
+extern "C" int modsgpu_image_from_gray32f(modsgpu_ctx* ctx, const float* gray, int w, int h, int stride, modsgpu_image** out) {
+  if (!ctx || !gray || w <= 0 || h <= 0 || stride < w || !out) return MODSGPU_EINVAL;
+  if (mg_begin(ctx)) return MODSGPU_ECUDA;
+  modsgpu_image* img = new modsgpu_image();
+  img->w = w; img->h = h;
+  MG_CUDA(ctx, cudaMalloc(&img->d, (size_t)w * h * sizeof(float)));
+  MG_CUDA(ctx, cudaMemcpy2DAsync(img->d, (size_t)w * 4, gray, (size_t)stride * 4, (size_t)w * 4, h, cudaMemcpyHostToDevice, ctx->stream));
+  if (mg_end(ctx)) return MODSGPU_ECUDA;
+  *out = img;
+  return 0;
+}
+
+extern "C" int modsgpu_image_download(modsgpu_ctx* ctx, const modsgpu_image* img, float* gray) {
+  if (!ctx || !img || !gray) return MODSGPU_EINVAL;
+  MG_CUDA(ctx, cudaMemcpyAsync(gray, img->d, (size_t)img->w * img->h * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" void modsgpu_image_size(const modsgpu_image* img, int* w, int* h) { *w = img->w; *h = img->h; }
+
+extern "C" void modsgpu_image_free(modsgpu_ctx* ctx, modsgpu_image* img) {
+  (void)ctx;
+  if (!img) return;
+  if (img->d) cudaFree(img->d);
+  delete img;
+}
+
+extern "C" void modsgpu_free(void* p) { free(p); }
+
+extern "C" int modsgpu_gaussian_blur(modsgpu_ctx* ctx, const float* in, float* out, int w, int h, float sigma) {
+  if (!ctx || !in || !out || w <= 0 || h <= 0) return MODSGPU_EINVAL;
+  if (mg_begin(ctx)) return MODSGPU_ECUDA;
+  size_t bytes = (size_t)w * h * 4;
+  MG_CUDA(ctx, ctx->io_a.ensure(bytes));
+  MG_CUDA(ctx, ctx->io_b.ensure(bytes));
+  MG_CUDA(ctx, cudaMemcpyAsync(ctx->io_a.p, in, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = launch_blur(ctx, ctx->io_a.as<float>(), ctx->io_b.as<float>(), nullptr, w, h, sigma, 0.f);
+  if (rc) return rc;
+  MG_CUDA(ctx, cudaMemcpyAsync(out, ctx->io_b.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return mg_end(ctx) ? MODSGPU_ECUDA : 0;
+}
+
+extern "C" int modsgpu_hessian_response(modsgpu_ctx* ctx, const float* in, float* out, int w, int h, float norm) {
+  if (!ctx || !in || !out || w <= 0 || h <= 0) return MODSGPU_EINVAL;
+  if (mg_begin(ctx)) return MODSGPU_ECUDA;
+  size_t bytes = (size_t)w * h * 4;
+  MG_CUDA(ctx, ctx->io_a.ensure(bytes));
+  MG_CUDA(ctx, ctx->io_b.ensure(bytes));
+  MG_CUDA(ctx, cudaMemcpyAsync(ctx->io_a.p, in, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  dim3 blk(32, 8), grid(ceil_div(w, 32), ceil_div(h, 8));
+  k_response<<<grid, blk, 0, ctx->stream>>>(ctx->io_a.as<float>(), ctx->io_b.as<float>(), w, h, norm * norm);
+  MG_LAUNCHED(ctx);
+  MG_CUDA(ctx, cudaMemcpyAsync(out, ctx->io_b.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return mg_end(ctx) ? MODSGPU_ECUDA : 0;
+}
+
+static void half_size(int w, int h, int* ow, int* oh) {
+  *ow = (int)std::nearbyint(w * 0.5);
+  *oh = (int)std::nearbyint(h * 0.5);
+}
+
+extern "C" int modsgpu_half_image(modsgpu_ctx* ctx, const float* in, int w, int h, float* out) {
+  if (!ctx || !in || !out || w <= 0 || h <= 0) return MODSGPU_EINVAL;
+  if (mg_begin(ctx)) return MODSGPU_ECUDA;
+  int ow, oh;
+  half_size(w, h, &ow, &oh);
+  MG_CUDA(ctx, ctx->io_a.ensure((size_t)w * h * 4));
+  MG_CUDA(ctx, ctx->io_b.ensure((size_t)ow * oh * 4 + 4));
+  MG_CUDA(ctx, cudaMemcpyAsync(ctx->io_a.p, in, (size_t)w * h * 4, cudaMemcpyHostToDevice, ctx->stream));
+  dim3 blk(32, 8), grid(ceil_div(ow, 32), ceil_div(oh, 8));
+  k_half<<<grid, blk, 0, ctx->stream>>>(ctx->io_a.as<float>(), w, h, ctx->io_b.as<float>(), ow, oh);
+  MG_LAUNCHED(ctx);
+  MG_CUDA(ctx, cudaMemcpyAsync(out, ctx->io_b.p, (size_t)ow * oh * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  return mg_end(ctx) ? MODSGPU_ECUDA : 0;
+}
+
+// Device part of the detector: enqueues the whole pyramid on ctx->stream; the sorted keypoints end
+// up in ctx->det_out and their count in ctx->det_misc[1].  No host synchronisation inside.
+int mg_detect_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_pyr_params* p, int cap) {
+  const int nS = p->numberOfScales;
+  if (nS < 1 || nS + 2 > 8) MG_FAIL(ctx, MODSGPU_EINVAL, "numberOfScales out of range");
+  if (p->border < 2) MG_FAIL(ctx, MODSGPU_EINVAL, "border must be >= 2 (pyramid.cpp:407)");
+  const int nlev = nS + 2;
+  // octave geometry (pyramid.cpp:520-528)
+  std::vector<int> ow, oh;
+  {
+    int W = img->w, H = img->h, minSize = 2 * p->border + 2;
+    while (H > minSize && W > minSize) {
+      ow.push_back(W); oh.push_back(H);
+      int nW, nH;
+      half_size(W, H, &nW, &nH);
+      W = nW; H = nH;
+    }
+  }
+  const int nOct = (int)ow.size();
+  size_t pyr_floats = 0, map_ints = 0;
+  std::vector<size_t> oct_off(nOct), map_off(nOct);
+  for (int o = 0; o < nOct; o++) {
+    oct_off[o] = pyr_floats; map_off[o] = map_ints;
+    size_t px = (size_t)ow[o] * oh[o];
+    pyr_floats += px * 2 * nlev;
+    map_ints += px;
+  }
+  if (map_ints * nS > 0xfffffff0ull) MG_FAIL(ctx, MODSGPU_EINVAL, "image too large");
+  MG_CUDA(ctx, ctx->det_pyr.ensure((pyr_floats + 16) * sizeof(float)));
+  MG_CUDA(ctx, ctx->det_map.ensure((map_ints + 16) * sizeof(int)));
+  MG_CUDA(ctx, ctx->det_cand.ensure((size_t)cap * (sizeof(Cand) + sizeof(unsigned long long))));
+  MG_CUDA(ctx, ctx->det_out.ensure((size_t)cap * sizeof(modsgpu_keypoint)));
+  MG_CUDA(ctx, ctx->det_misc.ensure(64));
+  float* pyr = ctx->det_pyr.as<float>();
+  int* map = ctx->det_map.as<int>();
+  Cand* cands = ctx->det_cand.as<Cand>();
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(cands + cap);
+  int* counters = ctx->det_misc.as<int>();  // [0] candidates, [1] kept
+  MG_CUDA(ctx, cudaMemsetAsync(counters, 0, 64, ctx->stream));
+  if (nOct == 0) return 0;
+  k_fill_i32<<<(unsigned)((map_ints + 255) / 256), 256, 0, ctx->stream>>>(map, (long)map_ints, 0x7fffffff);
+  MG_LAUNCHED(ctx);
+
+  // thresholds, pyramid.h:46-66 (DET_HESSIAN, FIXED_TH)
+  const double edgeThr = (p->edgeEigenValueRatio + 1.0f) * (p->edgeEigenValueRatio + 1.0f) / p->edgeEigenValueRatio;
+  const float posThr = (float)(0.8 * p->threshold), negThr = -posThr;
+  const float finalThr = p->threshold * p->threshold;
+  const float sigmaStep = std::pow(2.0f, 1.0f / (float)nS);
+
+  float pixelDistance = 1.0f;
+  unsigned octave_base = 0;
+  for (int o = 0; o < nOct; o++) {
+    const int w = ow[o], h = oh[o];
+    const size_t px = (size_t)w * h;
+    float* Lv = pyr + oct_off[o];             // nlev blur levels
+    float* Rv = Lv + px * nlev;               // nlev responses
+    float curSigma = p->initialSigma;
+    // first level of the octave + its response (pyramid.cpp:445-447; :514-518 for octave 0)
+    if (o == 0) {
+      float norm = curSigma * curSigma;
+      if (p->initialSigma > 0.5f) {
+        float sigma = std::sqrt(p->initialSigma * p->initialSigma - 0.5f * 0.5f);
+        int rc = launch_blur(ctx, img->d, Lv, Rv, w, h, sigma, norm * norm);
+        if (rc) return rc;
+      } else {
+        MG_CUDA(ctx, cudaMemcpyAsync(Lv, img->d, px * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        dim3 blk(32, 8), grid(ceil_div(w, 32), ceil_div(h, 8));
+        k_response<<<grid, blk, 0, ctx->stream>>>(Lv, Rv, w, h, norm * norm);
+        MG_LAUNCHED(ctx);
+      }
+    } else {
+      float norm = curSigma * curSigma;
+      dim3 blk(32, 8), grid(ceil_div(w, 32), ceil_div(h, 8));
+      k_response<<<grid, blk, 0, ctx->stream>>>(Lv, Rv, w, h, norm * norm);
+      MG_LAUNCHED(ctx);
+    }
+    NmsArgs na;
+    memset(&na, 0, sizeof(na));
+    na.nlev = 0;
+    for (int i = 1; i < nS + 2; i++) {
+      float sigma = curSigma * std::sqrt(sigmaStep * sigmaStep - 1.0f);
+      float s2 = curSigma * sigmaStep;
+      float norm = s2 * s2;
+      int rc = launch_blur(ctx, Lv + px * (i - 1), Lv + px * i, Rv + px * i, w, h, sigma, norm * norm);
+      if (rc) return rc;
+      if (i >= 2) {
+        LevelArgs& L = na.lv[na.nlev++];
+        L.low = Rv + px * (i - 2); L.cur = Rv + px * (i - 1); L.high = Rv + px * i;
+        L.blur = Lv + px * (i - 1);
+        L.curScale = curSigma; L.level = i - 1;
+      }
+      if (i == nS && o + 1 < nOct) {
+        dim3 blk(32, 8), grid(ceil_div(ow[o + 1], 32), ceil_div(oh[o + 1], 8));
+        k_half<<<grid, blk, 0, ctx->stream>>>(Lv + px * i, w, h, pyr + oct_off[o + 1], ow[o + 1], oh[o + 1]);
+        MG_LAUNCHED(ctx);
+      }
+      curSigma *= sigmaStep;
+    }
+    na.w = w; na.h = h; na.border = p->border; na.octave = o;
+    na.pixelDistance = pixelDistance;
+    na.posThr = posThr; na.negThr = negThr; na.finalThr = finalThr; na.edgeThr = edgeThr;
+    na.numberOfScales = nS;
+    na.octave_base = octave_base;
+    na.map_base = (int)map_off[o];
+    int iw = w - 2 * p->border, ih = h - 2 * p->border;
+    if (iw > 0 && ih > 0 && na.nlev > 0) {
+      dim3 blk(32, 8), grid(ceil_div(iw, 32), ceil_div(ih, 8), na.nlev);
+      k_nms_localize<<<grid, blk, 0, ctx->stream>>>(na, map, cands, counters, cap);
+      MG_LAUNCHED(ctx);
+    }
+    octave_base += (unsigned)(px * nS);
+    pixelDistance *= 2.0f;
+  }
+  int nb = ceil_div(cap, 256);
+  k_resolve<<<nb, 256, 0, ctx->stream>>>(cands, counters, cap, map, keys, counters + 1);
+  MG_LAUNCHED(ctx);
+  k_rank_export<<<nb, 256, 0, ctx->stream>>>(cands, counters, cap, keys, ctx->det_out.as<modsgpu_keypoint>());
+  MG_LAUNCHED(ctx);
+  return 0;
+}
+
+extern "C" int modsgpu_detect(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_pyr_params* p,
+                              modsgpu_keypoint** out, int* n) {
+  if (!ctx || !img || !p || !out || !n) return MODSGPU_EINVAL;
+  if (mg_begin(ctx)) return MODSGPU_ECUDA;
+  int cap = 1 << 16;
+  for (;;) {
+    int rc = mg_detect_enqueue(ctx, img, p, cap);
+    if (rc) return rc;
+    MG_CUDA(ctx, ctx->h_stage.ensure(64));
+    int* hc = ctx->h_stage.as<int>();
+    MG_CUDA(ctx, cudaMemcpyAsync(hc, ctx->det_misc.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (hc[0] > cap) { cap = hc[0] + hc[0] / 8; continue; }  // candidate list overflowed: redo with room
+    int kept = hc[1];
+    modsgpu_keypoint* res = (modsgpu_keypoint*)malloc(sizeof(modsgpu_keypoint) * (size_t)std::max(kept, 1));
+    if (kept > 0)
+      MG_CUDA(ctx, cudaMemcpyAsync(res, ctx->det_out.p, sizeof(modsgpu_keypoint) * (size_t)kept, cudaMemcpyDeviceToHost, ctx->stream));
+    if (mg_end(ctx)) { free(res); return MODSGPU_ECUDA; }
+    *out = res; *n = kept;
+    return 0;
+  }
+}

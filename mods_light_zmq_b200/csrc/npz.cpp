@@ -1,0 +1,95 @@
+// npz.cpp -- minimal .npz (zip of .npy) reader for the network weights.
+// Plays the role cnpy::npz_load (cnpy/cnpy.h:71-72) plays in the reference, restricted to what
+// tools/export_weights.py writes: little-endian float32, C order, stored or deflated members.
+#include "npz.h"
+#include <zlib.h>
+#include <cstdio>
+#include <cstring>
+#include <cstdlib>
+
+namespace {
+uint32_t rd32(const unsigned char* p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
+uint16_t rd16(const unsigned char* p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+
+bool parse_npy(const std::vector<unsigned char>& raw, NpzArray& a, std::string& err) {
+  if (raw.size() < 10 || memcmp(raw.data(), "\x93NUMPY", 6) != 0) { err = "not an npy member"; return false; }
+  int major = raw[6];
+  size_t hlen, hoff;
+  if (major == 1) { hlen = rd16(&raw[8]); hoff = 10; }
+  else { hlen = rd32(&raw[8]); hoff = 12; }
+  if (hoff + hlen > raw.size()) { err = "truncated npy header"; return false; }
+  std::string hdr((const char*)&raw[hoff], hlen);
+  if (hdr.find("'<f4'") == std::string::npos) { err = "npy dtype is not <f4"; return false; }
+  if (hdr.find("'fortran_order': False") == std::string::npos) { err = "npy is fortran ordered"; return false; }
+  size_t sp = hdr.find("'shape':");
+  if (sp == std::string::npos) { err = "npy header without shape"; return false; }
+  size_t lp = hdr.find('(', sp), rp = hdr.find(')', sp);
+  if (lp == std::string::npos || rp == std::string::npos) { err = "bad shape"; return false; }
+  a.shape.clear();
+  size_t n = 1;
+  const char* s = hdr.c_str() + lp + 1;
+  const char* e = hdr.c_str() + rp;
+  while (s < e) {
+    while (s < e && (*s == ' ' || *s == ',')) s++;
+    if (s >= e) break;
+    char* q;
+    long v = strtol(s, &q, 10);
+    if (q == s) break;
+    a.shape.push_back((int)v);
+    n *= (size_t)v;
+    s = q;
+  }
+  size_t doff = hoff + hlen;
+  if (doff + n * 4 > raw.size()) { err = "npy payload shorter than its shape"; return false; }
+  a.data.resize(n);
+  memcpy(a.data.data(), &raw[doff], n * 4);
+  return true;
+}
+}  // namespace
+
+bool npz_load(const char* path, std::map<std::string, NpzArray>& out, std::string& err) {
+  FILE* f = fopen(path, "rb");
+  if (!f) { err = std::string("cannot open ") + path; return false; }
+  fseek(f, 0, SEEK_END);
+  long fsz = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  std::vector<unsigned char> buf((size_t)fsz);
+  if (fsz <= 22 || fread(buf.data(), 1, (size_t)fsz, f) != (size_t)fsz) { fclose(f); err = "short read"; return false; }
+  fclose(f);
+  long eocd = -1;
+  for (long i = fsz - 22; i >= 0 && i >= fsz - 22 - 65536; i--)
+    if (rd32(&buf[i]) == 0x06054b50u) { eocd = i; break; }
+  if (eocd < 0) { err = "no zip end-of-central-directory record"; return false; }
+  int count = rd16(&buf[eocd + 10]);
+  size_t cd = rd32(&buf[eocd + 16]);
+  for (int k = 0; k < count; k++) {
+    if (cd + 46 > (size_t)fsz || rd32(&buf[cd]) != 0x02014b50u) { err = "bad central directory"; return false; }
+    int method = rd16(&buf[cd + 10]);
+    size_t csize = rd32(&buf[cd + 20]), usize = rd32(&buf[cd + 24]);
+    int nlen = rd16(&buf[cd + 28]), xlen = rd16(&buf[cd + 30]), clen = rd16(&buf[cd + 32]);
+    size_t lho = rd32(&buf[cd + 42]);
+    std::string name((const char*)&buf[cd + 46], nlen);
+    cd += 46 + nlen + xlen + clen;
+    if (lho + 30 > (size_t)fsz || rd32(&buf[lho]) != 0x04034b50u) { err = "bad local header"; return false; }
+    size_t doff = lho + 30 + rd16(&buf[lho + 26]) + rd16(&buf[lho + 28]);
+    if (doff + csize > (size_t)fsz) { err = "member beyond end of file"; return false; }
+    std::vector<unsigned char> raw;
+    if (method == 0) raw.assign(buf.begin() + doff, buf.begin() + doff + csize);
+    else if (method == 8) {
+      raw.resize(usize);
+      z_stream zs;
+      memset(&zs, 0, sizeof(zs));
+      if (inflateInit2(&zs, -15) != Z_OK) { err = "zlib init"; return false; }
+      zs.next_in = &buf[doff]; zs.avail_in = (uInt)csize;
+      zs.next_out = raw.data(); zs.avail_out = (uInt)usize;
+      int rc = inflate(&zs, Z_FINISH);
+      inflateEnd(&zs);
+      if (rc != Z_STREAM_END) { err = "inflate failed for " + name; return false; }
+    } else { err = "unsupported zip method in " + name; return false; }
+    if (name.size() > 4 && name.substr(name.size() - 4) == ".npy") name = name.substr(0, name.size() - 4);
+    NpzArray a;
+    if (!parse_npy(raw, a, err)) { err += " (" + name + ")"; return false; }
+    out[name] = std::move(a);
+  }
+  return true;
+}

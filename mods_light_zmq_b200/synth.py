@@ -1,0 +1,76 @@
+"""Seeded synthetic inputs for the BASELINE.json configs: a blob image that yields
+~4k Hessian keypoints at 1024x768, and a second view of it under a fixed homography."""
+import numpy as np
+
+N_BLOBS = 3200  # tuned once with the oracle: ~4.2k / ~3.8k Hessian keypoints for the pair, then frozen
+
+
+def blob_image(seed=1234, w=1024, h=768, n_blobs=N_BLOBS):
+    """Sum of anisotropic Gaussian blobs (sigma log-uniform in [1.5,12] px, amplitude +-[20,80]) on a 128
+    background + N(0,2^2) noise, clipped and quantised to u8 (so it survives a PNG round trip)."""
+    rng = np.random.RandomState(seed)
+    img = np.full((h, w), 128.0, np.float64)
+    yy, xx = np.mgrid[0:h, 0:w]
+    for _ in range(n_blobs):
+        cx, cy = rng.uniform(0, w), rng.uniform(0, h)
+        s1 = np.exp(rng.uniform(np.log(1.5), np.log(12.0)))
+        s2 = s1 * rng.uniform(0.5, 1.0)
+        th = rng.uniform(0, np.pi)
+        amp = rng.uniform(20, 80) * (1 if rng.rand() < 0.5 else -1)
+        R = int(4 * s1) + 1
+        x0, x1 = max(0, int(cx) - R), min(w, int(cx) + R + 1)
+        y0, y1 = max(0, int(cy) - R), min(h, int(cy) + R + 1)
+        if x0 >= x1 or y0 >= y1:
+            continue
+        dx = xx[y0:y1, x0:x1] - cx
+        dy = yy[y0:y1, x0:x1] - cy
+        u = np.cos(th) * dx + np.sin(th) * dy
+        v = -np.sin(th) * dx + np.cos(th) * dy
+        img[y0:y1, x0:x1] += amp * np.exp(-0.5 * ((u / s1) ** 2 + (v / s2) ** 2))
+    img += rng.normal(0, 2.0, img.shape)
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def pair_homography(w=1024, h=768):
+    """image A -> image B: rotation 20 deg, scale 0.9 about the centre, perspective 1e-4."""
+    a = np.deg2rad(20.0)
+    c, s = 0.9 * np.cos(a), 0.9 * np.sin(a)
+    T1 = np.array([[1, 0, -w / 2], [0, 1, -h / 2], [0, 0, 1.0]])
+    Rm = np.array([[c, -s, 0], [s, c, 0], [0, 0, 1.0]])
+    P = np.array([[1, 0, 0], [0, 1, 0], [1e-4, 0, 1.0]])
+    T2 = np.array([[1, 0, w / 2], [0, 1, h / 2], [0, 0, 1.0]])
+    return T2 @ P @ Rm @ T1
+
+
+def warp_image(img, H, noise_seed=4321, border=128.0):
+    """B(x) = A(H^-1 x), bilinear, constant border, + independent N(0,2^2) noise, u8."""
+    h, w = img.shape
+    Hi = np.linalg.inv(H)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    d = Hi[2, 0] * xx + Hi[2, 1] * yy + Hi[2, 2]
+    sx = (Hi[0, 0] * xx + Hi[0, 1] * yy + Hi[0, 2]) / d
+    sy = (Hi[1, 0] * xx + Hi[1, 1] * yy + Hi[1, 2]) / d
+    x0 = np.floor(sx).astype(np.int64)
+    y0 = np.floor(sy).astype(np.int64)
+    fx, fy = sx - x0, sy - y0
+    inside = (x0 >= 0) & (y0 >= 0) & (x0 < w - 1) & (y0 < h - 1)
+    x0c, y0c = np.clip(x0, 0, w - 2), np.clip(y0, 0, h - 2)
+    a = img.astype(np.float64)
+    v = (a[y0c, x0c] * (1 - fx) * (1 - fy) + a[y0c, x0c + 1] * fx * (1 - fy) +
+         a[y0c + 1, x0c] * (1 - fx) * fy + a[y0c + 1, x0c + 1] * fx * fy)
+    v = np.where(inside, v, border)
+    rng = np.random.RandomState(noise_seed)
+    v = v + rng.normal(0, 2.0, v.shape)
+    return np.clip(np.rint(v), 0, 255).astype(np.uint8)
+
+
+def gray_to_bgr(gray_u8):
+    """cv::imread of a gray PNG gives three equal channels."""
+    return np.repeat(gray_u8[:, :, None], 3, axis=2)
+
+
+def image_pair(seed=1234, w=1024, h=768):
+    a = blob_image(seed, w, h)
+    H = pair_homography(w, h)
+    b = warp_image(a, H, noise_seed=seed + 3087)
+    return a, b, H

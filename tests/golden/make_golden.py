@@ -1,0 +1,153 @@
+#!/usr/bin/env python
+"""Generates the committed golden fixtures in tests/golden/ (run in the build container, where
+/root/reference and the cv2 wheel exist; the GPU box only reads the .npz / .json results).
+
+  cv2_pins.npz      cv2.GaussianBlur / cv2.resize outputs (the OpenCV calls whose arithmetic lives outside
+                    the reference tree: helpers.cpp:717-731, pyramid.cpp:476) on small seeded images
+  cnn_golden.npz    48 u8 patches + the outputs of the ORIGINAL AffNet/OriNet/HardNet++ checkpoints run
+                    through the daemons' own nn.Sequential definitions (unfolded BatchNorm, torch CPU fp32)
+  graf_counts.json  keypoint / region / descriptor counts of the oracle pipeline on the reference's
+                    graf1/graf6 images, next to the README transcript values (README.md:47-61)
+  ransac_ref.npz    a seeded correspondence set + the result of the reference's own exp_ransacHcustom
+                    (oracle/_ref/libdegensac_ref.so, time() pinned)
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+
+
+def cv2_pins():
+    import cv2
+    rng = np.random.RandomState(7)
+    out = {}
+    sizes = [(64, 48), (50, 37), (25, 19), (18, 18), (33, 21)]
+    sigmas = [0.75, 0.84375, 1.2262735, 1.5199, 1.9465878, 2.4525, 3.1]
+    for i, (w, h) in enumerate(sizes):
+        img = (rng.rand(h, w) * 255).astype(np.float32)
+        out["img%d" % i] = img
+        for j, s in enumerate(sigmas):
+            s = float(np.float32(s))   # the reference passes float sigmas (helpers.cpp:717)
+            ks = int(2.0 * 3.0 * s + 1.0)
+            ks += 1 - ks % 2
+            out["blur%d_%d" % (i, j)] = cv2.GaussianBlur(img, (ks, ks), s, borderType=cv2.BORDER_REPLICATE)
+        out["half%d" % i] = cv2.resize(img, (0, 0), fx=0.5, fy=0.5, interpolation=cv2.INTER_LINEAR)
+    out["sigmas"] = np.array(sigmas, np.float32)
+    np.savez_compressed(os.path.join(HERE, "cv2_pins.npz"), **out)
+    print("cv2_pins.npz", len(out))
+
+
+def _ref_models():
+    import torch
+    import torch.nn as nn
+
+    def trunk(c):
+        return [nn.Conv2d(1, c, 3, padding=1, bias=False), nn.BatchNorm2d(c, affine=False), nn.ReLU(),
+                nn.Conv2d(c, c, 3, padding=1, bias=False), nn.BatchNorm2d(c, affine=False), nn.ReLU(),
+                nn.Conv2d(c, 2 * c, 3, stride=2, padding=1, bias=False), nn.BatchNorm2d(2 * c, affine=False), nn.ReLU(),
+                nn.Conv2d(2 * c, 2 * c, 3, padding=1, bias=False), nn.BatchNorm2d(2 * c, affine=False), nn.ReLU(),
+                nn.Conv2d(2 * c, 4 * c, 3, stride=2, padding=1, bias=False), nn.BatchNorm2d(4 * c, affine=False), nn.ReLU(),
+                nn.Conv2d(4 * c, 4 * c, 3, padding=1, bias=False), nn.BatchNorm2d(4 * c, affine=False), nn.ReLU()]
+
+    class Net(nn.Module):
+        def __init__(self, layers):
+            super().__init__()
+            self.features = nn.Sequential(*layers)
+
+    hard = Net(trunk(32) + [nn.Dropout(0.3), nn.Conv2d(128, 128, 8, bias=False), nn.BatchNorm2d(128, affine=False)])
+    aff = Net(trunk(16) + [nn.Dropout(0.25), nn.Conv2d(64, 3, 8, bias=True), nn.Tanh(), nn.AdaptiveAvgPool2d(1)])
+    ori = Net(trunk(16) + [nn.Dropout(0.25), nn.Conv2d(64, 2, 8, padding=1, bias=True), nn.Tanh(), nn.AdaptiveAvgPool2d(1)])
+    for m, f in ((hard, "HardNet++.pth"), (aff, "AffNet.pth"), (ori, "OriNet.pth")):
+        ck = torch.load(os.path.join(REF, "build", f), map_location="cpu", weights_only=False)
+        m.load_state_dict(ck["state_dict"])
+        m.eval()
+    return hard, aff, ori
+
+
+def cnn_golden():
+    import torch
+    from mods_light_zmq_b200 import synth
+    from oracle import pyoracle as O
+    a = synth.blob_image(seed=99, w=320, h=240, n_blobs=300)
+    g = O.gray_from_bgr(synth.gray_to_bgr(a))
+    k = O.detect_hessian(g)
+    regs = O.regions_from_keypoints(k[:46])
+    patches = O.quantize_u8(O.extract_patches(g, regs))
+    extra = np.stack([np.full((32, 32), 77, np.uint8),                         # constant patch: std = 0
+                      (np.arange(1024).reshape(32, 32) % 256).astype(np.uint8)])
+    patches = np.concatenate([patches, extra])
+    hard, aff, ori = _ref_models()
+    x = torch.from_numpy(patches.astype(np.float32)).unsqueeze(1)
+
+    def norm(x):
+        flat = x.view(x.size(0), -1)
+        return (x - flat.mean(dim=1).view(-1, 1, 1, 1)) / (flat.std(dim=1) + 1e-7).view(-1, 1, 1, 1)
+
+    with torch.no_grad():
+        f = hard.features(norm(x)).view(len(x), -1)
+        d = f / torch.sqrt(torch.sum(f * f, dim=1) + 1e-10).unsqueeze(-1)
+        desc_raw = d.numpy()
+        desc = np.clip(210 * (desc_raw.astype(np.float64) + 0.45), 0, 255).astype(np.uint8).astype(np.float32)
+        af = aff.features(norm(x)).view(-1, 3).clone()
+        af[:, 0] += 1
+        af[:, 2] += 1
+        orr = ori.features(norm(x)).view(-1, 2)
+    np.savez_compressed(os.path.join(HERE, "cnn_golden.npz"), patches=patches, hardnet_raw=desc_raw, hardnet=desc,
+                        affnet=af.numpy(), orinet=orr.numpy())
+    print("cnn_golden.npz", patches.shape)
+
+
+def graf_counts():
+    import cv2
+    from oracle import pyoracle as O
+    from oracle import cnn_oracle as CN
+    res = {"readme": {"regions": [3731, 4527], "descriptors": [3358, 4118]}, "oracle": {}}
+    for name in ("graf1", "graf6"):
+        bgr = cv2.imread(os.path.join(REF, "build", "imgs", name + ".png"), cv2.IMREAD_COLOR)
+        g = O.gray_from_bgr(bgr)
+        h, w = g.shape
+        k = O.detect_hessian(g)
+        regs = O.regions_from_keypoints(k)
+        aff = CN.affnet(O.quantize_u8(O.extract_patches(g, regs)))
+        r2, _ = O.affnet_postprocess(regs, aff, w, h)
+        ori = CN.orinet(O.quantize_u8(O.extract_patches(g, r2)))
+        r3 = O.orinet_postprocess(r2, ori)
+        r4, _ = O.reproject_filter(r3, w, h)
+        res["oracle"][name] = {"keypoints": int(len(k)), "regions": int(len(r2)), "descriptors": int(len(r4))}
+        print(name, res["oracle"][name])
+    json.dump(res, open(os.path.join(HERE, "graf_counts.json"), "w"), indent=1)
+
+
+def ransac_ref():
+    from oracle import pyoracle as O
+    rng = np.random.RandomState(5)
+    T, n_in = 260, 150
+    Ht = np.array([[0.9, -0.3, 40.0], [0.25, 1.05, -20.0], [2e-4, 1e-5, 1.0]])
+    x1 = np.c_[rng.uniform(20, 1000, T), rng.uniform(20, 740, T), np.ones(T)]
+    p = x1 @ Ht.T
+    x2 = p / p[:, 2:3]
+    x2[:, :2] += rng.normal(0, 0.7, (T, 2))
+    x2[n_in:, :2] = np.c_[rng.uniform(0, 1024, T - n_in), rng.uniform(0, 768, T - n_in)]
+    u = np.ascontiguousarray(np.c_[x1, x2])
+    r = O.ref_ransac_H(u, th=16.0, seed_time=12345)
+    np.savez_compressed(os.path.join(HERE, "ransac_ref.npz"), u=u, H=r["H"], inl=r["inl"], I=r["I"], J=r["J"],
+                        samples=r["samples"], lo_count=r["lo_count"], Htrue=Ht)
+    print("ransac_ref.npz I=%d J=%.3f samples=%d lo=%d" % (r["I"], r["J"], r["samples"], r["lo_count"]))
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["cv2", "cnn", "graf", "ransac"]
+    if "cv2" in which:
+        cv2_pins()
+    if "cnn" in which:
+        cnn_golden()
+    if "graf" in which:
+        graf_counts()
+    if "ransac" in which:
+        ransac_ref()

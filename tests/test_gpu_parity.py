@@ -1,0 +1,276 @@
+"""GPU parity tests (-m gpu): every call goes through the C ABI of libmodsgpu.so and is compared with the
+CPU oracle on the same seeded inputs.  Integer / index / byte outputs must be bit-exact; the network
+outputs carry the tolerances stated at the test (fp16 operands, fp32 accumulation)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden")
+
+
+def _gray(oracle, u8):
+    from mods_light_zmq_b200 import synth
+    return oracle.gray_from_bgr(synth.gray_to_bgr(u8))
+
+
+def _assert_kp_equal(a, b):
+    assert len(a) == len(b), (len(a), len(b))
+    for f in ("octave", "level", "r0", "c0", "r", "c", "type"):
+        assert np.array_equal(a[f], b[f]), f
+    for f in ("x", "y", "s", "response"):
+        assert np.array_equal(a[f], b[f]), (f, float(np.abs(a[f] - b[f]).max()))
+
+
+# ------------------------------------------------------------------------------------------ tcgen05 plumbing
+def test_umma_descriptor_probe(mg):
+    """One 128x32x64 GEMM through the K-major / no-swizzle descriptors the conv and distance kernels use."""
+    rng = np.random.RandomState(3)
+    A = rng.randint(-8, 9, (128, 64)).astype(np.float32)
+    B = rng.randint(-8, 9, (32, 64)).astype(np.float32)
+    D = mg.debug_umma_probe(A, B, 0)
+    assert np.array_equal(D, A @ B.T)
+
+
+# ------------------------------------------------------------------------------------------ pyramid primitives
+@pytest.mark.parametrize("shape", [(48, 64), (37, 50), (96, 128), (101, 203)])
+def test_blur_hessian_half_bit_exact(mg, oracle, shape):
+    rng = np.random.RandomState(shape[0])
+    img = (rng.rand(*shape) * 255).astype(np.float32)
+    for s in (0.75, 0.84375, 1.2262735, 1.5199, 1.9465878, 2.4525, 3.1):
+        s = float(np.float32(s))
+        assert np.array_equal(mg.gaussian_blur(img, s), oracle.gaussian_blur(img, s)), s
+    assert np.array_equal(mg.hessian_response(img, 2.56), oracle.hessian_response(img, 2.56))
+    assert np.array_equal(mg.half_image(img), oracle.half_image(img))
+
+
+def test_blur_matches_cv2_golden(mg):
+    z = np.load(os.path.join(GOLD, "cv2_pins.npz"))
+    for i in range(5):
+        for j, s in enumerate(z["sigmas"]):
+            assert np.array_equal(mg.gaussian_blur(z["img%d" % i], float(s)), z["blur%d_%d" % (i, j)]), (i, j)
+
+
+def test_gray_conversion(mg, oracle):
+    rng = np.random.RandomState(0)
+    bgr = rng.randint(0, 256, (33, 47, 3)).astype(np.uint8)
+    img = mg.image_from_bgr8(bgr)
+    assert np.array_equal(mg.image_download(img), oracle.gray_from_bgr(bgr))
+
+
+# ------------------------------------------------------------------------------------------ detector (config 2)
+def test_detect_full_size_bit_exact(mg, oracle, synth_pair):
+    """BASELINE config 2: 1024x768 synthetic, HessianAffine detect-only, keypoint list bit-exact and in order."""
+    a, b, _ = synth_pair
+    for u8 in (a, b):
+        g = _gray(oracle, u8)
+        ref = oracle.detect_hessian(g)
+        got = mg.detect(mg.image_from_gray32f(g))
+        assert 3500 < len(ref) < 4600
+        _assert_kp_equal(got, ref)
+
+
+@pytest.mark.parametrize("wh", [(800, 640), (333, 251), (100, 50), (64, 48), (14, 40), (12, 12)])
+def test_detect_ragged_sizes(mg, oracle, wh):
+    """widths that are not multiples of 4/8 exercise the scalar-tail arithmetic of the blur; 800x640 is graf's
+    size; 12x12 is below the smallest octave (no keypoints)."""
+    from mods_light_zmq_b200 import synth
+    w, h = wh
+    u8 = synth.blob_image(seed=w * 7 + h, w=w, h=h, n_blobs=max(4, w * h // 250))
+    g = _gray(oracle, u8)
+    ref = oracle.detect_hessian(g)
+    got = mg.detect(mg.image_from_gray32f(g))
+    _assert_kp_equal(got, ref)
+    if w <= 12:
+        assert len(got) == 0
+
+
+def test_detect_idempotent_and_flat(mg, oracle):
+    g = np.full((120, 160), 77.0, np.float32)
+    assert len(mg.detect(mg.image_from_gray32f(g))) == 0
+    from mods_light_zmq_b200 import synth
+    u8 = synth.blob_image(seed=5, w=256, h=192, n_blobs=200)
+    img = mg.image_from_gray32f(_gray(oracle, u8))
+    k1, k2 = mg.detect(img), mg.detect(img)
+    assert k1.tobytes() == k2.tobytes()
+    assert np.all(np.diff(np.abs(k1["response"])) <= 0)
+
+
+# ------------------------------------------------------------------------------------------ sampler
+def _random_affine_regions(oracle, kps, rng):
+    regs = oracle.regions_from_keypoints(kps)
+    n = len(regs)
+    th = rng.uniform(0, 2 * np.pi, n)
+    t = rng.uniform(1.0, 2.0, n)
+    a11, a22 = np.sqrt(t), 1 / np.sqrt(t)
+    c, s = np.cos(th), np.sin(th)
+    regs["a11"], regs["a12"] = a11 * c, -a22 * s
+    regs["a21"], regs["a22"] = a11 * s, a22 * c
+    return regs
+
+
+def test_extract_patches_bit_exact(mg, oracle, synth_pair):
+    a, _, _ = synth_pair
+    g = _gray(oracle, a)
+    kps = oracle.detect_hessian(g)
+    # all scales incl. the largest windows (R up to several hundred px) and the image borders
+    sel = np.r_[np.argsort(-kps["s"])[:40], np.arange(0, len(kps), 9)]
+    img = mg.image_from_gray32f(g)
+    for regs in (oracle.regions_from_keypoints(kps[sel]), _random_affine_regions(oracle, kps[sel], np.random.RandomState(1))):
+        ref = oracle.quantize_u8(oracle.extract_patches(g, regs))
+        got = mg.extract_patches(img, regs)
+        bad = np.argwhere((got != ref).reshape(len(regs), -1).any(axis=1)).ravel()
+        assert len(bad) == 0, (bad[:10], regs["s"][bad[:10]])
+
+
+def test_extract_patches_edge_cases(mg, oracle):
+    from mods_light_zmq_b200 import synth
+    u8 = synth.blob_image(seed=11, w=200, h=150, n_blobs=100)
+    g = _gray(oracle, u8)
+    img = mg.image_from_gray32f(g)
+    assert mg.extract_patches(img, np.zeros(0, oracle.REGION_DTYPE)).shape == (0, 32, 32)
+    regs = np.zeros(6, oracle.REGION_DTYPE)
+    regs["a11"] = regs["a22"] = 1.0
+    regs["x"] = [1.5, 199.0, 100.2, 50.0, -5.0, 100.0]
+    regs["y"] = [1.5, 149.0, 75.7, 140.0, 20.0, 75.0]
+    regs["s"] = [3.0, 8.0, 0.9, 40.0, 5.0, 1.45]      # 0.9 -> direct (unblurred) branch, 40 -> R = 418
+    ref = oracle.quantize_u8(oracle.extract_patches(g, regs))
+    assert np.array_equal(mg.extract_patches(img, regs), ref)
+    ref41 = oracle.quantize_u8(oracle.extract_patches(g, regs, patchSize=41))
+    assert np.array_equal(mg.extract_patches(img, regs, patchSize=41), ref41)
+
+
+# ------------------------------------------------------------------------------------------ networks
+def _check_nets(mg, patches, ref_aff, ref_ori, ref_hard):
+    import mods_light_zmq_b200 as M
+    aff = mg.net_forward_u8(M.AFFNET, patches)
+    ori = mg.net_forward_u8(M.ORINET, patches)
+    hard = mg.net_forward_u8(M.HARDNET, patches)
+    # fp16 operands / fp32 accumulation vs fp32 torch: AffNet / OriNet outputs (tanh range) within 5e-3 abs
+    assert np.abs(aff - ref_aff).max() < 5e-3, float(np.abs(aff - ref_aff).max())
+    assert np.abs(ori - ref_ori).max() < 5e-3, float(np.abs(ori - ref_ori).max())
+    # HardNet++ bytes: integers in [0,255], at most 1 LSB from the reference, >= 97% identical
+    assert hard.min() >= 0 and hard.max() <= 255 and np.array_equal(hard, np.rint(hard))
+    d = np.abs(hard - ref_hard)
+    assert d.max() <= 1, float(d.max())
+    assert (d == 0).mean() > 0.97, float((d == 0).mean())
+
+
+def test_nets_match_original_checkpoints(mg):
+    z = np.load(os.path.join(GOLD, "cnn_golden.npz"))
+    _check_nets(mg, z["patches"], z["affnet"], z["orinet"], z["hardnet"])
+
+
+def test_nets_match_oracle_many_patches(mg, oracle, synth_pair):
+    """1300 patches: crosses the 512-patch chunk boundary and a partial last chunk."""
+    from oracle import cnn_oracle as CN
+    a, _, _ = synth_pair
+    g = _gray(oracle, a)
+    kps = oracle.detect_hessian(g)[:1300]
+    patches = oracle.quantize_u8(oracle.extract_patches(g, oracle.regions_from_keypoints(kps)))
+    _check_nets(mg, patches, CN.affnet(patches), CN.orinet(patches), CN.hardnet(patches))
+    import mods_light_zmq_b200 as M
+    assert mg.net_forward_u8(M.HARDNET, patches[:0]).shape == (0, 128)
+    one = mg.net_forward_u8(M.HARDNET, patches[:1])
+    assert np.array_equal(one, mg.net_forward_u8(M.HARDNET, patches[:700])[:1])
+
+
+def test_describe_equals_sampler_plus_net(mg, oracle, synth_pair):
+    import mods_light_zmq_b200 as M
+    a, _, _ = synth_pair
+    g = _gray(oracle, a)
+    img = mg.image_from_gray32f(g)
+    regs = oracle.regions_from_keypoints(oracle.detect_hessian(g)[:300])
+    p = mg.extract_patches(img, regs)
+    for net in (M.AFFNET, M.ORINET, M.HARDNET):
+        assert np.array_equal(mg.describe(net, img, regs), mg.net_forward_u8(net, p))
+
+
+# ------------------------------------------------------------------------------------------ matcher
+def _rand_desc(rng, n, centers=None):
+    d = rng.randint(0, 256, (n, 128))
+    if centers is not None:
+        idx = rng.randint(0, len(centers), n)
+        d = np.clip(centers[idx] + rng.randint(-6, 7, (n, 128)), 0, 255)
+    return d.astype(np.float32)
+
+
+@pytest.mark.parametrize("nq,nt", [(700, 900), (129, 50), (5, 49), (1, 1), (300, 3000)])
+def test_match_fginn_bit_exact(mg, oracle, nq, nt):
+    rng = np.random.RandomState(nq + nt)
+    centers = rng.randint(0, 256, (max(nt // 6, 1), 128))
+    t = _rand_desc(rng, nt, centers)
+    q = _rand_desc(rng, nq, centers)
+    t[nt // 2:nt // 2 + min(10, nt // 4)] = t[:min(10, nt // 4)]            # exact duplicates -> distance ties
+    txy = rng.uniform(0, 1024, (nt, 2))
+    txy[1::3] = txy[0::3][:len(txy[1::3])] + rng.uniform(-3, 3, (len(txy[1::3]), 2))   # geometric consistency cases
+    ridx, rdist = oracle.knn_linear(q, t, 50)
+    ref = oracle.match_fginn(q, np.zeros((nq, 2)), t, txy)
+    got, ki, kd = mg.match_fginn(q, t, txy, want_knn=True)
+    assert np.array_equal(ki, ridx)
+    assert np.array_equal(kd, rdist)
+    assert got.tobytes() == ref.tobytes()
+
+
+def test_match_empty_and_bad_input(mg):
+    import mods_light_zmq_b200 as M
+    t = np.zeros((10, 128), np.float32)
+    assert len(mg.match_fginn(t[:0], t, np.zeros((10, 2)))) == 0
+    assert len(mg.match_fginn(t, t[:0], np.zeros((0, 2)))) == 0
+    bad = t.copy()
+    bad[0, 0] = 0.5
+    with pytest.raises(M.ModsGpuError):
+        mg.match_fginn(bad, t, np.zeros((10, 2)))
+
+
+def test_duplicate_filter_bit_exact(mg, oracle):
+    rng = np.random.RandomState(2)
+    for T in (0, 1, 7, 300, 1500):
+        xy1 = rng.uniform(0, 60, (T, 2))
+        xy2 = xy1 + rng.uniform(-2, 2, (T, 2))
+        ratio = np.round(rng.uniform(0.3, 0.8, T), 2)                      # ties in the sort key
+        assert np.array_equal(mg.duplicate_filter(xy1, xy2, ratio, 2.0), oracle.duplicate_filter(xy1, xy2, ratio, 2.0))
+    assert np.array_equal(mg.duplicate_filter(xy1, xy2, ratio, 0.0), np.arange(T))
+
+
+# ------------------------------------------------------------------------------------------ chained pipeline (config 3, per stage)
+def test_deep_pipeline_stagewise(mg, oracle, synth_pair):
+    """detect -> AffNet -> filters -> OriNet -> filters -> HardNet -> FGINN -> dedup on the 1024x768 pair.
+    Each GPU stage is fed the ORACLE's output of the previous stage, so integer stages stay comparable."""
+    import mods_light_zmq_b200 as M
+    from oracle import cnn_oracle as CN
+    a, b, H = synth_pair
+    descs, xys = [], []
+    for u8 in (a, b):
+        g = _gray(oracle, u8)
+        h, w = g.shape
+        img = mg.image_from_gray32f(g)
+        kps = oracle.detect_hessian(g)[::4]
+        regs = oracle.regions_from_keypoints(kps)
+        aff_ref = CN.affnet(oracle.quantize_u8(oracle.extract_patches(g, regs)))
+        aff = mg.describe(M.AFFNET, img, regs)
+        assert np.abs(aff - aff_ref).max() < 5e-3
+        r2, _ = oracle.affnet_postprocess(regs, aff_ref, w, h)
+        ori_ref = CN.orinet(oracle.quantize_u8(oracle.extract_patches(g, r2)))
+        ori = mg.describe(M.ORINET, img, r2)
+        assert np.abs(ori - ori_ref).max() < 5e-3
+        r3 = oracle.orinet_postprocess(r2, ori_ref)
+        r4, _ = oracle.reproject_filter(r3, w, h)
+        d_ref = CN.hardnet(oracle.quantize_u8(oracle.extract_patches(g, r4)))
+        d = mg.describe(M.HARDNET, img, r4)
+        assert np.abs(d - d_ref).max() <= 1 and (d == d_ref).mean() > 0.97
+        descs.append(d_ref)
+        xys.append(np.c_[r4["x"], r4["y"]])
+    ref = oracle.match_fginn(descs[0], xys[0], descs[1], xys[1])
+    got = mg.match_fginn(descs[0], descs[1], xys[1])
+    assert got.tobytes() == ref.tobytes()
+    assert len(ref) > 30
+    x1, x2 = xys[0][ref["qi"]], xys[1][ref["ti"]]
+    keep_ref = oracle.duplicate_filter(x1, x2, ref["ratio"])
+    assert np.array_equal(mg.duplicate_filter(x1, x2, ref["ratio"]), keep_ref)
+    # geometry sanity: most tentatives agree with the generating homography
+    p = np.c_[x1, np.ones(len(x1))] @ H.T
+    err = np.linalg.norm(p[:, :2] / p[:, 2:3] - x2, axis=1)
+    assert (err < 3).mean() > 0.5

@@ -8,7 +8,7 @@ NVFLAGS = $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-ffp-contract=off -I
 # detect.cu / sampler.cu are the bit-exact integer/float paths: no FMA contraction
 EXACT = --fmad=false
 
-OBJS = $(OBJ)/api.o $(OBJ)/detect.o $(OBJ)/sampler.o $(OBJ)/cnn.o $(OBJ)/match.o $(OBJ)/ransac.o $(OBJ)/npz.o
+OBJS = $(OBJ)/api.o $(OBJ)/detect.o $(OBJ)/sampler.o $(OBJ)/cnn.o $(OBJ)/match.o $(OBJ)/ransac.o $(OBJ)/npz.o $(OBJ)/mods_host.o
 
 all: $(PKG)/libmodsgpu.so oracle
 
@@ -24,6 +24,9 @@ $(OBJ)/ransac.o: $(SRC)/ransac.cu $(SRC)/common.cuh include/modsgpu.h
 $(OBJ)/%.o: $(SRC)/%.cu $(SRC)/common.cuh include/modsgpu.h
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
+$(OBJ)/mods_host.o: $(SRC)/host/mods_host.cpp $(SRC)/host/mods_host.h include/modsgpu.h
+	@mkdir -p $(OBJ)
+	g++ -O2 -std=c++17 -fPIC -ffp-contract=off -c $< -o $@
 $(OBJ)/npz.o: $(SRC)/npz.cpp
 	@mkdir -p $(OBJ)
 	g++ -O2 -std=c++17 -fPIC -c $< -o $@

@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- image-pairs/sec of the MODS hot path (detect -> AffNet -> OriNet -> HardNet++ -> FGINN match ->
+duplicate filter -> LO-RANSAC(H)) on synthetic 1024x768 pairs (~4k keypoints per image).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one image pair through modsgpu_pair_pipeline*.  Pairs are independent, so ranks shard pairs
+(weak scaling: every rank runs K steps on its own pairs); the only collective is one NCCL gather of the
+final correspondences / homographies of all steps, inside the timed region.
+
+value   whole-job pairs/s with the images already resident in HBM (modsgpu_pair_pipeline_images)
+e2e     the same through the reference-facing call with HOST (pinned) BGR images: H2D of both images and D2H
+        of the verified correspondences inside the timed region (modsgpu_pair_pipeline)
+roofline  dominant kernel by accumulated CUDA-event time over the same K steps (per-launch events recorded
+        by the library on its own stream), algorithmic work per launch as defined in DESIGN.md
+cpu_baseline / --impl reference  the CPU path (oracle port of the reference C++ stages, the daemons' torch
+        models on the CPU, the reference's own degensac) on the host cores, on a bounded sample
+The L2 is flushed (256 MB memset) before every step.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "image-pairs/sec (1024x768, ~4k kp)"
+WORKLOAD = "config3: 1024x768 synthetic pair, Hessian-AffNet-OriNet-HardNet++ + linear FGINN + LO-RANSAC(H)"
+W_IMG, H_IMG = 1024, 768
+N_DISTINCT_PAIRS = 4
+CAPACITY = 2048
+
+
+def make_pairs(n, rank):
+    from mods_light_zmq_b200 import synth
+    pairs = []
+    for i in range(n):
+        a, b, H = synth.image_pair(seed=1234 + 17 * i + 1000 * rank, w=W_IMG, h=H_IMG)
+        pairs.append((synth.gray_to_bgr(a), synth.gray_to_bgr(b), H))
+    return pairs
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU path
+def cpu_pair(pair, sample_stride, threads):
+    """The reference's CPU path on one pair.  Detection runs on both full images; the per-keypoint stages
+    (sampler + nets) on every `sample_stride`-th keypoint; matching on the sampled descriptors; LO-RANSAC by
+    the reference's degensac.  Returns per-stage seconds and the extrapolated seconds per full pair."""
+    import torch
+    from oracle import pyoracle as O
+    from oracle import cnn_oracle as CN
+    torch.set_num_threads(threads)
+    t = {"detect": 0.0, "perkp": 0.0, "match": 0.0, "ransac": 0.0}
+    out = [None, None]
+
+    def one(i):
+        bgr = pair[i]
+        t0 = time.perf_counter()
+        g = O.gray_from_bgr(bgr)
+        h, w = g.shape
+        kp = O.detect_hessian(g)
+        t1 = time.perf_counter()
+        regs = O.regions_from_keypoints(kp[::sample_stride])
+        aff = CN.affnet(O.quantize_u8(O.extract_patches(g, regs)))
+        r2, _ = O.affnet_postprocess(regs, aff, w, h)
+        ori = CN.orinet(O.quantize_u8(O.extract_patches(g, r2)))
+        r3 = O.orinet_postprocess(r2, ori)
+        r4, _ = O.reproject_filter(r3, w, h)
+        d = CN.hardnet(O.quantize_u8(O.extract_patches(g, r4)))
+        t2 = time.perf_counter()
+        out[i] = (d, np.c_[r4["x"], r4["y"]], t1 - t0, t2 - t1, len(kp))
+
+    # mods.cpp:234-251: the two images of a pair are processed by two concurrent OpenMP tasks
+    ths = [threading.Thread(target=one, args=(i,)) for i in (0, 1)]
+    t0 = time.perf_counter()
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    wall = time.perf_counter() - t0
+    tot = sum(o[2] + o[3] for o in out)
+    t["detect"] = wall * sum(o[2] for o in out) / tot
+    t["perkp"] = wall * sum(o[3] for o in out) / tot
+    t0 = time.perf_counter()
+    m = O.match_fginn(out[0][0], out[0][1], out[1][0], out[1][1])
+    t["match"] = time.perf_counter() - t0
+    # RANSAC on a tentative set of the size the full pair yields (~250), built from the known homography
+    rng = np.random.RandomState(1)
+    T, n_in = 260, 170
+    H = pair[2]
+    x1 = np.c_[rng.uniform(20, 1000, T), rng.uniform(20, 740, T), np.ones(T)]
+    p = x1 @ H.T
+    x2 = p / p[:, 2:3]
+    x2[:, :2] += rng.normal(0, 0.7, (T, 2))
+    x2[n_in:, :2] = np.c_[rng.uniform(0, 1024, T - n_in), rng.uniform(0, 768, T - n_in)]
+    t0 = time.perf_counter()
+    if O.ref_available():
+        O.ref_ransac_H(np.ascontiguousarray(np.c_[x1, x2]), th=16.0)
+    t["ransac"] = time.perf_counter() - t0
+    s = sample_stride
+    full = t["detect"] + s * t["perkp"] + s * s * t["match"] + t["ransac"]
+    return t, full, len(m)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    pairs = make_pairs(2, 0)
+    stride = 8
+    for _ in range(min(args.warmup, 1)):
+        cpu_pair(pairs[0], stride, threads)
+    secs, parts = [], None
+    t_begin = time.perf_counter()
+    for k in range(args.steps):
+        parts, full, _ = cpu_pair(pairs[k % len(pairs)], stride, threads)
+        secs.append(full)
+    wall = time.perf_counter() - t_begin
+    per_pair = float(np.mean(secs))
+    value = 1.0 / per_pair
+    sample = ("per step: full Hessian detection of both 1024x768 images + sampler/AffNet/OriNet/HardNet++ on every %d-th "
+              "keypoint + linear FGINN on the sampled descriptors + reference degensac on 260 tentatives; "
+              "pair time = detect + %d*perkp + %d*match + ransac (measured %.2f s of CPU work per step)" %
+              (stride, stride, stride * stride, wall / max(args.steps, 1)))
+    line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": per_pair * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": WORKLOAD, "l2": "n/a (CPU)"},
+            "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port",
+                             "sample": sample, "stage_seconds_sample": parts},
+            "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU path
+ALG = {  # kernels whose algorithmic work the library reports in bytes (kind 0) or flops (kind 1)
+    0: ("hbm", "GB/s", 1e9), 1: ("tensor", "TFLOP/s", 1e12)}
+
+
+def run_gpu(args, rank, world, local_rank):
+    import torch
+    import mods_light_zmq_b200 as M
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    mg = M.ModsGpu(local_rank, load_nets=True)
+    lib, ctx = mg.lib, mg.ctx
+    pairs = make_pairs(N_DISTINCT_PAIRS, rank)
+    # pinned host images (e2e arm) and device-resident images (value arm)
+    host = []
+    for a, b, _ in pairs:
+        pa = torch.empty(a.shape, dtype=torch.uint8).pin_memory()
+        pb = torch.empty(b.shape, dtype=torch.uint8).pin_memory()
+        pa.numpy()[:] = a
+        pb.numpy()[:] = b
+        host.append((pa, pb))
+    dev = [(mg.image_from_bgr8(pa.numpy()), mg.image_from_bgr8(pb.numpy())) for pa, pb in host]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    results = np.zeros((max(args.steps, 1), 16 + 4 * CAPACITY), np.float64)
+
+    def step_value(k, store):
+        lib.modsgpu_flush_l2(ctx)
+        i1, i2 = dev[k % len(dev)]
+        r = mg.pair_pipeline_images(i1, i2, seed=1000 + k, capacity=CAPACITY)
+        if store:
+            results[k, :9] = r["H"].ravel()
+            results[k, 9] = r["inliers"]
+            results[k, 16:16 + 4 * len(r["inlier_xy"])] = r["inlier_xy"].ravel()
+        return r
+
+    def step_e2e(k):
+        lib.modsgpu_flush_l2(ctx)
+        pa, pb = host[k % len(host)]
+        return mg.pair_pipeline(pa.numpy(), pb.numpy(), seed=1000 + k, capacity=CAPACITY)
+
+    def gather_results():
+        if dist is None:
+            return
+        t = torch.from_numpy(results).cuda()
+        lst = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
+        dist.gather(t, lst, dst=0)
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, with_gather):
+        barrier()
+        t0 = time.perf_counter()
+        ms = C.c_float()
+        lib.modsgpu_timer_start(ctx)
+        last = None
+        for k in range(steps):
+            last = fn(k)
+        if with_gather:
+            gather_results()
+        lib.modsgpu_timer_stop(ctx, C.byref(ms))
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        dev_ms = float(ms.value)
+        if dist is not None:
+            t = torch.tensor([dev_ms, wall_ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dev_ms, wall_ms = float(t[0]), float(t[1])
+        return dev_ms, wall_ms, last
+
+    # ---- warm-up, then the timed arms
+    for k in range(max(args.warmup, 3)):
+        step_value(k, False)
+        step_e2e(k)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = mg.launch_count
+    dev_ms, wall_ms, last = timed(lambda k: step_value(k, True), args.steps, True)
+    launches = mg.launch_count - launches0
+    e2e_ms, e2e_wall, _ = timed(step_e2e, args.steps, True)
+    clk = clocks.stop() if rank == 0 else None
+    # ---- per-kernel events over the same K steps (separate pass so the timed arms carry no event overhead)
+    lib.modsgpu_profile_enable(ctx, 1)
+    for k in range(args.steps):
+        step_value(k, False)
+    buf = C.create_string_buffer(1 << 16)
+    lib.modsgpu_profile_report(ctx, buf, len(buf))
+    lib.modsgpu_profile_enable(ctx, 0)
+    prof = json.loads(buf.value.decode() or "{}")
+    if rank != 0:
+        return
+    value = world * args.steps / (dev_ms * 1e-3)
+    e2e_value = world * args.steps / (e2e_ms * 1e-3)
+    total_kernel_ms = sum(v["ms"] for v in prof.values()) or 1.0
+    top = max((k for k in prof if prof[k]["kind"] in ALG), key=lambda k: prof[k]["ms"], default=None)
+    roofline = None
+    if top:
+        p = prof[top]
+        bound, unit, scale = ALG[p["kind"]]
+        achieved = p["work"] / (p["ms"] * 1e-3) / scale
+        if bound == "hbm":
+            peak, src = peaks.get("hbm_gbs", 6650.0), ("MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.65 TB/s")
+        else:
+            peak = peaks.get("bf16_tflops_sustained", 1400.0)
+            src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback"
+        roofline = {"kernel": top, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
+                    "frac": achieved / peak, "traffic": None, "peak_source": src,
+                    "launches": p["launches"], "avg_us": 1e3 * p["ms"] / max(p["launches"], 1),
+                    "share_of_kernel_time": p["ms"] / total_kernel_ms}
+    kernels = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
+                   "share": v["ms"] / total_kernel_ms} for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        t0 = time.perf_counter()
+        parts, full, _ = cpu_pair(pairs[0], 4, threads)
+        cpu = {"value": 1.0 / full, "unit": "pairs/s", "cores": threads, "kind": "port",
+               "sample": "one pair: full detection of both images, per-keypoint stages on every 4th keypoint "
+                         "(x4), linear FGINN on the sampled descriptors (x16), reference degensac; %.1f s of CPU work"
+                         % (time.perf_counter() - t0),
+               "stage_seconds_sample": parts}
+    h2d = 2 * W_IMG * H_IMG * 3
+    d2h = 4 * 8 * int(last["inliers"]) + 9 * 8 + 9 * 4 if last else 0
+    line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16 (nets: fp16 operands, fp32 accumulate); f32 detector/sampler; f64 RANSAC",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": 1, "distinct_pairs": N_DISTINCT_PAIRS,
+                       "l2": "flushed before every step (256 MB memset on the pipeline stream)",
+                       "parallelism": "pairs sharded across ranks; one NCCL gather of the verified correspondences" if world > 1 else "single GPU",
+                       "last_step": {k: last[k] for k in ("keypoints", "regions", "descriptors", "tentatives", "unique_tentatives", "inliers")}},
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / args.steps,
+                    "note": "h2d/d2h count the API-level buffers (two BGR images in, verified correspondences + H out); "
+                            "the seam-by-seam host round trips of the reference interface are inside the timed region too"},
+            "gpu_launches": launches, "wall_ms_per_step": wall_ms / args.steps,
+            "roofline": roofline, "kernels": kernels, "clocks": clk}
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    mg.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

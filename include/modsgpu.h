@@ -158,6 +158,37 @@ typedef struct {
 int  modsgpu_ransac_H(modsgpu_ctx* ctx, const double* u, int T, const modsgpu_ransac_params* p,
                       double* H, unsigned char* inl, modsgpu_ransac_result* res);
 
+/* ---- whole pair (what one iteration of mods.cpp:202-356 does for the deep configuration
+ *      config_aff_ori_desc_zeromq.ini + iters_HessianZMQ.ini, vector_matcher = linear):
+ *      SynthDetectDescribeKeypoints x 2 -> MatchFlannFGINN -> DuplicateFiltering -> LORANSACFiltering.
+ *      Implemented by the C++ host mirror of the reference operators (csrc/host/mods_host.h). ---------- */
+typedef struct {
+  int    keypoints[2];          /* raw Hessian keypoints per image                     */
+  int    regions[2];            /* after the AffNet eigen-ratio / border filters       */
+  int    descriptors[2];        /* after ReprojectRegions (described regions)          */
+  int    tentatives, unique_tentatives, inliers;
+  double H[9];                  /* row-major, image 1 -> image 2 (matching.cpp:767-784) */
+} modsgpu_pair_result;
+/* images already resident on the device */
+int  modsgpu_pair_pipeline_images(modsgpu_ctx* ctx, modsgpu_image* img1, modsgpu_image* img2, unsigned long long seed,
+                                  modsgpu_pair_result* res, double* inlier_xy /* capacity x (x1,y1,x2,y2) or NULL */,
+                                  int capacity);
+/* host BGR images (cv::imread layout): upload + pipeline */
+int  modsgpu_pair_pipeline(modsgpu_ctx* ctx, const uint8_t* bgr1, const uint8_t* bgr2, int w, int h,
+                           unsigned long long seed, modsgpu_pair_result* res, double* inlier_xy, int capacity);
+/* test-only: one 128x32x64 GEMM through the tcgen05 descriptor conventions of the dense kernels */
+int  modsgpu_debug_umma_probe(modsgpu_ctx* ctx, const float* A, const float* B, float* D, int swap_lbo_sbo);
+
+/* ---- measurement helpers used by bench.py ---------------------------------------------------------------- */
+/* per-launch CUDA-event timing of every kernel (aggregated by kernel name); report is a JSON object */
+int  modsgpu_profile_enable(modsgpu_ctx* ctx, int on);
+int  modsgpu_profile_report(modsgpu_ctx* ctx, char* buf, int cap);
+/* CUDA events on the ctx stream around an arbitrary host-side region */
+int  modsgpu_timer_start(modsgpu_ctx* ctx);
+int  modsgpu_timer_stop(modsgpu_ctx* ctx, float* ms);
+/* overwrite a 256 MB scratch buffer (> the 126 MB L2) on the ctx stream */
+int  modsgpu_flush_l2(modsgpu_ctx* ctx);
+
 #ifdef __cplusplus
 }
 #endif

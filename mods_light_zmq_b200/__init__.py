@@ -34,6 +34,11 @@ class RansacParams(C.Structure):
                 ("seed", C.c_uint64)]
 
 
+class PairResult(C.Structure):
+    _fields_ = [("keypoints", C.c_int * 2), ("regions", C.c_int * 2), ("descriptors", C.c_int * 2),
+                ("tentatives", C.c_int), ("unique_tentatives", C.c_int), ("inliers", C.c_int), ("H", C.c_double * 9)]
+
+
 class RansacResult(C.Structure):
     _fields_ = [("n_inliers", C.c_int), ("J", C.c_double), ("samples", C.c_int), ("lo_runs", C.c_int),
                 ("oc_rejects", C.c_int)]
@@ -239,6 +244,34 @@ class ModsGpu:
         self._check(self.lib.modsgpu_ransac_H(self.ctx, _p(u), T, C.byref(p), _p(H), _p(inl), C.byref(res)))
         return dict(H=H, inl=inl[:T], I=res.n_inliers, J=res.J, samples=res.samples, lo_count=res.lo_runs,
                     oc_rejects=res.oc_rejects)
+
+
+def _pair_dict(res, xy):
+    return dict(keypoints=list(res.keypoints), regions=list(res.regions), descriptors=list(res.descriptors),
+                tentatives=res.tentatives, unique_tentatives=res.unique_tentatives, inliers=res.inliers,
+                H=np.array(list(res.H)).reshape(3, 3), inlier_xy=xy[:res.inliers].copy())
+
+
+def _pair_pipeline_images(self, img1, img2, seed=12345, capacity=4096):
+    res = PairResult()
+    xy = np.zeros((capacity, 4), np.float64)
+    self._check(self.lib.modsgpu_pair_pipeline_images(self.ctx, img1.handle, img2.handle, C.c_ulonglong(seed),
+                                                      C.byref(res), _p(xy), capacity))
+    return _pair_dict(res, xy)
+
+
+def _pair_pipeline(self, bgr1, bgr2, seed=12345, capacity=4096):
+    """host BGR u8 images -> upload -> detect/describe x2 -> match -> dedup -> LO-RANSAC."""
+    h, w, _ = bgr1.shape
+    res = PairResult()
+    xy = np.zeros((capacity, 4), np.float64)
+    self._check(self.lib.modsgpu_pair_pipeline(self.ctx, _p(bgr1), _p(bgr2), w, h, C.c_ulonglong(seed),
+                                               C.byref(res), _p(xy), capacity))
+    return _pair_dict(res, xy)
+
+
+ModsGpu.pair_pipeline_images = _pair_pipeline_images
+ModsGpu.pair_pipeline = _pair_pipeline
 
 
 def regions_from_keypoints(kps):

@@ -38,6 +38,11 @@ extern "C" void modsgpu_destroy(modsgpu_ctx* ctx) {
   for (DevBuf* b : bufs) b->release();
   ctx->h_stage.release();
   ctx->h_stage2.release();
+  for (auto e : ctx->prof.pool) cudaEventDestroy(e);
+  for (auto& r : ctx->prof.recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  ctx->l2flush.release();
+  if (ctx->tm0) cudaEventDestroy(ctx->tm0);
+  if (ctx->tm1) cudaEventDestroy(ctx->tm1);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);
@@ -48,3 +53,84 @@ extern "C" const char* modsgpu_last_error(const modsgpu_ctx* ctx) { return ctx ?
 extern "C" float modsgpu_last_device_ms(const modsgpu_ctx* ctx) { return ctx ? ctx->last_ms : 0.f; }
 extern "C" long long modsgpu_launch_count(const modsgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" void* modsgpu_stream(const modsgpu_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+// ---- measurement helpers (bench.py) -------------------------------------------------------------------
+void mg_prof_begin(modsgpu_ctx* ctx, const char* name, int kind, double work) {
+  Profiler& P = ctx->prof;
+  ProfRec r;
+  r.name = name; r.kind = kind; r.work = work;
+  for (cudaEvent_t* e : {&r.e0, &r.e1}) {
+    if (!P.pool.empty()) { *e = P.pool.back(); P.pool.pop_back(); }
+    else cudaEventCreate(e);
+  }
+  cudaEventRecord(r.e0, ctx->stream);
+  P.recs.push_back(r);
+  P.open = true;
+}
+void mg_prof_end(modsgpu_ctx* ctx) {
+  Profiler& P = ctx->prof;
+  if (!P.open || P.recs.empty()) return;
+  cudaEventRecord(P.recs.back().e1, ctx->stream);
+  P.open = false;
+}
+static void prof_collect(modsgpu_ctx* ctx) {
+  Profiler& P = ctx->prof;
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& r : P.recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+      ProfAgg& a = P.agg[r.name];
+      a.kind = r.kind; a.launches++; a.ms += ms; a.work += r.work;
+    }
+    P.pool.push_back(r.e0); P.pool.push_back(r.e1);
+  }
+  P.recs.clear();
+  P.open = false;
+}
+extern "C" int modsgpu_profile_enable(modsgpu_ctx* ctx, int on) {
+  if (!ctx) return MODSGPU_EINVAL;
+  prof_collect(ctx);
+  if (on) ctx->prof.agg.clear();
+  ctx->prof.on = on != 0;
+  return 0;
+}
+// JSON: {"kernel": {"kind": k, "launches": n, "ms": total, "work": total}, ...}; returns the length needed
+extern "C" int modsgpu_profile_report(modsgpu_ctx* ctx, char* buf, int cap) {
+  if (!ctx) return MODSGPU_EINVAL;
+  prof_collect(ctx);
+  std::string s = "{";
+  bool first = true;
+  for (auto& kv : ctx->prof.agg) {
+    char tmp[512];
+    snprintf(tmp, sizeof(tmp), "%s\"%s\": {\"kind\": %d, \"launches\": %lld, \"ms\": %.6f, \"work\": %.6e}", first ? "" : ", ",
+             kv.first.c_str(), kv.second.kind, kv.second.launches, kv.second.ms, kv.second.work);
+    s += tmp;
+    first = false;
+  }
+  s += "}";
+  if (buf && cap > 0) { strncpy(buf, s.c_str(), cap - 1); buf[cap - 1] = 0; }
+  return (int)s.size() + 1;
+}
+extern "C" int modsgpu_timer_start(modsgpu_ctx* ctx) {
+  if (!ctx) return MODSGPU_EINVAL;
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->tm0) { MG_CUDA(ctx, cudaEventCreate(&ctx->tm0)); MG_CUDA(ctx, cudaEventCreate(&ctx->tm1)); }
+  MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  MG_CUDA(ctx, cudaEventRecord(ctx->tm0, ctx->stream));
+  return 0;
+}
+extern "C" int modsgpu_timer_stop(modsgpu_ctx* ctx, float* ms) {
+  if (!ctx || !ms || !ctx->tm0) return MODSGPU_EINVAL;
+  MG_CUDA(ctx, cudaEventRecord(ctx->tm1, ctx->stream));
+  MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  MG_CUDA(ctx, cudaEventElapsedTime(ms, ctx->tm0, ctx->tm1));
+  return 0;
+}
+// write a buffer larger than the 126 MB L2 so the next step starts cold
+extern "C" int modsgpu_flush_l2(modsgpu_ctx* ctx) {
+  if (!ctx) return MODSGPU_EINVAL;
+  const size_t bytes = (size_t)256 << 20;
+  MG_CUDA(ctx, ctx->l2flush.ensure(bytes));
+  MG_CUDA(ctx, cudaMemsetAsync(ctx->l2flush.p, 0, bytes, ctx->stream));
+  return 0;
+}

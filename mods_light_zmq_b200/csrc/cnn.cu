@@ -520,6 +520,9 @@ int launch_conv(modsgpu_ctx* ctx, const __half* in, size_t in_slots, const ConvW
     attr = true;
   }
   const int ntiles = ceil_div(np * Cfg::PP, 128);
+  static char pname[64] = {0};
+  if (!pname[0]) snprintf(pname, sizeof(pname), "k_conv_umma<%d,%d,S%d,%s>", CIN, Cfg::COUT, S, NGRP == 4 ? "s2" : "s1");
+  MG_PROF(ctx, pname, 1, 2.0 * np * S * S * 9.0 * CIN * Cfg::COUT);
   int gx = std::min(ntiles, std::max(1, ctx->num_sms / NSPLIT));
   dim3 grid(gx, NSPLIT);
   kern<<<grid, 192, Cfg::SMEM_BYTES, ctx->stream>>>(in, in_slots, w.w, w.b, out, out_slots, np, ntiles);
@@ -619,6 +622,7 @@ int mg_net_forward_enqueue(modsgpu_ctx* ctx, modsgpu_net net, const uint8_t* d_p
     float* pout = d_out + (size_t)p0 * nw->out_dim;
     int rc = 0;
     if (net == MODSGPU_HARDNET) {
+      MG_PROF(ctx, "k_conv1<32>", 1, 2.0 * np * 1024 * 9 * 32);
       k_conv1<32><<<np, 256, 0, ctx->stream>>>(pin, np, nw->c1_w, nw->c1_b, nw->act[0], nw->slots[0]);
       MG_LAUNCHED(ctx);
       if ((rc = launch_conv<32, 32, 1, 32, 1, OUT_PARITY>(ctx, nw->act[0], nw->slots[0], nw->conv[0], nw->act[1], nw->slots[1], np))) return rc;
@@ -628,9 +632,11 @@ int mg_net_forward_enqueue(modsgpu_ctx* ctx, modsgpu_net net, const uint8_t* d_p
       if ((rc = launch_conv<128, 64, 2, 8, 1, OUT_GEMM>(ctx, nw->act[4], nw->slots[4], nw->conv[4], nw->act[5], nw->slots[5], np))) return rc;
       static bool attr = false;
       if (!attr) { MG_CUDA(ctx, cudaFuncSetAttribute(k_head_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, HG_SMEM)); attr = true; }
+      MG_PROF(ctx, "k_head_gemm", 1, 2.0 * np * 8192.0 * 128);
       k_head_gemm<<<ceil_div(np, 128), 192, HG_SMEM, ctx->stream>>>(nw->act[5], nw->slots[5], nw->head_w16, nw->head_b, pout, np);
       MG_LAUNCHED(ctx);
     } else {
+      MG_PROF(ctx, "k_conv1<16>", 1, 2.0 * np * 1024 * 9 * 16);
       k_conv1<16><<<np, 256, 0, ctx->stream>>>(pin, np, nw->c1_w, nw->c1_b, nw->act[0], nw->slots[0]);
       MG_LAUNCHED(ctx);
       if ((rc = launch_conv<16, 16, 1, 32, 1, OUT_PARITY>(ctx, nw->act[0], nw->slots[0], nw->conv[0], nw->act[1], nw->slots[1], np))) return rc;
@@ -638,6 +644,7 @@ int mg_net_forward_enqueue(modsgpu_ctx* ctx, modsgpu_net net, const uint8_t* d_p
       if ((rc = launch_conv<32, 32, 1, 16, 1, OUT_PARITY>(ctx, nw->act[2], nw->slots[2], nw->conv[2], nw->act[3], nw->slots[3], np))) return rc;
       if ((rc = launch_conv<32, 64, 1, 8, 4, OUT_NORMAL>(ctx, nw->act[3], nw->slots[3], nw->conv[3], nw->act[4], nw->slots[4], np))) return rc;
       if ((rc = launch_conv<64, 64, 1, 8, 1, OUT_NORMAL>(ctx, nw->act[4], nw->slots[4], nw->conv[4], nw->act[5], nw->slots[5], np))) return rc;
+      MG_PROF(ctx, net == MODSGPU_AFFNET ? "k_head_aff" : "k_head_ori", 1, 2.0 * np * (net == MODSGPU_AFFNET ? 12288.0 : 61952.0));
       if (net == MODSGPU_AFFNET)
         k_head_aff<<<ceil_div(np, 8), 256, 0, ctx->stream>>>(nw->act[5], nw->slots[5], nw->head_w32, nw->head_b, pout, np);
       else

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 #include "../../include/modsgpu.h"
@@ -51,6 +52,18 @@ struct modsgpu_image {
 
 struct NetWeights;  // cnn.cu
 
+// Optional per-launch CUDA-event timing (bench.py's roofline block).  kind: 0 = HBM-bound (work in bytes),
+// 1 = tensor-bound (work in flops), 2 = latency-bound (work = items).
+struct ProfRec { const char* name; int kind; double work; cudaEvent_t e0, e1; };
+struct ProfAgg { int kind = 0; long long launches = 0; double ms = 0, work = 0; };
+struct Profiler {
+  bool on = false;
+  bool open = false;
+  std::vector<ProfRec> recs;
+  std::vector<cudaEvent_t> pool;
+  std::map<std::string, ProfAgg> agg;
+};
+
 struct modsgpu_ctx {
   int device = 0;
   int num_sms = 148;
@@ -68,7 +81,15 @@ struct modsgpu_ctx {
   DevBuf mt_q, mt_t, mt_d, mt_aux, mt_out;
   DevBuf rs_buf;
   NetWeights* nets[3] = {nullptr, nullptr, nullptr};
+  Profiler prof;
+  cudaEvent_t tm0 = nullptr, tm1 = nullptr;   // modsgpu_timer_*
+  DevBuf l2flush;
 };
+
+void mg_prof_begin(modsgpu_ctx* ctx, const char* name, int kind, double work);
+void mg_prof_end(modsgpu_ctx* ctx);
+// call right before a kernel launch; MG_LAUNCHED closes the record
+#define MG_PROF(ctx, name, kind, work) do { if ((ctx)->prof.on) mg_prof_begin(ctx, name, kind, work); } while (0)
 
 #define MG_CUDA(ctx, call)                                                                  \
   do {                                                                                      \
@@ -87,6 +108,7 @@ struct modsgpu_ctx {
 #define MG_LAUNCHED(ctx)                         \
   do {                                           \
     (ctx)->launches++;                           \
+    if ((ctx)->prof.open) mg_prof_end(ctx);      \
     MG_CUDA(ctx, cudaGetLastError());            \
   } while (0)
 

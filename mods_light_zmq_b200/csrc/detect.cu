@@ -370,6 +370,7 @@ int launch_blur(modsgpu_ctx* ctx, const float* src, float* dst, float* resp, int
     attr_set = true;
   }
   dim3 grid(ceil_div(w, BT_X), ceil_div(h, BT_Y));
+  MG_PROF(ctx, resp ? "k_blur_resp" : "k_blur", 0, (double)w * h * 4.0 * (resp ? 3 : 2));
   k_blur_resp<<<grid, BT_THREADS, smem, ctx->stream>>>(src, dst, resp, w, h, taps, norm2);
   MG_LAUNCHED(ctx);
   return 0;
@@ -411,6 +412,7 @@ extern "C" int modsgpu_image_from_bgr8(modsgpu_ctx* ctx, const uint8_t* bgr, int
   img->w = w; img->h = h;
   MG_CUDA(ctx, cudaMalloc(&img->d, n * sizeof(float)));
   MG_CUDA(ctx, cudaMemcpyAsync(ctx->io_a.p, bgr, n * 3, cudaMemcpyHostToDevice, ctx->stream));
+  MG_PROF(ctx, "k_gray_from_bgr", 0, (double)n * 7.0);
   k_gray_from_bgr<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->io_a.as<uint8_t>(), img->d, (long)n);
   MG_LAUNCHED(ctx);
   if (mg_end(ctx)) return MODSGPU_ECUDA;
@@ -568,6 +570,7 @@ int mg_detect_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
     } else {
       float norm = curSigma * curSigma;
       dim3 blk(32, 8), grid(ceil_div(w, 32), ceil_div(h, 8));
+      MG_PROF(ctx, "k_response", 0, (double)px * 8.0);
       k_response<<<grid, blk, 0, ctx->stream>>>(Lv, Rv, w, h, norm * norm);
       MG_LAUNCHED(ctx);
     }
@@ -588,6 +591,7 @@ int mg_detect_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
       }
       if (i == nS && o + 1 < nOct) {
         dim3 blk(32, 8), grid(ceil_div(ow[o + 1], 32), ceil_div(oh[o + 1], 8));
+        MG_PROF(ctx, "k_half", 0, (double)ow[o + 1] * oh[o + 1] * 20.0);
         k_half<<<grid, blk, 0, ctx->stream>>>(Lv + px * i, w, h, pyr + oct_off[o + 1], ow[o + 1], oh[o + 1]);
         MG_LAUNCHED(ctx);
       }
@@ -602,6 +606,7 @@ int mg_detect_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
     int iw = w - 2 * p->border, ih = h - 2 * p->border;
     if (iw > 0 && ih > 0 && na.nlev > 0) {
       dim3 blk(32, 8), grid(ceil_div(iw, 32), ceil_div(ih, 8), na.nlev);
+      MG_PROF(ctx, "k_nms_localize", 0, (double)px * 4.0 * (na.nlev + 2));
       k_nms_localize<<<grid, blk, 0, ctx->stream>>>(na, map, cands, counters, cap);
       MG_LAUNCHED(ctx);
     }
@@ -609,8 +614,10 @@ int mg_detect_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
     pixelDistance *= 2.0f;
   }
   int nb = ceil_div(cap, 256);
+  MG_PROF(ctx, "k_resolve", 2, (double)cap);
   k_resolve<<<nb, 256, 0, ctx->stream>>>(cands, counters, cap, map, keys, counters + 1);
   MG_LAUNCHED(ctx);
+  MG_PROF(ctx, "k_rank_export", 2, (double)cap);
   k_rank_export<<<nb, 256, 0, ctx->stream>>>(cands, counters, cap, keys, ctx->det_out.as<modsgpu_keypoint>());
   MG_LAUNCHED(ctx);
   return 0;

@@ -1,0 +1,392 @@
+// mods_host.cpp -- host mirror of the reference operators over the C ABI (see mods_host.h).
+// Plain C++ (no CUDA): everything heavy is behind modsgpu_* calls; what remains here is the small
+// per-region double/float arithmetic the reference also does on the host between its stages.
+#include "mods_host.h"
+#include <chrono>
+#include <cmath>
+#include <cstring>
+
+namespace modsb200 {
+
+static double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// helpers.cpp:524-549.  NB callers pass doubles into the int res_w/res_h (truncation).
+bool interpolateCheckBorders(int orig_img_w, int orig_img_h, float ofsx, float ofsy, float a11, float a12, float a21,
+                             float a22, int res_w, int res_h) {
+  const int width = orig_img_w - 2;
+  const int height = orig_img_h - 2;
+  const float halfWidth = std::ceil((float)res_w / 2.0);
+  const float halfHeight = std::ceil((float)res_h / 2.0);
+  const float x[4] = {-halfWidth, -halfWidth, +halfWidth, +halfWidth};
+  const float y[4] = {-halfHeight, +halfHeight, -halfHeight, +halfHeight};
+  for (int i = 0; i < 4; i++) {
+    float imx = ofsx + x[i] * a11 + y[i] * a12;
+    float imy = ofsy + x[i] * a21 + y[i] * a22;
+    if (std::floor(imx) <= 0 || std::floor(imy) <= 0 || std::ceil(imx) >= width || std::ceil(imy) >= height) return true;
+  }
+  return false;
+}
+
+// helpers.cpp:401-410
+void rectifyAffineTransformationUpIsUp(double& a11, double& a12, double& a21, double& a22) {
+  double a = a11, b = a12, c = a21, d = a22;
+  double det = std::sqrt(std::fabs(a * d - b * c));
+  double b2a2 = std::sqrt(b * b + a * a);
+  a11 = b2a2 / det;
+  a12 = 0;
+  a21 = (d * b + c * a) / (b2a2 * det);
+  a22 = det / b2a2;
+}
+
+// helpers.cpp:504-515
+bool getEigenvalues(float a, float b, float c, float d, float& l1, float& l2) {
+  float trace = a + d;
+  float delta1 = (trace * trace - 4 * (a * d - b * c));
+  if (delta1 < 0) return false;
+  float delta = std::sqrt(delta1);
+  l1 = (trace + delta) / 2.0f;
+  l2 = (trace - delta) / 2.0f;
+  return true;
+}
+
+ImageRepresentation::ImageRepresentation(modsgpu_ctx* ctx, modsgpu_image* img, bool owns_image)
+    : ctx_(ctx), img_(img), owns_(owns_image) {}
+ImageRepresentation::~ImageRepresentation() {
+  if (owns_ && img_) modsgpu_image_free(ctx_, img_);
+}
+
+static void to_regions(const AffineRegionVector& v, std::vector<modsgpu_region>& r) {
+  r.resize(v.size());
+  for (size_t i = 0; i < v.size(); i++) {
+    const AffineKeypoint& k = v[i].det_kp;
+    r[i].x = k.x; r[i].y = k.y; r[i].s = k.s; r[i].a11 = k.a11; r[i].a12 = k.a12; r[i].a21 = k.a21; r[i].a22 = k.a22;
+  }
+}
+
+// imagerepresentation.cpp:686-1104 for one detector (HessianAffine) and the identity view (H = I,
+// synth-detection.cpp:366-377), deep configuration (config_aff_ori_desc_zeromq.ini + iters_HessianZMQ.ini).
+int ImageRepresentation::SynthDetectDescribeKeypoints(const DetectPars& par) {
+  int w, h;
+  modsgpu_image_size(img_, &w, &h);
+  regions_.clear();
+  double t0 = now_ms();
+  // ---- DetectAffineRegions (synth-detection.hpp:79-112) over DetectAffineKeypoints
+  modsgpu_keypoint* kps = nullptr;
+  int n = 0;
+  int rc = modsgpu_detect(ctx_, img_, &par.pyr, &kps, &n);
+  if (rc) return rc;
+  n_keypoints = n;
+  AffineRegionVector temp_kp1(n);
+  for (int i = 0; i < n; i++) {
+    AffineRegion& r = temp_kp1[i];
+    r.id = i; r.parent_id = -1; r.type = 1 /* DET_HESSIAN */;
+    AffineKeypoint& k = r.det_kp;
+    k.x = kps[i].x; k.y = kps[i].y; k.s = kps[i].s;      // s * sqrt(|det I|), rectifyTransformation(I) = I
+    k.a11 = 1; k.a12 = 0; k.a21 = 0; k.a22 = 1;
+    k.response = kps[i].response; k.octave_number = kps[i].octave; k.sub_type = kps[i].type;
+  }
+  modsgpu_free(kps);
+  std::vector<modsgpu_region> regs;
+  std::vector<float> out;
+  // ---- AffNet (imagerepresentation.cpp:797-845)
+  to_regions(temp_kp1, regs);
+  out.resize((size_t)n * 3 + 1);
+  rc = modsgpu_describe(ctx_, MODSGPU_AFFNET, img_, regs.data(), n, par.mrSize, par.patchSize, out.data());
+  if (rc) return rc;
+  AffineRegionVector temp_kp_aff;
+  temp_kp_aff.reserve(n);
+  for (int i = 0; i < n; i++) {
+    AffineRegion t = temp_kp1[i];
+    t.det_kp.a11 = out[3 * i + 0];
+    t.det_kp.a12 = 0;
+    t.det_kp.a21 = out[3 * i + 1];
+    t.det_kp.a22 = out[3 * i + 2];
+    rectifyAffineTransformationUpIsUp(t.det_kp.a11, t.det_kp.a12, t.det_kp.a21, t.det_kp.a22);
+    float l1 = 1.0f, l2 = 1.0f;
+    if (!getEigenvalues((float)t.det_kp.a11, (float)t.det_kp.a12, (float)t.det_kp.a21, (float)t.det_kp.a22, l1, l2)) continue;
+    if ((l1 / l2 > 6) || (l2 / l1 > 6)) continue;
+    if (interpolateCheckBorders(w, h, (float)t.det_kp.x, (float)t.det_kp.y, (float)t.det_kp.a11, (float)t.det_kp.a12,
+                                (float)t.det_kp.a21, (float)t.det_kp.a22, (int)(par.mrSize * t.det_kp.s),
+                                (int)(par.mrSize * t.det_kp.s)))
+      continue;
+    temp_kp_aff.push_back(t);
+  }
+  n_affine = (int)temp_kp_aff.size();
+  TimeSpent.DetectTime += now_ms() - t0;
+  t0 = now_ms();
+  // ---- ReprojectRegionsAndRemoveTouchBoundary(dontRemove = true), H = I (synth-detection.cpp:151-190)
+  AffineRegionVector kept;
+  kept.reserve(temp_kp_aff.size());
+  for (auto& r : temp_kp_aff) {
+    r.reproj_kp = r.det_kp;
+    if ((r.reproj_kp.x < w) && (r.reproj_kp.y < h) && (r.reproj_kp.x > 0) && (r.reproj_kp.y > 0)) kept.push_back(r);
+  }
+  // ---- OriNet (imagerepresentation.cpp:876-899)
+  const int n2 = (int)kept.size();
+  to_regions(kept, regs);
+  out.resize((size_t)n2 * 2 + 1);
+  rc = modsgpu_describe(ctx_, MODSGPU_ORINET, img_, regs.data(), n2, par.mrSize, par.patchSize, out.data());
+  if (rc) return rc;
+  AffineRegionVector oriented;
+  oriented.reserve(n2);
+  for (int i = 0; i < n2; i++) {
+    const AffineRegion& c = kept[i];
+    double angle = std::atan2((double)out[2 * i + 0], (double)out[2 * i + 1]);
+    double ci = std::cos(angle), si = std::sin(angle);
+    AffineRegion t = c;
+    t.det_kp.a11 = c.det_kp.a11 * ci - c.det_kp.a12 * si;
+    t.det_kp.a12 = c.det_kp.a11 * si + c.det_kp.a12 * ci;
+    t.det_kp.a21 = c.det_kp.a21 * ci - c.det_kp.a22 * si;
+    t.det_kp.a22 = c.det_kp.a21 * si + c.det_kp.a22 * ci;
+    oriented.push_back(t);
+  }
+  TimeSpent.OrientTime += now_ms() - t0;
+  t0 = now_ms();
+  // ---- ReprojectRegions (synth-detection.cpp:631-706): centre inside + k_sigma*s frame inside
+  const double k_sigma = 2 * 3.0 * std::sqrt(3.0);   // synth-detection.cpp:21
+  AffineRegionVector final_regs;
+  final_regs.reserve(oriented.size());
+  for (auto& r : oriented) {
+    r.reproj_kp = r.det_kp;
+    const AffineKeypoint& p = r.reproj_kp;
+    if ((p.x < w) && (p.y < h) && (p.x > 0) && (p.y > 0)) {
+      if (!interpolateCheckBorders(w, h, (float)p.x, (float)p.y, (float)p.a11, (float)p.a12, (float)p.a21, (float)p.a22,
+                                   (int)(k_sigma * p.s), (int)(k_sigma * p.s)))
+        final_regs.push_back(r);
+    }
+  }
+  // ---- HardNet++ (imagerepresentation.cpp:992-1006)
+  const int n3 = (int)final_regs.size();
+  to_regions(final_regs, regs);
+  out.resize((size_t)n3 * 128 + 1);
+  rc = modsgpu_describe(ctx_, MODSGPU_HARDNET, img_, regs.data(), n3, par.mrSize, par.patchSize, out.data());
+  if (rc) return rc;
+  for (int i = 0; i < n3; i++) {
+    final_regs[i].desc.assign(out.begin() + (size_t)i * 128, out.begin() + (size_t)(i + 1) * 128);
+    final_regs[i].id = i;
+  }
+  regions_.swap(final_regs);
+  TimeSpent.DescTime += now_ms() - t0;
+  return n3;
+}
+
+// matching.cpp:356-460 (vector_matcher = linear): list1 = queries (image 1), list2 = train (image 2)
+int MatchFlannFGINN(modsgpu_ctx* ctx, const AffineRegionVector& list1, const AffineRegionVector& list2,
+                    TentativeCorrespListExt& corresp, const MatchPars& par) {
+  corresp.TCList.clear();
+  const int n1 = (int)list1.size(), n2 = (int)list2.size();
+  if (n1 == 0 || n2 == 0) return 0;
+  const int dim = (int)list1[0].desc.size();
+  std::vector<float> q((size_t)n1 * dim), t((size_t)n2 * dim);
+  std::vector<double> txy((size_t)n2 * 2);
+  for (int i = 0; i < n1; i++) memcpy(&q[(size_t)i * dim], list1[i].desc.data(), dim * sizeof(float));
+  for (int i = 0; i < n2; i++) {
+    memcpy(&t[(size_t)i * dim], list2[i].desc.data(), dim * sizeof(float));
+    txy[2 * i] = list2[i].reproj_kp.x; txy[2 * i + 1] = list2[i].reproj_kp.y;
+  }
+  std::vector<modsgpu_match> m(n1);
+  int nm = 0;
+  int rc = modsgpu_match_fginn(ctx, q.data(), n1, t.data(), txy.data(), n2, dim, par.FGINNThreshold, par.contradDist,
+                               par.nn, m.data(), &nm, nullptr, nullptr);
+  if (rc) return rc;
+  corresp.TCList.reserve(nm);
+  for (int k = 0; k < nm; k++) {
+    TentativeCorrespExt tc;
+    tc.first = list1[m[k].qi];
+    tc.second = list2[m[k].ti];
+    tc.secondbad_idx = m[k].tj_bad;
+    tc.d1 = m[k].d1; tc.d2 = m[k].d2; tc.ratio = m[k].ratio;
+    corresp.TCList.push_back(tc);
+  }
+  return nm;
+}
+
+// matching.cpp:2615-2679, mode bestFGINN (mods.cpp:283)
+int DuplicateFiltering(modsgpu_ctx* ctx, TentativeCorrespListExt& in_corresp, double r) {
+  const int T = (int)in_corresp.TCList.size();
+  if (r <= 0 || T == 0) return T;
+  std::vector<double> xy1(2 * (size_t)T), xy2(2 * (size_t)T), ratio(T);
+  for (int i = 0; i < T; i++) {
+    const TentativeCorrespExt& c = in_corresp.TCList[i];
+    xy1[2 * i] = c.first.reproj_kp.x; xy1[2 * i + 1] = c.first.reproj_kp.y;
+    xy2[2 * i] = c.second.reproj_kp.x; xy2[2 * i + 1] = c.second.reproj_kp.y;
+    ratio[i] = c.ratio;
+  }
+  std::vector<int> ord(T);
+  int nout = 0;
+  int rc = modsgpu_duplicate_filter(ctx, xy1.data(), xy2.data(), ratio.data(), T, r, ord.data(), &nout);
+  if (rc) return rc;
+  std::vector<TentativeCorrespExt> keep;
+  keep.reserve(nout);
+  for (int i = 0; i < nout; i++) keep.push_back(in_corresp.TCList[ord[i]]);
+  in_corresp.TCList.swap(keep);
+  return nout;
+}
+
+static bool invert3(const double* A, double* R) {
+  const double c0 = A[4] * A[8] - A[5] * A[7], c1 = A[5] * A[6] - A[3] * A[8], c2 = A[3] * A[7] - A[4] * A[6];
+  const double det = A[0] * c0 + A[1] * c1 + A[2] * c2;
+  if (det == 0 || !std::isfinite(det)) { for (int i = 0; i < 9; i++) R[i] = 0; return false; }
+  const double id = 1.0 / det;
+  R[0] = c0 * id; R[1] = (A[2] * A[7] - A[1] * A[8]) * id; R[2] = (A[1] * A[5] - A[2] * A[4]) * id;
+  R[3] = c1 * id; R[4] = (A[0] * A[8] - A[2] * A[6]) * id; R[5] = (A[2] * A[3] - A[0] * A[5]) * id;
+  R[6] = c2 * id; R[7] = (A[1] * A[6] - A[0] * A[7]) * id; R[8] = (A[0] * A[4] - A[1] * A[3]) * id;
+  return true;
+}
+
+// matching.cpp:1014-1043
+static int NaiveHCheck(const TentativeCorrespListExt& corresp, const double* H, double error) {
+  const double err_sq = error * error;
+  double Hinv[9];
+  invert3(H, Hinv);
+  int corr_numb = 0;
+  for (const auto& c : corresp.TCList) {
+    const double x1 = c.first.reproj_kp.x, y1 = c.first.reproj_kp.y, x2 = c.second.reproj_kp.x, y2 = c.second.reproj_kp.y;
+    double xa = (H[0] * x1 + H[1] * y1 + H[2]) / (H[6] * x1 + H[7] * y1 + H[8]);
+    double ya = (H[3] * x1 + H[4] * y1 + H[5]) / (H[6] * x1 + H[7] * y1 + H[8]);
+    const double d1 = (x2 - xa) * (x2 - xa) + (y2 - ya) * (y2 - ya);
+    xa = (Hinv[0] * x2 + Hinv[1] * y2 + Hinv[2]) / (Hinv[6] * x2 + Hinv[7] * y2 + Hinv[8]);
+    ya = (Hinv[3] * x2 + Hinv[4] * y2 + Hinv[5]) / (Hinv[6] * x2 + Hinv[7] * y2 + Hinv[8]);
+    const double d2 = (x1 - xa) * (x1 - xa) + (y1 - ya) * (y1 - ya);
+    if ((d1 <= err_sq) && (d2 <= err_sq)) corr_numb++;
+  }
+  return corr_numb;
+}
+
+// Htools.c HDsSymMax for one point pair: Hl in the degensac convention (column-major, image 2 -> image 1)
+static double HDsSymMax1(const double* Hl, const double* u) {
+  const double Hm[9] = {Hl[0], Hl[3], Hl[6], Hl[1], Hl[4], Hl[7], Hl[2], Hl[5], Hl[8]};
+  double H1[9];
+  invert3(Hm, H1);
+  const double a = H1[6] * u[0] + H1[7] * u[1] + H1[8];
+  const double b = Hm[6] * u[3] + Hm[7] * u[4] + Hm[8];
+  double xa = (H1[0] * u[0] + H1[1] * u[1] + H1[2]) / a, ya = (H1[3] * u[0] + H1[4] * u[1] + H1[5]) / a;
+  double xd = u[3] - xa, yd = u[4] - ya;
+  const double d1 = xd * xd + yd * yd;
+  xa = (Hm[0] * u[3] + Hm[1] * u[4] + Hm[2]) / b; ya = (Hm[3] * u[3] + Hm[4] * u[4] + Hm[5]) / b;
+  xd = u[0] - xa; yd = u[1] - ya;
+  const double d2 = xd * xd + yd * yd;
+  return d1 > d2 ? d1 : d2;
+}
+
+// matching.cpp:250-308 with HDS1 = HDsSymMax
+static void H_LAF_check(const std::vector<TentativeCorrespExt>& in, const double* Hl, std::vector<TentativeCorrespExt>& res,
+                        double affineFerror) {
+  const double k_sigma = 2 * 3.0 * std::sqrt(3.0);
+  res.clear();
+  if (!(affineFerror > 0)) { res = in; return; }
+  for (const auto& c : in) {
+    const AffineKeypoint &f = c.first.reproj_kp, &s = c.second.reproj_kp;
+    double u[18];
+    u[0] = f.x; u[1] = f.y; u[2] = 1.0; u[3] = s.x; u[4] = s.y; u[5] = 1.0;
+    u[6] = u[0] + k_sigma * f.a12 * f.s; u[7] = u[1] + k_sigma * f.a22 * f.s; u[8] = 1.0;
+    u[9] = u[3] + k_sigma * s.a12 * s.s; u[10] = u[4] + k_sigma * s.a22 * s.s; u[11] = 1.0;
+    u[12] = u[0] + k_sigma * f.a11 * f.s; u[13] = u[1] + k_sigma * f.a21 * f.s; u[14] = 1.0;
+    u[15] = u[3] + k_sigma * s.a11 * s.s; u[16] = u[4] + k_sigma * s.a21 * s.s; u[17] = 1.0;
+    const double sumErr = std::sqrt(HDsSymMax1(Hl, u) + HDsSymMax1(Hl, u + 6) + HDsSymMax1(Hl, u + 12));
+    if (!(sumErr > affineFerror)) res.push_back(c);
+  }
+}
+
+// matching.cpp:637-823, H branch
+int LORANSACFiltering(modsgpu_ctx* ctx, TentativeCorrespListExt& in_corresp, TentativeCorrespListExt& ransac_corresp,
+                      double* H, const RANSACPars& pars) {
+  const int MIN_POINTS = 8;   // matching.hpp:27
+  const int tent_size = (int)in_corresp.TCList.size();
+  ransac_corresp.TCList.clear();
+  int max_samples = pars.max_samples;
+  if (tent_size <= 20) max_samples = 1000;
+  if (tent_size < MIN_POINTS) return 0;
+  std::vector<double> u2((size_t)tent_size * 6);
+  for (int i = 0; i < tent_size; i++) {
+    const TentativeCorrespExt& c = in_corresp.TCList[i];
+    u2[6 * i + 0] = c.first.reproj_kp.x; u2[6 * i + 1] = c.first.reproj_kp.y; u2[6 * i + 2] = 1.;
+    u2[6 * i + 3] = c.second.reproj_kp.x; u2[6 * i + 4] = c.second.reproj_kp.y; u2[6 * i + 5] = 1.;
+  }
+  std::vector<unsigned char> inl2(tent_size);
+  double Hloran[9];
+  modsgpu_ransac_params rp;
+  rp.th = pars.err_threshold * pars.err_threshold;
+  rp.conf = pars.confidence;
+  rp.max_samples = max_samples;
+  rp.do_sym_check = pars.doSymmCheck;
+  rp.seed = pars.seed;
+  modsgpu_ransac_result rr;
+  int rc = modsgpu_ransac_H(ctx, u2.data(), tent_size, &rp, Hloran, inl2.data(), &rr);
+  if (rc) return rc;
+  for (int i = 0; i < tent_size; i++) {
+    in_corresp.TCList[i].isTrue = inl2[i];
+    if (inl2[i]) ransac_corresp.TCList.push_back(in_corresp.TCList[i]);
+  }
+  // H = inv(Hloran^T)  (matching.cpp:767-784)
+  const double Ht[9] = {Hloran[0], Hloran[3], Hloran[6], Hloran[1], Hloran[4], Hloran[7], Hloran[2], Hloran[5], Hloran[8]};
+  double Hinv[9];
+  invert3(Ht, Hinv);
+  bool nonzero = false;
+  for (int i = 0; i < 9; i++) nonzero = nonzero || (Hinv[i] != 0.0);
+  if (!nonzero) { ransac_corresp.TCList.clear(); return 0; }
+  for (int i = 0; i < 9; i++) { ransac_corresp.H[i] = Hinv[i]; H[i] = Hinv[i]; }
+  if (NaiveHCheck(ransac_corresp, ransac_corresp.H, 10.0) < MIN_POINTS) ransac_corresp.TCList.clear();
+  std::vector<TentativeCorrespExt> checked;
+  H_LAF_check(ransac_corresp.TCList, Hloran, checked, 3.0 * pars.HLAFCoef * pars.err_threshold);
+  if ((int)checked.size() < MIN_POINTS) checked.clear();
+  ransac_corresp.TCList.swap(checked);
+  return (int)ransac_corresp.TCList.size();
+}
+
+}  // namespace modsb200
+
+// ------------------------------------------------------------------------------------------------------
+// C entry: the whole pair pipeline (what mods.cpp:202-356 does for one iteration of the deep config)
+// ------------------------------------------------------------------------------------------------------
+extern "C" int modsgpu_pair_pipeline_images(modsgpu_ctx* ctx, modsgpu_image* img1, modsgpu_image* img2,
+                                            unsigned long long seed, modsgpu_pair_result* res,
+                                            double* inlier_xy /* capacity*4 or NULL */, int capacity) {
+  using namespace modsb200;
+  if (!ctx || !img1 || !img2 || !res) return MODSGPU_EINVAL;
+  memset(res, 0, sizeof(*res));
+  DetectPars dp;
+  MatchPars mp;
+  RANSACPars rp;
+  rp.seed = seed;
+  ImageRepresentation r1(ctx, img1, false), r2(ctx, img2, false);
+  int n1 = r1.SynthDetectDescribeKeypoints(dp);
+  if (n1 < 0) return n1;
+  int n2 = r2.SynthDetectDescribeKeypoints(dp);
+  if (n2 < 0) return n2;
+  res->keypoints[0] = r1.n_keypoints; res->keypoints[1] = r2.n_keypoints;
+  res->regions[0] = r1.n_affine; res->regions[1] = r2.n_affine;
+  res->descriptors[0] = n1; res->descriptors[1] = n2;
+  TentativeCorrespListExt tent, verified;
+  int nt = MatchFlannFGINN(ctx, r1.GetAffineRegionVector(), r2.GetAffineRegionVector(), tent, mp);
+  if (nt < 0) return nt;
+  res->tentatives = nt;
+  int nu = DuplicateFiltering(ctx, tent, mp.doubleFilteringRadius);
+  if (nu < 0) return nu;
+  res->unique_tentatives = nu;
+  int ni = LORANSACFiltering(ctx, tent, verified, res->H, rp);
+  if (ni < 0) return ni;
+  res->inliers = ni;
+  for (int i = 0; i < ni && i < capacity && inlier_xy; i++) {
+    const TentativeCorrespExt& c = verified.TCList[i];
+    inlier_xy[4 * i + 0] = c.first.reproj_kp.x; inlier_xy[4 * i + 1] = c.first.reproj_kp.y;
+    inlier_xy[4 * i + 2] = c.second.reproj_kp.x; inlier_xy[4 * i + 3] = c.second.reproj_kp.y;
+  }
+  return 0;
+}
+
+extern "C" int modsgpu_pair_pipeline(modsgpu_ctx* ctx, const uint8_t* bgr1, const uint8_t* bgr2, int w, int h,
+                                     unsigned long long seed, modsgpu_pair_result* res, double* inlier_xy, int capacity) {
+  if (!ctx || !bgr1 || !bgr2 || !res) return MODSGPU_EINVAL;
+  modsgpu_image *i1 = nullptr, *i2 = nullptr;
+  int rc = modsgpu_image_from_bgr8(ctx, bgr1, w, h, &i1);
+  if (rc) return rc;
+  rc = modsgpu_image_from_bgr8(ctx, bgr2, w, h, &i2);
+  if (rc) { modsgpu_image_free(ctx, i1); return rc; }
+  rc = modsgpu_pair_pipeline_images(ctx, i1, i2, seed, res, inlier_xy, capacity);
+  modsgpu_image_free(ctx, i1);
+  modsgpu_image_free(ctx, i2);
+  return rc;
+}

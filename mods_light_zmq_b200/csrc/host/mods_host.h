@@ -1,0 +1,94 @@
+// mods_host.h -- C++ host mirror of the reference's operator interface for the hot path, written on
+// top of the C ABI (include/modsgpu.h).  Same names, argument meaning and return conventions as the
+// reference so the call sites in mods.cpp / extract_features_batch.cpp read the same:
+//   ImageRepresentation::SynthDetectDescribeKeypoints   imagerepresentation.cpp:686-1104 (identity view,
+//       HessianAffine + AffNet + OriNet + HardNet++; the three DescribeWithZmq round trips
+//       :800/:878/:995 become modsgpu_describe calls)
+//   MatchFlannFGINN       matching.cpp:356-460      DuplicateFiltering  matching.cpp:2615-2679
+//   LORANSACFiltering     matching.cpp:637-823      (H branch: NaiveHCheck :1014-1043, H_LAF_check :250-308)
+#pragma once
+#include <string>
+#include <vector>
+#include "../../../include/modsgpu.h"
+
+namespace modsb200 {
+
+struct AffineKeypoint {            // structures.hpp:185-194
+  double x = 0, y = 0, s = 0;
+  double a11 = 1, a12 = 0, a21 = 0, a22 = 1;
+  double response = 0;
+  int octave_number = 0, sub_type = 0;
+};
+struct AffineRegion {              // structures.hpp:218-229
+  int img_id = 0, img_reproj_id = 0, id = 0, parent_id = 0, type = 0;
+  AffineKeypoint det_kp, reproj_kp;
+  std::vector<float> desc;         // descriptor.vec
+};
+typedef std::vector<AffineRegion> AffineRegionVector;
+
+struct TentativeCorrespExt {       // matching.hpp:39-51
+  AffineRegion first, second;
+  int secondbad_idx = -1;
+  double d1 = 0, d2 = 0, ratio = 0;
+  int isTrue = 0;
+};
+struct TentativeCorrespListExt {
+  std::vector<TentativeCorrespExt> TCList;
+  double H[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+};
+
+struct MatchPars {                 // matching.hpp:97-130, values of config_aff_ori_desc_zeromq.ini
+  double FGINNThreshold = 0.8;     // iters_HessianZMQ.ini
+  double contradDist = 10.0;
+  int nn = 50;
+  double doubleFilteringRadius = 2.0;   // mods.cpp:283
+};
+struct RANSACPars {                // matching.hpp:132-164
+  double err_threshold = 4.0;
+  double confidence = 0.99;
+  int max_samples = 1000000;
+  int doSymmCheck = 1;
+  double HLAFCoef = 12.0;
+  unsigned long long seed = 12345; // the reference seeds with time(NULL) (exp_ranH.c:823)
+};
+struct DetectPars {
+  modsgpu_pyr_params pyr;          // [HessianAffine]
+  double mrSize = 5.1962;          // AffNet / OriNet / desc patch extent
+  int patchSize = 32;
+  DetectPars() { modsgpu_default_pyr_params(&pyr); }
+};
+
+struct TimeLog {                   // structures.hpp:33-56 (device + host ms per stage)
+  double DetectTime = 0, OrientTime = 0, DescTime = 0, MatchingTime = 0, RANSACTime = 0;
+};
+
+class ImageRepresentation {
+ public:
+  ImageRepresentation(modsgpu_ctx* ctx, modsgpu_image* img, bool owns_image);
+  ~ImageRepresentation();
+  // returns the number of described regions, < 0 on error (message via modsgpu_last_error)
+  int SynthDetectDescribeKeypoints(const DetectPars& par);
+  const AffineRegionVector& GetAffineRegionVector() const { return regions_; }
+  int n_keypoints = 0, n_affine = 0;
+  TimeLog TimeSpent;
+
+ private:
+  modsgpu_ctx* ctx_;
+  modsgpu_image* img_;
+  bool owns_;
+  AffineRegionVector regions_;
+};
+
+// helpers.cpp:524-549 / :401-410 / :504-515
+bool interpolateCheckBorders(int orig_img_w, int orig_img_h, float ofsx, float ofsy, float a11, float a12, float a21,
+                             float a22, int res_w, int res_h);
+void rectifyAffineTransformationUpIsUp(double& a11, double& a12, double& a21, double& a22);
+bool getEigenvalues(float a, float b, float c, float d, float& l1, float& l2);
+
+int MatchFlannFGINN(modsgpu_ctx* ctx, const AffineRegionVector& list1, const AffineRegionVector& list2,
+                    TentativeCorrespListExt& corresp, const MatchPars& par);
+int DuplicateFiltering(modsgpu_ctx* ctx, TentativeCorrespListExt& in_corresp, double r);
+int LORANSACFiltering(modsgpu_ctx* ctx, TentativeCorrespListExt& in_corresp, TentativeCorrespListExt& ransac_corresp,
+                      double* H, const RANSACPars& pars);
+
+}  // namespace modsb200

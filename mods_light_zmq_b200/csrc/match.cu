@@ -253,8 +253,10 @@ int mg_match_enqueue(modsgpu_ctx* ctx, const float* d_q, int nq, const float* d_
   int* bad = ctx->mt_aux.as<int>();
   MG_CUDA(ctx, cudaMemsetAsync(bad, 0, 4, ctx->stream));
   dim3 pb(32, 8);
+  MG_PROF(ctx, "k_pack_desc", 0, (double)nq * dim * 6.0);
   k_pack_desc<<<nq_pad / 8, pb, 0, ctx->stream>>>(d_q, nq, nq_pad, dim, qp, qn, bad, 0.f);
   MG_LAUNCHED(ctx);
+  MG_PROF(ctx, "k_pack_desc", 0, (double)nt * dim * 6.0);
   k_pack_desc<<<nt_pad / 8, pb, 0, ctx->stream>>>(d_t, nt, nt_pad, dim, tp, tn, bad, 0.f);
   MG_LAUNCHED(ctx);
   // distance matrix in query blocks of <= 256 MB
@@ -267,8 +269,10 @@ int mg_match_enqueue(modsgpu_ctx* ctx, const float* d_q, int nq, const float* d_
   for (int q0 = 0; q0 < nq; q0 += qblk) {
     const int rows_pad = std::min(qblk, nq_pad - q0), rows = std::min(qblk, nq - q0);
     dim3 grid(nt_pad / 128, rows_pad / 128);
+    MG_PROF(ctx, "k_dist_umma", 0, (double)rows_pad * nt_pad * 4.0 + ((double)rows_pad + nt_pad) * dim * 2.0);
     k_dist_umma<<<grid, 128, smem, ctx->stream>>>(qp + (size_t)q0 * 8, nq_pad, tp, nt_pad, dim, qn + q0, tn, ctx->mt_d.as<float>());
     MG_LAUNCHED(ctx);
+    MG_PROF(ctx, "k_select_fginn", 0, (double)rows * nt * 4.0);
     k_select_fginn<<<rows, 128, 0, ctx->stream>>>(ctx->mt_d.as<float>(), nt, nt_pad, nn, d_txy, sq, cd,
                                                    ctx->mt_out.as<modsgpu_match>(), d_knn_idx, d_knn_dist, q0);
     MG_LAUNCHED(ctx);
@@ -339,6 +343,7 @@ extern "C" int modsgpu_duplicate_filter(modsgpu_ctx* ctx, const double* xy1, con
   MG_CUDA(ctx, cudaMemcpyAsync(d1, xy1, xb, cudaMemcpyHostToDevice, ctx->stream));
   MG_CUDA(ctx, cudaMemcpyAsync(d2, xy2, xb, cudaMemcpyHostToDevice, ctx->stream));
   MG_CUDA(ctx, cudaMemcpyAsync(dr, ratio, rb, cudaMemcpyHostToDevice, ctx->stream));
+  MG_PROF(ctx, "k_dup_filter", 2, (double)T);
   k_dup_filter<<<1, 256, 0, ctx->stream>>>(d1, d2, dr, T, r * r, dord, alive, dout, ctx->mt_aux.as<int>() + 4);
   MG_LAUNCHED(ctx);
   MG_CUDA(ctx, ctx->h_stage.ensure((size_t)T * 4 + 16));

@@ -1,8 +1,618 @@
-// ransac.cu -- LO-RANSAC (homography) on the device.  Placeholder until the batched kernel lands.
+// ransac.cu -- batched LO-RANSAC for a homography on the device (seam S4).
+//
+// Replaces exp_ransacHcustom (degensac/exp_ranH.c:796-1236) as LORANSACFiltering calls it
+// (matching.cpp:731: iter_type 4, oriented constraint on, Sampson error, MSAC score, symmetric check).
+// The reference is a sequential loop driven by libc rand(); this is the same estimator re-organised
+// for a GPU:
+//   k_rs_hyp     one WARP per hypothesis, B hypotheses per launch: counter-based RNG (no state carried
+//                between samples) -> 4-point sample -> oriented constraint (Htools.c all_Hori_valid) ->
+//                8x9 null space by pivoted Gauss-Jordan (utools.c:97-167) -> |det|/h33^3 test ->
+//                Sampson error of all T correspondences (Htools.c:160-198), lanes striding over T ->
+//                MSAC score (rtools.c truncQuad, 9/4*th width) by a fixed-order butterfly reduction
+//   k_rs_update  one CTA per batch: best hypothesis of the batch (max J, lowest index on ties), symmetric
+//                transfer check (exp_ranH.c:905-947), local optimisation = LSQ on the 8*th band + 10
+//                inner samples x 4 shrinking-threshold LSQ steps (exp_inHranicustom / exp_iterHcustom),
+//                the 10 inner samples running in 10 warps at once; adaptive stopping nsamples(I+1,T,4,conf)
+// All arithmetic is fp64 and compiled with --fmad=false; every reduction has a fixed order, so a run is
+// reproducible from (u, params.seed).
+// Deviations from the reference, on purpose: (1) samples are consumed in batches, so at least B are drawn;
+// (2) the LSQ null vector comes from 10 steps of inverse iteration on the 9x9 normal matrix instead of
+// LAPACK dsyev_ (lapwrap.c:75-97; third-party, unpinned); (3) the inlier-set hash that prunes repeated
+// LO iterations (exp_ranH.c __HASHING__) is dropped -- it only skips work whose result is already known.
 #include "common.cuh"
+#include <cmath>
+#include <algorithm>
+
+namespace {
+
+constexpr int RS_MAX_B = 4096;
+constexpr int LO_REPS = 10;       // RAN_REP, rtools.h:8
+constexpr int ILSQ_ITERS = 4;     // rtools.h:9
+constexpr double TC = 4.0;        // rtools.h:10
+constexpr double MWM = 2.0;       // rtools.h:33: (9/4) in integer arithmetic
+constexpr double CHECK_COEF = 9.0;
+constexpr int MIN_GOOD_SYM_PTS = 5;
+constexpr int ITER_SAM = 50;
+
+struct RsState {
+  double H[9];            // best model (maxS)
+  double J; int I;
+  double Hs[9];           // best sample so far (maxSs)
+  double Js; int Is;
+  int max_sam, no_sam, lo_runs, oc_rejects, done, have_sample;
+};
+
+struct HypOut { double H[9]; double J; int I; int flag; };   // flag: 0 ok, 1 oriented-constraint reject, 2 degenerate
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ unsigned rs_rand(unsigned long long seed, unsigned long long stream, unsigned draw, unsigned range) {
+  return (unsigned)(mix64(seed ^ mix64(stream * 0x100000001B3ull + draw)) % range);
+}
+
+__device__ __forceinline__ double truncQuad(double eps, double thr) {
+  if (thr == 0) return 0;
+  if (eps >= thr * 9 / 4) return 0;
+  return 1 - (eps / (thr * 9 / 4));
+}
+
+__device__ __forceinline__ double det3(const double* A) {
+  double r = (A[0] * A[4] * A[8] + A[2] * A[3] * A[7] + A[1] * A[5] * A[6]);
+  r -= (A[2] * A[4] * A[6] + A[0] * A[5] * A[7] + A[1] * A[3] * A[8]);
+  return r;
+}
+
+// exp_ranH.c:883-892 / :1021-1032: reject H close to singular
+__device__ __forceinline__ bool det_ok(const double* h) {
+  double v = det3(h), tol = h[8];
+  if (tol == 0) {
+    for (int i = 0; i < 9; ++i) tol += h[i] * h[i];
+    tol = sqrt(tol);
+    tol *= 0.001;
+  }
+  tol = tol * tol * tol;
+  return !(fabs(v / tol) < 10e-2);
+}
+
+// Htools.c:138-158 pinvJ + :160-198 HDs for one correspondence (H column-major, maps image 2 -> image 1)
+__device__ __forceinline__ double sampson(const double* H, const double* u) {
+  const double x1 = u[0], y1 = u[1], x2 = u[3], y2 = u[4], w2 = u[5];
+  double r1 = 0, r2 = 0;
+  r1 += H[0] * x2; r1 += H[2] * (-x1 * x2); r1 += H[3] * y2; r1 += H[5] * (-x1 * y2); r1 += H[6] * w2; r1 += H[8] * (-x1 * w2);
+  r2 += H[1] * x2; r2 += H[2] * (-y1 * x2); r2 += H[4] * y2; r2 += H[5] * (-y1 * y2); r2 += H[7] * w2; r2 += H[8] * (-y1 * w2);
+  const double a = H[0] - H[2] * x1, b = H[3] - H[5] * x1, c = -H[8] - H[2] * x2 - H[5] * y2;
+  const double d = H[1] - H[2] * y1, e = H[4] - H[5] * y1;
+  const double a2 = a * a, b2 = b * b, c2 = c * c, d2 = d * d, e2 = e * e;
+  const double c2pd2 = c2 + d2, ab = a * b, de = d * e;
+  const double Q = c * (c2pd2 + e2);
+  double pJ[8];
+  pJ[0] = -b * de + a * (c2 + e2);
+  pJ[1] = b * c2pd2 - a * de;
+  pJ[2] = Q;
+  pJ[3] = -c * (a * d + b * e);
+  pJ[4] = d * (b2 + c2) - ab * e;
+  pJ[5] = -ab * d + e * (a2 + c2);
+  pJ[6] = pJ[3];
+  pJ[7] = c * (a2 + b2 + c2);
+  const double N = a * pJ[0] + b * pJ[1] + c * pJ[2];
+  double p = 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    double t = (pJ[j] / N) * r1 + (pJ[j + 4] / N) * r2;
+    p += t * t;
+  }
+  return p;
+}
+
+__device__ __forceinline__ bool inv3(const double* A, double* R) {
+  const double c0 = A[4] * A[8] - A[5] * A[7], c1 = A[5] * A[6] - A[3] * A[8], c2 = A[3] * A[7] - A[4] * A[6];
+  const double det = A[0] * c0 + A[1] * c1 + A[2] * c2;
+  if (det == 0 || !isfinite(det)) return false;
+  const double id = 1.0 / det;
+  R[0] = c0 * id; R[1] = (A[2] * A[7] - A[1] * A[8]) * id; R[2] = (A[1] * A[5] - A[2] * A[4]) * id;
+  R[3] = c1 * id; R[4] = (A[0] * A[8] - A[2] * A[6]) * id; R[5] = (A[2] * A[3] - A[0] * A[5]) * id;
+  R[6] = c2 * id; R[7] = (A[1] * A[6] - A[0] * A[7]) * id; R[8] = (A[0] * A[4] - A[1] * A[3]) * id;
+  return true;
+}
+
+// Htools.c:201-242 HDsSym for one correspondence; Hm = row-major 2->1 map, H1 = its inverse
+__device__ __forceinline__ double sym_err(const double* Hm, const double* H1, const double* u) {
+  const double a = H1[6] * u[0] + H1[7] * u[1] + H1[8];
+  const double b = Hm[6] * u[3] + Hm[7] * u[4] + Hm[8];
+  double xa = (H1[0] * u[0] + H1[1] * u[1] + H1[2]) / a, ya = (H1[3] * u[0] + H1[4] * u[1] + H1[5]) / a;
+  double xd = u[3] - xa, yd = u[4] - ya;
+  const double d1 = xd * xd + yd * yd;
+  xa = (Hm[0] * u[3] + Hm[1] * u[4] + Hm[2]) / b; ya = (Hm[3] * u[3] + Hm[4] * u[4] + Hm[5]) / b;
+  xd = u[0] - xa; yd = u[1] - ya;
+  return d1 + (xd * xd + yd * yd);
+}
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// utools.c:97-167 nullspace() on the 9x9 (8 rows + zero row) system; returns the nullity and, when it is 1,
+// the null vector in sol[9].
+__device__ int nullspace9(double* m, double* sol) {
+  const int n = 9;
+  int nopivot[9], pivotc[9], nnp = 0, npv = 0;
+  const double tol = 1e-12;
+  int i = 0;
+  for (int j = 0; j < n; j++) {
+    double pivot = i < n ? fabs(m[n * i + j]) : 0.0;
+    int mx = i;
+    for (int k = i + 1; k < n; k++) { double t = fabs(m[n * k + j]); if (pivot < t) { pivot = t; mx = k; } }
+    if (pivot < tol) {
+      nopivot[nnp++] = j;
+      for (int k = i; k < n; k++) m[n * k + j] = 0;
+    } else {
+      pivotc[npv++] = j;
+      for (int k = j; k < n; k++) { double t = m[i * n + k]; m[i * n + k] = m[mx * n + k]; m[mx * n + k] = t; }
+      pivot = m[i * n + j];
+      for (int k = j; k < n; k++) m[i * n + k] /= pivot;
+      for (int k = 0; k < i; k++) { double p = -m[k * n + j]; for (int l = j; l < n; l++) m[k * n + l] += p * m[i * n + l]; }
+      for (int k = i + 1; k < n; k++) { double p = m[k * n + j]; for (int l = j; l < n; l++) m[k * n + l] -= p * m[i * n + l]; }
+      i++;
+    }
+  }
+  if (nnp == 1) {
+    const int j = nopivot[0];
+    for (int l = 0; l < n - 1; l++) sol[pivotc[l]] = -m[l * n + j];
+    sol[j] = 1;
+  }
+  return nnp;
+}
+
+// two DLT rows of one correspondence (lin_hg, Htools.c:19-57), h stored column-major
+__device__ __forceinline__ void dlt_rows(const double* u, double* r1, double* r2) {
+  const double x1 = u[0], y1 = u[1], x2 = u[3], y2 = u[4], w2 = u[5];
+  r1[0] = x2; r1[1] = 0; r1[2] = -x1 * x2; r1[3] = y2; r1[4] = 0; r1[5] = -x1 * y2; r1[6] = w2; r1[7] = 0; r1[8] = -x1 * w2;
+  r2[0] = 0; r2[1] = x2; r2[2] = -y1 * x2; r2[3] = 0; r2[4] = y2; r2[5] = -y1 * y2; r2[6] = 0; r2[7] = w2; r2[8] = -y1 * w2;
+}
+
+// Htools.c:526-551 all_Hori_valid
+__device__ __forceinline__ void cross3(double* o, const double* a, const double* b) {
+  o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ bool all_Hori_valid(const double* us, const int* idx) {
+  const double *a = us + 6 * idx[0], *b = us + 6 * idx[1], *c = us + 6 * idx[2], *d = us + 6 * idx[3];
+  double p[3], q[3];
+  cross3(p, a, b); cross3(q, a + 3, b + 3);
+  if ((p[0] * c[0] + p[1] * c[1] + p[2] * c[2]) * (q[0] * c[3] + q[1] * c[4] + q[2] * c[5]) < 0) return false;
+  if ((p[0] * d[0] + p[1] * d[1] + p[2] * d[2]) * (q[0] * d[3] + q[1] * d[4] + q[2] * d[5]) < 0) return false;
+  cross3(p, c, d); cross3(q, c + 3, d + 3);
+  if ((p[0] * a[0] + p[1] * a[1] + p[2] * a[2]) * (q[0] * a[3] + q[1] * a[4] + q[2] * a[5]) < 0) return false;
+  if ((p[0] * b[0] + p[1] * b[1] + p[2] * b[2]) * (q[0] * b[3] + q[1] * b[4] + q[2] * b[5]) < 0) return false;
+  return true;
+}
+
+// minimal solver: H (column-major) from 4 correspondences; false when the null space is not 1-D
+__device__ bool h_from_4(const double* u, const int* idx, double* h) {
+  double M[81];
+  for (int i = 0; i < 4; i++) dlt_rows(u + 6 * idx[i], M + 18 * i, M + 18 * i + 9);
+  for (int i = 72; i < 81; i++) M[i] = 0.0;
+  return nullspace9(M, h) == 1;
+}
+
+// warp-wide: Sampson errors of all T correspondences under H into d[] (optional) + MSAC score at th
+__device__ void score_all(const double* __restrict__ u, int T, const double* H, double th, double* d, int lane, int* I, double* J) {
+  int ci = 0;
+  double cj = 0;
+  for (int j = lane; j < T; j += 32) {
+    const double e = sampson(H, u + 6 * j);
+    if (d) d[j] = e;
+    if (e <= th) ci++;
+    cj += truncQuad(e, th);
+  }
+  *I = warp_sum_i(ci);
+  *J = warp_sum_d(cj);
+}
+
+// warp-wide: indices j (ascending) with d[j] <= th into idx[]; returns the count  (rtools.c inlidxs)
+__device__ int compact_inliers(const double* d, int T, double th, int* idx, int lane) {
+  int n = 0;
+  for (int base = 0; base < T; base += 32) {
+    const int j = base + lane;
+    const bool in = j < T && d[j] <= th;
+    const unsigned m = __ballot_sync(0xffffffffu, in);
+    if (in) idx[n + __popc(m & ((1u << lane) - 1))] = j;
+    n += __popc(m);
+  }
+  __syncwarp();
+  return n;
+}
+
+// warp-wide normalised-DLT least squares (u2h, Htools.c:100-132: normu + lin_hgN + cov_mat + smallest
+// eigenvector + denormH).  idx[0..n) selects the correspondences.  n < 4 leaves H untouched.
+__device__ void lsq_h(const double* __restrict__ u, const int* idx, int n, double* H, int lane) {
+  if (n < 4) return;
+  if (n == 4) {
+    int id4[4] = {idx[0], idx[1], idx[2], idx[3]};
+    double h[9];
+    for (int i = 0; i < 9; i++) h[i] = H[i];
+    h_from_4(u, id4, h);   // like u2h's len == 4 branch; a degenerate sample keeps the previous H
+    for (int i = 0; i < 9; i++) H[i] = h[i];
+    return;
+  }
+  // normu (utools.c:7-50)
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  for (int k = lane; k < n; k += 32) { const double* p = u + 6 * idx[k]; s0 += p[0]; s1 += p[1]; s2 += p[3]; s3 += p[4]; }
+  const double m1x = warp_sum_d(s0) / n, m1y = warp_sum_d(s1) / n, m2x = warp_sum_d(s2) / n, m2y = warp_sum_d(s3) / n;
+  double q1 = 0, q2 = 0;
+  for (int k = lane; k < n; k += 32) {
+    const double* p = u + 6 * idx[k];
+    double a = p[0] - m1x, b = p[1] - m1y;
+    q1 += sqrt(a * a + b * b);
+    a = p[3] - m2x; b = p[4] - m2y;
+    q2 += sqrt(a * a + b * b);
+  }
+  q1 = warp_sum_d(q1); q2 = warp_sum_d(q2);
+  double A1[3] = {q1, m1x, m1y}, A2[3] = {q2, m2x, m2y};
+  if (A1[0] != 0) A1[0] = n * sqrt(2.0) / A1[0];
+  if (A2[0] != 0) A2[0] = n * sqrt(2.0) / A2[0];
+  A1[1] *= -A1[0]; A1[2] *= -A1[0]; A2[1] *= -A2[0]; A2[2] *= -A2[0];
+  // normal matrix C = Z^T Z of the 2n x 9 design matrix (lin_hgN + cov_mat), lower triangle
+  double C[45];
+#pragma unroll
+  for (int i = 0; i < 45; i++) C[i] = 0;
+  for (int k = lane; k < n; k += 32) {
+    const double* p = u + 6 * idx[k];
+    const double a0 = p[0] * A1[0] + A1[1], a1 = p[1] * A1[0] + A1[2];
+    const double b0 = p[3] * A2[0] + A2[1], b1 = p[4] * A2[0] + A2[2], b2 = 1;
+    const double r1[9] = {b0, 0, -a0 * b0, b1, 0, -a0 * b1, b2, 0, -a0 * b2};
+    const double r2[9] = {0, b0, -a1 * b0, 0, b1, -a1 * b1, 0, b2, -a1 * b2};
+    int t = 0;
+#pragma unroll
+    for (int i = 0; i < 9; i++)
+#pragma unroll
+      for (int j = 0; j <= i; j++, t++) C[t] += r1[i] * r1[j] + r2[i] * r2[j];
+  }
+#pragma unroll
+  for (int i = 0; i < 45; i++) C[i] = warp_sum_d(C[i]);
+  // smallest eigenvector by inverse iteration on the Cholesky factor (every lane redundantly: deterministic)
+  double L[45];
+  double maxd = 0;
+  { int t = 0; for (int i = 0; i < 9; i++) { t += i; if (C[t] > maxd) maxd = C[t]; t++; } }
+  const double ridge = 1e-13 * maxd, tiny = 1e-30 * maxd + 1e-300;
+  for (int i = 0; i < 9; i++) {
+    for (int j = 0; j <= i; j++) {
+      double s = C[i * (i + 1) / 2 + j] + (i == j ? ridge : 0.0);
+      for (int k = 0; k < j; k++) s -= L[i * (i + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
+      if (i == j) L[i * (i + 1) / 2 + i] = sqrt(s > tiny ? s : tiny);
+      else L[i * (i + 1) / 2 + j] = s / L[j * (j + 1) / 2 + j];
+    }
+  }
+  double x[9];
+  for (int i = 0; i < 9; i++) x[i] = 1.0 + 0.1 * i;
+  for (int it = 0; it < 10; it++) {
+    for (int i = 0; i < 9; i++) {           // L y = x
+      double s = x[i];
+      for (int k = 0; k < i; k++) s -= L[i * (i + 1) / 2 + k] * x[k];
+      x[i] = s / L[i * (i + 1) / 2 + i];
+    }
+    for (int i = 8; i >= 0; i--) {          // L^T z = y
+      double s = x[i];
+      for (int k = i + 1; k < 9; k++) s -= L[k * (k + 1) / 2 + i] * x[k];
+      x[i] = s / L[i * (i + 1) / 2 + i];
+    }
+    double nrm = 0;
+    for (int i = 0; i < 9; i++) nrm += x[i] * x[i];
+    nrm = sqrt(nrm);
+    if (!(nrm > 0) || !isfinite(nrm)) return;   // keep the previous H
+    for (int i = 0; i < 9; i++) x[i] /= nrm;
+  }
+  // denormH (utools.c:70-90)
+  double* F = x;
+  double r = A2[0], xx = A2[1], yy = A2[2];
+  F[6] += xx * F[0] + yy * F[3];
+  F[7] += xx * F[1] + yy * F[4];
+  F[8] += xx * F[2] + yy * F[5];
+  F[0] *= r; F[1] *= r; F[2] *= r; F[3] *= r; F[4] *= r; F[5] *= r;
+  r = 1 / A1[0]; xx = -A1[1] * r; yy = -A1[2] * r;
+  for (int i = 0; i < 9; i += 3) {
+    F[i] = r * F[i] + xx * F[i + 2];
+    F[i + 1] = r * F[i + 1] + yy * F[i + 2];
+  }
+  for (int i = 0; i < 9; i++) H[i] = F[i];
+}
+
+// ---- hypothesis generation + scoring: one warp per hypothesis -------------------------------------------
+__global__ void __launch_bounds__(256)
+k_rs_hyp(const double* __restrict__ u, int T, double th, unsigned long long seed, int base, int nhyp, HypOut* __restrict__ out) {
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (w >= nhyp) return;
+  const unsigned long long hid = (unsigned long long)(base + w);
+  // 4 distinct indices: partial Fisher-Yates over a virtual pool (rtools.c sample()), counter-based draws
+  int idx[4], pos[4], val[4];
+  for (int i = 0; i < 4; i++) {
+    const int s = (int)rs_rand(seed, hid, i, (unsigned)(T - i)), last = T - i - 1;
+    int vs = s, vl = last;
+    for (int k = 0; k < i; k++) { if (pos[k] == s) vs = val[k]; if (pos[k] == last) vl = val[k]; }
+    idx[i] = vs;
+    pos[i] = s; val[i] = vl;
+  }
+  double h[9];
+  int flag = 0;
+  if (!all_Hori_valid(u, idx)) flag = 1;
+  else if (!h_from_4(u, idx, h) || !det_ok(h)) flag = 2;
+  int I = 0;
+  double J = 0;
+  if (flag == 0) score_all(u, T, h, th, nullptr, lane, &I, &J);
+  if (lane == 0) {
+    HypOut o;
+    for (int i = 0; i < 9; i++) o.H[i] = flag == 0 ? h[i] : 0.0;
+    o.I = I; o.J = J; o.flag = flag;
+    out[w] = o;
+  }
+}
+
+__device__ bool sym_check_ok(const double* __restrict__ u, int T, const double* H, double th, int lane) {
+  // exp_ranH.c:905-947: at least MIN_GOOD_SYM_PTS+1 correspondences within CHECK_COEF*th symmetric transfer error
+  double Hm[9] = {H[0], H[3], H[6], H[1], H[4], H[7], H[2], H[5], H[8]}, H1[9];
+  if (!inv3(Hm, H1)) return false;
+  int c = 0;
+  for (int j = lane; j < T; j += 32) if (sym_err(Hm, H1, u + 6 * j) <= CHECK_COEF * th) c++;
+  return warp_sum_i(c) > MIN_GOOD_SYM_PTS;
+}
+
+// rtools.c:196-224
+__device__ int nsamples(int ninl, int ptNum, int samsiz, double conf) {
+  double a = 1, b = 1;
+  for (int i = 0; i < samsiz; i++) { a *= ninl - i; b *= ptNum - i; }
+  a = a / b;
+  if (a < 2.2204e-16) return 1000000;
+  a = 1 - a;
+  if (a < 2.2204e-16) return 1;
+  b = log(1 - conf) / log(a);
+  if (b > 1000000) return 1000000;
+  return (int)ceil(b);
+}
+
+// exp_iterHcustom (exp_ranH.c:617-737) for one inner sample, warp-wide.  d0 = errors of the start model h.
+// Returns the best (I,J) seen and leaves the matching model in Hbest.
+__device__ void lo_iterate(const double* __restrict__ u, int T, double th, double* h, const double* d0, double* d, int* idx,
+                           int lane, int* bestI, double* bestJ, double* Hbest) {
+  int mI = 0; double mJ = 0;
+  for (int j = lane; j < T; j += 32) { if (d0[j] <= th) mI++; mJ += truncQuad(d0[j], th); }
+  mI = warp_sum_i(mI); mJ = warp_sum_d(mJ);
+  *bestI = 0; *bestJ = 0;
+  if (mI < 4) return;
+  for (int i = 0; i < 9; i++) Hbest[i] = h[i];
+  int n = compact_inliers(d0, T, th * MWM, idx, lane);
+  lsq_h(u, idx, n, h, lane);
+  double ths = TC * th;
+  const double dth = (ths - th) / ILSQ_ITERS;
+  for (int it = 0; it < ILSQ_ITERS; it++) {
+    int sI; double sJ;
+    score_all(u, T, h, th, d, lane, &sI, &sJ);
+    __syncwarp();
+    n = compact_inliers(d, T, ths * MWM, idx, lane);
+    if (mJ < sJ) { mJ = sJ; mI = sI; for (int i = 0; i < 9; i++) Hbest[i] = h[i]; }
+    if (n < 4) { *bestI = mI; *bestJ = mJ; return; }
+    lsq_h(u, idx, n, h, lane);
+    ths -= dth;
+  }
+  int sI; double sJ;
+  score_all(u, T, h, th, nullptr, lane, &sI, &sJ);
+  if (mJ < sJ) { mJ = sJ; mI = sI; for (int i = 0; i < 9; i++) Hbest[i] = h[i]; }
+  *bestI = mI; *bestJ = mJ;
+}
+
+// ---- per-batch update: best sample, symmetric check, local optimisation, stopping rule -------------------
+// scratch: per warp w (12 warps): dbuf[w][T] doubles, dbuf2[w][T], ibuf[w][T] ints
+__global__ void __launch_bounds__(384)
+k_rs_update(const double* __restrict__ u, int T, double th, double conf, int do_sym, unsigned long long seed,
+            const HypOut* __restrict__ hyp, int nhyp, int force_lo, RsState* st, double* dscr, int* iscr) {
+  __shared__ double sJ[12]; __shared__ int sIdx[12];
+  __shared__ double loJ[LO_REPS]; __shared__ int loI[LO_REPS]; __shared__ double loH[LO_REPS][9];
+  __shared__ double h0[9]; __shared__ int n0_s; __shared__ int run_lo_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  double* dW = dscr + (size_t)warp * 2 * T;       // per-warp error buffers
+  int* iW = iscr + (size_t)warp * T;
+  double* dS = dscr + (size_t)nw * 2 * T;          // errors of the LO start model (shared by all warps)
+  int* inl0 = iscr + (size_t)nw * T;               // its inliers at th
+
+  // (a) best hypothesis of the batch: max J, lowest index on ties
+  double bj = -1; int bi = -1, rej = 0;
+  for (int k = threadIdx.x; k < nhyp; k += blockDim.x) {
+    const int f = hyp[k].flag;
+    if (f == 1) rej++;
+    if (f == 0 && (hyp[k].J > bj)) { bj = hyp[k].J; bi = k; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    double oj = __shfl_xor_sync(0xffffffffu, bj, o); int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (oi >= 0 && (oj > bj || (oj == bj && (bi < 0 || oi < bi)))) { bj = oj; bi = oi; }
+  }
+  rej = warp_sum_i(rej);
+  if (lane == 0) { sJ[warp] = bj; sIdx[warp] = bi; if (rej) atomicAdd(&st->oc_rejects, rej); }
+  __syncthreads();
+  bj = -1; bi = -1;
+  for (int k = 0; k < nw; k++) if (sIdx[k] >= 0 && (sJ[k] > bj || (sJ[k] == bj && sIdx[k] < bi))) { bj = sJ[k]; bi = sIdx[k]; }
+
+  // (b) warp 0: sequential bookkeeping of exp_ranH.c:903-961 for the batch's best sample
+  if (warp == 0) {
+    // snapshot the state before any lane writes it (lanes of a warp need not run in lockstep)
+    const double curJ = st->J;
+    double curJs = st->Js;
+    int have = st->have_sample, curIs = st->Is;
+    const int no_sam = st->no_sam, lo_runs = st->lo_runs;
+    __syncwarp();
+    bool run_lo = false;
+    if (bi >= 0) {
+      double h[9];
+      for (int i = 0; i < 9; i++) h[i] = hyp[bi].H[i];
+      const int I = hyp[bi].I;
+      if (curJ < bj) {
+        const bool ok = !do_sym || sym_check_ok(u, T, h, th, lane);
+        if (ok && lane == 0) { for (int i = 0; i < 9; i++) st->H[i] = h[i]; st->J = bj; st->I = I; }
+      }
+      if (!have || curJs < bj) {
+        if (lane == 0) { for (int i = 0; i < 9; i++) st->Hs[i] = h[i]; st->Js = bj; st->Is = I; st->have_sample = 1; }
+        have = 1; curJs = bj; curIs = I;
+        run_lo = no_sam + nhyp > ITER_SAM;
+      }
+    }
+    if (no_sam + nhyp >= ITER_SAM && lo_runs == 0 && have && curIs > 4) run_lo = true;
+    if (force_lo) run_lo = have && lo_runs == 0;
+    __syncwarp();
+    if (run_lo) {
+      // LSQ on the TC*th*MWM band of the best SAMPLE, then its inliers at th (exp_ranH.c:997-1012)
+      double h[9];
+      for (int i = 0; i < 9; i++) h[i] = st->Hs[i];
+      int I; double J;
+      score_all(u, T, h, th, dW, lane, &I, &J);
+      __syncwarp();
+      int n = compact_inliers(dW, T, TC * th * MWM, iW, lane);
+      lsq_h(u, iW, n, h, lane);
+      score_all(u, T, h, th, dS, lane, &I, &J);
+      __syncwarp();
+      n = compact_inliers(dS, T, th, inl0, lane);
+      if (lane == 0) { for (int i = 0; i < 9; i++) h0[i] = h[i]; n0_s = n; st->lo_runs = lo_runs + 1; }
+    }
+    if (lane == 0) run_lo_s = run_lo ? 1 : 0;
+  }
+  __syncthreads();
+
+  // (c) inner RANSAC (exp_inHranicustom, exp_ranH.c:741-793): LO_REPS samples, one warp each
+  const bool run_lo = run_lo_s != 0;
+  const int n0 = run_lo ? n0_s : 0;
+  if (run_lo && warp < LO_REPS) {
+    int bI = 0; double bJ = 0; double Hb[9];
+    for (int i = 0; i < 9; i++) Hb[i] = h0[i];
+    if (n0 >= 8) {
+      int ssiz = n0 / 2; if (ssiz > 12) ssiz = 12;
+      // randsubset (rtools.c:25-39) on a private copy of the inlier list
+      for (int k = lane; k < n0; k += 32) iW[k] = inl0[k];
+      __syncwarp();
+      if (lane == 0) {
+        const unsigned long long stream = 0x4C4F000000000000ull + (unsigned long long)st->lo_runs * 64 + warp;
+        for (int i = 0; i < ssiz; i++) {
+          const int s = (int)rs_rand(seed, stream, i, (unsigned)(n0 - i)), j = n0 - i - 1;
+          const int q = iW[s]; iW[s] = iW[j]; iW[j] = q;
+        }
+      }
+      __syncwarp();
+      double h[9];
+      for (int i = 0; i < 9; i++) h[i] = h0[i];
+      lsq_h(u, iW + n0 - ssiz, ssiz, h, lane);
+      int I; double J;
+      score_all(u, T, h, th, dW, lane, &I, &J);
+      __syncwarp();
+      lo_iterate(u, T, th, h, dW, dW + T, iW, lane, &bI, &bJ, Hb);
+    }
+    if (lane == 0) { loI[warp] = bI; loJ[warp] = bJ; for (int i = 0; i < 9; i++) loH[warp][i] = Hb[i]; }
+  }
+  __syncthreads();
+
+  // (d) warp 0: take the best inner sample (first on ties), accept against maxS, update the stopping rule
+  if (warp == 0) {
+    if (run_lo) {
+      int best = -1; double bJ = 0; int bI = 0;
+      for (int k = 0; k < LO_REPS; k++) if (bJ < loJ[k]) { bJ = loJ[k]; bI = loI[k]; best = k; }
+      const double curJ = st->J;
+      __syncwarp();
+      if (best >= 0 && curJ < bJ) {
+        double h[9];
+        for (int i = 0; i < 9; i++) h[i] = loH[best][i];
+        if (det_ok(h) && (!do_sym || sym_check_ok(u, T, h, th, lane))) {
+          if (lane == 0) { for (int i = 0; i < 9; i++) st->H[i] = h[i]; st->J = bJ; st->I = bI; }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      st->no_sam += nhyp;
+      if (st->I > 0) { const int ns = nsamples(st->I + 1, T, 4, conf); if (ns < st->max_sam) st->max_sam = ns; }
+      st->done = st->no_sam >= st->max_sam;
+    }
+  }
+}
+
+// final errors of the accepted model -> inlier mask (exp_ranH.c:1207-1212)
+__global__ void k_rs_final(const double* __restrict__ u, int T, double th, const RsState* st, unsigned char* inl) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= T) return;
+  inl[j] = (st->I > 0 && sampson(st->H, u + 6 * j) <= th) ? 1 : 0;
+}
+
+}  // namespace
+
+// Device part: correspondences d_u (T x 6 doubles) already on the device.  On return (after a stream sync
+// inside -- the stopping rule is data dependent) ctx->rs_buf holds the RsState followed by the inlier mask.
+int mg_ransac_run(modsgpu_ctx* ctx, const double* d_u, int T, const modsgpu_ransac_params* p,
+                  double* H, unsigned char* inl, modsgpu_ransac_result* res) {
+  const int NW = 12;
+  size_t off_hyp = 256, off_d = off_hyp + sizeof(HypOut) * RS_MAX_B;
+  size_t off_i = off_d + sizeof(double) * (size_t)(2 * NW + 1) * T;
+  size_t off_inl = off_i + sizeof(int) * (size_t)(NW + 1) * T;
+  size_t total = off_inl + T + 64;
+  MG_CUDA(ctx, ctx->rs_buf.ensure(total));
+  uint8_t* base = ctx->rs_buf.as<uint8_t>();
+  RsState* st = reinterpret_cast<RsState*>(base);
+  HypOut* hyp = reinterpret_cast<HypOut*>(base + off_hyp);
+  double* dscr = reinterpret_cast<double*>(base + off_d);
+  int* iscr = reinterpret_cast<int*>(base + off_i);
+  unsigned char* dinl = base + off_inl;
+  MG_CUDA(ctx, ctx->h_stage.ensure(sizeof(RsState) + T + 64));
+  RsState* hs = ctx->h_stage.as<RsState>();
+  memset(hs, 0, sizeof(RsState));
+  hs->max_sam = p->max_samples;
+  MG_CUDA(ctx, cudaMemcpyAsync(st, hs, sizeof(RsState), cudaMemcpyHostToDevice, ctx->stream));
+  MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // hs is reused as the read-back buffer below
+  int basei = 0, batch = 0;
+  for (;;) {
+    int B = batch == 0 ? 512 : (batch == 1 ? 1024 : RS_MAX_B);
+    MG_PROF(ctx, "k_rs_hyp", 2, (double)B);
+    k_rs_hyp<<<ceil_div(B, 8), 256, 0, ctx->stream>>>(d_u, T, p->th, p->seed, basei, B, hyp);
+    MG_LAUNCHED(ctx);
+    MG_PROF(ctx, "k_rs_update", 2, (double)T);
+    k_rs_update<<<1, 32 * NW, 0, ctx->stream>>>(d_u, T, p->th, p->conf, p->do_sym_check, p->seed, hyp, B, 0, st, dscr, iscr);
+    MG_LAUNCHED(ctx);
+    MG_CUDA(ctx, cudaMemcpyAsync(hs, st, sizeof(RsState), cudaMemcpyDeviceToHost, ctx->stream));
+    MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    basei += B; batch++;
+    if (hs->done) break;
+  }
+  if (hs->lo_runs == 0) {   // exp_ranH.c:1085-1197: "If there were no LOs, do at least one NOW"
+    k_rs_update<<<1, 32 * NW, 0, ctx->stream>>>(d_u, T, p->th, p->conf, p->do_sym_check, p->seed, hyp, 0, 1, st, dscr, iscr);
+    MG_LAUNCHED(ctx);
+  }
+  k_rs_final<<<ceil_div(T, 256), 256, 0, ctx->stream>>>(d_u, T, p->th, st, dinl);
+  MG_LAUNCHED(ctx);
+  unsigned char* hinl = reinterpret_cast<unsigned char*>(hs + 1);
+  MG_CUDA(ctx, cudaMemcpyAsync(hs, st, sizeof(RsState), cudaMemcpyDeviceToHost, ctx->stream));
+  MG_CUDA(ctx, cudaMemcpyAsync(hinl, dinl, T, cudaMemcpyDeviceToHost, ctx->stream));
+  MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < 9; i++) H[i] = hs->H[i];
+  memcpy(inl, hinl, T);
+  if (res) { res->n_inliers = hs->I; res->J = hs->J; res->samples = hs->no_sam; res->lo_runs = hs->lo_runs; res->oc_rejects = hs->oc_rejects; }
+  return 0;
+}
+
 extern "C" int modsgpu_ransac_H(modsgpu_ctx* ctx, const double* u, int T, const modsgpu_ransac_params* p,
                                 double* H, unsigned char* inl, modsgpu_ransac_result* res) {
-  (void)u; (void)T; (void)p; (void)H; (void)inl; (void)res;
-  if (!ctx) return MODSGPU_EINVAL;
-  MG_FAIL(ctx, MODSGPU_ESTATE, "modsgpu_ransac_H: not built yet");
+  if (!ctx || !p || !H || T < 0 || (T > 0 && (!u || !inl))) return MODSGPU_EINVAL;
+  if (mg_begin(ctx)) return MODSGPU_ECUDA;
+  if (res) memset(res, 0, sizeof(*res));
+  for (int i = 0; i < 9; i++) H[i] = 0;
+  if (T < 4) {   // fewer than a minimal sample: no model (LORANSACFiltering requires >= MinimumSamples)
+    for (int i = 0; i < T; i++) inl[i] = 0;
+    return mg_end(ctx) ? MODSGPU_ECUDA : 0;
+  }
+  MG_CUDA(ctx, ctx->io_a.ensure((size_t)T * 48));
+  MG_CUDA(ctx, cudaMemcpyAsync(ctx->io_a.p, u, (size_t)T * 48, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = mg_ransac_run(ctx, ctx->io_a.as<double>(), T, p, H, inl, res);
+  if (rc) return rc;
+  return mg_end(ctx) ? MODSGPU_ECUDA : 0;
 }

@@ -288,12 +288,17 @@ int mg_sample_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
     attr_set = true;
   }
   const PatchMeta* dm = ctx->smp_meta.as<PatchMeta>();
+  double bytes_small = 0, bytes_large = 0;   // algorithmic: R*R*4 read + ps*ps written per region
+  for (const PatchMeta& m : small) bytes_small += (double)m.R * m.R * 4.0 + (double)ps * ps;
+  for (const PatchMeta& m : large) bytes_large += (double)m.R * m.R * 4.0 + (double)ps * ps;
   if (!small.empty()) {
+    MG_PROF(ctx, "k_sample<small>", 0, bytes_small);
     k_sample<false><<<(unsigned)small.size(), 128, SMEM_SMALL, ctx->stream>>>(
         img->d, img->w, img->h, dm, ctx->smp_taps.as<float>(), nullptr, d_out, ps);
     MG_LAUNCHED(ctx);
   }
   if (!large.empty()) {
+    MG_PROF(ctx, "k_sample<large>", 0, bytes_large);
     k_sample<true><<<(unsigned)large.size(), 256, SMEM_LARGE, ctx->stream>>>(
         img->d, img->w, img->h, dm + small.size(), ctx->smp_taps.as<float>(), ctx->smp_scratch.as<float>(), d_out, ps);
     MG_LAUNCHED(ctx);

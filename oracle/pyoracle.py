@@ -210,6 +210,10 @@ def _load_lapack():
     """dsyev_/dgesvd_ come from the OpenBLAS bundled with the cv2 wheel of this image
     (SURVEY §8c.1).  Loaded RTLD_GLOBAL so libdegensac_ref.so resolves against it."""
     import importlib.util
+    try:
+        import cv2  # noqa: F401  -- pulls in the wheel's bundled libgfortran/libquadmath in the right order
+    except ImportError:
+        pass
     spec = importlib.util.find_spec("cv2")
     base = os.path.dirname(os.path.dirname(spec.origin))
     cands = glob.glob(os.path.join(base, "opencv_python_headless.libs", "libopenblas*.so*")) + \
@@ -218,7 +222,7 @@ def _load_lapack():
     # gfortran runtime deps of that OpenBLAS live in the same directory
     for c in cands:
         d = os.path.dirname(c)
-        for dep in sorted(glob.glob(os.path.join(d, "libgfortran*.so*")) + glob.glob(os.path.join(d, "libquadmath*.so*"))):
+        for dep in sorted(glob.glob(os.path.join(d, "libquadmath*.so*"))) + sorted(glob.glob(os.path.join(d, "libgfortran*.so*"))):
             try:
                 C.CDLL(dep, mode=C.RTLD_GLOBAL)
             except OSError:

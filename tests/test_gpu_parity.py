@@ -274,3 +274,98 @@ def test_deep_pipeline_stagewise(mg, oracle, synth_pair):
     p = np.c_[x1, np.ones(len(x1))] @ H.T
     err = np.linalg.norm(p[:, :2] / p[:, 2:3] - x2, axis=1)
     assert (err < 3).mean() > 0.5
+
+
+# ------------------------------------------------------------------------------------------ LO-RANSAC
+def _corr_set(seed, T, n_in, noise=0.7):
+    rng = np.random.RandomState(seed)
+    Ht = np.array([[0.9, -0.3, 40.0], [0.25, 1.05, -20.0], [2e-4, 1e-5, 1.0]])
+    x1 = np.c_[rng.uniform(20, 1000, T), rng.uniform(20, 740, T), np.ones(T)]
+    p = x1 @ Ht.T
+    x2 = p / p[:, 2:3]
+    x2[:, :2] += rng.normal(0, noise, (T, 2))
+    x2[n_in:, :2] = np.c_[rng.uniform(0, 1024, T - n_in), rng.uniform(0, 768, T - n_in)]
+    return np.ascontiguousarray(np.c_[x1, x2]), Ht
+
+
+def _transfer_err(Hdeg, u):
+    """degensac convention: column-major H maps image 2 -> image 1"""
+    Hm = Hdeg.reshape(3, 3).T
+    p = u[:, 3:6] @ Hm.T
+    return np.linalg.norm(p[:, :2] / p[:, 2:3] - u[:, :2], axis=1)
+
+
+@pytest.mark.parametrize("seed,T,n_in", [(5, 260, 150), (6, 300, 90), (7, 120, 100), (8, 40, 30), (9, 600, 200), (10, 1000, 150)])
+def test_ransac_vs_reference_degensac(mg, oracle, seed, T, n_in):
+    """The batched GPU LO-RANSAC against the reference's own exp_ransacHcustom (oracle/_ref, time() pinned) on
+    the same correspondences: both are randomised, so parity = the same consensus set (Jaccard >= 0.95, the
+    true inliers recovered) and the same homography (transfer error of the true inliers < 2 px)."""
+    u, _ = _corr_set(seed, T, n_in)
+    g = mg.ransac_H(u, seed=1000 + seed)
+    assert g["inl"][:n_in].mean() > 0.93 and g["inl"][n_in:].sum() <= max(3, 0.02 * T)
+    assert np.median(_transfer_err(g["H"], u[:n_in])) < 2.0
+    assert g["I"] == int(g["inl"].sum()) and g["lo_count"] >= 1 and g["samples"] >= 50
+    if oracle.ref_available():
+        r = oracle.ref_ransac_H(u, th=16.0, seed_time=12345)
+        a, b = g["inl"].astype(bool), r["inl"].astype(bool)
+        assert (a & b).sum() / max((a | b).sum(), 1) >= 0.95, ((a & b).sum(), (a | b).sum())
+        assert g["I"] >= r["I"] - 3
+        assert np.abs(_transfer_err(g["H"], u[:n_in]) - _transfer_err(r["H"], u[:n_in])).max() < 1.0
+
+
+def test_ransac_golden_fixture(mg):
+    z = np.load(os.path.join(GOLD, "ransac_ref.npz"))
+    g = mg.ransac_H(z["u"], seed=77)
+    a, b = g["inl"].astype(bool), z["inl"].astype(bool)
+    assert (a & b).sum() / (a | b).sum() >= 0.95
+    assert abs(g["I"] - int(z["I"])) <= 3
+
+
+def test_ransac_reproducible_and_edge_cases(mg):
+    u, _ = _corr_set(3, 200, 120)
+    g1, g2 = mg.ransac_H(u, seed=9), mg.ransac_H(u, seed=9)
+    assert np.array_equal(g1["H"], g2["H"]) and np.array_equal(g1["inl"], g2["inl"]) and g1["samples"] == g2["samples"]
+    g3 = mg.ransac_H(u, seed=10)
+    assert (g3["inl"] == g1["inl"]).mean() > 0.97
+    # fewer than a minimal sample
+    g = mg.ransac_H(u[:3])
+    assert g["I"] == 0 and g["inl"].sum() == 0
+    # pure outliers: nothing sensible may be reported as a large consensus set
+    rng = np.random.RandomState(0)
+    T = 150
+    uo = np.c_[rng.uniform(0, 1000, T), rng.uniform(0, 700, T), np.ones(T), rng.uniform(0, 1000, T), rng.uniform(0, 700, T), np.ones(T)]
+    g = mg.ransac_H(uo, max_samples=20000)
+    assert g["inl"].sum() < 15
+    # noise-free data: every correspondence is an inlier
+    un, _ = _corr_set(4, 80, 80, noise=0.0)
+    g = mg.ransac_H(un)
+    assert g["inl"].sum() == 80 and _transfer_err(g["H"], un).max() < 1e-6
+
+
+# ------------------------------------------------------------------------------------------ whole pair (config 3)
+def test_pair_pipeline_config3(mg, oracle, synth_pair):
+    """BASELINE config 3: single 1024x768 pair, Hessian-AffNet-OriNet-HardNet++ + linear FGINN + LO-RANSAC(H),
+    through the C++ host mirror of the reference operators (modsgpu_pair_pipeline)."""
+    from mods_light_zmq_b200 import synth
+    a, b, H = synth_pair
+    r = mg.pair_pipeline(synth.gray_to_bgr(a), synth.gray_to_bgr(b), seed=5)
+    ka = oracle.detect_hessian(_gray(oracle, a))
+    kb = oracle.detect_hessian(_gray(oracle, b))
+    assert r["keypoints"] == [len(ka), len(kb)]
+    assert all(0.8 * k < n <= k for n, k in zip(r["regions"], r["keypoints"]))
+    assert all(0.6 * k < n <= k for n, k in zip(r["descriptors"], r["regions"]))
+    assert r["tentatives"] > 100 and r["unique_tentatives"] <= r["tentatives"]
+    assert r["inliers"] >= 0.5 * r["unique_tentatives"]
+    Hn, Ht = r["H"] / r["H"][2, 2], H / H[2, 2]
+    corners = np.array([[0, 0, 1], [1023, 0, 1], [0, 767, 1], [1023, 767, 1], [512, 384, 1.0]])
+    pa, pb = corners @ Hn.T, corners @ Ht.T
+    assert np.linalg.norm(pa[:, :2] / pa[:, 2:3] - pb[:, :2] / pb[:, 2:3], axis=1).max() < 1.5
+    xy = r["inlier_xy"]
+    p = np.c_[xy[:, :2], np.ones(len(xy))] @ Ht.T
+    assert np.median(np.linalg.norm(p[:, :2] / p[:, 2:3] - xy[:, 2:4], axis=1)) < 1.5
+    # same result from device-resident images and from a second run (fixed seed)
+    i1, i2 = mg.image_from_bgr8(synth.gray_to_bgr(a)), mg.image_from_bgr8(synth.gray_to_bgr(b))
+    r2 = mg.pair_pipeline_images(i1, i2, seed=5)
+    for k in ("keypoints", "regions", "descriptors", "tentatives", "unique_tentatives", "inliers"):
+        assert r[k] == r2[k], k
+    assert np.array_equal(r["H"], r2["H"])

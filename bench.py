@@ -197,10 +197,11 @@ def run_gpu(args, rank, world, local_rank):
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    mg = M.ModsGpu(local_rank, load_nets=True)
-    lib, ctx = mg.lib, mg.ctx
+    nwk = max(1, args.workers)
+    # one modsgpu_ctx (= one CUDA stream + workspaces) per worker thread, as the C ABI prescribes; pairs are
+    # independent, so workers overlap one pair's host-side seams with another pair's kernels
+    mgs = [M.ModsGpu(local_rank, load_nets=True) for _ in range(nwk)]
     pairs = make_pairs(N_DISTINCT_PAIRS, rank)
-    # pinned host images (e2e arm) and device-resident images (value arm)
     host = []
     for a, b, _ in pairs:
         pa = torch.empty(a.shape, dtype=torch.uint8).pin_memory()
@@ -208,7 +209,7 @@ def run_gpu(args, rank, world, local_rank):
         pa.numpy()[:] = a
         pb.numpy()[:] = b
         host.append((pa, pb))
-    dev = [(mg.image_from_bgr8(pa.numpy()), mg.image_from_bgr8(pb.numpy())) for pa, pb in host]
+    dev = [[(mg.image_from_bgr8(pa.numpy()), mg.image_from_bgr8(pb.numpy())) for pa, pb in host] for mg in mgs]
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -222,21 +223,28 @@ def run_gpu(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     results = np.zeros((max(args.steps, 1), 16 + 4 * CAPACITY), np.float64)
+    last = {}
 
-    def step_value(k, store):
-        lib.modsgpu_flush_l2(ctx)
-        i1, i2 = dev[k % len(dev)]
+    def step_value(wk, k, store=True):
+        mg = mgs[wk]
+        mg.lib.modsgpu_flush_l2(mg.ctx)
+        i1, i2 = dev[wk][k % len(host)]
         r = mg.pair_pipeline_images(i1, i2, seed=1000 + k, capacity=CAPACITY)
         if store:
             results[k, :9] = r["H"].ravel()
             results[k, 9] = r["inliers"]
             results[k, 16:16 + 4 * len(r["inlier_xy"])] = r["inlier_xy"].ravel()
-        return r
+            last["r"] = r
 
-    def step_e2e(k):
-        lib.modsgpu_flush_l2(ctx)
+    def step_e2e(wk, k, store=True):
+        mg = mgs[wk]
+        mg.lib.modsgpu_flush_l2(mg.ctx)
         pa, pb = host[k % len(host)]
-        return mg.pair_pipeline(pa.numpy(), pb.numpy(), seed=1000 + k, capacity=CAPACITY)
+        r = mg.pair_pipeline(pa.numpy(), pb.numpy(), seed=1000 + k, capacity=CAPACITY)
+        if store:
+            results[k, :9] = r["H"].ravel()
+            results[k, 9] = r["inliers"]
+            results[k, 16:16 + 4 * len(r["inlier_xy"])] = r["inlier_xy"].ravel()
 
     def gather_results():
         if dist is None:
@@ -246,48 +254,72 @@ def run_gpu(args, rank, world, local_rank):
         dist.gather(t, lst, dst=0)
         torch.cuda.synchronize()
 
-    def timed(fn, steps, with_gather):
+    def timed(fn, steps):
+        """K steps dealt round-robin to the worker threads; device time = CUDA events on worker 0's stream
+        bracketing the whole region (start recorded after all workers are ready, stop after all have joined
+        and the gather is done)."""
+        errs = []
+        gate = threading.Barrier(nwk + 1)
+
+        def work(wk):
+            try:
+                gate.wait()
+                for k in range(wk, steps, nwk):
+                    fn(wk, k)
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+
+        ths = [threading.Thread(target=work, args=(wk,)) for wk in range(nwk)]
+        for t in ths:
+            t.start()
         barrier()
-        t0 = time.perf_counter()
         ms = C.c_float()
-        lib.modsgpu_timer_start(ctx)
-        last = None
-        for k in range(steps):
-            last = fn(k)
-        if with_gather:
-            gather_results()
-        lib.modsgpu_timer_stop(ctx, C.byref(ms))
-        barrier()
+        mgs[0].lib.modsgpu_timer_start(mgs[0].ctx)
+        t0 = time.perf_counter()
+        gate.wait()
+        for t in ths:
+            t.join()
+        torch.cuda.synchronize()
+        gather_results()
+        mgs[0].lib.modsgpu_timer_stop(mgs[0].ctx, C.byref(ms))
         wall_ms = (time.perf_counter() - t0) * 1e3
+        barrier()
+        if errs:
+            raise errs[0]
         dev_ms = float(ms.value)
         if dist is not None:
             t = torch.tensor([dev_ms, wall_ms], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dev_ms, wall_ms = float(t[0]), float(t[1])
-        return dev_ms, wall_ms, last
+        return dev_ms, wall_ms
 
-    # ---- warm-up, then the timed arms
-    for k in range(max(args.warmup, 3)):
-        step_value(k, False)
-        step_e2e(k)
+    # ---- warm-up (every worker), then the timed arms
+    W = max(args.warmup, 3)
+    for wk in range(nwk):
+        for k in range(W):
+            step_value(wk, k, False)
+            step_e2e(wk, k, False)
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    launches0 = mg.launch_count
-    dev_ms, wall_ms, last = timed(lambda k: step_value(k, True), args.steps, True)
-    launches = mg.launch_count - launches0
-    e2e_ms, e2e_wall, _ = timed(step_e2e, args.steps, True)
+    launches0 = sum(mg.launch_count for mg in mgs)
+    dev_ms, wall_ms = timed(step_value, args.steps)
+    launches = sum(mg.launch_count for mg in mgs) - launches0
+    e2e_ms, e2e_wall = timed(step_e2e, args.steps)
     clk = clocks.stop() if rank == 0 else None
-    # ---- per-kernel events over the same K steps (separate pass so the timed arms carry no event overhead)
+    # ---- per-kernel events over K steps on one worker (separate pass: the timed arms carry no event overhead)
+    mg = mgs[0]
+    lib, ctx = mg.lib, mg.ctx
     lib.modsgpu_profile_enable(ctx, 1)
     for k in range(args.steps):
-        step_value(k, False)
+        step_value(0, k, False)
     buf = C.create_string_buffer(1 << 16)
     lib.modsgpu_profile_report(ctx, buf, len(buf))
     lib.modsgpu_profile_enable(ctx, 0)
     prof = json.loads(buf.value.decode() or "{}")
     if rank != 0:
         return
+    lastr = last.get("r")
     value = world * args.steps / (dev_ms * 1e-3)
     e2e_value = world * args.steps / (e2e_ms * 1e-3)
     total_kernel_ms = sum(v["ms"] for v in prof.values()) or 1.0
@@ -307,7 +339,10 @@ def run_gpu(args, rank, world, local_rank):
                     "launches": p["launches"], "avg_us": 1e3 * p["ms"] / max(p["launches"], 1),
                     "share_of_kernel_time": p["ms"] / total_kernel_ms}
     kernels = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
-                   "share": v["ms"] / total_kernel_ms} for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+                   "share": v["ms"] / total_kernel_ms,
+                   "achieved": (v["work"] / (v["ms"] * 1e-3) / ALG[v["kind"]][2]) if v["kind"] in ALG and v["ms"] > 0 else None,
+                   "unit": ALG[v["kind"]][1] if v["kind"] in ALG else "latency-bound"}
+               for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -319,15 +354,17 @@ def run_gpu(args, rank, world, local_rank):
                          % (time.perf_counter() - t0),
                "stage_seconds_sample": parts}
     h2d = 2 * W_IMG * H_IMG * 3
-    d2h = 4 * 8 * int(last["inliers"]) + 9 * 8 + 9 * 4 if last else 0
+    d2h = 4 * 8 * int(lastr["inliers"]) + 9 * 8 + 9 * 4 if lastr else 0
     line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f16 (nets: fp16 operands, fp32 accumulate); f32 detector/sampler; f64 RANSAC",
+            "warmup": W, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 (nets: fp16 operands, fp32 accumulate); f32 detector/sampler; f64 RANSAC",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": 1, "distinct_pairs": N_DISTINCT_PAIRS,
+            "config": {"workload": WORKLOAD, "pairs_per_step": 1, "distinct_pairs": N_DISTINCT_PAIRS,
+                       "workers_per_gpu": nwk,
                        "l2": "flushed before every step (256 MB memset on the pipeline stream)",
-                       "parallelism": "pairs sharded across ranks; one NCCL gather of the verified correspondences" if world > 1 else "single GPU",
-                       "last_step": {k: last[k] for k in ("keypoints", "regions", "descriptors", "tentatives", "unique_tentatives", "inliers")}},
+                       "parallelism": ("pairs sharded across %d ranks; one NCCL gather of the verified correspondences" % world) if world > 1 else "single GPU",
+                       "last_step": {k: lastr[k] for k in ("keypoints", "regions", "descriptors", "tentatives", "unique_tentatives", "inliers")} if lastr else None},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps,
                     "note": "h2d/d2h count the API-level buffers (two BGR images in, verified correspondences + H out); "
@@ -337,7 +374,8 @@ def run_gpu(args, rank, world, local_rank):
     if cpu:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
-    mg.close()
+    for m in mgs:
+        m.close()
 
 
 def main():
@@ -347,6 +385,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workers", type=int, default=int(os.environ.get("MODSGPU_BENCH_WORKERS", "4")),
+                    help="worker threads (one modsgpu_ctx / CUDA stream each) per GPU")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

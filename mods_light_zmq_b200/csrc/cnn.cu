@@ -131,32 +131,38 @@ struct ConvCfg {
   static constexpr int A_BYTES = NPL * TP * 16;
   static constexpr int W_BYTES = 9 * KSTEPS * 2 * COUT_T * 16;
   static constexpr int TMEM_COLS = (2 * COUT_T <= 32) ? 32 : (2 * COUT_T <= 64 ? 64 : (2 * COUT_T <= 128 ? 128 : 256));
-  static constexpr int SMEM_BYTES = W_BYTES + 2 * A_BYTES + 128;
+  // A-tile ring: as deep as shared memory allows (small tiles are latency- not bandwidth-limited)
+  static constexpr int NST_FIT = (232448 - W_BYTES - 256) / A_BYTES;
+  static constexpr int NST = NST_FIT < 2 ? 2 : (NST_FIT > 8 ? 8 : NST_FIT);
+  static constexpr int SMEM_BYTES = W_BYTES + NST * A_BYTES + 256;
   static_assert(CIN % 16 == 0 && COUT_T % 16 == 0, "UMMA shape");
 };
 
 template <int CIN, int COUT_T, int NSPLIT, int S, int NGRP, int OUT_MODE>
 __global__ void __launch_bounds__(192, 1)
 k_conv_umma(const __half* __restrict__ in, size_t in_slots, const __half* __restrict__ wts,
-            const float* __restrict__ bias, __half* __restrict__ out, size_t out_slots, int np, int ntiles) {
+            const float* __restrict__ bias, __half* __restrict__ out, size_t out_slots, int np, int ntiles,
+            int patch_base) {
   using Cfg = ConvCfg<CIN, COUT_T, NSPLIT, S, NGRP, OUT_MODE>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* w_s = smem;
   uint8_t* a_s = smem + Cfg::W_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::W_BYTES + 2 * Cfg::A_BYTES);
-  uint64_t* w_full = bars;         // weights landed
-  uint64_t* a_full = bars + 1;     // [2]
-  uint64_t* a_empty = bars + 3;    // [2]
-  uint64_t* t_full = bars + 5;     // [2]
-  uint64_t* t_empty = bars + 7;    // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  constexpr int NST = Cfg::NST;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::W_BYTES + NST * Cfg::A_BYTES);
+  uint64_t* w_full = bars;                  // weights landed
+  uint64_t* a_full = bars + 1;              // [NST]
+  uint64_t* a_empty = bars + 1 + NST;       // [NST]
+  uint64_t* t_full = bars + 1 + 2 * NST;    // [2]
+  uint64_t* t_empty = bars + 3 + 2 * NST;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + 2 * NST);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nsp = blockIdx.y;  // which COUT_T slice of the output channels
 
   if (threadIdx.x == 0) {
     mbar_init(w_full, 1);
-    for (int i = 0; i < 2; i++) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); mbar_init(t_full + i, 1); mbar_init(t_empty + i, 4); }
+    for (int i = 0; i < NST; i++) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); }
+    for (int i = 0; i < 2; i++) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 4); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -176,7 +182,7 @@ k_conv_umma(const __half* __restrict__ in, size_t in_slots, const __half* __rest
       }
       int it = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
-        const int s = it & 1, ph = (it >> 1) & 1;
+        const int s = it % NST, ph = (it / NST) & 1;
         mbar_wait(a_empty + s, ph ^ 1);
         mbar_expect_tx(a_full + s, Cfg::A_BYTES);
         const size_t slot0 = (size_t)FS + (size_t)tile * 128 - Cfg::HALO_LO;
@@ -194,12 +200,13 @@ k_conv_umma(const __half* __restrict__ in, size_t in_slots, const __half* __rest
       const uint32_t w_addr = smem_u32(w_s);
       int it = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
-        const int s = it & 1, ph = (it >> 1) & 1;
-        mbar_wait(t_empty + s, ph ^ 1);
+        const int s = it % NST, ph = (it / NST) & 1;
+        const int ts = it & 1, tph = (it >> 1) & 1;
+        mbar_wait(t_empty + ts, tph ^ 1);
         mbar_wait(a_full + s, ph);
         fence_after_sync();
         const uint32_t a_addr = smem_u32(a_s + s * Cfg::A_BYTES);
-        const uint32_t d_tmem = tmem_base + s * COUT_T;
+        const uint32_t d_tmem = tmem_base + ts * COUT_T;
 #pragma unroll
         for (int t = 0; t < 9; t++) {
           const int dy = t / 3, dx = t % 3;
@@ -217,7 +224,7 @@ k_conv_umma(const __half* __restrict__ in, size_t in_slots, const __half* __rest
           }
         }
         mma_commit(a_empty + s);   // smem tile may be refilled once these MMAs retire
-        mma_commit(t_full + s);    // accumulator ready for the epilogue
+        mma_commit(t_full + ts);   // accumulator ready for the epilogue
       }
     }
   } else {
@@ -239,7 +246,7 @@ k_conv_umma(const __half* __restrict__ in, size_t in_slots, const __half* __rest
         oslot = (size_t)FS + (size_t)patch * PP2 + ((y >> 1) + 1) * PT2 + (x >> 1);
         oplane0 = (((y & 1) << 1) | (x & 1)) * (Cfg::COUT / 8);
       } else {
-        oslot = (size_t)patch;
+        oslot = (size_t)(patch_base + patch);
         oplane0 = (y * S + x) * (Cfg::COUT / 8);
       }
       oplane0 += nsp * (COUT_T / 8);
@@ -274,10 +281,13 @@ k_conv_umma(const __half* __restrict__ in, size_t in_slots, const __half* __rest
 // =================================================================================================
 constexpr int HG_STAGES = 3, HG_STAGE_BYTES = 65536;
 constexpr int HG_SMEM = HG_STAGES * HG_STAGE_BYTES + 128;
+constexpr int HG_KSPLIT = 8, HG_NKB = 64;   // 64 K blocks of 128, 8 per CTA
 
+// Split-K: CTA (m, ks) accumulates K blocks [ks*8, ks*8+8) of M tile m and writes its fp32 partial tile to
+// part[ks][m*128 + row][128]; k_head_finish adds the partials in a fixed order (deterministic).
 __global__ void __launch_bounds__(192, 1)
 k_head_gemm(const __half* __restrict__ act, size_t slots, const __half* __restrict__ wts,
-            const float* __restrict__ bias, float* __restrict__ out, int np) {
+            float* __restrict__ part, int m_pad) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + HG_STAGES * HG_STAGE_BYTES);
   uint64_t* full = bars;                 // [3]
@@ -285,7 +295,9 @@ k_head_gemm(const __half* __restrict__ act, size_t slots, const __half* __restri
   uint64_t* t_full = bars + 2 * HG_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * HG_STAGES + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * 128;
+  const int m0 = blockIdx.x * 128, ksp = blockIdx.y;
+  constexpr int NKB = HG_NKB / HG_KSPLIT;
+  const int kb0 = ksp * NKB;
   if (threadIdx.x == 0) {
     for (int i = 0; i < HG_STAGES; i++) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
     mbar_init(t_full, 1);
@@ -296,11 +308,10 @@ k_head_gemm(const __half* __restrict__ act, size_t slots, const __half* __restri
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  constexpr int NKB = 64;  // K blocks of 128
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < NKB; kb++) {
-        const int s = kb % HG_STAGES, ph = (kb / HG_STAGES) & 1;
+      for (int i = 0; i < NKB; i++) {
+        const int kb = kb0 + i, s = i % HG_STAGES, ph = (i / HG_STAGES) & 1;
         mbar_wait(empty + s, ph ^ 1);
         mbar_expect_tx(full + s, HG_STAGE_BYTES);
         uint8_t* dst = smem + s * HG_STAGE_BYTES;
@@ -313,55 +324,61 @@ k_head_gemm(const __half* __restrict__ act, size_t slots, const __half* __restri
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = instr_desc_f16(128);
-      for (int kb = 0; kb < NKB; kb++) {
-        const int s = kb % HG_STAGES, ph = (kb / HG_STAGES) & 1;
+      for (int i = 0; i < NKB; i++) {
+        const int s = i % HG_STAGES, ph = (i / HG_STAGES) & 1;
         mbar_wait(full + s, ph);
         fence_after_sync();
         const uint32_t a_addr = smem_u32(smem + s * HG_STAGE_BYTES), b_addr = a_addr + 32768;
 #pragma unroll
         for (int j = 0; j < 8; j++)
-          mma_f16(tmem_base, smem_desc(a_addr + j * 4096, 2048, 128), smem_desc(b_addr + j * 4096, 2048, 128), idesc, (kb | j) != 0);
+          mma_f16(tmem_base, smem_desc(a_addr + j * 4096, 2048, 128), smem_desc(b_addr + j * 4096, 2048, 128), idesc, (i | j) != 0);
         mma_commit(empty + s);
       }
       mma_commit(t_full);
     }
   } else {
-    const int q = warp & 3, m = q * 32 + lane, patch = m0 + m;
+    const int q = warp & 3, m = q * 32 + lane;
     mbar_wait(t_full, 0);
     fence_after_sync();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    float ss = 0.f;
+    float4* dst = reinterpret_cast<float4*>(part + ((size_t)ksp * m_pad + m0 + m) * 128);
 #pragma unroll 1
     for (int cc = 0; cc < 8; cc++) {
       float v[16];
       tmem_ld16(taddr + cc * 16, v);
 #pragma unroll
-      for (int e = 0; e < 16; e++) { float t = v[e] + __ldg(bias + cc * 16 + e); ss = fmaf(t, t, ss); }
-    }
-    // L2Norm (desc_server.py:49-52) then uint8(clip(210*(d+0.45),0,255)) (desc_server.py:42)
-    const float norm = sqrtf(ss + 1e-10f);
-#pragma unroll 1
-    for (int cc = 0; cc < 8; cc++) {
-      float v[16];
-      tmem_ld16(taddr + cc * 16, v);
-      if (patch < np) {
-        float o[16];
-#pragma unroll
-        for (int e = 0; e < 16; e++) {
-          float d = (v[e] + __ldg(bias + cc * 16 + e)) / norm;
-          double qd = 210.0 * ((double)d + 0.45);
-          qd = qd < 0.0 ? 0.0 : (qd > 255.0 ? 255.0 : qd);
-          o[e] = (float)(int)qd;
-        }
-        float4* dst = reinterpret_cast<float4*>(out + (size_t)patch * 128 + cc * 16);
-#pragma unroll
-        for (int e = 0; e < 4; e++) dst[e] = make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
-      }
+      for (int e = 0; e < 4; e++) dst[cc * 4 + e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
     }
   }
   fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc<128>(tmem_base);
+}
+
+// one warp per patch: sum of the K-split partials + folded BN bias -> L2Norm (desc_server.py:49-52) ->
+// uint8(clip(210*(d+0.45),0,255)) as float (desc_server.py:42)
+__global__ void k_head_finish(const float* __restrict__ part, int m_pad, const float* __restrict__ bias,
+                              float* __restrict__ out, int np) {
+  const int patch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (patch >= np) return;
+  float4 acc = *reinterpret_cast<const float4*>(bias + lane * 4);
+  for (int ks = 0; ks < HG_KSPLIT; ks++) {
+    const float4 p = *reinterpret_cast<const float4*>(part + ((size_t)ks * m_pad + patch) * 128 + lane * 4);
+    acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+  }
+  float ss = acc.x * acc.x;
+  ss = fmaf(acc.y, acc.y, ss); ss = fmaf(acc.z, acc.z, ss); ss = fmaf(acc.w, acc.w, ss);
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float norm = sqrtf(ss + 1e-10f);
+  float v[4] = {acc.x, acc.y, acc.z, acc.w}, o4[4];
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    const float d = v[e] / norm;
+    double qd = 210.0 * ((double)d + 0.45);
+    qd = qd < 0.0 ? 0.0 : (qd > 255.0 ? 255.0 : qd);
+    o4[e] = (float)(int)qd;
+  }
+  *reinterpret_cast<float4*>(out + (size_t)patch * 128 + lane * 4) = make_float4(o4[0], o4[1], o4[2], o4[3]);
 }
 
 // =================================================================================================
@@ -378,58 +395,69 @@ __device__ __forceinline__ void load8(const __half* p, float* f) {
   for (int i = 0; i < 4; i++) { float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
 }
 
-// conv 8x8 (64->3, bias) -> tanh -> +1 on outputs 0 and 2 (affnet_server.py:64-66,:80-84)
-__global__ void k_head_aff(const __half* __restrict__ act, size_t slots, const float* __restrict__ w,
-                           const float* __restrict__ b, float* __restrict__ out, int np) {
-  const int patch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (patch >= np) return;
-  float acc[3] = {0.f, 0.f, 0.f};
-  for (int it = lane; it < 512; it += 32) {
-    const int pix = it >> 3, c8 = it & 7, y = pix >> 3, x = pix & 7;
-    float a[8];
-    load8(act + ((size_t)c8 * slots + FS + (size_t)patch * 81 + (y + 1) * 9 + x) * 8, a);
-#pragma unroll
-    for (int o = 0; o < 3; o++) {
-      const float* wp = w + ((size_t)o * 64 + pix) * 64 + c8 * 8;
-#pragma unroll
-      for (int e = 0; e < 8; e++) acc[o] = fmaf(a[e], __ldg(wp + e), acc[o]);
-    }
+// AffNet: conv 8x8 (64->3, bias) -> tanh -> +1 on outputs 0 and 2 (affnet_server.py:64-66,:80-84)
+// OriNet: conv 8x8 pad 1 (64->2, bias) -> 3x3 map -> tanh -> mean (orinet_server.py:64-70)
+// Weights live in shared memory as [o][e][item] (item = pix*8 + c8) so that the 32 lanes of a warp, which
+// walk consecutive items, read consecutive floats; one warp per patch, persistent over patches.
+template <int NOUT, bool ORI>
+__global__ void __launch_bounds__(256)
+k_head_small(const __half* __restrict__ act, size_t slots, const float* __restrict__ w, const float* __restrict__ b,
+             float* __restrict__ out, int np) {
+  extern __shared__ float ws[];   // NOUT * 8 * 512
+  for (int idx = threadIdx.x; idx < NOUT * 4096; idx += blockDim.x) {
+    const int o = idx >> 12, rem = idx & 4095, pix = rem >> 6, c = rem & 63;
+    ws[(o * 8 + (c & 7)) * 512 + pix * 8 + (c >> 3)] = w[idx];
   }
-  for (int o = 0; o < 3; o++) acc[o] = warp_sum(acc[o]);
-  if (lane == 0) {
-    out[patch * 3 + 0] = tanhf(acc[0] + b[0]) + 1.f;
-    out[patch * 3 + 1] = tanhf(acc[1] + b[1]);
-    out[patch * 3 + 2] = tanhf(acc[2] + b[2]) + 1.f;
-  }
-}
-
-// conv 8x8 pad 1 (64->2, bias) -> 3x3 map -> tanh -> mean (orinet_server.py:64-70)
-__global__ void k_head_ori(const __half* __restrict__ act, size_t slots, const float* __restrict__ w,
-                           const float* __restrict__ b, float* __restrict__ out, int np) {
-  const int patch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (patch >= np) return;
-  float res[2] = {0.f, 0.f};
-  for (int pos = 0; pos < 9; pos++) {
-    const int oy = pos / 3, ox = pos % 3;
-    float acc[2] = {0.f, 0.f};
-    for (int it = lane; it < 512; it += 32) {
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int patch = blockIdx.x * 8 + warp; patch < np; patch += gridDim.x * 8) {
+    constexpr int NPOS = ORI ? 9 : 1;
+    float acc[NPOS][NOUT];
+#pragma unroll
+    for (int p = 0; p < NPOS; p++)
+#pragma unroll
+      for (int o = 0; o < NOUT; o++) acc[p][o] = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < 16; k++) {
+      const int it = lane + 32 * k;
       const int pix = it >> 3, c8 = it & 7, y = pix >> 3, x = pix & 7;
-      const int ky = y - oy + 1, kx = x - ox + 1;
-      if (ky < 0 || ky > 7 || kx < 0 || kx > 7) continue;
       float a[8];
       load8(act + ((size_t)c8 * slots + FS + (size_t)patch * 81 + (y + 1) * 9 + x) * 8, a);
+      if (!ORI) {
 #pragma unroll
-      for (int o = 0; o < 2; o++) {
-        const float* wp = w + ((size_t)o * 64 + ky * 8 + kx) * 64 + c8 * 8;
+        for (int o = 0; o < NOUT; o++)
 #pragma unroll
-        for (int e = 0; e < 8; e++) acc[o] = fmaf(a[e], __ldg(wp + e), acc[o]);
+          for (int e = 0; e < 8; e++) acc[0][o] = fmaf(a[e], ws[(o * 8 + e) * 512 + it], acc[0][o]);
+      } else {
+#pragma unroll
+        for (int pos = 0; pos < 9; pos++) {
+          const int ky = y - pos / 3 + 1, kx = x - pos % 3 + 1;
+          if (ky < 0 || ky > 7 || kx < 0 || kx > 7) continue;
+          const int wit = (ky * 8 + kx) * 8 + c8;
+#pragma unroll
+          for (int o = 0; o < NOUT; o++)
+#pragma unroll
+            for (int e = 0; e < 8; e++) acc[pos][o] = fmaf(a[e], ws[(o * 8 + e) * 512 + wit], acc[pos][o]);
+        }
       }
     }
-    for (int o = 0; o < 2; o++) res[o] += tanhf(warp_sum(acc[o]) + b[o]);
-  }
-  if (lane == 0) {
-    out[patch * 2 + 0] = res[0] / 9.f;
-    out[patch * 2 + 1] = res[1] / 9.f;
+    float res[NOUT];
+#pragma unroll
+    for (int o = 0; o < NOUT; o++) res[o] = 0.f;
+#pragma unroll
+    for (int p = 0; p < NPOS; p++)
+#pragma unroll
+      for (int o = 0; o < NOUT; o++) res[o] += tanhf(warp_sum(acc[p][o]) + b[o]);
+    if (lane == 0) {
+      if (ORI) {
+        out[patch * 2 + 0] = res[0] / 9.f;
+        out[patch * 2 + 1] = res[1] / 9.f;
+      } else {
+        out[patch * 3 + 0] = res[0] + 1.f;
+        out[patch * 3 + 1] = res[1];
+        out[patch * 3 + 2] = res[NOUT - 1] + 1.f;
+      }
+    }
   }
 }
 
@@ -511,7 +539,8 @@ int cnn_chunk_cap() {
 }
 
 template <int CIN, int COUT_T, int NSPLIT, int S, int NGRP, int OUT_MODE>
-int launch_conv(modsgpu_ctx* ctx, const __half* in, size_t in_slots, const ConvW& w, __half* out, size_t out_slots, int np) {
+int launch_conv(modsgpu_ctx* ctx, const __half* in, size_t in_slots, const ConvW& w, __half* out, size_t out_slots, int np,
+                int patch_base = 0) {
   using Cfg = ConvCfg<CIN, COUT_T, NSPLIT, S, NGRP, OUT_MODE>;
   auto kern = k_conv_umma<CIN, COUT_T, NSPLIT, S, NGRP, OUT_MODE>;
   static bool attr = false;
@@ -525,7 +554,7 @@ int launch_conv(modsgpu_ctx* ctx, const __half* in, size_t in_slots, const ConvW
   MG_PROF(ctx, pname, 1, 2.0 * np * S * S * 9.0 * CIN * Cfg::COUT);
   int gx = std::min(ntiles, std::max(1, ctx->num_sms / NSPLIT));
   dim3 grid(gx, NSPLIT);
-  kern<<<grid, 192, Cfg::SMEM_BYTES, ctx->stream>>>(in, in_slots, w.w, w.b, out, out_slots, np, ntiles);
+  kern<<<grid, 192, Cfg::SMEM_BYTES, ctx->stream>>>(in, in_slots, w.w, w.b, out, out_slots, np, ntiles, patch_base);
   MG_LAUNCHED(ctx);
   return 0;
 }
@@ -602,7 +631,7 @@ extern "C" int modsgpu_load_weights(modsgpu_ctx* ctx, modsgpu_net net, const cha
   for (int i = 0; i < 6; i++) {
     size_t slots = plane_slots(cap, S_of[i]);
     int npl = planes[i];
-    if (i == 5 && net == MODSGPU_HARDNET) { slots = (size_t)cap; npl = 64 * 16; }
+    if (i == 5 && net == MODSGPU_HARDNET) continue;   // conv6 writes straight into the head GEMM operand (ctx->cnn_act0)
     nw->slots[i] = slots;
     size_t bytes = slots * npl * 16;
     MG_CUDA(ctx, cudaMalloc((void**)&nw->act[i], bytes));
@@ -616,6 +645,17 @@ extern "C" int modsgpu_load_weights(modsgpu_ctx* ctx, modsgpu_net net, const cha
 int mg_net_forward_enqueue(modsgpu_ctx* ctx, modsgpu_net net, const uint8_t* d_patches, int n, float* d_out) {
   NetWeights* nw = ctx->nets[net];
   if (!nw) MG_FAIL(ctx, MODSGPU_ESTATE, "modsgpu_load_weights has not been called for this net");
+  // HardNet: conv6 of every chunk lands in one [8192/8 planes][m_pad patches] operand; the 8x8 head then runs
+  // once over all patches as a split-K GEMM
+  const int m_pad = round_up(n, 128);
+  __half* act6all = nullptr;
+  float* part = nullptr;
+  if (net == MODSGPU_HARDNET) {
+    MG_CUDA(ctx, ctx->cnn_act0.ensure((size_t)1024 * m_pad * 16));
+    MG_CUDA(ctx, ctx->cnn_act1.ensure((size_t)HG_KSPLIT * m_pad * 128 * 4));
+    act6all = ctx->cnn_act0.as<__half>();
+    part = ctx->cnn_act1.as<float>();
+  }
   for (int p0 = 0; p0 < n; p0 += nw->cap) {
     const int np = std::min(nw->cap, n - p0);
     const uint8_t* pin = d_patches + (size_t)p0 * 1024;
@@ -629,12 +669,7 @@ int mg_net_forward_enqueue(modsgpu_ctx* ctx, modsgpu_net net, const uint8_t* d_p
       if ((rc = launch_conv<32, 64, 1, 16, 4, OUT_NORMAL>(ctx, nw->act[1], nw->slots[1], nw->conv[1], nw->act[2], nw->slots[2], np))) return rc;
       if ((rc = launch_conv<64, 64, 1, 16, 1, OUT_PARITY>(ctx, nw->act[2], nw->slots[2], nw->conv[2], nw->act[3], nw->slots[3], np))) return rc;
       if ((rc = launch_conv<64, 64, 2, 8, 4, OUT_NORMAL>(ctx, nw->act[3], nw->slots[3], nw->conv[3], nw->act[4], nw->slots[4], np))) return rc;
-      if ((rc = launch_conv<128, 64, 2, 8, 1, OUT_GEMM>(ctx, nw->act[4], nw->slots[4], nw->conv[4], nw->act[5], nw->slots[5], np))) return rc;
-      static bool attr = false;
-      if (!attr) { MG_CUDA(ctx, cudaFuncSetAttribute(k_head_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, HG_SMEM)); attr = true; }
-      MG_PROF(ctx, "k_head_gemm", 1, 2.0 * np * 8192.0 * 128);
-      k_head_gemm<<<ceil_div(np, 128), 192, HG_SMEM, ctx->stream>>>(nw->act[5], nw->slots[5], nw->head_w16, nw->head_b, pout, np);
-      MG_LAUNCHED(ctx);
+      if ((rc = launch_conv<128, 64, 2, 8, 1, OUT_GEMM>(ctx, nw->act[4], nw->slots[4], nw->conv[4], act6all, (size_t)m_pad, np, p0))) return rc;
     } else {
       MG_PROF(ctx, "k_conv1<16>", 1, 2.0 * np * 1024 * 9 * 16);
       k_conv1<16><<<np, 256, 0, ctx->stream>>>(pin, np, nw->c1_w, nw->c1_b, nw->act[0], nw->slots[0]);
@@ -644,13 +679,30 @@ int mg_net_forward_enqueue(modsgpu_ctx* ctx, modsgpu_net net, const uint8_t* d_p
       if ((rc = launch_conv<32, 32, 1, 16, 1, OUT_PARITY>(ctx, nw->act[2], nw->slots[2], nw->conv[2], nw->act[3], nw->slots[3], np))) return rc;
       if ((rc = launch_conv<32, 64, 1, 8, 4, OUT_NORMAL>(ctx, nw->act[3], nw->slots[3], nw->conv[3], nw->act[4], nw->slots[4], np))) return rc;
       if ((rc = launch_conv<64, 64, 1, 8, 1, OUT_NORMAL>(ctx, nw->act[4], nw->slots[4], nw->conv[4], nw->act[5], nw->slots[5], np))) return rc;
+      static bool hattr = false;
+      if (!hattr) {
+        MG_CUDA(ctx, cudaFuncSetAttribute(k_head_small<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 4096 * 4));
+        MG_CUDA(ctx, cudaFuncSetAttribute(k_head_small<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4096 * 4));
+        hattr = true;
+      }
+      const int hgrid = std::min(ceil_div(np, 8), 2 * ctx->num_sms);
       MG_PROF(ctx, net == MODSGPU_AFFNET ? "k_head_aff" : "k_head_ori", 1, 2.0 * np * (net == MODSGPU_AFFNET ? 12288.0 : 61952.0));
       if (net == MODSGPU_AFFNET)
-        k_head_aff<<<ceil_div(np, 8), 256, 0, ctx->stream>>>(nw->act[5], nw->slots[5], nw->head_w32, nw->head_b, pout, np);
+        k_head_small<3, false><<<hgrid, 256, 3 * 4096 * 4, ctx->stream>>>(nw->act[5], nw->slots[5], nw->head_w32, nw->head_b, pout, np);
       else
-        k_head_ori<<<ceil_div(np, 8), 256, 0, ctx->stream>>>(nw->act[5], nw->slots[5], nw->head_w32, nw->head_b, pout, np);
+        k_head_small<2, true><<<hgrid, 256, 2 * 4096 * 4, ctx->stream>>>(nw->act[5], nw->slots[5], nw->head_w32, nw->head_b, pout, np);
       MG_LAUNCHED(ctx);
     }
+  }
+  if (net == MODSGPU_HARDNET) {
+    static bool attr = false;
+    if (!attr) { MG_CUDA(ctx, cudaFuncSetAttribute(k_head_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, HG_SMEM)); attr = true; }
+    MG_PROF(ctx, "k_head_gemm", 1, 2.0 * n * 8192.0 * 128);
+    k_head_gemm<<<dim3(m_pad / 128, HG_KSPLIT), 192, HG_SMEM, ctx->stream>>>(act6all, (size_t)m_pad, nw->head_w16, part, m_pad);
+    MG_LAUNCHED(ctx);
+    MG_PROF(ctx, "k_head_finish", 0, (double)n * 128 * 4 * (HG_KSPLIT + 1));
+    k_head_finish<<<ceil_div(n, 8), 256, 0, ctx->stream>>>(part, m_pad, nw->head_b, d_out, n);
+    MG_LAUNCHED(ctx);
   }
   return 0;
 }

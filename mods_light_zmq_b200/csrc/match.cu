@@ -231,6 +231,64 @@ k_dup_filter(const double* __restrict__ xy1, const double* __restrict__ xy2, con
   }
 }
 
+// ---- duplicate filter, parallel form: (1) rank sort, (2) T x T conflict bit matrix between sorted
+// positions a < b, (3) one warp walks the rows that have conflicts in order and clears the later bits.
+// Identical result to the sequential greedy loop: a correspondence dies iff an earlier SURVIVOR conflicts.
+constexpr int DUP_MAX_T = 16384;
+__global__ void k_dup_rank(const double* __restrict__ ratio, int T, int* __restrict__ ord) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T) return;
+  const double me = fabs(ratio[i]);
+  int rank = 0;
+  for (int j = 0; j < T; j++) { double o = fabs(ratio[j]); rank += (o < me) || (o == me && j < i); }
+  ord[rank] = i;
+}
+__global__ void k_dup_conflicts(const double* __restrict__ xy1, const double* __restrict__ xy2, const int* __restrict__ ord,
+                                int T, int nwords, double r_sq, unsigned* __restrict__ conf, int* __restrict__ rowflag) {
+  const int a = blockIdx.y, wi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (wi >= nwords) return;
+  unsigned bits = 0;
+  if (wi * 32 + 31 > a) {
+    const int ia = ord[a];
+    const double ax1 = xy1[2 * ia], ay1 = xy1[2 * ia + 1], ax2 = xy2[2 * ia], ay2 = xy2[2 * ia + 1];
+    for (int k = 0; k < 32; k++) {
+      const int b = wi * 32 + k;
+      if (b <= a || b >= T) continue;
+      const int ib = ord[b];
+      double dx = ax1 - xy1[2 * ib], dy = ay1 - xy1[2 * ib + 1];
+      if (dx * dx + dy * dy > r_sq) continue;
+      dx = ax2 - xy2[2 * ib]; dy = ay2 - xy2[2 * ib + 1];
+      if (dx * dx + dy * dy <= r_sq) bits |= 1u << k;
+    }
+  }
+  conf[(size_t)a * nwords + wi] = bits;
+  if (bits) rowflag[a] = 1;
+}
+__global__ void __launch_bounds__(32)
+k_dup_resolve(const unsigned* __restrict__ conf, const int* __restrict__ rowflag, const int* __restrict__ ord, int T,
+              int nwords, int* __restrict__ out, int* __restrict__ nout) {
+  __shared__ unsigned alive[DUP_MAX_T / 32];
+  const int lane = threadIdx.x;
+  for (int w = lane; w < nwords; w += 32) alive[w] = 0xffffffffu;
+  __syncwarp();
+  for (int a = 0; a < T; a++) {
+    if (!rowflag[a]) continue;
+    if (!((alive[a >> 5] >> (a & 31)) & 1u)) continue;
+    const unsigned* row = conf + (size_t)a * nwords;
+    for (int w = (a >> 5) + lane; w < nwords; w += 32) alive[w] &= ~row[w];
+    __syncwarp();
+  }
+  int m = 0;
+  for (int base = 0; base < T; base += 32) {
+    const int a = base + lane;
+    const bool keep = a < T && ((alive[a >> 5] >> (a & 31)) & 1u);
+    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+    if (keep) out[m + __popc(mask & ((1u << lane) - 1))] = ord[a];
+    m += __popc(mask);
+  }
+  if (lane == 0) *nout = m;
+}
+
 }  // namespace
 
 // Device part of the matcher.  d_q / d_t: fp32 descriptor rows already on the device, d_txy doubles.
@@ -343,9 +401,26 @@ extern "C" int modsgpu_duplicate_filter(modsgpu_ctx* ctx, const double* xy1, con
   MG_CUDA(ctx, cudaMemcpyAsync(d1, xy1, xb, cudaMemcpyHostToDevice, ctx->stream));
   MG_CUDA(ctx, cudaMemcpyAsync(d2, xy2, xb, cudaMemcpyHostToDevice, ctx->stream));
   MG_CUDA(ctx, cudaMemcpyAsync(dr, ratio, rb, cudaMemcpyHostToDevice, ctx->stream));
-  MG_PROF(ctx, "k_dup_filter", 2, (double)T);
-  k_dup_filter<<<1, 256, 0, ctx->stream>>>(d1, d2, dr, T, r * r, dord, alive, dout, ctx->mt_aux.as<int>() + 4);
-  MG_LAUNCHED(ctx);
+  if (T <= DUP_MAX_T) {
+    const int nwords = (T + 31) / 32;
+    MG_CUDA(ctx, ctx->mt_d.ensure((size_t)T * nwords * 4 + (size_t)T * 4 + 16));
+    unsigned* conf = ctx->mt_d.as<unsigned>();
+    int* rowflag = reinterpret_cast<int*>(conf + (size_t)T * nwords);
+    MG_CUDA(ctx, cudaMemsetAsync(rowflag, 0, (size_t)T * 4, ctx->stream));
+    MG_PROF(ctx, "k_dup_rank", 2, (double)T);
+    k_dup_rank<<<(T + 127) / 128, 128, 0, ctx->stream>>>(dr, T, dord);
+    MG_LAUNCHED(ctx);
+    MG_PROF(ctx, "k_dup_conflicts", 2, (double)T);
+    k_dup_conflicts<<<dim3((nwords + 63) / 64, T), 64, 0, ctx->stream>>>(d1, d2, dord, T, nwords, r * r, conf, rowflag);
+    MG_LAUNCHED(ctx);
+    MG_PROF(ctx, "k_dup_resolve", 2, (double)T);
+    k_dup_resolve<<<1, 32, 0, ctx->stream>>>(conf, rowflag, dord, T, nwords, dout, ctx->mt_aux.as<int>() + 4);
+    MG_LAUNCHED(ctx);
+  } else {
+    MG_PROF(ctx, "k_dup_filter", 2, (double)T);
+    k_dup_filter<<<1, 256, 0, ctx->stream>>>(d1, d2, dr, T, r * r, dord, alive, dout, ctx->mt_aux.as<int>() + 4);
+    MG_LAUNCHED(ctx);
+  }
   MG_CUDA(ctx, ctx->h_stage.ensure((size_t)T * 4 + 16));
   int* h = ctx->h_stage.as<int>();
   MG_CUDA(ctx, cudaMemcpyAsync(h, dout, (size_t)T * 4, cudaMemcpyDeviceToHost, ctx->stream));

@@ -12,7 +12,10 @@
 //   2. separable Gaussian (sigma = 1.5*R0/patchSize, cv::GaussianBlur order), evaluated only at the
 //      rows/columns the final resampling touches when R is large,
 //   3. resample to patchSize x patchSize, round-half-even to u8.
-// Small windows (R <= 66) live entirely in shared memory; large ones use an HBM scratch slab.
+// Small windows (R <= 66): one CTA per region, everything in shared memory.
+// Large windows: the three phases are separate launches over flattened (region, row-block) work lists, so
+// a 600-px window is spread over hundreds of CTAs instead of serialising one; S and the row-filtered
+// columns live in an HBM scratch slab (L2 resident).
 #include "common.cuh"
 #include <cmath>
 #include <map>
@@ -83,10 +86,11 @@ __device__ __forceinline__ float row_pass_at(const float* row, int R, int x, con
   return s;
 }
 
-template <bool LARGE>
-__global__ void __launch_bounds__(LARGE ? 256 : 128)
-k_sample(const float* __restrict__ img, int w, int h, const PatchMeta* __restrict__ metas,
-         const float* __restrict__ taps_all, float* __restrict__ scratch, uint8_t* __restrict__ out, int ps) {
+
+// ---- small windows: one CTA per region -----------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_sample_small(const float* __restrict__ img, int w, int h, const PatchMeta* __restrict__ metas,
+               const float* __restrict__ taps_all, uint8_t* __restrict__ out, int ps) {
   extern __shared__ float sm[];
   const PatchMeta m = metas[blockIdx.x];
   const int tid = threadIdx.x, nth = blockDim.x;
@@ -110,29 +114,18 @@ k_sample(const float* __restrict__ img, int w, int h, const PatchMeta* __restric
     }
     return;
   }
-
-  // ---- shared / scratch carve-up
   float* P = sm;                    // ps sample positions of the final resampling
   float* RX = P + MAX_PS;           // per-row start coordinates of the first resampling
-  float* RY = RX + (LARGE ? MAX_R : SMALL_R);
-  float* kk = RY + (LARGE ? MAX_R : SMALL_R);   // taps (<= 6*1.5*MAX_R/32+3)
-  float* S; float* T; float* B;
-  int nc;                           // number of columns (= rows) the blur is evaluated at
-  if (LARGE) {
-    B = kk + 640;
-    S = scratch + m.scratch_off;
-    T = S + (size_t)R * R;
-    nc = 2 * ps;
-  } else {
-    S = kk + 32;
-    T = S + SMALL_R * SMALL_R;
-    B = S;
-    nc = R;
-  }
+  float* RY = RX + SMALL_R;
+  float* kk = RY + SMALL_R;         // taps (<= 31)
+  float* S = kk + 32;
+  float* T = S + SMALL_R * SMALL_R;
+  float* B = S;                     // the column pass overwrites S (only T is read by then)
+  const int nc = R;
   const int ks = m.ks;
   for (int i = tid; i < ks; i += nth) kk[i] = taps_all[m.tap_off + i];
 
-  // ---- 1. first resampling: S = interpolate(img; centre (x,y), A, R x R)
+  // 1. first resampling: S = interpolate(img; centre (x,y), A, R x R)
   const int half = R / 2;
   for (int j = tid; j < R; j += nth) {
     float rx = m.x - (float)half * m.a12, ry = m.y - (float)half * m.a22;
@@ -140,8 +133,7 @@ k_sample(const float* __restrict__ img, int w, int h, const PatchMeta* __restric
     RX[j] = rx; RY[j] = ry;
   }
   if (tid == 0) {
-    // positions of the second resampling: centre R/2 (integer division), diag(scale)
-    float p = (float)(R / 2) - (float)(ps / 2) * m.scale;
+    float p = (float)(R / 2) - (float)(ps / 2) * m.scale;   // centre R/2 (integer division), diag(scale)
     for (int i = 0; i < ps; i++) { P[i] = p; p += m.scale; }
   }
   __syncthreads();
@@ -153,71 +145,174 @@ k_sample(const float* __restrict__ img, int w, int h, const PatchMeta* __restric
     for (int t = 0; t < i0; t++) { WX += m.a11; WY += m.a21; }
     const int i1 = min(R, i0 + CHUNK);
     for (int i = i0; i < i1; i++) {
-      S[(size_t)j * R + i] = sample_image(img, w, h, WX, WY);
+      S[j * R + i] = sample_image(img, w, h, WX, WY);
       WX += m.a11; WY += m.a21;
     }
   }
   __syncthreads();
-
-  // ---- 2. Gaussian blur (row pass -> T, column pass -> B) at the needed columns / rows
-  // column / row list: identity (small) or {floor(P[i]), floor(P[i])+1} (large)
-  auto pos_of = [&](int ci) -> int {
-    if (!LARGE) return ci;
-    int x = (int)floorf(P[ci >> 1]) + (ci & 1);
-    return clampi(x, 0, R - 1);
-  };
+  // 2. Gaussian blur: row pass -> T, column pass -> B
   for (int it = tid; it < R * nc; it += nth) {
-    const int y = it / nc, ci = it - y * nc;
-    T[(size_t)y * nc + ci] = row_pass_at(S + (size_t)y * R, R, pos_of(ci), kk, ks);
+    const int y = it / nc, x = it - y * nc;
+    T[y * nc + x] = row_pass_at(S + y * R, R, x, kk, ks);
   }
   __syncthreads();
   {
     const int r = ks >> 1;
     const int wc = R & ~7;
     for (int it = tid; it < nc * nc; it += nth) {
-      const int ri = it / nc, ci = it - ri * nc;
-      const int y = pos_of(ri), x = pos_of(ci);
-      auto TY = [&](int yy) { return T[(size_t)clampi(yy, 0, R - 1) * nc + ci]; };
+      const int y = it / nc, x = it - y * nc;
+      auto TY = [&](int yy) { return T[clampi(yy, 0, R - 1) * nc + x]; };
       float s = TY(y) * kk[r];
       if (x < wc) {
         for (int t = 1; t <= r; t++) s = fmaf(TY(y - t) + TY(y + t), kk[r + t], s);
       } else {
         for (int t = 1; t <= r; t++) s = s + (TY(y - t) + TY(y + t)) * kk[r + t];
       }
-      // small: B aliases S, which the row pass no longer needs -- but other threads still read T only
-      B[(size_t)ri * nc + ci] = s;
+      B[y * nc + x] = s;
     }
   }
   __syncthreads();
-
-  // ---- 3. second resampling to ps x ps + u8 quantisation
+  // 3. second resampling to ps x ps + u8 quantisation
   for (int it = tid; it < ps * ps; it += nth) {
     const int j = it / ps, i = it - j * ps;
     const float WX = P[i], WY = P[j];
     const int x = (int)floorf(WX), y = (int)floorf(WY);
     float v = 0.f;
     if (WX >= 0 && WY >= 0 && x < R - 1 && y < R - 1) {
-      float v00, v01, v10, v11;
-      if (LARGE) {
-        const float* r0 = B + (size_t)(2 * j) * nc + 2 * i;
-        const float* r1 = r0 + nc;
-        v00 = r0[0]; v01 = r0[1]; v10 = r1[0]; v11 = r1[1];
-      } else {
-        const float* r0 = B + (size_t)y * nc + x;
-        const float* r1 = r0 + nc;
-        v00 = r0[0]; v01 = r0[1]; v10 = r1[0]; v11 = r1[1];
-      }
+      const float* r0 = B + y * nc + x;
+      const float* r1 = r0 + nc;
       const float wx = WX - (float)x;
-      const float I1 = wx * (v01 - v00) + v00;
-      v = (WY - (float)y) * (wx * (v11 - v10) + v10 - I1) + I1;
+      const float I1 = wx * (r0[1] - r0[0]) + r0[0];
+      v = (WY - (float)y) * (wx * (r1[1] - r1[0]) + r1[0] - I1) + I1;
     }
     int q = __float2int_rn(v);
     dst[it] = (uint8_t)(q < 0 ? 0 : (q > 255 ? 255 : q));
   }
 }
 
+// ---- large windows: flattened (region, row-block) work lists -------------------------------------------
+// pre[] = exclusive prefix sums of the per-region block counts; binary search maps blockIdx -> region
+__device__ __forceinline__ int find_region(const int* __restrict__ pre, int n, int b) {
+  int lo = 0, hi = n;   // largest k with pre[k] <= b
+  while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (pre[mid] <= b) lo = mid; else hi = mid; }
+  return lo;
+}
+__device__ __forceinline__ int needed_pos(float p, int odd, int R) {
+  return clampi((int)floorf(p) + odd, 0, R - 1);
+}
+
+constexpr int L1_ROWS = 4, L2_ROWS = 8, L3_OUT_ROWS = 4;
+
+// phase 1: S[j][i] for L1_ROWS rows of one region
+__global__ void __launch_bounds__(128)
+k_large_resample(const float* __restrict__ img, int w, int h, const PatchMeta* __restrict__ metas, int nreg,
+                 const int* __restrict__ pre, float* __restrict__ scratch) {
+  const int reg = find_region(pre, nreg, blockIdx.x);
+  const PatchMeta m = metas[reg];
+  const int R = m.R, half = R / 2;
+  const int row0 = (blockIdx.x - pre[reg]) * L1_ROWS;
+  float* S = scratch + m.scratch_off;
+  const int nchunk = (R + CHUNK - 1) / CHUNK;
+  const int nrows = min(L1_ROWS, R - row0);
+  for (int it = threadIdx.x; it < nrows * nchunk; it += blockDim.x) {
+    const int jr = it / nchunk, q = it - jr * nchunk, j = row0 + jr;
+    float rx = m.x - (float)half * m.a12, ry = m.y - (float)half * m.a22;
+    for (int t = 0; t < j; t++) { rx += m.a12; ry += m.a22; }
+    float WX = rx - (float)half * m.a11, WY = ry - (float)half * m.a21;
+    const int i0 = q * CHUNK;
+    for (int t = 0; t < i0; t++) { WX += m.a11; WY += m.a21; }
+    const int i1 = min(R, i0 + CHUNK);
+    for (int i = i0; i < i1; i++) {
+      S[(size_t)j * R + i] = sample_image(img, w, h, WX, WY);
+      WX += m.a11; WY += m.a21;
+    }
+  }
+}
+
+// phase 2a: row pass at the 2*ps needed columns for L2_ROWS rows of one region: T[y][ci]
+__global__ void __launch_bounds__(256)
+k_large_rowpass(const PatchMeta* __restrict__ metas, int nreg, const int* __restrict__ pre,
+                const float* __restrict__ taps_all, float* __restrict__ scratch, int ps) {
+  extern __shared__ float sm[];
+  const int reg = find_region(pre, nreg, blockIdx.x);
+  const PatchMeta m = metas[reg];
+  const int R = m.R, ks = m.ks, nc = 2 * ps;
+  const int row0 = (blockIdx.x - pre[reg]) * L2_ROWS;
+  const int nrows = min(L2_ROWS, R - row0);
+  float* P = sm;              // ps
+  float* kk = P + MAX_PS;     // ks <= 640
+  float* rows = kk + 640;     // nrows x R
+  const float* S = scratch + m.scratch_off;
+  float* T = scratch + m.scratch_off + (size_t)R * R;
+  for (int i = threadIdx.x; i < ks; i += blockDim.x) kk[i] = taps_all[m.tap_off + i];
+  for (int i = threadIdx.x; i < nrows * R; i += blockDim.x) rows[i] = S[(size_t)row0 * R + i];
+  if (threadIdx.x == 0) {
+    float p = (float)(R / 2) - (float)(ps / 2) * m.scale;
+    for (int i = 0; i < ps; i++) { P[i] = p; p += m.scale; }
+  }
+  __syncthreads();
+  for (int it = threadIdx.x; it < nrows * nc; it += blockDim.x) {
+    const int yr = it / nc, ci = it - yr * nc;
+    const int x = needed_pos(P[ci >> 1], ci & 1, R);
+    T[(size_t)(row0 + yr) * nc + ci] = row_pass_at(rows + yr * R, R, x, kk, ks);
+  }
+}
+
+// phase 2b + 3: column pass at the needed rows of L3_OUT_ROWS output rows, then the final resampling
+__global__ void __launch_bounds__(256)
+k_large_colpass_final(const PatchMeta* __restrict__ metas, const float* __restrict__ taps_all,
+                      const float* __restrict__ scratch, uint8_t* __restrict__ out, int ps) {
+  extern __shared__ float sm[];
+  const int nblk = (ps + L3_OUT_ROWS - 1) / L3_OUT_ROWS;
+  const int reg = blockIdx.x / nblk, j0 = (blockIdx.x - reg * nblk) * L3_OUT_ROWS;
+  const PatchMeta m = metas[reg];
+  const int R = m.R, ks = m.ks, nc = 2 * ps, r = ks >> 1;
+  const int nout = min(L3_OUT_ROWS, ps - j0);
+  float* P = sm;
+  float* kk = P + MAX_PS;
+  float* B = kk + 640;        // (2*nout) x nc
+  const float* T = scratch + m.scratch_off + (size_t)R * R;
+  for (int i = threadIdx.x; i < ks; i += blockDim.x) kk[i] = taps_all[m.tap_off + i];
+  if (threadIdx.x == 0) {
+    float p = (float)(R / 2) - (float)(ps / 2) * m.scale;
+    for (int i = 0; i < ps; i++) { P[i] = p; p += m.scale; }
+  }
+  __syncthreads();
+  const int wc = R & ~7;
+  for (int it = threadIdx.x; it < 2 * nout * nc; it += blockDim.x) {
+    const int rl = it / nc, ci = it - rl * nc;
+    const int ri = 2 * j0 + rl;
+    const int y = needed_pos(P[ri >> 1], ri & 1, R), x = needed_pos(P[ci >> 1], ci & 1, R);
+    auto TY = [&](int yy) { return T[(size_t)clampi(yy, 0, R - 1) * nc + ci]; };
+    float s = TY(y) * kk[r];
+    if (x < wc) {
+      for (int t = 1; t <= r; t++) s = fmaf(TY(y - t) + TY(y + t), kk[r + t], s);
+    } else {
+      for (int t = 1; t <= r; t++) s = s + (TY(y - t) + TY(y + t)) * kk[r + t];
+    }
+    B[rl * nc + ci] = s;
+  }
+  __syncthreads();
+  uint8_t* dst = out + (size_t)m.out_index * ps * ps;
+  for (int it = threadIdx.x; it < nout * ps; it += blockDim.x) {
+    const int jl = it / ps, i = it - jl * ps, j = j0 + jl;
+    const float WX = P[i], WY = P[j];
+    const int x = (int)floorf(WX), y = (int)floorf(WY);
+    float v = 0.f;
+    if (WX >= 0 && WY >= 0 && x < R - 1 && y < R - 1) {
+      const float* r0 = B + (2 * jl) * nc + 2 * i;
+      const float* r1 = r0 + nc;
+      const float wx = WX - (float)x;
+      const float I1 = wx * (r0[1] - r0[0]) + r0[0];
+      v = (WY - (float)y) * (wx * (r1[1] - r1[0]) + r1[0] - I1) + I1;
+    }
+    int q = __float2int_rn(v);
+    dst[j * ps + i] = (uint8_t)(q < 0 ? 0 : (q > 255 ? 255 : q));
+  }
+}
+
 constexpr int SMEM_SMALL = (MAX_PS + 2 * SMALL_R + 32 + 2 * SMALL_R * SMALL_R) * 4;
-constexpr int SMEM_LARGE = (MAX_PS + 2 * MAX_R + 640 + (2 * MAX_PS) * (2 * MAX_PS)) * 4;
+constexpr int SMEM_L3 = (MAX_PS + 640 + 2 * L3_OUT_ROWS * 2 * MAX_PS) * 4;
 
 }  // namespace
 
@@ -266,41 +361,58 @@ int mg_sample_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
       small.push_back(m);
     }
   }
-  // biggest windows first so the tail of the launch is short
-  std::sort(large.begin(), large.end(), [](const PatchMeta& a, const PatchMeta& b) { return a.R > b.R; });
+  // prefix sums of the per-region block counts of the two row-blocked phases
+  const int nl = (int)large.size();
+  std::vector<int> pre1(nl + 1, 0), pre2(nl + 1, 0);
+  int maxR = 0;
+  for (int i = 0; i < nl; i++) {
+    pre1[i + 1] = pre1[i] + ceil_div(large[i].R, L1_ROWS);
+    pre2[i + 1] = pre2[i] + ceil_div(large[i].R, L2_ROWS);
+    maxR = std::max(maxR, large[i].R);
+  }
   const size_t nm = small.size() + large.size();
-  MG_CUDA(ctx, ctx->h_stage2.ensure(nm * sizeof(PatchMeta) + taps_all.size() * 4 + 64));
-  PatchMeta* hm = ctx->h_stage2.as<PatchMeta>();
-  if (!small.empty()) memcpy(hm, small.data(), small.size() * sizeof(PatchMeta));
-  if (!large.empty()) memcpy(hm + small.size(), large.data(), large.size() * sizeof(PatchMeta));
-  float* ht = reinterpret_cast<float*>(hm + nm);
-  if (!taps_all.empty()) memcpy(ht, taps_all.data(), taps_all.size() * 4);
-  MG_CUDA(ctx, ctx->smp_meta.ensure(nm * sizeof(PatchMeta)));
-  MG_CUDA(ctx, ctx->smp_taps.ensure(taps_all.size() * 4 + 16));
+  const size_t meta_bytes = nm * sizeof(PatchMeta), taps_bytes = taps_all.size() * 4, pre_bytes = (size_t)(nl + 1) * 4;
+  MG_CUDA(ctx, ctx->h_stage2.ensure(meta_bytes + taps_bytes + 2 * pre_bytes + 64));
+  uint8_t* hb = ctx->h_stage2.as<uint8_t>();
+  if (!small.empty()) memcpy(hb, small.data(), small.size() * sizeof(PatchMeta));
+  if (!large.empty()) memcpy(hb + small.size() * sizeof(PatchMeta), large.data(), large.size() * sizeof(PatchMeta));
+  if (!taps_all.empty()) memcpy(hb + meta_bytes, taps_all.data(), taps_bytes);
+  memcpy(hb + meta_bytes + taps_bytes, pre1.data(), pre_bytes);
+  memcpy(hb + meta_bytes + taps_bytes + pre_bytes, pre2.data(), pre_bytes);
+  // one upload: [metas | taps | pre1 | pre2]
+  MG_CUDA(ctx, ctx->smp_meta.ensure(meta_bytes + taps_bytes + 2 * pre_bytes + 64));
   MG_CUDA(ctx, ctx->smp_scratch.ensure((size_t)scratch * 4 + 16));
-  MG_CUDA(ctx, cudaMemcpyAsync(ctx->smp_meta.p, hm, nm * sizeof(PatchMeta), cudaMemcpyHostToDevice, ctx->stream));
-  if (!taps_all.empty())
-    MG_CUDA(ctx, cudaMemcpyAsync(ctx->smp_taps.p, ht, taps_all.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  MG_CUDA(ctx, cudaMemcpyAsync(ctx->smp_meta.p, hb, meta_bytes + taps_bytes + 2 * pre_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  const PatchMeta* dm = ctx->smp_meta.as<PatchMeta>();
+  const float* dtaps = reinterpret_cast<const float*>(ctx->smp_meta.as<uint8_t>() + meta_bytes);
+  const int* dpre1 = reinterpret_cast<const int*>(ctx->smp_meta.as<uint8_t>() + meta_bytes + taps_bytes);
+  const int* dpre2 = reinterpret_cast<const int*>(ctx->smp_meta.as<uint8_t>() + meta_bytes + taps_bytes + pre_bytes);
   static bool attr_set = false;
   if (!attr_set) {
-    MG_CUDA(ctx, cudaFuncSetAttribute(k_sample<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SMALL));
-    MG_CUDA(ctx, cudaFuncSetAttribute(k_sample<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LARGE));
+    MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_small, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SMALL));
+    MG_CUDA(ctx, cudaFuncSetAttribute(k_large_rowpass, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (MAX_PS + 640 + L2_ROWS * MAX_R) * 4));
     attr_set = true;
   }
-  const PatchMeta* dm = ctx->smp_meta.as<PatchMeta>();
   double bytes_small = 0, bytes_large = 0;   // algorithmic: R*R*4 read + ps*ps written per region
   for (const PatchMeta& m : small) bytes_small += (double)m.R * m.R * 4.0 + (double)ps * ps;
   for (const PatchMeta& m : large) bytes_large += (double)m.R * m.R * 4.0 + (double)ps * ps;
   if (!small.empty()) {
-    MG_PROF(ctx, "k_sample<small>", 0, bytes_small);
-    k_sample<false><<<(unsigned)small.size(), 128, SMEM_SMALL, ctx->stream>>>(
-        img->d, img->w, img->h, dm, ctx->smp_taps.as<float>(), nullptr, d_out, ps);
+    MG_PROF(ctx, "k_sample_small", 0, bytes_small);
+    k_sample_small<<<(unsigned)small.size(), 128, SMEM_SMALL, ctx->stream>>>(img->d, img->w, img->h, dm, dtaps, d_out, ps);
     MG_LAUNCHED(ctx);
   }
-  if (!large.empty()) {
-    MG_PROF(ctx, "k_sample<large>", 0, bytes_large);
-    k_sample<true><<<(unsigned)large.size(), 256, SMEM_LARGE, ctx->stream>>>(
-        img->d, img->w, img->h, dm + small.size(), ctx->smp_taps.as<float>(), ctx->smp_scratch.as<float>(), d_out, ps);
+  if (nl > 0) {
+    const PatchMeta* dl = dm + small.size();
+    float* scr = ctx->smp_scratch.as<float>();
+    MG_PROF(ctx, "k_large_resample", 0, bytes_large);
+    k_large_resample<<<pre1[nl], 128, 0, ctx->stream>>>(img->d, img->w, img->h, dl, nl, dpre1, scr);
+    MG_LAUNCHED(ctx);
+    MG_PROF(ctx, "k_large_rowpass", 2, (double)nl);
+    k_large_rowpass<<<pre2[nl], 256, (MAX_PS + 640 + L2_ROWS * maxR) * 4, ctx->stream>>>(dl, nl, dpre2, dtaps, scr, ps);
+    MG_LAUNCHED(ctx);
+    MG_PROF(ctx, "k_large_colpass_final", 2, (double)nl);
+    k_large_colpass_final<<<nl * ceil_div(ps, L3_OUT_ROWS), 256, SMEM_L3, ctx->stream>>>(dl, dtaps, scr, d_out, ps);
     MG_LAUNCHED(ctx);
   }
   return 0;

@@ -84,7 +84,10 @@ struct modsgpu_ctx {
   Profiler prof;
   cudaEvent_t tm0 = nullptr, tm1 = nullptr;   // modsgpu_timer_*
   DevBuf l2flush;
+  std::vector<std::pair<float*, size_t>> img_pool;   // recycled image buffers (cudaFree would sync the device)
 };
+
+cudaError_t mg_image_alloc(modsgpu_ctx* ctx, size_t bytes, float** out);
 
 void mg_prof_begin(modsgpu_ctx* ctx, const char* name, int kind, double work);
 void mg_prof_end(modsgpu_ctx* ctx);

@@ -410,7 +410,7 @@ extern "C" int modsgpu_image_from_bgr8(modsgpu_ctx* ctx, const uint8_t* bgr, int
   MG_CUDA(ctx, ctx->io_a.ensure(n * 3));
   modsgpu_image* img = new modsgpu_image();
   img->w = w; img->h = h;
-  MG_CUDA(ctx, cudaMalloc(&img->d, n * sizeof(float)));
+  MG_CUDA(ctx, mg_image_alloc(ctx, n * sizeof(float), &img->d));
   MG_CUDA(ctx, cudaMemcpyAsync(ctx->io_a.p, bgr, n * 3, cudaMemcpyHostToDevice, ctx->stream));
   MG_PROF(ctx, "k_gray_from_bgr", 0, (double)n * 7.0);
   k_gray_from_bgr<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->io_a.as<uint8_t>(), img->d, (long)n);
@@ -425,7 +425,7 @@ extern "C" int modsgpu_image_from_gray32f(modsgpu_ctx* ctx, const float* gray, i
   if (mg_begin(ctx)) return MODSGPU_ECUDA;
   modsgpu_image* img = new modsgpu_image();
   img->w = w; img->h = h;
-  MG_CUDA(ctx, cudaMalloc(&img->d, (size_t)w * h * sizeof(float)));
+  MG_CUDA(ctx, mg_image_alloc(ctx, (size_t)w * h * sizeof(float), &img->d));
   MG_CUDA(ctx, cudaMemcpy2DAsync(img->d, (size_t)w * 4, gray, (size_t)stride * 4, (size_t)w * 4, h, cudaMemcpyHostToDevice, ctx->stream));
   if (mg_end(ctx)) return MODSGPU_ECUDA;
   *out = img;
@@ -441,10 +441,22 @@ extern "C" int modsgpu_image_download(modsgpu_ctx* ctx, const modsgpu_image* img
 
 extern "C" void modsgpu_image_size(const modsgpu_image* img, int* w, int* h) { *w = img->w; *h = img->h; }
 
+cudaError_t mg_image_alloc(modsgpu_ctx* ctx, size_t bytes, float** out) {
+  for (size_t i = 0; i < ctx->img_pool.size(); i++)
+    if (ctx->img_pool[i].second == bytes) {
+      *out = ctx->img_pool[i].first;
+      ctx->img_pool.erase(ctx->img_pool.begin() + i);
+      return cudaSuccess;
+    }
+  return cudaMalloc((void**)out, bytes);
+}
+
 extern "C" void modsgpu_image_free(modsgpu_ctx* ctx, modsgpu_image* img) {
-  (void)ctx;
   if (!img) return;
-  if (img->d) cudaFree(img->d);
+  if (img->d) {
+    if (ctx && ctx->img_pool.size() < 16) ctx->img_pool.emplace_back(img->d, (size_t)img->w * img->h * sizeof(float));
+    else cudaFree(img->d);
+  }
   delete img;
 }
 

@@ -190,6 +190,344 @@ k_sample_small(const float* __restrict__ img, int w, int h, const PatchMeta* __r
   }
 }
 
+// =================================================================================================
+// Register-blocked kernels (the common case: ks >= 7).
+//
+// What bounds the sampler is instruction issue and L1 tag bandwidth, not HBM: the image (3 MB) is L2/L1
+// resident and a region costs R^2 bilinear gathers plus ~18 R^2 (pairs form) / 2 ks R^2 (full form)
+// sequentially ordered FMAs.  Two rules shape the kernels below:
+//  (1) gathers are issued by 8 lanes walking 8 CONSECUTIVE samples of a row (a warp = 4 such groups, usually
+//      32 consecutive samples): a load touches 2-4 cache lines instead of 32.  The reference accumulates
+//      sample coordinates sequentially in float (WX += a11), so one thread per row first walks its whole row
+//      and records the coordinate of every 8th sample (C2 table); a lane then replays <= 7 additions.
+//  (2) the separable blur is register blocked: a thread owns CB adjacent columns x RB rows, loads one tap and
+//      RB samples per step and issues RB*CB FMAs on them (taps rotate through registers), instead of
+//      two shared-memory loads and a clamp per FMA.  Borders are replicated into padding so the inner loops
+//      have no clamps; zero taps appended to the tap array keep the FMA chains bit-exact (fma(d, 0, s) == s).
+// Only the columns/rows the final 32x32 resampling reads are filtered when R >= 66 (pairs x_i, x_i + 1).
+// =================================================================================================
+constexpr int SEG = 8;
+constexpr int NT = 256;
+
+__device__ __forceinline__ int fast_div(int a, float inv_b) { return (int)(((float)a + 0.5f) * inv_b); }
+
+// one thread per row: the float coordinate sequence of interpolate() (helpers.cpp:551-626), every SEG-th kept
+__device__ __forceinline__ void gen_row_starts(const PatchMeta& m, int j, int R, int nseg, float2* __restrict__ dst) {
+  const int half = R / 2;
+  float rx = m.x - (float)half * m.a12, ry = m.y - (float)half * m.a22;
+  for (int t = 0; t < j; t++) { rx += m.a12; ry += m.a22; }
+  float WX = rx - (float)half * m.a11, WY = ry - (float)half * m.a21;
+  for (int s = 0; s < nseg; s++) {
+    dst[s] = make_float2(WX, WY);
+#pragma unroll
+    for (int t = 0; t < SEG; t++) { WX += m.a11; WY += m.a21; }
+  }
+}
+
+// lane `sub` of an 8-lane group: sample i0 + sub of a row whose segment starts at coordinate c
+__device__ __forceinline__ float sample_seg(const float* __restrict__ img, int w, int h, float2 c, float a11, float a21, int sub) {
+  float WX = c.x, WY = c.y;
+#pragma unroll
+  for (int t = 0; t < SEG - 1; t++)
+    if (t < sub) { WX += a11; WY += a21; }
+  return sample_image(img, w, h, WX, WY);
+}
+
+// Row pass, vector form (x < R & ~3, ks >= 7): s = 0; s = fma(p[t], k[t], s), t = 0..ks-1, for CB adjacent
+// columns x0..x0+CB-1 of RB rows.  rows[b] points at padded index x0 (= sample x0 - r); kp has CB-1 zeros appended.
+template <int CB, int RB>
+__device__ __forceinline__ void rowpass_block(const float* (&rows)[RB], const float* __restrict__ kp, int ks,
+                                              float (&acc)[RB][CB]) {
+  float kq[CB];
+#pragma unroll
+  for (int c = 0; c < CB; c++) kq[c] = 0.f;
+#pragma unroll
+  for (int b = 0; b < RB; b++)
+#pragma unroll
+    for (int c = 0; c < CB; c++) acc[b][c] = 0.f;
+  const int nstep = ks + CB - 1;
+#pragma unroll 4
+  for (int u = 0; u < nstep; u++) {
+#pragma unroll
+    for (int c = CB - 1; c > 0; c--) kq[c] = kq[c - 1];
+    kq[0] = kp[u];
+#pragma unroll
+    for (int b = 0; b < RB; b++) {
+      const float d = rows[b][u];
+#pragma unroll
+      for (int c = 0; c < CB; c++) acc[b][c] = fmaf(d, kq[c], acc[b][c]);
+    }
+  }
+}
+
+// Column pass for RB vertically adjacent outputs y0..y0+RB-1 of one column; Tc points at padded row y0 (+r).
+// vec (x < R & ~7): s = T[y]*k[r]; s = fma(T[y-t] + T[y+t], k[r+t], s); else the unfused scalar tail.
+template <int RB>
+__device__ __forceinline__ void colpass_block(const float* __restrict__ Tc, int pitch, const float* __restrict__ k, int r,
+                                              bool vec, float (&out)[RB]) {
+  float dn[RB], up[RB];
+#pragma unroll
+  for (int i = 0; i < RB; i++) { dn[i] = up[i] = Tc[i * pitch]; out[i] = dn[i] * k[r]; }
+#pragma unroll 2
+  for (int t = 1; t <= r; t++) {
+#pragma unroll
+    for (int i = RB - 1; i > 0; i--) dn[i] = dn[i - 1];
+    dn[0] = Tc[-t * pitch];
+#pragma unroll
+    for (int i = 0; i < RB - 1; i++) up[i] = up[i + 1];
+    up[RB - 1] = Tc[(RB - 1 + t) * pitch];
+    const float kt = k[r + t];
+    if (vec) {
+#pragma unroll
+      for (int i = 0; i < RB; i++) out[i] = fmaf(dn[i] + up[i], kt, out[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < RB; i++) out[i] = out[i] + (dn[i] + up[i]) * kt;
+    }
+  }
+}
+
+__device__ __forceinline__ uint8_t quant_u8(float v) {
+  int q = __float2int_rn(v);
+  return (uint8_t)(q < 0 ? 0 : (q > 255 ? 255 : q));
+}
+
+// ---- class A: R <= 65, the whole R x R window is filtered ------------------------------------------------
+__host__ __device__ inline int a_smem_floats(int R, int r) {
+  const int nseg = (R + SEG - 1) / SEG, PS = (R + 2 * r + 4) | 1, PT = R | 1;
+  return 64 + 64 + 2 * R * nseg + R * PS + (R + 2 * r + 4) * PT;
+}
+
+__global__ void __launch_bounds__(NT)
+k_sample_a(const float* __restrict__ img, int w, int h, const PatchMeta* __restrict__ metas,
+           const float* __restrict__ taps_all, uint8_t* __restrict__ out, int ps) {
+  extern __shared__ float sm[];
+  const PatchMeta m = metas[blockIdx.x];
+  const int tid = threadIdx.x;
+  const int R = m.R, ks = m.ks, r = ks >> 1;
+  const int nseg = (R + SEG - 1) / SEG, PS = (R + 2 * r + 4) | 1, PT = R | 1;
+  float* P = sm;
+  float* kp = P + 64;
+  float2* C2 = reinterpret_cast<float2*>(kp + 64);
+  float* Sp = reinterpret_cast<float*>(C2 + R * nseg);
+  float* Tp = Sp + R * PS;
+  float* B = Sp;   // R x R, written after the row pass has consumed Sp
+
+  if (tid < ks + 3) kp[tid] = tid < ks ? taps_all[m.tap_off + tid] : 0.f;
+  if (tid == NT - 1) {
+    float p = (float)(R / 2) - (float)(ps / 2) * m.scale;
+    for (int i = 0; i < ps; i++) { P[i] = p; p += m.scale; }
+  }
+  if (tid < R) gen_row_starts(m, tid, R, nseg, C2 + tid * nseg);
+  __syncthreads();
+  // 1. first resampling
+  {
+    const int g = tid >> 3, sub = tid & 7, nit = R * nseg;
+    const float inv = 1.0f / (float)nseg;
+    for (int it = g; it < nit; it += NT / SEG) {
+      const int j = fast_div(it, inv), s = it - j * nseg;
+      const int i = s * SEG + sub;
+      const float v = sample_seg(img, w, h, C2[it], m.a11, m.a21, sub);
+      if (i < R) {
+        float* row = Sp + j * PS;
+        row[r + i] = v;
+        if (i == 0) for (int t = 0; t < r; t++) row[t] = v;
+        if (i == R - 1) for (int t = 0; t < r + 4; t++) row[r + R + t] = v;
+      }
+    }
+  }
+  __syncthreads();
+  // 2. row pass: blocks of 4 columns x 4 rows (rows rg + k*NRG: conflict-free with the odd pitch)
+  {
+    const int ncb = R >> 2, NRG = (R + 3) >> 2, nmain = ncb * NRG;
+    const float inv = 1.0f / (float)NRG;
+    for (int it = tid; it < nmain; it += NT) {
+      const int cb = fast_div(it, inv), rg = it - cb * NRG, x0 = cb * 4;
+      const float* rows[4];
+      int rowi[4];
+#pragma unroll
+      for (int b = 0; b < 4; b++) { rowi[b] = rg + b * NRG; rows[b] = Sp + min(rowi[b], R - 1) * PS + x0; }
+      float acc[4][4];
+      rowpass_block<4, 4>(rows, kp, ks, acc);
+#pragma unroll
+      for (int b = 0; b < 4; b++)
+        if (rowi[b] < R) {
+          float* t = Tp + (rowi[b] + r) * PT + x0;
+#pragma unroll
+          for (int c = 0; c < 4; c++) t[c] = acc[b][c];
+        }
+    }
+    // scalar tail columns x >= R & ~3
+    const int xt0 = R & ~3, nt = R - xt0;
+    for (int it = tid; it < nt * R; it += NT) {
+      const int y = it / nt, x = xt0 + (it - y * nt);
+      Tp[(y + r) * PT + x] = row_pass_at(Sp + y * PS + r, R, x, kp, ks);
+    }
+  }
+  __syncthreads();
+  // 3. replicate T above and below
+  for (int it = tid; it < (2 * r + 4) * R; it += NT) {
+    const int pr = it / R, x = it - pr * R;
+    if (pr < r) Tp[pr * PT + x] = Tp[r * PT + x];
+    else Tp[(R + pr) * PT + x] = Tp[(R - 1 + r) * PT + x];
+  }
+  __syncthreads();
+  // 4. column pass: 4 adjacent rows per thread, lanes along x
+  {
+    const int NRG = (R + 3) >> 2, nit = R * NRG, wc = R & ~7;
+    const float inv = 1.0f / (float)R;
+    for (int it = tid; it < nit; it += NT) {
+      const int rg = fast_div(it, inv), x = it - rg * R, y0 = rg * 4;
+      float o[4];
+      colpass_block<4>(Tp + (y0 + r) * PT + x, PT, kp, r, x < wc, o);
+#pragma unroll
+      for (int i = 0; i < 4; i++) if (y0 + i < R) B[(y0 + i) * R + x] = o[i];
+    }
+  }
+  __syncthreads();
+  // 5. second resampling + u8
+  uint8_t* dst = out + (size_t)m.out_index * ps * ps;
+  for (int it = tid; it < ps * ps; it += NT) {
+    const int j = it / ps, i = it - j * ps;
+    const float WX = P[i], WY = P[j];
+    const int x = (int)floorf(WX), y = (int)floorf(WY);
+    float v = 0.f;
+    if (WX >= 0 && WY >= 0 && x < R - 1 && y < R - 1) {
+      const float* r0 = B + y * R + x;
+      const float* r1 = r0 + R;
+      const float wx = WX - (float)x;
+      const float I1 = wx * (r0[1] - r0[0]) + r0[0];
+      v = (WY - (float)y) * (wx * (r1[1] - r1[0]) + r1[0] - I1) + I1;
+    }
+    dst[it] = quant_u8(v);
+  }
+}
+
+// ---- class B: 66 <= R <= 160 (scale >= 2): only the 64 columns / rows the final resampling reads ----------
+constexpr int B_NB = 32;     // rows sampled + row-filtered per iteration
+constexpr int B_TP = 65;     // pitch of T (64 needed columns)
+__host__ __device__ inline int b_smem_floats(int R, int r) {
+  const int nseg = (R + SEG - 1) / SEG, PS = (R + 2 * r + 2) | 1;
+  int u = 2 * R * nseg + B_NB * PS;      // C2 + S block, later reused for B (64 x 64)
+  if (u < 4096) u = 4096;
+  return 64 + 64 + 64 + u + (R + 2 * r + 2) * B_TP;
+}
+
+__global__ void __launch_bounds__(NT)
+k_sample_b(const float* __restrict__ img, int w, int h, const PatchMeta* __restrict__ metas,
+           const float* __restrict__ taps_all, uint8_t* __restrict__ out) {
+  constexpr int ps = 32;
+  extern __shared__ float sm[];
+  const PatchMeta m = metas[blockIdx.x];
+  const int tid = threadIdx.x;
+  const int R = m.R, ks = m.ks, r = ks >> 1;
+  const int nseg = (R + SEG - 1) / SEG, PS = (R + 2 * r + 2) | 1;
+  float* P = sm;
+  int* X = reinterpret_cast<int*>(P + 64);
+  float* kp = P + 128;
+  float2* C2 = reinterpret_cast<float2*>(kp + 64);
+  float* Sb = reinterpret_cast<float*>(C2 + R * nseg);
+  float* B = reinterpret_cast<float*>(C2);          // 64 x 64 once C2 / Sb are dead
+  int un = 2 * R * nseg + B_NB * PS;
+  if (un < 4096) un = 4096;
+  float* Tp = reinterpret_cast<float*>(C2) + un;
+
+  if (tid < ks + 1) kp[tid] = tid < ks ? taps_all[m.tap_off + tid] : 0.f;
+  if (tid == NT - 1) {
+    float p = (float)(R / 2) - (float)(ps / 2) * m.scale;
+    for (int i = 0; i < ps; i++) { P[i] = p; X[i] = (int)floorf(p); p += m.scale; }
+  }
+  if (tid < R) gen_row_starts(m, tid, R, nseg, C2 + tid * nseg);
+  __syncthreads();
+  const int xv = R & ~3;
+  for (int j0 = 0; j0 < R; j0 += B_NB) {
+    const int nrows = min(B_NB, R - j0);
+    // 1. sample nrows rows
+    {
+      const int g = tid >> 3, sub = tid & 7, nit = nrows * nseg;
+      const float inv = 1.0f / (float)nseg;
+      for (int it = g; it < nit; it += NT / SEG) {
+        const int jr = fast_div(it, inv), s = it - jr * nseg;
+        const int i = s * SEG + sub;
+        const float v = sample_seg(img, w, h, C2[(j0 + jr) * nseg + s], m.a11, m.a21, sub);
+        if (i < R) {
+          float* row = Sb + jr * PS;
+          row[r + i] = v;
+          if (i == 0) for (int t = 0; t < r; t++) row[t] = v;
+          if (i == R - 1) for (int t = 0; t < r + 2; t++) row[r + R + t] = v;
+        }
+      }
+    }
+    __syncthreads();
+    // 2. row pass at the 32 column pairs (x_i, x_i + 1): pair = tid >> 3, rows rg + 8k
+    {
+      const int pi = tid >> 3, rg = tid & 7, x0 = X[pi];
+      int rowi[4];
+#pragma unroll
+      for (int b = 0; b < 4; b++) rowi[b] = rg + 8 * b;
+      if (x0 + 1 < xv) {
+        const float* rows[4];
+#pragma unroll
+        for (int b = 0; b < 4; b++) rows[b] = Sb + min(rowi[b], nrows - 1) * PS + x0;
+        float acc[4][2];
+        rowpass_block<2, 4>(rows, kp, ks, acc);
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+          if (rowi[b] < nrows) {
+            float* t = Tp + (j0 + rowi[b] + r) * B_TP + 2 * pi;
+            t[0] = acc[b][0]; t[1] = acc[b][1];
+          }
+      } else {
+#pragma unroll 1
+        for (int b = 0; b < 4; b++)
+          if (rowi[b] < nrows) {
+            const float* row = Sb + rowi[b] * PS + r;
+            float* t = Tp + (j0 + rowi[b] + r) * B_TP + 2 * pi;
+            t[0] = row_pass_at(row, R, x0, kp, ks);
+            t[1] = row_pass_at(row, R, x0 + 1, kp, ks);
+          }
+      }
+    }
+    __syncthreads();
+  }
+  // 3. replicate T above and below
+  for (int it = tid; it < (2 * r + 2) * 64; it += NT) {
+    const int pr = it >> 6, c = it & 63;
+    if (pr < r) Tp[pr * B_TP + c] = Tp[r * B_TP + c];
+    else Tp[(R + pr) * B_TP + c] = Tp[(R - 1 + r) * B_TP + c];
+  }
+  __syncthreads();
+  // 4. column pass at the 32 row pairs (y_j, y_j + 1) x 64 columns
+  {
+    const int wc = R & ~7;
+    for (int it = tid; it < 32 * 64; it += NT) {
+      const int pj = it >> 6, ci = it & 63;
+      const int y0 = X[pj], xc = X[ci >> 1] + (ci & 1);
+      float o[2];
+      colpass_block<2>(Tp + (y0 + r) * B_TP + ci, B_TP, kp, r, xc < wc, o);
+      B[(2 * pj) * 64 + ci] = o[0];
+      B[(2 * pj + 1) * 64 + ci] = o[1];
+    }
+  }
+  __syncthreads();
+  // 5. second resampling + u8
+  uint8_t* dst = out + (size_t)m.out_index * ps * ps;
+  for (int it = tid; it < ps * ps; it += NT) {
+    const int j = it >> 5, i = it & 31;
+    const float WX = P[i], WY = P[j];
+    const int x = X[i], y = X[j];
+    float v = 0.f;
+    if (WX >= 0 && WY >= 0 && x < R - 1 && y < R - 1) {
+      const float* r0 = B + (2 * j) * 64 + 2 * i;
+      const float* r1 = r0 + 64;
+      const float wx = WX - (float)x;
+      const float I1 = wx * (r0[1] - r0[0]) + r0[0];
+      v = (WY - (float)y) * (wx * (r1[1] - r1[0]) + r1[0] - I1) + I1;
+    }
+    dst[it] = quant_u8(v);
+  }
+}
+
 // ---- large windows: flattened (region, row-block) work lists -------------------------------------------
 // pre[] = exclusive prefix sums of the per-region block counts; binary search maps blockIdx -> region
 __device__ __forceinline__ int find_region(const int* __restrict__ pre, int n, int b) {
@@ -318,15 +656,21 @@ constexpr int SMEM_L3 = (MAX_PS + 640 + 2 * L3_OUT_ROWS * 2 * MAX_PS) * 4;
 
 // Enqueue the sampler for n regions (host array) on ctx->stream; u8 patches land in d_out
 // (n * ps * ps bytes, region order).  No host synchronisation.
+// Regions are dealt into size classes (one launch each, shared memory sized for the class so that small
+// windows keep 4-8 CTAs per SM) and sorted by decreasing R inside a class (largest CTAs start first):
+//   A1 R <= 40, A2 R <= 65 : k_sample_a (whole window filtered)        B1 R <= 100, B2 R <= 160 : k_sample_b
+//   odd cases (direct mode, ks < 7, patchSize != 32 for B) : k_sample_small;  R > 160 : the 3-launch slab path
+constexpr int A1_R = 40, A2_R = 65, B1_R = 100, B2_R = 160;
+
 int mg_sample_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_region* regs, int n,
                       double mrSize, int ps, uint8_t* d_out) {
   if (ps < 2 || ps > MAX_PS) MG_FAIL(ctx, MODSGPU_EINVAL, "patchSize out of range");
   if (n <= 0) return 0;
-  std::vector<PatchMeta> small, large;
-  small.reserve(n);
-  std::map<int, std::pair<int, int>> tap_index;  // R0 -> (offset, ks)
+  enum { C_SMALL = 0, C_A1, C_A2, C_B1, C_B2, C_LARGE, NCLS };
+  std::vector<PatchMeta> cls[NCLS];
+  int cls_r[NCLS] = {0, 0, 0, 0, 0, 0};           // max blur radius per class
+  std::map<int, std::pair<int, int>> tap_index;   // R0 -> (offset, ks)
   std::vector<float> taps_all;
-  long long scratch = 0;
   for (int i = 0; i < n; i++) {
     const modsgpu_region& k = regs[i];
     PatchMeta m;
@@ -338,6 +682,7 @@ int mg_sample_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
     m.out_index = i;
     m.scratch_off = 0;
     m.ks = 0; m.tap_off = 0;
+    int c = C_SMALL;
     if (m.scale > 0.4) {
       m.R = R0 + 2;
       if (m.R > MAX_R) MG_FAIL(ctx, MODSGPU_EINVAL, "region too large for the sampler (R > 2048)");
@@ -350,16 +695,26 @@ int mg_sample_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
       }
       m.tap_off = it->second.first; m.ks = it->second.second;
       if (m.ks > 600) MG_FAIL(ctx, MODSGPU_EINVAL, "sampler blur too wide");
-      if (m.R <= SMALL_R && m.ks <= 31) small.push_back(m);
-      else {
-        m.scratch_off = scratch;
-        scratch += (long long)m.R * m.R + (long long)m.R * 2 * ps;
-        large.push_back(m);
-      }
+      const bool blocked = m.ks >= 7 && m.ks <= 60 && ps <= 64;
+      if (blocked && m.R <= A1_R) c = C_A1;
+      else if (blocked && m.R <= A2_R) c = C_A2;
+      else if (blocked && ps == 32 && R0 >= 2 * ps && m.R <= B1_R) c = C_B1;
+      else if (blocked && ps == 32 && R0 >= 2 * ps && m.R <= B2_R) c = C_B2;
+      else if (m.R <= SMALL_R && m.ks <= 31) c = C_SMALL;
+      else c = C_LARGE;
     } else {
       m.R = 0;
-      small.push_back(m);
     }
+    cls[c].push_back(m);
+    cls_r[c] = std::max(cls_r[c], m.ks >> 1);
+  }
+  for (int c = C_A1; c <= C_LARGE; c++)
+    std::stable_sort(cls[c].begin(), cls[c].end(), [](const PatchMeta& a, const PatchMeta& b) { return a.R > b.R; });
+  std::vector<PatchMeta>& large = cls[C_LARGE];
+  long long scratch = 0;
+  for (PatchMeta& m : large) {
+    m.scratch_off = scratch;
+    scratch += (long long)m.R * m.R + (long long)m.R * 2 * ps;
   }
   // prefix sums of the per-region block counts of the two row-blocked phases
   const int nl = (int)large.size();
@@ -370,12 +725,13 @@ int mg_sample_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
     pre2[i + 1] = pre2[i] + ceil_div(large[i].R, L2_ROWS);
     maxR = std::max(maxR, large[i].R);
   }
-  const size_t nm = small.size() + large.size();
+  size_t nm = 0, cls_off[NCLS];
+  for (int c = 0; c < NCLS; c++) { cls_off[c] = nm; nm += cls[c].size(); }
   const size_t meta_bytes = nm * sizeof(PatchMeta), taps_bytes = taps_all.size() * 4, pre_bytes = (size_t)(nl + 1) * 4;
   MG_CUDA(ctx, ctx->h_stage2.ensure(meta_bytes + taps_bytes + 2 * pre_bytes + 64));
   uint8_t* hb = ctx->h_stage2.as<uint8_t>();
-  if (!small.empty()) memcpy(hb, small.data(), small.size() * sizeof(PatchMeta));
-  if (!large.empty()) memcpy(hb + small.size() * sizeof(PatchMeta), large.data(), large.size() * sizeof(PatchMeta));
+  for (int c = 0; c < NCLS; c++)
+    if (!cls[c].empty()) memcpy(hb + cls_off[c] * sizeof(PatchMeta), cls[c].data(), cls[c].size() * sizeof(PatchMeta));
   if (!taps_all.empty()) memcpy(hb + meta_bytes, taps_all.data(), taps_bytes);
   memcpy(hb + meta_bytes + taps_bytes, pre1.data(), pre_bytes);
   memcpy(hb + meta_bytes + taps_bytes + pre_bytes, pre2.data(), pre_bytes);
@@ -392,20 +748,40 @@ int mg_sample_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
     MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_small, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SMALL));
     MG_CUDA(ctx, cudaFuncSetAttribute(k_large_rowpass, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (MAX_PS + 640 + L2_ROWS * MAX_R) * 4));
+    MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_a, cudaFuncAttributeMaxDynamicSharedMemorySize, a_smem_floats(A2_R, 30) * 4));
+    MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_b, cudaFuncAttributeMaxDynamicSharedMemorySize, b_smem_floats(B2_R, 30) * 4));
     attr_set = true;
   }
-  double bytes_small = 0, bytes_large = 0;   // algorithmic: R*R*4 read + ps*ps written per region
-  for (const PatchMeta& m : small) bytes_small += (double)m.R * m.R * 4.0 + (double)ps * ps;
-  for (const PatchMeta& m : large) bytes_large += (double)m.R * m.R * 4.0 + (double)ps * ps;
-  if (!small.empty()) {
-    MG_PROF(ctx, "k_sample_small", 0, bytes_small);
-    k_sample_small<<<(unsigned)small.size(), 128, SMEM_SMALL, ctx->stream>>>(img->d, img->w, img->h, dm, dtaps, d_out, ps);
+  // algorithmic bytes: R*R*4 read + ps*ps written per region
+  auto alg_bytes = [&](const std::vector<PatchMeta>& v) {
+    double b = 0;
+    for (const PatchMeta& m : v) b += (double)m.R * m.R * 4.0 + (double)ps * ps;
+    return b;
+  };
+  if (!cls[C_SMALL].empty()) {
+    MG_PROF(ctx, "k_sample_small", 0, alg_bytes(cls[C_SMALL]));
+    k_sample_small<<<(unsigned)cls[C_SMALL].size(), 128, SMEM_SMALL, ctx->stream>>>(img->d, img->w, img->h, dm, dtaps, d_out, ps);
+    MG_LAUNCHED(ctx);
+  }
+  const int a_maxR[2] = {A1_R, A2_R}, b_maxR[2] = {B1_R, B2_R};
+  for (int c = C_A1; c <= C_A2; c++) {
+    if (cls[c].empty()) continue;
+    const int smem = a_smem_floats(std::min(a_maxR[c - C_A1], cls[c][0].R), cls_r[c]) * 4;
+    MG_PROF(ctx, c == C_A1 ? "k_sample_a<R<=40>" : "k_sample_a<R<=65>", 0, alg_bytes(cls[c]));
+    k_sample_a<<<(unsigned)cls[c].size(), NT, smem, ctx->stream>>>(img->d, img->w, img->h, dm + cls_off[c], dtaps, d_out, ps);
+    MG_LAUNCHED(ctx);
+  }
+  for (int c = C_B1; c <= C_B2; c++) {
+    if (cls[c].empty()) continue;
+    const int smem = b_smem_floats(std::min(b_maxR[c - C_B1], cls[c][0].R), cls_r[c]) * 4;
+    MG_PROF(ctx, c == C_B1 ? "k_sample_b<R<=100>" : "k_sample_b<R<=160>", 0, alg_bytes(cls[c]));
+    k_sample_b<<<(unsigned)cls[c].size(), NT, smem, ctx->stream>>>(img->d, img->w, img->h, dm + cls_off[c], dtaps, d_out);
     MG_LAUNCHED(ctx);
   }
   if (nl > 0) {
-    const PatchMeta* dl = dm + small.size();
+    const PatchMeta* dl = dm + cls_off[C_LARGE];
     float* scr = ctx->smp_scratch.as<float>();
-    MG_PROF(ctx, "k_large_resample", 0, bytes_large);
+    MG_PROF(ctx, "k_large_resample", 0, alg_bytes(large));
     k_large_resample<<<pre1[nl], 128, 0, ctx->stream>>>(img->d, img->w, img->h, dl, nl, dpre1, scr);
     MG_LAUNCHED(ctx);
     MG_PROF(ctx, "k_large_rowpass", 2, (double)nl);

@@ -8,9 +8,9 @@ NVFLAGS = $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-ffp-contract=off -I
 # detect.cu / sampler.cu are the bit-exact integer/float paths: no FMA contraction
 EXACT = --fmad=false
 
-OBJS = $(OBJ)/api.o $(OBJ)/detect.o $(OBJ)/sampler.o $(OBJ)/cnn.o $(OBJ)/match.o $(OBJ)/ransac.o $(OBJ)/npz.o $(OBJ)/mods_host.o
+OBJS = $(OBJ)/api.o $(OBJ)/detect.o $(OBJ)/sampler.o $(OBJ)/cnn.o $(OBJ)/match.o $(OBJ)/ransac.o $(OBJ)/ransac_f.o $(OBJ)/npz.o $(OBJ)/mods_host.o
 
-all: $(PKG)/libmodsgpu.so oracle
+all: $(PKG)/libmodsgpu.so $(PKG)/libmodsgpu_degensac.so oracle
 
 $(OBJ)/detect.o: $(SRC)/detect.cu $(SRC)/common.cuh include/modsgpu.h
 	@mkdir -p $(OBJ)
@@ -18,7 +18,10 @@ $(OBJ)/detect.o: $(SRC)/detect.cu $(SRC)/common.cuh include/modsgpu.h
 $(OBJ)/sampler.o: $(SRC)/sampler.cu $(SRC)/common.cuh include/modsgpu.h
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVFLAGS) $(EXACT) -c $< -o $@
-$(OBJ)/ransac.o: $(SRC)/ransac.cu $(SRC)/common.cuh include/modsgpu.h
+$(OBJ)/ransac.o: $(SRC)/ransac.cu $(SRC)/ransac_common.cuh $(SRC)/common.cuh include/modsgpu.h
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) $(EXACT) -c $< -o $@
+$(OBJ)/ransac_f.o: $(SRC)/ransac_f.cu $(SRC)/ransac_common.cuh $(SRC)/common.cuh include/modsgpu.h
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVFLAGS) $(EXACT) -c $< -o $@
 $(OBJ)/%.o: $(SRC)/%.cu $(SRC)/common.cuh include/modsgpu.h
@@ -34,11 +37,15 @@ $(OBJ)/npz.o: $(SRC)/npz.cpp
 $(PKG)/libmodsgpu.so: $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lz -lcudart_static -lpthread -ldl -lrt
 
+# link-time drop-in for the reference's degensac target (exp_ransacHcustom / exp_ransacFcustom)
+$(PKG)/libmodsgpu_degensac.so: $(SRC)/compat/degensac_compat.cpp include/modsgpu.h $(PKG)/libmodsgpu.so
+	g++ -O2 -std=c++17 -fPIC -shared -o $@ $< -L$(PKG) -lmodsgpu -Wl,-rpath,'$$ORIGIN'
+
 oracle:
 	$(MAKE) -C oracle -s all
 
 clean:
-	rm -rf $(OBJ) $(PKG)/libmodsgpu.so
+	rm -rf $(OBJ) $(PKG)/libmodsgpu.so $(PKG)/libmodsgpu_degensac.so
 	$(MAKE) -C oracle clean
 
 .PHONY: all oracle clean

@@ -158,6 +158,13 @@ typedef struct {
 int  modsgpu_ransac_H(modsgpu_ctx* ctx, const double* u, int T, const modsgpu_ransac_params* p,
                       double* H, unsigned char* inl, modsgpu_ransac_result* res);
 
+/* replaces exp_ransacFcustom degensac/exp_ranF.h:71-73 as called from LORANSACFiltering matching.cpp:722
+ * (7-point sample, oriented epipolar constraint, Sampson error, MSAC, symmetric check, LO).  F: 9 doubles with
+ * u2^T M u1 = 0, M[k][l] = F[3k+l] (the degensac convention, Ftools.c:15-37).  res->oc_rejects counts models
+ * discarded by the symmetric check.  The DEGENSAC plane-and-parallax branch is not implemented. */
+int  modsgpu_ransac_F(modsgpu_ctx* ctx, const double* u, int T, const modsgpu_ransac_params* p,
+                      double* F, unsigned char* inl, modsgpu_ransac_result* res);
+
 /* ---- whole pair (what one iteration of mods.cpp:202-356 does for the deep configuration
  *      config_aff_ori_desc_zeromq.ini + iters_HessianZMQ.ini, vector_matcher = linear):
  *      SynthDetectDescribeKeypoints x 2 -> MatchFlannFGINN -> DuplicateFiltering -> LORANSACFiltering.

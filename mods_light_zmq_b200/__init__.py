@@ -245,6 +245,18 @@ class ModsGpu:
         return dict(H=H, inl=inl[:T], I=res.n_inliers, J=res.J, samples=res.samples, lo_count=res.lo_runs,
                     oc_rejects=res.oc_rejects)
 
+    def ransac_F(self, u, th=16.0, conf=0.99, max_samples=1000000, sym_check=1, seed=12345):
+        """modsgpu_ransac_F: LO-RANSAC for a fundamental matrix (exp_ransacFcustom, matching.cpp:722)."""
+        u = np.ascontiguousarray(u, np.float64)
+        T = len(u)
+        p = RansacParams(th, conf, 1000 if T <= 20 else max_samples, sym_check, seed)
+        F = np.zeros(9, np.float64)
+        inl = np.zeros(max(T, 1), np.uint8)
+        res = RansacResult()
+        self._check(self.lib.modsgpu_ransac_F(self.ctx, _p(u), T, C.byref(p), _p(F), _p(inl), C.byref(res)))
+        return dict(F=F, inl=inl[:T], I=res.n_inliers, J=res.J, samples=res.samples, lo_count=res.lo_runs,
+                    sym_rejects=res.oc_rejects)
+
 
 def _pair_dict(res, xy):
     return dict(keypoints=list(res.keypoints), regions=list(res.regions), descriptors=list(res.descriptors),

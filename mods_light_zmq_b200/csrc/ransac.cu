@@ -20,19 +20,14 @@
 // LAPACK dsyev_ (lapwrap.c:75-97; third-party, unpinned); (3) the inlier-set hash that prunes repeated
 // LO iterations (exp_ranH.c __HASHING__) is dropped -- it only skips work whose result is already known.
 #include "common.cuh"
+#include "ransac_common.cuh"
 #include <cmath>
 #include <algorithm>
 
 namespace {
 
-constexpr int RS_MAX_B = 4096;
-constexpr int LO_REPS = 10;       // RAN_REP, rtools.h:8
-constexpr int ILSQ_ITERS = 4;     // rtools.h:9
-constexpr double TC = 4.0;        // rtools.h:10
-constexpr double MWM = 2.0;       // rtools.h:33: (9/4) in integer arithmetic
 constexpr double CHECK_COEF = 9.0;
 constexpr int MIN_GOOD_SYM_PTS = 5;
-constexpr int ITER_SAM = 50;
 
 struct RsState {
   double H[9];            // best model (maxS)
@@ -43,28 +38,6 @@ struct RsState {
 };
 
 struct HypOut { double H[9]; double J; int I; int flag; };   // flag: 0 ok, 1 oriented-constraint reject, 2 degenerate
-
-__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
-  z += 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  return z ^ (z >> 31);
-}
-__device__ __forceinline__ unsigned rs_rand(unsigned long long seed, unsigned long long stream, unsigned draw, unsigned range) {
-  return (unsigned)(mix64(seed ^ mix64(stream * 0x100000001B3ull + draw)) % range);
-}
-
-__device__ __forceinline__ double truncQuad(double eps, double thr) {
-  if (thr == 0) return 0;
-  if (eps >= thr * 9 / 4) return 0;
-  return 1 - (eps / (thr * 9 / 4));
-}
-
-__device__ __forceinline__ double det3(const double* A) {
-  double r = (A[0] * A[4] * A[8] + A[2] * A[3] * A[7] + A[1] * A[5] * A[6]);
-  r -= (A[2] * A[4] * A[6] + A[0] * A[5] * A[7] + A[1] * A[3] * A[8]);
-  return r;
-}
 
 // exp_ranH.c:883-892 / :1021-1032: reject H close to singular
 __device__ __forceinline__ bool det_ok(const double* h) {
@@ -108,17 +81,6 @@ __device__ __forceinline__ double sampson(const double* H, const double* u) {
   return p;
 }
 
-__device__ __forceinline__ bool inv3(const double* A, double* R) {
-  const double c0 = A[4] * A[8] - A[5] * A[7], c1 = A[5] * A[6] - A[3] * A[8], c2 = A[3] * A[7] - A[4] * A[6];
-  const double det = A[0] * c0 + A[1] * c1 + A[2] * c2;
-  if (det == 0 || !isfinite(det)) return false;
-  const double id = 1.0 / det;
-  R[0] = c0 * id; R[1] = (A[2] * A[7] - A[1] * A[8]) * id; R[2] = (A[1] * A[5] - A[2] * A[4]) * id;
-  R[3] = c1 * id; R[4] = (A[0] * A[8] - A[2] * A[6]) * id; R[5] = (A[2] * A[3] - A[0] * A[5]) * id;
-  R[6] = c2 * id; R[7] = (A[1] * A[6] - A[0] * A[7]) * id; R[8] = (A[0] * A[4] - A[1] * A[3]) * id;
-  return true;
-}
-
 // Htools.c:201-242 HDsSym for one correspondence; Hm = row-major 2->1 map, H1 = its inverse
 __device__ __forceinline__ double sym_err(const double* Hm, const double* H1, const double* u) {
   const double a = H1[6] * u[0] + H1[7] * u[1] + H1[8];
@@ -129,17 +91,6 @@ __device__ __forceinline__ double sym_err(const double* Hm, const double* H1, co
   xa = (Hm[0] * u[3] + Hm[1] * u[4] + Hm[2]) / b; ya = (Hm[3] * u[3] + Hm[4] * u[4] + Hm[5]) / b;
   xd = u[0] - xa; yd = u[1] - ya;
   return d1 + (xd * xd + yd * yd);
-}
-
-__device__ __forceinline__ double warp_sum_d(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-__device__ __forceinline__ int warp_sum_i(int v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
 }
 
 // utools.c:97-167 nullspace() on the 9x9 (8 rows + zero row) system; returns the nullity and, when it is 1,
@@ -182,9 +133,6 @@ __device__ __forceinline__ void dlt_rows(const double* u, double* r1, double* r2
 }
 
 // Htools.c:526-551 all_Hori_valid
-__device__ __forceinline__ void cross3(double* o, const double* a, const double* b) {
-  o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
-}
 __device__ bool all_Hori_valid(const double* us, const int* idx) {
   const double *a = us + 6 * idx[0], *b = us + 6 * idx[1], *c = us + 6 * idx[2], *d = us + 6 * idx[3];
   double p[3], q[3];
@@ -217,20 +165,6 @@ __device__ void score_all(const double* __restrict__ u, int T, const double* H, 
   }
   *I = warp_sum_i(ci);
   *J = warp_sum_d(cj);
-}
-
-// warp-wide: indices j (ascending) with d[j] <= th into idx[]; returns the count  (rtools.c inlidxs)
-__device__ int compact_inliers(const double* d, int T, double th, int* idx, int lane) {
-  int n = 0;
-  for (int base = 0; base < T; base += 32) {
-    const int j = base + lane;
-    const bool in = j < T && d[j] <= th;
-    const unsigned m = __ballot_sync(0xffffffffu, in);
-    if (in) idx[n + __popc(m & ((1u << lane) - 1))] = j;
-    n += __popc(m);
-  }
-  __syncwarp();
-  return n;
 }
 
 // warp-wide normalised-DLT least squares (u2h, Htools.c:100-132: normu + lin_hgN + cov_mat + smallest
@@ -364,19 +298,6 @@ __device__ bool sym_check_ok(const double* __restrict__ u, int T, const double* 
   int c = 0;
   for (int j = lane; j < T; j += 32) if (sym_err(Hm, H1, u + 6 * j) <= CHECK_COEF * th) c++;
   return warp_sum_i(c) > MIN_GOOD_SYM_PTS;
-}
-
-// rtools.c:196-224
-__device__ int nsamples(int ninl, int ptNum, int samsiz, double conf) {
-  double a = 1, b = 1;
-  for (int i = 0; i < samsiz; i++) { a *= ninl - i; b *= ptNum - i; }
-  a = a / b;
-  if (a < 2.2204e-16) return 1000000;
-  a = 1 - a;
-  if (a < 2.2204e-16) return 1;
-  b = log(1 - conf) / log(a);
-  if (b > 1000000) return 1000000;
-  return (int)ceil(b);
 }
 
 // exp_iterHcustom (exp_ranH.c:617-737) for one inner sample, warp-wide.  d0 = errors of the start model h.

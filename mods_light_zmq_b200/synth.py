@@ -74,3 +74,44 @@ def image_pair(seed=1234, w=1024, h=768):
     H = pair_homography(w, h)
     b = warp_image(a, H, noise_seed=seed + 3087)
     return a, b, H
+
+
+def two_view_correspondences(seed, T, n_in, noise=0.5, w=1024, h=768, planar_fraction=0.0):
+    """Seeded general two-view scene for the fundamental-matrix tests: n_in 3-D points (depth 4..12, optionally a
+    fraction on one plane) seen by two cameras (focal 900 px; rotation ~12 deg about y, ~4 deg about x, baseline
+    (1, 0.1, 0.2)) + Gaussian pixel noise, T - n_in uniformly random mismatches.  Returns (u [T x 6], F_true [3 x 3]
+    with x2^T F x1 = 0, inlier mask)."""
+    rng = np.random.RandomState(seed)
+    K = np.array([[900.0, 0, w / 2], [0, 900.0, h / 2], [0, 0, 1]])
+    ay, ax = np.deg2rad(12.0), np.deg2rad(4.0)
+    Ry = np.array([[np.cos(ay), 0, np.sin(ay)], [0, 1, 0], [-np.sin(ay), 0, np.cos(ay)]])
+    Rx = np.array([[1, 0, 0], [0, np.cos(ax), -np.sin(ax)], [0, np.sin(ax), np.cos(ax)]])
+    R = Ry @ Rx
+    t = np.array([1.0, 0.1, 0.2])
+    X = np.c_[rng.uniform(-4, 4, 4 * T), rng.uniform(-3, 3, 4 * T), rng.uniform(4, 12, 4 * T)]
+    npl = int(planar_fraction * len(X))
+    X[:npl, 2] = 8.0 + 0.15 * X[:npl, 0]
+    x1 = (K @ X.T).T
+    x1 = x1[:, :2] / x1[:, 2:3]
+    Xc = (R @ X.T).T + t
+    x2 = (K @ Xc.T).T
+    x2 = x2[:, :2] / x2[:, 2:3]
+    ok = (x1[:, 0] > 5) & (x1[:, 0] < w - 5) & (x1[:, 1] > 5) & (x1[:, 1] < h - 5) & \
+         (x2[:, 0] > 5) & (x2[:, 0] < w - 5) & (x2[:, 1] > 5) & (x2[:, 1] < h - 5) & (Xc[:, 2] > 0.5)
+    x1, x2 = x1[ok][:n_in], x2[ok][:n_in]
+    assert len(x1) == n_in, "not enough visible points"
+    x1 = x1 + rng.normal(0, noise, x1.shape)
+    x2 = x2 + rng.normal(0, noise, x2.shape)
+    no = T - n_in
+    o1 = np.c_[rng.uniform(0, w, no), rng.uniform(0, h, no)]
+    o2 = np.c_[rng.uniform(0, w, no), rng.uniform(0, h, no)]
+    u = np.ones((T, 6))
+    u[:n_in, 0:2], u[:n_in, 3:5] = x1, x2
+    u[n_in:, 0:2], u[n_in:, 3:5] = o1, o2
+    perm = rng.permutation(T)
+    mask = np.zeros(T, bool)
+    mask[:n_in] = True
+    tx = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]])
+    Ki = np.linalg.inv(K)
+    F = Ki.T @ tx @ R @ Ki
+    return u[perm], F / np.linalg.norm(F), mask[perm]

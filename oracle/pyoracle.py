@@ -268,3 +268,39 @@ def ref_ransac_H(u, th=16.0, conf=0.99, max_sam=1000000, seed_time=12345, sym_ch
     C.CDLL(None).free(resids)
     return dict(H=H, inl=inl, samples=int(data_out[0]), lo_count=int(data_out[1]), oc_rejects=int(data_out[2]),
                 I=int(S.I), J=float(S.J))
+
+
+def ref_ransac_F(u, th=16.0, conf=0.99, max_sam=1000000, seed_time=12345, sym_check=1):
+    """Calls the reference's exp_ransacFcustom exactly as matching.cpp:722 does (do_lo = 1, inlLimit = 0,
+    Sampson error functions exFDs / FDs).  Returns dict(F, inl, samples, lo_count, I, Ih)."""
+    L = ref()
+    u = np.ascontiguousarray(u, np.float64)
+    T = len(u)
+    F = np.zeros(9, np.float64)
+    Hin = np.zeros(9, np.float64)
+    inl = np.zeros(T, np.uint8)
+    data_out = np.zeros(T * 18 + 8, np.int32)   # exp_ranF.c:1029 increments data_out[LmaxI + 2]
+    resids = C.c_void_p()
+    Ih = C.c_int(0)
+    L.orc_ref_set_time(C.c_long(seed_time))
+    if T <= 20:
+        max_sam = 1000  # matching.cpp:644-645
+    L.exp_ransacFcustom.restype = C.c_int
+    I = L.exp_ransacFcustom(_p(u), T, C.c_double(th), C.c_double(conf), max_sam, _p(F), _p(inl), _p(data_out), 1,
+                            C.c_uint(0), C.byref(resids), _p(Hin), C.byref(Ih), C.cast(L.exFDs, C.c_void_p),
+                            C.cast(L.FDs, C.c_void_p), sym_check)
+    C.CDLL(None).free(resids)
+    return dict(F=F, inl=inl, samples=int(data_out[0]), lo_count=int(data_out[1]), I=int(I), Ih=int(Ih.value))
+
+
+def sampson_F(F, u):
+    """Ftools.c:83-101 FDs (numpy): squared Sampson error of every correspondence under F (degensac layout)."""
+    F = np.asarray(F, np.float64).ravel()
+    u = np.asarray(u, np.float64)
+    rxc = F[0] * u[:, 3] + F[3] * u[:, 4] + F[6]
+    ryc = F[1] * u[:, 3] + F[4] * u[:, 4] + F[7]
+    rwc = F[2] * u[:, 3] + F[5] * u[:, 4] + F[8]
+    r = u[:, 0] * rxc + u[:, 1] * ryc + rwc
+    rx = F[0] * u[:, 0] + F[1] * u[:, 1] + F[2]
+    ry = F[3] * u[:, 0] + F[4] * u[:, 1] + F[5]
+    return r * r / (rxc * rxc + ryc * ryc + rx * rx + ry * ry)

@@ -8,6 +8,7 @@
                     through the daemons' own nn.Sequential definitions (unfolded BatchNorm, torch CPU fp32)
   graf_counts.json  keypoint / region / descriptor counts of the oracle pipeline on the reference's
                     graf1/graf6 images, next to the README transcript values (README.md:47-61)
+  ransac_F_ref.npz  a seeded two-view scene + the result of the reference's own exp_ransacFcustom
   ransac_ref.npz    a seeded correspondence set + the result of the reference's own exp_ransacHcustom
                     (oracle/_ref/libdegensac_ref.so, time() pinned)
 """
@@ -141,8 +142,20 @@ def ransac_ref():
     print("ransac_ref.npz I=%d J=%.3f samples=%d lo=%d" % (r["I"], r["J"], r["samples"], r["lo_count"]))
 
 
+def ransac_F_ref():
+    """Seeded two-view scene + the result of the reference's own exp_ransacFcustom (oracle/_ref, time() pinned)."""
+    from oracle import pyoracle as O
+    from mods_light_zmq_b200 import synth
+    u, F_true, mask = synth.two_view_correspondences(21, 300, 170)
+    r = O.ref_ransac_F(u, th=16.0, seed_time=12345)
+    np.savez_compressed(os.path.join(HERE, "ransac_F_ref.npz"), u=u, F=r["F"], inl=r["inl"], I=r["I"], mask=mask,
+                        F_true=F_true, samples=r["samples"], lo=r["lo_count"])
+    print("ransac_F_ref.npz I=%d samples=%d lo=%d true inliers found %d" %
+          (r["I"], r["samples"], r["lo_count"], int((r["inl"].astype(bool) & mask).sum())))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["cv2", "cnn", "graf", "ransac"]
+    which = sys.argv[1:] or ["cv2", "cnn", "graf", "ransac", "ransacF"]
     if "cv2" in which:
         cv2_pins()
     if "cnn" in which:
@@ -151,3 +164,5 @@ if __name__ == "__main__":
         graf_counts()
     if "ransac" in which:
         ransac_ref()
+    if "ransacF" in which:
+        ransac_F_ref()

@@ -90,6 +90,37 @@ def test_reference_degensac_fixture(oracle):
     assert r["inl"][:150].sum() >= 145 and r["inl"][150:].sum() <= 3
 
 
+def test_reference_degensac_F_fixture(oracle):
+    """The reference's own exp_ransacFcustom (oracle/_ref) on the committed fixture: its model is the scene's
+    epipolar geometry and the stored result lies in the band the reference itself produces."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref/libdegensac_ref.so not built")
+    z = np.load(os.path.join(GOLD, "ransac_F_ref.npz"))
+    mask = z["mask"]
+    # NB the reference reads uninitialised heap in exp_ransacFcustom (errs[4] = errs[3] before any write,
+    # exp_ranF.c:870-872; data_out histogram :1029): with time() pinned its result still differs between the
+    # first and later calls of one process (I = 144..172 on this fixture).  So the fixture pins a band.
+    for _ in range(2):
+        r = oracle.ref_ransac_F(z["u"], th=16.0, seed_time=12345)
+        assert int(z["I"]) - 5 <= r["I"] <= int(mask.sum()) + 8, r["I"]
+        d = oracle.sampson_F(r["F"], z["u"])
+        assert ((d <= 16.0) == r["inl"].astype(bool)).mean() > 0.97
+        assert (r["inl"].astype(bool) & mask).sum() >= 0.8 * mask.sum()
+    d = oracle.sampson_F(z["F"], z["u"])
+    assert np.array_equal(d <= 16.0, z["inl"].astype(bool)) and int(z["I"]) == int(z["inl"].sum())
+    # the seeded scene's true F explains its inliers (checks sampson_F's layout convention too)
+    assert np.median(oracle.sampson_F(z["F_true"].ravel(), z["u"])[z["mask"]]) < 1.0
+
+
+def test_degensac_shim_exports_reference_symbols():
+    import mods_light_zmq_b200 as M
+    path = os.path.join(os.path.dirname(M.LIB_PATH), "libmodsgpu_degensac.so")
+    assert os.path.exists(path), "run make"
+    lib = ctypes.CDLL(path)
+    for n in ("exp_ransacHcustom", "exp_ransacFcustom", "modsgpu_ransac_set_seed"):
+        assert hasattr(lib, n), n
+
+
 def test_oracle_matcher_small(oracle):
     rng = np.random.RandomState(0)
     t = rng.randint(0, 256, (70, 128)).astype(np.float32)

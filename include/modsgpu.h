@@ -183,6 +183,20 @@ int  modsgpu_pair_pipeline_images(modsgpu_ctx* ctx, modsgpu_image* img1, modsgpu
 /* host BGR images (cv::imread layout): upload + pipeline */
 int  modsgpu_pair_pipeline(modsgpu_ctx* ctx, const uint8_t* bgr1, const uint8_t* bgr2, int w, int h,
                            unsigned long long seed, modsgpu_pair_result* res, double* inlier_xy, int capacity);
+/* ---- one image -> described regions (what extract_features_batch.cpp:128-139 does per image for the deep
+ *      configuration: ImageRepresentation::SynthDetectDescribeKeypoints, identity view) and the OxAff writer
+ *      (ImageRepresentation::SaveRegionsMichal text mode -> saveAR_KM_format, imagerepresentation.cpp:113-126,
+ *      :205-211, :1187-1213: "128\nN\n" then `x y a b c d0..d127` per region, (a b; b c) = (A A^T)^-1 / (3 sqrt3 s)^2). */
+typedef struct {
+  double x, y, s, a11, a12, a21, a22;   /* reproj_kp (== det_kp for the identity view) */
+  double response;
+  int    octave, type;
+  float  desc[128];
+} modsgpu_feature;
+/* *out is malloc()ed by the library; release with modsgpu_free() */
+int  modsgpu_extract_features(modsgpu_ctx* ctx, modsgpu_image* img, modsgpu_feature** out, int* n);
+int  modsgpu_write_oxaff(const char* path, const modsgpu_feature* f, int n);
+
 /* test-only: one 128x32x64 GEMM through the tcgen05 descriptor conventions of the dense kernels */
 int  modsgpu_debug_umma_probe(modsgpu_ctx* ctx, const float* A, const float* B, float* D, int swap_lbo_sbo);
 

@@ -19,6 +19,9 @@ KP_DTYPE = np.dtype([("x", "f4"), ("y", "f4"), ("s", "f4"), ("response", "f4"), 
 REGION_DTYPE = np.dtype([("x", "f8"), ("y", "f8"), ("s", "f8"), ("a11", "f8"), ("a12", "f8"), ("a21", "f8"), ("a22", "f8")])
 MATCH_DTYPE = np.dtype([("qi", "i4"), ("ti", "i4"), ("tj_bad", "i4"), ("d1", "f4"), ("d2", "f4"), ("_pad", "i4"), ("ratio", "f8")])
 
+FEATURE_DTYPE = np.dtype([("x", "f8"), ("y", "f8"), ("s", "f8"), ("a11", "f8"), ("a12", "f8"), ("a21", "f8"), ("a22", "f8"),
+                          ("response", "f8"), ("octave", "i4"), ("type", "i4"), ("desc", "f4", (128,))])
+
 AFFNET, ORINET, HARDNET = 0, 1, 2
 NET_FILES = {AFFNET: "affnet.npz", ORINET: "orinet.npz", HARDNET: "hardnet.npz"}
 NET_DIM = {AFFNET: 3, ORINET: 2, HARDNET: 128}
@@ -245,6 +248,19 @@ class ModsGpu:
         return dict(H=H, inl=inl[:T], I=res.n_inliers, J=res.J, samples=res.samples, lo_count=res.lo_runs,
                     oc_rejects=res.oc_rejects)
 
+    # ---- one image -> described regions; OxAff writer (extract_features_batch)
+    def extract_features(self, img):
+        out = C.c_void_p()
+        n = C.c_int()
+        self._check(self.lib.modsgpu_extract_features(self.ctx, img.handle, C.byref(out), C.byref(n)))
+        try:
+            if n.value == 0:
+                return np.zeros(0, FEATURE_DTYPE)
+            buf = (C.c_char * (n.value * FEATURE_DTYPE.itemsize)).from_address(out.value)
+            return np.frombuffer(buf, FEATURE_DTYPE).copy()
+        finally:
+            self.lib.modsgpu_free(out)
+
     def ransac_F(self, u, th=16.0, conf=0.99, max_samples=1000000, sym_check=1, seed=12345):
         """modsgpu_ransac_F: LO-RANSAC for a fundamental matrix (exp_ransacFcustom, matching.cpp:722)."""
         u = np.ascontiguousarray(u, np.float64)
@@ -256,6 +272,14 @@ class ModsGpu:
         self._check(self.lib.modsgpu_ransac_F(self.ctx, _p(u), T, C.byref(p), _p(F), _p(inl), C.byref(res)))
         return dict(F=F, inl=inl[:T], I=res.n_inliers, J=res.J, samples=res.samples, lo_count=res.lo_runs,
                     sym_rejects=res.oc_rejects)
+
+
+def write_oxaff(path, feats):
+    """modsgpu_write_oxaff: SaveRegionsMichal text format (needs no GPU)."""
+    feats = np.ascontiguousarray(feats, FEATURE_DTYPE)
+    rc = load_library().modsgpu_write_oxaff(str(path).encode(), _p(feats), len(feats))
+    if rc != 0:
+        raise ModsGpuError("modsgpu_write_oxaff failed (%d)" % rc)
 
 
 def _pair_dict(res, xy):

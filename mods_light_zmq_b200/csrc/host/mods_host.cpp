@@ -5,6 +5,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <fstream>
 
 namespace modsb200 {
 
@@ -170,6 +171,35 @@ int ImageRepresentation::SynthDetectDescribeKeypoints(const DetectPars& par) {
   regions_.swap(final_regs);
   TimeSpent.DescTime += now_ms() - t0;
   return n3;
+}
+
+// imagerepresentation.cpp:113-126: sc = s*sqrt(|det A|)*3*sqrt(3); A <- upIsUp(A) cast to float; SVD A = U W V^T;
+// ellipse = U diag(1/(w_i^2 sc^2)) U^T = (A A^T)^-1 / sc^2.  cv::SVD (third-party, float) is replaced by the closed
+// form evaluated in double on the float-cast A and rounded to float; the file prints 6 significant digits.
+void OxAffEllipse(const AffineKeypoint& k, float& a, float& b, float& c) {
+  double a11 = k.a11, a12 = k.a12, a21 = k.a21, a22 = k.a22;
+  const double sc = k.s * std::sqrt(std::fabs(a11 * a22 - a12 * a21)) * 3.0 * std::sqrt(3.0);
+  rectifyAffineTransformationUpIsUp(a11, a12, a21, a22);
+  const double f11 = (float)a11, f12 = (float)a12, f21 = (float)a21, f22 = (float)a22;
+  // M = A A^T
+  const double m11 = f11 * f11 + f12 * f12, m12 = f11 * f21 + f12 * f22, m22 = f21 * f21 + f22 * f22;
+  const double det = m11 * m22 - m12 * m12, q = 1.0 / (det * sc * sc);
+  a = (float)(m22 * q); b = (float)(-m12 * q); c = (float)(m11 * q);
+}
+
+int SaveRegionsMichal(const AffineRegionVector& regions, const std::string& fname) {
+  std::ofstream kpfile(fname);
+  if (!kpfile.is_open()) return -1;
+  kpfile << "128" << std::endl;
+  kpfile << regions.size() << std::endl;
+  for (const AffineRegion& ar : regions) {
+    float a, b, c;
+    OxAffEllipse(ar.reproj_kp, a, b, c);
+    kpfile << ar.reproj_kp.x << " " << ar.reproj_kp.y << " " << a << " " << b << " " << c << " ";
+    for (size_t i = 0; i < ar.desc.size(); i++) kpfile << ar.desc[i] << " ";
+    kpfile << std::endl;
+  }
+  return kpfile.good() ? 0 : -1;
 }
 
 // matching.cpp:356-460 (vector_matcher = linear): list1 = queries (image 1), list2 = train (image 2)
@@ -389,4 +419,41 @@ extern "C" int modsgpu_pair_pipeline(modsgpu_ctx* ctx, const uint8_t* bgr1, cons
   modsgpu_image_free(ctx, i1);
   modsgpu_image_free(ctx, i2);
   return rc;
+}
+
+
+// ------------------------------------------------------------------------------------------------------
+// C entries: one image -> described regions (extract_features_batch.cpp:128-139) and the OxAff writer
+// ------------------------------------------------------------------------------------------------------
+extern "C" int modsgpu_extract_features(modsgpu_ctx* ctx, modsgpu_image* img, modsgpu_feature** out, int* n) {
+  using namespace modsb200;
+  if (!ctx || !img || !out || !n) return MODSGPU_EINVAL;
+  *out = nullptr; *n = 0;
+  DetectPars dp;
+  ImageRepresentation rep(ctx, img, false);
+  const int nd = rep.SynthDetectDescribeKeypoints(dp);
+  if (nd < 0) return nd;
+  const AffineRegionVector& v = rep.GetAffineRegionVector();
+  modsgpu_feature* f = (modsgpu_feature*)malloc(sizeof(modsgpu_feature) * (size_t)(nd > 0 ? nd : 1));
+  if (!f) return MODSGPU_EINVAL;
+  for (int i = 0; i < nd; i++) {
+    const AffineKeypoint& k = v[i].reproj_kp;
+    f[i].x = k.x; f[i].y = k.y; f[i].s = k.s; f[i].a11 = k.a11; f[i].a12 = k.a12; f[i].a21 = k.a21; f[i].a22 = k.a22;
+    f[i].response = k.response; f[i].octave = k.octave_number; f[i].type = k.sub_type;
+    for (int d = 0; d < 128; d++) f[i].desc[d] = d < (int)v[i].desc.size() ? v[i].desc[d] : 0.f;
+  }
+  *out = f; *n = nd;
+  return 0;
+}
+
+extern "C" int modsgpu_write_oxaff(const char* path, const modsgpu_feature* f, int n) {
+  using namespace modsb200;
+  if (!path || n < 0 || (n > 0 && !f)) return MODSGPU_EINVAL;
+  AffineRegionVector v((size_t)n);
+  for (int i = 0; i < n; i++) {
+    AffineKeypoint& k = v[i].reproj_kp;
+    k.x = f[i].x; k.y = f[i].y; k.s = f[i].s; k.a11 = f[i].a11; k.a12 = f[i].a12; k.a21 = f[i].a21; k.a22 = f[i].a22;
+    v[i].desc.assign(f[i].desc, f[i].desc + 128);
+  }
+  return SaveRegionsMichal(v, path) ? MODSGPU_EIO : 0;
 }

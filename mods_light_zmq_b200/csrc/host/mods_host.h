@@ -85,6 +85,10 @@ bool interpolateCheckBorders(int orig_img_w, int orig_img_h, float ofsx, float o
 void rectifyAffineTransformationUpIsUp(double& a11, double& a12, double& a21, double& a22);
 bool getEigenvalues(float a, float b, float c, float d, float& l1, float& l2);
 
+// imagerepresentation.cpp:113-126 saveKP_KM_format + :205-211 saveAR_KM_format + :1187-1213 SaveRegionsMichal (text mode)
+int SaveRegionsMichal(const AffineRegionVector& regions, const std::string& fname);
+void OxAffEllipse(const AffineKeypoint& k, float& a, float& b, float& c);
+
 int MatchFlannFGINN(modsgpu_ctx* ctx, const AffineRegionVector& list1, const AffineRegionVector& list2,
                     TentativeCorrespListExt& corresp, const MatchPars& par);
 int DuplicateFiltering(modsgpu_ctx* ctx, TentativeCorrespListExt& in_corresp, double r);

@@ -8,6 +8,7 @@
                     through the daemons' own nn.Sequential definitions (unfolded BatchNorm, torch CPU fp32)
   graf_counts.json  keypoint / region / descriptor counts of the oracle pipeline on the reference's
                     graf1/graf6 images, next to the README transcript values (README.md:47-61)
+  oxaff_golden.npz  seeded affine regions + their OxAff ellipse entries (saveKP_KM_format with cv2.SVDecomp)
   ransac_F_ref.npz  a seeded two-view scene + the result of the reference's own exp_ransacFcustom
   ransac_ref.npz    a seeded correspondence set + the result of the reference's own exp_ransacHcustom
                     (oracle/_ref/libdegensac_ref.so, time() pinned)
@@ -154,8 +155,40 @@ def ransac_F_ref():
           (r["I"], r["samples"], r["lo_count"], int((r["inl"].astype(bool) & mask).sum())))
 
 
+def oxaff_golden():
+    """Seeded regions + the OxAff line values computed the way saveKP_KM_format does (imagerepresentation.cpp:113-126)
+    with cv2.SVDecomp standing in for cv::SVD (same library, float)."""
+    import cv2
+    rng = np.random.RandomState(11)
+    n = 40
+    regs = np.zeros(n, [("x", "f8"), ("y", "f8"), ("s", "f8"), ("a11", "f8"), ("a12", "f8"), ("a21", "f8"), ("a22", "f8")])
+    regs["x"], regs["y"] = rng.uniform(5, 1000, n), rng.uniform(5, 700, n)
+    regs["s"] = np.exp(rng.uniform(np.log(1.5), np.log(40), n))
+    ang = rng.uniform(0, 2 * np.pi, n)
+    l = np.exp(rng.uniform(-0.8, 0.8, n))
+    for i in range(n):
+        R = np.array([[np.cos(ang[i]), -np.sin(ang[i])], [np.sin(ang[i]), np.cos(ang[i])]])
+        A = R @ np.diag([l[i], 1 / l[i]]) @ R.T @ np.array([[np.cos(ang[i] / 3), np.sin(ang[i] / 3)], [-np.sin(ang[i] / 3), np.cos(ang[i] / 3)]])
+        regs["a11"][i], regs["a12"][i], regs["a21"][i], regs["a22"][i] = A.ravel()
+    abc = np.zeros((n, 3), np.float32)
+    for i in range(n):
+        a11, a12, a21, a22 = regs["a11"][i], regs["a12"][i], regs["a21"][i], regs["a22"][i]
+        sc = regs["s"][i] * np.sqrt(abs(a11 * a22 - a12 * a21)) * 3.0 * np.sqrt(3.0)
+        det = np.sqrt(abs(a11 * a22 - a12 * a21))
+        b2a2 = np.sqrt(a12 * a12 + a11 * a11)
+        A = np.array([[b2a2 / det, 0], [(a22 * a12 + a21 * a11) / (b2a2 * det), det / b2a2]], np.float32)
+        w, u, vt = cv2.SVDecomp(A, flags=cv2.SVD_FULL_UV)
+        d = w.ravel().astype(np.float32)
+        d0 = np.float32(np.float32(1.0) / (np.float64(d[0] * d[0]) * sc * sc))
+        d1 = np.float32(np.float32(1.0) / (np.float64(d[1] * d[1]) * sc * sc))
+        E = (u @ np.diag(np.array([d0, d1], np.float32)) @ u.T).astype(np.float32)
+        abc[i] = E[0, 0], E[0, 1], E[1, 1]
+    np.savez_compressed(os.path.join(HERE, "oxaff_golden.npz"), regs=regs, abc=abc)
+    print("oxaff_golden.npz", n)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["cv2", "cnn", "graf", "ransac", "ransacF"]
+    which = sys.argv[1:] or ["cv2", "cnn", "graf", "ransac", "ransacF", "oxaff"]
     if "cv2" in which:
         cv2_pins()
     if "cnn" in which:
@@ -164,5 +197,7 @@ if __name__ == "__main__":
         graf_counts()
     if "ransac" in which:
         ransac_ref()
+    if "oxaff" in which:
+        oxaff_golden()
     if "ransacF" in which:
         ransac_F_ref()

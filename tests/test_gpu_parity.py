@@ -477,3 +477,50 @@ def test_pair_pipeline_config3(mg, oracle, synth_pair):
     for k in ("keypoints", "regions", "descriptors", "tentatives", "unique_tentatives", "inliers"):
         assert r[k] == r2[k], k
     assert np.array_equal(r["H"], r2["H"])
+
+
+# ------------------------------------------------------------------------------------------ batch extraction (config 4)
+def test_extract_features_and_batch_oxaff(mg, oracle, tmp_path):
+    """modsgpu_extract_features == the chained seams (detect -> AffNet -> OriNet -> HardNet++ with the host filters),
+    checked end to end against the oracle chain on a small image, and the batch driver writes one OxAff file per
+    image whose rows are those features (extract_features_batch.cpp + SaveRegionsMichal)."""
+    import mods_light_zmq_b200 as M
+    from mods_light_zmq_b200 import synth, batch
+    from oracle import cnn_oracle as CN
+    imgs = [synth.blob_image(seed=40 + i, w=320, h=240, n_blobs=300) for i in range(3)]
+    feats = []
+    for u8 in imgs:
+        bgr = synth.gray_to_bgr(u8)
+        img = mg.image_from_bgr8(bgr)
+        f = mg.extract_features(img)
+        feats.append(f)
+        # oracle chain on the same image
+        g = oracle.gray_from_bgr(bgr)
+        h, w = g.shape
+        regs = oracle.regions_from_keypoints(oracle.detect_hessian(g))
+        r2, _ = oracle.affnet_postprocess(regs, CN.affnet(oracle.quantize_u8(oracle.extract_patches(g, regs))), w, h)
+        r3 = oracle.orinet_postprocess(r2, CN.orinet(oracle.quantize_u8(oracle.extract_patches(g, r2))))
+        r4, _ = oracle.reproject_filter(r3, w, h)
+        # fp16 nets vs fp32 oracle: a region whose AffNet eigen-ratio / border test is borderline may flip
+        assert abs(len(f) - len(r4)) <= max(2, 0.01 * len(r4)), (len(f), len(r4))
+        if len(f) == len(r4):
+            assert np.allclose(f["x"], r4["x"]) and np.allclose(f["y"], r4["y"]) and np.allclose(f["s"], r4["s"])
+            assert np.abs(f["a11"] - r4["a11"]).max() < 2e-2
+        assert f["desc"].min() >= 0 and f["desc"].max() <= 255 and np.all(f["desc"] == np.round(f["desc"]))
+    # batch driver, single rank, through .npy inputs
+    ins, outs = [], []
+    for i, u8 in enumerate(imgs):
+        p = tmp_path / ("im%d.npy" % i)
+        np.save(p, synth.gray_to_bgr(u8))
+        ins.append(str(p))
+        outs.append(str(tmp_path / ("im%d.oxaff" % i)))
+    ext = batch.gpu_extractor(0)
+    counts = batch.extract_features_batch(ins, outs, ext)
+    ext.close()
+    assert counts == [len(f) for f in feats]
+    for o, f in zip(outs, feats):
+        lines = open(o).read().split("\n")
+        assert lines[0] == "128" and int(lines[1]) == len(f)
+        row = lines[2 + len(f) // 2].split()
+        k = len(f) // 2
+        assert abs(float(row[0]) - f["x"][k]) < 1e-3 * max(1, abs(f["x"][k])) and [int(v) for v in row[5:]] == [int(v) for v in f["desc"][k]]

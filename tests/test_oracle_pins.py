@@ -99,13 +99,14 @@ def test_reference_degensac_F_fixture(oracle):
     mask = z["mask"]
     # NB the reference reads uninitialised heap in exp_ransacFcustom (errs[4] = errs[3] before any write,
     # exp_ranF.c:870-872; data_out histogram :1029): with time() pinned its result still differs between the
-    # first and later calls of one process (I = 144..172 on this fixture).  So the fixture pins a band.
+    # first and later calls of one process and between processes (I = 116..172 observed on this fixture, 170 true
+    # inliers).  So the fixture pins a band, not a value.
     for _ in range(2):
         r = oracle.ref_ransac_F(z["u"], th=16.0, seed_time=12345)
-        assert int(z["I"]) - 5 <= r["I"] <= int(mask.sum()) + 8, r["I"]
+        assert 0.6 * mask.sum() <= r["I"] <= int(mask.sum()) + 8, r["I"]
         d = oracle.sampson_F(r["F"], z["u"])
         assert ((d <= 16.0) == r["inl"].astype(bool)).mean() > 0.97
-        assert (r["inl"].astype(bool) & mask).sum() >= 0.8 * mask.sum()
+        assert (r["inl"].astype(bool) & mask).sum() >= 0.6 * mask.sum()
     d = oracle.sampson_F(z["F"], z["u"])
     assert np.array_equal(d <= 16.0, z["inl"].astype(bool)) and int(z["I"]) == int(z["inl"].sum())
     # the seeded scene's true F explains its inliers (checks sampson_F's layout convention too)
@@ -119,6 +120,31 @@ def test_degensac_shim_exports_reference_symbols():
     lib = ctypes.CDLL(path)
     for n in ("exp_ransacHcustom", "exp_ransacFcustom", "modsgpu_ransac_set_seed"):
         assert hasattr(lib, n), n
+
+
+def test_oxaff_writer_matches_cv2_golden(tmp_path):
+    """modsgpu_write_oxaff (SaveRegionsMichal text mode) against ellipse entries computed with cv2.SVDecomp the way
+    saveKP_KM_format does (imagerepresentation.cpp:113-126); the file prints 6 significant digits."""
+    import mods_light_zmq_b200 as M
+    z = np.load(os.path.join(GOLD, "oxaff_golden.npz"))
+    regs, abc = z["regs"], z["abc"]
+    f = np.zeros(len(regs), M.FEATURE_DTYPE)
+    for k in ("x", "y", "s", "a11", "a12", "a21", "a22"):
+        f[k] = regs[k]
+    rng = np.random.RandomState(0)
+    f["desc"] = rng.randint(0, 256, (len(regs), 128))
+    path = str(tmp_path / "img.oxaff")
+    M.write_oxaff(path, f)
+    lines = open(path).read().split("\n")
+    assert lines[0] == "128" and int(lines[1]) == len(regs)
+    rows = [l.split() for l in lines[2:] if l.strip()]
+    assert len(rows) == len(regs) and all(len(r) == 5 + 128 for r in rows)
+    got = np.array([[float(v) for v in r[:5]] for r in rows])
+    assert np.allclose(got[:, 0], regs["x"], rtol=1e-5) and np.allclose(got[:, 1], regs["y"], rtol=1e-5)
+    assert np.allclose(got[:, 2:], abc, rtol=3e-5, atol=1e-12), np.abs(got[:, 2:] / abc - 1).max()
+    assert [int(v) for v in rows[3][5:]] == [int(v) for v in f["desc"][3]]
+    M.write_oxaff(path, f[:0])
+    assert open(path).read().split() == ["128", "0"]
 
 
 def test_oracle_matcher_small(oracle):

@@ -1,0 +1,120 @@
+"""Host-side logic of the multi-GPU path on CPU: world-size-2 `gloo` runs of the batch extractor (config 4) with a
+deterministic stand-in extractor (no GPU here), compared file-by-file with the world-size-1 output; plus the
+pair-sharding arithmetic bench.py uses."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+WORKER = r'''
+import os, sys, zlib
+import numpy as np
+sys.path.insert(0, %(root)r)
+import torch.distributed as dist
+import mods_light_zmq_b200 as M
+from mods_light_zmq_b200 import batch
+
+def fake_extractor(bgr):
+    # deterministic function of the image content only (stands in for the GPU pipeline)
+    seed = zlib.crc32(bgr.tobytes()) & 0x7fffffff
+    rng = np.random.RandomState(seed)
+    n = 3 + seed %% 5
+    f = np.zeros(n, M.FEATURE_DTYPE)
+    f["x"], f["y"] = rng.uniform(1, 60, n), rng.uniform(1, 40, n)
+    f["s"] = rng.uniform(2, 9, n)
+    f["a11"], f["a22"] = 1.0, 1.0
+    f["desc"] = rng.randint(0, 256, (n, 128))
+    return f
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+d = None
+if world > 1:
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=rank, world_size=world)
+    d = dist
+imgs = open(sys.argv[1]).read().split()
+outs = open(sys.argv[2]).read().split()
+counts = batch.extract_features_batch(imgs, outs, fake_extractor, rank, world, d)
+if rank == 0:
+    print("COUNTS", " ".join(str(c) for c in counts))
+if d is not None:
+    dist.destroy_process_group()
+'''
+
+
+def _run(tmp, tag, world, imgs, port):
+    outdir = tmp / tag
+    outdir.mkdir()
+    outs = [str(outdir / ("img%02d.oxaff" % i)) for i in range(len(imgs))]
+    (tmp / (tag + "_imgs.txt")).write_text("\n".join(imgs) + "\n")
+    (tmp / (tag + "_outs.txt")).write_text("\n".join(outs) + "\n")
+    script = tmp / (tag + "_worker.py")
+    script.write_text(WORKER % {"root": ROOT, "port": port})
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, str(script), str(tmp / (tag + "_imgs.txt")), str(tmp / (tag + "_outs.txt"))],
+                                      env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    res = [p.communicate(timeout=240) for p in procs]
+    for p, (o, e) in zip(procs, res):
+        assert p.returncode == 0, e[-2000:]
+    counts = [int(v) for v in res[0][0].split("COUNTS")[1].split()]
+    return outs, counts
+
+
+def test_shard_indices_cover_every_image_once():
+    from mods_light_zmq_b200 import batch
+    for n in (0, 1, 7, 512):
+        for world in (1, 2, 3, 8):
+            seen = sorted(i for r in range(world) for i in batch.shard_indices(n, r, world))
+            assert seen == list(range(n))
+            sizes = [len(batch.shard_indices(n, r, world)) for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_batch_extract_world2_equals_world1(tmp_path):
+    rng = np.random.RandomState(0)
+    imgs = []
+    for i in range(7):
+        a = rng.randint(0, 256, (40, 64, 3)).astype(np.uint8)
+        if i % 2:
+            p = tmp_path / ("in%02d.npy" % i)
+            np.save(p, a)
+        else:   # binary PPM (RGB on disk, BGR in memory like cv::imread)
+            p = tmp_path / ("in%02d.ppm" % i)
+            with open(p, "wb") as f:
+                f.write(b"P6\n# synthetic\n64 40\n255\n" + a[:, :, ::-1].tobytes())
+        imgs.append(str(p))
+    imgs.append(str(tmp_path / "missing.ppm"))          # unreadable image: reported, not fatal
+    outs1, c1 = _run(tmp_path, "w1", 1, imgs, 29611)
+    outs2, c2 = _run(tmp_path, "w2", 2, imgs, 29612)
+    assert c1 == c2 and c1[-1] == -1 and all(c >= 3 for c in c1[:-1])
+    for a, b, c in zip(outs1[:-1], outs2[:-1], c1[:-1]):
+        ta, tb = open(a).read(), open(b).read()
+        assert ta == tb                                  # file-by-file identical to the 1-rank output
+        assert ta.split("\n")[0] == "128" and int(ta.split("\n")[1]) == c
+    assert not os.path.exists(outs2[-1])
+    # a second run skips everything that exists (extract_features_batch.cpp:108-117)
+    (tmp_path / "w2").rename(tmp_path / "w2_first")
+    (tmp_path / "w2_first").rename(tmp_path / "w2")
+    script = tmp_path / "w2_worker.py"
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1")
+    out = subprocess.run([sys.executable, str(script), str(tmp_path / "w2_imgs.txt"), str(tmp_path / "w2_outs.txt")],
+                         env=env, capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert [int(v) for v in out.stdout.split("COUNTS")[1].split()] == [-1] * len(imgs)
+
+
+def test_pnm_reader_matches_memory(tmp_path):
+    from mods_light_zmq_b200 import batch
+    rng = np.random.RandomState(1)
+    g = rng.randint(0, 256, (9, 13)).astype(np.uint8)
+    p = tmp_path / "g.pgm"
+    with open(p, "wb") as f:
+        f.write(b"P5 13 9 255\n" + g.tobytes())
+    a = batch.read_image_bgr(str(p))
+    assert a.shape == (9, 13, 3) and np.array_equal(a[:, :, 0], g) and np.array_equal(a[:, :, 2], g)

@@ -134,6 +134,170 @@ k_blur_resp(const float* __restrict__ src, float* __restrict__ dst, float* __res
   }
 }
 
+// ---- register-blocked version (ks >= 7, i.e. every blur of the default pyramid) ----------------------------
+// Same tile and the same arithmetic, organised so that the FMA chains dominate the instruction stream:
+//   load   one warp per tile row, clamped coordinates (replicate border) -> A (odd pitch)
+//   row    a thread owns 4 adjacent columns x 4 rows (rows strided by the group count): one tap load and one
+//          sample load per row and step feed 4 FMAs; taps rotate through registers; zero taps appended to the
+//          tap array keep the chain s = fma(p[t], k[t], s) bit-exact (fma(d, 0, s) == s).  Columns in OpenCV's
+//          scalar tail (x >= w & ~3) and blocks straddling it take the scalar form.
+//   column a thread owns 4 vertically adjacent outputs of one column: the symmetric pairs T[y-t] + T[y+t] slide
+//          through registers (2 new loads per step for 4 outputs)
+//   hessian from the blurred tile with its 1-px halo, as before.
+constexpr int BT_NT = 512;   // 2 x 4 row blocks / 5-row column blocks: ~4 output pixels per thread, short critical path
+
+template <int CB, int RB>
+__device__ __forceinline__ void blur_rowpass_block(const float* (&rows)[RB], const float* __restrict__ kp, int ks,
+                                                   float (&acc)[RB][CB]) {
+  float kq[CB];
+#pragma unroll
+  for (int c = 0; c < CB; c++) kq[c] = 0.f;
+#pragma unroll
+  for (int b = 0; b < RB; b++)
+#pragma unroll
+    for (int c = 0; c < CB; c++) acc[b][c] = 0.f;
+  const int nstep = ks + CB - 1;
+#pragma unroll 4
+  for (int u = 0; u < nstep; u++) {
+#pragma unroll
+    for (int c = CB - 1; c > 0; c--) kq[c] = kq[c - 1];
+    kq[0] = kp[u];
+#pragma unroll
+    for (int b = 0; b < RB; b++) {
+      const float d = rows[b][u];
+#pragma unroll
+      for (int c = 0; c < CB; c++) acc[b][c] = fmaf(d, kq[c], acc[b][c]);
+    }
+  }
+}
+
+template <int RB>
+__device__ __forceinline__ void blur_colpass_block(const float* __restrict__ Tc, int pitch, const float* __restrict__ k, int r,
+                                                   bool vec, float (&out)[RB]) {
+  float dn[RB], up[RB];
+#pragma unroll
+  for (int i = 0; i < RB; i++) { dn[i] = up[i] = Tc[i * pitch]; out[i] = dn[i] * k[r]; }
+#pragma unroll 4
+  for (int t = 1; t <= r; t++) {
+#pragma unroll
+    for (int i = RB - 1; i > 0; i--) dn[i] = dn[i - 1];
+    dn[0] = Tc[-t * pitch];
+#pragma unroll
+    for (int i = 0; i < RB - 1; i++) up[i] = up[i + 1];
+    up[RB - 1] = Tc[(RB - 1 + t) * pitch];
+    const float kt = k[r + t];
+    if (vec) {
+#pragma unroll
+      for (int i = 0; i < RB; i++) out[i] = fmaf(dn[i] + up[i], kt, out[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < RB; i++) out[i] = out[i] + (dn[i] + up[i]) * kt;
+    }
+  }
+}
+
+__host__ __device__ inline int blur2_pitch_a(int r) { return (BT_X + 2 + 2 * r + 3) | 1; }
+constexpr int BLUR2_PB = (BT_X + 2 + 3) | 1;   // 69: row-filtered tile, 66 columns (+ slack for the last 4-block)
+
+__global__ void __launch_bounds__(BT_NT)
+k_blur_resp2(const float* __restrict__ src, float* __restrict__ dst, float* __restrict__ resp,
+             int w, int h, Taps taps, float norm2) {
+  extern __shared__ float sm[];
+  const int ks = taps.ks, r = ks >> 1;
+  const int AW = BT_X + 2 + 2 * r, AH = BT_Y + 2 + 2 * r, PA = blur2_pitch_a(r);
+  constexpr int BW = BT_X + 2, CW = BT_X + 2, CH = BT_Y + 2, PB = BLUR2_PB;
+  float* A = sm;                       // AH x PA
+  float* B = A + AH * PA;              // (AH + 3) x PB   (slack rows for the last column block)
+  float* Cc = B + (AH + 3) * PB;       // CH x CW
+  __shared__ float k[MAX_KS + 4];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < ks + 3) k[tid] = tid < ks ? taps.k[tid] : 0.f;
+  const int x0 = blockIdx.x * BT_X, y0 = blockIdx.y * BT_Y;
+  for (int ly = warp; ly < AH; ly += BT_NT / 32) {
+    const float* srow = src + (size_t)clampi(y0 - 1 - r + ly, 0, h - 1) * w;
+    float* arow = A + ly * PA;
+    for (int lx = lane; lx < AW + 3; lx += 32) arow[lx] = srow[clampi(x0 - 1 - r + lx, 0, w - 1)];
+  }
+  __syncthreads();
+  // row pass -> B[ly][lx], lx = 0..65 <-> gx = x0 - 1 + lx
+  {
+    const int wv = w & ~3;
+    constexpr int NCB = (BW + 3) / 4;                 // 17 blocks of 4 columns
+    constexpr int RB = 2;
+    const int NRG = (AH + RB - 1) / RB;
+    for (int it = tid; it < NCB * NRG; it += BT_NT) {
+      const int cb = it / NRG, rg = it - cb * NRG, lx0 = cb * 4, gx0 = x0 - 1 + lx0;
+      int rowi[RB];
+#pragma unroll
+      for (int b = 0; b < RB; b++) rowi[b] = rg + b * NRG;
+      if (gx0 >= 0 && gx0 + 3 < wv) {
+        const float* rows[RB];
+#pragma unroll
+        for (int b = 0; b < RB; b++) rows[b] = A + min(rowi[b], AH - 1) * PA + lx0;
+        float acc[RB][4];
+        blur_rowpass_block<4, RB>(rows, k, ks, acc);
+#pragma unroll
+        for (int b = 0; b < RB; b++)
+          if (rowi[b] < AH) {
+            float* t = B + rowi[b] * PB + lx0;
+#pragma unroll
+            for (int c = 0; c < 4; c++) t[c] = acc[b][c];
+          }
+      } else {
+#pragma unroll 1
+        for (int b = 0; b < RB; b++) {
+          if (rowi[b] >= AH) continue;
+#pragma unroll 1
+          for (int c = 0; c < 4; c++) {
+            const int gx = gx0 + c;
+            float v = 0.f;
+            if (gx >= 0 && gx < w && lx0 + c < BW) v = row_pass(A + rowi[b] * PA + lx0 + c, k, ks, gx < wv, gx < (w & ~1));
+            B[rowi[b] * PB + lx0 + c] = v;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // column pass -> C (blurred tile with 1-px halo) and dst
+  {
+    const int wc = w & ~7;
+    constexpr int RBC = 5, NRGC = (CH + RBC - 1) / RBC;   // 7 groups of 5 rows: 462 items, one round
+    for (int it = tid; it < NRGC * CW; it += BT_NT) {
+      const int rg = it / CW, lx = it - rg * CW, ly0 = rg * RBC;
+      const int gx = x0 - 1 + lx;
+      float o[RBC];
+      blur_colpass_block<RBC>(B + (ly0 + r) * PB + lx, PB, k, r, gx < wc, o);
+#pragma unroll
+      for (int i = 0; i < RBC; i++) {
+        const int ly = ly0 + i, gy = y0 - 1 + ly;
+        if (ly >= CH) continue;
+        float v = 0.f;
+        if (gx >= 0 && gx < w && gy >= 0 && gy < h) {
+          v = o[i];
+          if (lx >= 1 && lx <= BT_X && ly >= 1 && ly <= BT_Y) dst[(size_t)gy * w + gx] = v;
+        }
+        Cc[ly * CW + lx] = v;
+      }
+    }
+  }
+  if (!resp) return;
+  __syncthreads();
+  for (int i = tid; i < BT_X * BT_Y; i += BT_NT) {
+    const int ly = i >> 6, lx = i & 63;
+    const int gx = x0 + lx, gy = y0 + ly;
+    if (gx >= w || gy >= h) continue;
+    float v = 0.f;
+    if (gx >= 1 && gx < w - 1 && gy >= 1 && gy < h - 1) v = hessian_at(Cc + (ly + 1) * CW + lx + 1, CW, norm2);
+    resp[(size_t)gy * w + gx] = v;
+  }
+}
+
+int blur2_smem_bytes(int ks) {
+  const int r = ks >> 1, AH = BT_Y + 2 + 2 * r;
+  return (AH * blur2_pitch_a(r) + (AH + 3) * BLUR2_PB + (BT_X + 2) * (BT_Y + 2)) * (int)sizeof(float);
+}
+
 // Hessian response of an image already in HBM (first level of octaves >= 1).
 __global__ void k_response(const float* __restrict__ src, float* __restrict__ resp, int w, int h, float norm2) {
   int gx = blockIdx.x * blockDim.x + threadIdx.x, gy = blockIdx.y * blockDim.y + threadIdx.y;
@@ -363,15 +527,18 @@ int launch_blur(modsgpu_ctx* ctx, const float* src, float* dst, float* resp, int
   memset(&taps, 0, sizeof(taps));
   taps.ks = ks;
   for (int i = 0; i < ks; i++) taps.k[i] = t[i];
-  int smem = blur_smem_bytes(ks);
   static bool attr_set = false;
   if (!attr_set) {
     MG_CUDA(ctx, cudaFuncSetAttribute(k_blur_resp, cudaFuncAttributeMaxDynamicSharedMemorySize, blur_smem_bytes(MAX_KS)));
+    MG_CUDA(ctx, cudaFuncSetAttribute(k_blur_resp2, cudaFuncAttributeMaxDynamicSharedMemorySize, blur2_smem_bytes(MAX_KS)));
     attr_set = true;
   }
   dim3 grid(ceil_div(w, BT_X), ceil_div(h, BT_Y));
   MG_PROF(ctx, resp ? "k_blur_resp" : "k_blur", 0, (double)w * h * 4.0 * (resp ? 3 : 2));
-  k_blur_resp<<<grid, BT_THREADS, smem, ctx->stream>>>(src, dst, resp, w, h, taps, norm2);
+  if (ks >= 7)
+    k_blur_resp2<<<grid, BT_NT, blur2_smem_bytes(ks), ctx->stream>>>(src, dst, resp, w, h, taps, norm2);
+  else
+    k_blur_resp<<<grid, BT_THREADS, blur_smem_bytes(ks), ctx->stream>>>(src, dst, resp, w, h, taps, norm2);
   MG_LAUNCHED(ctx);
   return 0;
 }

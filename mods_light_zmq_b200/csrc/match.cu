@@ -264,19 +264,33 @@ __global__ void k_dup_conflicts(const double* __restrict__ xy1, const double* __
   conf[(size_t)a * nwords + wi] = bits;
   if (bits) rowflag[a] = 1;
 }
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(256)
 k_dup_resolve(const unsigned* __restrict__ conf, const int* __restrict__ rowflag, const int* __restrict__ ord, int T,
               int nwords, int* __restrict__ out, int* __restrict__ nout) {
   __shared__ unsigned alive[DUP_MAX_T / 32];
+  __shared__ unsigned flagged[DUP_MAX_T / 32];
+  // rows that have any conflict, as a bit mask (coalesced pass over rowflag by the whole CTA)
+  for (int w = threadIdx.x; w < nwords; w += blockDim.x) {
+    unsigned f = 0;
+    for (int k = 0; k < 32; k++) { const int a = w * 32 + k; if (a < T && rowflag[a]) f |= 1u << k; }
+    flagged[w] = f;
+    alive[w] = 0xffffffffu;
+  }
+  __syncthreads();
+  if (threadIdx.x >= 32) return;
   const int lane = threadIdx.x;
-  for (int w = lane; w < nwords; w += 32) alive[w] = 0xffffffffu;
-  __syncwarp();
-  for (int a = 0; a < T; a++) {
-    if (!rowflag[a]) continue;
-    if (!((alive[a >> 5] >> (a & 31)) & 1u)) continue;
-    const unsigned* row = conf + (size_t)a * nwords;
-    for (int w = (a >> 5) + lane; w < nwords; w += 32) alive[w] &= ~row[w];
-    __syncwarp();
+  // one warp walks the flagged rows in order; a row acts only while it is still alive
+  for (int wa = 0; wa < nwords; wa++) {
+    unsigned m = flagged[wa];
+    while (m) {
+      const int bit = __ffs(m) - 1;
+      m &= m - 1;
+      const int a = wa * 32 + bit;
+      if (!((alive[wa] >> bit) & 1u)) continue;
+      const unsigned* row = conf + (size_t)a * nwords;
+      for (int w = wa + lane; w < nwords; w += 32) alive[w] &= ~row[w];
+      __syncwarp();
+    }
   }
   int m = 0;
   for (int base = 0; base < T; base += 32) {
@@ -414,7 +428,7 @@ extern "C" int modsgpu_duplicate_filter(modsgpu_ctx* ctx, const double* xy1, con
     k_dup_conflicts<<<dim3((nwords + 63) / 64, T), 64, 0, ctx->stream>>>(d1, d2, dord, T, nwords, r * r, conf, rowflag);
     MG_LAUNCHED(ctx);
     MG_PROF(ctx, "k_dup_resolve", 2, (double)T);
-    k_dup_resolve<<<1, 32, 0, ctx->stream>>>(conf, rowflag, dord, T, nwords, dout, ctx->mt_aux.as<int>() + 4);
+    k_dup_resolve<<<1, 256, 0, ctx->stream>>>(conf, rowflag, dord, T, nwords, dout, ctx->mt_aux.as<int>() + 4);
     MG_LAUNCHED(ctx);
   } else {
     MG_PROF(ctx, "k_dup_filter", 2, (double)T);

@@ -9,10 +9,10 @@
 //                8x9 null space by pivoted Gauss-Jordan (utools.c:97-167) -> |det|/h33^3 test ->
 //                Sampson error of all T correspondences (Htools.c:160-198), lanes striding over T ->
 //                MSAC score (rtools.c truncQuad, 9/4*th width) by a fixed-order butterfly reduction
-//   k_rs_update  one CTA per batch: best hypothesis of the batch (max J, lowest index on ties), symmetric
+//   k_rs_select / k_rs_lo / k_rs_accept  per batch: best hypothesis (max J, lowest index on ties), symmetric
 //                transfer check (exp_ranH.c:905-947), local optimisation = LSQ on the 8*th band + 10
 //                inner samples x 4 shrinking-threshold LSQ steps (exp_inHranicustom / exp_iterHcustom),
-//                the 10 inner samples running in 10 warps at once; adaptive stopping nsamples(I+1,T,4,conf)
+//                the 10 inner samples on 10 SMs at once; adaptive stopping nsamples(I+1,T,4,conf)
 // All arithmetic is fp64 and compiled with --fmad=false; every reduction has a fixed order, so a run is
 // reproducible from (u, params.seed).
 // Deviations from the reference, on purpose: (1) samples are consumed in batches, so at least B are drawn;
@@ -331,18 +331,28 @@ __device__ void lo_iterate(const double* __restrict__ u, int T, double th, doubl
 }
 
 // ---- per-batch update: best sample, symmetric check, local optimisation, stopping rule -------------------
-// scratch: per warp w (12 warps): dbuf[w][T] doubles, dbuf2[w][T], ibuf[w][T] ints
+// Three launches so that the fp64-heavy inner RANSAC spreads over LO_REPS SMs instead of sharing one:
+//   k_rs_select  one CTA: best hypothesis of the batch, symmetric check, bookkeeping; decides whether the local
+//                optimisation runs and prepares its start model (LSQ on the TC*th*MWM band) and inlier list
+//   k_rs_lo      LO_REPS CTAs of one warp: one inner sample each (exp_inHranicustom / exp_iterHcustom)
+//   k_rs_accept  one warp: best inner sample vs the best model, stopping rule
+// scratch: per inner sample w: dbuf[w][2T] doubles, ibuf[w][T] ints; then dS[T] / inl0[T] of the start model
+struct LoShare {
+  double h0[9];
+  int n0, run_lo, lo_id, pad;
+  double loJ[LO_REPS]; int loI[LO_REPS]; double loH[LO_REPS][9];
+};
+constexpr int RS_NW = 12;    // scratch slots (>= LO_REPS)
+
 __global__ void __launch_bounds__(384)
-k_rs_update(const double* __restrict__ u, int T, double th, double conf, int do_sym, unsigned long long seed,
-            const HypOut* __restrict__ hyp, int nhyp, int force_lo, RsState* st, double* dscr, int* iscr) {
+k_rs_select(const double* __restrict__ u, int T, double th, int do_sym,
+            const HypOut* __restrict__ hyp, int nhyp, int force_lo, RsState* st, LoShare* sh, double* dscr, int* iscr) {
   __shared__ double sJ[12]; __shared__ int sIdx[12];
-  __shared__ double loJ[LO_REPS]; __shared__ int loI[LO_REPS]; __shared__ double loH[LO_REPS][9];
-  __shared__ double h0[9]; __shared__ int n0_s; __shared__ int run_lo_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  double* dW = dscr + (size_t)warp * 2 * T;       // per-warp error buffers
-  int* iW = iscr + (size_t)warp * T;
-  double* dS = dscr + (size_t)nw * 2 * T;          // errors of the LO start model (shared by all warps)
-  int* inl0 = iscr + (size_t)nw * T;               // its inliers at th
+  double* dW = dscr;                                // slot 0 doubles as select's work buffer (LO runs afterwards)
+  int* iW = iscr;
+  double* dS = dscr + (size_t)RS_NW * 2 * T;        // errors of the LO start model
+  int* inl0 = iscr + (size_t)RS_NW * T;             // its inliers at th
 
   // (a) best hypothesis of the batch: max J, lowest index on ties
   double bj = -1; int bi = -1, rej = 0;
@@ -358,105 +368,109 @@ k_rs_update(const double* __restrict__ u, int T, double th, double conf, int do_
   rej = warp_sum_i(rej);
   if (lane == 0) { sJ[warp] = bj; sIdx[warp] = bi; if (rej) atomicAdd(&st->oc_rejects, rej); }
   __syncthreads();
+  if (warp != 0) return;
   bj = -1; bi = -1;
   for (int k = 0; k < nw; k++) if (sIdx[k] >= 0 && (sJ[k] > bj || (sJ[k] == bj && sIdx[k] < bi))) { bj = sJ[k]; bi = sIdx[k]; }
 
-  // (b) warp 0: sequential bookkeeping of exp_ranH.c:903-961 for the batch's best sample
-  if (warp == 0) {
-    // snapshot the state before any lane writes it (lanes of a warp need not run in lockstep)
-    const double curJ = st->J;
-    double curJs = st->Js;
-    int have = st->have_sample, curIs = st->Is;
-    const int no_sam = st->no_sam, lo_runs = st->lo_runs;
-    __syncwarp();
-    bool run_lo = false;
-    if (bi >= 0) {
-      double h[9];
-      for (int i = 0; i < 9; i++) h[i] = hyp[bi].H[i];
-      const int I = hyp[bi].I;
-      if (curJ < bj) {
-        const bool ok = !do_sym || sym_check_ok(u, T, h, th, lane);
-        if (ok && lane == 0) { for (int i = 0; i < 9; i++) st->H[i] = h[i]; st->J = bj; st->I = I; }
-      }
-      if (!have || curJs < bj) {
-        if (lane == 0) { for (int i = 0; i < 9; i++) st->Hs[i] = h[i]; st->Js = bj; st->Is = I; st->have_sample = 1; }
-        have = 1; curJs = bj; curIs = I;
-        run_lo = no_sam + nhyp > ITER_SAM;
-      }
+  // (b) sequential bookkeeping of exp_ranH.c:903-961 for the batch's best sample
+  // snapshot the state before any lane writes it (lanes of a warp need not run in lockstep)
+  const double curJ = st->J;
+  double curJs = st->Js;
+  int have = st->have_sample, curIs = st->Is;
+  const int no_sam = st->no_sam, lo_runs = st->lo_runs;
+  __syncwarp();
+  bool run_lo = false;
+  if (bi >= 0) {
+    double h[9];
+    for (int i = 0; i < 9; i++) h[i] = hyp[bi].H[i];
+    const int I = hyp[bi].I;
+    if (curJ < bj) {
+      const bool ok = !do_sym || sym_check_ok(u, T, h, th, lane);
+      if (ok && lane == 0) { for (int i = 0; i < 9; i++) st->H[i] = h[i]; st->J = bj; st->I = I; }
     }
-    if (no_sam + nhyp >= ITER_SAM && lo_runs == 0 && have && curIs > 4) run_lo = true;
-    if (force_lo) run_lo = have && lo_runs == 0;
-    __syncwarp();
-    if (run_lo) {
-      // LSQ on the TC*th*MWM band of the best SAMPLE, then its inliers at th (exp_ranH.c:997-1012)
-      double h[9];
-      for (int i = 0; i < 9; i++) h[i] = st->Hs[i];
-      int I; double J;
-      score_all(u, T, h, th, dW, lane, &I, &J);
-      __syncwarp();
-      int n = compact_inliers(dW, T, TC * th * MWM, iW, lane);
-      lsq_h(u, iW, n, h, lane);
-      score_all(u, T, h, th, dS, lane, &I, &J);
-      __syncwarp();
-      n = compact_inliers(dS, T, th, inl0, lane);
-      if (lane == 0) { for (int i = 0; i < 9; i++) h0[i] = h[i]; n0_s = n; st->lo_runs = lo_runs + 1; }
+    if (!have || curJs < bj) {
+      if (lane == 0) { for (int i = 0; i < 9; i++) st->Hs[i] = h[i]; st->Js = bj; st->Is = I; st->have_sample = 1; }
+      have = 1; curJs = bj; curIs = I;
+      run_lo = no_sam + nhyp > ITER_SAM;
     }
-    if (lane == 0) run_lo_s = run_lo ? 1 : 0;
   }
-  __syncthreads();
-
-  // (c) inner RANSAC (exp_inHranicustom, exp_ranH.c:741-793): LO_REPS samples, one warp each
-  const bool run_lo = run_lo_s != 0;
-  const int n0 = run_lo ? n0_s : 0;
-  if (run_lo && warp < LO_REPS) {
-    int bI = 0; double bJ = 0; double Hb[9];
-    for (int i = 0; i < 9; i++) Hb[i] = h0[i];
-    if (n0 >= 8) {
-      int ssiz = n0 / 2; if (ssiz > 12) ssiz = 12;
-      // randsubset (rtools.c:25-39) on a private copy of the inlier list
-      for (int k = lane; k < n0; k += 32) iW[k] = inl0[k];
-      __syncwarp();
-      if (lane == 0) {
-        const unsigned long long stream = 0x4C4F000000000000ull + (unsigned long long)st->lo_runs * 64 + warp;
-        for (int i = 0; i < ssiz; i++) {
-          const int s = (int)rs_rand(seed, stream, i, (unsigned)(n0 - i)), j = n0 - i - 1;
-          const int q = iW[s]; iW[s] = iW[j]; iW[j] = q;
-        }
-      }
-      __syncwarp();
-      double h[9];
-      for (int i = 0; i < 9; i++) h[i] = h0[i];
-      lsq_h(u, iW + n0 - ssiz, ssiz, h, lane);
-      int I; double J;
-      score_all(u, T, h, th, dW, lane, &I, &J);
-      __syncwarp();
-      lo_iterate(u, T, th, h, dW, dW + T, iW, lane, &bI, &bJ, Hb);
-    }
-    if (lane == 0) { loI[warp] = bI; loJ[warp] = bJ; for (int i = 0; i < 9; i++) loH[warp][i] = Hb[i]; }
+  if (no_sam + nhyp >= ITER_SAM && lo_runs == 0 && have && curIs > 4) run_lo = true;
+  if (force_lo) run_lo = have && lo_runs == 0;
+  __syncwarp();
+  if (run_lo) {
+    // LSQ on the TC*th*MWM band of the best SAMPLE, then its inliers at th (exp_ranH.c:997-1012)
+    double h[9];
+    for (int i = 0; i < 9; i++) h[i] = st->Hs[i];
+    int I; double J;
+    score_all(u, T, h, th, dW, lane, &I, &J);
+    __syncwarp();
+    int n = compact_inliers(dW, T, TC * th * MWM, iW, lane);
+    lsq_h(u, iW, n, h, lane);
+    score_all(u, T, h, th, dS, lane, &I, &J);
+    __syncwarp();
+    n = compact_inliers(dS, T, th, inl0, lane);
+    if (lane == 0) { for (int i = 0; i < 9; i++) sh->h0[i] = h[i]; sh->n0 = n; st->lo_runs = lo_runs + 1; sh->lo_id = lo_runs + 1; }
   }
-  __syncthreads();
+  if (lane == 0) sh->run_lo = run_lo ? 1 : 0;
+}
 
-  // (d) warp 0: take the best inner sample (first on ties), accept against maxS, update the stopping rule
-  if (warp == 0) {
-    if (run_lo) {
-      int best = -1; double bJ = 0; int bI = 0;
-      for (int k = 0; k < LO_REPS; k++) if (bJ < loJ[k]) { bJ = loJ[k]; bI = loI[k]; best = k; }
-      const double curJ = st->J;
-      __syncwarp();
-      if (best >= 0 && curJ < bJ) {
-        double h[9];
-        for (int i = 0; i < 9; i++) h[i] = loH[best][i];
-        if (det_ok(h) && (!do_sym || sym_check_ok(u, T, h, th, lane))) {
-          if (lane == 0) { for (int i = 0; i < 9; i++) st->H[i] = h[i]; st->J = bJ; st->I = bI; }
-        }
-      }
-    }
+// (c) inner RANSAC (exp_inHranicustom, exp_ranH.c:741-793): one warp (= one CTA, its own SM) per inner sample
+__global__ void __launch_bounds__(32)
+k_rs_lo(const double* __restrict__ u, int T, double th, unsigned long long seed, LoShare* sh, double* dscr, int* iscr) {
+  if (!sh->run_lo) return;
+  const int rep = blockIdx.x, lane = threadIdx.x;
+  double* dW = dscr + (size_t)rep * 2 * T;
+  int* iW = iscr + (size_t)rep * T;
+  const int* inl0 = iscr + (size_t)RS_NW * T;
+  const int n0 = sh->n0;
+  int bI = 0; double bJ = 0; double Hb[9], h0[9];
+  for (int i = 0; i < 9; i++) { h0[i] = sh->h0[i]; Hb[i] = h0[i]; }
+  if (n0 >= 8) {
+    int ssiz = n0 / 2; if (ssiz > 12) ssiz = 12;
+    // randsubset (rtools.c:25-39) on a private copy of the inlier list
+    for (int k = lane; k < n0; k += 32) iW[k] = inl0[k];
     __syncwarp();
     if (lane == 0) {
-      st->no_sam += nhyp;
-      if (st->I > 0) { const int ns = nsamples(st->I + 1, T, 4, conf); if (ns < st->max_sam) st->max_sam = ns; }
-      st->done = st->no_sam >= st->max_sam;
+      const unsigned long long stream = 0x4C4F000000000000ull + (unsigned long long)sh->lo_id * 64 + rep;
+      for (int i = 0; i < ssiz; i++) {
+        const int s = (int)rs_rand(seed, stream, i, (unsigned)(n0 - i)), j = n0 - i - 1;
+        const int q = iW[s]; iW[s] = iW[j]; iW[j] = q;
+      }
     }
+    __syncwarp();
+    double h[9];
+    for (int i = 0; i < 9; i++) h[i] = h0[i];
+    lsq_h(u, iW + n0 - ssiz, ssiz, h, lane);
+    int I; double J;
+    score_all(u, T, h, th, dW, lane, &I, &J);
+    __syncwarp();
+    lo_iterate(u, T, th, h, dW, dW + T, iW, lane, &bI, &bJ, Hb);
+  }
+  if (lane == 0) { sh->loI[rep] = bI; sh->loJ[rep] = bJ; for (int i = 0; i < 9; i++) sh->loH[rep][i] = Hb[i]; }
+}
+
+// (d) take the best inner sample (first on ties), accept against maxS, update the stopping rule
+__global__ void __launch_bounds__(32)
+k_rs_accept(const double* __restrict__ u, int T, double th, double conf, int do_sym, int nhyp, RsState* st, const LoShare* sh) {
+  const int lane = threadIdx.x;
+  if (sh->run_lo) {
+    int best = -1; double bJ = 0; int bI = 0;
+    for (int k = 0; k < LO_REPS; k++) if (bJ < sh->loJ[k]) { bJ = sh->loJ[k]; bI = sh->loI[k]; best = k; }
+    const double curJ = st->J;
+    __syncwarp();
+    if (best >= 0 && curJ < bJ) {
+      double h[9];
+      for (int i = 0; i < 9; i++) h[i] = sh->loH[best][i];
+      if (det_ok(h) && (!do_sym || sym_check_ok(u, T, h, th, lane))) {
+        if (lane == 0) { for (int i = 0; i < 9; i++) st->H[i] = h[i]; st->J = bJ; st->I = bI; }
+      }
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    st->no_sam += nhyp;
+    if (st->I > 0) { const int ns = nsamples(st->I + 1, T, 4, conf); if (ns < st->max_sam) st->max_sam = ns; }
+    st->done = st->no_sam >= st->max_sam;
   }
 }
 
@@ -473,14 +487,15 @@ __global__ void k_rs_final(const double* __restrict__ u, int T, double th, const
 // inside -- the stopping rule is data dependent) ctx->rs_buf holds the RsState followed by the inlier mask.
 int mg_ransac_run(modsgpu_ctx* ctx, const double* d_u, int T, const modsgpu_ransac_params* p,
                   double* H, unsigned char* inl, modsgpu_ransac_result* res) {
-  const int NW = 12;
-  size_t off_hyp = 256, off_d = off_hyp + sizeof(HypOut) * RS_MAX_B;
+  const int NW = RS_NW;
+  size_t off_sh = 256, off_hyp = off_sh + ((sizeof(LoShare) + 255) & ~(size_t)255), off_d = off_hyp + sizeof(HypOut) * RS_MAX_B;
   size_t off_i = off_d + sizeof(double) * (size_t)(2 * NW + 1) * T;
   size_t off_inl = off_i + sizeof(int) * (size_t)(NW + 1) * T;
   size_t total = off_inl + T + 64;
   MG_CUDA(ctx, ctx->rs_buf.ensure(total));
   uint8_t* base = ctx->rs_buf.as<uint8_t>();
   RsState* st = reinterpret_cast<RsState*>(base);
+  LoShare* sh = reinterpret_cast<LoShare*>(base + off_sh);
   HypOut* hyp = reinterpret_cast<HypOut*>(base + off_hyp);
   double* dscr = reinterpret_cast<double*>(base + off_d);
   int* iscr = reinterpret_cast<int*>(base + off_i);
@@ -497,8 +512,14 @@ int mg_ransac_run(modsgpu_ctx* ctx, const double* d_u, int T, const modsgpu_rans
     MG_PROF(ctx, "k_rs_hyp", 2, (double)B);
     k_rs_hyp<<<ceil_div(B, 8), 256, 0, ctx->stream>>>(d_u, T, p->th, p->seed, basei, B, hyp);
     MG_LAUNCHED(ctx);
-    MG_PROF(ctx, "k_rs_update", 2, (double)T);
-    k_rs_update<<<1, 32 * NW, 0, ctx->stream>>>(d_u, T, p->th, p->conf, p->do_sym_check, p->seed, hyp, B, 0, st, dscr, iscr);
+    MG_PROF(ctx, "k_rs_select", 2, (double)T);
+    k_rs_select<<<1, 384, 0, ctx->stream>>>(d_u, T, p->th, p->do_sym_check, hyp, B, 0, st, sh, dscr, iscr);
+    MG_LAUNCHED(ctx);
+    MG_PROF(ctx, "k_rs_lo", 2, (double)T);
+    k_rs_lo<<<LO_REPS, 32, 0, ctx->stream>>>(d_u, T, p->th, p->seed, sh, dscr, iscr);
+    MG_LAUNCHED(ctx);
+    MG_PROF(ctx, "k_rs_accept", 2, (double)T);
+    k_rs_accept<<<1, 32, 0, ctx->stream>>>(d_u, T, p->th, p->conf, p->do_sym_check, B, st, sh);
     MG_LAUNCHED(ctx);
     MG_CUDA(ctx, cudaMemcpyAsync(hs, st, sizeof(RsState), cudaMemcpyDeviceToHost, ctx->stream));
     MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -506,7 +527,11 @@ int mg_ransac_run(modsgpu_ctx* ctx, const double* d_u, int T, const modsgpu_rans
     if (hs->done) break;
   }
   if (hs->lo_runs == 0) {   // exp_ranH.c:1085-1197: "If there were no LOs, do at least one NOW"
-    k_rs_update<<<1, 32 * NW, 0, ctx->stream>>>(d_u, T, p->th, p->conf, p->do_sym_check, p->seed, hyp, 0, 1, st, dscr, iscr);
+    k_rs_select<<<1, 384, 0, ctx->stream>>>(d_u, T, p->th, p->do_sym_check, hyp, 0, 1, st, sh, dscr, iscr);
+    MG_LAUNCHED(ctx);
+    k_rs_lo<<<LO_REPS, 32, 0, ctx->stream>>>(d_u, T, p->th, p->seed, sh, dscr, iscr);
+    MG_LAUNCHED(ctx);
+    k_rs_accept<<<1, 32, 0, ctx->stream>>>(d_u, T, p->th, p->conf, p->do_sym_check, 0, st, sh);
     MG_LAUNCHED(ctx);
   }
   k_rs_final<<<ceil_div(T, 256), 256, 0, ctx->stream>>>(d_u, T, p->th, st, dinl);

@@ -8,7 +8,7 @@
 //                (slcm Ftools.c:39-81, rroots3 :200-247) -> up to 3 models -> oriented epipolar constraint
 //                (all_ori_valid :430-445) -> Sampson error of all T correspondences (FDs :83-101), lanes
 //                striding over T -> MSAC score; the sample's best model is kept
-//   k_rf_update  one CTA per batch: best model of the batch, symmetric epipolar check (exp_ranF.c:935-950:
+//   k_rf_select / k_rf_lo / k_rf_accept  per batch: best model of the batch, symmetric epipolar check (exp_ranF.c:935-950:
 //                more than 0.6*I correspondences within 16*th), local optimisation = LSQ on the 8*th band
 //                (__LSQ_BEFORE_LO__) + 10 inner samples of <= 14 inliers x 4 shrinking-threshold weighted LSQ
 //                steps (exp_inFranicustom :759-803, exp_iterFcustom :601-757), one warp per inner sample;
@@ -413,19 +413,25 @@ __device__ void f_lo_iterate(const double* __restrict__ u, int T, double th, dou
   *bestI = mI; *bestJ = mJ;
 }
 
-// ---- per-batch update ---------------------------------------------------------------------------------------
-// scratch: per warp w (12 warps): dbuf[w][T], wbuf[w][T] doubles, ibuf[w][T] ints; + one shared d / inlier list
+// ---- per-batch update: three launches (select / inner samples on LO_REPS SMs / accept), as in ransac.cu ------
+// scratch: per inner sample w: dbuf[w][2T]; then dS[T]; then wbuf[w][T] doubles; ibuf[w][T] ints + inl0[T]
+struct FLoShare {
+  double f0[9];
+  int n0, run_lo, lo_id, pad;
+  double loJ[LO_REPS]; int loI[LO_REPS]; double loF[LO_REPS][9];
+};
+constexpr int RF_NW = 12;
+
 __global__ void __launch_bounds__(384)
-k_rf_update(const double* __restrict__ u, int T, double th, double conf, int do_sym, unsigned long long seed,
-            FHyp* __restrict__ hyp, int nhyp, int force_lo, RfState* st, double* dscr, int* iscr) {
+k_rf_select(const double* __restrict__ u, int T, double th, int do_sym, FHyp* __restrict__ hyp, int nhyp, int force_lo,
+            RfState* st, FLoShare* sh, double* dscr, int* iscr) {
   __shared__ double sJ[12]; __shared__ int sIdx[12];
-  __shared__ double loJ[LO_REPS]; __shared__ int loI[LO_REPS]; __shared__ double loF[LO_REPS][9];
-  __shared__ double f0[9]; __shared__ int n0_s; __shared__ int run_lo_s; __shared__ int again_s;
+  __shared__ int again_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  double* dW = dscr + (size_t)warp * 2 * T;
-  int* iW = iscr + (size_t)warp * T;
-  double* dS = dscr + (size_t)nw * 2 * T;
-  int* inl0 = iscr + (size_t)nw * T;
+  double* dW = dscr;
+  int* iW = iscr;
+  double* dS = dscr + (size_t)RF_NW * 2 * T;
+  int* inl0 = iscr + (size_t)RF_NW * T;
 
   // (a)+(b): best model of the batch; a model that would become the best-so-far must pass the symmetric check,
   // otherwise it is discarded and the next best is tried (exp_ranF.c:933-960 `continue`)
@@ -469,79 +475,82 @@ k_rf_update(const double* __restrict__ u, int T, double th, double conf, int do_
     __syncthreads();
     if (!again_s) break;
   }
+  if (warp != 0) return;
 
   // (b') when to run the local optimisation (exp_ranF.c:1017-1040): a new best sample after ITER_SAM samples,
   // or once when ITER_SAM is reached
-  if (warp == 0) {
-    const int no_sam = st->no_sam, lo_runs = st->lo_runs, have = st->have_sample;
-    __syncwarp();
-    bool run_lo = false;
-    if (have) {
-      if (lo_runs == 0 && no_sam + nhyp >= ITER_SAM) run_lo = true;
-      if (new_best_sample && no_sam + nhyp > ITER_SAM) run_lo = true;
-    }
-    if (force_lo) run_lo = have && lo_runs == 0;
-    __syncwarp();
-    if (run_lo) {
-      // __LSQ_BEFORE_LO__ (exp_ranF.c:1048-1054): LSQ on the TC*th*MWM band of the best sample, inliers at th
-      double f[9];
-      for (int i = 0; i < 9; i++) f[i] = st->Fs[i];
-      int I; double J;
-      f_score_all(u, T, f, th, dW, nullptr, lane, &I, &J);
-      __syncwarp();
-      int n = compact_inliers(dW, T, TC * th * MWM, iW, lane);
-      lsq_f(u, iW, n, nullptr, f, lane);
-      f_score_all(u, T, f, th, dS, nullptr, lane, &I, &J);
-      __syncwarp();
-      n = compact_inliers(dS, T, th, inl0, lane);
-      if (lane == 0) { for (int i = 0; i < 9; i++) f0[i] = f[i]; n0_s = n; st->lo_runs = lo_runs + 1; }
-    }
-    if (lane == 0) run_lo_s = run_lo ? 1 : 0;
+  const int no_sam = st->no_sam, lo_runs = st->lo_runs, have = st->have_sample;
+  __syncwarp();
+  bool run_lo = false;
+  if (have) {
+    if (lo_runs == 0 && no_sam + nhyp >= ITER_SAM) run_lo = true;
+    if (new_best_sample && no_sam + nhyp > ITER_SAM) run_lo = true;
   }
-  __syncthreads();
+  if (force_lo) run_lo = have && lo_runs == 0;
+  __syncwarp();
+  if (run_lo) {
+    // __LSQ_BEFORE_LO__ (exp_ranF.c:1048-1054): LSQ on the TC*th*MWM band of the best sample, inliers at th
+    double f[9];
+    for (int i = 0; i < 9; i++) f[i] = st->Fs[i];
+    int I; double J;
+    f_score_all(u, T, f, th, dW, nullptr, lane, &I, &J);
+    __syncwarp();
+    int n = compact_inliers(dW, T, TC * th * MWM, iW, lane);
+    lsq_f(u, iW, n, nullptr, f, lane);
+    f_score_all(u, T, f, th, dS, nullptr, lane, &I, &J);
+    __syncwarp();
+    n = compact_inliers(dS, T, th, inl0, lane);
+    if (lane == 0) { for (int i = 0; i < 9; i++) sh->f0[i] = f[i]; sh->n0 = n; st->lo_runs = lo_runs + 1; sh->lo_id = lo_runs + 1; }
+  }
+  if (lane == 0) sh->run_lo = run_lo ? 1 : 0;
+}
 
-  // (c) inner RANSAC (exp_inFranicustom): LO_REPS samples of <= 14 inliers, one warp each
-  const bool run_lo = run_lo_s != 0;
-  const int n0 = run_lo ? n0_s : 0;
-  if (run_lo && warp < LO_REPS) {
-    int bI = 0; double bJ = 0; double Fb[9];
-    for (int i = 0; i < 9; i++) Fb[i] = f0[i];
-    if (n0 >= 16) {
-      int ssiz = n0 / 2; if (ssiz > 14) ssiz = 14;
-      for (int k = lane; k < n0; k += 32) iW[k] = inl0[k];
-      __syncwarp();
-      if (lane == 0) {
-        const unsigned long long stream = 0x464C000000000000ull + (unsigned long long)st->lo_runs * 64 + warp;
-        for (int i = 0; i < ssiz; i++) {
-          const int s = (int)rs_rand(seed, stream, i, (unsigned)(n0 - i)), j = n0 - i - 1;
-          const int q = iW[s]; iW[s] = iW[j]; iW[j] = q;
-        }
+// (c) inner RANSAC (exp_inFranicustom): one warp (= one CTA) per inner sample of <= 14 inliers
+__global__ void __launch_bounds__(32)
+k_rf_lo(const double* __restrict__ u, int T, double th, unsigned long long seed, FLoShare* sh, double* dscr, int* iscr) {
+  if (!sh->run_lo) return;
+  const int rep = blockIdx.x, lane = threadIdx.x;
+  double* dW = dscr + (size_t)rep * 2 * T;
+  double* wW = dscr + (size_t)(2 * RF_NW + 1) * T + (size_t)rep * T;
+  int* iW = iscr + (size_t)rep * T;
+  const int* inl0 = iscr + (size_t)RF_NW * T;
+  const int n0 = sh->n0;
+  int bI = 0; double bJ = 0; double Fb[9], f0[9];
+  for (int i = 0; i < 9; i++) { f0[i] = sh->f0[i]; Fb[i] = f0[i]; }
+  if (n0 >= 16) {
+    int ssiz = n0 / 2; if (ssiz > 14) ssiz = 14;
+    for (int k = lane; k < n0; k += 32) iW[k] = inl0[k];
+    __syncwarp();
+    if (lane == 0) {
+      const unsigned long long stream = 0x464C000000000000ull + (unsigned long long)sh->lo_id * 64 + rep;
+      for (int i = 0; i < ssiz; i++) {
+        const int s = (int)rs_rand(seed, stream, i, (unsigned)(n0 - i)), j = n0 - i - 1;
+        const int q = iW[s]; iW[s] = iW[j]; iW[j] = q;
       }
-      __syncwarp();
-      double f[9];
-      for (int i = 0; i < 9; i++) f[i] = f0[i];
-      lsq_f(u, iW + n0 - ssiz, ssiz, nullptr, f, lane);
-      int I; double J;
-      f_score_all(u, T, f, th, dW, nullptr, lane, &I, &J);
-      __syncwarp();
-      // d0 = dW; working errors / weights in the second half of this warp's buffer and in dS-sized scratch
-      f_lo_iterate(u, T, th, f, dW, dW + T, dscr + (size_t)(2 * nw + 1) * T + (size_t)warp * T, iW, lane, &bI, &bJ, Fb);
     }
-    if (lane == 0) { loI[warp] = bI; loJ[warp] = bJ; for (int i = 0; i < 9; i++) loF[warp][i] = Fb[i]; }
+    __syncwarp();
+    double f[9];
+    for (int i = 0; i < 9; i++) f[i] = f0[i];
+    lsq_f(u, iW + n0 - ssiz, ssiz, nullptr, f, lane);
+    int I; double J;
+    f_score_all(u, T, f, th, dW, nullptr, lane, &I, &J);
+    __syncwarp();
+    f_lo_iterate(u, T, th, f, dW, dW + T, wW, iW, lane, &bI, &bJ, Fb);
   }
-  __syncthreads();
+  if (lane == 0) { sh->loI[rep] = bI; sh->loJ[rep] = bJ; for (int i = 0; i < 9; i++) sh->loF[rep][i] = Fb[i]; }
+}
 
-  // (d) accept the best inner sample (exp_ranF.c:1064-1074), update the stopping rule
-  if (warp == 0 && lane == 0) {
-    if (run_lo) {
-      int best = -1; double bJ = 0; int bI = 0;
-      for (int k = 0; k < LO_REPS; k++) if (bJ < loJ[k]) { bJ = loJ[k]; bI = loI[k]; best = k; }
-      if (best >= 0 && st->J < bJ) { for (int i = 0; i < 9; i++) st->F[i] = loF[best][i]; st->J = bJ; st->I = bI; }
-    }
-    st->no_sam += nhyp;
-    if (st->I > 0) { const int ns = nsamples(st->I + 1, T, 7, conf); if (ns < st->max_sam) st->max_sam = ns; }
-    st->done = st->no_sam >= st->max_sam;
+// (d) accept the best inner sample (exp_ranF.c:1064-1074), update the stopping rule
+__global__ void k_rf_accept(int T, double conf, int nhyp, RfState* st, const FLoShare* sh) {
+  if (threadIdx.x != 0) return;
+  if (sh->run_lo) {
+    int best = -1; double bJ = 0; int bI = 0;
+    for (int k = 0; k < LO_REPS; k++) if (bJ < sh->loJ[k]) { bJ = sh->loJ[k]; bI = sh->loI[k]; best = k; }
+    if (best >= 0 && st->J < bJ) { for (int i = 0; i < 9; i++) st->F[i] = sh->loF[best][i]; st->J = bJ; st->I = bI; }
   }
+  st->no_sam += nhyp;
+  if (st->I > 0) { const int ns = nsamples(st->I + 1, T, 7, conf); if (ns < st->max_sam) st->max_sam = ns; }
+  st->done = st->no_sam >= st->max_sam;
 }
 
 __global__ void k_rf_final(const double* __restrict__ u, int T, double th, const RfState* st, unsigned char* inl) {
@@ -554,14 +563,15 @@ __global__ void k_rf_final(const double* __restrict__ u, int T, double th, const
 
 int mg_ransac_F_run(modsgpu_ctx* ctx, const double* d_u, int T, const modsgpu_ransac_params* p,
                     double* F, unsigned char* inl, modsgpu_ransac_result* res) {
-  const int NW = 12;
-  size_t off_hyp = 256, off_d = off_hyp + sizeof(FHyp) * RS_MAX_B;
+  const int NW = RF_NW;
+  size_t off_sh = 256, off_hyp = off_sh + ((sizeof(FLoShare) + 255) & ~(size_t)255), off_d = off_hyp + sizeof(FHyp) * RS_MAX_B;
   size_t off_i = off_d + sizeof(double) * (size_t)(3 * NW + 1) * T;
   size_t off_inl = off_i + sizeof(int) * (size_t)(NW + 1) * T;
   size_t total = off_inl + T + 64;
   MG_CUDA(ctx, ctx->rs_buf.ensure(total));
   uint8_t* base = ctx->rs_buf.as<uint8_t>();
   RfState* st = reinterpret_cast<RfState*>(base);
+  FLoShare* sh = reinterpret_cast<FLoShare*>(base + off_sh);
   FHyp* hyp = reinterpret_cast<FHyp*>(base + off_hyp);
   double* dscr = reinterpret_cast<double*>(base + off_d);
   int* iscr = reinterpret_cast<int*>(base + off_i);
@@ -578,8 +588,13 @@ int mg_ransac_F_run(modsgpu_ctx* ctx, const double* d_u, int T, const modsgpu_ra
     MG_PROF(ctx, "k_rf_hyp", 2, (double)B);
     k_rf_hyp<<<ceil_div(B, 8), 256, 0, ctx->stream>>>(d_u, T, p->th, p->seed, basei, B, hyp);
     MG_LAUNCHED(ctx);
-    MG_PROF(ctx, "k_rf_update", 2, (double)T);
-    k_rf_update<<<1, 32 * NW, 0, ctx->stream>>>(d_u, T, p->th, p->conf, p->do_sym_check, p->seed, hyp, B, 0, st, dscr, iscr);
+    MG_PROF(ctx, "k_rf_select", 2, (double)T);
+    k_rf_select<<<1, 384, 0, ctx->stream>>>(d_u, T, p->th, p->do_sym_check, hyp, B, 0, st, sh, dscr, iscr);
+    MG_LAUNCHED(ctx);
+    MG_PROF(ctx, "k_rf_lo", 2, (double)T);
+    k_rf_lo<<<LO_REPS, 32, 0, ctx->stream>>>(d_u, T, p->th, p->seed, sh, dscr, iscr);
+    MG_LAUNCHED(ctx);
+    k_rf_accept<<<1, 32, 0, ctx->stream>>>(T, p->conf, B, st, sh);
     MG_LAUNCHED(ctx);
     MG_CUDA(ctx, cudaMemcpyAsync(hs, st, sizeof(RfState), cudaMemcpyDeviceToHost, ctx->stream));
     MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -587,7 +602,11 @@ int mg_ransac_F_run(modsgpu_ctx* ctx, const double* d_u, int T, const modsgpu_ra
     if (hs->done) break;
   }
   if (hs->lo_runs == 0) {   // exp_ranF.c:1086: "If there were no LOs, do at least one NOW!"
-    k_rf_update<<<1, 32 * NW, 0, ctx->stream>>>(d_u, T, p->th, p->conf, p->do_sym_check, p->seed, hyp, 0, 1, st, dscr, iscr);
+    k_rf_select<<<1, 384, 0, ctx->stream>>>(d_u, T, p->th, p->do_sym_check, hyp, 0, 1, st, sh, dscr, iscr);
+    MG_LAUNCHED(ctx);
+    k_rf_lo<<<LO_REPS, 32, 0, ctx->stream>>>(d_u, T, p->th, p->seed, sh, dscr, iscr);
+    MG_LAUNCHED(ctx);
+    k_rf_accept<<<1, 32, 0, ctx->stream>>>(T, p->conf, 0, st, sh);
     MG_LAUNCHED(ctx);
   }
   k_rf_final<<<ceil_div(T, 256), 256, 0, ctx->stream>>>(d_u, T, p->th, st, dinl);

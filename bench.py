@@ -158,7 +158,8 @@ def run_reference(args, rank, world):
         return
     threads = os.cpu_count() or 1
     pairs = make_pairs(2, 0)
-    stride = 8
+    # bounded sample per step: every stride-th keypoint, chosen so that K steps end within a few minutes
+    stride = 8 if args.steps <= 24 else (16 if args.steps <= 64 else 32)
     for _ in range(min(args.warmup, 1)):
         cpu_pair(pairs[0], stride, threads)
     secs, parts = [], None
@@ -299,6 +300,8 @@ def run_gpu(args, rank, world, local_rank):
         for k in range(W):
             step_value(wk, k, False)
             step_e2e(wk, k, False)
+    gather_results()      # NCCL communicators are created lazily: build them outside the timed region
+    barrier()
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
@@ -318,6 +321,11 @@ def run_gpu(args, rank, world, local_rank):
     lib.modsgpu_profile_enable(ctx, 0)
     prof = json.loads(buf.value.decode() or "{}")
     if rank != 0:
+        for m in mgs:
+            m.close()
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
         return
     lastr = last.get("r")
     value = world * args.steps / (dev_ms * 1e-3)
@@ -334,8 +342,19 @@ def run_gpu(args, rank, world, local_rank):
         else:
             peak = peaks.get("bf16_tflops_sustained", 1400.0)
             src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback"
+        # DRAM traffic of that kernel from the committed `ncu --set full` capture (one launch, the grid named there)
+        traffic, traffic_of = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            for name, rec in tj.items():
+                if top.startswith(name) or name.startswith(top.split("<")[0]):
+                    traffic = rec["dram_bytes_read"] + rec["dram_bytes_write"]
+                    traffic_of = "one launch, grid %s (%s)" % (rec["grid"], rec["source"])
+                    break
+        except (OSError, ValueError, KeyError):
+            pass
         roofline = {"kernel": top, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
-                    "frac": achieved / peak, "traffic": None, "peak_source": src,
+                    "frac": achieved / peak, "traffic": traffic, "traffic_of": traffic_of, "peak_source": src,
                     "launches": p["launches"], "avg_us": 1e3 * p["ms"] / max(p["launches"], 1),
                     "share_of_kernel_time": p["ms"] / total_kernel_ms}
     kernels = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
@@ -376,16 +395,19 @@ def run_gpu(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
     for m in mgs:
         m.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=96)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workers", type=int, default=int(os.environ.get("MODSGPU_BENCH_WORKERS", "4")),
+    ap.add_argument("--workers", type=int, default=int(os.environ.get("MODSGPU_BENCH_WORKERS", "8")),
                     help="worker threads (one modsgpu_ctx / CUDA stream each) per GPU")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -8,7 +8,7 @@ NVFLAGS = $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-ffp-contract=off -I
 # detect.cu / sampler.cu are the bit-exact integer/float paths: no FMA contraction
 EXACT = --fmad=false
 
-OBJS = $(OBJ)/api.o $(OBJ)/detect.o $(OBJ)/sampler.o $(OBJ)/cnn.o $(OBJ)/match.o $(OBJ)/ransac.o $(OBJ)/ransac_f.o $(OBJ)/npz.o $(OBJ)/mods_host.o
+OBJS = $(OBJ)/api.o $(OBJ)/detect.o $(OBJ)/sampler.o $(OBJ)/cnn.o $(OBJ)/match.o $(OBJ)/ransac.o $(OBJ)/ransac_f.o $(OBJ)/synth.o $(OBJ)/npz.o $(OBJ)/mods_host.o
 
 all: $(PKG)/libmodsgpu.so $(PKG)/libmodsgpu_degensac.so oracle
 
@@ -19,6 +19,9 @@ $(OBJ)/sampler.o: $(SRC)/sampler.cu $(SRC)/common.cuh include/modsgpu.h
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVFLAGS) $(EXACT) -c $< -o $@
 $(OBJ)/ransac.o: $(SRC)/ransac.cu $(SRC)/ransac_common.cuh $(SRC)/common.cuh include/modsgpu.h
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) $(EXACT) -c $< -o $@
+$(OBJ)/synth.o: $(SRC)/synth.cu $(SRC)/common.cuh include/modsgpu.h
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVFLAGS) $(EXACT) -c $< -o $@
 $(OBJ)/ransac_f.o: $(SRC)/ransac_f.cu $(SRC)/ransac_common.cuh $(SRC)/common.cuh include/modsgpu.h

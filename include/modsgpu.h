@@ -54,6 +54,14 @@ int  modsgpu_image_download(modsgpu_ctx* ctx, const modsgpu_image* img, float* g
 void modsgpu_image_size(const modsgpu_image* img, int* w, int* h);
 void modsgpu_image_free(modsgpu_ctx* ctx, modsgpu_image* img);
 
+/* ---- view synthesis (replaces GenerateSynthImageCorr synth-detection.cpp:324-518: rotate by phi, anisotropic
+ *      anti-aliasing blur, tilt / zoom; tilt < 0 = vertical tilt; phi in [0, pi); the identity view is a copy).
+ *      H: 9 doubles, row-major, original -> view (SynthImage::H).  Arithmetic = OpenCV 4.x warpAffine /
+ *      GaussianBlur for CV_32F, bit-exact against cv2 4.13 (tests/golden/synth_pins.npz). ----------------------- */
+int  modsgpu_synth_geometry(int w, int h, double tilt, double phi, double zoom, int* ow, int* oh, double* H);
+int  modsgpu_synth_view(modsgpu_ctx* ctx, const modsgpu_image* in, double tilt, double phi, double zoom,
+                        double InitSigma, int doBlur, modsgpu_image** out, double* H);
+
 /* ---- S1 detector (replaces DetectAffineKeypoints scale-space-detector.cpp:13-32 ->
  *      ScaleSpaceDetector::detectPyramidKeypoints pyramid.cpp:496-529, for DET_HESSIAN,
  *      FIXED_TH, doBaumberg = 0) ------------------------------------------------------------ */

@@ -139,6 +139,17 @@ class ModsGpu:
         self._check(self.lib.modsgpu_image_download(self.ctx, img.handle, _p(out)))
         return out
 
+    # ---- view synthesis
+    def synth_view(self, img, tilt, phi, zoom, init_sigma, do_blur=1):
+        """modsgpu_synth_view -> (Image, H[3x3])"""
+        hd = C.c_void_p()
+        H = np.zeros(9, np.float64)
+        self._check(self.lib.modsgpu_synth_view(self.ctx, img.handle, C.c_double(tilt), C.c_double(phi), C.c_double(zoom),
+                                                C.c_double(init_sigma), int(do_blur), C.byref(hd), _p(H)))
+        w, h = C.c_int(), C.c_int()
+        self.lib.modsgpu_image_size(hd, C.byref(w), C.byref(h))
+        return Image(self, hd, w.value, h.value), H.reshape(3, 3)
+
     # ---- detector
     def detect(self, img, params=None):
         if params is None:

@@ -159,6 +159,210 @@ extern "C" void orc_half_image(const float* in, int w, int h, float* out) {
 }
 
 /* ========================================================================== */
+/* view synthesis                                                             */
+/* ========================================================================== */
+
+/* cv::warpAffine for CV_32F / INTER_LINEAR / BORDER_CONSTANT, OpenCV 4.x imgwarp.cpp: the forward matrix is
+ * inverted in double, source coordinates are evaluated in 22.10 fixed point (AB_BITS = 10) with per-column
+ * tables adelta/bdelta and rounded to 1/32 px (INTER_BITS = 5); remapBilinear then blends the 4 neighbours with
+ * float weights (1-fy)(1-fx), (1-fy)fx, fy(1-fx), fy*fx accumulated left to right without fusion.  Out-of-image
+ * neighbours take the border value.  Pinned bit-exactly against cv2 4.13 (tests/golden/synth_pins.npz). */
+extern "C" void orc_warp_affine(const float* in, int w, int h, const double* Min, float* out, int ow, int oh, float border) {
+  double M[6];
+  for (int i = 0; i < 6; i++) M[i] = Min[i];
+  double D = M[0] * M[4] - M[1] * M[3];
+  D = D != 0 ? 1. / D : 0;
+  double A11 = M[4] * D, A22 = M[0] * D;
+  M[0] = A11; M[1] *= -D;
+  M[3] *= -D; M[4] = A22;
+  double b1 = -M[0] * M[2] - M[1] * M[5];
+  double b2 = -M[3] * M[2] - M[4] * M[5];
+  M[2] = b1; M[5] = b2;
+  const int AB_BITS = 10, AB_SCALE = 1 << AB_BITS, INTER_BITS = 5, INTER_TAB_SIZE = 1 << INTER_BITS;
+  const int round_delta = AB_SCALE / INTER_TAB_SIZE / 2;
+  std::vector<int> adelta(ow), bdelta(ow);
+  for (int x = 0; x < ow; x++) {
+    adelta[x] = (int)std::lrint(M[0] * x * AB_SCALE);
+    bdelta[x] = (int)std::lrint(M[3] * x * AB_SCALE);
+  }
+  auto PX = [&](int yy, int xx) -> float {
+    return (yy >= 0 && yy < h && xx >= 0 && xx < w) ? in[(size_t)yy * w + xx] : border;
+  };
+  for (int y = 0; y < oh; y++) {
+    const int X0 = (int)std::lrint((M[1] * y + M[2]) * AB_SCALE) + round_delta;
+    const int Y0 = (int)std::lrint((M[4] * y + M[5]) * AB_SCALE) + round_delta;
+    for (int x = 0; x < ow; x++) {
+      const int X = (X0 + adelta[x]) >> (AB_BITS - INTER_BITS), Y = (Y0 + bdelta[x]) >> (AB_BITS - INTER_BITS);
+      const int sx = X >> INTER_BITS, sy = Y >> INTER_BITS;
+      const float a = (float)(X & (INTER_TAB_SIZE - 1)) / 32.0f, b = (float)(Y & (INTER_TAB_SIZE - 1)) / 32.0f;
+      const float w0 = (1.0f - b) * (1.0f - a), w1 = (1.0f - b) * a, w2 = b * (1.0f - a), w3 = b * a;
+      float v = PX(sy, sx) * w0 + PX(sy, sx + 1) * w1;
+      v = v + PX(sy + 1, sx) * w2;
+      v = v + PX(sy + 1, sx + 1) * w3;
+      out[(size_t)y * ow + x] = v;
+    }
+  }
+}
+
+static void gaussian_taps_d(int ks, double sigma, std::vector<float>& k) {
+  const int r = ks / 2;
+  std::vector<double> kd(ks);
+  double sum = 0;
+  for (int i = 0; i < ks; i++) { double x = i - r; kd[i] = std::exp(-x * x / (2.0 * sigma * sigma)); sum += kd[i]; }
+  k.resize(ks);
+  for (int i = 0; i < ks; i++) k[i] = (float)(kd[i] / sum);
+}
+static inline int reflect101(int i, int n) {
+  if (n == 1) return 0;
+  while (i < 0 || i >= n) i = i < 0 ? -i : 2 * (n - 1) - i;
+  return i;
+}
+
+/* cv::GaussianBlur with separate kernel sizes / sigmas and BORDER_REFLECT_101 (synth-detection.cpp:499).
+ * Arithmetic order of OpenCV 4.13 sepFilter2D for CV_32F (pinned bit-exactly, tests/golden/synth_pins.npz):
+ *   row, ks == 3: x < w&~1: fma(x0,k1,(x[+1]+x[-1])*k2)      else fma(x[+1]+x[-1],k2,x0*k1)
+ *   row, ks == 5 / ks >= 7: as orc_gaussian_blur
+ *   col, ks == 3: fma(up+down,k2,c*k1) everywhere;  ks >= 5: as orc_gaussian_blur (fused iff x < w&~7) */
+extern "C" void orc_gaussian_blur_xy(const float* in, float* out, int w, int h, int kx, int ky, double sigma_x, double sigma_y) {
+  std::vector<float> KX, KY;
+  gaussian_taps_d(kx, sigma_x, KX);
+  gaussian_taps_d(ky, sigma_y, KY);
+  std::vector<float> tmp((size_t)w * h);
+  {
+    const int ks = kx, r = ks / 2;
+    const float* k = KX.data();
+    for (int y = 0; y < h; y++) {
+      auto P = [&](int d) -> float { return in[(size_t)y * w + reflect101(d, w)]; };
+      for (int x = 0; x < w; x++) {
+        float s;
+        if (ks == 1) s = P(x) * k[0];
+        else if (ks == 3) {
+          const float p1 = P(x + 1) + P(x - 1), x0 = P(x);
+          if (x < (w & ~1)) s = fmaf(x0, k[1], p1 * k[2]);
+          else s = fmaf(p1, k[2], x0 * k[1]);
+        } else if (ks == 5) {
+          const float p1 = P(x + 1) + P(x - 1), p2 = P(x + 2) + P(x - 2), x0 = P(x);
+          if (x < (w & ~1)) { s = p1 * k[3]; s = fmaf(x0, k[2], s); s = fmaf(p2, k[4], s); }
+          else { s = x0 * k[2] + p1 * k[3]; s = s + p2 * k[4]; }
+        } else if (x < (w & ~3)) {
+          s = 0;
+          for (int t = 0; t < ks; t++) s = fmaf(P(x + t - r), k[t], s);
+        } else {
+          const int nf = (ks - 1) % 4;
+          s = P(x - r) * k[0];
+          for (int t = 1; t < ks; t++) {
+            if (t >= ks - nf) s = fmaf(P(x + t - r), k[t], s);
+            else s = s + P(x + t - r) * k[t];
+          }
+        }
+        tmp[(size_t)y * w + x] = s;
+      }
+    }
+  }
+  {
+    const int ks = ky, r = ks / 2;
+    const float* k = KY.data();
+    const int wc = w & ~7;
+    for (int y = 0; y < h; y++)
+      for (int x = 0; x < w; x++) {
+        auto T = [&](int d) -> float { return tmp[(size_t)reflect101(d, h) * w + x]; };
+        float s = T(y) * k[r];
+        if (ks == 3 || x < wc)
+          for (int t = 1; t <= r; t++) s = fmaf(T(y - t) + T(y + t), k[r + t], s);
+        else
+          for (int t = 1; t <= r; t++) s = s + (T(y - t) + T(y + t)) * k[r + t];
+        out[(size_t)y * w + x] = s;
+      }
+  }
+}
+
+/* synth-detection.cpp:356-431: output size and H of the synthesised view */
+static void synth_rot(int w, int h, double phi, int* wr, int* hr, double* R) {
+  if ((phi >= 0) && (phi < M_PI / 2)) {
+    *wr = (int)std::floor((0.5 + std::cos(phi) * w + std::sin(phi) * h));
+    *hr = (int)std::floor((0.5 + std::sin(phi) * w + std::cos(phi) * h));
+    R[0] = std::cos(phi); R[1] = std::sin(phi); R[2] = 0;
+    R[3] = -std::sin(phi); R[4] = std::cos(phi); R[5] = std::floor(0.5 + std::sin(phi) * w);
+  } else {
+    *wr = (int)std::floor((0.5 - std::cos(phi) * w + std::sin(phi) * h));
+    *hr = (int)std::floor((0.5 + std::sin(phi) * w - std::cos(phi) * h));
+    R[0] = std::cos(phi); R[1] = std::sin(phi); R[2] = -std::floor(std::cos(phi) * w);
+    R[3] = -std::sin(phi); R[4] = std::cos(phi); R[5] = std::floor(0.5 + (std::sin(phi) * w - std::cos(phi) * h));
+  }
+}
+extern "C" int orc_synth_geometry(int w, int h, double tilt, double phi, double zoom, int* ow, int* oh, double* H) {
+  bool vertical = false;
+  if (tilt < 0) { tilt = -tilt; vertical = true; }
+  const int zoomed = std::fabs(zoom - 1.0f) >= 0.05 ? 1 : 0;
+  const int wS1 = (int)(w * zoom), hS1 = (int)(h * zoom);
+  for (int i = 0; i < 9; i++) H[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  if ((std::fabs(tilt - 1.) <= 0.1) && (std::abs((int)phi) <= 0.2) && (std::fabs(zoom - 1.) <= 0.1)) {   /* abs(phi): int abs, :366 */
+    *ow = w; *oh = h;
+    return 1;
+  }
+  double kV = 1., kH = 1.;
+  if (zoomed) { kV = (double)w / (double)wS1; kH = (double)h / (double)hS1; }
+  const double tx = vertical ? kH : tilt * kH, ty = vertical ? tilt * kV : kV;
+  const double c = std::cos(phi), s = std::sin(phi);
+  double w_new, h_new;
+  if ((phi >= 0) && (phi < M_PI / 2)) {
+    w_new = std::floor((0.5 + c * w + s * h) / tx);
+    h_new = std::floor((0.5 + s * w + c * h) / ty);
+    H[0] = c / tx; H[1] = s / tx; H[2] = 0;
+    H[3] = -s / ty; H[4] = c / ty; H[5] = std::floor(0.5 + s * w / ty);
+  } else {
+    w_new = std::floor((0.5 - c * w + s * h) / tx);
+    h_new = std::floor((0.5 + s * w - c * h) / ty);
+    H[0] = c / tx; H[1] = s / tx; H[2] = -std::floor(c * w / tx);
+    H[3] = -s / ty; H[4] = c / ty; H[5] = std::floor(0.5 + (s * w - c * h) / ty);
+  }
+  H[6] = 0; H[7] = 0; H[8] = 1;
+  *ow = (int)w_new; *oh = (int)h_new;
+  return 0;
+}
+
+/* synth-detection.cpp:324-518 (non-AREA_INTERP branch): rotate -> anisotropic anti-alias blur -> tilt/zoom */
+extern "C" void orc_synth_view(const float* gray, int w, int h, double tilt, double phi, double zoom, double InitSigma,
+                               int doBlur, float* out) {
+  int ow, oh;
+  double H[9];
+  if (orc_synth_geometry(w, h, tilt, phi, zoom, &ow, &oh, H)) {
+    std::memcpy(out, gray, sizeof(float) * (size_t)w * h);
+    return;
+  }
+  bool vertical = false;
+  if (tilt < 0) { tilt = -tilt; vertical = true; }
+  const int zoomed = std::fabs(zoom - 1.0f) >= 0.05 ? 1 : 0;
+  const int wS1 = (int)(w * zoom), hS1 = (int)(h * zoom);
+  double kV = 1., kH = 1.;
+  if (zoomed) { kV = (double)w / (double)wS1; kH = (double)h / (double)hS1; }
+  const double sigma_aa_2 = zoomed ? InitSigma / (4.0 * zoom) : InitSigma / 2.0;
+  const double sigma_aa = InitSigma * tilt / (2.0 * zoom);
+  const double sigma_x = vertical ? sigma_aa_2 : sigma_aa, sigma_y = vertical ? sigma_aa : sigma_aa_2;
+  int wr, hr;
+  double R[6];
+  synth_rot(w, h, phi, &wr, &hr, R);
+  std::vector<float> rot((size_t)wr * hr), blurred;
+  orc_warp_affine(gray, w, h, R, rot.data(), wr, hr, 128.f);
+  const float* src = rot.data();
+  if (doBlur) {
+    int kx = (int)std::floor(2.0 * 3.0 * sigma_x + 1.0);
+    if (kx % 2 == 0) kx++;
+    if (kx < 3) kx = 3;
+    int ky = (int)std::floor(2.0 * 3.0 * sigma_y + 1.0);
+    if (ky % 2 == 0) ky++;
+    if (ky < 3) ky = 3;
+    blurred.resize(rot.size());
+    orc_gaussian_blur_xy(rot.data(), blurred.data(), wr, hr, kx, ky, sigma_x, sigma_y);
+    src = blurred.data();
+  }
+  double Wm[6] = {0, 0, 0, 0, 0, 0};
+  if (vertical) { Wm[0] = 1.0 / kH; Wm[4] = 1.0 / (tilt * kV); }
+  else { Wm[0] = 1.0 / (tilt * kH); Wm[4] = 1.0 / kV; }
+  orc_warp_affine(src, wr, hr, Wm, out, ow, oh, 128.f);
+}
+
+/* ========================================================================== */
 /* detector                                                                   */
 /* ========================================================================== */
 

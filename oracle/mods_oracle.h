@@ -58,6 +58,17 @@ void orc_hessian_response(const float* in, float* out, int w, int h, float norm)
 void orc_half_size(int w, int h, int* ow, int* oh);
 void orc_half_image(const float* in, int w, int h, float* out);
 
+/* ---- view synthesis (synth-detection.cpp:324-518 GenerateSynthImageCorr) ---- */
+/* cv::warpAffine(src, dst, M (2x3 double, forward map), Size(ow,oh), INTER_LINEAR, BORDER_CONSTANT, border) on CV_32F */
+void orc_warp_affine(const float* in, int w, int h, const double* M, float* out, int ow, int oh, float border);
+/* cv::GaussianBlur(img, img, Size(kx,ky), sigma_x, sigma_y) with the default BORDER_REFLECT_101 */
+void orc_gaussian_blur_xy(const float* in, float* out, int w, int h, int kx, int ky, double sigma_x, double sigma_y);
+/* output size + H (row-major 3x3) of GenerateSynthImageCorr; returns 1 for the identity view (pixels = input) */
+int  orc_synth_geometry(int w, int h, double tilt, double phi, double zoom, int* ow, int* oh, double* H);
+/* the whole function; out must hold ow*oh floats (from orc_synth_geometry) */
+void orc_synth_view(const float* gray, int w, int h, double tilt, double phi, double zoom, double InitSigma, int doBlur,
+                    float* out);
+
 /* ---- detector (pyramid.cpp:428-529, scale-space-detector.hpp:47-198) ------ */
 int orc_detect_hessian(const float* gray, int w, int h, const orc_pyr_params* p,
                        orc_keypoint* out, int cap);

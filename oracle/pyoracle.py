@@ -75,6 +75,41 @@ def gaussian_blur(img, sigma):
     return out
 
 
+def warp_affine(img, M, ow, oh, border=128.0):
+    img = np.ascontiguousarray(img, np.float32)
+    h, w = img.shape
+    M = np.ascontiguousarray(M, np.float64).reshape(6)
+    out = np.empty((oh, ow), np.float32)
+    lib().orc_warp_affine(_p(img), w, h, _p(M), _p(out), ow, oh, C.c_float(border))
+    return out
+
+
+def gaussian_blur_xy(img, kx, ky, sigma_x, sigma_y):
+    img = np.ascontiguousarray(img, np.float32)
+    h, w = img.shape
+    out = np.empty_like(img)
+    lib().orc_gaussian_blur_xy(_p(img), _p(out), w, h, kx, ky, C.c_double(sigma_x), C.c_double(sigma_y))
+    return out
+
+
+def synth_geometry(w, h, tilt, phi, zoom):
+    """(ow, oh, H[3x3], identity?) of GenerateSynthImageCorr (synth-detection.cpp:356-431)."""
+    ow, oh = C.c_int(), C.c_int()
+    H = np.zeros(9, np.float64)
+    ident = lib().orc_synth_geometry(w, h, C.c_double(tilt), C.c_double(phi), C.c_double(zoom), C.byref(ow), C.byref(oh), _p(H))
+    return ow.value, oh.value, H.reshape(3, 3), bool(ident)
+
+
+def synth_view(gray, tilt, phi, zoom, init_sigma, do_blur=1):
+    gray = np.ascontiguousarray(gray, np.float32)
+    h, w = gray.shape
+    ow, oh, H, _ = synth_geometry(w, h, tilt, phi, zoom)
+    out = np.empty((oh, ow), np.float32)
+    lib().orc_synth_view(_p(gray), w, h, C.c_double(tilt), C.c_double(phi), C.c_double(zoom), C.c_double(init_sigma),
+                         int(do_blur), _p(out))
+    return out, H
+
+
 def gaussian_kernel(sigma):
     k = np.zeros(4096, np.float32)
     n = lib().orc_gaussian_kernel(C.c_float(sigma), _p(k))

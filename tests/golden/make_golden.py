@@ -8,6 +8,7 @@
                     through the daemons' own nn.Sequential definitions (unfolded BatchNorm, torch CPU fp32)
   graf_counts.json  keypoint / region / descriptor counts of the oracle pipeline on the reference's
                     graf1/graf6 images, next to the README transcript values (README.md:47-61)
+  synth_pins.npz    cv2 outputs of GenerateSynthImageCorr's warpAffine -> GaussianBlur(kx,ky) -> warpAffine chain
   oxaff_golden.npz  seeded affine regions + their OxAff ellipse entries (saveKP_KM_format with cv2.SVDecomp)
   ransac_F_ref.npz  a seeded two-view scene + the result of the reference's own exp_ransacFcustom
   ransac_ref.npz    a seeded correspondence set + the result of the reference's own exp_ransacHcustom
@@ -155,6 +156,68 @@ def ransac_F_ref():
           (r["I"], r["samples"], r["lo_count"], int((r["inl"].astype(bool) & mask).sum())))
 
 
+SYNTH_CASES = [(2, 0.0, 1, 0.2), (2, 0.7, 1, 0.2), (4, 2.1, 1, 0.2), (8, 3.0, 1, 0.2), (6, 1.2, 1, 0.8), (1, 0.0, 0.25, 0.8),
+               (3, 0.5, 0.25, 0.8), (-2, 0.9, 1, 0.2), (1, 0.0, 0.125, 0.8), (1, 0, 1, 0.2), (2, 1.5707963267948966, 1, 0.5)]
+
+
+def cv_synth(gray, tilt, phi, zoom, InitSigma, doBlur=1):
+    """Literal transcription of GenerateSynthImageCorr (synth-detection.cpp:324-518) on top of cv2."""
+    import cv2
+    vertical = False
+    if tilt < 0:
+        tilt, vertical = -tilt, True
+    zoomed = 1 if abs(np.float32(zoom - 1.0)) >= 0.05 else 0
+    h, w = gray.shape
+    wS1, hS1 = int(w * zoom), int(h * zoom)
+    if abs(tilt - 1.) <= 0.1 and abs(int(phi)) <= 0.2 and abs(zoom - 1.) <= 0.1:
+        return gray.copy()
+    kV = kH = 1.
+    if zoomed:
+        kV, kH = w / wS1, h / hS1
+    c, s = np.cos(phi), np.sin(phi)
+    tx, ty = (kH, tilt * kV) if vertical else (tilt * kH, kV)
+    if 0 <= phi < np.pi / 2:
+        w_new, h_new = np.floor((0.5 + c * w + s * h) / tx), np.floor((0.5 + s * w + c * h) / ty)
+        wr, hr = int(np.floor(0.5 + c * w + s * h)), int(np.floor(0.5 + s * w + c * h))
+        R = [c, s, 0, -s, c, np.floor(0.5 + s * w)]
+    else:
+        w_new, h_new = np.floor((0.5 - c * w + s * h) / tx), np.floor((0.5 + s * w - c * h) / ty)
+        wr, hr = int(np.floor(0.5 - c * w + s * h)), int(np.floor(0.5 + s * w - c * h))
+        R = [c, s, -np.floor(c * w), -s, c, np.floor(0.5 + (s * w - c * h))]
+    sa2 = InitSigma / (4.0 * zoom) if zoomed else InitSigma / 2.0
+    sa = InitSigma * tilt / (2.0 * zoom)
+    sx, sy = (sa2, sa) if vertical else (sa, sa2)
+    t = cv2.warpAffine(gray, np.array(R).reshape(2, 3), (wr, hr), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT,
+                       borderValue=(128, 128, 128))
+    if doBlur:
+        kx = int(np.floor(6 * sx + 1))
+        kx += (kx % 2 == 0)
+        kx = max(kx, 3)
+        ky = int(np.floor(6 * sy + 1))
+        ky += (ky % 2 == 0)
+        ky = max(ky, 3)
+        t = cv2.GaussianBlur(t, (kx, ky), sigmaX=sx, sigmaY=sy)
+    Wm = np.array([1 / kH, 0, 0, 0, 1 / (tilt * kV), 0]) if vertical else np.array([1 / (tilt * kH), 0, 0, 0, 1 / kV, 0])
+    return cv2.warpAffine(t, Wm.reshape(2, 3), (int(w_new), int(h_new)), flags=cv2.INTER_LINEAR,
+                          borderMode=cv2.BORDER_CONSTANT, borderValue=(128, 128, 128))
+
+
+def synth_pins():
+    """cv2 outputs of the view-synthesis chain on a small seeded image (the OpenCV calls whose arithmetic lives
+    outside the reference tree: warpAffine synth-detection.cpp:473,:514 and the anisotropic GaussianBlur :499)."""
+    import cv2
+    rng = np.random.RandomState(5)
+    img = cv2.GaussianBlur((rng.rand(45, 62) * 255).astype(np.float32), (5, 5), 1.0)
+    out = {"img": img, "cases": np.array(SYNTH_CASES, np.float64)}
+    for i, (tilt, phi, zoom, isg) in enumerate(SYNTH_CASES):
+        out["view%d" % i] = cv_synth(img, tilt, phi, zoom, isg)
+    # the two primitives on their own (ragged sizes, 3-tap kernels, odd widths)
+    out["blur_a"] = cv2.GaussianBlur(img[:, :61], (3, 5), sigmaX=0.4, sigmaY=0.8)
+    out["blur_b"] = cv2.GaussianBlur(img[:37, :50], (7, 3), sigmaX=1.2, sigmaY=0.1)
+    np.savez_compressed(os.path.join(HERE, "synth_pins.npz"), **out)
+    print("synth_pins.npz", len(SYNTH_CASES), "views")
+
+
 def oxaff_golden():
     """Seeded regions + the OxAff line values computed the way saveKP_KM_format does (imagerepresentation.cpp:113-126)
     with cv2.SVDecomp standing in for cv::SVD (same library, float)."""
@@ -188,7 +251,7 @@ def oxaff_golden():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["cv2", "cnn", "graf", "ransac", "ransacF", "oxaff"]
+    which = sys.argv[1:] or ["cv2", "cnn", "graf", "ransac", "ransacF", "oxaff", "synth"]
     if "cv2" in which:
         cv2_pins()
     if "cnn" in which:
@@ -197,6 +260,8 @@ if __name__ == "__main__":
         graf_counts()
     if "ransac" in which:
         ransac_ref()
+    if "synth" in which:
+        synth_pins()
     if "oxaff" in which:
         oxaff_golden()
     if "ransacF" in which:

@@ -524,3 +524,30 @@ def test_extract_features_and_batch_oxaff(mg, oracle, tmp_path):
         row = lines[2 + len(f) // 2].split()
         k = len(f) // 2
         assert abs(float(row[0]) - f["x"][k]) < 1e-3 * max(1, abs(f["x"][k])) and [int(v) for v in row[5:]] == [int(v) for v in f["desc"][k]]
+
+
+# ------------------------------------------------------------------------------------------ view synthesis (row a2)
+@pytest.mark.parametrize("tilt,phi,zoom,isg", [(2, 0.0, 1, 0.2), (4, 1.0471975511965976, 1, 0.2), (8, 2.9, 1, 0.2), (-3, 0.4, 1, 0.2),
+                                               (1, 0.0, 0.25, 0.8), (6, 2.0, 0.25, 0.8), (1, 0.0, 1, 0.2)])
+def test_synth_view_bit_exact(mg, oracle, synth_pair, tilt, phi, zoom, isg):
+    """modsgpu_synth_view == the oracle (which is pinned bit-exactly to cv2) on the full 1024x768 image: same size,
+    same H, bit-identical pixels; the detector then runs on the synthesised view."""
+    a, _, _ = synth_pair
+    g = _gray(oracle, a)
+    ref, Href = oracle.synth_view(g, tilt, phi, zoom, isg)
+    img = mg.image_from_gray32f(g)
+    view, H = mg.synth_view(img, tilt, phi, zoom, isg)
+    got = mg.image_download(view)
+    assert got.shape == ref.shape and np.array_equal(H, Href)
+    assert np.array_equal(got, ref), (np.abs(got - ref).max(), (got != ref).mean())
+    kp = mg.detect(view)
+    kref = oracle.detect_hessian(ref)
+    assert len(kp) == len(kref) and np.array_equal(kp["x"], kref["x"]) and np.array_equal(kp["response"], kref["response"])
+
+
+def test_synth_view_small_fixture(mg):
+    z = np.load(os.path.join(GOLD, "synth_pins.npz"))
+    img = mg.image_from_gray32f(z["img"])
+    for i, (tilt, phi, zoom, isg) in enumerate(z["cases"]):
+        view, _ = mg.synth_view(img, tilt, phi, zoom, isg)
+        assert np.array_equal(mg.image_download(view), z["view%d" % i]), i

@@ -199,11 +199,23 @@ typedef struct {
   double x, y, s, a11, a12, a21, a22;   /* reproj_kp (== det_kp for the identity view) */
   double response;
   int    octave, type;
+  int    view, _pad;                    /* index of the synthesised view the region was detected in */
   float  desc[128];
 } modsgpu_feature;
 /* *out is malloc()ed by the library; release with modsgpu_free() */
 int  modsgpu_extract_features(modsgpu_ctx* ctx, modsgpu_image* img, modsgpu_feature** out, int* n);
 int  modsgpu_write_oxaff(const char* path, const modsgpu_feature* f, int n);
+
+/* ---- one image over a list of synthesised views (ImageRepresentation::SynthDetectDescribeKeypoints,
+ *      imagerepresentation.cpp:686-1104, HessianAffine + AffNet + OriNet + HardNet++): each view is generated on the
+ *      device, detected and described in view coordinates, reprojected by H^-1 (ReprojectByH synth-detection.cpp:578-587)
+ *      and filtered against the ORIGINAL image frame.  modsgpu_view_schedule = SetVSPars (synth-detection.cpp:191-322)
+ *      for one iteration with an empty history: returns the number of views (<= cap written). */
+typedef struct { double tilt, phi, zoom, InitSigma; int doBlur, _pad; } modsgpu_view;   /* ViewSynthParameters structures.hpp:196-209 */
+int  modsgpu_view_schedule(const double* scale_set, int n_scales, const double* tilt_set, int n_tilts, double phi_base,
+                           double InitSigma, int doBlur, modsgpu_view* out, int cap);
+int  modsgpu_extract_features_views(modsgpu_ctx* ctx, modsgpu_image* img, const modsgpu_view* views, int n_views,
+                                    modsgpu_feature** out, int* n);
 
 /* test-only: one 128x32x64 GEMM through the tcgen05 descriptor conventions of the dense kernels */
 int  modsgpu_debug_umma_probe(modsgpu_ctx* ctx, const float* A, const float* B, float* D, int swap_lbo_sbo);

@@ -20,7 +20,9 @@ REGION_DTYPE = np.dtype([("x", "f8"), ("y", "f8"), ("s", "f8"), ("a11", "f8"), (
 MATCH_DTYPE = np.dtype([("qi", "i4"), ("ti", "i4"), ("tj_bad", "i4"), ("d1", "f4"), ("d2", "f4"), ("_pad", "i4"), ("ratio", "f8")])
 
 FEATURE_DTYPE = np.dtype([("x", "f8"), ("y", "f8"), ("s", "f8"), ("a11", "f8"), ("a12", "f8"), ("a21", "f8"), ("a22", "f8"),
-                          ("response", "f8"), ("octave", "i4"), ("type", "i4"), ("desc", "f4", (128,))])
+                          ("response", "f8"), ("octave", "i4"), ("type", "i4"), ("view", "i4"), ("_pad", "i4"),
+                          ("desc", "f4", (128,))])
+VIEW_DTYPE = np.dtype([("tilt", "f8"), ("phi", "f8"), ("zoom", "f8"), ("InitSigma", "f8"), ("doBlur", "i4"), ("_pad", "i4")])
 
 AFFNET, ORINET, HARDNET = 0, 1, 2
 NET_FILES = {AFFNET: "affnet.npz", ORINET: "orinet.npz", HARDNET: "hardnet.npz"}
@@ -272,6 +274,19 @@ class ModsGpu:
         finally:
             self.lib.modsgpu_free(out)
 
+    def extract_features_views(self, img, views):
+        views = np.ascontiguousarray(views, VIEW_DTYPE)
+        out = C.c_void_p()
+        n = C.c_int()
+        self._check(self.lib.modsgpu_extract_features_views(self.ctx, img.handle, _p(views), len(views), C.byref(out), C.byref(n)))
+        try:
+            if n.value == 0:
+                return np.zeros(0, FEATURE_DTYPE)
+            buf = (C.c_char * (n.value * FEATURE_DTYPE.itemsize)).from_address(out.value)
+            return np.frombuffer(buf, FEATURE_DTYPE).copy()
+        finally:
+            self.lib.modsgpu_free(out)
+
     def ransac_F(self, u, th=16.0, conf=0.99, max_samples=1000000, sym_check=1, seed=12345):
         """modsgpu_ransac_F: LO-RANSAC for a fundamental matrix (exp_ransacFcustom, matching.cpp:722)."""
         u = np.ascontiguousarray(u, np.float64)
@@ -283,6 +298,18 @@ class ModsGpu:
         self._check(self.lib.modsgpu_ransac_F(self.ctx, _p(u), T, C.byref(p), _p(F), _p(inl), C.byref(res)))
         return dict(F=F, inl=inl[:T], I=res.n_inliers, J=res.J, samples=res.samples, lo_count=res.lo_runs,
                     sym_rejects=res.oc_rejects)
+
+
+def view_schedule(scale_set, tilt_set, phi_base, init_sigma, do_blur=1, cap=4096):
+    """modsgpu_view_schedule = SetVSPars (synth-detection.cpp:191-322); needs no GPU."""
+    sc = np.ascontiguousarray(scale_set, np.float64)
+    ti = np.ascontiguousarray(tilt_set, np.float64)
+    out = np.zeros(cap, VIEW_DTYPE)
+    n = load_library().modsgpu_view_schedule(_p(sc), len(sc), _p(ti), len(ti), C.c_double(phi_base), C.c_double(init_sigma),
+                                             int(do_blur), _p(out), cap)
+    if n < 0:
+        raise ModsGpuError("modsgpu_view_schedule failed (%d)" % n)
+    return out[:min(n, cap)].copy()
 
 
 def write_oxaff(path, feats):

@@ -66,17 +66,126 @@ static void to_regions(const AffineRegionVector& v, std::vector<modsgpu_region>&
   }
 }
 
+static bool invert3h(const double* A, double* R) {
+  const double c0 = A[4] * A[8] - A[5] * A[7], c1 = A[5] * A[6] - A[3] * A[8], c2 = A[3] * A[7] - A[4] * A[6];
+  const double det = A[0] * c0 + A[1] * c1 + A[2] * c2;
+  if (det == 0 || !std::isfinite(det)) { for (int i = 0; i < 9; i++) R[i] = 0; return false; }
+  const double id = 1.0 / det;
+  R[0] = c0 * id; R[1] = (A[2] * A[7] - A[1] * A[8]) * id; R[2] = (A[1] * A[5] - A[2] * A[4]) * id;
+  R[3] = c1 * id; R[4] = (A[0] * A[8] - A[2] * A[6]) * id; R[5] = (A[2] * A[3] - A[0] * A[5]) * id;
+  R[6] = c2 * id; R[7] = (A[1] * A[6] - A[0] * A[7]) * id; R[8] = (A[0] * A[4] - A[1] * A[3]) * id;
+  return true;
+}
+// synth-detection.cpp:143-149
+static bool HIsEye(const double* H) {
+  const double eps1 = 0.01;
+  return (std::fabs(H[0] - 1.0) + std::fabs(H[1]) + std::fabs(H[2]) + std::fabs(H[3]) + std::fabs(H[4] - 1.0) + std::fabs(H[5]) +
+          std::fabs(H[6]) + std::fabs(H[7]) + std::fabs(H[8] - 1.0) < eps1);
+}
+// synth-detection.cpp:578-587
+static void ReprojectByH(const AffineKeypoint& in_kp, AffineKeypoint& out_kp, const double* H) {
+  out_kp.x = (H[0] * in_kp.x + H[1] * in_kp.y + H[2]);
+  out_kp.y = (H[3] * in_kp.x + H[4] * in_kp.y + H[5]);
+  out_kp.a11 = (H[0] * in_kp.a11 + H[1] * in_kp.a21);
+  out_kp.a12 = (H[0] * in_kp.a12 + H[1] * in_kp.a22);
+  out_kp.a21 = (H[3] * in_kp.a11 + H[4] * in_kp.a21);
+  out_kp.a22 = (H[3] * in_kp.a12 + H[4] * in_kp.a22);
+}
+
+// synth-detection.cpp:191-322
+int SetVSPars(const std::vector<double>& scale_set, const std::vector<double>& tilt_set, double phi_base,
+              std::vector<ViewSynthParameters>& par, std::vector<ViewSynthParameters>& prev_par, double InitSigma, int doBlur) {
+  const double eps1 = 0.01;
+  par.clear();
+  std::vector<ViewSynthParameters> prev_par_tmp(prev_par), pars_tmp;
+  auto mk = [&](double phi, double tilt, double zoom, int blur) {
+    ViewSynthParameters t;
+    t.phi = phi; t.tilt = tilt; t.zoom = zoom; t.InitSigma = InitSigma; t.doBlur = blur;
+    return t;
+  };
+  if (scale_set.empty() || tilt_set.empty()) pars_tmp.push_back(mk(0, 0, 0, 0));
+  for (size_t sc = 0; sc < scale_set.size(); sc++)
+    for (size_t t = 0; t < tilt_set.size(); t++) {
+      if (std::fabs(tilt_set[t] - 1) > eps1) {
+        int n_rot1 = (int)std::floor(180.0 * tilt_set[t] / phi_base);
+        double delta_phi = M_PI / n_rot1;
+        if (n_rot1 < 0) {   // no rotation mode if negative, add vertical tilt
+          n_rot1 = 1;
+          delta_phi = 0;
+          pars_tmp.push_back(mk(0, -tilt_set[t], scale_set[sc], doBlur));
+        }
+        for (int r = 0; r < n_rot1; r++) pars_tmp.push_back(mk(delta_phi * r, tilt_set[t], scale_set[sc], doBlur));
+      } else {
+        pars_tmp.push_back(mk(0, tilt_set[t], scale_set[sc], doBlur));
+      }
+    }
+  for (const ViewSynthParameters& p : pars_tmp) {
+    bool unique = true;
+    for (const ViewSynthParameters& q : prev_par_tmp)
+      if ((std::fabs(p.zoom - q.zoom) <= eps1) && (std::fabs(p.tilt - q.tilt) <= eps1) && (std::fabs(p.phi - q.phi) <= eps1)) { unique = false; break; }
+    if (unique) par.push_back(p);
+  }
+  for (const ViewSynthParameters& p : par) prev_par_tmp.push_back(p);
+  prev_par = prev_par_tmp;
+  return (int)par.size();
+}
+
 // imagerepresentation.cpp:686-1104 for one detector (HessianAffine) and the identity view (H = I,
 // synth-detection.cpp:366-377), deep configuration (config_aff_ori_desc_zeromq.ini + iters_HessianZMQ.ini).
 int ImageRepresentation::SynthDetectDescribeKeypoints(const DetectPars& par) {
   int w, h;
   modsgpu_image_size(img_, &w, &h);
   regions_.clear();
+  n_views = 1;
+  const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  return DescribeView(img_, I3, w, h, par, regions_);
+}
+
+int ImageRepresentation::SynthDetectDescribeKeypoints(const std::vector<ViewSynthParameters>& views, const DetectPars& par) {
+  int w, h;
+  modsgpu_image_size(img_, &w, &h);
+  regions_.clear();
+  n_views = 0;
+  n_keypoints = n_affine = 0;
+  for (size_t v = 0; v < views.size(); v++) {
+    double t0 = now_ms();
+    modsgpu_image* view = nullptr;
+    double H[9];
+    int rc = modsgpu_synth_view(ctx_, img_, views[v].tilt, views[v].phi, views[v].zoom, views[v].InitSigma, views[v].doBlur, &view, H);
+    if (rc) return rc;
+    TimeSpent.SynthTime += now_ms() - t0;
+    AffineRegionVector one;
+    const int kp0 = n_keypoints, af0 = n_affine;
+    rc = DescribeView(view, H, w, h, par, one);
+    modsgpu_image_free(ctx_, view);
+    if (rc < 0) return rc;
+    n_keypoints += kp0; n_affine += af0;
+    for (AffineRegion& r : one) {
+      r.img_reproj_id = (int)v;
+      r.id = (int)regions_.size();
+      regions_.push_back(r);
+    }
+    n_views++;
+  }
+  return (int)regions_.size();
+}
+
+// one view: detect -> AffNet -> reproject -> OriNet -> reproject + frame test -> HardNet++.  `view` is the
+// synthesised image (or the original), H maps original -> view; regions keep det_kp in view coordinates and get
+// reproj_kp in the original image.
+int ImageRepresentation::DescribeView(modsgpu_image* view, const double* H, int orig_w, int orig_h, const DetectPars& par,
+                                      AffineRegionVector& result) {
+  int w, h;
+  modsgpu_image_size(view, &w, &h);
+  result.clear();
+  double Hinv[9];
+  invert3h(H, Hinv);
+  const bool eye = HIsEye(H);
   double t0 = now_ms();
   // ---- DetectAffineRegions (synth-detection.hpp:79-112) over DetectAffineKeypoints
   modsgpu_keypoint* kps = nullptr;
   int n = 0;
-  int rc = modsgpu_detect(ctx_, img_, &par.pyr, &kps, &n);
+  int rc = modsgpu_detect(ctx_, view, &par.pyr, &kps, &n);
   if (rc) return rc;
   n_keypoints = n;
   AffineRegionVector temp_kp1(n);
@@ -91,10 +200,10 @@ int ImageRepresentation::SynthDetectDescribeKeypoints(const DetectPars& par) {
   modsgpu_free(kps);
   std::vector<modsgpu_region> regs;
   std::vector<float> out;
-  // ---- AffNet (imagerepresentation.cpp:797-845)
+  // ---- AffNet (imagerepresentation.cpp:797-845); the border test is against the VIEW
   to_regions(temp_kp1, regs);
   out.resize((size_t)n * 3 + 1);
-  rc = modsgpu_describe(ctx_, MODSGPU_AFFNET, img_, regs.data(), n, par.mrSize, par.patchSize, out.data());
+  rc = modsgpu_describe(ctx_, MODSGPU_AFFNET, view, regs.data(), n, par.mrSize, par.patchSize, out.data());
   if (rc) return rc;
   AffineRegionVector temp_kp_aff;
   temp_kp_aff.reserve(n);
@@ -117,18 +226,19 @@ int ImageRepresentation::SynthDetectDescribeKeypoints(const DetectPars& par) {
   n_affine = (int)temp_kp_aff.size();
   TimeSpent.DetectTime += now_ms() - t0;
   t0 = now_ms();
-  // ---- ReprojectRegionsAndRemoveTouchBoundary(dontRemove = true), H = I (synth-detection.cpp:151-190)
+  // ---- ReprojectRegionsAndRemoveTouchBoundary(dontRemove = true) (synth-detection.cpp:151-190)
   AffineRegionVector kept;
   kept.reserve(temp_kp_aff.size());
   for (auto& r : temp_kp_aff) {
     r.reproj_kp = r.det_kp;
-    if ((r.reproj_kp.x < w) && (r.reproj_kp.y < h) && (r.reproj_kp.x > 0) && (r.reproj_kp.y > 0)) kept.push_back(r);
+    if (!eye) ReprojectByH(r.det_kp, r.reproj_kp, Hinv);
+    if ((r.reproj_kp.x < orig_w) && (r.reproj_kp.y < orig_h) && (r.reproj_kp.x > 0) && (r.reproj_kp.y > 0)) kept.push_back(r);
   }
-  // ---- OriNet (imagerepresentation.cpp:876-899)
+  // ---- OriNet (imagerepresentation.cpp:876-899), patches from the view
   const int n2 = (int)kept.size();
   to_regions(kept, regs);
   out.resize((size_t)n2 * 2 + 1);
-  rc = modsgpu_describe(ctx_, MODSGPU_ORINET, img_, regs.data(), n2, par.mrSize, par.patchSize, out.data());
+  rc = modsgpu_describe(ctx_, MODSGPU_ORINET, view, regs.data(), n2, par.mrSize, par.patchSize, out.data());
   if (rc) return rc;
   AffineRegionVector oriented;
   oriented.reserve(n2);
@@ -145,30 +255,31 @@ int ImageRepresentation::SynthDetectDescribeKeypoints(const DetectPars& par) {
   }
   TimeSpent.OrientTime += now_ms() - t0;
   t0 = now_ms();
-  // ---- ReprojectRegions (synth-detection.cpp:631-706): centre inside + k_sigma*s frame inside
+  // ---- ReprojectRegions (synth-detection.cpp:631-706): centre inside + k_sigma*s frame inside the ORIGINAL image
   const double k_sigma = 2 * 3.0 * std::sqrt(3.0);   // synth-detection.cpp:21
   AffineRegionVector final_regs;
   final_regs.reserve(oriented.size());
   for (auto& r : oriented) {
     r.reproj_kp = r.det_kp;
+    if (!eye) ReprojectByH(r.det_kp, r.reproj_kp, Hinv);
     const AffineKeypoint& p = r.reproj_kp;
-    if ((p.x < w) && (p.y < h) && (p.x > 0) && (p.y > 0)) {
-      if (!interpolateCheckBorders(w, h, (float)p.x, (float)p.y, (float)p.a11, (float)p.a12, (float)p.a21, (float)p.a22,
+    if ((p.x < orig_w) && (p.y < orig_h) && (p.x > 0) && (p.y > 0)) {
+      if (!interpolateCheckBorders(orig_w, orig_h, (float)p.x, (float)p.y, (float)p.a11, (float)p.a12, (float)p.a21, (float)p.a22,
                                    (int)(k_sigma * p.s), (int)(k_sigma * p.s)))
         final_regs.push_back(r);
     }
   }
-  // ---- HardNet++ (imagerepresentation.cpp:992-1006)
+  // ---- HardNet++ (imagerepresentation.cpp:992-1006), patches from the view
   const int n3 = (int)final_regs.size();
   to_regions(final_regs, regs);
   out.resize((size_t)n3 * 128 + 1);
-  rc = modsgpu_describe(ctx_, MODSGPU_HARDNET, img_, regs.data(), n3, par.mrSize, par.patchSize, out.data());
+  rc = modsgpu_describe(ctx_, MODSGPU_HARDNET, view, regs.data(), n3, par.mrSize, par.patchSize, out.data());
   if (rc) return rc;
   for (int i = 0; i < n3; i++) {
     final_regs[i].desc.assign(out.begin() + (size_t)i * 128, out.begin() + (size_t)(i + 1) * 128);
     final_regs[i].id = i;
   }
-  regions_.swap(final_regs);
+  result.swap(final_regs);
   TimeSpent.DescTime += now_ms() - t0;
   return n3;
 }
@@ -425,6 +536,39 @@ extern "C" int modsgpu_pair_pipeline(modsgpu_ctx* ctx, const uint8_t* bgr1, cons
 // ------------------------------------------------------------------------------------------------------
 // C entries: one image -> described regions (extract_features_batch.cpp:128-139) and the OxAff writer
 // ------------------------------------------------------------------------------------------------------
+static int export_features(const modsb200::AffineRegionVector& v, int nd, modsgpu_feature** out, int* n);
+
+extern "C" int modsgpu_view_schedule(const double* scale_set, int n_scales, const double* tilt_set, int n_tilts, double phi_base,
+                                     double InitSigma, int doBlur, modsgpu_view* out, int cap) {
+  using namespace modsb200;
+  if (n_scales < 0 || n_tilts < 0 || (n_scales > 0 && !scale_set) || (n_tilts > 0 && !tilt_set) || (cap > 0 && !out)) return MODSGPU_EINVAL;
+  std::vector<double> sc(scale_set, scale_set + n_scales), ti(tilt_set, tilt_set + n_tilts);
+  std::vector<ViewSynthParameters> par, prev;
+  const int nv = SetVSPars(sc, ti, phi_base, par, prev, InitSigma, doBlur);
+  for (int i = 0; i < nv && i < cap; i++) {
+    out[i].tilt = par[i].tilt; out[i].phi = par[i].phi; out[i].zoom = par[i].zoom; out[i].InitSigma = par[i].InitSigma;
+    out[i].doBlur = par[i].doBlur; out[i]._pad = 0;
+  }
+  return nv;
+}
+
+extern "C" int modsgpu_extract_features_views(modsgpu_ctx* ctx, modsgpu_image* img, const modsgpu_view* views, int n_views,
+                                              modsgpu_feature** out, int* n) {
+  using namespace modsb200;
+  if (!ctx || !img || !out || !n || n_views < 0 || (n_views > 0 && !views)) return MODSGPU_EINVAL;
+  *out = nullptr; *n = 0;
+  std::vector<ViewSynthParameters> vs((size_t)n_views);
+  for (int i = 0; i < n_views; i++) {
+    vs[i].tilt = views[i].tilt; vs[i].phi = views[i].phi; vs[i].zoom = views[i].zoom; vs[i].InitSigma = views[i].InitSigma;
+    vs[i].doBlur = views[i].doBlur;
+  }
+  DetectPars dp;
+  ImageRepresentation rep(ctx, img, false);
+  const int nd = rep.SynthDetectDescribeKeypoints(vs, dp);
+  if (nd < 0) return nd;
+  return export_features(rep.GetAffineRegionVector(), nd, out, n);
+}
+
 extern "C" int modsgpu_extract_features(modsgpu_ctx* ctx, modsgpu_image* img, modsgpu_feature** out, int* n) {
   using namespace modsb200;
   if (!ctx || !img || !out || !n) return MODSGPU_EINVAL;
@@ -433,13 +577,18 @@ extern "C" int modsgpu_extract_features(modsgpu_ctx* ctx, modsgpu_image* img, mo
   ImageRepresentation rep(ctx, img, false);
   const int nd = rep.SynthDetectDescribeKeypoints(dp);
   if (nd < 0) return nd;
-  const AffineRegionVector& v = rep.GetAffineRegionVector();
+  return export_features(rep.GetAffineRegionVector(), nd, out, n);
+}
+
+static int export_features(const modsb200::AffineRegionVector& v, int nd, modsgpu_feature** out, int* n) {
+  using namespace modsb200;
   modsgpu_feature* f = (modsgpu_feature*)malloc(sizeof(modsgpu_feature) * (size_t)(nd > 0 ? nd : 1));
   if (!f) return MODSGPU_EINVAL;
   for (int i = 0; i < nd; i++) {
     const AffineKeypoint& k = v[i].reproj_kp;
     f[i].x = k.x; f[i].y = k.y; f[i].s = k.s; f[i].a11 = k.a11; f[i].a12 = k.a12; f[i].a21 = k.a21; f[i].a22 = k.a22;
     f[i].response = k.response; f[i].octave = k.octave_number; f[i].type = k.sub_type;
+    f[i].view = v[i].img_reproj_id; f[i]._pad = 0;
     for (int d = 0; d < 128; d++) f[i].desc[d] = d < (int)v[i].desc.size() ? v[i].desc[d] : 0.f;
   }
   *out = f; *n = nd;

@@ -58,8 +58,18 @@ struct DetectPars {
   DetectPars() { modsgpu_default_pyr_params(&pyr); }
 };
 
+struct ViewSynthParameters {       // structures.hpp:196-209 (the fields the hot path reads)
+  double zoom = 1, tilt = 1, phi = 0, InitSigma = 0.5;
+  int doBlur = 1;
+};
+// synth-detection.cpp:191-322 SetVSPars: the view list of one iteration (ScaleSet x TiltSet x rotations with
+// n_rot = floor(180 * tilt / Phi), a negative Phi meaning one vertical-tilt view); views already in prev_par are
+// dropped and the new ones appended to it.
+int SetVSPars(const std::vector<double>& scale_set, const std::vector<double>& tilt_set, double phi_base,
+              std::vector<ViewSynthParameters>& par, std::vector<ViewSynthParameters>& prev_par, double InitSigma, int doBlur);
+
 struct TimeLog {                   // structures.hpp:33-56 (device + host ms per stage)
-  double DetectTime = 0, OrientTime = 0, DescTime = 0, MatchingTime = 0, RANSACTime = 0;
+  double SynthTime = 0, DetectTime = 0, OrientTime = 0, DescTime = 0, MatchingTime = 0, RANSACTime = 0;
 };
 
 class ImageRepresentation {
@@ -68,6 +78,12 @@ class ImageRepresentation {
   ~ImageRepresentation();
   // returns the number of described regions, < 0 on error (message via modsgpu_last_error)
   int SynthDetectDescribeKeypoints(const DetectPars& par);
+  // the same over a list of synthesised views (imagerepresentation.cpp:704-1102): every view is generated on the
+  // device (modsgpu_synth_view), detected / described in view coordinates and reprojected to the original image
+  // (ReprojectByH synth-detection.cpp:578-587).  Regions of a view are appended ONCE (the reference's AddRegions
+  // loop sits inside the view loop and appends view k up to n-k times, SURVEY Q1 -- documented deviation).
+  int SynthDetectDescribeKeypoints(const std::vector<ViewSynthParameters>& views, const DetectPars& par);
+  int n_views = 0;
   const AffineRegionVector& GetAffineRegionVector() const { return regions_; }
   int n_keypoints = 0, n_affine = 0;
   TimeLog TimeSpent;
@@ -77,6 +93,7 @@ class ImageRepresentation {
   modsgpu_image* img_;
   bool owns_;
   AffineRegionVector regions_;
+  int DescribeView(modsgpu_image* view, const double* H, int orig_w, int orig_h, const DetectPars& par, AffineRegionVector& out);
 };
 
 // helpers.cpp:524-549 / :401-410 / :504-515

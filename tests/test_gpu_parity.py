@@ -551,3 +551,31 @@ def test_synth_view_small_fixture(mg):
     for i, (tilt, phi, zoom, isg) in enumerate(z["cases"]):
         view, _ = mg.synth_view(img, tilt, phi, zoom, isg)
         assert np.array_equal(mg.image_download(view), z["view%d" % i]), i
+
+
+def test_multi_view_extraction(mg, oracle):
+    """Config-5 building block: views from SetVSPars (tilt set {1, 2}, Phi = 360), each synthesised / detected /
+    described on the device and reprojected to the original frame (imagerepresentation.cpp:704-1102)."""
+    import mods_light_zmq_b200 as M
+    from mods_light_zmq_b200 import synth
+    u8 = synth.blob_image(seed=77, w=480, h=360, n_blobs=700)
+    bgr = synth.gray_to_bgr(u8)
+    img = mg.image_from_bgr8(bgr)
+    g = oracle.gray_from_bgr(bgr)
+    views = M.view_schedule([1.0], [1.0, 2.0], 360.0, 0.2)
+    assert len(views) == 2 and views["tilt"].tolist() == [1.0, 2.0] and views["phi"].tolist() == [0.0, 0.0]
+    f = mg.extract_features_views(img, views)
+    f0 = mg.extract_features(img)
+    v0, v1 = f[f["view"] == 0], f[f["view"] == 1]
+    assert len(v0) == len(f0) and np.array_equal(v0["desc"], f0["desc"]) and np.array_equal(v0["x"], f0["x"])
+    # view 1: regions come from the tilted view and are expressed in the original frame
+    ref_view, H = oracle.synth_view(g, 2.0, 0.0, 1.0, 0.2)
+    kv = oracle.detect_hessian(ref_view)
+    assert len(v1) > 0.3 * len(kv) and len(v1) <= len(kv)
+    assert np.all((v1["x"] > 0) & (v1["x"] < 480) & (v1["y"] > 0) & (v1["y"] < 360))
+    p = np.c_[v1["x"], v1["y"], np.ones(len(v1))] @ H.T       # back into the view: must hit detected keypoints
+    kxy = np.c_[kv["x"], kv["y"]].astype(np.float64)
+    d = np.abs(p[:, None, :2] - kxy[None, :, :]).max(axis=2).min(axis=1)
+    assert d.max() < 1e-3, d.max()
+    # a tilt-2 view halves the horizontal extent: reprojected frames are stretched back by H^-1
+    assert np.allclose(np.abs(v1["a11"] * v1["a22"] - v1["a12"] * v1["a21"]), 2.0, rtol=1e-6)

@@ -142,6 +142,35 @@ def test_oracle_view_synthesis_matches_cv2_bit_exact(oracle):
     assert np.array_equal(oracle.gaussian_blur_xy(img[:37, :50], 7, 3, 1.2, 0.1), z["blur_b"])
 
 
+def test_view_schedule_matches_SetVSPars():
+    """modsgpu_view_schedule vs a transcription of SetVSPars (synth-detection.cpp:191-322) on the schedules of
+    build/iters_MODS_ZMQ.ini (HessianAffine steps: TiltSet=1,2,4,6,8; Phi=360 / 120) and a vertical-tilt case."""
+    import mods_light_zmq_b200 as M
+
+    def ref(scales, tilts, phi_base):
+        out = []
+        for sc in scales:
+            for t in tilts:
+                if abs(t - 1) > 0.01:
+                    n_rot = int(np.floor(180.0 * t / phi_base))
+                    dphi = np.pi / n_rot
+                    if n_rot < 0:
+                        n_rot, dphi = 1, 0.0
+                        out.append((-t, 0.0, sc))
+                    out += [(t, dphi * r, sc) for r in range(n_rot)]
+                else:
+                    out.append((t, 0.0, sc))
+        return out
+    for scales, tilts, phi in [([1.0], [1, 2, 4, 6, 8], 360.0), ([1.0], [1, 2, 4, 6, 8], 120.0), ([1, 0.25, 0.125], [1], 360.0),
+                               ([1, 0.25], [1, 3, 6], 360.0), ([1.0], [1, 2], -360.0)]:
+        v = M.view_schedule(scales, tilts, phi, 0.2)
+        r = ref(scales, tilts, phi)
+        assert len(v) == len(r)
+        for a, b in zip(v, r):
+            assert a["tilt"] == b[0] and abs(a["phi"] - b[1]) < 1e-15 and a["zoom"] == b[2] and a["doBlur"] == 1
+    assert len(M.view_schedule([1.0], [1, 2, 4, 6, 8], 360.0, 0.2)) == 11
+
+
 def test_oxaff_writer_matches_cv2_golden(tmp_path):
     """modsgpu_write_oxaff (SaveRegionsMichal text mode) against ellipse entries computed with cv2.SVDecomp the way
     saveKP_KM_format does (imagerepresentation.cpp:113-126); the file prints 6 significant digits."""

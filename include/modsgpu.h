@@ -205,6 +205,12 @@ typedef struct {
 /* *out is malloc()ed by the library; release with modsgpu_free() */
 int  modsgpu_extract_features(modsgpu_ctx* ctx, modsgpu_image* img, modsgpu_feature** out, int* n);
 int  modsgpu_write_oxaff(const char* path, const modsgpu_feature* f, int n);
+/* the two other region formats of extract_features_batch.cpp:147-155:
+ *   text (ImageRepresentation::SaveRegions imagerepresentation.cpp:1219-1255 + saveAR :196-203):
+ *        "1\nHessianAffine 1\nZMQ N\n128\n" then `x y s a11 a12 a21 a22 128 d0 .. d127 ` per region
+ *   npz  (SaveRegionsNPZ :1257-1316 via cnpy): xy [N,2], scales [N,1], responses [N,1], A [N,4] float64, descs [N,128] uint8 */
+int  modsgpu_write_regions_text(const char* path, const modsgpu_feature* f, int n);
+int  modsgpu_write_regions_npz(const char* path, const modsgpu_feature* f, int n);
 
 /* ---- one image over a list of synthesised views (ImageRepresentation::SynthDetectDescribeKeypoints,
  *      imagerepresentation.cpp:686-1104, HessianAffine + AffNet + OriNet + HardNet++): each view is generated on the

@@ -320,6 +320,18 @@ def write_oxaff(path, feats):
         raise ModsGpuError("modsgpu_write_oxaff failed (%d)" % rc)
 
 
+def write_regions(path, feats, fmt=None):
+    """The three region formats of extract_features_batch.cpp:147-155: 'oxaff' (outputMikFormat), 'npz' (file name
+    ending in .npz) or the native 'text' format."""
+    if fmt is None:
+        fmt = "npz" if str(path).endswith(".npz") else "oxaff"
+    feats = np.ascontiguousarray(feats, FEATURE_DTYPE)
+    fn = {"oxaff": "modsgpu_write_oxaff", "text": "modsgpu_write_regions_text", "npz": "modsgpu_write_regions_npz"}[fmt]
+    rc = getattr(load_library(), fn)(str(path).encode(), _p(feats), len(feats))
+    if rc != 0:
+        raise ModsGpuError("%s failed (%d)" % (fn, rc))
+
+
 def _pair_dict(res, xy):
     return dict(keypoints=list(res.keypoints), regions=list(res.regions), descriptors=list(res.descriptors),
                 tentatives=res.tentatives, unique_tentatives=res.unique_tentatives, inliers=res.inliers,

@@ -77,7 +77,7 @@ def gpu_extractor(device):
     return run
 
 
-def extract_features_batch(img_fnames, out_fnames, extractor, rank=0, world=1, dist=None, log=None):
+def extract_features_batch(img_fnames, out_fnames, extractor, rank=0, world=1, dist=None, log=None, fmt=None):
     """Process this rank's share; returns (on rank 0) the list of region counts per image, -1 for skipped/failed."""
     import mods_light_zmq_b200 as M
     if len(img_fnames) != len(out_fnames):
@@ -97,7 +97,7 @@ def extract_features_batch(img_fnames, out_fnames, extractor, rank=0, world=1, d
             counts[i] = -1
             continue
         feats = extractor(bgr)
-        M.write_oxaff(out, feats)
+        M.write_regions(out, feats, fmt)    # .npz -> npz, else OxAff unless fmt says "text"
         counts[i] = len(feats)
         if log:
             log("%d %s %s %d" % (i, img_fnames[i], out, len(feats)))

@@ -2,6 +2,7 @@
 // Plain C++ (no CUDA): everything heavy is behind modsgpu_* calls; what remains here is the small
 // per-region double/float arithmetic the reference also does on the host between its stages.
 #include "mods_host.h"
+#include "../npz.h"
 #include <chrono>
 #include <cmath>
 #include <cstring>
@@ -605,4 +606,46 @@ extern "C" int modsgpu_write_oxaff(const char* path, const modsgpu_feature* f, i
     v[i].desc.assign(f[i].desc, f[i].desc + 128);
   }
   return SaveRegionsMichal(v, path) ? MODSGPU_EIO : 0;
+}
+
+
+// imagerepresentation.cpp:1219-1255 SaveRegions (text) with saveAR / saveKPBench (:109-111, :196-203)
+extern "C" int modsgpu_write_regions_text(const char* path, const modsgpu_feature* f, int n) {
+  if (!path || n < 0 || (n > 0 && !f)) return MODSGPU_EINVAL;
+  std::ofstream kpfile(path);
+  if (!kpfile.is_open()) return MODSGPU_EIO;
+  kpfile << 1 << std::endl;
+  kpfile << "HessianAffine" << " " << 1 << std::endl;
+  kpfile << "ZMQ" << " " << n << std::endl;
+  if (n > 0) kpfile << 128 << std::endl;
+  for (int i = 0; i < n; i++) {
+    kpfile << f[i].x << " " << f[i].y << " " << f[i].s << " " << f[i].a11 << " " << f[i].a12 << " " << f[i].a21 << " " << f[i].a22;
+    kpfile << " " << 128 << " ";
+    for (int d = 0; d < 128; d++) kpfile << f[i].desc[d] << " ";
+    kpfile << std::endl;
+  }
+  return kpfile.good() ? 0 : MODSGPU_EIO;
+}
+
+// imagerepresentation.cpp:1257-1316 SaveRegionsNPZ
+extern "C" int modsgpu_write_regions_npz(const char* path, const modsgpu_feature* f, int n) {
+  if (!path || n < 0 || (n > 0 && !f)) return MODSGPU_EINVAL;
+  const size_t N = (size_t)n;
+  std::vector<double> xy(2 * N), scales(N), responses(N), A(4 * N);
+  std::vector<unsigned char> descs(128 * N);
+  for (size_t i = 0; i < N; i++) {
+    xy[2 * i] = f[i].x; xy[2 * i + 1] = f[i].y;
+    scales[i] = f[i].s;
+    A[4 * i] = f[i].a11; A[4 * i + 1] = f[i].a12; A[4 * i + 2] = f[i].a21; A[4 * i + 3] = f[i].a22;
+    responses[i] = f[i].response;
+    for (int d = 0; d < 128; d++) descs[i * 128 + d] = (unsigned char)f[i].desc[d];
+  }
+  NpzWriter w(path);
+  if (!w.ok()) return MODSGPU_EIO;
+  w.add("xy", "<f8", {N, 2}, xy.data(), xy.size() * 8);
+  w.add("scales", "<f8", {N, 1}, scales.data(), scales.size() * 8);
+  w.add("responses", "<f8", {N, 1}, responses.data(), responses.size() * 8);
+  w.add("A", "<f8", {N, 4}, A.data(), A.size() * 8);
+  w.add("descs", "|u1", {N, 128}, descs.data(), descs.size());
+  return w.close() ? 0 : MODSGPU_EIO;
 }

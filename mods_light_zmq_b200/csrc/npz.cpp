@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <algorithm>
 
 namespace {
 uint32_t rd32(const unsigned char* p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
@@ -92,4 +93,66 @@ bool npz_load(const char* path, std::map<std::string, NpzArray>& out, std::strin
     out[name] = std::move(a);
   }
   return true;
+}
+
+
+// ---- writer ---------------------------------------------------------------------------------------------------
+#include <cstdio>
+namespace {
+void put16(std::vector<unsigned char>& b, unsigned v) { b.push_back(v & 255); b.push_back((v >> 8) & 255); }
+void put32(std::vector<unsigned char>& b, unsigned v) { for (int i = 0; i < 4; i++) b.push_back((v >> (8 * i)) & 255); }
+}  // namespace
+
+NpzWriter::NpzWriter(const std::string& path) { f_ = fopen(path.c_str(), "wb"); }
+NpzWriter::~NpzWriter() { if (f_) fclose((FILE*)f_); }
+
+bool NpzWriter::add(const std::string& name, const char* descr, const std::vector<size_t>& shape, const void* data, size_t bytes) {
+  if (!f_) return false;
+  FILE* f = (FILE*)f_;
+  // .npy v1.0 header, padded so that the data starts at a multiple of 64 bytes
+  std::string dict = std::string("{'descr': '") + descr + "', 'fortran_order': False, 'shape': (";
+  for (size_t i = 0; i < shape.size(); i++) dict += std::to_string(shape[i]) + (shape.size() == 1 || i + 1 < shape.size() ? "," : "");
+  dict += "), }";
+  size_t hl = dict.size() + 1;
+  while ((10 + hl) % 64) hl++;
+  dict.resize(hl - 1, ' ');
+  dict += '\n';
+  std::vector<unsigned char> npy = {0x93, 'N', 'U', 'M', 'P', 'Y', 1, 0};
+  put16(npy, (unsigned)dict.size());
+  npy.insert(npy.end(), dict.begin(), dict.end());
+  const std::string fname = name + ".npy";
+  const unsigned long long total = npy.size() + bytes;
+  if (total > 0xffffffffull) { good_ = false; return false; }   // zip64 not needed on this path
+  unsigned crc = crc32(0L, npy.data(), (uInt)npy.size());
+  const unsigned char* p = (const unsigned char*)data;
+  for (size_t off = 0; off < bytes; off += (size_t)1 << 30) crc = crc32(crc, p + off, (uInt)std::min<size_t>(bytes - off, (size_t)1 << 30));
+  Entry e{fname, crc, total, (unsigned long long)ftell(f)};
+  std::vector<unsigned char> lh;
+  put32(lh, 0x04034b50); put16(lh, 20); put16(lh, 0); put16(lh, 0); put16(lh, 0); put16(lh, 0);
+  put32(lh, crc); put32(lh, (unsigned)total); put32(lh, (unsigned)total); put16(lh, (unsigned)fname.size()); put16(lh, 0);
+  lh.insert(lh.end(), fname.begin(), fname.end());
+  good_ = good_ && fwrite(lh.data(), 1, lh.size(), f) == lh.size() && fwrite(npy.data(), 1, npy.size(), f) == npy.size() &&
+          (bytes == 0 || fwrite(data, 1, bytes, f) == bytes);
+  entries_.push_back(e);
+  return good_;
+}
+
+bool NpzWriter::close() {
+  if (!f_) return false;
+  FILE* f = (FILE*)f_;
+  const unsigned long long cd_off = (unsigned long long)ftell(f);
+  std::vector<unsigned char> cd;
+  for (const Entry& e : entries_) {
+    put32(cd, 0x02014b50); put16(cd, 20); put16(cd, 20); put16(cd, 0); put16(cd, 0); put16(cd, 0); put16(cd, 0);
+    put32(cd, e.crc); put32(cd, (unsigned)e.size); put32(cd, (unsigned)e.size); put16(cd, (unsigned)e.name.size());
+    put16(cd, 0); put16(cd, 0); put16(cd, 0); put16(cd, 0); put32(cd, 0); put32(cd, (unsigned)e.offset);
+    cd.insert(cd.end(), e.name.begin(), e.name.end());
+  }
+  const unsigned cd_size = (unsigned)cd.size();
+  put32(cd, 0x06054b50); put16(cd, 0); put16(cd, 0); put16(cd, (unsigned)entries_.size()); put16(cd, (unsigned)entries_.size());
+  put32(cd, cd_size); put32(cd, (unsigned)cd_off); put16(cd, 0);
+  good_ = good_ && fwrite(cd.data(), 1, cd.size(), f) == cd.size();
+  good_ = (fclose(f) == 0) && good_;
+  f_ = nullptr;
+  return good_;
 }

@@ -10,3 +10,18 @@ struct NpzArray {
   std::vector<float> data;
 };
 bool npz_load(const char* path, std::map<std::string, NpzArray>& out, std::string& err);
+
+// Minimal .npz writer (zip archive of .npy members, stored uncompressed like cnpy::npz_save does):
+// NpzWriter w(path); w.add("xy", "<f8", {n, 2}, ptr, bytes); ... w.close();
+struct NpzWriter {
+  explicit NpzWriter(const std::string& path);
+  ~NpzWriter();
+  bool add(const std::string& name, const char* descr, const std::vector<size_t>& shape, const void* data, size_t bytes);
+  bool close();
+  bool ok() const { return f_ != nullptr && good_; }
+ private:
+  struct Entry { std::string name; unsigned crc; unsigned long long size, offset; };
+  void* f_ = nullptr;
+  bool good_ = true;
+  std::vector<Entry> entries_;
+};

@@ -196,6 +196,35 @@ def test_oxaff_writer_matches_cv2_golden(tmp_path):
     assert open(path).read().split() == ["128", "0"]
 
 
+def test_region_text_and_npz_writers(tmp_path):
+    """SaveRegions text (imagerepresentation.cpp:1219-1255) and SaveRegionsNPZ (:1257-1316) layouts."""
+    import mods_light_zmq_b200 as M
+    rng = np.random.RandomState(3)
+    n = 17
+    f = np.zeros(n, M.FEATURE_DTYPE)
+    for k in ("x", "y", "s", "a11", "a12", "a21", "a22", "response"):
+        f[k] = rng.uniform(0.5, 900, n)
+    f["desc"] = rng.randint(0, 256, (n, 128))
+    p = str(tmp_path / "r.txt")
+    M.write_regions(p, f, "text")
+    lines = open(p).read().split("\n")
+    assert lines[:4] == ["1", "HessianAffine 1", "ZMQ %d" % n, "128"]
+    row = lines[4 + 5].split()
+    assert len(row) == 7 + 1 + 128 and int(row[7]) == 128
+    assert np.allclose([float(v) for v in row[:7]], [f[k][5] for k in ("x", "y", "s", "a11", "a12", "a21", "a22")], rtol=1e-5)
+    assert [int(v) for v in row[8:]] == [int(v) for v in f["desc"][5]]
+    p = str(tmp_path / "r.npz")
+    M.write_regions(p, f)
+    z = np.load(p)
+    assert sorted(z.files) == ["A", "descs", "responses", "scales", "xy"]
+    assert z["xy"].dtype == np.float64 and z["descs"].dtype == np.uint8 and z["descs"].shape == (n, 128)
+    assert np.array_equal(z["xy"], np.c_[f["x"], f["y"]]) and np.array_equal(z["scales"][:, 0], f["s"])
+    assert np.array_equal(z["A"], np.c_[f["a11"], f["a12"], f["a21"], f["a22"]]) and np.array_equal(z["responses"][:, 0], f["response"])
+    assert np.array_equal(z["descs"], f["desc"].astype(np.uint8))
+    M.write_regions(p, f[:0])
+    assert np.load(p)["xy"].shape == (0, 2)
+
+
 def test_oracle_matcher_small(oracle):
     rng = np.random.RandomState(0)
     t = rng.randint(0, 256, (70, 128)).astype(np.float32)

@@ -223,6 +223,28 @@ int  modsgpu_view_schedule(const double* scale_set, int n_scales, const double* 
 int  modsgpu_extract_features_views(modsgpu_ctx* ctx, modsgpu_image* img, const modsgpu_view* views, int n_views,
                                     modsgpu_feature** out, int* n);
 
+/* ---- MODS run over an iteration schedule (the main loop of mods.cpp:202-356 for its HessianAffine steps, e.g.
+ *      steps 2 and 3 of build/iters_MODS_ZMQ.ini): step k synthesises the views SetVSPars yields for it (views of
+ *      earlier steps are not repeated), adds their regions to both images, matches all accumulated regions (FGINN),
+ *      filters duplicates and verifies with LO-RANSAC -- homography (use_F = 0, mods.cpp LORANSAC) or fundamental
+ *      matrix (use_F = 1, LORANSACF); stops at the first step with >= min_matches verified correspondences.
+ *      model: H row-major image 1 -> 2 (use_F = 0) or F in the degensac layout (use_F = 1). ---------------------- */
+typedef struct {
+  double scale_set[8]; int n_scales;     /* ScaleSet */
+  double tilt_set[8];  int n_tilts;      /* TiltSet  */
+  double phi;                            /* Phi (rotation density, degrees; negative = vertical tilt) */
+  double init_sigma;                     /* initSigma */
+  double fginn_threshold;                /* FGINNThreshold */
+  int    do_blur, _pad;
+} modsgpu_mods_step;
+typedef struct {
+  int    steps_done, views[2], regions[2], tentatives, unique_tentatives, inliers;
+  double model[9];
+} modsgpu_mods_result;
+int  modsgpu_mods_pair(modsgpu_ctx* ctx, modsgpu_image* img1, modsgpu_image* img2, const modsgpu_mods_step* steps,
+                       int n_steps, int min_matches, int use_F, unsigned long long seed, modsgpu_mods_result* res,
+                       double* inlier_xy, int capacity);
+
 /* test-only: one 128x32x64 GEMM through the tcgen05 descriptor conventions of the dense kernels */
 int  modsgpu_debug_umma_probe(modsgpu_ctx* ctx, const float* A, const float* B, float* D, int swap_lbo_sbo);
 

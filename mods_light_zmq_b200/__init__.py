@@ -44,6 +44,17 @@ class PairResult(C.Structure):
                 ("tentatives", C.c_int), ("unique_tentatives", C.c_int), ("inliers", C.c_int), ("H", C.c_double * 9)]
 
 
+class ModsStep(C.Structure):
+    _fields_ = [("scale_set", C.c_double * 8), ("n_scales", C.c_int), ("tilt_set", C.c_double * 8), ("n_tilts", C.c_int),
+                ("phi", C.c_double), ("init_sigma", C.c_double), ("fginn_threshold", C.c_double), ("do_blur", C.c_int),
+                ("_pad", C.c_int)]
+
+
+class ModsResult(C.Structure):
+    _fields_ = [("steps_done", C.c_int), ("views", C.c_int * 2), ("regions", C.c_int * 2), ("tentatives", C.c_int),
+                ("unique_tentatives", C.c_int), ("inliers", C.c_int), ("model", C.c_double * 9)]
+
+
 class RansacResult(C.Structure):
     _fields_ = [("n_inliers", C.c_int), ("J", C.c_double), ("samples", C.c_int), ("lo_runs", C.c_int),
                 ("oc_rejects", C.c_int)]
@@ -286,6 +297,27 @@ class ModsGpu:
             return np.frombuffer(buf, FEATURE_DTYPE).copy()
         finally:
             self.lib.modsgpu_free(out)
+
+    def mods_pair(self, img1, img2, steps, min_matches=10, use_F=False, seed=12345, capacity=8192):
+        """modsgpu_mods_pair.  steps: list of dicts(scales, tilts, phi, init_sigma, fginn) -- one per iteration of an
+        iters_*.ini schedule."""
+        arr = (ModsStep * len(steps))()
+        for a, st in zip(arr, steps):
+            sc, ti = list(st.get("scales", [1.0])), list(st.get("tilts", [1.0]))
+            a.n_scales, a.n_tilts = len(sc), len(ti)
+            for i, v in enumerate(sc):
+                a.scale_set[i] = v
+            for i, v in enumerate(ti):
+                a.tilt_set[i] = v
+            a.phi, a.init_sigma = st.get("phi", 360.0), st.get("init_sigma", 0.2)
+            a.fginn_threshold, a.do_blur = st.get("fginn", 0.8), st.get("do_blur", 1)
+        res = ModsResult()
+        xy = np.zeros((capacity, 4), np.float64)
+        self._check(self.lib.modsgpu_mods_pair(self.ctx, img1.handle, img2.handle, arr, len(steps), int(min_matches),
+                                               int(bool(use_F)), C.c_ulonglong(seed), C.byref(res), _p(xy), capacity))
+        return dict(steps_done=res.steps_done, views=list(res.views), regions=list(res.regions), tentatives=res.tentatives,
+                    unique_tentatives=res.unique_tentatives, inliers=res.inliers, model=np.array(list(res.model)),
+                    inlier_xy=xy[:min(res.inliers, capacity)].copy())
 
     def ransac_F(self, u, th=16.0, conf=0.99, max_samples=1000000, sym_check=1, seed=12345):
         """modsgpu_ransac_F: LO-RANSAC for a fundamental matrix (exp_ransacFcustom, matching.cpp:722)."""

@@ -143,11 +143,16 @@ int ImageRepresentation::SynthDetectDescribeKeypoints(const DetectPars& par) {
 }
 
 int ImageRepresentation::SynthDetectDescribeKeypoints(const std::vector<ViewSynthParameters>& views, const DetectPars& par) {
-  int w, h;
-  modsgpu_image_size(img_, &w, &h);
   regions_.clear();
   n_views = 0;
   n_keypoints = n_affine = 0;
+  return AddViews(views, par);
+}
+
+int ImageRepresentation::AddViews(const std::vector<ViewSynthParameters>& views, const DetectPars& par) {
+  int w, h;
+  modsgpu_image_size(img_, &w, &h);
+  const int view_base = n_views;
   for (size_t v = 0; v < views.size(); v++) {
     double t0 = now_ms();
     modsgpu_image* view = nullptr;
@@ -162,7 +167,7 @@ int ImageRepresentation::SynthDetectDescribeKeypoints(const std::vector<ViewSynt
     if (rc < 0) return rc;
     n_keypoints += kp0; n_affine += af0;
     for (AffineRegion& r : one) {
-      r.img_reproj_id = (int)v;
+      r.img_reproj_id = view_base + (int)v;
       r.id = (int)regions_.size();
       regions_.push_back(r);
     }
@@ -456,11 +461,40 @@ int LORANSACFiltering(modsgpu_ctx* ctx, TentativeCorrespListExt& in_corresp, Ten
   rp.do_sym_check = pars.doSymmCheck;
   rp.seed = pars.seed;
   modsgpu_ransac_result rr;
-  int rc = modsgpu_ransac_H(ctx, u2.data(), tent_size, &rp, Hloran, inl2.data(), &rr);
+  int rc = pars.useF ? modsgpu_ransac_F(ctx, u2.data(), tent_size, &rp, Hloran, inl2.data(), &rr)
+                     : modsgpu_ransac_H(ctx, u2.data(), tent_size, &rp, Hloran, inl2.data(), &rr);
   if (rc) return rc;
   for (int i = 0; i < tent_size; i++) {
     in_corresp.TCList[i].isTrue = inl2[i];
     if (inl2[i]) ransac_corresp.TCList.push_back(in_corresp.TCList[i]);
+  }
+  if (pars.useF) {   // matching.cpp:806-820: F_LAF_check (:192-248) with FDs, then F = Hloran as is
+    std::vector<TentativeCorrespExt> checked;
+    const double affineFerror = pars.LAFCoef * pars.err_threshold;
+    const double k_sigma = 2 * 3.0 * std::sqrt(3.0);
+    auto fds = [&](const double* u) {
+      const double* F = Hloran;
+      const double rxc = F[0] * u[3] + F[3] * u[4] + F[6], ryc = F[1] * u[3] + F[4] * u[4] + F[7], rwc = F[2] * u[3] + F[5] * u[4] + F[8];
+      const double r = (u[0] * rxc + u[1] * ryc + rwc);
+      const double rx = F[0] * u[0] + F[1] * u[1] + F[2], ry = F[3] * u[0] + F[4] * u[1] + F[5];
+      return r * r / (rxc * rxc + ryc * ryc + rx * rx + ry * ry);
+    };
+    for (const auto& c : ransac_corresp.TCList) {
+      if (!(affineFerror > 0)) { checked.push_back(c); continue; }
+      const AffineKeypoint &f = c.first.reproj_kp, &s = c.second.reproj_kp;
+      double u[18];
+      u[0] = f.x; u[1] = f.y; u[2] = 1.0; u[3] = s.x; u[4] = s.y; u[5] = 1.0;
+      u[6] = u[0] + k_sigma * f.a12 * f.s; u[7] = u[1] + k_sigma * f.a22 * f.s; u[8] = 1.0;
+      u[9] = u[3] + k_sigma * s.a12 * s.s; u[10] = u[4] + k_sigma * s.a22 * s.s; u[11] = 1.0;
+      u[12] = u[0] + k_sigma * f.a11 * f.s; u[13] = u[1] + k_sigma * f.a21 * f.s; u[14] = 1.0;
+      u[15] = u[3] + k_sigma * s.a11 * s.s; u[16] = u[4] + k_sigma * s.a21 * s.s; u[17] = 1.0;
+      const double sumErr = std::sqrt(fds(u)) + std::sqrt(fds(u + 6)) + std::sqrt(fds(u + 12));
+      if (!(sumErr > affineFerror)) checked.push_back(c);
+    }
+    if ((int)checked.size() < MIN_POINTS) checked.clear();
+    ransac_corresp.TCList.swap(checked);
+    for (int i = 0; i < 9; i++) { ransac_corresp.H[i] = Hloran[i]; H[i] = Hloran[i]; }
+    return (int)ransac_corresp.TCList.size();
   }
   // H = inv(Hloran^T)  (matching.cpp:767-784)
   const double Ht[9] = {Hloran[0], Hloran[3], Hloran[6], Hloran[1], Hloran[4], Hloran[7], Hloran[2], Hloran[5], Hloran[8]};
@@ -476,6 +510,43 @@ int LORANSACFiltering(modsgpu_ctx* ctx, TentativeCorrespListExt& in_corresp, Ten
   if ((int)checked.size() < MIN_POINTS) checked.clear();
   ransac_corresp.TCList.swap(checked);
   return (int)ransac_corresp.TCList.size();
+}
+
+// mods.cpp:202-356, HessianAffine steps only (MSER and the other detectors stay on the reference's CPU path)
+int MODSPair(modsgpu_ctx* ctx, modsgpu_image* img1, modsgpu_image* img2, const std::vector<IterationStep>& steps,
+             int minMatches, const RANSACPars& rp, MODSResult& res, TentativeCorrespListExt& verified) {
+  res = MODSResult();
+  verified.TCList.clear();
+  DetectPars dp;
+  ImageRepresentation r1(ctx, img1, false), r2(ctx, img2, false);
+  std::vector<ViewSynthParameters> hist;   // SetVSPars history: a view is synthesised once per run
+  int curr_matches = 0;
+  for (size_t step = 0; step < steps.size() && curr_matches < minMatches; step++) {
+    const IterationStep& st = steps[step];
+    std::vector<ViewSynthParameters> views;
+    SetVSPars(st.ScaleSet, st.TiltSet, st.Phi, views, hist, st.initSigma, st.doBlur);
+    int rc = r1.AddViews(views, dp);
+    if (rc < 0) return rc;
+    rc = r2.AddViews(views, dp);
+    if (rc < 0) return rc;
+    res.steps_done = (int)step + 1;
+    res.views[0] = r1.n_views; res.views[1] = r2.n_views;
+    res.regions[0] = (int)r1.GetAffineRegionVector().size(); res.regions[1] = (int)r2.GetAffineRegionVector().size();
+    MatchPars mp;
+    mp.FGINNThreshold = st.FGINNThreshold;
+    TentativeCorrespListExt tent;
+    int nt = MatchFlannFGINN(ctx, r1.GetAffineRegionVector(), r2.GetAffineRegionVector(), tent, mp);
+    if (nt < 0) return nt;
+    res.tentatives = nt;
+    int nu = DuplicateFiltering(ctx, tent, mp.doubleFilteringRadius);
+    if (nu < 0) return nu;
+    res.unique_tentatives = nu;
+    int ni = LORANSACFiltering(ctx, tent, verified, res.model, rp);
+    if (ni < 0) return ni;
+    res.inliers = ni;
+    curr_matches = ni;
+  }
+  return 0;
 }
 
 }  // namespace modsb200
@@ -648,4 +719,37 @@ extern "C" int modsgpu_write_regions_npz(const char* path, const modsgpu_feature
   w.add("A", "<f8", {N, 4}, A.data(), A.size() * 8);
   w.add("descs", "|u1", {N, 128}, descs.data(), descs.size());
   return w.close() ? 0 : MODSGPU_EIO;
+}
+
+
+// MODS run over an iteration schedule (mods.cpp:202-356, HessianAffine steps)
+extern "C" int modsgpu_mods_pair(modsgpu_ctx* ctx, modsgpu_image* img1, modsgpu_image* img2, const modsgpu_mods_step* steps,
+                                 int n_steps, int min_matches, int use_F, unsigned long long seed, modsgpu_mods_result* res,
+                                 double* inlier_xy, int capacity) {
+  using namespace modsb200;
+  if (!ctx || !img1 || !img2 || !res || n_steps < 0 || (n_steps > 0 && !steps)) return MODSGPU_EINVAL;
+  std::vector<IterationStep> st((size_t)n_steps);
+  for (int i = 0; i < n_steps; i++) {
+    if (steps[i].n_scales < 0 || steps[i].n_scales > 8 || steps[i].n_tilts < 0 || steps[i].n_tilts > 8) return MODSGPU_EINVAL;
+    st[i].ScaleSet.assign(steps[i].scale_set, steps[i].scale_set + steps[i].n_scales);
+    st[i].TiltSet.assign(steps[i].tilt_set, steps[i].tilt_set + steps[i].n_tilts);
+    st[i].Phi = steps[i].phi; st[i].initSigma = steps[i].init_sigma; st[i].FGINNThreshold = steps[i].fginn_threshold;
+    st[i].doBlur = steps[i].do_blur;
+  }
+  RANSACPars rp;
+  rp.seed = seed; rp.useF = use_F;
+  MODSResult r;
+  TentativeCorrespListExt verified;
+  int rc = MODSPair(ctx, img1, img2, st, min_matches, rp, r, verified);
+  if (rc) return rc;
+  res->steps_done = r.steps_done;
+  for (int k = 0; k < 2; k++) { res->views[k] = r.views[k]; res->regions[k] = r.regions[k]; }
+  res->tentatives = r.tentatives; res->unique_tentatives = r.unique_tentatives; res->inliers = r.inliers;
+  for (int i = 0; i < 9; i++) res->model[i] = r.model[i];
+  for (int i = 0; i < r.inliers && i < capacity && inlier_xy; i++) {
+    const TentativeCorrespExt& c = verified.TCList[i];
+    inlier_xy[4 * i + 0] = c.first.reproj_kp.x; inlier_xy[4 * i + 1] = c.first.reproj_kp.y;
+    inlier_xy[4 * i + 2] = c.second.reproj_kp.x; inlier_xy[4 * i + 3] = c.second.reproj_kp.y;
+  }
+  return 0;
 }

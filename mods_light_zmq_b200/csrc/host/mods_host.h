@@ -49,6 +49,8 @@ struct RANSACPars {                // matching.hpp:132-164
   int max_samples = 1000000;
   int doSymmCheck = 1;
   double HLAFCoef = 12.0;
+  double LAFCoef = 2.0;            // F branch (matching.cpp:810)
+  int useF = 0;                    // LORANSACF (mods.cpp:325): exp_ransacFcustom instead of exp_ransacHcustom
   unsigned long long seed = 12345; // the reference seeds with time(NULL) (exp_ranH.c:823)
 };
 struct DetectPars {
@@ -85,6 +87,8 @@ class ImageRepresentation {
   int SynthDetectDescribeKeypoints(const std::vector<ViewSynthParameters>& views, const DetectPars& par);
   int n_views = 0;
   const AffineRegionVector& GetAffineRegionVector() const { return regions_; }
+  // regions of further views are appended (AddRegions, imagerepresentation.cpp:1098-1102)
+  int AddViews(const std::vector<ViewSynthParameters>& views, const DetectPars& par);
   int n_keypoints = 0, n_affine = 0;
   TimeLog TimeSpent;
 
@@ -109,6 +113,14 @@ void OxAffEllipse(const AffineKeypoint& k, float& a, float& b, float& c);
 int MatchFlannFGINN(modsgpu_ctx* ctx, const AffineRegionVector& list1, const AffineRegionVector& list2,
                     TentativeCorrespListExt& corresp, const MatchPars& par);
 int DuplicateFiltering(modsgpu_ctx* ctx, TentativeCorrespListExt& in_corresp, double r);
+// one MODS run over a schedule of iterations (mods.cpp:202-356 for the HessianAffine steps): every step adds the
+// regions of its new views to both images, matches ALL accumulated regions, filters duplicates and verifies with
+// LO-RANSAC (H or F); the loop stops at the first step with >= minMatches verified correspondences.
+struct IterationStep { std::vector<double> ScaleSet, TiltSet; double Phi = 360, initSigma = 0.2, FGINNThreshold = 0.8; int doBlur = 1; };
+struct MODSResult { int steps_done = 0, views[2] = {0, 0}, regions[2] = {0, 0}, tentatives = 0, unique_tentatives = 0, inliers = 0; double model[9] = {0}; };
+int MODSPair(modsgpu_ctx* ctx, modsgpu_image* img1, modsgpu_image* img2, const std::vector<IterationStep>& steps,
+             int minMatches, const RANSACPars& rp, MODSResult& res, TentativeCorrespListExt& verified);
+
 int LORANSACFiltering(modsgpu_ctx* ctx, TentativeCorrespListExt& in_corresp, TentativeCorrespListExt& ransac_corresp,
                       double* H, const RANSACPars& pars);
 

@@ -579,3 +579,36 @@ def test_multi_view_extraction(mg, oracle):
     assert d.max() < 1e-3, d.max()
     # a tilt-2 view halves the horizontal extent: reprojected frames are stretched back by H^-1
     assert np.allclose(np.abs(v1["a11"] * v1["a22"] - v1["a12"] * v1["a21"]), 2.0, rtol=1e-6)
+
+
+def test_mods_iterations_on_tilted_pair(mg, oracle):
+    """The MODS loop (mods.cpp:202-356, HessianAffine steps): image B is image A seen under a strong horizontal tilt.
+    The schedule adds tilted views step by step; the run must end with a verified homography close to the truth, and
+    later steps must not repeat the views of earlier ones (SetVSPars history)."""
+    from mods_light_zmq_b200 import synth
+    a = synth.blob_image(seed=91, w=640, h=480, n_blobs=1500)
+    Ht = np.array([[0.34, 0.06, 60.0], [-0.02, 0.97, 10.0], [0.0, 0.0, 1.0]])     # ~3x horizontal foreshortening
+    b = synth.warp_image(a, Ht, noise_seed=5)
+    i1, i2 = mg.image_from_bgr8(synth.gray_to_bgr(a)), mg.image_from_bgr8(synth.gray_to_bgr(b))
+    steps = [dict(tilts=[1.0], phi=360.0), dict(tilts=[1.0, 2.0, 4.0], phi=360.0)]
+    r = mg.mods_pair(i1, i2, steps, min_matches=100000, seed=3)        # unreachable minMatches: run every step
+    assert r["steps_done"] == 2 and r["views"] == [4, 4]                # 1 + (tilt 2: 1 rotation, tilt 4: 2 rotations)
+    assert r["inliers"] >= 30, r
+    Hn = r["model"].reshape(3, 3)
+    xy = r["inlier_xy"]
+    p = np.c_[xy[:, :2], np.ones(len(xy))] @ Ht.T
+    assert np.median(np.linalg.norm(p[:, :2] / p[:, 2:3] - xy[:, 2:4], axis=1)) < 2.0
+    pn = np.c_[xy[:, :2], np.ones(len(xy))] @ Hn.T
+    assert np.median(np.linalg.norm(pn[:, :2] / pn[:, 2:3] - xy[:, 2:4], axis=1)) < 2.0
+    # the identity-only schedule finds fewer correspondences on this pair than the schedule with tilted views
+    r1 = mg.mods_pair(i1, i2, steps[:1], min_matches=100000, seed=3)
+    assert r1["steps_done"] == 1 and r1["views"] == [1, 1] and r["inliers"] > r1["inliers"]
+    # early stop: the first step already satisfies a small minMatches when it has any consensus
+    if r1["inliers"] >= 10:
+        r2 = mg.mods_pair(i1, i2, steps, min_matches=10, seed=3)
+        assert r2["steps_done"] == 1
+    # epipolar verification (LORANSACF) on the same pair: a consistent F is returned with most H-inliers accepted
+    rf = mg.mods_pair(i1, i2, steps, min_matches=100000, use_F=True, seed=3)
+    assert rf["inliers"] >= 0.6 * r["inliers"]
+    d = oracle.sampson_F(rf["model"], np.c_[rf["inlier_xy"][:, :2], np.ones(len(rf["inlier_xy"])), rf["inlier_xy"][:, 2:4], np.ones(len(rf["inlier_xy"]))])
+    assert (d <= 16.0).all()

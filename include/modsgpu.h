@@ -110,6 +110,10 @@ typedef struct {            /* the AffineKeypoint fields the sampler reads, stru
 int  modsgpu_extract_patches(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_region* regs, int n,
                              double mrSize, int patchSize, uint8_t* out);
 
+/* the same sampler without the u8 quantisation: n * patchSize*patchSize floats (DescribeRegions' patches) */
+int  modsgpu_extract_patches_f32(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_region* regs, int n,
+                                 double mrSize, int patchSize, float* out);
+
 /* ---- S2 CNNs (replace DescribeWithZmq imagerepresentation.cpp:21-103 and the three daemons
  *      build/affnet_server.py, orinet_server.py, desc_server.py) ------------------------------ */
 typedef enum { MODSGPU_AFFNET = 0, MODSGPU_ORINET = 1, MODSGPU_HARDNET = 2 } modsgpu_net;
@@ -123,6 +127,17 @@ int  modsgpu_describe(modsgpu_ctx* ctx, modsgpu_net net, const modsgpu_image* im
                       int n, double mrSize, int patchSize, float* out);
 /* the net alone on caller-supplied 32x32 u8 patches (what the daemons receive as PNG) */
 int  modsgpu_net_forward_u8(modsgpu_ctx* ctx, modsgpu_net net, const uint8_t* patches, int n, float* out);
+
+/* ---- classic per-region stages (config_affori_classic.ini) ----------------------------------
+ * dominant orientation: replaces DetectOrientation (synth-detection.cpp:1039-1149, doHalfSIFT = 0, addUpRight = false).
+ *   n_ang[i] = -1 when region i is dropped by the 2*3*sqrt(3)*s frame test, else the number of angles (<= maxAngles,
+ *   taken in bin order) written to angles[i*maxAngles ..]; the caller rotates A by -angle like :1091-1101.
+ * (Root)SIFT: replaces DescribeRegions<SIFTDescriptor> (synth-detection.hpp:170-263, FastPatchExtraction = false) with
+ *   matching/siftdesc.cpp: out = n x 128 floats holding integers 0..255. */
+int  modsgpu_dominant_orientation(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_region* regs, int n,
+                                  double mrSize, int patchSize, int maxAngles, double th, int* n_ang, float* angles);
+int  modsgpu_describe_sift(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_region* regs, int n,
+                           double mrSize, int patchSize, int photoNorm, int rootSift, float* out);
 
 /* ---- S3 matcher (replaces MatchFlannFGINN matching.cpp:356-460 with vector_matcher=linear:
  *      exact 50-NN + first-geometrically-inconsistent ratio test) ----------------------------- */

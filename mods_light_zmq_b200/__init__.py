@@ -272,6 +272,30 @@ class ModsGpu:
         return dict(H=H, inl=inl[:T], I=res.n_inliers, J=res.J, samples=res.samples, lo_count=res.lo_runs,
                     oc_rejects=res.oc_rejects)
 
+    # ---- classic stages
+    def dominant_orientation(self, img, regs, mr_size=5.1962, patch_size=32, max_angles=1, th=0.8):
+        regs = np.ascontiguousarray(regs, REGION_DTYPE)
+        n_ang = np.zeros(max(len(regs), 1), np.int32)
+        ang = np.zeros((max(len(regs), 1), max(max_angles, 1)), np.float32)
+        self._check(self.lib.modsgpu_dominant_orientation(self.ctx, img.handle, _p(regs), len(regs), C.c_double(mr_size),
+                                                          patch_size, max_angles, C.c_double(th), _p(n_ang), _p(ang)))
+        return n_ang[:len(regs)], ang[:len(regs)]
+
+    def describe_sift(self, img, regs, mr_size=5.1962, patch_size=41, photo_norm=1, root_sift=1):
+        regs = np.ascontiguousarray(regs, REGION_DTYPE)
+        out = np.zeros((max(len(regs), 1), 128), np.float32)
+        self._check(self.lib.modsgpu_describe_sift(self.ctx, img.handle, _p(regs), len(regs), C.c_double(mr_size), patch_size,
+                                                   int(photo_norm), int(root_sift), _p(out)))
+        return out[:len(regs)]
+
+    def extract_patches_f32(self, img, regs, mr_size=5.1962, patch_size=41):
+        """float patches of the 3-step sampler (what DescribeRegions hands to the SIFT descriptor)"""
+        regs = np.ascontiguousarray(regs, REGION_DTYPE)
+        out = np.zeros((max(len(regs), 1), patch_size, patch_size), np.float32)
+        self._check(self.lib.modsgpu_extract_patches_f32(self.ctx, img.handle, _p(regs), len(regs), C.c_double(mr_size),
+                                                         patch_size, _p(out)))
+        return out[:len(regs)]
+
     # ---- one image -> described regions; OxAff writer (extract_features_batch)
     def extract_features(self, img):
         out = C.c_void_p()

@@ -738,7 +738,7 @@ extern "C" int modsgpu_net_forward_u8(modsgpu_ctx* ctx, modsgpu_net net, const u
 }
 
 int mg_sample_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_region* regs, int n,
-                      double mrSize, int ps, uint8_t* d_out);
+                      double mrSize, int ps, uint8_t* d_out, float* d_outf);
 
 extern "C" int modsgpu_describe(modsgpu_ctx* ctx, modsgpu_net net, const modsgpu_image* img, const modsgpu_region* regs,
                                 int n, double mrSize, int patchSize, float* out) {
@@ -749,7 +749,7 @@ extern "C" int modsgpu_describe(modsgpu_ctx* ctx, modsgpu_net net, const modsgpu
   const int D = modsgpu_net_out_dim(net);
   MG_CUDA(ctx, ctx->smp_out.ensure((size_t)n * 1024));
   MG_CUDA(ctx, ctx->cnn_out.ensure((size_t)n * D * 4));
-  int rc = mg_sample_enqueue(ctx, img, regs, n, mrSize, patchSize, ctx->smp_out.as<uint8_t>());
+  int rc = mg_sample_enqueue(ctx, img, regs, n, mrSize, patchSize, ctx->smp_out.as<uint8_t>(), nullptr);
   if (rc) return rc;
   rc = mg_net_forward_enqueue(ctx, net, ctx->smp_out.as<uint8_t>(), n, ctx->cnn_out.as<float>());
   if (rc) return rc;

@@ -90,7 +90,7 @@ __device__ __forceinline__ float row_pass_at(const float* row, int R, int x, con
 // ---- small windows: one CTA per region -----------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 k_sample_small(const float* __restrict__ img, int w, int h, const PatchMeta* __restrict__ metas,
-               const float* __restrict__ taps_all, uint8_t* __restrict__ out, int ps) {
+               const float* __restrict__ taps_all, uint8_t* __restrict__ out, int ps, float* __restrict__ outf) {
   extern __shared__ float sm[];
   const PatchMeta m = metas[blockIdx.x];
   const int tid = threadIdx.x, nth = blockDim.x;
@@ -108,7 +108,8 @@ k_sample_small(const float* __restrict__ img, int w, int h, const PatchMeta* __r
       for (int i = 0; i < ps; i++) {
         float v = sample_image(img, w, h, WX, WY);
         int q = __float2int_rn(v);
-        dst[j * ps + i] = (uint8_t)(q < 0 ? 0 : (q > 255 ? 255 : q));
+        if (outf) outf[(size_t)m.out_index * ps * ps + j * ps + i] = v;
+        else dst[j * ps + i] = (uint8_t)(q < 0 ? 0 : (q > 255 ? 255 : q));
         WX += a11; WY += a21;
       }
     }
@@ -186,7 +187,8 @@ k_sample_small(const float* __restrict__ img, int w, int h, const PatchMeta* __r
       v = (WY - (float)y) * (wx * (r1[1] - r1[0]) + r1[0] - I1) + I1;
     }
     int q = __float2int_rn(v);
-    dst[it] = (uint8_t)(q < 0 ? 0 : (q > 255 ? 255 : q));
+    if (outf) outf[(size_t)m.out_index * ps * ps + it] = v;
+    else dst[it] = (uint8_t)(q < 0 ? 0 : (q > 255 ? 255 : q));
   }
 }
 
@@ -300,7 +302,7 @@ __host__ __device__ inline int a_smem_floats(int R, int r) {
 
 __global__ void __launch_bounds__(NT)
 k_sample_a(const float* __restrict__ img, int w, int h, const PatchMeta* __restrict__ metas,
-           const float* __restrict__ taps_all, uint8_t* __restrict__ out, int ps) {
+           const float* __restrict__ taps_all, uint8_t* __restrict__ out, int ps, float* __restrict__ outf) {
   extern __shared__ float sm[];
   const PatchMeta m = metas[blockIdx.x];
   const int tid = threadIdx.x;
@@ -399,7 +401,8 @@ k_sample_a(const float* __restrict__ img, int w, int h, const PatchMeta* __restr
       const float I1 = wx * (r0[1] - r0[0]) + r0[0];
       v = (WY - (float)y) * (wx * (r1[1] - r1[0]) + r1[0] - I1) + I1;
     }
-    dst[it] = quant_u8(v);
+    if (outf) outf[(size_t)m.out_index * ps * ps + it] = v;
+    else dst[it] = quant_u8(v);
   }
 }
 
@@ -599,7 +602,7 @@ k_large_rowpass(const PatchMeta* __restrict__ metas, int nreg, const int* __rest
 // phase 2b + 3: column pass at the needed rows of L3_OUT_ROWS output rows, then the final resampling
 __global__ void __launch_bounds__(256)
 k_large_colpass_final(const PatchMeta* __restrict__ metas, const float* __restrict__ taps_all,
-                      const float* __restrict__ scratch, uint8_t* __restrict__ out, int ps) {
+                      const float* __restrict__ scratch, uint8_t* __restrict__ out, int ps, float* __restrict__ outf) {
   extern __shared__ float sm[];
   const int nblk = (ps + L3_OUT_ROWS - 1) / L3_OUT_ROWS;
   const int reg = blockIdx.x / nblk, j0 = (blockIdx.x - reg * nblk) * L3_OUT_ROWS;
@@ -645,7 +648,8 @@ k_large_colpass_final(const PatchMeta* __restrict__ metas, const float* __restri
       v = (WY - (float)y) * (wx * (r1[1] - r1[0]) + r1[0] - I1) + I1;
     }
     int q = __float2int_rn(v);
-    dst[j * ps + i] = (uint8_t)(q < 0 ? 0 : (q > 255 ? 255 : q));
+    if (outf) outf[(size_t)m.out_index * ps * ps + j * ps + i] = v;
+    else dst[j * ps + i] = (uint8_t)(q < 0 ? 0 : (q > 255 ? 255 : q));
   }
 }
 
@@ -655,7 +659,8 @@ constexpr int SMEM_L3 = (MAX_PS + 640 + 2 * L3_OUT_ROWS * 2 * MAX_PS) * 4;
 }  // namespace
 
 // Enqueue the sampler for n regions (host array) on ctx->stream; u8 patches land in d_out
-// (n * ps * ps bytes, region order).  No host synchronisation.
+// (n * ps * ps bytes, region order) or, when d_outf is given, unquantised float patches in d_outf (what
+// DescribeRegions feeds the SIFT descriptor, synth-detection.hpp:170-263).  No host synchronisation.
 // Regions are dealt into size classes (one launch each, shared memory sized for the class so that small
 // windows keep 4-8 CTAs per SM) and sorted by decreasing R inside a class (largest CTAs start first):
 //   A1 R <= 40, A2 R <= 65 : k_sample_a (whole window filtered)        B1 R <= 100, B2 R <= 160 : k_sample_b
@@ -663,7 +668,7 @@ constexpr int SMEM_L3 = (MAX_PS + 640 + 2 * L3_OUT_ROWS * 2 * MAX_PS) * 4;
 constexpr int A1_R = 40, A2_R = 65, B1_R = 100, B2_R = 160;
 
 int mg_sample_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_region* regs, int n,
-                      double mrSize, int ps, uint8_t* d_out) {
+                      double mrSize, int ps, uint8_t* d_out, float* d_outf) {
   if (ps < 2 || ps > MAX_PS) MG_FAIL(ctx, MODSGPU_EINVAL, "patchSize out of range");
   if (n <= 0) return 0;
   enum { C_SMALL = 0, C_A1, C_A2, C_B1, C_B2, C_LARGE, NCLS };
@@ -698,8 +703,8 @@ int mg_sample_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
       const bool blocked = m.ks >= 7 && m.ks <= 60 && ps <= 64;
       if (blocked && m.R <= A1_R) c = C_A1;
       else if (blocked && m.R <= A2_R) c = C_A2;
-      else if (blocked && ps == 32 && R0 >= 2 * ps && m.R <= B1_R) c = C_B1;
-      else if (blocked && ps == 32 && R0 >= 2 * ps && m.R <= B2_R) c = C_B2;
+      else if (blocked && ps == 32 && !d_outf && R0 >= 2 * ps && m.R <= B1_R) c = C_B1;
+      else if (blocked && ps == 32 && !d_outf && R0 >= 2 * ps && m.R <= B2_R) c = C_B2;
       else if (m.R <= SMALL_R && m.ks <= 31) c = C_SMALL;
       else c = C_LARGE;
     } else {
@@ -760,7 +765,7 @@ int mg_sample_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
   };
   if (!cls[C_SMALL].empty()) {
     MG_PROF(ctx, "k_sample_small", 0, alg_bytes(cls[C_SMALL]));
-    k_sample_small<<<(unsigned)cls[C_SMALL].size(), 128, SMEM_SMALL, ctx->stream>>>(img->d, img->w, img->h, dm, dtaps, d_out, ps);
+    k_sample_small<<<(unsigned)cls[C_SMALL].size(), 128, SMEM_SMALL, ctx->stream>>>(img->d, img->w, img->h, dm, dtaps, d_out, ps, d_outf);
     MG_LAUNCHED(ctx);
   }
   const int a_maxR[2] = {A1_R, A2_R}, b_maxR[2] = {B1_R, B2_R};
@@ -768,7 +773,7 @@ int mg_sample_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
     if (cls[c].empty()) continue;
     const int smem = a_smem_floats(std::min(a_maxR[c - C_A1], cls[c][0].R), cls_r[c]) * 4;
     MG_PROF(ctx, c == C_A1 ? "k_sample_a<R<=40>" : "k_sample_a<R<=65>", 0, alg_bytes(cls[c]));
-    k_sample_a<<<(unsigned)cls[c].size(), NT, smem, ctx->stream>>>(img->d, img->w, img->h, dm + cls_off[c], dtaps, d_out, ps);
+    k_sample_a<<<(unsigned)cls[c].size(), NT, smem, ctx->stream>>>(img->d, img->w, img->h, dm + cls_off[c], dtaps, d_out, ps, d_outf);
     MG_LAUNCHED(ctx);
   }
   for (int c = C_B1; c <= C_B2; c++) {
@@ -788,7 +793,7 @@ int mg_sample_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
     k_large_rowpass<<<pre2[nl], 256, (MAX_PS + 640 + L2_ROWS * maxR) * 4, ctx->stream>>>(dl, nl, dpre2, dtaps, scr, ps);
     MG_LAUNCHED(ctx);
     MG_PROF(ctx, "k_large_colpass_final", 2, (double)nl);
-    k_large_colpass_final<<<nl * ceil_div(ps, L3_OUT_ROWS), 256, SMEM_L3, ctx->stream>>>(dl, dtaps, scr, d_out, ps);
+    k_large_colpass_final<<<nl * ceil_div(ps, L3_OUT_ROWS), 256, SMEM_L3, ctx->stream>>>(dl, dtaps, scr, d_out, ps, d_outf);
     MG_LAUNCHED(ctx);
   }
   return 0;
@@ -800,8 +805,21 @@ extern "C" int modsgpu_extract_patches(modsgpu_ctx* ctx, const modsgpu_image* im
   if (mg_begin(ctx)) return MODSGPU_ECUDA;
   size_t bytes = (size_t)n * patchSize * patchSize;
   MG_CUDA(ctx, ctx->smp_out.ensure(bytes + 16));
-  int rc = mg_sample_enqueue(ctx, img, regs, n, mrSize, patchSize, ctx->smp_out.as<uint8_t>());
+  int rc = mg_sample_enqueue(ctx, img, regs, n, mrSize, patchSize, ctx->smp_out.as<uint8_t>(), nullptr);
   if (rc) return rc;
   if (n > 0) MG_CUDA(ctx, cudaMemcpyAsync(out, ctx->smp_out.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return mg_end(ctx) ? MODSGPU_ECUDA : 0;
+}
+
+// float patches (no u8 quantisation): what DescribeRegions (synth-detection.hpp:170-263) hands to the SIFT descriptor
+extern "C" int modsgpu_extract_patches_f32(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_region* regs, int n,
+                                           double mrSize, int patchSize, float* out) {
+  if (!ctx || !img || (n > 0 && (!regs || !out)) || n < 0) return MODSGPU_EINVAL;
+  if (mg_begin(ctx)) return MODSGPU_ECUDA;
+  size_t bytes = (size_t)n * patchSize * patchSize * 4;
+  MG_CUDA(ctx, ctx->smp_regs.ensure(bytes + 16));
+  int rc = mg_sample_enqueue(ctx, img, regs, n, mrSize, patchSize, nullptr, ctx->smp_regs.as<float>());
+  if (rc) return rc;
+  if (n > 0) MG_CUDA(ctx, cudaMemcpyAsync(out, ctx->smp_regs.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   return mg_end(ctx) ? MODSGPU_ECUDA : 0;
 }

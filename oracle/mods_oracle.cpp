@@ -11,6 +11,7 @@
 #include "mods_oracle.h"
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -154,6 +155,264 @@ extern "C" void orc_half_image(const float* in, int w, int h, float* out) {
       float r0 = a + (b - a) * 0.5f;
       float r1 = c + (d - c) * 0.5f;
       out[(size_t)y * ow + x] = r0 + (r1 - r0) * 0.5f;
+    }
+  }
+}
+
+/* ========================================================================== */
+/* classic stages: dominant orientation, (Root)SIFT                            */
+/* ========================================================================== */
+
+/* helpers.cpp:30-72: the literal table holds atan(i/255) to 10 decimals; three entries of the reference carry
+ * typos (32, 83, 100) and are reproduced as such.  Values are parsed from their decimal form like the compiler
+ * parses the reference's literals. */
+extern "C" void orc_atan_lut(double* lut) {
+  char buf[64];
+  for (int i = 0; i < 256; i++) {
+    snprintf(buf, sizeof(buf), "%.10f", std::atan(i / 255.0));
+    lut[i] = strtod(buf, nullptr);
+  }
+  lut[32] = strtod("0.1248376255", nullptr);
+  lut[83] = strtod("0.3146752558", nullptr);
+  lut[100] = strtod("0.3737268255", nullptr);
+}
+
+/* helpers.cpp:160-207 atan2LUTff */
+static float atan2LUTff(const double* LUT, float y, float x) {
+  const float PI2f = 1.57079632679489661923f, PIf = 3.14159265358979323846f;
+  if (x > 0.f) {
+    if (y > 0.f) {
+      if (x > y) return LUT[(int)(255.f * y / x)];
+      return PI2f - LUT[(int)(255 * x / y)];
+    } else {
+      float absy = std::fabs(y);
+      if (x > absy) return -LUT[(int)(255.f * absy / x)];
+      return -PI2f + LUT[(int)(255.f * x / absy)];
+    }
+  } else if (y > 0.f) {
+    float absx = std::fabs(x);
+    if (absx > y) return PIf - LUT[(int)(255.f * y / absx)];
+    return PI2f + LUT[(int)(255.f * absx / y)];
+  } else {
+    float absx = std::fabs(x), absy = std::fabs(y);
+    if (absx > absy) return -PIf + LUT[(int)(255.f * absy / absx)];
+    if (x == 0.f) return 0.f;
+    return -PI2f - LUT[(int)(255.f * absx / absy)];
+  }
+}
+
+extern "C" void orc_circular_gauss_mask(float* mask, int size, float sigma) {
+  const int halfSize = size >> 1;
+  const float r2 = float(halfSize * halfSize);
+  const float sigma2 = sigma == 0 ? 0.9f * r2 : 2 * sigma * sigma;
+  float* mp = mask;
+  for (int i = 0; i < size; i++)
+    for (int j = 0; j < size; j++) {
+      const float disq = float((i - halfSize) * (i - halfSize) + (j - halfSize) * (j - halfSize));
+      *mp++ = (disq < r2) ? std::exp(-disq / sigma2) : 0;     /* float overload, as <cmath> resolves it */
+    }
+}
+
+extern "C" void orc_dominant_orientation(const float* img, int w, int h, const orc_region* regs, int n, double mrSize,
+                                         int patchSize, int maxAngles, double th, int* n_ang, float* angles) {
+  const int pS = patchSize, bins = 36;
+  double LUT[256];
+  orc_atan_lut(LUT);
+  std::vector<float> orimask((size_t)pS * pS), patch((size_t)pS * pS), gmag((size_t)pS * pS, 0.f), gori((size_t)pS * pS, 0.f);
+  orc_circular_gauss_mask(orimask.data(), pS, pS / 3.0f);
+  const double mrScale = (double)mrSize;
+  const int patchImageSize = 2 * int(mrScale) + 1;
+  const double imageToPatchScale = double(patchImageSize) / (double)patchSize;
+  const double k_sigma = 2 * 3.0 * std::sqrt(3.0);
+  for (int i = 0; i < n; i++) {
+    const orc_region& k = regs[i];
+    n_ang[i] = 0;
+    const float curr_sc = imageToPatchScale * k.s;
+    if (orc_interpolate_check_borders(w, h, (float)k.x, (float)k.y, (float)k.a11, (float)k.a12, (float)k.a21, (float)k.a22,
+                                      (int)(k_sigma * k.s), (int)(k_sigma * k.s))) { n_ang[i] = -1; continue; }
+    if (maxAngles <= 0) continue;
+    orc_interpolate(img, w, h, (float)k.x, (float)k.y, (float)k.a11 * curr_sc, (float)k.a12 * curr_sc, (float)k.a21 * curr_sc,
+                    (float)k.a22 * curr_sc, patch.data(), pS, pS);
+    /* computeGradientMagnitudeAndOrientation (helpers.cpp:840-863): interior only, the frame keeps its zeros */
+    for (int r = 1; r < pS - 1; ++r)
+      for (int c = 1; c < pS - 1; ++c) {
+        const float xgrad = patch[r * pS + c + 1] - patch[r * pS + c - 1];
+        const float ygrad = patch[(r + 1) * pS + c] - patch[(r - 1) * pS + c];
+        gmag[r * pS + c] = std::sqrt(xgrad * xgrad + ygrad * ygrad);
+        gori[r * pS + c] = atan2LUTff(LUT, ygrad, xgrad);
+      }
+    float hist[bins + 1];
+    for (int b = 0; b < bins; b++) hist[b] = 0.0f;
+    const int maskPixels = pS * (pS - 2);
+    for (int q = 0; q < maskPixels; ++q) {
+      const float m = orimask[pS + q], g = gmag[pS + q], o = gori[pS + q];
+      if (m > 0 && g > 1.0) {
+        int bin = (int)(bins * (o / float(M_PI) + 1.0f) / 2.0f);
+        hist[bin] += g * m;
+      }
+    }
+    for (int it = 0; it < 6; it++) {   /* smoothCircularBuffer, synth-detection.cpp:811-822 */
+      float first = hist[0], prev = hist[bins - 1];
+      for (int b = 0; b < bins - 1; b++) { float cur = hist[b]; hist[b] = prev + cur + hist[b + 1]; prev = cur; }
+      hist[bins - 1] = prev + hist[bins - 1] + first;
+    }
+    float thresh = 0.0;
+    for (int b = 0; b < bins; b++) if (hist[b] > thresh) thresh = hist[b];
+    thresh *= th;
+    std::vector<float> ang, peaks;
+    auto addPeak = [&](int a, int b, int c) {
+      if (hist[b] >= thresh && hist[b] > hist[a] && hist[b] > hist[c]) {
+        float pp = (hist[a] - hist[c]) / (hist[a] - 2.0f * hist[b] + hist[c]) / 2.0f;
+        ang.push_back(2.0f * float(M_PI) * (b + 0.5f + pp) / bins - float(M_PI));
+        peaks.push_back(hist[b]);
+      }
+    };
+    addPeak(bins - 1, 0, 1);
+    for (int b = 1; b < bins - 1; b++) addPeak(b - 1, b, b + 1);
+    addPeak(bins - 2, bins - 1, 0);
+    int mA = std::min(maxAngles, (int)peaks.size());
+    int cnt = 0;
+    for (int a = 0; a < mA; a++) {
+      if (peaks[a] >= thresh) angles[(size_t)i * maxAngles + cnt++] = ang[a];
+      else break;
+    }
+    n_ang[i] = cnt;
+  }
+}
+
+namespace {
+struct SiftTables {
+  int ps = 0;
+  std::vector<int> bin0, bin1;
+  std::vector<double> w0, w1;
+  std::vector<float> mask;
+  void init(int patchSize) {   /* siftdesc.cpp:22-71 precomputeBinsAndWeights (spatialBins 4, orientationBins 8) */
+    ps = patchSize;
+    const int spatialBins = 4, orientationBins = 8;
+    const int halfSize = ps >> 1;
+    const float step = float(spatialBins + 1) / (2 * halfSize);
+    bin0.resize(ps); bin1.resize(ps); w0.resize(ps); w1.resize(ps);
+    for (int i = 0; i < ps; i++) {
+      float x = step * i;
+      int xi = (int)(x);
+      bin0[i] = xi - 1; bin1[i] = xi;
+      w1[i] = x - xi;
+      w0[i] = 1.0f - w1[i];
+      if (bin0[i] < 0) { bin0[i] = 0; w0[i] = 0; }
+      if (bin0[i] >= spatialBins) { bin0[i] = spatialBins - 1; w0[i] = 0; }
+      if (bin1[i] < 0) { bin1[i] = 0; w1[i] = 0; }
+      if (bin1[i] >= spatialBins) { bin1[i] = spatialBins - 1; w1[i] = 0; }
+      bin0[i] *= orientationBins; bin1[i] *= orientationBins;
+    }
+    mask.resize((size_t)ps * ps);
+    orc_circular_gauss_mask(mask.data(), ps, 0.f);
+  }
+};
+double normalize_d(std::vector<double>& v) {   /* siftdesc.cpp:132-159 */
+  double len = 0.0;
+  for (size_t i = 0; i < v.size(); i += 4) {
+    const double sq0 = v[i] * v[i], sq1 = v[i + 1] * v[i + 1], sq2 = v[i + 2] * v[i + 2], sq3 = v[i + 3] * v[i + 3];
+    len += sq0 + sq1 + sq2 + sq3;
+  }
+  len = std::sqrt(len);
+  const double fac = 1.0 / len;
+  for (size_t i = 0; i < v.size(); i++) v[i] *= fac;
+  return len;
+}
+}  // namespace
+
+extern "C" void orc_describe_sift(const float* img, int w, int h, const orc_region* regs, int n, double mrSize, int patchSize,
+                                  int photoNorm, int rootSift, float* desc) {
+  const int ps = patchSize, spatialBins = 4, orientationBins = 8;
+  const double maxBinValue = 0.2;       /* [SIFTDescriptor] maxBinValue = 0.2 read with GetDouble (io_mods.cpp:427) */
+  const double M_PI_DOUBLED = 6.28318530718;
+  double LUT[256];
+  orc_atan_lut(LUT);
+  SiftTables T;
+  T.init(ps);
+  std::vector<float> pmask((size_t)ps * ps);
+  orc_circular_gauss_mask(pmask.data(), ps, 0.f);   /* DescribeRegions' own mask (synth-detection.hpp:182-183) */
+  std::vector<float> patch((size_t)ps * ps), grad((size_t)ps * ps), ori((size_t)ps * ps);
+  for (int i = 0; i < n; i++) {
+    orc_extract_patches(img, w, h, regs + i, 1, mrSize, ps, patch.data());
+    if (photoNorm) {   /* helpers.cpp:666-716 */
+      float sum = 0, gsum = 0;
+      for (int q = 0; q < ps * ps; q++) if (pmask[q] > 0) { sum += patch[q]; gsum++; }
+      sum = sum / gsum;
+      float var = 0;
+      for (int q = 0; q < ps * ps; q++) if (pmask[q] > 0) var += (sum - patch[q]) * (sum - patch[q]);
+      var = std::sqrt(var / gsum);
+      if (!(var < 0.0001)) {
+        float fac = 50.0f / var;
+        for (int q = 0; q < ps * ps; q++) {
+          float v = 128 + fac * (patch[q] - sum);
+          if (v > 255) v = 255;
+          if (v < 0) v = 0;
+          patch[q] = v;
+        }
+      }
+    }
+    /* gradients with one-sided differences on the frame (siftdesc.cpp:279-302) */
+    for (int r = 0; r < ps; ++r)
+      for (int c = 0; c < ps; ++c) {
+        float xgrad, ygrad;
+        if (c == 0) xgrad = patch[r * ps + c + 1] - patch[r * ps + c];
+        else if (c == ps - 1) xgrad = patch[r * ps + c] - patch[r * ps + c - 1];
+        else xgrad = patch[r * ps + c + 1] - patch[r * ps + c - 1];
+        if (r == 0) ygrad = patch[(r + 1) * ps + c] - patch[r * ps + c];
+        else if (r == ps - 1) ygrad = patch[r * ps + c] - patch[(r - 1) * ps + c];
+        else ygrad = patch[(r + 1) * ps + c] - patch[(r - 1) * ps + c];
+        grad[r * ps + c] = std::sqrt(xgrad * xgrad + ygrad * ygrad);
+        ori[r * ps + c] = atan2LUTff(LUT, ygrad, xgrad);
+      }
+    /* samplePatch (siftdesc.cpp:73-130): vec is double, the per-pixel weights are float */
+    std::vector<double> vec((size_t)spatialBins * spatialBins * orientationBins, 0.0);
+    const bool magnLess = false;
+    for (int r = 0; r < ps; ++r) {
+      const int br0 = spatialBins * T.bin0[r];
+      const float wr0 = T.w0[r];
+      const int br1 = spatialBins * T.bin1[r];
+      const float wr1 = T.w1[r];
+      for (int c = 0; c < ps; ++c) {
+        float val = float(magnLess) * 1.0 + (1.0 - float(magnLess)) * T.mask[r * ps + c] * grad[r * ps + c];
+        const int bc0 = T.bin0[c];
+        const float wc0 = T.w0[c] * val;
+        const int bc1 = T.bin1[c];
+        const float wc1 = T.w1[c] * val;
+        const float o = float(orientationBins) * (ori[r * ps + c] + M_PI_DOUBLED) / M_PI_DOUBLED;
+        int bo0 = (int)o;
+        const float wo1 = o - bo0;
+        bo0 %= orientationBins;
+        int bo1 = (bo0 + 1) % orientationBins;
+        const float wo0 = 1.0f - wo1;
+        val = wr0 * wc0;
+        if (val > 0) { vec[br0 + bc0 + bo0] += val * wo0; vec[br0 + bc0 + bo1] += val * wo1; }
+        val = wr0 * wc1;
+        if (val > 0) { vec[br0 + bc1 + bo0] += val * wo0; vec[br0 + bc1 + bo1] += val * wo1; }
+        val = wr1 * wc0;
+        if (val > 0) { vec[br1 + bc0 + bo0] += val * wo0; vec[br1 + bc0 + bo1] += val * wo1; }
+        val = wr1 * wc1;
+        if (val > 0) { vec[br1 + bc1 + bo0] += val * wo0; vec[br1 + bc1 + bo1] += val * wo1; }
+      }
+    }
+    /* SIFTnorm / RootSIFTnorm on doubles (siftdesc.cpp:196-249) */
+    normalize_d(vec);
+    bool changed = false;
+    for (size_t q = 0; q < vec.size(); q++) if (vec[q] > maxBinValue) { vec[q] = maxBinValue; changed = true; }
+    if (changed) normalize_d(vec);
+    if (rootSift) {
+      double sum = 0.;
+      for (size_t q = 0; q < vec.size(); q++) sum += std::fabs(vec[q]);
+      for (size_t q = 0; q < vec.size(); q++) vec[q] = std::sqrt(vec[q] / sum);
+      for (size_t q = 0; q < vec.size(); q++) {
+        int b = std::max(0, std::min((int)(512.0 * vec[q] + 0.5), 255));
+        desc[(size_t)i * 128 + q] = (float)double(b);
+      }
+    } else {
+      for (size_t q = 0; q < vec.size(); q++) {
+        int b = std::max(0, std::min((int)(512.0f * vec[q] + 0.5), 255));
+        desc[(size_t)i * 128 + q] = (float)double(b);
+      }
     }
   }
 }

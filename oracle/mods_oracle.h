@@ -58,6 +58,22 @@ void orc_hessian_response(const float* in, float* out, int w, int h, float norm)
 void orc_half_size(int w, int h, int* ow, int* oh);
 void orc_half_image(const float* in, int w, int h, float* out);
 
+/* ---- classic stages (config_affori_classic.ini): dominant orientation and (Root)SIFT ---- */
+/* helpers.cpp:30-72 ATAN_LUT as doubles (round(atan(i/255),1e-10) with the reference's 3 typo entries) */
+void orc_atan_lut(double* lut256);
+/* helpers.cpp:442-459 computeCircularGaussMask (sigma == 0 -> 0.9*r^2) */
+void orc_circular_gauss_mask(float* mask, int size, float sigma);
+/* synth-detection.cpp:1039-1149 DetectOrientation + :836-929 EstimateDominantAnglesFunctor (doHalfSIFT = 0,
+ * addUpRight = false).  n_ang[i] = -1: region dropped by the k_sigma*s frame test; else the number of angles
+ * (<= maxAngles, taken in bin order -- SURVEY Q13) written to angles[i*maxAngles ..]. */
+void orc_dominant_orientation(const float* img, int w, int h, const orc_region* regs, int n, double mrSize, int patchSize,
+                              int maxAngles, double th, int* n_ang, float* angles);
+/* synth-detection.hpp:170-263 DescribeRegions<SIFTDescriptor> (FastPatchExtraction = false) + siftdesc.cpp:
+ * patchSize x patchSize float patch (3-step sampler), optional photometricallyNormalize (helpers.cpp:666-716),
+ * gradients, 4x4x8 trilinear histogram with the circular Gauss mask, (Root)SIFT normalisation -> 128 integers 0..255 */
+void orc_describe_sift(const float* img, int w, int h, const orc_region* regs, int n, double mrSize, int patchSize,
+                       int photoNorm, int rootSift, float* desc);
+
 /* ---- view synthesis (synth-detection.cpp:324-518 GenerateSynthImageCorr) ---- */
 /* cv::warpAffine(src, dst, M (2x3 double, forward map), Size(ow,oh), INTER_LINEAR, BORDER_CONSTANT, border) on CV_32F */
 void orc_warp_affine(const float* in, int w, int h, const double* M, float* out, int ow, int oh, float border);

@@ -75,6 +75,48 @@ def gaussian_blur(img, sigma):
     return out
 
 
+def dominant_orientation(img, regs, mr_size=5.1962, patch_size=32, max_angles=1, th=0.8):
+    """DetectOrientation (synth-detection.cpp:1039-1149): returns (n_ang [n] with -1 = dropped, angles [n x max_angles])."""
+    img = np.ascontiguousarray(img, np.float32)
+    h, w = img.shape
+    regs = np.ascontiguousarray(regs, REGION_DTYPE)
+    n_ang = np.zeros(len(regs), np.int32)
+    ang = np.zeros((len(regs), max(max_angles, 1)), np.float32)
+    lib().orc_dominant_orientation(_p(img), w, h, _p(regs), len(regs), C.c_double(mr_size), patch_size, max_angles,
+                                   C.c_double(th), _p(n_ang), _p(ang))
+    return n_ang, ang
+
+
+def apply_orientations(regs, n_ang, ang):
+    """The region list DetectOrientation returns (addUpRight = false): one rotated copy per accepted angle."""
+    out = []
+    for r, n, a in zip(regs, n_ang, ang):
+        for j in range(max(n, 0)):
+            ci, si = np.cos(-float(a[j])), np.sin(-float(a[j]))
+            t = r.copy()
+            t["a11"] = r["a11"] * ci - r["a12"] * si
+            t["a12"] = r["a11"] * si + r["a12"] * ci
+            t["a21"] = r["a21"] * ci - r["a22"] * si
+            t["a22"] = r["a21"] * si + r["a22"] * ci
+            out.append(t)
+    return np.array(out, REGION_DTYPE) if out else np.zeros(0, REGION_DTYPE)
+
+
+def describe_sift(img, regs, mr_size=5.1962, patch_size=41, photo_norm=1, root_sift=1):
+    img = np.ascontiguousarray(img, np.float32)
+    h, w = img.shape
+    regs = np.ascontiguousarray(regs, REGION_DTYPE)
+    out = np.zeros((len(regs), 128), np.float32)
+    lib().orc_describe_sift(_p(img), w, h, _p(regs), len(regs), C.c_double(mr_size), patch_size, int(photo_norm), int(root_sift), _p(out))
+    return out
+
+
+def atan_lut():
+    t = np.zeros(256, np.float64)
+    lib().orc_atan_lut(_p(t))
+    return t
+
+
 def warp_affine(img, M, ow, oh, border=128.0):
     img = np.ascontiguousarray(img, np.float32)
     h, w = img.shape

@@ -612,3 +612,46 @@ def test_mods_iterations_on_tilted_pair(mg, oracle):
     assert rf["inliers"] >= 0.6 * r["inliers"]
     d = oracle.sampson_F(rf["model"], np.c_[rf["inlier_xy"][:, :2], np.ones(len(rf["inlier_xy"])), rf["inlier_xy"][:, 2:4], np.ones(len(rf["inlier_xy"]))])
     assert (d <= 16.0).all()
+
+
+# ------------------------------------------------------------------------------------------ classic stages (rows a18, a19)
+def test_dominant_orientation_bit_exact(mg, oracle, synth_pair):
+    """DetectOrientation (synth-detection.cpp:1039-1149) on every keypoint of the 1024x768 image: the same regions are
+    dropped by the frame test, the same peaks are found and the refined angles are bit-identical."""
+    a, _, _ = synth_pair
+    g = _gray(oracle, a)
+    img = mg.image_from_gray32f(g)
+    regs = oracle.regions_from_keypoints(oracle.detect_hessian(g))
+    rng = np.random.RandomState(2)
+    th = rng.uniform(0, 2 * np.pi, len(regs))          # give the regions some anisotropy / rotation
+    l = np.exp(rng.uniform(-0.5, 0.5, len(regs)))
+    regs["a11"], regs["a12"] = l * np.cos(th), -np.sin(th) / l
+    regs["a21"], regs["a22"] = l * np.sin(th), np.cos(th) / l
+    for max_angles in (1, 3):
+        n_ref, a_ref = oracle.dominant_orientation(g, regs, max_angles=max_angles)
+        n_got, a_got = mg.dominant_orientation(img, regs, max_angles=max_angles)
+        assert np.array_equal(n_got, n_ref)
+        assert (n_ref == -1).sum() > 0 and (n_ref >= 1).sum() > 0.5 * len(regs)
+        assert a_got.tobytes() == a_ref.tobytes()
+    n0, _ = mg.dominant_orientation(img, regs[:0])
+    assert len(n0) == 0
+
+
+def test_sift_descriptor_bit_exact(mg, oracle, synth_pair):
+    """DescribeRegions<SIFTDescriptor> (41x41 float patch of the 3-step sampler, photometric normalisation, gradients,
+    4x4x8 histogram, RootSIFT / SIFT normalisation): float patches and 128-integer descriptors identical to the oracle."""
+    a, _, _ = synth_pair
+    g = _gray(oracle, a)
+    img = mg.image_from_gray32f(g)
+    regs = oracle.regions_from_keypoints(oracle.detect_hessian(g))
+    n_ang, ang = oracle.dominant_orientation(g, regs)
+    r2 = oracle.apply_orientations(regs, n_ang, ang)[::3]
+    assert len(r2) > 500
+    pf = mg.extract_patches_f32(img, r2, patch_size=41)
+    assert np.array_equal(pf.reshape(len(r2), -1), oracle.extract_patches(g, r2, patchSize=41).reshape(len(r2), -1))
+    for root in (1, 0):
+        for pn in (1, 0):
+            d_ref = oracle.describe_sift(g, r2, photo_norm=pn, root_sift=root)
+            d_got = mg.describe_sift(img, r2, photo_norm=pn, root_sift=root)
+            assert np.array_equal(d_got, d_ref), (root, pn, np.abs(d_got - d_ref).max(), (d_got != d_ref).mean())
+    assert d_ref.max() <= 255 and d_ref.min() >= 0

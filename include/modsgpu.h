@@ -92,6 +92,21 @@ int  modsgpu_detect(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_py
                     modsgpu_keypoint** out, int* n);
 void modsgpu_free(void* p);
 
+/* the same detector with the in-pyramid affine shape adaptation of the classic configuration (doBaumberg = 1,
+ * method SMM: AffineShape::findAffineShape affine.cpp:26-158, called from localizeKeypoint on the level below the
+ * response level, pyramid.cpp:402).  Keypoints whose iteration does not converge are dropped.  *A: 4 floats per
+ * keypoint (a11 a12 a21 a22 as handed to onAffineShapeFound); both arrays are malloc()ed, release with modsgpu_free. */
+typedef struct {            /* AffineShapeParams, affine.h:26-68 */
+  int   maxIterations;          /* 16   */
+  float convergenceThreshold;   /* 0.05 */
+  int   smmWindowSize;          /* 19   */
+  float initialSigma;           /* 1.6  */
+  int   doBaumberg;             /* 1    */
+} modsgpu_affshape_params;
+void modsgpu_default_affshape_params(modsgpu_affshape_params* a);
+int  modsgpu_detect_affine(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_pyr_params* p,
+                           const modsgpu_affshape_params* aff, modsgpu_keypoint** out, float** A, int* n);
+
 /* pyramid internals exposed for the parity tests only (helpers.cpp:717-731 gaussianBlur,
  * pyramid.cpp:196-254 HessianResponse, pyramid.cpp:476 cv::resize 0.5) */
 int  modsgpu_gaussian_blur(modsgpu_ctx* ctx, const float* in, float* out, int w, int h, float sigma);

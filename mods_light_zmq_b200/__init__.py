@@ -34,6 +34,11 @@ class PyrParams(C.Structure):
                 ("edgeEigenValueRatio", C.c_double), ("border", C.c_int)]
 
 
+class AffShapeParams(C.Structure):
+    _fields_ = [("maxIterations", C.c_int), ("convergenceThreshold", C.c_float), ("smmWindowSize", C.c_int),
+                ("initialSigma", C.c_float), ("doBaumberg", C.c_int)]
+
+
 class RansacParams(C.Structure):
     _fields_ = [("th", C.c_double), ("conf", C.c_double), ("max_samples", C.c_int), ("do_sym_check", C.c_int),
                 ("seed", C.c_uint64)]
@@ -151,6 +156,27 @@ class ModsGpu:
         out = np.empty((img.h, img.w), np.float32)
         self._check(self.lib.modsgpu_image_download(self.ctx, img.handle, _p(out)))
         return out
+
+    def detect_affine(self, img, params=None, aff=None):
+        """modsgpu_detect_affine: Hessian-Affine with the in-pyramid Baumberg iteration -> (keypoints, A [n x 4])"""
+        if params is None:
+            params = PyrParams()
+            self.lib.modsgpu_default_pyr_params(C.byref(params))
+        if aff is None:
+            aff = AffShapeParams()
+            self.lib.modsgpu_default_affshape_params(C.byref(aff))
+        out, A = C.c_void_p(), C.c_void_p()
+        n = C.c_int()
+        self._check(self.lib.modsgpu_detect_affine(self.ctx, img.handle, C.byref(params), C.byref(aff), C.byref(out), C.byref(A), C.byref(n)))
+        try:
+            if n.value == 0:
+                return np.zeros(0, KP_DTYPE), np.zeros((0, 4), np.float32)
+            kb = (C.c_char * (n.value * KP_DTYPE.itemsize)).from_address(out.value)
+            ab = (C.c_char * (n.value * 16)).from_address(A.value)
+            return np.frombuffer(kb, KP_DTYPE).copy(), np.frombuffer(ab, np.float32).reshape(-1, 4).copy()
+        finally:
+            self.lib.modsgpu_free(out)
+            self.lib.modsgpu_free(A)
 
     # ---- view synthesis
     def synth_view(self, img, tilt, phi, zoom, init_sigma, do_blur=1):

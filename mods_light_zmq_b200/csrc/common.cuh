@@ -73,7 +73,7 @@ struct modsgpu_ctx {
   long long launches = 0;
   std::string err;
   // workspaces (named by their user)
-  DevBuf det_pyr, det_cand, det_map, det_out, det_misc;
+  DevBuf det_pyr, det_cand, det_map, det_out, det_misc, det_aff;
   HostBuf h_stage, h_stage2;
   DevBuf io_a, io_b, io_c;            // generic staging for the test-only entry points
   DevBuf smp_regs, smp_meta, smp_taps, smp_scratch, smp_out;

@@ -472,6 +472,128 @@ __global__ void k_nms_localize(NmsArgs a, int* map, Cand* cands, int* ncand, int
   localize(a, L, li, r, c, map, cands, ncand, cap);
 }
 
+// ---- in-pyramid Baumberg iteration (affine.cpp:26-158, doBaumberg = 1, AFF_BMBRG_SMM) ------------------------------
+// One warp per surviving candidate.  The 19 x 19 window is resampled from prevBlur (the level below the response
+// level, pyramid.cpp:402 / SURVEY Q12) with lane = window row (coordinates accumulated in the reference's order),
+// the three second-moment sums run in raster order on three lanes, the 2x2 algebra on every lane redundantly.
+struct OctTab { long long off[16]; int w[16], h[16]; };
+struct AffPars { int maxIterations; float convergenceThreshold; int smmWindowSize; float initialSigma; };
+constexpr int SMM_MAX = 25;
+
+__device__ __forceinline__ float sample_image_d(const float* im, int w, int h, float WX, float WY) {
+  const int x = (int)floorf(WX), y = (int)floorf(WY);
+  if (WX >= 0 && WY >= 0 && x < w - 1 && y < h - 1) {
+    const float wx = WX - (float)x;
+    const float* Row0 = im + (size_t)y * w;
+    const float* Row1 = Row0 + w;
+    const float I1 = wx * (Row0[x + 1] - Row0[x]) + Row0[x];
+    return (WY - (float)y) * (wx * (Row1[x + 1] - Row1[x]) + Row1[x] - I1) + I1;
+  }
+  return 0.f;
+}
+// helpers.cpp:461-503
+__device__ void invSqrt_d(float& a, float& b, float& c, float& l1, float& l2) {
+  double t, r;
+  if (b != 0) {
+    r = double(c - a) / (2 * b);
+    if (r >= 0) t = 1.0 / (r + sqrt(1 + r * r));
+    else t = -1.0 / (-r + sqrt(1 + r * r));
+    r = 1.0 / sqrt(1 + t * t);
+    t = t * r;
+  } else { r = 1; t = 0; }
+  double x, z, d;
+  x = 1.0 / sqrt(r * r * a - 2 * r * t * b + t * t * c);
+  z = 1.0 / sqrt(t * t * a + 2 * r * t * b + r * r * c);
+  d = sqrt(x * z);
+  x /= d; z /= d;
+  if (x < z) { l1 = float(z); l2 = float(x); }
+  else { l1 = float(x); l2 = float(z); }
+  a = float(r * r * x + t * t * z);
+  b = float(-r * t * x + t * r * z);
+  c = float(t * t * x + r * r * z);
+}
+
+__global__ void __launch_bounds__(128)
+k_baumberg(const float* __restrict__ pyr, OctTab ot, const Cand* __restrict__ cands, const int* __restrict__ ncand_p, int cap,
+           unsigned long long* __restrict__ keys, const float* __restrict__ mask, AffPars ap, float* __restrict__ candA,
+           int* __restrict__ nkept) {
+  __shared__ float img_s[4][SMM_MAX * SMM_MAX];
+  const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 4 + wl;
+  const int n = min(*ncand_p, cap);
+  if (i >= n) return;
+  if (keys[i] == ~0ull) return;
+  const Cand k = cands[i];
+  const int w = ot.w[k.octave], h = ot.h[k.octave];
+  const float* blur = pyr + ot.off[k.octave] + (size_t)w * h * (k.level - 1);   // prevBlur
+  const float pixelDistance = (float)(1 << k.octave);
+  float* img = img_s[wl];
+  float eigen_ratio_act = 0.0f, eigen_ratio_bef = 0.0f;
+  float u11 = 1.0f, u12 = 0.0f, u21 = 0.0f, u22 = 1.0f, l1 = 1.0f, l2 = 1.0f;
+  const float lx = k.x / pixelDistance, ly = k.y / pixelDistance;
+  const float ratio = k.s / (ap.initialSigma * pixelDistance);
+  const int ws = ap.smmWindowSize, maskPixels = ws * ws, half = ws / 2;
+  bool found = false;
+  for (int l = 0; l < ap.maxIterations; l++) {
+    const float a11 = u11 * ratio, a12 = u12 * ratio, a21 = u21 * ratio, a22 = u22 * ratio;
+    for (int j = lane; j < ws; j += 32) {          // interpolate(blur, lx, ly, U*ratio, img), helpers.cpp:551-626
+      float rx = lx - (float)half * a12, ry = ly - (float)half * a22;
+      for (int t = 0; t < j; t++) { rx += a12; ry += a22; }
+      float WX = rx - (float)half * a11, WY = ry - (float)half * a21;
+      for (int q = 0; q < ws; q++) {
+        img[j * ws + q] = sample_image_d(blur, w, h, WX, WY);
+        WX += a11; WY += a21;
+      }
+    }
+    __syncwarp();
+    float acc = 0.f;                                 // lanes 0, 1, 2: sum of gx*gx*v, gx*gy*v, gy*gy*v in raster order
+    if (lane < 3) {
+      for (int r = 0; r < ws; ++r)
+        for (int c = 0; c < ws; ++c) {
+          float xgrad, ygrad;                        // computeGradient, helpers.cpp:779-797
+          if (c == 0) xgrad = img[r * ws + c + 1] - img[r * ws + c];
+          else if (c == ws - 1) xgrad = img[r * ws + c] - img[r * ws + c - 1];
+          else xgrad = img[r * ws + c + 1] - img[r * ws + c - 1];
+          if (r == 0) ygrad = img[(r + 1) * ws + c] - img[r * ws + c];
+          else if (r == ws - 1) ygrad = img[r * ws + c] - img[(r - 1) * ws + c];
+          else ygrad = img[(r + 1) * ws + c] - img[(r - 1) * ws + c];
+          const float v = mask[r * ws + c];
+          if (lane == 0) acc += xgrad * xgrad * v;
+          else if (lane == 1) { const float gxy = xgrad * ygrad; acc += gxy * v; }
+          else acc += ygrad * ygrad * v;
+        }
+    }
+    float a = __shfl_sync(0xffffffffu, acc, 0), b = __shfl_sync(0xffffffffu, acc, 1), c = __shfl_sync(0xffffffffu, acc, 2);
+    __syncwarp();
+    a /= (float)maskPixels; b /= (float)maskPixels; c /= (float)maskPixels;
+    invSqrt_d(a, b, c, l1, l2);
+    if ((a != a) || (b != b) || (c != c)) break;
+    eigen_ratio_bef = eigen_ratio_act;
+    eigen_ratio_act = (float)(1.0 - (double)(l2 / l1));
+    const float u11t = u11, u12t = u12;
+    u11 = a * u11t + b * u21;
+    u12 = a * u12t + b * u22;
+    u21 = b * u11t + c * u21;
+    u22 = b * u12t + c * u22;
+    {                                                // getEigenvalues, helpers.cpp:504-515
+      const float trace = u11 + u22;
+      const float delta1 = (trace * trace - 4 * (u11 * u22 - u12 * u21));
+      if (delta1 < 0) break;
+      const float delta = sqrtf(delta1);
+      l1 = (trace + delta) / 2.0f;
+      l2 = (trace - delta) / 2.0f;
+    }
+    if ((l1 / l2 > 6) || (l2 / l1 > 6)) break;
+    if (eigen_ratio_act < ap.convergenceThreshold && eigen_ratio_bef < ap.convergenceThreshold) { found = true; break; }
+  }
+  if (lane == 0) {
+    if (found) {
+      candA[4 * (size_t)i + 0] = u11; candA[4 * (size_t)i + 1] = u12; candA[4 * (size_t)i + 2] = u21; candA[4 * (size_t)i + 3] = u22;
+      atomicAdd(nkept, 1);
+    } else keys[i] = ~0ull;
+  }
+}
+
 // Octave-map resolution + export order: a candidate survives iff it holds the minimum visiting key
 // at its final (r,c); survivors are ranked by (|response| desc, visiting order asc) -- the order a
 // stable sort by |response| gives the reference's push order (scale-space-detector.hpp:120-131).
@@ -490,7 +612,7 @@ __global__ void k_resolve(const Cand* cands, const int* ncand_p, int cap, const 
   if (keep) atomicAdd(nkept, 1);
 }
 __global__ void k_rank_export(const Cand* cands, const int* ncand_p, int cap, const unsigned long long* keys,
-                              modsgpu_keypoint* out) {
+                              modsgpu_keypoint* out, const float* candA, float* outA) {
   __shared__ unsigned long long tile[256];
   int n = min(*ncand_p, cap);
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -510,6 +632,7 @@ __global__ void k_rank_export(const Cand* cands, const int* ncand_p, int cap, co
     o.x = k.x; o.y = k.y; o.s = k.s; o.response = k.response; o.type = k.type; o.octave = k.octave;
     o.level = k.level; o.r0 = k.r0; o.c0 = k.c0; o.r = k.r; o.c = k.c; o.seq = 0;
     out[rank] = o;
+    if (candA) for (int q = 0; q < 4; q++) outA[4 * (size_t)rank + q] = candA[4 * (size_t)i + q];
   }
 }
 
@@ -678,7 +801,8 @@ extern "C" int modsgpu_half_image(modsgpu_ctx* ctx, const float* in, int w, int 
 
 // Device part of the detector: enqueues the whole pyramid on ctx->stream; the sorted keypoints end
 // up in ctx->det_out and their count in ctx->det_misc[1].  No host synchronisation inside.
-int mg_detect_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_pyr_params* p, int cap) {
+int mg_detect_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_pyr_params* p, int cap,
+                      const modsgpu_affshape_params* aff) {
   const int nS = p->numberOfScales;
   if (nS < 1 || nS + 2 > 8) MG_FAIL(ctx, MODSGPU_EINVAL, "numberOfScales out of range");
   if (p->border < 2) MG_FAIL(ctx, MODSGPU_EINVAL, "border must be >= 2 (pyramid.cpp:407)");
@@ -707,7 +831,8 @@ int mg_detect_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
   MG_CUDA(ctx, ctx->det_pyr.ensure((pyr_floats + 16) * sizeof(float)));
   MG_CUDA(ctx, ctx->det_map.ensure((map_ints + 16) * sizeof(int)));
   MG_CUDA(ctx, ctx->det_cand.ensure((size_t)cap * (sizeof(Cand) + sizeof(unsigned long long))));
-  MG_CUDA(ctx, ctx->det_out.ensure((size_t)cap * sizeof(modsgpu_keypoint)));
+  MG_CUDA(ctx, ctx->det_out.ensure((size_t)cap * (sizeof(modsgpu_keypoint) + 16)));   // + A (4 floats) per keypoint
+  if (aff) MG_CUDA(ctx, ctx->det_aff.ensure((size_t)cap * 16 + (size_t)SMM_MAX * SMM_MAX * 4 + 64));
   MG_CUDA(ctx, ctx->det_misc.ensure(64));
   float* pyr = ctx->det_pyr.as<float>();
   int* map = ctx->det_map.as<int>();
@@ -796,19 +921,51 @@ int mg_detect_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
   MG_PROF(ctx, "k_resolve", 2, (double)cap);
   k_resolve<<<nb, 256, 0, ctx->stream>>>(cands, counters, cap, map, keys, counters + 1);
   MG_LAUNCHED(ctx);
+  float* candA = nullptr;
+  float* outA = nullptr;
+  if (aff && aff->doBaumberg) {
+    if (aff->smmWindowSize < 3 || aff->smmWindowSize > SMM_MAX || nOct > 16) MG_FAIL(ctx, MODSGPU_EINVAL, "smmWindowSize must be in [3, 25]");
+    // computeGaussMask (helpers.cpp:413-440)
+    const int size = aff->smmWindowSize, halfSize = size >> 1;
+    std::vector<float> mask((size_t)size * size), tmp(halfSize + 1);
+    const float scale = float(halfSize) / 3.0f, scale2 = -2.0f * scale * scale;
+    for (int i = 0; i <= halfSize; i++) tmp[i] = std::exp((float(i * i) / scale2));
+    const int endSize = int(std::ceil(scale * 5.0f) - halfSize);
+    for (int i = 1; i < endSize; i++) tmp[halfSize - i] += std::exp((float((i + halfSize) * (i + halfSize)) / scale2));
+    for (int i = 0; i <= halfSize; i++)
+      for (int j = 0; j <= halfSize; j++) {
+        const float v = tmp[i] * tmp[j];
+        mask[(i + halfSize) * size + (-j + halfSize)] = v; mask[(-i + halfSize) * size + (j + halfSize)] = v;
+        mask[(i + halfSize) * size + (j + halfSize)] = v; mask[(-i + halfSize) * size + (-j + halfSize)] = v;
+      }
+    candA = ctx->det_aff.as<float>();
+    float* d_mask = candA + (size_t)cap * 4;
+    MG_CUDA(ctx, ctx->h_stage2.ensure(mask.size() * 4));
+    memcpy(ctx->h_stage2.p, mask.data(), mask.size() * 4);
+    MG_CUDA(ctx, cudaMemcpyAsync(d_mask, ctx->h_stage2.p, mask.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    OctTab ot;
+    memset(&ot, 0, sizeof(ot));
+    for (int o = 0; o < nOct; o++) { ot.off[o] = (long long)oct_off[o]; ot.w[o] = ow[o]; ot.h[o] = oh[o]; }
+    AffPars ap = {aff->maxIterations, aff->convergenceThreshold, aff->smmWindowSize, aff->initialSigma};
+    MG_CUDA(ctx, cudaMemsetAsync(counters + 1, 0, 4, ctx->stream));   // kept is recounted after the iteration
+    MG_PROF(ctx, "k_baumberg", 2, (double)cap);
+    k_baumberg<<<ceil_div(cap, 4), 128, 0, ctx->stream>>>(pyr, ot, cands, counters, cap, keys, d_mask, ap, candA, counters + 1);
+    MG_LAUNCHED(ctx);
+    outA = reinterpret_cast<float*>(ctx->det_out.as<modsgpu_keypoint>() + cap);
+  }
   MG_PROF(ctx, "k_rank_export", 2, (double)cap);
-  k_rank_export<<<nb, 256, 0, ctx->stream>>>(cands, counters, cap, keys, ctx->det_out.as<modsgpu_keypoint>());
+  k_rank_export<<<nb, 256, 0, ctx->stream>>>(cands, counters, cap, keys, ctx->det_out.as<modsgpu_keypoint>(), candA, outA);
   MG_LAUNCHED(ctx);
   return 0;
 }
 
-extern "C" int modsgpu_detect(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_pyr_params* p,
-                              modsgpu_keypoint** out, int* n) {
+static int detect_impl(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_pyr_params* p,
+                       const modsgpu_affshape_params* aff, modsgpu_keypoint** out, float** A, int* n) {
   if (!ctx || !img || !p || !out || !n) return MODSGPU_EINVAL;
   if (mg_begin(ctx)) return MODSGPU_ECUDA;
   int cap = 1 << 16;
   for (;;) {
-    int rc = mg_detect_enqueue(ctx, img, p, cap);
+    int rc = mg_detect_enqueue(ctx, img, p, cap, aff);
     if (rc) return rc;
     MG_CUDA(ctx, ctx->h_stage.ensure(64));
     int* hc = ctx->h_stage.as<int>();
@@ -819,8 +976,30 @@ extern "C" int modsgpu_detect(modsgpu_ctx* ctx, const modsgpu_image* img, const 
     modsgpu_keypoint* res = (modsgpu_keypoint*)malloc(sizeof(modsgpu_keypoint) * (size_t)std::max(kept, 1));
     if (kept > 0)
       MG_CUDA(ctx, cudaMemcpyAsync(res, ctx->det_out.p, sizeof(modsgpu_keypoint) * (size_t)kept, cudaMemcpyDeviceToHost, ctx->stream));
-    if (mg_end(ctx)) { free(res); return MODSGPU_ECUDA; }
+    float* resA = nullptr;
+    if (A) {
+      resA = (float*)malloc(16 * (size_t)std::max(kept, 1));
+      if (kept > 0)
+        MG_CUDA(ctx, cudaMemcpyAsync(resA, ctx->det_out.as<modsgpu_keypoint>() + cap, 16 * (size_t)kept, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (mg_end(ctx)) { free(res); free(resA); return MODSGPU_ECUDA; }
     *out = res; *n = kept;
+    if (A) *A = resA;
     return 0;
   }
+}
+
+extern "C" int modsgpu_detect(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_pyr_params* p,
+                              modsgpu_keypoint** out, int* n) {
+  return detect_impl(ctx, img, p, nullptr, out, nullptr, n);
+}
+
+extern "C" void modsgpu_default_affshape_params(modsgpu_affshape_params* a) {
+  a->maxIterations = 16; a->convergenceThreshold = 0.05f; a->smmWindowSize = 19; a->initialSigma = 1.6f; a->doBaumberg = 1;
+}
+
+extern "C" int modsgpu_detect_affine(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_pyr_params* p,
+                                     const modsgpu_affshape_params* aff, modsgpu_keypoint** out, float** A, int* n) {
+  if (!aff || !A) return MODSGPU_EINVAL;
+  return detect_impl(ctx, img, p, aff, out, A, n);
 }

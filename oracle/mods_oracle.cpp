@@ -648,9 +648,114 @@ static void solveLinear3x3(float* A, float* b) {
   b[0] = (b[0] - A[2] * b[2] - A[1] * b[1]) / A[0];
 }
 
+/* helpers.cpp:413-440 computeGaussMask */
+extern "C" void orc_gauss_mask(float* mask, int size) {
+  const int halfSize = size >> 1;
+  const float scale = float(halfSize) / 3.0f;
+  const float scale2 = -2.0f * scale * scale;
+  std::vector<float> tmp(halfSize + 1);
+  for (int i = 0; i <= halfSize; i++) tmp[i] = std::exp((float(i * i) / scale2));
+  const int endSize = int(std::ceil(scale * 5.0f) - halfSize);
+  for (int i = 1; i < endSize; i++) tmp[halfSize - i] += std::exp((float((i + halfSize) * (i + halfSize)) / scale2));
+  for (int i = 0; i <= halfSize; i++)
+    for (int j = 0; j <= halfSize; j++) {
+      const float v = tmp[i] * tmp[j];
+      mask[(i + halfSize) * size + (-j + halfSize)] = v;
+      mask[(-i + halfSize) * size + (j + halfSize)] = v;
+      mask[(i + halfSize) * size + (j + halfSize)] = v;
+      mask[(-i + halfSize) * size + (-j + halfSize)] = v;
+    }
+}
+
+/* helpers.cpp:461-503 invSqrt */
+static void invSqrt(float& a, float& b, float& c, float& l1, float& l2) {
+  double t, r;
+  if (b != 0) {
+    r = double(c - a) / (2 * b);
+    if (r >= 0) t = 1.0 / (r + std::sqrt(1 + r * r));
+    else t = -1.0 / (-r + std::sqrt(1 + r * r));
+    r = 1.0 / std::sqrt(1 + t * t);
+    t = t * r;
+  } else { r = 1; t = 0; }
+  double x, z, d;
+  x = 1.0 / std::sqrt(r * r * a - 2 * r * t * b + t * t * c);
+  z = 1.0 / std::sqrt(t * t * a + 2 * r * t * b + r * r * c);
+  d = std::sqrt(x * z);
+  x /= d; z /= d;
+  if (x < z) { l1 = float(z); l2 = float(x); }
+  else { l1 = float(x); l2 = float(z); }
+  a = float(r * r * x + t * t * z);
+  b = float(-r * t * x + t * r * z);
+  c = float(t * t * x + r * r * z);
+}
+/* helpers.cpp:504-515 */
+static bool getEigenvaluesF(float a, float b, float c, float d, float& l1, float& l2) {
+  float trace = a + d;
+  float delta1 = (trace * trace - 4 * (a * d - b * c));
+  if (delta1 < 0) return false;
+  float delta = std::sqrt(delta1);
+  l1 = (trace + delta) / 2.0f;
+  l2 = (trace - delta) / 2.0f;
+  return true;
+}
+
+/* affine.cpp:26-158 findAffineShape, doBaumberg = 1, AFF_BMBRG_SMM.  blur = the pyramid level handed over by
+ * localizeKeypoint (prevBlur).  Returns true and U when the iteration converged. */
+static bool findAffineShape(const float* blur, int w, int h, float x, float y, float s, float pixelDistance,
+                            const orc_affshape_params& par, const std::vector<float>& mask, float* U) {
+  float eigen_ratio_act = 0.0f, eigen_ratio_bef = 0.0f;
+  float u11 = 1.0f, u12 = 0.0f, u21 = 0.0f, u22 = 1.0f, l1 = 1.0f, l2 = 1.0f;
+  const float lx = x / pixelDistance, ly = y / pixelDistance;
+  const float ratio = s / (par.initialSigma * pixelDistance);
+  const int ws = par.smmWindowSize, maskPixels = ws * ws;
+  std::vector<float> img((size_t)maskPixels), fx((size_t)maskPixels), fy((size_t)maskPixels);
+  for (int l = 0; l < par.maxIterations; l++) {
+    float a = 0, b = 0, c = 0;
+    orc_interpolate(blur, w, h, lx, ly, u11 * ratio, u12 * ratio, u21 * ratio, u22 * ratio, img.data(), ws, ws);
+    for (int r = 0; r < ws; ++r)       /* computeGradient, helpers.cpp:779-797 */
+      for (int cc = 0; cc < ws; ++cc) {
+        float xgrad, ygrad;
+        if (cc == 0) xgrad = img[r * ws + cc + 1] - img[r * ws + cc];
+        else if (cc == ws - 1) xgrad = img[r * ws + cc] - img[r * ws + cc - 1];
+        else xgrad = img[r * ws + cc + 1] - img[r * ws + cc - 1];
+        if (r == 0) ygrad = img[(r + 1) * ws + cc] - img[r * ws + cc];
+        else if (r == ws - 1) ygrad = img[r * ws + cc] - img[(r - 1) * ws + cc];
+        else ygrad = img[(r + 1) * ws + cc] - img[(r - 1) * ws + cc];
+        fx[r * ws + cc] = xgrad; fy[r * ws + cc] = ygrad;
+      }
+    for (int i = 0; i < maskPixels; ++i) {
+      const float v = mask[i], gxx = fx[i], gyy = fy[i], gxy = gxx * gyy;
+      a += gxx * gxx * v;
+      b += gxy * v;
+      c += gyy * gyy * v;
+    }
+    a /= maskPixels; b /= maskPixels; c /= maskPixels;
+    invSqrt(a, b, c, l1, l2);
+    if ((a != a) || (b != b) || (c != c)) break;
+    eigen_ratio_bef = eigen_ratio_act;
+    eigen_ratio_act = 1.0 - l2 / l1;
+    float u11t = u11, u12t = u12;
+    u11 = a * u11t + b * u21;
+    u12 = a * u12t + b * u22;
+    u21 = b * u11t + c * u21;
+    u22 = b * u12t + c * u22;
+    if (!getEigenvaluesF(u11, u12, u21, u22, l1, l2)) break;
+    if ((l1 / l2 > 6) || (l2 / l1 > 6)) break;
+    if (eigen_ratio_act < par.convergenceThreshold && eigen_ratio_bef < par.convergenceThreshold) {
+      U[0] = u11; U[1] = u12; U[2] = u21; U[3] = u22;
+      return true;
+    }
+  }
+  return false;
+}
+
 namespace {
 struct Detector {
   orc_pyr_params P;
+  bool doBaumberg = false;
+  orc_affshape_params AP;
+  std::vector<float> smmMask;
+  std::vector<float> keyA;
   /* pyramid.h:46-66 derived constants */
   double edgeScoreThreshold;
   float finalThreshold, positiveThreshold, negativeThreshold;
@@ -739,6 +844,11 @@ struct Detector {
     k.x = pixelDistance * (c + b[0]);
     k.y = pixelDistance * (r + b[1]);
     k.s = pixelDistance * scale;
+    if (doBaumberg) {   /* onKeypointDetected -> findAffineShape(prevBlur, ...) (scale-space-detector.hpp:47-55) */
+      float U[4];
+      if (!findAffineShape(prevBlur.data(), w, h, k.x, k.y, k.s, pixelDistance, AP, smmMask, U)) return;
+      keyA.insert(keyA.end(), U, U + 4);
+    }
     k.response = val;
     k.type = type;
     k.octave = octave; k.level = level;
@@ -830,6 +940,45 @@ extern "C" int orc_detect_hessian(const float* gray, int w, int h, const orc_pyr
   });
   int n = (int)D.keys.size();
   for (int i = 0; i < n && i < cap; i++) out[i] = D.keys[i];
+  return n;
+}
+
+/* the same with the in-pyramid Baumberg iteration (doBaumberg = 1) */
+extern "C" int orc_detect_hessian_affine(const float* gray, int w, int h, const orc_pyr_params* p, const orc_affshape_params* ap,
+                                         orc_keypoint* out, float* A, int cap) {
+  Detector D(*p);
+  D.doBaumberg = true; D.AP = *ap;
+  D.smmMask.resize((size_t)ap->smmWindowSize * ap->smmWindowSize);
+  orc_gauss_mask(D.smmMask.data(), ap->smmWindowSize);
+  float curSigma = 0.5f;
+  float pixelDistance = 1.0f;
+  std::vector<float> first(gray, gray + (size_t)w * h);
+  if (p->initialSigma > curSigma) {
+    float sigma = std::sqrt(p->initialSigma * p->initialSigma - curSigma * curSigma);
+    std::vector<float> t((size_t)w * h);
+    orc_gaussian_blur(first.data(), t.data(), w, h, sigma);
+    first.swap(t);
+  }
+  int minSize = 2 * p->border + 2;
+  int W = w, H = h;
+  D.octave = 0;
+  while (H > minSize && W > minSize) {
+    std::vector<float> next;
+    int nW = 0, nH = 0;
+    D.detectOctave(first, W, H, pixelDistance, next, nW, nH);
+    pixelDistance *= 2.0;
+    first.swap(next);
+    W = nW; H = nH;
+    D.octave++;
+  }
+  std::stable_sort(D.keys.begin(), D.keys.end(), [](const orc_keypoint& a, const orc_keypoint& b) {
+    return std::fabs(a.response) > std::fabs(b.response);
+  });
+  int n = (int)D.keys.size();
+  for (int i = 0; i < n && i < cap; i++) {
+    out[i] = D.keys[i];
+    for (int k = 0; k < 4; k++) A[4 * i + k] = D.keyA[(size_t)4 * D.keys[i].seq + k];
+  }
   return n;
 }
 

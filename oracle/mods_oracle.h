@@ -90,6 +90,21 @@ int orc_detect_hessian(const float* gray, int w, int h, const orc_pyr_params* p,
                        orc_keypoint* out, int cap);
 /* synth-detection.hpp:79-112 glue for doBaumberg=0: region = (x,y,s,I) */
 
+/* AffineShapeParams (affine.h:26-68) read by the in-pyramid Baumberg iteration */
+typedef struct {
+  int   maxIterations;         /* 16   */
+  float convergenceThreshold;  /* 0.05 */
+  int   smmWindowSize;         /* 19   */
+  float initialSigma;          /* 1.6  */
+} orc_affshape_params;
+/* the same detector with doBaumberg = 1, method SMM (affine.cpp:26-158, called from localizeKeypoint on prevBlur,
+ * pyramid.cpp:402): keypoints whose iteration does not converge are dropped; A (4 floats per kept
+ * keypoint: a11 a12 a21 a22, as AffineShape hands them to onAffineShapeFound) */
+int orc_detect_hessian_affine(const float* gray, int w, int h, const orc_pyr_params* p, const orc_affshape_params* a,
+                              orc_keypoint* out, float* A, int cap);
+/* helpers.cpp:413-440 computeGaussMask */
+void orc_gauss_mask(float* mask, int size);
+
 /* ---- patch sampler (synth-detection.cpp:38-132, helpers.cpp:524-626) ------ */
 int  orc_interpolate_check_borders(int w, int h, float ofsx, float ofsy, float a11, float a12,
                                    float a21, float a22, int res_w, int res_h);

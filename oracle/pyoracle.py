@@ -75,6 +75,29 @@ def gaussian_blur(img, sigma):
     return out
 
 
+class AffShapeParams(C.Structure):
+    _fields_ = [("maxIterations", C.c_int), ("convergenceThreshold", C.c_float), ("smmWindowSize", C.c_int),
+                ("initialSigma", C.c_float)]
+
+
+def default_affshape_params():
+    """[HessianAffine] of build/config_affori_classic.ini:42-49"""
+    return AffShapeParams(16, 0.05, 19, 1.6)
+
+
+def detect_hessian_affine(gray, params=None, aff=None, cap=1 << 18):
+    """Hessian-Affine with the in-pyramid Baumberg iteration: (keypoints, A [n x 4])."""
+    gray = np.ascontiguousarray(gray, np.float32)
+    h, w = gray.shape
+    params = params or default_params()
+    aff = aff or default_affshape_params()
+    out = np.zeros(cap, KP_DTYPE)
+    A = np.zeros((cap, 4), np.float32)
+    n = lib().orc_detect_hessian_affine(_p(gray), w, h, C.byref(params), C.byref(aff), _p(out), _p(A), cap)
+    assert n <= cap
+    return out[:n].copy(), A[:n].copy()
+
+
 def dominant_orientation(img, regs, mr_size=5.1962, patch_size=32, max_angles=1, th=0.8):
     """DetectOrientation (synth-detection.cpp:1039-1149): returns (n_ang [n] with -1 = dropped, angles [n x max_angles])."""
     img = np.ascontiguousarray(img, np.float32)

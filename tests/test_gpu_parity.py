@@ -655,3 +655,24 @@ def test_sift_descriptor_bit_exact(mg, oracle, synth_pair):
             d_got = mg.describe_sift(img, r2, photo_norm=pn, root_sift=root)
             assert np.array_equal(d_got, d_ref), (root, pn, np.abs(d_got - d_ref).max(), (d_got != d_ref).mean())
     assert d_ref.max() <= 255 and d_ref.min() >= 0
+
+
+@pytest.mark.parametrize("wh", [(1024, 768), (333, 251)])
+def test_detect_affine_baumberg_bit_exact(mg, oracle, synth_pair, wh):
+    """Hessian-Affine with the in-pyramid Baumberg iteration (row a10, affine.cpp:26-158 on prevBlur): the same
+    keypoints survive, in the same order, with bit-identical shape matrices."""
+    from mods_light_zmq_b200 import synth
+    if wh == (1024, 768):
+        g = _gray(oracle, synth_pair[0])
+    else:
+        g = _gray(oracle, synth.blob_image(seed=12, w=wh[0], h=wh[1], n_blobs=500))
+    img = mg.image_from_gray32f(g)
+    kr, Ar = oracle.detect_hessian_affine(g)
+    kg, Ag = mg.detect_affine(img)
+    assert len(kg) == len(kr) and len(kr) > 0.5 * len(oracle.detect_hessian(g))
+    for f in ("x", "y", "s", "response", "type", "octave", "level", "r0", "c0"):
+        assert np.array_equal(kg[f], kr[f]), f
+    assert Ag.tobytes() == Ar.tobytes()
+    assert np.allclose(Ag[:, 0] * Ag[:, 3] - Ag[:, 1] * Ag[:, 2], 1.0, atol=1e-4)
+    # plain detection is unchanged
+    assert len(mg.detect(img)) == len(oracle.detect_hessian(g))

@@ -99,14 +99,17 @@ def test_reference_degensac_F_fixture(oracle):
     mask = z["mask"]
     # NB the reference reads uninitialised heap in exp_ransacFcustom (errs[4] = errs[3] before any write,
     # exp_ranF.c:870-872; data_out histogram :1029): with time() pinned its result still differs between the
-    # first and later calls of one process and between processes (I = 116..172 observed on this fixture, 170 true
-    # inliers).  So the fixture pins a band, not a value.
-    for _ in range(2):
+    # first and later calls of one process and between processes (I = 81..172 observed on this fixture, 170 true
+    # inliers).  So the fixture pins a band over several calls, not a value.
+    best = 0
+    for _ in range(5):
         r = oracle.ref_ransac_F(z["u"], th=16.0, seed_time=12345)
-        assert 0.6 * mask.sum() <= r["I"] <= int(mask.sum()) + 8, r["I"]
+        assert r["I"] <= int(mask.sum()) + 8, r["I"]
         d = oracle.sampson_F(r["F"], z["u"])
-        assert ((d <= 16.0) == r["inl"].astype(bool)).mean() > 0.97
-        assert (r["inl"].astype(bool) & mask).sum() >= 0.6 * mask.sum()
+        assert ((d <= 16.0) == r["inl"].astype(bool)).mean() > 0.9
+        assert (r["inl"].astype(bool) & mask).sum() >= 0.3 * mask.sum()      # I = 81 has been observed
+        best = max(best, int((r["inl"].astype(bool) & mask).sum()))
+    assert best >= 0.3 * mask.sum()      # a whole process can stay in the weak state, so no tighter bound holds
     d = oracle.sampson_F(z["F"], z["u"])
     assert np.array_equal(d <= 16.0, z["inl"].astype(bool)) and int(z["I"]) == int(z["inl"].sum())
     # the seeded scene's true F explains its inliers (checks sampson_F's layout convention too)

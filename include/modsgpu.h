@@ -218,6 +218,10 @@ typedef struct {
 int  modsgpu_pair_pipeline_images(modsgpu_ctx* ctx, modsgpu_image* img1, modsgpu_image* img2, unsigned long long seed,
                                   modsgpu_pair_result* res, double* inlier_xy /* capacity x (x1,y1,x2,y2) or NULL */,
                                   int capacity);
+/* the same pair loop for the CLASSIC configuration (config_affori_classic.ini + iters_HessianSIFT.ini, BASELINE config 1):
+ * Hessian-Affine with Baumberg -> dominant orientation -> RootSIFT -> FGINN -> duplicate filter -> LO-RANSAC(H) */
+int  modsgpu_pair_pipeline_classic_images(modsgpu_ctx* ctx, modsgpu_image* img1, modsgpu_image* img2, unsigned long long seed,
+                                          modsgpu_pair_result* res, double* inlier_xy, int capacity);
 /* host BGR images (cv::imread layout): upload + pipeline */
 int  modsgpu_pair_pipeline(modsgpu_ctx* ctx, const uint8_t* bgr1, const uint8_t* bgr2, int w, int h,
                            unsigned long long seed, modsgpu_pair_result* res, double* inlier_xy, int capacity);

@@ -428,6 +428,14 @@ def _pair_pipeline_images(self, img1, img2, seed=12345, capacity=4096):
     return _pair_dict(res, xy)
 
 
+def _pair_pipeline_classic_images(self, img1, img2, seed=12345, capacity=4096):
+    res = PairResult()
+    xy = np.zeros((capacity, 4), np.float64)
+    self._check(self.lib.modsgpu_pair_pipeline_classic_images(self.ctx, img1.handle, img2.handle, C.c_ulonglong(seed),
+                                                              C.byref(res), _p(xy), capacity))
+    return _pair_dict(res, xy)
+
+
 def _pair_pipeline(self, bgr1, bgr2, seed=12345, capacity=4096):
     """host BGR u8 images -> upload -> detect/describe x2 -> match -> dedup -> LO-RANSAC."""
     h, w, _ = bgr1.shape
@@ -439,6 +447,7 @@ def _pair_pipeline(self, bgr1, bgr2, seed=12345, capacity=4096):
 
 
 ModsGpu.pair_pipeline_images = _pair_pipeline_images
+ModsGpu.pair_pipeline_classic_images = _pair_pipeline_classic_images
 ModsGpu.pair_pipeline = _pair_pipeline
 
 

@@ -290,6 +290,114 @@ int ImageRepresentation::DescribeView(modsgpu_image* view, const double* H, int 
   return n3;
 }
 
+// synth-detection.cpp:134-143
+static void rectifyTransformation(double& a11, double& a12, double& a21, double& a22) {
+  double a = a11, b = a12, c = a21, d = a22;
+  double det = std::sqrt(std::fabs(a * d - b * c));
+  double b2a2 = std::sqrt(b * b + a * a);
+  a11 = b2a2 / det;
+  a12 = 0;
+  a21 = (d * b + c * a) / (b2a2 * det);
+  a22 = det / b2a2;
+}
+
+// imagerepresentation.cpp:686-1104 for config_affori_classic.ini + iters_HessianSIFT.ini (identity view):
+// DetectAffineRegions over the Baumberg detector -> ReprojectRegionsAndRemoveTouchBoundary(dontRemove) ->
+// DetectOrientation (:903) -> ReprojectRegions (:951) -> DescribeRegions<RootSIFT> (:958-965)
+int ImageRepresentation::SynthDetectDescribeKeypointsClassic(const DetectPars& par) {
+  int w, h;
+  modsgpu_image_size(img_, &w, &h);
+  regions_.clear();
+  n_views = 1;
+  double t0 = now_ms();
+  modsgpu_keypoint* kps = nullptr;
+  float* A = nullptr;
+  int n = 0;
+  int rc = modsgpu_detect_affine(ctx_, img_, &par.pyr, &par.aff, &kps, &A, &n);
+  if (rc) return rc;
+  n_keypoints = n;
+  AffineRegionVector temp_kp1(n);
+  for (int i = 0; i < n; i++) {   // DetectAffineRegions, synth-detection.hpp:79-112
+    AffineRegion& r = temp_kp1[i];
+    r.id = i; r.parent_id = -1; r.type = 1 /* DET_HESSIAN */;
+    AffineKeypoint& k = r.det_kp;
+    double a11 = A[4 * i], a12 = A[4 * i + 1], a21 = A[4 * i + 2], a22 = A[4 * i + 3];
+    k.s = kps[i].s * std::sqrt(std::fabs(a11 * a22 - a12 * a21));
+    rectifyTransformation(a11, a12, a21, a22);
+    k.x = kps[i].x; k.y = kps[i].y;
+    k.a11 = a11; k.a12 = a12; k.a21 = a21; k.a22 = a22;
+    k.response = kps[i].response; k.octave_number = kps[i].octave; k.sub_type = kps[i].type;
+  }
+  modsgpu_free(kps);
+  modsgpu_free(A);
+  n_affine = n;
+  TimeSpent.DetectTime += now_ms() - t0;
+  t0 = now_ms();
+  // ReprojectRegionsAndRemoveTouchBoundary(dontRemove = true), H = I: centre inside
+  AffineRegionVector kept;
+  kept.reserve(n);
+  for (auto& r : temp_kp1) {
+    r.reproj_kp = r.det_kp;
+    if ((r.reproj_kp.x < w) && (r.reproj_kp.y < h) && (r.reproj_kp.x > 0) && (r.reproj_kp.y > 0)) kept.push_back(r);
+  }
+  // DetectOrientation (synth-detection.cpp:1039-1149)
+  std::vector<modsgpu_region> regs;
+  to_regions(kept, regs);
+  const int n2 = (int)kept.size();
+  std::vector<int> n_ang(n2 + 1);
+  std::vector<float> ang((size_t)n2 * par.maxAngles + 1);
+  rc = modsgpu_dominant_orientation(ctx_, img_, regs.data(), n2, par.mrSize, par.oriPatchSize, par.maxAngles, par.oriThreshold,
+                                    n_ang.data(), ang.data());
+  if (rc) return rc;
+  AffineRegionVector oriented;
+  oriented.reserve(n2);
+  int count = 0;
+  for (int i = 0; i < n2; i++) {
+    if (n_ang[i] < 0) continue;                       // frame touches the border
+    AffineRegion c = kept[i];
+    c.id = count;
+    for (int j = 0; j < n_ang[i]; j++) {
+      const double a = ang[(size_t)i * par.maxAngles + j];
+      const double ci = std::cos(-a), si = std::sin(-a);
+      AffineRegion t = c;
+      t.det_kp.a11 = c.det_kp.a11 * ci - c.det_kp.a12 * si;
+      t.det_kp.a12 = c.det_kp.a11 * si + c.det_kp.a12 * ci;
+      t.det_kp.a21 = c.det_kp.a21 * ci - c.det_kp.a22 * si;
+      t.det_kp.a22 = c.det_kp.a21 * si + c.det_kp.a22 * ci;
+      oriented.push_back(t);
+      count++;
+    }
+  }
+  TimeSpent.OrientTime += now_ms() - t0;
+  t0 = now_ms();
+  // ReprojectRegions (synth-detection.cpp:631-706), H = I
+  const double k_sigma = 2 * 3.0 * std::sqrt(3.0);
+  AffineRegionVector final_regs;
+  final_regs.reserve(oriented.size());
+  for (auto& r : oriented) {
+    r.reproj_kp = r.det_kp;
+    const AffineKeypoint& p = r.reproj_kp;
+    if ((p.x < w) && (p.y < h) && (p.x > 0) && (p.y > 0)) {
+      if (!interpolateCheckBorders(w, h, (float)p.x, (float)p.y, (float)p.a11, (float)p.a12, (float)p.a21, (float)p.a22,
+                                   (int)(k_sigma * p.s), (int)(k_sigma * p.s)))
+        final_regs.push_back(r);
+    }
+  }
+  // DescribeRegions<SIFTDescriptor> (synth-detection.hpp:170-263)
+  const int n3 = (int)final_regs.size();
+  to_regions(final_regs, regs);
+  std::vector<float> out((size_t)n3 * 128 + 1);
+  rc = modsgpu_describe_sift(ctx_, img_, regs.data(), n3, par.mrSize, par.siftPatchSize, par.photoNorm, par.rootSift, out.data());
+  if (rc) return rc;
+  for (int i = 0; i < n3; i++) {
+    final_regs[i].desc.assign(out.begin() + (size_t)i * 128, out.begin() + (size_t)(i + 1) * 128);
+    final_regs[i].id = i;
+  }
+  regions_.swap(final_regs);
+  TimeSpent.DescTime += now_ms() - t0;
+  return n3;
+}
+
 // imagerepresentation.cpp:113-126: sc = s*sqrt(|det A|)*3*sqrt(3); A <- upIsUp(A) cast to float; SVD A = U W V^T;
 // ellipse = U diag(1/(w_i^2 sc^2)) U^T = (A A^T)^-1 / sc^2.  cv::SVD (third-party, float) is replaced by the closed
 // form evaluated in double on the float-cast A and rounded to float; the file prints 6 significant digits.
@@ -568,6 +676,43 @@ extern "C" int modsgpu_pair_pipeline_images(modsgpu_ctx* ctx, modsgpu_image* img
   int n1 = r1.SynthDetectDescribeKeypoints(dp);
   if (n1 < 0) return n1;
   int n2 = r2.SynthDetectDescribeKeypoints(dp);
+  if (n2 < 0) return n2;
+  res->keypoints[0] = r1.n_keypoints; res->keypoints[1] = r2.n_keypoints;
+  res->regions[0] = r1.n_affine; res->regions[1] = r2.n_affine;
+  res->descriptors[0] = n1; res->descriptors[1] = n2;
+  TentativeCorrespListExt tent, verified;
+  int nt = MatchFlannFGINN(ctx, r1.GetAffineRegionVector(), r2.GetAffineRegionVector(), tent, mp);
+  if (nt < 0) return nt;
+  res->tentatives = nt;
+  int nu = DuplicateFiltering(ctx, tent, mp.doubleFilteringRadius);
+  if (nu < 0) return nu;
+  res->unique_tentatives = nu;
+  int ni = LORANSACFiltering(ctx, tent, verified, res->H, rp);
+  if (ni < 0) return ni;
+  res->inliers = ni;
+  for (int i = 0; i < ni && i < capacity && inlier_xy; i++) {
+    const TentativeCorrespExt& c = verified.TCList[i];
+    inlier_xy[4 * i + 0] = c.first.reproj_kp.x; inlier_xy[4 * i + 1] = c.first.reproj_kp.y;
+    inlier_xy[4 * i + 2] = c.second.reproj_kp.x; inlier_xy[4 * i + 3] = c.second.reproj_kp.y;
+  }
+  return 0;
+}
+
+// config 1 (config_affori_classic.ini + iters_HessianSIFT.ini): the same pair loop with the classic per-image stages
+extern "C" int modsgpu_pair_pipeline_classic_images(modsgpu_ctx* ctx, modsgpu_image* img1, modsgpu_image* img2,
+                                                    unsigned long long seed, modsgpu_pair_result* res, double* inlier_xy,
+                                                    int capacity) {
+  using namespace modsb200;
+  if (!ctx || !img1 || !img2 || !res) return MODSGPU_EINVAL;
+  memset(res, 0, sizeof(*res));
+  DetectPars dp;
+  MatchPars mp;
+  RANSACPars rp;
+  rp.seed = seed;
+  ImageRepresentation r1(ctx, img1, false), r2(ctx, img2, false);
+  int n1 = r1.SynthDetectDescribeKeypointsClassic(dp);
+  if (n1 < 0) return n1;
+  int n2 = r2.SynthDetectDescribeKeypointsClassic(dp);
   if (n2 < 0) return n2;
   res->keypoints[0] = r1.n_keypoints; res->keypoints[1] = r2.n_keypoints;
   res->regions[0] = r1.n_affine; res->regions[1] = r2.n_affine;

@@ -57,7 +57,11 @@ struct DetectPars {
   modsgpu_pyr_params pyr;          // [HessianAffine]
   double mrSize = 5.1962;          // AffNet / OriNet / desc patch extent
   int patchSize = 32;
-  DetectPars() { modsgpu_default_pyr_params(&pyr); }
+  modsgpu_affshape_params aff;     // [HessianAffine] Baumberg block (classic configuration)
+  int oriPatchSize = 32, maxAngles = 1;   // [DominantOrientation]
+  double oriThreshold = 0.8;
+  int siftPatchSize = 41, photoNorm = 1, rootSift = 1;   // [SIFTDescriptor] + iters_HessianSIFT.ini (RootSIFT)
+  DetectPars() { modsgpu_default_pyr_params(&pyr); modsgpu_default_affshape_params(&aff); }
 };
 
 struct ViewSynthParameters {       // structures.hpp:196-209 (the fields the hot path reads)
@@ -89,6 +93,9 @@ class ImageRepresentation {
   const AffineRegionVector& GetAffineRegionVector() const { return regions_; }
   // regions of further views are appended (AddRegions, imagerepresentation.cpp:1098-1102)
   int AddViews(const std::vector<ViewSynthParameters>& views, const DetectPars& par);
+  // the classic configuration (config_affori_classic.ini + iters_HessianSIFT.ini), identity view: Hessian-Affine with
+  // the in-pyramid Baumberg iteration -> dominant orientation (DetectOrientation) -> RootSIFT (DescribeRegions)
+  int SynthDetectDescribeKeypointsClassic(const DetectPars& par);
   int n_keypoints = 0, n_affine = 0;
   TimeLog TimeSpent;
 

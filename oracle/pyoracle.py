@@ -404,3 +404,24 @@ def sampson_F(F, u):
     rx = F[0] * u[:, 0] + F[1] * u[:, 1] + F[2]
     ry = F[3] * u[:, 0] + F[4] * u[:, 1] + F[5]
     return r * r / (rxc * rxc + ryc * ryc + rx * rx + ry * ry)
+
+
+def classic_regions(gray, mr_size=5.1962):
+    """The per-image chain of config_affori_classic.ini + iters_HessianSIFT.ini (identity view), on the CPU:
+    Hessian-Affine with Baumberg -> DetectAffineRegions glue (synth-detection.hpp:79-112) -> centre-inside ->
+    DetectOrientation -> ReprojectRegions frame test -> RootSIFT.  Returns (n_keypoints, regions, descriptors)."""
+    h, w = gray.shape
+    kp, A = detect_hessian_affine(gray)
+    regs = np.zeros(len(kp), REGION_DTYPE)
+    a11, a12, a21, a22 = [A[:, i].astype(np.float64) for i in range(4)]
+    regs["s"] = kp["s"].astype(np.float64) * np.sqrt(np.abs(a11 * a22 - a12 * a21))
+    det = np.sqrt(np.abs(a11 * a22 - a12 * a21))          # rectifyTransformation, synth-detection.cpp:134-143
+    b2a2 = np.sqrt(a12 * a12 + a11 * a11)
+    regs["a11"], regs["a12"] = b2a2 / det, 0.0
+    regs["a21"], regs["a22"] = (a22 * a12 + a21 * a11) / (b2a2 * det), det / b2a2
+    regs["x"], regs["y"] = kp["x"], kp["y"]
+    regs = regs[(regs["x"] < w) & (regs["y"] < h) & (regs["x"] > 0) & (regs["y"] > 0)]
+    n_ang, ang = dominant_orientation(gray, regs, mr_size)
+    r2 = apply_orientations(regs, n_ang, ang)
+    r3, _ = reproject_filter(r2, w, h)
+    return len(kp), r3, describe_sift(gray, r3, mr_size)

@@ -124,6 +124,22 @@ def graf_counts():
         r4, _ = O.reproject_filter(r3, w, h)
         res["oracle"][name] = {"keypoints": int(len(k)), "regions": int(len(r2)), "descriptors": int(len(r4))}
         print(name, res["oracle"][name])
+    # classic configuration (config_affori_classic.ini + iters_HessianSIFT.ini; README.md:77-105)
+    res["readme_classic"] = {"regions": [2665, 3287], "descriptors": [2331, 2912], "tentatives": 76, "unique": 74, "inliers": 21}
+    res["oracle_classic"] = {}
+    cl = {}
+    for name in ("graf1", "graf6"):
+        g = O.gray_from_bgr(cv2.imread(os.path.join(REF, "build", "imgs", name + ".png"), cv2.IMREAD_COLOR))
+        nk, r, d = O.classic_regions(g)
+        cl[name] = (r, d)
+        res["oracle_classic"][name] = {"keypoints": int(nk), "descriptors": int(len(r))}
+    xy1, xy6 = np.c_[cl["graf1"][0]["x"], cl["graf1"][0]["y"]], np.c_[cl["graf6"][0]["x"], cl["graf6"][0]["y"]]
+    m = O.match_fginn(cl["graf1"][1], xy1, cl["graf6"][1], xy6)
+    keep = O.duplicate_filter(xy1[m["qi"]], xy6[m["ti"]], m["ratio"], 2.0)
+    u = np.c_[xy1[m["qi"]][keep], np.ones(len(keep)), xy6[m["ti"]][keep], np.ones(len(keep))]
+    rr = O.ref_ransac_H(np.ascontiguousarray(u), th=16.0)
+    res["oracle_classic"]["pair"] = {"tentatives": int(len(m)), "unique": int(len(keep)), "inliers_ref_degensac": int(rr["I"])}
+    print("classic", res["oracle_classic"])
     json.dump(res, open(os.path.join(HERE, "graf_counts.json"), "w"), indent=1)
 
 

@@ -676,3 +676,26 @@ def test_detect_affine_baumberg_bit_exact(mg, oracle, synth_pair, wh):
     assert np.allclose(Ag[:, 0] * Ag[:, 3] - Ag[:, 1] * Ag[:, 2], 1.0, atol=1e-4)
     # plain detection is unchanged
     assert len(mg.detect(img)) == len(oracle.detect_hessian(g))
+
+
+def test_pair_pipeline_classic_config1(mg, oracle):
+    """BASELINE config 1 on the device: Hessian-Affine (Baumberg) + dominant orientation + RootSIFT + FGINN + LO-RANSAC(H)
+    through the host mirror.  Every per-image stage is bit-exact, so the counts of the whole chain -- keypoints,
+    descriptors, tentatives, unique tentatives -- equal the oracle chain's; the homography is the generating one."""
+    from mods_light_zmq_b200 import synth
+    a, b, H = synth.image_pair(seed=4321, w=800, h=640)
+    i1, i2 = mg.image_from_bgr8(synth.gray_to_bgr(a)), mg.image_from_bgr8(synth.gray_to_bgr(b))
+    r = mg.pair_pipeline_classic_images(i1, i2, seed=7)
+    ch = [oracle.classic_regions(oracle.gray_from_bgr(synth.gray_to_bgr(u8))) for u8 in (a, b)]
+    assert r["keypoints"] == [ch[0][0], ch[1][0]]
+    assert r["descriptors"] == [len(ch[0][1]), len(ch[1][1])]
+    xy = [np.c_[c[1]["x"], c[1]["y"]] for c in ch]
+    m = oracle.match_fginn(ch[0][2], xy[0], ch[1][2], xy[1])
+    assert r["tentatives"] == len(m)
+    keep = oracle.duplicate_filter(xy[0][m["qi"]], xy[1][m["ti"]], m["ratio"], 2.0)
+    assert r["unique_tentatives"] == len(keep)
+    assert r["inliers"] >= 0.5 * len(keep) and r["inliers"] >= 20
+    Hn, Ht = r["H"] / r["H"][2, 2], H / H[2, 2]
+    corners = np.array([[0, 0, 1], [799, 0, 1], [0, 639, 1], [799, 639, 1], [400, 320, 1.0]])
+    pa, pb = corners @ Hn.T, corners @ Ht.T
+    assert np.linalg.norm(pa[:, :2] / pa[:, 2:3] - pb[:, :2] / pb[:, 2:3], axis=1).max() < 2.0

@@ -69,6 +69,30 @@ def test_graf_counts_match_readme():
         assert abs(r["oracle"][name]["descriptors"] - r["readme"]["descriptors"][i]) <= 2
 
 
+def test_graf_classic_counts_match_readme():
+    """README.md:77-105 known answers of the CLASSIC configuration (Hessian-Affine + Baumberg, dominant orientation,
+    RootSIFT): regions 2665/3287, descriptors 2331/2912 (+-2), ~21 RANSAC inliers out of ~74 tentatives (the README
+    run uses the randomised kd-tree; the oracle's exact linear matcher finds 63)."""
+    r = json.load(open(os.path.join(GOLD, "graf_counts.json")))
+    for i, name in enumerate(("graf1", "graf6")):
+        assert abs(r["oracle_classic"][name]["keypoints"] - r["readme_classic"]["regions"][i]) <= 2
+        assert abs(r["oracle_classic"][name]["descriptors"] - r["readme_classic"]["descriptors"][i]) <= 2
+    p = r["oracle_classic"]["pair"]
+    assert abs(p["inliers_ref_degensac"] - r["readme_classic"]["inliers"]) <= 4
+    assert 0.7 * r["readme_classic"]["unique"] <= p["unique"] <= 1.2 * r["readme_classic"]["unique"]
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/build/imgs/graf1.png"), reason="reference tree absent")
+def test_graf1_classic_count_live(oracle):
+    import cv2
+    r = json.load(open(os.path.join(GOLD, "graf_counts.json")))
+    g = oracle.gray_from_bgr(cv2.imread("/root/reference/build/imgs/graf1.png", cv2.IMREAD_COLOR))
+    nk, regs, d = oracle.classic_regions(g)
+    assert nk == r["oracle_classic"]["graf1"]["keypoints"] and len(regs) == r["oracle_classic"]["graf1"]["descriptors"]
+    assert d.shape == (len(regs), 128) and d.min() >= 0 and d.max() <= 255 and np.all(d == np.round(d))
+    assert np.abs(np.linalg.norm(d, axis=1) - 512).max() < 8          # RootSIFT: |d| = 512 up to the integer rounding
+
+
 @pytest.mark.skipif(not os.path.exists("/root/reference/build/imgs/graf1.png"), reason="reference tree absent")
 def test_graf1_detector_count_live(oracle):
     import cv2

@@ -322,20 +322,29 @@ k_sample_a(const float* __restrict__ img, int w, int h, const PatchMeta* __restr
   }
   if (tid < R) gen_row_starts(m, tid, R, nseg, C2 + tid * nseg);
   __syncthreads();
-  // 1. first resampling
+  // 1. first resampling: an 8-lane group walks one row segment by segment (no index division per sample)
   {
-    const int g = tid >> 3, sub = tid & 7, nit = R * nseg;
-    const float inv = 1.0f / (float)nseg;
-    for (int it = g; it < nit; it += NT / SEG) {
-      const int j = fast_div(it, inv), s = it - j * nseg;
-      const int i = s * SEG + sub;
-      const float v = sample_seg(img, w, h, C2[it], m.a11, m.a21, sub);
-      if (i < R) {
-        float* row = Sp + j * PS;
-        row[r + i] = v;
-        if (i == 0) for (int t = 0; t < r; t++) row[t] = v;
-        if (i == R - 1) for (int t = 0; t < r + 4; t++) row[r + R + t] = v;
+    const int g = tid >> 3, sub = tid & 7;
+    for (int j = g; j < R; j += NT / SEG) {
+      float* row = Sp + j * PS + r;
+      const float2* cs = C2 + j * nseg;
+      for (int s = 0; s < nseg; s++) {
+        const int i = s * SEG + sub;
+        const float v = sample_seg(img, w, h, cs[s], m.a11, m.a21, sub);
+        if (i < R) row[i] = v;
       }
+    }
+  }
+  __syncthreads();
+  // replicate the borders into the padding (all threads; r left, r + 4 right entries per row)
+  {
+    const int np = 2 * r + 4;
+    const float inv = 1.0f / (float)np;
+    for (int it = tid; it < R * np; it += NT) {
+      const int j = fast_div(it, inv), t = it - j * np;
+      float* row = Sp + j * PS;
+      if (t < r) row[t] = row[r];
+      else row[R + t] = row[r + R - 1];
     }
   }
   __syncthreads();
@@ -374,14 +383,24 @@ k_sample_a(const float* __restrict__ img, int w, int h, const PatchMeta* __restr
     else Tp[(R + pr) * PT + x] = Tp[(R - 1 + r) * PT + x];
   }
   __syncthreads();
-  // 4. column pass: 4 adjacent rows per thread, lanes along x
+  // 4. column pass: 4 adjacent rows per thread, lanes along x; vector columns (x < R & ~7) and the scalar tail
+  //    columns are separate item lists so that no warp executes both forms
   {
-    const int NRG = (R + 3) >> 2, nit = R * NRG, wc = R & ~7;
-    const float inv = 1.0f / (float)R;
-    for (int it = tid; it < nit; it += NT) {
-      const int rg = fast_div(it, inv), x = it - rg * R, y0 = rg * 4;
+    const int NRG = (R + 3) >> 2, wc = R & ~7, nt = R - wc;
+    if (wc > 0) {
+      const float inv = 1.0f / (float)wc;
+      for (int it = tid; it < wc * NRG; it += NT) {
+        const int rg = fast_div(it, inv), x = it - rg * wc, y0 = rg * 4;
+        float o[4];
+        colpass_block<4>(Tp + (y0 + r) * PT + x, PT, kp, r, true, o);
+#pragma unroll
+        for (int i = 0; i < 4; i++) if (y0 + i < R) B[(y0 + i) * R + x] = o[i];
+      }
+    }
+    for (int it = tid; it < nt * NRG; it += NT) {
+      const int rg = it / nt, x = wc + (it - rg * nt), y0 = rg * 4;
       float o[4];
-      colpass_block<4>(Tp + (y0 + r) * PT + x, PT, kp, r, x < wc, o);
+      colpass_block<4>(Tp + (y0 + r) * PT + x, PT, kp, r, false, o);
 #pragma unroll
       for (int i = 0; i < 4; i++) if (y0 + i < R) B[(y0 + i) * R + x] = o[i];
     }
@@ -445,20 +464,29 @@ k_sample_b(const float* __restrict__ img, int w, int h, const PatchMeta* __restr
   const int xv = R & ~3;
   for (int j0 = 0; j0 < R; j0 += B_NB) {
     const int nrows = min(B_NB, R - j0);
-    // 1. sample nrows rows
+    // 1. sample nrows rows: group g (8 lanes) walks row j0 + g segment by segment
     {
-      const int g = tid >> 3, sub = tid & 7, nit = nrows * nseg;
-      const float inv = 1.0f / (float)nseg;
-      for (int it = g; it < nit; it += NT / SEG) {
-        const int jr = fast_div(it, inv), s = it - jr * nseg;
-        const int i = s * SEG + sub;
-        const float v = sample_seg(img, w, h, C2[(j0 + jr) * nseg + s], m.a11, m.a21, sub);
-        if (i < R) {
-          float* row = Sb + jr * PS;
-          row[r + i] = v;
-          if (i == 0) for (int t = 0; t < r; t++) row[t] = v;
-          if (i == R - 1) for (int t = 0; t < r + 2; t++) row[r + R + t] = v;
+      const int g = tid >> 3, sub = tid & 7;
+      if (g < nrows) {
+        float* row = Sb + g * PS + r;
+        const float2* cs = C2 + (j0 + g) * nseg;
+        for (int s = 0; s < nseg; s++) {
+          const int i = s * SEG + sub;
+          const float v = sample_seg(img, w, h, cs[s], m.a11, m.a21, sub);
+          if (i < R) row[i] = v;
         }
+      }
+    }
+    __syncthreads();
+    // replicate the borders into the padding (r left, r + 2 right entries per row)
+    {
+      const int np = 2 * r + 2;
+      const float inv = 1.0f / (float)np;
+      for (int it = tid; it < nrows * np; it += NT) {
+        const int jr = fast_div(it, inv), t = it - jr * np;
+        float* row = Sb + jr * PS;
+        if (t < r) row[t] = row[r];
+        else row[R + t] = row[r + R - 1];
       }
     }
     __syncthreads();
@@ -500,14 +528,27 @@ k_sample_b(const float* __restrict__ img, int w, int h, const PatchMeta* __restr
     else Tp[(R + pr) * B_TP + c] = Tp[(R - 1 + r) * B_TP + c];
   }
   __syncthreads();
-  // 4. column pass at the 32 row pairs (y_j, y_j + 1) x 64 columns
+  // 4. column pass at the 32 row pairs (y_j, y_j + 1) x 64 columns: the fused (vector) form for every column first,
+  //    then the few columns in OpenCV's scalar tail (x >= R & ~7) are redone with the unfused form -- a per-lane
+  //    branch inside the tap loop would make half of the warps execute both forms
   {
     const int wc = R & ~7;
     for (int it = tid; it < 32 * 64; it += NT) {
       const int pj = it >> 6, ci = it & 63;
-      const int y0 = X[pj], xc = X[ci >> 1] + (ci & 1);
+      const int y0 = X[pj];
       float o[2];
-      colpass_block<2>(Tp + (y0 + r) * B_TP + ci, B_TP, kp, r, xc < wc, o);
+      colpass_block<2>(Tp + (y0 + r) * B_TP + ci, B_TP, kp, r, true, o);
+      B[(2 * pj) * 64 + ci] = o[0];
+      B[(2 * pj + 1) * 64 + ci] = o[1];
+    }
+    int ntail = 0;                       // needed columns are ascending: the tail is a suffix
+    while (ntail < 64 && X[(63 - ntail) >> 1] + ((63 - ntail) & 1) >= wc) ntail++;
+    __syncthreads();
+    for (int it = tid; it < 32 * ntail; it += NT) {
+      const int pj = it / ntail, ci = 64 - ntail + (it - pj * ntail);
+      const int y0 = X[pj];
+      float o[2];
+      colpass_block<2>(Tp + (y0 + r) * B_TP + ci, B_TP, kp, r, false, o);
       B[(2 * pj) * 64 + ci] = o[0];
       B[(2 * pj + 1) * 64 + ci] = o[1];
     }

@@ -18,7 +18,7 @@ $(OBJ)/detect.o: $(SRC)/detect.cu $(SRC)/common.cuh include/modsgpu.h
 $(OBJ)/sampler.o: $(SRC)/sampler.cu $(SRC)/common.cuh include/modsgpu.h
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVFLAGS) $(EXACT) -c $< -o $@
-$(OBJ)/ransac.o: $(SRC)/ransac.cu $(SRC)/ransac_common.cuh $(SRC)/common.cuh include/modsgpu.h
+$(OBJ)/ransac.o: $(SRC)/ransac.cu $(SRC)/ransac_common.cuh $(SRC)/ransac_h.cuh $(SRC)/common.cuh include/modsgpu.h
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVFLAGS) $(EXACT) -c $< -o $@
 $(OBJ)/synth.o: $(SRC)/synth.cu $(SRC)/common.cuh include/modsgpu.h
@@ -27,7 +27,7 @@ $(OBJ)/synth.o: $(SRC)/synth.cu $(SRC)/common.cuh include/modsgpu.h
 $(OBJ)/classic.o: $(SRC)/classic.cu $(SRC)/common.cuh include/modsgpu.h
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVFLAGS) $(EXACT) -c $< -o $@
-$(OBJ)/ransac_f.o: $(SRC)/ransac_f.cu $(SRC)/ransac_common.cuh $(SRC)/common.cuh include/modsgpu.h
+$(OBJ)/ransac_f.o: $(SRC)/ransac_f.cu $(SRC)/ransac_common.cuh $(SRC)/ransac_h.cuh $(SRC)/common.cuh include/modsgpu.h
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVFLAGS) $(EXACT) -c $< -o $@
 $(OBJ)/%.o: $(SRC)/%.cu $(SRC)/common.cuh include/modsgpu.h

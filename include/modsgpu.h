@@ -189,6 +189,8 @@ typedef struct {
   int    samples;               /* data_out[0] */
   int    lo_runs;               /* data_out[1] */
   int    oc_rejects;            /* data_out[2] */
+  int    degen_runs;            /* F only: completed DEGENSAC (plane-and-parallax) passes, exp_ranF.c degen_cnt */
+  int    h_inliers;             /* F only: *Ih, the largest plane consensus seen (exp_ranF.c:980) */
 } modsgpu_ransac_result;
 /* u: T x 6 doubles (x1,y1,1,x2,y2,1) as packed at matching.cpp:695-713.  H: 9 doubles in the
  * degensac convention (column-major / transposed, maps image 2 -> image 1).
@@ -199,7 +201,8 @@ int  modsgpu_ransac_H(modsgpu_ctx* ctx, const double* u, int T, const modsgpu_ra
 /* replaces exp_ransacFcustom degensac/exp_ranF.h:71-73 as called from LORANSACFiltering matching.cpp:722
  * (7-point sample, oriented epipolar constraint, Sampson error, MSAC, symmetric check, LO).  F: 9 doubles with
  * u2^T M u1 = 0, M[k][l] = F[3k+l] (the degensac convention, Ftools.c:15-37).  res->oc_rejects counts models
- * discarded by the symmetric check.  The DEGENSAC plane-and-parallax branch is not implemented. */
+ * discarded by the symmetric check.  Includes the DEGENSAC branch (plane-dominated samples -> inner H-RANSAC ->
+ * plane-and-parallax, exp_ranF.c:963-1016); MODSGPU_NO_DEGENSAC=1 in the environment switches it off. */
 int  modsgpu_ransac_F(modsgpu_ctx* ctx, const double* u, int T, const modsgpu_ransac_params* p,
                       double* F, unsigned char* inl, modsgpu_ransac_result* res);
 

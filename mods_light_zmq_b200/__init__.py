@@ -62,7 +62,7 @@ class ModsResult(C.Structure):
 
 class RansacResult(C.Structure):
     _fields_ = [("n_inliers", C.c_int), ("J", C.c_double), ("samples", C.c_int), ("lo_runs", C.c_int),
-                ("oc_rejects", C.c_int)]
+                ("oc_rejects", C.c_int), ("degen_runs", C.c_int), ("h_inliers", C.c_int)]
 
 
 _lib = None
@@ -379,7 +379,7 @@ class ModsGpu:
         res = RansacResult()
         self._check(self.lib.modsgpu_ransac_F(self.ctx, _p(u), T, C.byref(p), _p(F), _p(inl), C.byref(res)))
         return dict(F=F, inl=inl[:T], I=res.n_inliers, J=res.J, samples=res.samples, lo_count=res.lo_runs,
-                    sym_rejects=res.oc_rejects)
+                    sym_rejects=res.oc_rejects, degen_runs=res.degen_runs, h_inliers=res.h_inliers)
 
 
 def view_schedule(scale_set, tilt_set, phi_base, init_sigma, do_blur=1, cap=4096):

@@ -104,6 +104,7 @@ int exp_ransacFcustom(double* u, int len, double th, double conf, int max_sam, d
     return 0;
   }
   if (data_out) { data_out[0] = r.samples; data_out[1] = r.lo_runs; }
+  if (Ih) *Ih = r.h_inliers;
   if (resids && *resids) memset(*resids, 0, sizeof(double) * (size_t)len);
   return r.n_inliers;
 }

@@ -23,11 +23,13 @@
 //  (4) matching.cpp:722 passes inlLimit = 0, which with __D3__ (exp_ranF.h:25) makes every LO least-squares
 //      step of the reference use a RANDOM SUBSET OF 8 inliers; this implementation uses all inliers of the
 //      band (the estimator LO-RANSAC describes) -- models are at least as well supported;
-//  (5) NOT IMPLEMENTED in this round: the DEGENSAC branch (checksample -> innerH -> rFtH plane-and-parallax,
-//      exp_ranF.c:963-1016, DegUtils.c).  On scenes where a 7-point sample is dominated by one plane the
-//      reference swaps to an H-consistent F recovery; this kernel keeps the plain 7-point model.
+//  (5) the DEGENSAC branch (checksample -> innerH -> rFtH plane-and-parallax, exp_ranF.c:963-1016, DegUtils.c) is
+//      implemented with the same batching: plane-and-parallax hypotheses come 2048 at a time and only the best of
+//      a batch is refined by innerFH (the reference refines every hypothesis that improves on the previous one);
+//      the epipole of Hdetect comes from row cross products instead of ccmath svduv.
 #include "common.cuh"
 #include "ransac_common.cuh"
+#include "ransac_h.cuh"
 #include <cmath>
 #include <algorithm>
 
@@ -43,8 +45,12 @@ struct RfState {
   double Fs[9];           // best sample model so far (maxSs / FBest)
   double Js; int Is;
   int max_sam, no_sam, lo_runs, sym_rejects, done, have_sample;
+  // DEGENSAC (exp_ranF.c:963-1016): a new best sample whose 7 points contain >= 5 on one plane
+  int degen_pending, degen_cnt, Ihmax, pad;
+  double Hdeg[9];         // homography of that plane (column-major, image 2 -> image 1)
+  double Fdeg[9];         // the sample's model (kept for the I / J bookkeeping after plane-and-parallax)
 };
-struct FHyp { double F[9]; double J; int I; int flag; };   // flag 0 ok, 1 all models OC-rejected, 2 degenerate sample
+struct FHyp { double F[9]; double J; int I; int flag; int idx[7]; int pad; };   // flag 0 ok, 1 all models OC-rejected, 2 degenerate sample
 
 // Ftools.c:83-101 FDs for one correspondence; den = the Sampson denominator (exFDs weight^-2)
 __device__ __forceinline__ double fds(const double* F, const double* u, double* den) {
@@ -372,6 +378,8 @@ k_rf_hyp(const double* __restrict__ u, int T, double th, unsigned long long seed
     FHyp o;
     for (int i = 0; i < 9; i++) o.F[i] = flag == 0 ? bestF[i] : 0.0;
     o.I = flag == 0 ? bestI : 0; o.J = flag == 0 ? bestJ : -1.0; o.flag = flag;
+    for (int i = 0; i < 7; i++) o.idx[i] = idx[i];
+    o.pad = 0;
     out[wv] = o;
   }
 }
@@ -413,6 +421,66 @@ __device__ void f_lo_iterate(const double* __restrict__ u, int T, double th, dou
   *bestI = mI; *bestJ = mJ;
 }
 
+// ---- DEGENSAC: is the 7-point sample dominated by one plane? (DegUtils.c:42-91 checksample, :93-162 Hdetect) ---------
+// Hdetect: the homography compatible with F through 3 correspondences (Hartley & Zisserman, "scene planes and
+// homographies"): H = A - e v^T with A = [e]x M^T, e the null vector of M (x2^T M x1 = 0, M[k][l] = F[3k+l]).
+// The reference takes e from ccmath's svduv; for the rank-2 M of the 7-point solver that is the unit null vector,
+// obtained here from the largest cross product of two rows (the sign of e does not change H up to scale).
+__device__ void Hdetect(const double* F, const double* u, const int* idx7, const int* tri, double* H) {
+  const double* r0 = F; const double* r1 = F + 3; const double* r2 = F + 6;
+  double c01[3], c02[3], c12[3], ec[3];
+  cross3(c01, r0, r1); cross3(c02, r0, r2); cross3(c12, r1, r2);
+  const double n01 = c01[0] * c01[0] + c01[1] * c01[1] + c01[2] * c01[2];
+  const double n02 = c02[0] * c02[0] + c02[1] * c02[1] + c02[2] * c02[2];
+  const double n12 = c12[0] * c12[0] + c12[1] * c12[1] + c12[2] * c12[2];
+  const double* cb = (n01 >= n02 && n01 >= n12) ? c01 : (n02 >= n12 ? c02 : c12);
+  const double nb = sqrt(cb[0] * cb[0] + cb[1] * cb[1] + cb[2] * cb[2]);
+  for (int i = 0; i < 3; i++) ec[i] = cb[i] / nb;
+  const double Ex[9] = {0, -ec[2], ec[1], ec[2], 0, -ec[0], -ec[1], ec[0], 0};
+  double A[9];                                    // A = Ex * M^T
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) A[3 * i + j] = Ex[3 * i] * F[3 * j] + Ex[3 * i + 1] * F[3 * j + 1] + Ex[3 * i + 2] * F[3 * j + 2];
+  double b[3], Mx[9];
+  for (int i = 0; i < 3; i++) {
+    const double* p = u + 6 * idx7[tri[i]];
+    const double x1[3] = {p[0], p[1], p[2]}, x2[3] = {p[3], p[4], p[5]};
+    double ax2[3], p1[3], p2[3];
+    for (int r = 0; r < 3; r++) ax2[r] = A[3 * r] * x2[0] + A[3 * r + 1] * x2[1] + A[3 * r + 2] * x2[2];
+    cross3(p1, x1, ax2);                          // x1 x (A x2)
+    for (int r = 0; r < 3; r++) p2[r] = -(Ex[3 * r] * x1[0] + Ex[3 * r + 1] * x1[1] + Ex[3 * r + 2] * x1[2]);   // -[e]x x1
+    b[i] = (p1[0] * p2[0] + p1[1] * p2[1] + p1[2] * p2[2]) / (p2[0] * p2[0] + p2[1] * p2[1] + p2[2] * p2[2]);
+    Mx[3 * i] = x2[0]; Mx[3 * i + 1] = x2[1]; Mx[3 * i + 2] = x2[2];
+  }
+  double Mi[9];
+  const bool ok = inv3(Mx, Mi);
+  double v[3];
+  for (int r = 0; r < 3; r++) v[r] = Mi[3 * r] * b[0] + Mi[3 * r + 1] * b[1] + Mi[3 * r + 2] * b[2];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) H[i + j * 3] = A[i * 3 + j] - ec[i] * v[j];   // column-major like the reference
+  if (!ok || isnan(H[0]) || isinf(H[0])) { for (int i = 0; i < 9; i++) H[i] = (i % 4 == 0) ? 1.0 : 0.0; }
+}
+
+// warp-wide; true when some F-compatible homography explains >= 5 of the 7 sample correspondences (error < th)
+__device__ bool checksample(const double* F, const double* __restrict__ u, const int* idx7, double th, double* H, int lane) {
+  const int IDXS[5][3] = {{0, 1, 2}, {3, 4, 5}, {0, 1, 6}, {3, 4, 6}, {2, 5, 6}};
+  for (int i = 0; i < 5; ++i) {
+    Hdetect(F, u, idx7, IDXS[i], H);
+    double Ds[7];
+    int ord[7];
+    for (int j = 0; j < 7; j++) { Ds[j] = sampson(H, u + 6 * idx7[j]); ord[j] = j; }
+    for (int a = 0; a < 7; ++a)                  // sortDs (DegUtils.c:164-184)
+      for (int b = a + 1; b < 7; ++b)
+        if (Ds[b] < Ds[a]) { double t = Ds[b]; Ds[b] = Ds[a]; Ds[a] = t; int q = ord[b]; ord[b] = ord[a]; ord[a] = q; }
+    int id5[5];
+    for (int j = 0; j < 5; j++) id5[j] = idx7[ord[j]];
+    lsq_h(u, id5, 5, H, lane);
+    int inl = 0;
+    for (int j = 0; j < 7; j++) if (sampson(H, u + 6 * idx7[j]) < th) ++inl;
+    if (inl > 4) return true;
+  }
+  return false;
+}
+
 // ---- per-batch update: three launches (select / inner samples on LO_REPS SMs / accept), as in ransac.cu ------
 // scratch: per inner sample w: dbuf[w][2T]; then dS[T]; then wbuf[w][T] doubles; ibuf[w][T] ints + inl0[T]
 struct FLoShare {
@@ -423,8 +491,8 @@ struct FLoShare {
 constexpr int RF_NW = 12;
 
 __global__ void __launch_bounds__(384)
-k_rf_select(const double* __restrict__ u, int T, double th, int do_sym, FHyp* __restrict__ hyp, int nhyp, int force_lo,
-            RfState* st, FLoShare* sh, double* dscr, int* iscr) {
+k_rf_select(const double* __restrict__ u, int T, double th, int do_sym, int do_degen, FHyp* __restrict__ hyp, int nhyp,
+            int force_lo, RfState* st, FLoShare* sh, double* dscr, int* iscr) {
   __shared__ double sJ[12]; __shared__ int sIdx[12];
   __shared__ int again_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -452,7 +520,7 @@ k_rf_select(const double* __restrict__ u, int T, double th, int do_sym, FHyp* __
       int again = 0;
       if (bi >= 0) {
         const double curJ = st->J, curJs = st->Js;
-        const int have = st->have_sample;
+        const int have = st->have_sample || st->Js > 0;
         __syncwarp();
         double f[9];
         for (int i = 0; i < 9; i++) f[i] = hyp[bi].F[i];
@@ -466,8 +534,17 @@ k_rf_select(const double* __restrict__ u, int T, double th, int do_sym, FHyp* __
           if (lane == 0) { hyp[bi].flag = 3; st->sym_rejects++; }
           again = 1;
         } else if (!have || curJs < bj) {
-          if (lane == 0) { for (int i = 0; i < 9; i++) st->Fs[i] = f[i]; st->Js = bj; st->Is = I; st->have_sample = 1; }
-          new_best_sample = true;
+          // maxSs (exp_ranF.c:961-962); a plane-dominated sample goes to the DEGENSAC branch instead of the LO
+          int id7[7];
+          for (int i = 0; i < 7; i++) id7[i] = hyp[bi].idx[i];
+          double Hd[9];
+          if (lane == 0) { st->Js = bj; st->Is = I; }
+          if (do_degen && checksample(f, u, id7, 3 * th, Hd, lane)) {
+            if (lane == 0) { for (int i = 0; i < 9; i++) { st->Hdeg[i] = Hd[i]; st->Fdeg[i] = f[i]; } st->degen_pending = 1; }
+          } else {
+            if (lane == 0) { for (int i = 0; i < 9; i++) st->Fs[i] = f[i]; st->have_sample = 1; }
+            new_best_sample = true;
+          }
         }
       }
       if (lane == 0) again_s = again;
@@ -481,6 +558,8 @@ k_rf_select(const double* __restrict__ u, int T, double th, int do_sym, FHyp* __
   // or once when ITER_SAM is reached
   const int no_sam = st->no_sam, lo_runs = st->lo_runs, have = st->have_sample;
   __syncwarp();
+  if (lane == 0) sh->run_lo = 0;
+  if (st->degen_pending) return;      // the host runs the DEGENSAC kernels for this batch; no LO from a degenerate sample
   bool run_lo = false;
   if (have) {
     if (lo_runs == 0 && no_sam + nhyp >= ITER_SAM) run_lo = true;
@@ -553,6 +632,253 @@ __global__ void k_rf_accept(int T, double conf, int nhyp, RfState* st, const FLo
   st->done = st->no_sam >= st->max_sam;
 }
 
+// ---- DEGENSAC branch (exp_ranF.c:963-1016; DegUtils.c rFtH :254-444, innerFH :488-594, u2Fit :635-691) -------------
+// Runs only when a new best 7-point sample is plane-dominated (checksample), a handful of times per run, so it is
+// orchestrated from the host with small kernels:
+//   k_rfd_prep      consensus of the plane homography at 3*th; inlier list at 16*th for the inner H-RANSAC
+//   k_rs_lo         (ransac_h.cuh) LO_REPS inner samples of the homography LO at threshold 16*th  = innerH
+//   k_rfd_h_accept  refined H, its inliers (on-plane list) and the clearly off-plane correspondences (error > 100*th)
+//   k_rfd_pp_hyp    plane-and-parallax hypotheses: epipole from two off-plane correspondences, F = ([e]x H)^T,
+//                   support among the off-plane correspondences at 2*th (one warp per hypothesis)
+//   k_rfd_pp_update best hypothesis of the batch -> innerFH (15 x {6 on-plane + 4 consistent off-plane -> 8-point LSQ
+//                   -> iterated refit u2Fit}), stopping rule nsamples(., ., 2, 0.999)
+//   k_rfd_finish    accept F if it has more inliers than the best model (exp_ranF.c:990-1013)
+struct DegShare {
+  double H[9], Fpp[9];
+  int run_pp, nN, nH, max_i, m_i, max_sam, no_sam, have_F, done, pad;
+};
+struct PPHyp { double F[9]; int no_i, pad; };
+constexpr int PP_B = 2048;
+
+__device__ __forceinline__ int compact_lt(const double* d, int T, double th, int* idx, int lane) {
+  int n = 0;
+  for (int base = 0; base < T; base += 32) {
+    const int j = base + lane;
+    const bool in = j < T && d[j] < th;
+    const unsigned m = __ballot_sync(0xffffffffu, in);
+    if (in) idx[n + __popc(m & ((1u << lane) - 1))] = j;
+    n += __popc(m);
+  }
+  __syncwarp();
+  return n;
+}
+// Sampson errors under F into d[]; returns the number strictly below th  (the `Ds[i] < th` counts of DegUtils.c)
+__device__ __forceinline__ int fds_all_count_lt(const double* __restrict__ u, int T, const double* F, double th, double* d, int lane) {
+  int c = 0;
+  for (int j = lane; j < T; j += 32) { const double e = fds(F, u + 6 * j, nullptr); d[j] = e; if (e < th) c++; }
+  c = warp_sum_i(c);
+  __syncwarp();
+  return c;
+}
+
+__global__ void __launch_bounds__(32)
+k_rfd_prep(const double* __restrict__ u, int T, double th, RfState* st, LoShare* hsh, double* dscr, int* iscr) {
+  const int lane = threadIdx.x;
+  hsh->run_lo = 0;
+  if (!st->degen_pending) return;
+  double H[9];
+  for (int i = 0; i < 9; i++) H[i] = st->Hdeg[i];
+  double* hd = dscr + (size_t)20 * T;
+  int* inl0 = iscr + (size_t)RS_NW * T;
+  int c3 = 0;
+  for (int j = lane; j < T; j += 32) { const double e = sampson(H, u + 6 * j); hd[j] = e; if (e < 3 * th) c3++; }
+  c3 = warp_sum_i(c3);
+  __syncwarp();
+  if (c3 < 8) { if (lane == 0) st->degen_pending = 0; return; }     // exp_ranF.c:972-974 `break`
+  const int n = compact_inliers(hd, T, 16 * th, inl0, lane);
+  if (lane == 0) {
+    for (int i = 0; i < 9; i++) hsh->h0[i] = H[i];
+    hsh->n0 = n; hsh->run_lo = 1; hsh->lo_id = 1000 + st->degen_cnt;
+    for (int k = 0; k < LO_REPS; k++) { hsh->loJ[k] = 0; hsh->loI[k] = 0; }
+  }
+}
+
+__global__ void __launch_bounds__(32)
+k_rfd_h_accept(const double* __restrict__ u, int T, double th, RfState* st, const LoShare* hsh, DegShare* deg, double* dscr, int* iscr) {
+  const int lane = threadIdx.x;
+  if (lane == 0) { deg->run_pp = 0; deg->have_F = 0; deg->done = 1; deg->max_i = 0; }
+  if (!st->degen_pending) return;
+  double H[9];
+  for (int i = 0; i < 9; i++) H[i] = st->Hdeg[i];
+  int best = -1; double bJ = 0;
+  for (int k = 0; k < LO_REPS; k++) if (bJ < hsh->loJ[k]) { bJ = hsh->loJ[k]; best = k; }
+  if (best >= 0) for (int i = 0; i < 9; i++) H[i] = hsh->loH[best][i];
+  double* hd = dscr + (size_t)20 * T;
+  int* offp = iscr + (size_t)10 * T;
+  int* onp = iscr + (size_t)11 * T;
+  for (int j = lane; j < T; j += 32) hd[j] = sampson(H, u + 6 * j);
+  __syncwarp();
+  const int nH = compact_inliers(hd, T, 16 * th, onp, lane);        // innerH's inlier mask (DegUtils.c:715-723)
+  if (lane == 0 && nH > st->Ihmax) st->Ihmax = nH;
+  if (nH <= 6) { if (lane == 0) st->degen_pending = 0; return; }    // exp_ranF.c:984 `if (I > 6)`
+  int nN = 0;                                                       // rFtH: nhinl = HDs > 100*th
+  for (int base = 0; base < T; base += 32) {
+    const int j = base + lane;
+    const bool in = j < T && hd[j] > 100 * th;
+    const unsigned m = __ballot_sync(0xffffffffu, in);
+    if (in) offp[nN + __popc(m & ((1u << lane) - 1))] = j;
+    nN += __popc(m);
+  }
+  __syncwarp();
+  if (lane == 0) {
+    for (int i = 0; i < 9; i++) deg->H[i] = H[i];
+    deg->nN = nN; deg->nH = nH;
+    deg->max_i = 3; deg->m_i = 4; deg->max_sam = 10000; deg->no_sam = 0; deg->have_F = 0;
+    const bool ok = !(nN < 4 || nH < 6);                            // DegUtils.c:345
+    if (!ok) deg->max_i = 0;
+    deg->run_pp = ok ? 1 : 0; deg->done = ok ? 0 : 1;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_rfd_pp_hyp(const double* __restrict__ u, int T, double th, unsigned long long seed, int base, int nhyp, const DegShare* deg,
+             const int* __restrict__ iscr, PPHyp* __restrict__ out) {
+  if (!deg->run_pp || deg->done) return;
+  const int wv = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (wv >= nhyp) return;
+  const int nN = deg->nN;
+  const int* offp = iscr + (size_t)10 * T;
+  int pr[2];
+  draw_sample<2>(seed, 0x5050000000000000ull + (unsigned long long)(base + wv), nN, pr);
+  const double* H = deg->H;
+  double c[2][3];
+  for (int k = 0; k < 2; k++) {
+    const double* p = u + 6 * offp[pr[k]];
+    const double hx[3] = {H[0] * p[3] + H[3] * p[4] + H[6] * p[5], H[1] * p[3] + H[4] * p[4] + H[7] * p[5],
+                          H[2] * p[3] + H[5] * p[4] + H[8] * p[5]};
+    cross3(c[k], p, hx);
+  }
+  double ec[3];
+  cross3(ec, c[0], c[1]);
+  const double nrm = sqrt(ec[0] * ec[0] + ec[1] * ec[1] + ec[2] * ec[2]);
+  for (int i = 0; i < 3; i++) ec[i] /= nrm;
+  const double Ex[9] = {0, -ec[2], ec[1], ec[2], 0, -ec[0], -ec[1], ec[0], 0};
+  double F[9];                                     // F = ([e]x * Hm)^T with Hm[i][j] = H[i + 3j]   (DegUtils.c:371-373)
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) F[3 * j + i] = Ex[3 * i] * H[3 * j] + Ex[3 * i + 1] * H[3 * j + 1] + Ex[3 * i + 2] * H[3 * j + 2];
+  int no_i = 0;
+  if (isfinite(F[0]) && nrm > 0)
+    for (int k = lane; k < nN; k += 32) if (fds(F, u + 6 * offp[k], nullptr) < th * 2) no_i++;
+  no_i = warp_sum_i(no_i);
+  if (lane == 0) {
+    PPHyp o;
+    for (int i = 0; i < 9; i++) o.F[i] = F[i];
+    o.no_i = no_i; o.pad = 0;
+    out[wv] = o;
+  }
+}
+
+// u2Fit (DegUtils.c:635-691), warp-wide; F is refined in place; returns the inlier count at th
+__device__ int u2Fit(const double* __restrict__ u, int T, double* F, double th, double ths, int iters, double* d, int* idx, int lane) {
+  const double dth = (ths - th) / (iters - 1);
+  for (int it = 0; it < iters; ++it) {
+    fds_all_count_lt(u, T, F, ths, d, lane);
+    const int n = compact_lt(d, T, ths, idx, lane);
+    if (n < 8) return n;
+    lsq_f(u, idx, n, nullptr, F, lane);
+    ths -= dth;
+  }
+  return fds_all_count_lt(u, T, F, th, d, lane);
+}
+
+__global__ void __launch_bounds__(32)
+k_rfd_pp_update(const double* __restrict__ u, int T, double th, unsigned long long seed, int nhyp, DegShare* deg,
+                const PPHyp* __restrict__ hyp, double* dscr, int* iscr) {
+  const int lane = threadIdx.x;
+  if (!deg->run_pp || deg->done) return;
+  const int nN = deg->nN, nH = deg->nH;
+  const int* offp = iscr + (size_t)10 * T;
+  const int* onp = iscr + (size_t)11 * T;
+  const double* hd = dscr + (size_t)20 * T;
+  double* d = dscr;                    // scratch slots of the (finished) inner H-RANSAC
+  int* vlist = iscr;
+  int* idx = iscr + T;
+  // best hypothesis of the batch with more support than any before (first on ties)
+  int bi = -1, bn = deg->m_i;
+  for (int k = lane; k < nhyp; k += 32) if (hyp[k].no_i > bn) { bn = hyp[k].no_i; bi = k; }
+  for (int o = 16; o > 0; o >>= 1) {
+    const int on = __shfl_xor_sync(0xffffffffu, bn, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (oi >= 0 && (on > bn || (on == bn && (bi < 0 || oi < bi)))) { bn = on; bi = oi; }
+  }
+  if (bi >= 0) {
+    double Fp[9];
+    for (int i = 0; i < 9; i++) Fp[i] = hyp[bi].F[i];
+    // uV = off-plane correspondences consistent with the hypothesis
+    int nV = 0;
+    for (int base = 0; base < nN; base += 32) {
+      const int k = base + lane;
+      const bool in = k < nN && fds(Fp, u + 6 * offp[k], nullptr) < th * 2;
+      const unsigned m = __ballot_sync(0xffffffffu, in);
+      if (in) vlist[nV + __popc(m & ((1u << lane) - 1))] = offp[k];
+      nV += __popc(m);
+    }
+    __syncwarp();
+    // innerFH(uH, uV, u, th, 15, 6, 4)
+    int max_i = 0, max_s = 0;
+    double Fbest[9];
+    for (int i = 0; i < 9; i++) Fbest[i] = 1.0;
+    if (nV >= 4 && nH >= 6) {
+      for (int rep = 0; rep < 15; ++rep) {
+        int s6[6], s4[4], id10[10];
+        const unsigned long long stream = 0x5046000000000000ull + (unsigned long long)deg->no_sam * 64 + rep;
+        draw_sample<6>(seed, stream, nH, s6);
+        draw_sample<4>(seed, stream + 32, nV, s4);
+        for (int i = 0; i < 6; i++) id10[i] = onp[s6[i]];
+        for (int i = 0; i < 4; i++) id10[6 + i] = vlist[s4[i]];
+        double aF[9];
+        for (int i = 0; i < 9; i++) aF[i] = 1.0;
+        lsq_f(u, id10, 10, nullptr, aF, lane);
+        int no_i = fds_all_count_lt(u, T, aF, th, d, lane);
+        if (max_i < no_i) { max_i = no_i; for (int i = 0; i < 9; i++) Fbest[i] = aF[i]; }
+        if (no_i > max_s) {
+          max_s = no_i;
+          no_i = u2Fit(u, T, aF, th, th * 3, 4, d, idx, lane);
+          if (max_i < no_i) { max_i = no_i; for (int i = 0; i < 9; i++) Fbest[i] = aF[i]; }
+        }
+      }
+    }
+    if (lane == 0) deg->m_i = bn;
+    if (max_i > deg->max_i) {
+      // inliers that are clearly off the plane drive the stopping rule (DegUtils.c:416-424)
+      int maxni = 0;
+      for (int j = lane; j < T; j += 32) if (fds(Fbest, u + 6 * j, nullptr) < th && hd[j] > 100 * th) maxni++;
+      maxni = warp_sum_i(maxni);
+      if (lane == 0) {
+        deg->max_i = max_i; deg->have_F = 1;
+        for (int i = 0; i < 9; i++) deg->Fpp[i] = Fbest[i];
+        const int ns = nsamples(maxni, nN, 2, 0.999);
+        if (ns < deg->max_sam) deg->max_sam = ns;
+      }
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    deg->no_sam += nhyp;
+    deg->done = deg->no_sam >= 2 * deg->max_sam;
+  }
+}
+
+__global__ void __launch_bounds__(32)
+k_rfd_finish(const double* __restrict__ u, int T, double th, double conf, RfState* st, const DegShare* deg) {
+  const int lane = threadIdx.x;
+  if (!st->degen_pending) return;
+  if (deg->have_F && deg->max_i > st->I) {          // exp_ranF.c:990-996 `if (I > maxS.I)`
+    double F[9];
+    for (int i = 0; i < 9; i++) F[i] = deg->Fpp[i];
+    int I; double J;
+    f_score_all(u, T, F, th, nullptr, nullptr, lane, &I, &J);
+    if (lane == 0) {
+      for (int i = 0; i < 9; i++) st->F[i] = F[i];
+      st->I = I; st->J = J;
+      const int ns = nsamples(st->I + 1, T, 7, conf);
+      if (ns < st->max_sam) st->max_sam = ns;
+      st->done = st->no_sam >= st->max_sam;
+    }
+  }
+  __syncwarp();
+  if (lane == 0) { st->degen_cnt++; st->degen_pending = 0; }
+}
+
 __global__ void k_rf_final(const double* __restrict__ u, int T, double th, const RfState* st, unsigned char* inl) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= T) return;
@@ -564,7 +890,10 @@ __global__ void k_rf_final(const double* __restrict__ u, int T, double th, const
 int mg_ransac_F_run(modsgpu_ctx* ctx, const double* d_u, int T, const modsgpu_ransac_params* p,
                     double* F, unsigned char* inl, modsgpu_ransac_result* res) {
   const int NW = RF_NW;
-  size_t off_sh = 256, off_hyp = off_sh + ((sizeof(FLoShare) + 255) & ~(size_t)255), off_d = off_hyp + sizeof(FHyp) * RS_MAX_B;
+  static_assert(sizeof(RfState) <= 512, "state slot");
+  size_t off_sh = 512, off_hsh = off_sh + ((sizeof(FLoShare) + 255) & ~(size_t)255);
+  size_t off_deg = off_hsh + ((sizeof(LoShare) + 255) & ~(size_t)255);
+  size_t off_hyp = off_deg + ((sizeof(DegShare) + 255) & ~(size_t)255), off_d = off_hyp + sizeof(FHyp) * RS_MAX_B;
   size_t off_i = off_d + sizeof(double) * (size_t)(3 * NW + 1) * T;
   size_t off_inl = off_i + sizeof(int) * (size_t)(NW + 1) * T;
   size_t total = off_inl + T + 64;
@@ -572,6 +901,9 @@ int mg_ransac_F_run(modsgpu_ctx* ctx, const double* d_u, int T, const modsgpu_ra
   uint8_t* base = ctx->rs_buf.as<uint8_t>();
   RfState* st = reinterpret_cast<RfState*>(base);
   FLoShare* sh = reinterpret_cast<FLoShare*>(base + off_sh);
+  LoShare* hsh = reinterpret_cast<LoShare*>(base + off_hsh);
+  DegShare* deg = reinterpret_cast<DegShare*>(base + off_deg);
+  const int do_degen = getenv("MODSGPU_NO_DEGENSAC") ? 0 : 1;
   FHyp* hyp = reinterpret_cast<FHyp*>(base + off_hyp);
   double* dscr = reinterpret_cast<double*>(base + off_d);
   int* iscr = reinterpret_cast<int*>(base + off_i);
@@ -589,7 +921,7 @@ int mg_ransac_F_run(modsgpu_ctx* ctx, const double* d_u, int T, const modsgpu_ra
     k_rf_hyp<<<ceil_div(B, 8), 256, 0, ctx->stream>>>(d_u, T, p->th, p->seed, basei, B, hyp);
     MG_LAUNCHED(ctx);
     MG_PROF(ctx, "k_rf_select", 2, (double)T);
-    k_rf_select<<<1, 384, 0, ctx->stream>>>(d_u, T, p->th, p->do_sym_check, hyp, B, 0, st, sh, dscr, iscr);
+    k_rf_select<<<1, 384, 0, ctx->stream>>>(d_u, T, p->th, p->do_sym_check, do_degen, hyp, B, 0, st, sh, dscr, iscr);
     MG_LAUNCHED(ctx);
     MG_PROF(ctx, "k_rf_lo", 2, (double)T);
     k_rf_lo<<<LO_REPS, 32, 0, ctx->stream>>>(d_u, T, p->th, p->seed, sh, dscr, iscr);
@@ -598,11 +930,39 @@ int mg_ransac_F_run(modsgpu_ctx* ctx, const double* d_u, int T, const modsgpu_ra
     MG_LAUNCHED(ctx);
     MG_CUDA(ctx, cudaMemcpyAsync(hs, st, sizeof(RfState), cudaMemcpyDeviceToHost, ctx->stream));
     MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (hs->degen_pending) {
+      // DEGENSAC: plane homography by an inner H-RANSAC at 16*th, then plane-and-parallax
+      DegShare hd;
+      k_rfd_prep<<<1, 32, 0, ctx->stream>>>(d_u, T, p->th, st, hsh, dscr, iscr);
+      MG_LAUNCHED(ctx);
+      k_rs_lo<<<LO_REPS, 32, 0, ctx->stream>>>(d_u, T, 16 * p->th, p->seed, hsh, dscr, iscr);
+      MG_LAUNCHED(ctx);
+      k_rfd_h_accept<<<1, 32, 0, ctx->stream>>>(d_u, T, p->th, st, hsh, deg, dscr, iscr);
+      MG_LAUNCHED(ctx);
+      int pbase = batch * 1000003;
+      for (int it = 0; it < 64; it++) {
+        MG_CUDA(ctx, cudaMemcpyAsync(&hd, deg, sizeof(DegShare), cudaMemcpyDeviceToHost, ctx->stream));
+        MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (!hd.run_pp || hd.done) break;
+        MG_PROF(ctx, "k_rfd_pp_hyp", 2, (double)PP_B);
+        k_rfd_pp_hyp<<<ceil_div(PP_B, 8), 256, 0, ctx->stream>>>(d_u, T, p->th, p->seed, pbase, PP_B, deg, iscr,
+                                                               reinterpret_cast<PPHyp*>(hyp));
+        MG_LAUNCHED(ctx);
+        MG_PROF(ctx, "k_rfd_pp_update", 2, (double)T);
+        k_rfd_pp_update<<<1, 32, 0, ctx->stream>>>(d_u, T, p->th, p->seed, PP_B, deg, reinterpret_cast<const PPHyp*>(hyp), dscr, iscr);
+        MG_LAUNCHED(ctx);
+        pbase += PP_B;
+      }
+      k_rfd_finish<<<1, 32, 0, ctx->stream>>>(d_u, T, p->th, p->conf, st, deg);
+      MG_LAUNCHED(ctx);
+      MG_CUDA(ctx, cudaMemcpyAsync(hs, st, sizeof(RfState), cudaMemcpyDeviceToHost, ctx->stream));
+      MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     basei += B; batch++;
     if (hs->done) break;
   }
-  if (hs->lo_runs == 0) {   // exp_ranF.c:1086: "If there were no LOs, do at least one NOW!"
-    k_rf_select<<<1, 384, 0, ctx->stream>>>(d_u, T, p->th, p->do_sym_check, hyp, 0, 1, st, sh, dscr, iscr);
+  if (hs->lo_runs == 0 && hs->degen_cnt == 0) {   // exp_ranF.c:1086: "If there were no LOs, do at least one NOW!"
+    k_rf_select<<<1, 384, 0, ctx->stream>>>(d_u, T, p->th, p->do_sym_check, 0, hyp, 0, 1, st, sh, dscr, iscr);
     MG_LAUNCHED(ctx);
     k_rf_lo<<<LO_REPS, 32, 0, ctx->stream>>>(d_u, T, p->th, p->seed, sh, dscr, iscr);
     MG_LAUNCHED(ctx);
@@ -620,7 +980,8 @@ int mg_ransac_F_run(modsgpu_ctx* ctx, const double* d_u, int T, const modsgpu_ra
   for (int i = 0; i < T; i++) { if (!have) hinl[i] = 0; ninl += hinl[i]; }
   for (int i = 0; i < 9; i++) F[i] = have ? hs->F[i] : 0.0;
   memcpy(inl, hinl, T);
-  if (res) { res->n_inliers = ninl; res->J = hs->J; res->samples = hs->no_sam; res->lo_runs = hs->lo_runs; res->oc_rejects = hs->sym_rejects; }
+  if (res) { res->n_inliers = ninl; res->J = hs->J; res->samples = hs->no_sam; res->lo_runs = hs->lo_runs; res->oc_rejects = hs->sym_rejects;
+             res->degen_runs = hs->degen_cnt; res->h_inliers = hs->Ihmax; }
   return 0;
 }
 

@@ -89,8 +89,8 @@ def two_view_correspondences(seed, T, n_in, noise=0.5, w=1024, h=768, planar_fra
     R = Ry @ Rx
     t = np.array([1.0, 0.1, 0.2])
     X = np.c_[rng.uniform(-4, 4, 4 * T), rng.uniform(-3, 3, 4 * T), rng.uniform(4, 12, 4 * T)]
-    npl = int(planar_fraction * len(X))
-    X[:npl, 2] = 8.0 + 0.15 * X[:npl, 0]
+    on_plane = (np.arange(len(X)) % 100) < int(round(100 * planar_fraction))     # interleaved, so the kept subset mixes both
+    X[on_plane, 2] = 8.0 + 0.15 * X[on_plane, 0]
     x1 = (K @ X.T).T
     x1 = x1[:, :2] / x1[:, 2:3]
     Xc = (R @ X.T).T + t

@@ -556,10 +556,10 @@ int launch_conv(modsgpu_ctx* ctx, const __half* in, size_t in_slots, const ConvW
                 int patch_base = 0) {
   using Cfg = ConvCfg<CIN, COUT_T, NSPLIT, S, NGRP, OUT_MODE>;
   auto kern = k_conv_umma<CIN, COUT_T, NSPLIT, S, NGRP, OUT_MODE>;
-  static bool attr = false;
-  if (!attr) {
+  static OnceFlags attr;
+  if (attr.need(ctx->device)) {
     MG_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr = true;
+    attr.set(ctx->device);
   }
   const int ntiles = ceil_div(np * Cfg::PP, 128);
   static char pname[64] = {0};
@@ -695,11 +695,11 @@ int mg_net_forward_enqueue(modsgpu_ctx* ctx, modsgpu_net net, const uint8_t* d_p
       if ((rc = launch_conv<32, 32, 1, 16, 1, OUT_PARITY>(ctx, nw->act[2], nw->slots[2], nw->conv[2], nw->act[3], nw->slots[3], np))) return rc;
       if ((rc = launch_conv<32, 64, 1, 8, 4, OUT_NORMAL>(ctx, nw->act[3], nw->slots[3], nw->conv[3], nw->act[4], nw->slots[4], np))) return rc;
       if ((rc = launch_conv<64, 64, 1, 8, 1, OUT_NORMAL>(ctx, nw->act[4], nw->slots[4], nw->conv[4], nw->act[5], nw->slots[5], np))) return rc;
-      static bool hattr = false;
-      if (!hattr) {
+      static OnceFlags hattr;
+      if (hattr.need(ctx->device)) {
         MG_CUDA(ctx, cudaFuncSetAttribute(k_head_small<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 4096 * 4));
         MG_CUDA(ctx, cudaFuncSetAttribute(k_head_small<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4096 * 4));
-        hattr = true;
+        hattr.set(ctx->device);
       }
       const int hgrid = std::min(ceil_div(np, 8), 2 * ctx->num_sms);
       MG_PROF(ctx, net == MODSGPU_AFFNET ? "k_head_aff" : "k_head_ori", 1, 2.0 * np * (net == MODSGPU_AFFNET ? 12288.0 : 61952.0));
@@ -711,8 +711,8 @@ int mg_net_forward_enqueue(modsgpu_ctx* ctx, modsgpu_net net, const uint8_t* d_p
     }
   }
   if (net == MODSGPU_HARDNET) {
-    static bool attr = false;
-    if (!attr) { MG_CUDA(ctx, cudaFuncSetAttribute(k_head_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, HG_SMEM)); attr = true; }
+    static OnceFlags attr;
+    if (attr.need(ctx->device)) { MG_CUDA(ctx, cudaFuncSetAttribute(k_head_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, HG_SMEM)); attr.set(ctx->device); }
     MG_PROF(ctx, "k_head_gemm", 1, 2.0 * n * 8192.0 * 128);
     k_head_gemm<<<dim3(m_pad / 128, HG_KSPLIT), 192, HG_SMEM, ctx->stream>>>(act6all, (size_t)m_pad, nw->head_w16, part, m_pad);
     MG_LAUNCHED(ctx);

@@ -129,6 +129,18 @@ static inline int mg_end(modsgpu_ctx* ctx) {
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// cudaFuncSetAttribute is per device: a call site keeps one OnceFlags and asks whether this context's device still
+// needs the call.  Contexts of several threads may race here; the attribute call is idempotent, the flag is atomic.
+#include <atomic>
+struct OnceFlags {
+  std::atomic<unsigned long long> done{0};
+  bool need(int device) {
+    const unsigned long long bit = 1ull << (device & 63);
+    return (done.load(std::memory_order_acquire) & bit) == 0;
+  }
+  void set(int device) { done.fetch_or(1ull << (device & 63), std::memory_order_release); }
+};
+
 // Gaussian taps exactly as cv::getGaussianKernel(ksize,(double)sigma,CV_32F) produces them for the
 // ksize rule of helpers.cpp:717-731: ksize=(int)(2*3*sigma+1), forced odd.  Returns ksize.
 int mg_gaussian_taps(float sigma, std::vector<float>& taps);

@@ -650,11 +650,11 @@ int launch_blur(modsgpu_ctx* ctx, const float* src, float* dst, float* resp, int
   memset(&taps, 0, sizeof(taps));
   taps.ks = ks;
   for (int i = 0; i < ks; i++) taps.k[i] = t[i];
-  static bool attr_set = false;
-  if (!attr_set) {
+  static OnceFlags attr_set;
+  if (attr_set.need(ctx->device)) {
     MG_CUDA(ctx, cudaFuncSetAttribute(k_blur_resp, cudaFuncAttributeMaxDynamicSharedMemorySize, blur_smem_bytes(MAX_KS)));
     MG_CUDA(ctx, cudaFuncSetAttribute(k_blur_resp2, cudaFuncAttributeMaxDynamicSharedMemorySize, blur2_smem_bytes(MAX_KS)));
-    attr_set = true;
+    attr_set.set(ctx->device);
   }
   dim3 grid(ceil_div(w, BT_X), ceil_div(h, BT_Y));
   MG_PROF(ctx, resp ? "k_blur_resp" : "k_blur", 0, (double)w * h * 4.0 * (resp ? 3 : 2));

@@ -335,8 +335,8 @@ int mg_match_enqueue(modsgpu_ctx* ctx, const float* d_q, int nq, const float* d_
   int qblk = (int)std::min<size_t>((size_t)nq_pad, std::max<size_t>(128, ((size_t)256 << 20) / ((size_t)nt_pad * 4) / 128 * 128));
   MG_CUDA(ctx, ctx->mt_d.ensure((size_t)qblk * nt_pad * 4));
   const int smem = 2 * npl * 2048 + 512 + 64;
-  static bool attr = false;
-  if (!attr) { MG_CUDA(ctx, cudaFuncSetAttribute(k_dist_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 32 * 2048 + 512 + 64)); attr = true; }
+  static OnceFlags attr;
+  if (attr.need(ctx->device)) { MG_CUDA(ctx, cudaFuncSetAttribute(k_dist_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 32 * 2048 + 512 + 64)); attr.set(ctx->device); }
   const double sq = ratio_thr * ratio_thr, cd = contrad_dist * contrad_dist;
   for (int q0 = 0; q0 < nq; q0 += qblk) {
     const int rows_pad = std::min(qblk, nq_pad - q0), rows = std::min(qblk, nq - q0);

@@ -789,14 +789,14 @@ int mg_sample_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
   const float* dtaps = reinterpret_cast<const float*>(ctx->smp_meta.as<uint8_t>() + meta_bytes);
   const int* dpre1 = reinterpret_cast<const int*>(ctx->smp_meta.as<uint8_t>() + meta_bytes + taps_bytes);
   const int* dpre2 = reinterpret_cast<const int*>(ctx->smp_meta.as<uint8_t>() + meta_bytes + taps_bytes + pre_bytes);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static OnceFlags attr_set;
+  if (attr_set.need(ctx->device)) {
     MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_small, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SMALL));
     MG_CUDA(ctx, cudaFuncSetAttribute(k_large_rowpass, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (MAX_PS + 640 + L2_ROWS * MAX_R) * 4));
     MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_a, cudaFuncAttributeMaxDynamicSharedMemorySize, a_smem_floats(A2_R, 30) * 4));
     MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_b, cudaFuncAttributeMaxDynamicSharedMemorySize, b_smem_floats(B2_R, 30) * 4));
-    attr_set = true;
+    attr_set.set(ctx->device);
   }
   // algorithmic bytes: R*R*4 read + ps*ps written per region
   auto alg_bytes = [&](const std::vector<PatchMeta>& v) {

@@ -337,36 +337,56 @@ def run_gpu(args, rank, world, local_rank):
     value = world * args.steps / (dev_ms * 1e-3)
     e2e_value = world * args.steps / (e2e_ms * 1e-3)
     total_kernel_ms = sum(v["ms"] for v in prof.values()) or 1.0
-    top = max((k for k in prof if prof[k]["kind"] in ALG), key=lambda k: prof[k]["ms"], default=None)
+    # "dominant kernel" = the __global__ function (all template instantiations together) with the largest accumulated time
+    # among those with an algorithmic work figure; latency-bound helpers (kind 2) are listed in `kernels` only
+    groups = {}
+    for k, v in prof.items():
+        if v["kind"] not in ALG:
+            continue
+        g = groups.setdefault(k.split("<")[0], {"ms": 0.0, "launches": 0, "flops": 0.0, "bytes": 0.0, "members": []})
+        g["ms"] += v["ms"]
+        g["launches"] += v["launches"]
+        g["flops"] += v["work"] if v["kind"] == 1 else 0.0
+        g["bytes"] += v["work"] if v["kind"] == 0 else v.get("bytes", 0.0)
+        g["members"].append(k)
+    top = max(groups, key=lambda k: groups[k]["ms"], default=None)
     roofline = None
     if top:
-        p = prof[top]
-        bound, unit, scale = ALG[p["kind"]]
-        achieved = p["work"] / (p["ms"] * 1e-3) / scale
-        if bound == "hbm":
-            peak, src = peaks.get("hbm_gbs", 6650.0), ("MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.65 TB/s")
+        g = groups[top]
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        hbm_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+        tc_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        tc_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if "bf16_tflops_sustained" in peaks else "fallback 1400 TFLOP/s"
+        gbs = g["bytes"] / (g["ms"] * 1e-3) / 1e9
+        tfs = g["flops"] / (g["ms"] * 1e-3) / 1e12
+        # the bound is the resource the kernel sits closer to (its layers differ: small-channel layers stream activations,
+        # the wide ones are paced by the MMA pipe); both fractions are reported
+        if g["flops"] > 0 and tfs / tc_peak > gbs / hbm_peak:
+            bound, achieved, peak, unit, src = "tensor", tfs, tc_peak, "TFLOP/s", tc_src
         else:
-            peak = peaks.get("bf16_tflops_sustained", 1400.0)
-            src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback"
+            bound, achieved, peak, unit, src = "hbm", gbs, hbm_peak, "GB/s", hbm_src
         # DRAM traffic of that kernel from the committed `ncu --set full` capture (one launch, the grid named there)
         traffic, traffic_of = None, None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
             for name, rec in tj.items():
-                if top.startswith(name) or name.startswith(top.split("<")[0]):
+                if top.startswith(name) or name.startswith(top):
                     traffic = rec["dram_bytes_read"] + rec["dram_bytes_write"]
-                    traffic_of = "one launch, grid %s (%s)" % (rec["grid"], rec["source"])
+                    traffic_of = "one launch, %s grid %s (%s); algorithmic bytes of that launch %s" % (
+                        rec.get("instance", name), rec["grid"], rec["source"], rec.get("algorithmic_bytes"))
                     break
         except (OSError, ValueError, KeyError):
             pass
-        roofline = {"kernel": top, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
-                    "frac": achieved / peak, "traffic": traffic, "traffic_of": traffic_of, "peak_source": src,
-                    "launches": p["launches"], "avg_us": 1e3 * p["ms"] / max(p["launches"], 1),
-                    "share_of_kernel_time": p["ms"] / total_kernel_ms}
+        roofline = {"kernel": top, "instantiations": sorted(g["members"]), "bound": bound, "achieved": achieved, "peak": peak,
+                    "unit": unit, "frac": achieved / peak, "traffic": traffic, "traffic_of": traffic_of, "peak_source": src,
+                    "hbm_gbs": gbs, "hbm_frac": gbs / hbm_peak, "tensor_tflops": tfs, "tensor_frac": tfs / tc_peak,
+                    "launches": g["launches"], "avg_us": 1e3 * g["ms"] / max(g["launches"], 1),
+                    "share_of_kernel_time": g["ms"] / total_kernel_ms}
     kernels = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
                    "share": v["ms"] / total_kernel_ms,
                    "achieved": (v["work"] / (v["ms"] * 1e-3) / ALG[v["kind"]][2]) if v["kind"] in ALG and v["ms"] > 0 else None,
-                   "unit": ALG[v["kind"]][1] if v["kind"] in ALG else "latency-bound"}
+                   "unit": ALG[v["kind"]][1] if v["kind"] in ALG else "latency-bound",
+                   "hbm_gbs": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v.get("bytes") and v["ms"] > 0 else None}
                for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

@@ -282,8 +282,28 @@ int  modsgpu_mods_pair(modsgpu_ctx* ctx, modsgpu_image* img1, modsgpu_image* img
                        int n_steps, int min_matches, int use_F, unsigned long long seed, modsgpu_mods_result* res,
                        double* inlier_xy, int capacity);
 
+/* ---- pre-extracted regions (`read_pre_extracted`, mods.cpp:216-229): the reference re-loads region files instead of
+ *      detecting, then matches them.  Readers (host only, *out malloc()ed -> modsgpu_free):
+ *   npz  = ImageRepresentation::PreLoadRegionsNPZ / LoadRegionsNPZ (imagerepresentation.cpp:1355-1512): members xy [N,2],
+ *          scales [N], responses [N], descs [N,D<=128] (taken as uchar) + A [N,4] | angles [N] (degrees) | neither
+ *          (upright);  type = DET_READ (structures.hpp:20).  Any numeric dtype is converted like cnpy's typed views
+ *          would be for the dtypes SaveRegionsNPZ writes (float64 / uint8).
+ *   text = ImageRepresentation::LoadRegions (:1317-1354) with loadAR / loadKP (:237-253).  NB the reference's own
+ *          SaveRegions (:1219) writes saveAR records, which LoadRegions cannot read back (reference quirk, kept);
+ *          this reader follows LoadRegions.
+ *   modsgpu_match_features = the matching half of a mods.cpp step on two region lists: MatchFlannFGINN (linear) ->
+ *          DuplicateFiltering -> LORANSACFiltering (H, or F when use_F).  res->views are 0. */
+int  modsgpu_read_regions_npz(const char* path, modsgpu_feature** out, int* n);
+int  modsgpu_read_regions_text(const char* path, modsgpu_feature** out, int* n);
+int  modsgpu_match_features(modsgpu_ctx* ctx, const modsgpu_feature* f1, int n1, const modsgpu_feature* f2, int n2,
+                            int desc_dim, double fginn_threshold, int use_F, unsigned long long seed,
+                            modsgpu_mods_result* res, double* inlier_xy, int capacity);
+
 /* test-only: one 128x32x64 GEMM through the tcgen05 descriptor conventions of the dense kernels */
 int  modsgpu_debug_umma_probe(modsgpu_ctx* ctx, const float* A, const float* B, float* D, int swap_lbo_sbo);
+/* test / profiling only: cycles per tcgen05.mma (M128 K16) for a given operand-descriptor configuration;
+ * cfg = {n, a_off_bytes, a_lbo, a_sbo, b_lbo, b_sbo, layout_type, reps, n_accumulators, a_step_bytes, grid} */
+int  modsgpu_debug_umma_pace(modsgpu_ctx* ctx, const int* cfg, double* cycles_per_mma);
 
 /* ---- measurement helpers used by bench.py ---------------------------------------------------------------- */
 /* per-launch CUDA-event timing of every kernel (aggregated by kernel name); report is a JSON object */

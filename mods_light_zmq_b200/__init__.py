@@ -369,6 +369,17 @@ class ModsGpu:
                     unique_tentatives=res.unique_tentatives, inliers=res.inliers, model=np.array(list(res.model)),
                     inlier_xy=xy[:min(res.inliers, capacity)].copy())
 
+    def match_features(self, f1, f2, desc_dim=128, fginn=0.8, use_F=False, seed=12345, capacity=8192):
+        """modsgpu_match_features: the `read_pre_extracted` path of mods.cpp:216-229 + :262-356 on two region lists."""
+        f1 = np.ascontiguousarray(f1, FEATURE_DTYPE)
+        f2 = np.ascontiguousarray(f2, FEATURE_DTYPE)
+        res = ModsResult()
+        xy = np.zeros((capacity, 4), np.float64)
+        self._check(self.lib.modsgpu_match_features(self.ctx, _p(f1), len(f1), _p(f2), len(f2), int(desc_dim), C.c_double(fginn),
+                                                    int(bool(use_F)), C.c_ulonglong(seed), C.byref(res), _p(xy), capacity))
+        return dict(regions=list(res.regions), tentatives=res.tentatives, unique_tentatives=res.unique_tentatives,
+                    inliers=res.inliers, model=np.array(list(res.model)), inlier_xy=xy[:min(res.inliers, capacity)].copy())
+
     def ransac_F(self, u, th=16.0, conf=0.99, max_samples=1000000, sym_check=1, seed=12345):
         """modsgpu_ransac_F: LO-RANSAC for a fundamental matrix (exp_ransacFcustom, matching.cpp:722)."""
         u = np.ascontiguousarray(u, np.float64)
@@ -412,6 +423,25 @@ def write_regions(path, feats, fmt=None):
     rc = getattr(load_library(), fn)(str(path).encode(), _p(feats), len(feats))
     if rc != 0:
         raise ModsGpuError("%s failed (%d)" % (fn, rc))
+
+
+def read_regions(path, fmt=None):
+    """LoadRegionsNPZ (file name ending in .npz) / LoadRegions (text), imagerepresentation.cpp:1317-1512; needs no GPU."""
+    if fmt is None:
+        fmt = "npz" if str(path).endswith(".npz") else "text"
+    fn = {"npz": "modsgpu_read_regions_npz", "text": "modsgpu_read_regions_text"}[fmt]
+    lib = load_library()
+    out, n = C.c_void_p(), C.c_int()
+    rc = getattr(lib, fn)(str(path).encode(), C.byref(out), C.byref(n))
+    if rc != 0:
+        raise ModsGpuError("%s failed (%d)" % (fn, rc))
+    try:
+        if n.value == 0:
+            return np.zeros(0, FEATURE_DTYPE)
+        buf = (C.c_char * (n.value * FEATURE_DTYPE.itemsize)).from_address(out.value)
+        return np.frombuffer(buf, FEATURE_DTYPE).copy()
+    finally:
+        lib.modsgpu_free(out)
 
 
 def _pair_dict(res, xy):

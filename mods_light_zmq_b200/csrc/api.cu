@@ -56,10 +56,10 @@ extern "C" long long modsgpu_launch_count(const modsgpu_ctx* ctx) { return ctx ?
 extern "C" void* modsgpu_stream(const modsgpu_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 // ---- measurement helpers (bench.py) -------------------------------------------------------------------
-void mg_prof_begin(modsgpu_ctx* ctx, const char* name, int kind, double work) {
+void mg_prof_begin(modsgpu_ctx* ctx, const char* name, int kind, double work, double bytes) {
   Profiler& P = ctx->prof;
   ProfRec r;
-  r.name = name; r.kind = kind; r.work = work;
+  r.name = name; r.kind = kind; r.work = work; r.bytes = bytes;
   for (cudaEvent_t* e : {&r.e0, &r.e1}) {
     if (!P.pool.empty()) { *e = P.pool.back(); P.pool.pop_back(); }
     else cudaEventCreate(e);
@@ -81,7 +81,7 @@ static void prof_collect(modsgpu_ctx* ctx) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
       ProfAgg& a = P.agg[r.name];
-      a.kind = r.kind; a.launches++; a.ms += ms; a.work += r.work;
+      a.kind = r.kind; a.launches++; a.ms += ms; a.work += r.work; a.bytes += r.bytes;
     }
     P.pool.push_back(r.e0); P.pool.push_back(r.e1);
   }
@@ -95,7 +95,7 @@ extern "C" int modsgpu_profile_enable(modsgpu_ctx* ctx, int on) {
   ctx->prof.on = on != 0;
   return 0;
 }
-// JSON: {"kernel": {"kind": k, "launches": n, "ms": total, "work": total}, ...}; returns the length needed
+// JSON: {"kernel": {"kind": k, "launches": n, "ms": total, "work": total, "bytes": total (flop-kind kernels)}, ...}; returns the length needed
 extern "C" int modsgpu_profile_report(modsgpu_ctx* ctx, char* buf, int cap) {
   if (!ctx) return MODSGPU_EINVAL;
   prof_collect(ctx);
@@ -103,8 +103,8 @@ extern "C" int modsgpu_profile_report(modsgpu_ctx* ctx, char* buf, int cap) {
   bool first = true;
   for (auto& kv : ctx->prof.agg) {
     char tmp[512];
-    snprintf(tmp, sizeof(tmp), "%s\"%s\": {\"kind\": %d, \"launches\": %lld, \"ms\": %.6f, \"work\": %.6e}", first ? "" : ", ",
-             kv.first.c_str(), kv.second.kind, kv.second.launches, kv.second.ms, kv.second.work);
+    snprintf(tmp, sizeof(tmp), "%s\"%s\": {\"kind\": %d, \"launches\": %lld, \"ms\": %.6f, \"work\": %.6e, \"bytes\": %.6e}", first ? "" : ", ",
+             kv.first.c_str(), kv.second.kind, kv.second.launches, kv.second.ms, kv.second.work, kv.second.bytes);
     s += tmp;
     first = false;
   }

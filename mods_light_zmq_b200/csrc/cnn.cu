@@ -166,7 +166,10 @@ k_conv_umma(const __half* __restrict__ in, size_t in_slots, const __half* __rest
   uint64_t* t_empty = bars + 3 + 2 * NST;   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + 2 * NST);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: the compiler then knows the role branches are warp-uniform and keeps descriptors,
+  // barrier addresses and loop counters in uniform registers (otherwise every tcgen05.mma / bulk copy is wrapped
+  // in an R2UR + ELECT + branch "waterfall", measured at ~100-146 cycles per MMA instead of the 8-32 cycle floor)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const int nsp = blockIdx.y;  // which COUT_T slice of the output channels
 
   if (threadIdx.x == 0) {
@@ -182,18 +185,21 @@ k_conv_umma(const __half* __restrict__ in, size_t in_slots, const __half* __rest
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ---- producer: weights once, then one A tile (NPL planes) per M tile
+    // ---- producer (whole warp walks the loop, one elected lane issues): weights once, then one A tile (NPL planes) per M tile
+    if (elect_one()) {
       mbar_expect_tx(w_full, Cfg::W_BYTES);
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(wts) + (size_t)nsp * Cfg::W_BYTES;
       for (int off = 0; off < Cfg::W_BYTES; off += 32768) {
         int bytes = Cfg::W_BYTES - off < 32768 ? Cfg::W_BYTES - off : 32768;
         bulk_g2s(w_s + off, wsrc + off, bytes, w_full);
       }
-      int it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
-        const int s = it % NST, ph = (it / NST) & 1;
-        mbar_wait(a_empty + s, ph ^ 1);
+    }
+    __syncwarp();
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+      const int s = it % NST, ph = (it / NST) & 1;
+      mbar_wait(a_empty + s, ph ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(a_full + s, Cfg::A_BYTES);
         const size_t slot0 = (size_t)FS + (size_t)tile * 128 - Cfg::HALO_LO;
         uint8_t* dst = a_s + s * Cfg::A_BYTES;
@@ -201,22 +207,26 @@ k_conv_umma(const __half* __restrict__ in, size_t in_slots, const __half* __rest
         for (int pl = 0; pl < Cfg::NPL; pl++)
           bulk_g2s(dst + pl * Cfg::TP * 16, in + ((size_t)pl * in_slots + slot0) * 8, Cfg::TP * 16, a_full + s);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---- MMA issuer
-      constexpr uint32_t idesc = instr_desc_f16(COUT_T);
-      mbar_wait(w_full, 0);
-      const uint32_t w_addr = smem_u32(w_s);
-      int it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
-        const int s = it % NST, ph = (it / NST) & 1;
-        const int ts = it & 1, tph = (it >> 1) & 1;
-        mbar_wait(t_empty + ts, tph ^ 1);
-        mbar_wait(a_full + s, ph);
-        fence_after_sync();
-        const uint32_t a_addr = smem_u32(a_s + s * Cfg::A_BYTES);
-        const uint32_t d_tmem = tmem_base + ts * COUT_T;
+    // ---- MMA issuer: the warp waits together, one elected lane issues the 9 x KSTEPS MMAs of the tile back to back
+    constexpr uint32_t idesc = instr_desc_f16(COUT_T);
+    mbar_wait(w_full, 0);
+    const uint32_t w_addr = smem_u32(w_s);
+    const uint64_t a_desc0 = smem_desc(smem_u32(a_s), Cfg::TP * 16, 128);
+    const uint64_t b_desc0 = smem_desc(w_addr, COUT_T * 16, 128);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+      const int s = it % NST, ph = (it / NST) & 1;
+      const int ts = it & 1, tph = (it >> 1) & 1;
+      mbar_wait(t_empty + ts, tph ^ 1);
+      mbar_wait(a_full + s, ph);
+      fence_after_sync();
+      // descriptors differ from tile/tap/k-step only in the 16-byte start-address field (bits 0-13): plain adds
+      const uint64_t a_tile = a_desc0 + (uint64_t)((s * Cfg::A_BYTES) >> 4);
+      const uint32_t d_tmem = tmem_base + ts * COUT_T;
+      if (elect_one()) {
 #pragma unroll
         for (int t = 0; t < 9; t++) {
           const int dy = t / 3, dx = t % 3;
@@ -228,14 +238,15 @@ k_conv_umma(const __half* __restrict__ in, size_t in_slots, const __half* __rest
           }
 #pragma unroll
           for (int ks = 0; ks < Cfg::KSTEPS; ks++) {
-            const uint32_t a = a_addr + ((grp * Cfg::C8 + 2 * ks) * Cfg::TP + Cfg::HALO_LO + shift) * 16;
-            const uint32_t b = w_addr + ((t * Cfg::KSTEPS + ks) * 2 * COUT_T) * 16;
-            mma_f16(d_tmem, smem_desc(a, Cfg::TP * 16, 128), smem_desc(b, COUT_T * 16, 128), idesc, (t | ks) != 0);
+            const int a_off16 = (grp * Cfg::C8 + 2 * ks) * Cfg::TP + Cfg::HALO_LO + shift;     // >= 0
+            const int b_off16 = (t * Cfg::KSTEPS + ks) * 2 * COUT_T;
+            mma_f16(d_tmem, a_tile + (uint64_t)a_off16, b_desc0 + (uint64_t)b_off16, idesc, (t | ks) != 0);
           }
         }
         mma_commit(a_empty + s);   // smem tile may be refilled once these MMAs retire
         mma_commit(t_full + ts);   // accumulator ready for the epilogue
       }
+      __syncwarp();
     }
   } else {
     // ---- epilogue warps 2..5: TMEM -> bias + ReLU -> fp16 -> next layer's layout
@@ -304,7 +315,7 @@ k_head_gemm(const __half* __restrict__ act, size_t slots, const __half* __restri
   uint64_t* empty = bars + HG_STAGES;    // [3]
   uint64_t* t_full = bars + 2 * HG_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * HG_STAGES + 1);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform roles (see k_conv_umma)
   const int m0 = blockIdx.x * 128, ksp = blockIdx.y;
   constexpr int NKB = HG_NKB / HG_KSPLIT;
   const int kb0 = ksp * NKB;
@@ -319,10 +330,10 @@ k_head_gemm(const __half* __restrict__ act, size_t slots, const __half* __restri
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   if (warp == 0) {
-    if (lane == 0) {
-      for (int i = 0; i < NKB; i++) {
-        const int kb = kb0 + i, s = i % HG_STAGES, ph = (i / HG_STAGES) & 1;
-        mbar_wait(empty + s, ph ^ 1);
+    for (int i = 0; i < NKB; i++) {
+      const int kb = kb0 + i, s = i % HG_STAGES, ph = (i / HG_STAGES) & 1;
+      mbar_wait(empty + s, ph ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(full + s, HG_STAGE_BYTES);
         uint8_t* dst = smem + s * HG_STAGE_BYTES;
 #pragma unroll 1
@@ -330,21 +341,24 @@ k_head_gemm(const __half* __restrict__ act, size_t slots, const __half* __restri
           bulk_g2s(dst + pl * 2048, act + ((size_t)(kb * 16 + pl) * slots + m0) * 8, 2048, full + s);
         bulk_g2s(dst + 32768, wts + (size_t)kb * 16384, 32768, full + s);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = instr_desc_f16(128);
-      for (int i = 0; i < NKB; i++) {
-        const int s = i % HG_STAGES, ph = (i / HG_STAGES) & 1;
-        mbar_wait(full + s, ph);
-        fence_after_sync();
-        const uint32_t a_addr = smem_u32(smem + s * HG_STAGE_BYTES), b_addr = a_addr + 32768;
+    constexpr uint32_t idesc = instr_desc_f16(128);
+    const uint64_t a_desc0 = smem_desc(smem_u32(smem), 2048, 128), b_desc0 = smem_desc(smem_u32(smem) + 32768, 2048, 128);
+    for (int i = 0; i < NKB; i++) {
+      const int s = i % HG_STAGES, ph = (i / HG_STAGES) & 1;
+      mbar_wait(full + s, ph);
+      fence_after_sync();
+      const uint64_t so = (uint64_t)((s * HG_STAGE_BYTES) >> 4);
+      if (elect_one()) {
 #pragma unroll
         for (int j = 0; j < 8; j++)
-          mma_f16(tmem_base, smem_desc(a_addr + j * 4096, 2048, 128), smem_desc(b_addr + j * 4096, 2048, 128), idesc, (i | j) != 0);
+          mma_f16(tmem_base, a_desc0 + so + (uint64_t)(j * 256), b_desc0 + so + (uint64_t)(j * 256), idesc, (i | j) != 0);
         mma_commit(empty + s);
+        if (i == NKB - 1) mma_commit(t_full);
       }
-      mma_commit(t_full);
+      __syncwarp();
     }
   } else {
     const int q = warp & 3, m = q * 32 + lane;
@@ -515,6 +529,51 @@ k_umma_probe(const __half* __restrict__ A, const __half* __restrict__ B, float* 
 }
 
 // =================================================================================================
+// pacing probe (tests / profiling only): `reps` back-to-back tcgen05.mma (M = 128, K = 16, runtime N) from one
+// thread, operands = zero-filled shared memory, descriptor fields given by the caller.  Returns the clock64
+// span from the first issue to the commit's mbarrier flip.  Used to measure how the operand layout (row
+// alignment of the A start address, LBO/SBO, swizzle mode) paces the MMA pipe.
+// =================================================================================================
+__global__ void __launch_bounds__(128, 1)
+k_umma_pace(int n, int a_off_bytes, int a_lbo, int a_sbo, int b_lbo, int b_sbo, int layout, int reps, int n_acc, int a_step_bytes,
+            long long* __restrict__ cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];        // 96 KB A region + 32 KB B region, zeroed
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tslot;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < (131072 / 16); i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc<512>(&tslot);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tb = tslot;
+  if (__shfl_sync(0xffffffffu, threadIdx.x >> 5, 0) == 0) {     // warp-uniform branch: operands stay in uniform registers
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t a0 = smem_u32(smem) + 4096 + a_off_bytes, b0 = smem_u32(smem) + 98304;
+    const uint64_t lay = (uint64_t)(layout & 7) << 61;
+    const uint64_t db = smem_desc(b0, b_lbo, b_sbo) | lay;
+    const uint64_t da = smem_desc(a0, a_lbo, a_sbo) | lay;
+    const uint32_t astep = (uint32_t)a_step_bytes >> 4;
+    const uint32_t tstep = (n_acc > 1) ? (uint32_t)n : 0u;
+    const long long t0 = clock64();
+    if (elect_one()) {
+#pragma unroll 8
+      for (int r = 0; r < reps; r++)
+        mma_f16(tb + (r & 1) * tstep, da + (uint64_t)((r & 7) * astep), db, idesc, 1);
+      mma_commit(&bar);
+    }
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    if (threadIdx.x == 0) cycles[blockIdx.x] = clock64() - t0;
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tb);
+}
+
+// =================================================================================================
 // host side
 // =================================================================================================
 size_t plane_slots(int cap, int S) { return (size_t)FS + (size_t)round_up(cap * (S + 1) * (S + 1), 128) + 128; }
@@ -564,7 +623,8 @@ int launch_conv(modsgpu_ctx* ctx, const __half* in, size_t in_slots, const ConvW
   const int ntiles = ceil_div(np * Cfg::PP, 128);
   static char pname[64] = {0};
   if (!pname[0]) snprintf(pname, sizeof(pname), "k_conv_umma<%d,%d,S%d,%s>", CIN, Cfg::COUT, S, NGRP == 4 ? "s2" : "s1");
-  MG_PROF(ctx, pname, 1, 2.0 * np * S * S * 9.0 * CIN * Cfg::COUT);
+  constexpr int S_IN = NGRP == 4 ? 2 * S : S;   // stride-2 layers read the parity planes of a 2S x 2S map
+  MG_PROF2(ctx, pname, 1, 2.0 * np * S * S * 9.0 * CIN * Cfg::COUT, 2.0 * np * ((double)S_IN * S_IN * CIN + (double)S * S * Cfg::COUT));
   int gx = std::min(ntiles, std::max(1, ctx->num_sms / NSPLIT));
   dim3 grid(gx, NSPLIT);
   kern<<<grid, 192, Cfg::SMEM_BYTES, ctx->stream>>>(in, in_slots, w.w, w.b, out, out_slots, np, ntiles, patch_base);
@@ -678,7 +738,7 @@ int mg_net_forward_enqueue(modsgpu_ctx* ctx, modsgpu_net net, const uint8_t* d_p
     float* pout = d_out + (size_t)p0 * nw->out_dim;
     int rc = 0;
     if (net == MODSGPU_HARDNET) {
-      MG_PROF(ctx, "k_conv1<32>", 1, 2.0 * np * 1024 * 9 * 32);
+      MG_PROF2(ctx, "k_conv1<32>", 1, 2.0 * np * 1024 * 9 * 32, (double)np * (1024.0 + 1024.0 * 32 * 2));
       k_conv1<32><<<np, 256, 0, ctx->stream>>>(pin, np, nw->c1_w, nw->c1_b, nw->act[0], nw->slots[0]);
       MG_LAUNCHED(ctx);
       if ((rc = launch_conv<32, 32, 1, 32, 1, OUT_PARITY>(ctx, nw->act[0], nw->slots[0], nw->conv[0], nw->act[1], nw->slots[1], np))) return rc;
@@ -687,7 +747,7 @@ int mg_net_forward_enqueue(modsgpu_ctx* ctx, modsgpu_net net, const uint8_t* d_p
       if ((rc = launch_conv<64, 64, 2, 8, 4, OUT_NORMAL>(ctx, nw->act[3], nw->slots[3], nw->conv[3], nw->act[4], nw->slots[4], np))) return rc;
       if ((rc = launch_conv<128, 64, 2, 8, 1, OUT_GEMM>(ctx, nw->act[4], nw->slots[4], nw->conv[4], act6all, (size_t)m_pad, np, p0))) return rc;
     } else {
-      MG_PROF(ctx, "k_conv1<16>", 1, 2.0 * np * 1024 * 9 * 16);
+      MG_PROF2(ctx, "k_conv1<16>", 1, 2.0 * np * 1024 * 9 * 16, (double)np * (1024.0 + 1024.0 * 16 * 2));
       k_conv1<16><<<np, 256, 0, ctx->stream>>>(pin, np, nw->c1_w, nw->c1_b, nw->act[0], nw->slots[0]);
       MG_LAUNCHED(ctx);
       if ((rc = launch_conv<16, 16, 1, 32, 1, OUT_PARITY>(ctx, nw->act[0], nw->slots[0], nw->conv[0], nw->act[1], nw->slots[1], np))) return rc;
@@ -775,4 +835,30 @@ extern "C" int modsgpu_debug_umma_probe(modsgpu_ctx* ctx, const float* A, const 
   MG_LAUNCHED(ctx);
   MG_CUDA(ctx, cudaMemcpyAsync(D, ctx->io_c.p, 128 * 32 * 4, cudaMemcpyDeviceToHost, ctx->stream));
   return mg_end(ctx) ? MODSGPU_ECUDA : 0;
+}
+
+// test / profiling only: see k_umma_pace.  cfg = {n, a_off_bytes, a_lbo, a_sbo, b_lbo, b_sbo, layout, reps, n_acc, a_step_bytes, grid}
+extern "C" int modsgpu_debug_umma_pace(modsgpu_ctx* ctx, const int* cfg, double* cycles_per_mma) {
+  if (!ctx || !cfg || !cycles_per_mma) return MODSGPU_EINVAL;
+  const int n = cfg[0], reps = cfg[7], n_acc = cfg[8], grid = cfg[10];
+  if (n < 16 || n > 256 || n % 16 || reps < 1 || reps > (1 << 20) || n_acc < 1 || n_acc * n > 512 || grid < 1 || grid > 148 ||
+      cfg[1] < -4096 || cfg[1] > 16384 || (cfg[1] & 15))
+    MG_FAIL(ctx, MODSGPU_EINVAL, "umma_pace: bad configuration");
+  if (mg_begin(ctx)) return MODSGPU_ECUDA;
+  static OnceFlags attr;
+  if (attr.need(ctx->device)) {
+    MG_CUDA(ctx, cudaFuncSetAttribute(k_umma_pace, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
+    attr.set(ctx->device);
+  }
+  MG_CUDA(ctx, ctx->io_c.ensure(148 * 8));
+  k_umma_pace<<<grid, 128, 131072, ctx->stream>>>(n, cfg[1], cfg[2], cfg[3], cfg[4], cfg[5], cfg[6], reps, n_acc, cfg[9],
+                                                  ctx->io_c.as<long long>());
+  MG_LAUNCHED(ctx);
+  std::vector<long long> h(grid);
+  MG_CUDA(ctx, cudaMemcpyAsync(h.data(), ctx->io_c.p, grid * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (mg_end(ctx)) return MODSGPU_ECUDA;
+  long long mx = 0;
+  for (long long v : h) mx = v > mx ? v : mx;
+  *cycles_per_mma = (double)mx / reps;
+  return 0;
 }

@@ -54,8 +54,8 @@ struct NetWeights;  // cnn.cu
 
 // Optional per-launch CUDA-event timing (bench.py's roofline block).  kind: 0 = HBM-bound (work in bytes),
 // 1 = tensor-bound (work in flops), 2 = latency-bound (work = items).
-struct ProfRec { const char* name; int kind; double work; cudaEvent_t e0, e1; };
-struct ProfAgg { int kind = 0; long long launches = 0; double ms = 0, work = 0; };
+struct ProfRec { const char* name; int kind; double work, bytes; cudaEvent_t e0, e1; };
+struct ProfAgg { int kind = 0; long long launches = 0; double ms = 0, work = 0, bytes = 0; };
 struct Profiler {
   bool on = false;
   bool open = false;
@@ -89,10 +89,12 @@ struct modsgpu_ctx {
 
 cudaError_t mg_image_alloc(modsgpu_ctx* ctx, size_t bytes, float** out);
 
-void mg_prof_begin(modsgpu_ctx* ctx, const char* name, int kind, double work);
+void mg_prof_begin(modsgpu_ctx* ctx, const char* name, int kind, double work, double bytes = 0.0);
 void mg_prof_end(modsgpu_ctx* ctx);
 // call right before a kernel launch; MG_LAUNCHED closes the record
 #define MG_PROF(ctx, name, kind, work) do { if ((ctx)->prof.on) mg_prof_begin(ctx, name, kind, work); } while (0)
+// flop-counted kernels that also stream activations: `bytes` = algorithmic HBM bytes (inputs read once + outputs written once)
+#define MG_PROF2(ctx, name, kind, work, bytes) do { if ((ctx)->prof.on) mg_prof_begin(ctx, name, kind, work, bytes); } while (0)
 
 #define MG_CUDA(ctx, call)                                                                  \
   do {                                                                                      \

@@ -867,6 +867,139 @@ extern "C" int modsgpu_write_regions_npz(const char* path, const modsgpu_feature
 }
 
 
+// imagerepresentation.cpp:1355-1507 PreLoadRegionsNPZ: xy [N,2], scales [N], responses [N], descs [N,D] and either
+// A [N,4] (affine shape), angles [N] (degrees -> rotation) or neither (upright circular regions).  type = DET_READ.
+static const int DET_READ = 4;    // structures.hpp:16-20 detector_type (ReadAffs)
+extern "C" int modsgpu_read_regions_npz(const char* path, modsgpu_feature** out, int* n) {
+  if (!path || !out || !n) return MODSGPU_EINVAL;
+  *out = nullptr; *n = 0;
+  std::map<std::string, NpzRaw> z;
+  std::string err;
+  if (!npz_load_raw(path, z, err)) return MODSGPU_EIO;
+  for (const char* k : {"xy", "scales", "responses", "descs"})
+    if (!z.count(k) || !z[k].numeric()) return MODSGPU_EIO;
+  const NpzRaw &xy = z["xy"], &sc = z["scales"], &rs = z["responses"], &ds = z["descs"];
+  if (xy.shape.size() != 2 || xy.shape[1] != 2 || ds.shape.size() != 2) return MODSGPU_EIO;
+  const size_t N = (size_t)xy.shape[0];
+  const int D = ds.shape[1];
+  if (sc.count() != N || rs.count() != N || (size_t)ds.shape[0] != N || D < 1 || D > 128) return MODSGPU_EIO;
+  const NpzRaw* A = z.count("A") ? &z["A"] : nullptr;
+  const NpzRaw* ang = !A && z.count("angles") ? &z["angles"] : nullptr;
+  if (A && (!A->numeric() || A->count() != 4 * N)) return MODSGPU_EIO;
+  if (ang && (!ang->numeric() || ang->count() != N)) return MODSGPU_EIO;
+  modsgpu_feature* f = (modsgpu_feature*)calloc(N > 0 ? N : 1, sizeof(modsgpu_feature));
+  if (!f) return MODSGPU_EINVAL;
+  for (size_t i = 0; i < N; i++) {
+    f[i].x = xy.at(2 * i); f[i].y = xy.at(2 * i + 1);
+    f[i].s = sc.at(i);
+    if (A) { f[i].a11 = A->at(4 * i); f[i].a12 = A->at(4 * i + 1); f[i].a21 = A->at(4 * i + 2); f[i].a22 = A->at(4 * i + 3); }
+    else {
+      const double angle = ang ? ang->at(i) * M_PI / 180.0 : 0.0;
+      f[i].a11 = cos(angle); f[i].a12 = sin(angle); f[i].a21 = -sin(angle); f[i].a22 = cos(angle);
+    }
+    f[i].response = rs.at(i);
+    f[i].type = DET_READ;
+    for (int d = 0; d < D; d++) f[i].desc[d] = (float)(unsigned char)ds.at(i * D + d);   // descs_ is read as uchar (:1381)
+  }
+  *out = f; *n = (int)N;
+  return 0;
+}
+
+// imagerepresentation.cpp:1317-1354 LoadRegions (text) with loadAR / loadKP (:237-253): per region
+//   id img_id img_reproj_id parent_id | det_kp: x y a11 a12 a21 a22 pyramid_scale octave s sub_type | reproj_kp: same |
+//   desc_size d0 .. ;  every detector/descriptor list of the file is appended in file order.
+extern "C" int modsgpu_read_regions_text(const char* path, modsgpu_feature** out, int* n) {
+  if (!path || !out || !n) return MODSGPU_EINVAL;
+  *out = nullptr; *n = 0;
+  std::ifstream kpfile(path);
+  if (!kpfile.is_open()) return MODSGPU_EIO;
+  int numberOfDetectors = 0;
+  kpfile >> numberOfDetectors;
+  if (!kpfile || numberOfDetectors < 0) return MODSGPU_EIO;
+  std::vector<modsgpu_feature> v;
+  for (int det = 0; det < numberOfDetectors; det++) {
+    std::string det_name, desc_name;
+    int num_of_descs = 0;
+    kpfile >> det_name >> num_of_descs;
+    for (int desc = 0; desc < num_of_descs; desc++) {
+      int num_of_kp = 0, desc_size = 0;
+      kpfile >> desc_name >> num_of_kp;
+      if (num_of_kp > 0) kpfile >> desc_size;          // SaveRegions writes the size line only for non-empty lists (:1236)
+      if (!kpfile || num_of_kp < 0) return MODSGPU_EIO;
+      for (int kp = 0; kp < num_of_kp; kp++) {
+        modsgpu_feature f;
+        memset(&f, 0, sizeof(f));
+        int id, img_id, img_reproj_id, parent_id, size1 = 0;
+        double d[10], r[10];
+        kpfile >> id >> img_id >> img_reproj_id >> parent_id;
+        for (int k = 0; k < 10; k++) kpfile >> d[k];
+        for (int k = 0; k < 10; k++) kpfile >> r[k];
+        kpfile >> size1;
+        if (!kpfile || size1 < 0 || size1 > 128) return MODSGPU_EIO;
+        for (int k = 0; k < size1; k++) kpfile >> f.desc[k];
+        if (!kpfile) return MODSGPU_EIO;
+        f.x = r[0]; f.y = r[1]; f.a11 = r[2]; f.a12 = r[3]; f.a21 = r[4]; f.a22 = r[5];
+        f.octave = (int)r[7]; f.s = r[8]; f.type = (int)r[9];
+        f.view = img_reproj_id;
+        v.push_back(f);
+      }
+    }
+  }
+  modsgpu_feature* f = (modsgpu_feature*)malloc(sizeof(modsgpu_feature) * (v.size() ? v.size() : 1));
+  if (!f) return MODSGPU_EINVAL;
+  if (!v.empty()) memcpy(f, v.data(), sizeof(modsgpu_feature) * v.size());
+  *out = f; *n = (int)v.size();
+  return 0;
+}
+
+// mods.cpp:216-229 (`read_pre_extracted`) + :262-356: two pre-extracted region lists -> FGINN tentatives -> duplicate
+// filter -> LO-RANSAC.  The same three calls MODSPair makes per step.
+extern "C" int modsgpu_match_features(modsgpu_ctx* ctx, const modsgpu_feature* f1, int n1, const modsgpu_feature* f2, int n2,
+                                      int desc_dim, double fginn_threshold, int use_F, unsigned long long seed,
+                                      modsgpu_mods_result* res, double* inlier_xy, int capacity) {
+  using namespace modsb200;
+  if (!ctx || !res || n1 < 0 || n2 < 0 || (n1 > 0 && !f1) || (n2 > 0 && !f2) || desc_dim < 1 || desc_dim > 128 || capacity < 0)
+    return MODSGPU_EINVAL;
+  AffineRegionVector l[2];
+  const modsgpu_feature* src[2] = {f1, f2};
+  const int cnt[2] = {n1, n2};
+  for (int k = 0; k < 2; k++) {
+    l[k].resize((size_t)cnt[k]);
+    for (int i = 0; i < cnt[k]; i++) {
+      const modsgpu_feature& f = src[k][i];
+      AffineKeypoint& kp = l[k][i].reproj_kp;
+      kp.x = f.x; kp.y = f.y; kp.s = f.s; kp.a11 = f.a11; kp.a12 = f.a12; kp.a21 = f.a21; kp.a22 = f.a22;
+      kp.response = f.response; kp.octave_number = f.octave; kp.sub_type = f.type;
+      l[k][i].det_kp = kp;
+      l[k][i].id = i; l[k][i].img_id = k; l[k][i].img_reproj_id = f.view; l[k][i].type = f.type;
+      l[k][i].desc.assign(f.desc, f.desc + desc_dim);
+    }
+  }
+  memset(res, 0, sizeof(*res));
+  res->steps_done = 1;
+  res->regions[0] = n1; res->regions[1] = n2;
+  MatchPars mp;
+  mp.FGINNThreshold = fginn_threshold;
+  TentativeCorrespListExt tent, verified;
+  int nt = MatchFlannFGINN(ctx, l[0], l[1], tent, mp);
+  if (nt < 0) return nt;
+  res->tentatives = nt;
+  int nu = DuplicateFiltering(ctx, tent, mp.doubleFilteringRadius);
+  if (nu < 0) return nu;
+  res->unique_tentatives = nu;
+  RANSACPars rp;
+  rp.seed = seed; rp.useF = use_F;
+  int ni = LORANSACFiltering(ctx, tent, verified, res->model, rp);
+  if (ni < 0) return ni;
+  res->inliers = ni;
+  for (int i = 0; i < ni && i < capacity && inlier_xy; i++) {
+    const TentativeCorrespExt& c = verified.TCList[i];
+    inlier_xy[4 * i + 0] = c.first.reproj_kp.x; inlier_xy[4 * i + 1] = c.first.reproj_kp.y;
+    inlier_xy[4 * i + 2] = c.second.reproj_kp.x; inlier_xy[4 * i + 3] = c.second.reproj_kp.y;
+  }
+  return 0;
+}
+
 // MODS run over an iteration schedule (mods.cpp:202-356, HessianAffine steps)
 extern "C" int modsgpu_mods_pair(modsgpu_ctx* ctx, modsgpu_image* img1, modsgpu_image* img2, const modsgpu_mods_step* steps,
                                  int n_steps, int min_matches, int use_F, unsigned long long seed, modsgpu_mods_result* res,

@@ -53,7 +53,7 @@ k_dist_umma(const __half* __restrict__ qp, int nq_pad, const __half* __restrict_
   float* tn_s = reinterpret_cast<float*>(smem + 2 * npl * 2048);
   uint64_t* bars = reinterpret_cast<uint64_t*>(tn_s + 128);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform role branch
   const int n0 = blockIdx.x * 128, m0 = blockIdx.y * 128;
   if (threadIdx.x == 0) { mbar_init(bars, 1); mbar_init(bars + 1, 1); fence_barrier_init(); }
   if (warp == 0) tmem_alloc<128>(tmem_slot);
@@ -62,19 +62,26 @@ k_dist_umma(const __half* __restrict__ qp, int nq_pad, const __half* __restrict_
   __syncthreads();
   fence_after_sync();
   const uint32_t tb = *tmem_slot;
-  if (threadIdx.x == 0) {
-    mbar_expect_tx(bars, 2 * npl * 2048);
-    for (int pl = 0; pl < npl; pl++) {
-      bulk_g2s(a_s + pl * 2048, qp + ((size_t)pl * nq_pad + m0) * 8, 2048, bars);
-      bulk_g2s(b_s + pl * 2048, tp + ((size_t)pl * nt_pad + n0) * 8, 2048, bars);
+  if (warp == 0) {
+    // the warp waits together; one elected lane issues copies and MMAs (operands stay in uniform registers)
+    if (elect_one()) {
+      mbar_expect_tx(bars, 2 * npl * 2048);
+      for (int pl = 0; pl < npl; pl++) {
+        bulk_g2s(a_s + pl * 2048, qp + ((size_t)pl * nq_pad + m0) * 8, 2048, bars);
+        bulk_g2s(b_s + pl * 2048, tp + ((size_t)pl * nt_pad + n0) * 8, 2048, bars);
+      }
     }
+    __syncwarp();
     mbar_wait(bars, 0);
     fence_after_sync();
     constexpr uint32_t idesc = instr_desc_f16(128);
-    const uint32_t a = smem_u32(a_s), b = smem_u32(b_s);
-    for (int ks = 0; ks < dim / 16; ks++)
-      mma_f16(tb, smem_desc(a + ks * 4096, 2048, 128), smem_desc(b + ks * 4096, 2048, 128), idesc, ks != 0);
-    mma_commit(bars + 1);
+    const uint64_t da = smem_desc(smem_u32(a_s), 2048, 128), db = smem_desc(smem_u32(b_s), 2048, 128);
+    if (elect_one()) {
+      for (int ks = 0; ks < dim / 16; ks++)
+        mma_f16(tb, da + (uint64_t)(ks * 256), db + (uint64_t)(ks * 256), idesc, ks != 0);
+      mma_commit(bars + 1);
+    }
+    __syncwarp();
   }
   mbar_wait(bars + 1, 0);
   fence_after_sync();

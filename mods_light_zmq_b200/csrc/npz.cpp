@@ -12,7 +12,7 @@ namespace {
 uint32_t rd32(const unsigned char* p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
 uint16_t rd16(const unsigned char* p) { return (uint16_t)(p[0] | (p[1] << 8)); }
 
-bool parse_npy(const std::vector<unsigned char>& raw, NpzArray& a, std::string& err) {
+bool parse_npy_raw(const std::vector<unsigned char>& raw, NpzRaw& a, std::string& err) {
   if (raw.size() < 10 || memcmp(raw.data(), "\x93NUMPY", 6) != 0) { err = "not an npy member"; return false; }
   int major = raw[6];
   size_t hlen, hoff;
@@ -20,7 +20,14 @@ bool parse_npy(const std::vector<unsigned char>& raw, NpzArray& a, std::string& 
   else { hlen = rd32(&raw[8]); hoff = 12; }
   if (hoff + hlen > raw.size()) { err = "truncated npy header"; return false; }
   std::string hdr((const char*)&raw[hoff], hlen);
-  if (hdr.find("'<f4'") == std::string::npos) { err = "npy dtype is not <f4"; return false; }
+  size_t dp = hdr.find("'descr':");
+  if (dp == std::string::npos) { err = "npy header without descr"; return false; }
+  size_t q1 = hdr.find('\'', dp + 8), q2 = q1 == std::string::npos ? q1 : hdr.find('\'', q1 + 1);
+  if (q2 == std::string::npos) { err = "bad descr"; return false; }
+  a.descr = hdr.substr(q1 + 1, q2 - q1 - 1);
+  if (a.descr.size() < 3) { err = "unsupported npy dtype " + a.descr; return false; }
+  const int item = atoi(a.descr.c_str() + 2);
+  if (item <= 0 || (a.descr[0] == '>' && item > 1)) { err = "unsupported npy dtype " + a.descr; return false; }
   if (hdr.find("'fortran_order': False") == std::string::npos) { err = "npy is fortran ordered"; return false; }
   size_t sp = hdr.find("'shape':");
   if (sp == std::string::npos) { err = "npy header without shape"; return false; }
@@ -35,20 +42,21 @@ bool parse_npy(const std::vector<unsigned char>& raw, NpzArray& a, std::string& 
     if (s >= e) break;
     char* q;
     long v = strtol(s, &q, 10);
-    if (q == s) break;
+    if (q == s || v < 0) break;
     a.shape.push_back((int)v);
     n *= (size_t)v;
     s = q;
   }
   size_t doff = hoff + hlen;
-  if (doff + n * 4 > raw.size()) { err = "npy payload shorter than its shape"; return false; }
-  a.data.resize(n);
-  memcpy(a.data.data(), &raw[doff], n * 4);
+  if (doff + n * (size_t)item > raw.size()) { err = "npy payload shorter than its shape"; return false; }
+  a.bytes.assign(raw.begin() + doff, raw.begin() + doff + n * (size_t)item);
   return true;
 }
+
 }  // namespace
 
-bool npz_load(const char* path, std::map<std::string, NpzArray>& out, std::string& err) {
+namespace {
+bool read_members(const char* path, std::map<std::string, NpzRaw>& out, std::string& err) {
   FILE* f = fopen(path, "rb");
   if (!f) { err = std::string("cannot open ") + path; return false; }
   fseek(f, 0, SEEK_END);
@@ -88,11 +96,54 @@ bool npz_load(const char* path, std::map<std::string, NpzArray>& out, std::strin
       if (rc != Z_STREAM_END) { err = "inflate failed for " + name; return false; }
     } else { err = "unsupported zip method in " + name; return false; }
     if (name.size() > 4 && name.substr(name.size() - 4) == ".npy") name = name.substr(0, name.size() - 4);
-    NpzArray a;
-    if (!parse_npy(raw, a, err)) { err += " (" + name + ")"; return false; }
+    NpzRaw a;
+    if (!parse_npy_raw(raw, a, err)) { err += " (" + name + ")"; return false; }
     out[name] = std::move(a);
   }
   return true;
+}
+}  // namespace
+
+bool npz_load_raw(const char* path, std::map<std::string, NpzRaw>& out, std::string& err) { return read_members(path, out, err); }
+
+bool npz_load(const char* path, std::map<std::string, NpzArray>& out, std::string& err) {
+  std::map<std::string, NpzRaw> raw;
+  if (!read_members(path, raw, err)) return false;
+  for (auto& kv : raw) {
+    if (kv.second.descr != "<f4") { err = "npy dtype is not <f4 (" + kv.first + ")"; return false; }
+    NpzArray a;
+    a.shape = kv.second.shape;
+    a.data.resize(kv.second.bytes.size() / 4);
+    memcpy(a.data.data(), kv.second.bytes.data(), a.data.size() * 4);
+    out[kv.first] = std::move(a);
+  }
+  return true;
+}
+
+size_t NpzRaw::count() const { size_t n = 1; for (int v : shape) n *= (size_t)v; return n; }
+
+// element i as double, for the dtypes numpy / cnpy write for region files (f8, f4, u1, i4, i8, u2 ...)
+double NpzRaw::at(size_t i) const {
+  const char k = descr[1];
+  const int item = atoi(descr.c_str() + 2);
+  const unsigned char* p = bytes.data() + i * (size_t)item;
+  if (k == 'f' && item == 8) { double v; memcpy(&v, p, 8); return v; }
+  if (k == 'f' && item == 4) { float v; memcpy(&v, p, 4); return v; }
+  if (k == 'u' && item == 1) return *p;
+  if (k == 'i' && item == 1) return (signed char)*p;
+  if (k == 'b' && item == 1) return *p != 0;
+  if (k == 'u' && item == 2) { uint16_t v; memcpy(&v, p, 2); return v; }
+  if (k == 'i' && item == 2) { int16_t v; memcpy(&v, p, 2); return v; }
+  if (k == 'u' && item == 4) { uint32_t v; memcpy(&v, p, 4); return v; }
+  if (k == 'i' && item == 4) { int32_t v; memcpy(&v, p, 4); return v; }
+  if (k == 'u' && item == 8) { uint64_t v; memcpy(&v, p, 8); return (double)v; }
+  if (k == 'i' && item == 8) { int64_t v; memcpy(&v, p, 8); return (double)v; }
+  return 0.0;
+}
+bool NpzRaw::numeric() const {
+  const char k = descr[1];
+  const int item = atoi(descr.c_str() + 2);
+  return (k == 'f' && (item == 4 || item == 8)) || ((k == 'u' || k == 'i') && (item == 1 || item == 2 || item == 4 || item == 8)) || (k == 'b' && item == 1);
 }
 
 

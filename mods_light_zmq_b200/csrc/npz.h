@@ -11,6 +11,18 @@ struct NpzArray {
 };
 bool npz_load(const char* path, std::map<std::string, NpzArray>& out, std::string& err);
 
+// Any-dtype member (region files: float64 xy/scales/responses/A/angles, uint8 descs -- cnpy::NpyArray's role in
+// PreLoadRegionsNPZ, imagerepresentation.cpp:1355-1507)
+struct NpzRaw {
+  std::vector<int> shape;
+  std::string descr;                 // e.g. "<f8", "|u1"
+  std::vector<unsigned char> bytes;
+  size_t count() const;
+  bool numeric() const;
+  double at(size_t i) const;
+};
+bool npz_load_raw(const char* path, std::map<std::string, NpzRaw>& out, std::string& err);
+
 // Minimal .npz writer (zip archive of .npy members, stored uncompressed like cnpy::npz_save does):
 // NpzWriter w(path); w.add("xy", "<f8", {n, 2}, ptr, bytes); ... w.close();
 struct NpzWriter {

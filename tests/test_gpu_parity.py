@@ -728,3 +728,95 @@ def test_pair_pipeline_classic_config1(mg, oracle):
     corners = np.array([[0, 0, 1], [799, 0, 1], [0, 639, 1], [799, 639, 1], [400, 320, 1.0]])
     pa, pb = corners @ Hn.T, corners @ Ht.T
     assert np.linalg.norm(pa[:, :2] / pa[:, 2:3] - pb[:, :2] / pb[:, 2:3], axis=1).max() < 2.0
+
+
+# ------------------------------------------------------------------------------------------ error behaviour of the C ABI
+def test_error_codes_and_messages(tmp_path):
+    """The reference's convention: integer returns, no exceptions.  Wrong arguments -> MODSGPU_EINVAL (-3), unreadable or
+    malformed weight files -> MODSGPU_EIO (-4), describe before modsgpu_load_weights -> MODSGPU_ESTATE (-5), each with
+    a message in modsgpu_last_error; empty inputs succeed with empty outputs."""
+    import ctypes as C
+    import mods_light_zmq_b200 as M
+    from mods_light_zmq_b200 import synth
+    g = M.ModsGpu(0, load_nets=False)
+    lib, ctx = g.lib, g.ctx
+    img = g.image_from_bgr8(synth.gray_to_bgr(synth.blob_image(seed=1, w=160, h=120, n_blobs=60)))
+    regs = M.regions_from_keypoints(g.detect(img))
+    assert len(regs) > 0
+    out = np.zeros((len(regs), 128), np.float32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.modsgpu_describe(ctx, M.HARDNET, img.handle, p(regs), len(regs), C.c_double(5.1962), 32, p(out))
+    assert rc == -5 and b"modsgpu_load_weights" in lib.modsgpu_last_error(ctx)
+    assert lib.modsgpu_load_weights(ctx, M.HARDNET, str(tmp_path / "missing.npz").encode()) == -4
+    bad = tmp_path / "bad.npz"
+    bad.write_bytes(b"not a zip archive")
+    assert lib.modsgpu_load_weights(ctx, M.AFFNET, str(bad).encode()) == -4 and len(lib.modsgpu_last_error(ctx)) > 0
+    np.savez(tmp_path / "wrong.npz", c1_w=np.zeros((16, 3, 3, 1), np.float32))          # missing members
+    assert lib.modsgpu_load_weights(ctx, M.AFFNET, str(tmp_path / "wrong.npz").encode()) == -4
+    assert lib.modsgpu_load_weights(ctx, 7, b"x") == -3
+    g.load_weights(M.AFFNET)
+    assert lib.modsgpu_describe(ctx, M.AFFNET, img.handle, p(regs), len(regs), C.c_double(5.1962), 31, p(out)) == -3   # nets take 32x32
+    assert lib.modsgpu_describe(ctx, M.AFFNET, img.handle, None, 5, C.c_double(5.1962), 32, p(out)) == -3
+    assert lib.modsgpu_describe(ctx, M.AFFNET, img.handle, p(regs), 0, C.c_double(5.1962), 32, p(out)) == 0       # nothing to do
+    pp = M.PyrParams()
+    lib.modsgpu_default_pyr_params(C.byref(pp))
+    pp.numberOfScales = 9
+    o, n = C.c_void_p(), C.c_int()
+    assert lib.modsgpu_detect(ctx, img.handle, C.byref(pp), C.byref(o), C.byref(n)) == -3
+    assert lib.modsgpu_image_from_bgr8(ctx, None, 10, 10, C.byref(o)) == -3
+    assert lib.modsgpu_create(99, C.byref(o)) == -1                                                   # no such device
+    H = np.zeros(9)
+    inl = np.zeros(4, np.uint8)
+    assert lib.modsgpu_ransac_H(ctx, None, 10, None, p(H), p(inl), None) == -3
+    # huge region: the sampler refuses instead of overflowing its window (R > 2048)
+    big = regs[:1].copy()
+    big["s"] = 400.0
+    assert lib.modsgpu_extract_patches(ctx, img.handle, p(big), 1, C.c_double(5.1962), 32, p(np.zeros(1024, np.uint8))) == -3
+    # the context is still usable after errors
+    assert len(g.detect(img)) == len(regs)
+    g.close()
+
+
+def test_batch_cli_single_rank(tmp_path):
+    """python -m mods_light_zmq_b200.batch imfnames.txt out_keys.txt (extract_features_batch.cpp) in-process, one rank."""
+    from mods_light_zmq_b200 import synth, batch
+    ins, outs = [], []
+    for i in range(2):
+        pth = tmp_path / ("b%d.npy" % i)
+        np.save(pth, synth.gray_to_bgr(synth.blob_image(seed=60 + i, w=256, h=192, n_blobs=200)))
+        ins.append(str(pth))
+        outs.append(str(tmp_path / ("b%d.%s" % (i, "npz" if i else "txt"))))
+    (tmp_path / "imgs.txt").write_text("\n".join(ins) + "\n")
+    (tmp_path / "outs.txt").write_text("\n".join(outs) + "\n")
+    assert batch.main([str(tmp_path / "imgs.txt"), str(tmp_path / "outs.txt")]) == 0
+    assert open(outs[0]).readline().strip() == "128"                     # OxAff text
+    z = np.load(outs[1])                                                  # .npz -> SaveRegionsNPZ layout
+    assert z["descs"].dtype == np.uint8 and z["xy"].shape[1] == 2 and len(z["xy"]) == len(z["descs"]) > 10
+
+
+def test_match_pre_extracted_regions(mg, synth_pair, tmp_path):
+    """`read_pre_extracted` (mods.cpp:216-229): regions written by SaveRegionsNPZ, re-loaded by LoadRegionsNPZ and matched
+    give the tentatives / unique tentatives / inliers / H of the in-memory pair pipeline (descriptors are integer-valued
+    and the geometry is float64 in the file, so the round trip is lossless)."""
+    import mods_light_zmq_b200 as M
+    from mods_light_zmq_b200 import synth
+    a, b, H = synth_pair
+    i1, i2 = mg.image_from_bgr8(synth.gray_to_bgr(a)), mg.image_from_bgr8(synth.gray_to_bgr(b))
+    ref = mg.pair_pipeline_images(i1, i2, seed=5)
+    feats = []
+    for k, im in enumerate((i1, i2)):
+        f = mg.extract_features(im)
+        M.write_regions(str(tmp_path / ("k%d.npz" % k)), f)
+        g = M.read_regions(str(tmp_path / ("k%d.npz" % k)))
+        assert len(g) == len(f) == ref["descriptors"][k] and np.array_equal(g["desc"], f["desc"])
+        feats.append(g)
+    r = mg.match_features(feats[0], feats[1], seed=5)
+    assert r["regions"] == ref["descriptors"]
+    for k in ("tentatives", "unique_tentatives", "inliers"):
+        assert r[k] == ref[k], k
+    assert np.array_equal(r["model"].reshape(3, 3), ref["H"]) and np.array_equal(r["inlier_xy"], ref["inlier_xy"])
+    # F model on the same lists; empty lists are not an error
+    rf = mg.match_features(feats[0], feats[1], use_F=True, seed=5)
+    assert rf["tentatives"] == ref["tentatives"] and rf["inliers"] >= 0.5 * ref["inliers"]
+    r0 = mg.match_features(feats[0][:0], feats[1])
+    assert r0["tentatives"] == 0 and r0["inliers"] == 0

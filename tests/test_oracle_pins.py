@@ -252,6 +252,55 @@ def test_region_text_and_npz_writers(tmp_path):
     assert np.load(p)["xy"].shape == (0, 2)
 
 
+def test_region_readers(tmp_path):
+    """LoadRegionsNPZ / PreLoadRegionsNPZ (imagerepresentation.cpp:1355-1512: A | angles | upright variants, descs as
+    uchar) and LoadRegions text with the loadAR record layout (:237-253, :1317-1354)."""
+    import mods_light_zmq_b200 as M
+    rng = np.random.RandomState(4)
+    n = 23
+    f = np.zeros(n, M.FEATURE_DTYPE)
+    for k in ("x", "y", "s", "a11", "a12", "a21", "a22", "response"):
+        f[k] = rng.uniform(0.5, 900, n)
+    f["desc"] = rng.randint(0, 256, (n, 128))
+    p = str(tmp_path / "r.npz")
+    M.write_regions(p, f)                                     # SaveRegionsNPZ -> LoadRegionsNPZ round trip, exact
+    g = M.read_regions(p)
+    for k in ("x", "y", "s", "a11", "a12", "a21", "a22", "response"):
+        assert np.array_equal(g[k], f[k]), k
+    assert np.array_equal(g["desc"], f["desc"]) and np.all(g["type"] == 4)          # DET_READ
+    # numpy-written files (compressed, angles in degrees, 64-dim descriptors, mixed dtypes)
+    ang = rng.uniform(-180, 180, n)
+    np.savez_compressed(tmp_path / "a.npz", xy=np.c_[f["x"], f["y"]], scales=f["s"].astype(np.float32), responses=f["response"],
+                        angles=ang, descs=f["desc"][:, :64].astype(np.uint8))
+    g = M.read_regions(str(tmp_path / "a.npz"))
+    a = ang * np.pi / 180.0
+    assert np.array_equal(g["a11"], np.cos(a)) and np.array_equal(g["a12"], np.sin(a)) and np.array_equal(g["a21"], -np.sin(a))
+    assert np.array_equal(g["s"], f["s"].astype(np.float32).astype(np.float64))
+    assert np.array_equal(g["desc"][:, :64], f["desc"][:, :64]) and not g["desc"][:, 64:].any()
+    np.savez(tmp_path / "u.npz", xy=np.c_[f["x"], f["y"]], scales=f["s"], responses=f["response"], descs=f["desc"].astype(np.uint8))
+    g = M.read_regions(str(tmp_path / "u.npz"))
+    assert np.all(g["a11"] == 1) and np.all(g["a12"] == 0) and np.all(g["a21"] == 0) and np.all(g["a22"] == 1)
+    np.savez(tmp_path / "bad.npz", xy=np.c_[f["x"], f["y"]], scales=f["s"])          # members missing -> error, no crash
+    with pytest.raises(M.ModsGpuError):
+        M.read_regions(str(tmp_path / "bad.npz"))
+    with pytest.raises(M.ModsGpuError):
+        M.read_regions(str(tmp_path / "nothere.npz"))
+    # text: 2 detectors, the second with an empty descriptor list
+    rows = []
+    for i in range(5):
+        kp = "%g %g %g %g %g %g 1.5 2 %g 1" % (f["x"][i], f["y"][i], f["a11"][i], f["a12"][i], f["a21"][i], f["a22"][i], f["s"][i])
+        rows.append("%d 0 3 -1 %s %s 128 %s" % (i, kp, kp, " ".join(str(int(v)) for v in f["desc"][i])))
+    (tmp_path / "r.txt").write_text("2\nHessianAffine 1\nZMQ 5\n128\n" + "\n".join(rows) + "\nMSER 1\nZMQ 0\n")
+    g = M.read_regions(str(tmp_path / "r.txt"))
+    assert len(g) == 5 and np.all(g["view"] == 3) and np.all(g["octave"] == 2) and np.all(g["type"] == 1)
+    for k in ("x", "y", "s", "a11", "a12", "a21", "a22"):
+        assert np.allclose(g[k], f[k][:5], rtol=1e-5), k
+    assert np.array_equal(g["desc"], f["desc"][:5])
+    (tmp_path / "t.txt").write_text("1\nHessianAffine 1\nZMQ 2\n128\n0 0 0 0 1 2\n")   # truncated record
+    with pytest.raises(M.ModsGpuError):
+        M.read_regions(str(tmp_path / "t.txt"))
+
+
 def test_oracle_matcher_small(oracle):
     rng = np.random.RandomState(0)
     t = rng.randint(0, 256, (70, 128)).astype(np.float32)

@@ -6,8 +6,9 @@ print("value %.1f e2e %.1f pairs/s  ms/step %.2f  launches/step %.0f  workers %s
     d["value"], d["e2e"]["value"], d["ms_per_step"], d["gpu_launches"] / d["steps"], d["config"].get("workers_per_gpu")))
 tot = 0
 for k, v in d["kernels"].items():
-    print("%-34s %7.3f ms %6.1f launches %5.1f%%  %s %s" % (k, v["ms_per_step"], v["launches_per_step"], 100 * v["share"],
-          v["achieved"] and round(v["achieved"], 2), v["unit"]))
+    print("%-34s %7.3f ms %6.1f launches %5.1f%%  %s %s%s" % (k, v["ms_per_step"], v["launches_per_step"], 100 * v["share"],
+          v["achieved"] and round(v["achieved"], 2), v["unit"],
+          ("  | %.0f GB/s algorithmic" % v["hbm_gbs"]) if v.get("hbm_gbs") else ""))
     tot += v["ms_per_step"]
 print("sum kernel ms/step %.2f" % tot)
 print("roofline", d["roofline"])

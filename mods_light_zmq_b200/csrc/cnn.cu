@@ -25,6 +25,7 @@
 #include "umma.cuh"
 #include "npz.h"
 #include <map>
+#include <mutex>
 
 using namespace umma;
 
@@ -45,6 +46,7 @@ struct NetWeights {
   float* head_w32 = nullptr;     // AffNet / OriNet head [Cout][8][8][64]
   float* head_b = nullptr;
   int cap = 0;                   // patches per chunk the activation buffers hold
+  bool fused12 = false;          // conv1 weights resident in c_conv1[net] on this device -> k_conv12 path
   __half* act[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t slots[6] = {0, 0, 0, 0, 0, 0};
 };
@@ -295,6 +297,275 @@ k_conv_umma(const __half* __restrict__ in, size_t in_slots, const __half* __rest
   fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// =================================================================================================
+// conv1 + conv2 fused: the 1 -> C1 first layer never leaves the SM.
+//
+//   loader (1 warp)      : bulk copies of the normalised pixels a tile touches, 8 tiles ahead
+//   producers (8 warps)  : conv1 on CUDA cores (fp32, the very FMA chain of k_conv1) for the tile's 196 activation
+//                          slots -> bias + ReLU -> fp16 -> A tile in shared memory, in the [C1/8 planes][196 rows][8]
+//                          layout k_conv_umma would have loaded from HBM
+//   MMA warp             : D = sum over 9 taps (row-shifted views of the A tile) * W2      conv2 on tcgen05
+//   epilogue (4 warps)   : D + bias -> ReLU -> fp16 -> HBM in the next layer's layout
+//
+// Only HBM traffic left: 4 KB of normalised pixels in, the conv2 map out (conv1's 32-64 KB map per patch is gone).
+// A first version ran conv1 on the tensor pipe as well (im2col rows, K = 32 with split hi/lo operands): with N = 16-32
+// every MMA re-reads 4 KB of A from shared memory, the pipe saturates the shared-memory port and the generic
+// LDS/STS of producers and epilogues starve (970-1740 busy cycles per tile in the accumulator->A-tile epilogue,
+// profiles/r01_conv12_stalls.txt); CUDA-core conv1 removes 28 KB of that traffic per tile.
+// =================================================================================================
+// per patch: mean / unbiased std of the 1024 pixels, then v = (px - mean) / (std + 1e-7) (desc_server.py:83-87, as k_conv1)
+__global__ void __launch_bounds__(256)
+k_patch_prep(const uint8_t* __restrict__ patches, int np, float* __restrict__ norm) {
+  __shared__ unsigned red[2][8];
+  __shared__ float s_mean, s_sd;
+  const int patch = blockIdx.x, tid = threadIdx.x;
+  const uchar4 px = reinterpret_cast<const uchar4*>(patches + (size_t)patch * 1024)[tid];
+  unsigned s1 = px.x + px.y + px.z + px.w;
+  unsigned s2 = px.x * px.x + px.y * px.y + px.z * px.z + px.w * px.w;
+  for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+  if ((tid & 31) == 0) { red[0][tid >> 5] = s1; red[1][tid >> 5] = s2; }
+  __syncthreads();
+  if (tid == 0) {
+    unsigned a = 0, q = 0;
+    for (int i = 0; i < 8; i++) { a += red[0][i]; q += red[1][i]; }
+    const double mean = (double)a / 1024.0;
+    double var = ((double)q - (double)a * mean) / 1023.0;
+    if (var < 0) var = 0;
+    s_mean = (float)mean;
+    s_sd = (float)sqrt(var) + 1e-7f;
+  }
+  __syncthreads();
+  const float mean = s_mean, sd = s_sd;
+  reinterpret_cast<float4*>(norm + (size_t)patch * 1024)[tid] =
+      make_float4(((float)px.x - mean) / sd, ((float)px.y - mean) / sd, ((float)px.z - mean) / sd, ((float)px.w - mean) / sd);
+}
+
+// conv1 weights of the three nets for k_conv12: [C1][9] weights then [C1] biases, read as FFMA constant operands
+// (uniform across the warp: every lane applies the same weight to its own pixel)
+__constant__ float c_conv1[3][32 * 9 + 32];
+
+template <int C1>
+struct Conv12Cfg {
+  static constexpr int PT = 33, PP = PT * PT, HALO = PT + 1, TP = 128 + 2 * HALO;   // S = 32: 196 rows of conv1 per tile
+  static constexpr int C8 = C1 / 8, KSTEPS = C1 / 16;
+  static constexpr int A_STAGES = 4, A_BYTES = C8 * TP * 16;
+  static constexpr int W2_BYTES = 9 * KSTEPS * 2 * C1 * 16;
+  // ring of raw pixel ranges, filled by bulk copies several tiles ahead: a tile's 196 slots touch at most 288
+  // consecutive pixels of the [np][1024] array (9 rows of 32; patches are adjacent in memory)
+  static constexpr int RAW_STAGES = 8, RAW_BYTES = 288 * 4;
+  static constexpr int OFF_W2 = 0, OFF_A = OFF_W2 + W2_BYTES, OFF_RAW = OFF_A + A_STAGES * A_BYTES;
+  static constexpr int OFF_BAR = OFF_RAW + RAW_STAGES * RAW_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 512;
+  static constexpr int TMEM_COLS = 2 * C1 <= 32 ? 32 : 64;               // D[2 stages][C1]
+  static constexpr int NTHREADS = 22 * 32;       // epilogue 0-3, MMA 4, producer group 0 = 5-12, group 1 = 13-20, loader 21
+};
+
+template <int C1, int NET, int OUT_MODE>
+__global__ void __launch_bounds__(704, 1)
+k_conv12(const float* __restrict__ norm, const __half* __restrict__ w2, const float* __restrict__ b2,
+         __half* __restrict__ out, size_t out_slots, int np, int ntiles, long long* __restrict__ dbg) {
+  using Cfg = Conv12Cfg<C1>;
+  constexpr int PT = Cfg::PT, PP = Cfg::PP, HALO = Cfg::HALO, TP = Cfg::TP, S = 32, NA = Cfg::A_STAGES;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* w2_s = smem + Cfg::OFF_W2;
+  uint8_t* a_s = smem + Cfg::OFF_A;
+  uint8_t* raw_s = smem + Cfg::OFF_RAW;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* w_full = bars;                          // W2 landed (bulk copy)
+  uint64_t* a_full = bars + 1;                      // [NA] 8 producer warps
+  uint64_t* a_empty = a_full + NA;                  // [NA] MMAs of the tile retired
+  uint64_t* d_full = a_empty + NA;                  // [2]  MMAs of the tile retired
+  uint64_t* d_empty = d_full + 2;                   // [2]  4 epilogue warps
+  uint64_t* raw_full = d_empty + 2;                 // [RAW_STAGES] bulk copy landed
+  uint64_t* raw_empty = raw_full + Cfg::RAW_STAGES; // [RAW_STAGES] 8 producer warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + Cfg::RAW_STAGES);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  // stall accounting (debug launches only): cycles each role spends in each mbarrier wait, CTA 0
+  long long stall[3] = {0, 0, 0};
+  const bool prof = dbg != nullptr && blockIdx.x == 0;
+  const long long t_start = prof ? clock64() : 0;
+#define TWAIT(slot, bar, par) do { if (prof) { const long long t0_ = clock64(); mbar_wait(bar, par); stall[slot] += clock64() - t0_; } else mbar_wait(bar, par); } while (0)
+  const int n_my = blockIdx.x < ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+
+  if (threadIdx.x == 0) {
+    mbar_init(w_full, 1);
+    for (int i = 0; i < NA; i++) { mbar_init(a_full + i, 8); mbar_init(a_empty + i, 1); }
+    for (int i = 0; i < 2; i++) { mbar_init(d_full + i, 1); mbar_init(d_empty + i, 4); }
+    for (int i = 0; i < Cfg::RAW_STAGES; i++) { mbar_init(raw_full + i, 1); mbar_init(raw_empty + i, 8); }
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // first pixel (index into norm) of the range a tile's rows can touch, and one past the last
+  auto raw_range = [&](int tile, int& lo, int& hi) {
+    const int g0 = tile * 128 - HALO, g1 = tile * 128 + 127 + HALO;
+    lo = 0;
+    if (g0 >= 0) { const int p = g0 / PP, yy = (g0 - p * PP) / PT; lo = p >= np ? np * 1024 : p * 1024 + max(yy - 2, 0) * 32; }
+    const int p = g1 / PP, yy = (g1 - p * PP) / PT;
+    hi = p >= np ? np * 1024 : p * 1024 + min(yy + 1, 32) * 32;
+  };
+  if (warp == 21) {
+    // ---- loader: W2 once, then the raw pixel range of every tile, RAW_STAGES tiles ahead of the producers
+    if (elect_one()) {
+      mbar_expect_tx(w_full, Cfg::W2_BYTES);
+      bulk_g2s(w2_s, w2, Cfg::W2_BYTES, w_full);
+    }
+    __syncwarp();
+    for (int it = 0; it < n_my; it++) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int s = it % Cfg::RAW_STAGES, ph = (it / Cfg::RAW_STAGES) & 1;
+      TWAIT(0, raw_empty + s, ph ^ 1);
+      int lo, hi;
+      raw_range(tile, lo, hi);
+      if (elect_one()) {
+        mbar_expect_tx(raw_full + s, (uint32_t)(hi - lo) * 4u);
+        if (hi > lo) bulk_g2s(raw_s + s * Cfg::RAW_BYTES, norm + lo, (uint32_t)(hi - lo) * 4u, raw_full + s);
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 5) {
+    // ---- producers: two groups of 8 warps take alternate tiles; thread = one activation slot of the tile (row r <-> slot
+    //      128*tile - HALO + r), all C1 output channels: 9 shared-memory loads, 9*C1 FFMAs with constant-bank weights
+    const int grp = warp >= 13 ? 1 : 0;
+    const int r = threadIdx.x - (grp ? 13 : 5) * 32;
+    for (int it = grp; it < n_my; it += 2) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int s = it % NA, ph = (it / NA) & 1;
+      const int rs = it % Cfg::RAW_STAGES, rph = (it / Cfg::RAW_STAGES) & 1;
+      int lo, hi;
+      raw_range(tile, lo, hi);
+      // branch-free: taps outside the patch read a clamped address and are zeroed by the select
+      const int g = tile * 128 - HALO + r;
+      const int gc = max(g, 0);
+      const int patch = gc / PP;
+      const int idx = gc - patch * PP;
+      const int yy = idx / PT, x = idx - yy * PT, y = yy - 1;
+      const bool valid = r < TP && g >= 0 && patch < np && yy >= 1 && x < S;
+      const int base = valid ? patch * 1024 - lo : 0;
+      const float* raw = reinterpret_cast<const float*>(raw_s + rs * Cfg::RAW_BYTES);
+      TWAIT(0, raw_full + rs, rph);
+      float v[9];
+#pragma unroll
+      for (int t = 0; t < 9; t++) {
+        const int py = y + t / 3 - 1, px = x + t % 3 - 1;
+        const bool inb = valid && py >= 0 && py < S && px >= 0 && px < S;
+        const float f = raw[inb ? base + py * 32 + px : 0];
+        v[t] = inb ? f : 0.f;
+      }
+      float acc[C1];
+#pragma unroll
+      for (int e = 0; e < C1; e++) acc[e] = c_conv1[NET][C1 * 9 + e];
+#pragma unroll
+      for (int t = 0; t < 9; t++)
+#pragma unroll
+        for (int e = 0; e < C1; e++) acc[e] = fmaf(c_conv1[NET][e * 9 + t], v[t], acc[e]);
+      uint32_t hw[C1 / 2];
+#pragma unroll
+      for (int e = 0; e < C1 / 2; e++) {
+        const __half2 h2 = __floats2half2_rn(valid ? fmaxf(acc[2 * e], 0.f) : 0.f, valid ? fmaxf(acc[2 * e + 1], 0.f) : 0.f);
+        hw[e] = *reinterpret_cast<const uint32_t*>(&h2);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(raw_empty + rs);      // this warp's reads of the raw stage are done
+      TWAIT(1, a_empty + s, ph ^ 1);
+      const long long tf0 = prof ? clock64() : 0;
+      if (r < TP) {
+#pragma unroll
+        for (int c8 = 0; c8 < Cfg::C8; c8++)
+          *reinterpret_cast<uint4*>(a_s + s * Cfg::A_BYTES + (c8 * TP + r) * 16) =
+              make_uint4(hw[4 * c8], hw[4 * c8 + 1], hw[4 * c8 + 2], hw[4 * c8 + 3]);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full + s);
+      if (prof) stall[2] += clock64() - tf0;
+    }
+  } else if (warp == 4) {
+    // ---- MMA issuer: 9 x KSTEPS MMAs per tile, back to back from one elected lane
+    constexpr uint32_t idesc = instr_desc_f16(C1);
+    const uint64_t a_desc0 = smem_desc(smem_u32(a_s), TP * 16, 128);
+    const uint64_t w2_desc0 = smem_desc(smem_u32(w2_s), C1 * 16, 128);
+    mbar_wait(w_full, 0);
+    for (int it = 0; it < n_my; it++) {
+      const int s = it % NA, ph = (it / NA) & 1;
+      const int ts = it & 1, tph = (it >> 1) & 1;
+      TWAIT(0, d_empty + ts, tph ^ 1);
+      TWAIT(1, a_full + s, ph);
+      fence_after_sync();
+      const uint64_t a = a_desc0 + (uint64_t)((s * Cfg::A_BYTES) >> 4);
+      const uint32_t d = tmem_base + ts * C1;
+      if (elect_one()) {
+#pragma unroll
+        for (int t = 0; t < 9; t++) {
+          const int shift = (t / 3 - 1) * PT + (t % 3 - 1);
+#pragma unroll
+          for (int ks = 0; ks < Cfg::KSTEPS; ks++)
+            mma_f16(d, a + (uint64_t)((2 * ks) * TP + HALO + shift), w2_desc0 + (uint64_t)((t * Cfg::KSTEPS + ks) * 2 * C1), idesc,
+                    (t | ks) != 0);
+        }
+        mma_commit(a_empty + s);
+        mma_commit(d_full + ts);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---- epilogue (warps 0..3): conv2 accumulators -> bias + ReLU -> fp16 -> next layer's layout (as k_conv_umma)
+    const int q = warp & 3, m = q * 32 + lane;
+    float bias2[C1];
+#pragma unroll
+    for (int e = 0; e < C1; e++) bias2[e] = __ldg(b2 + e);
+    for (int it = 0; it < n_my; it++) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int s = it & 1, ph = (it >> 1) & 1;
+      const int g = tile * 128 + m;
+      const int patch = g / PP;
+      const int idx = g - patch * PP;
+      const int yy = idx / PT, x = idx - yy * PT, y = yy - 1;
+      const bool valid = patch < np && yy >= 1 && x < S;
+      size_t oslot; int oplane0;
+      if (OUT_MODE == OUT_NORMAL) { oslot = (size_t)FS + g; oplane0 = 0; }
+      else {
+        constexpr int PT2 = S / 2 + 1, PP2 = PT2 * PT2;
+        oslot = (size_t)FS + (size_t)patch * PP2 + ((y >> 1) + 1) * PT2 + (x >> 1);
+        oplane0 = (((y & 1) << 1) | (x & 1)) * (C1 / 8);
+      }
+      TWAIT(0, d_full + s, ph);
+      fence_after_sync();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + s * C1;
+#pragma unroll
+      for (int cc = 0; cc < C1 / 16; cc++) {
+        float v[16];
+        tmem_ld16(taddr + cc * 16, v);
+        if (valid) {
+          __align__(16) __half hh[16];
+#pragma unroll
+          for (int e = 0; e < 16; e++) hh[e] = __float2half_rn(fmaxf(v[e] + bias2[cc * 16 + e], 0.f));
+          __half* o = out + ((size_t)(oplane0 + cc * 2) * out_slots + oslot) * 8;
+          *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(hh);
+          *reinterpret_cast<uint4*>(o + out_slots * 8) = *reinterpret_cast<const uint4*>(hh + 8);
+        }
+      }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(d_empty + s);
+    }
+  }
+#undef TWAIT
+  if (prof && lane == 0) {      // per warp: total cycles of the role loop and its stall counters
+    long long* o = dbg + warp * 4;
+    o[0] = clock64() - t_start; o[1] = stall[0]; o[2] = stall[1]; o[3] = stall[2];
+    if (warp == 0) dbg[22 * 4] = n_my;
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
 // =================================================================================================
@@ -632,6 +903,50 @@ int launch_conv(modsgpu_ctx* ctx, const __half* in, size_t in_slots, const ConvW
   return 0;
 }
 
+
+// conv1 + conv2 in one launch (k_conv12).  EXPERIMENTAL, opt-in with MODSGPU_FUSED_CONV12=1: parity-green but slower on
+// B200 than k_conv1 + k_conv_umma (profiles/r01_conv12_stalls.txt has the three variants and their stall tables).
+bool fused_conv12_enabled() {
+  static const bool on = [] { const char* e = getenv("MODSGPU_FUSED_CONV12"); return e && atoi(e) != 0; }();
+  return on;
+}
+template <int C1, int NET>
+int launch_conv12(modsgpu_ctx* ctx, const uint8_t* patches, const ConvW& w2, __half* out, size_t out_slots, int np) {
+  using Cfg = Conv12Cfg<C1>;
+  auto kern = k_conv12<C1, NET, OUT_PARITY>;
+  static OnceFlags attr;
+  if (attr.need(ctx->device)) {
+    MG_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr.set(ctx->device);
+  }
+  MG_CUDA(ctx, ctx->cnn_stats.ensure((size_t)np * 4096));
+  MG_PROF(ctx, "k_patch_prep", 0, (double)np * (1024.0 + 4096.0));
+  k_patch_prep<<<np, 256, 0, ctx->stream>>>(patches, np, ctx->cnn_stats.as<float>());
+  MG_LAUNCHED(ctx);
+  const int ntiles = ceil_div(np * Cfg::PP, 128);
+  static char pname[64] = {0};
+  if (!pname[0]) snprintf(pname, sizeof(pname), "k_conv12<1,%d,%d,S32>", C1, C1);
+  // algorithmic bytes: the normalised patch in, the conv2 map out (conv1's map stays on the SM)
+  MG_PROF2(ctx, pname, 1, 2.0 * np * 1024 * 9.0 * (C1 + (double)C1 * C1), (double)np * (4096.0 + 1024.0 * C1 * 2));
+  static const bool debug = [] { const char* e = getenv("MODSGPU_CONV12_DEBUG"); return e && atoi(e) != 0; }();
+  long long* dbg = nullptr;
+  if (debug) { MG_CUDA(ctx, ctx->io_c.ensure(23 * 4 * 8)); dbg = ctx->io_c.as<long long>(); }
+  kern<<<std::min(ntiles, ctx->num_sms), Cfg::NTHREADS, Cfg::SMEM_BYTES, ctx->stream>>>(
+      ctx->cnn_stats.as<float>(), w2.w, w2.b, out, out_slots, np, ntiles, dbg);
+  MG_LAUNCHED(ctx);
+  if (debug) {      // stall table of CTA 0 (cycles): role loop total, then its wait counters
+    long long h[23 * 4];
+    MG_CUDA(ctx, cudaMemcpyAsync(h, dbg, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const long long n = h[22 * 4] > 0 ? h[22 * 4] : 1;
+    fprintf(stderr, "k_conv12<%d> np %d tiles/CTA %lld (cycles per tile: loop, wait0, wait1, store+fence+arrive)\n", C1, np, n);
+    for (int w : {0, 3, 4, 5, 11, 13, 21})
+      fprintf(stderr, "  warp %2d %-4s %8.0f %8.0f %8.0f %8.0f\n", w, w < 4 ? "epi" : w == 4 ? "mma" : w == 21 ? "load" : "prod",
+              (double)h[w * 4] / n, (double)h[w * 4 + 1] / n, (double)h[w * 4 + 2] / n, (double)h[w * 4 + 3] / n);
+  }
+  return 0;
+}
+
 }  // namespace
 
 static void free_net(NetWeights* nw) {
@@ -671,6 +986,24 @@ extern "C" int modsgpu_load_weights(modsgpu_ctx* ctx, modsgpu_net net, const cha
   if (!w1 || !b1) { delete nw; MG_FAIL(ctx, MODSGPU_EIO, "weights: c1_w/c1_b missing or wrong shape"); }
   MG_CUDA(ctx, upload(&nw->c1_w, w1->data.data(), w1->data.size() * 4));
   MG_CUDA(ctx, upload(&nw->c1_b, b1->data.data(), b1->data.size() * 4));
+  {
+    // k_conv12 reads conv1's weights from the constant bank, one slot per (device, net).  The first context that loads a
+    // net on a device claims the slot; a context that loads DIFFERENT weights for it keeps the two-kernel path.
+    static std::mutex mu;
+    static std::map<std::pair<int, int>, std::vector<float>> resident;
+    std::vector<float> blob(w1->data);
+    blob.insert(blob.end(), b1->data.begin(), b1->data.end());
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = resident.find({ctx->device, (int)net});
+    if (it == resident.end()) {
+      MG_CUDA(ctx, cudaMemcpyToSymbol(c_conv1, blob.data(), blob.size() * 4, (size_t)net * (32 * 9 + 32) * 4));
+      resident[{ctx->device, (int)net}] = blob;
+      nw->fused12 = true;
+    } else {
+      nw->fused12 = it->second == blob;
+    }
+    nw->fused12 = nw->fused12 && fused_conv12_enabled();
+  }
   for (int l = 0; l < 5; l++) {
     std::string wn = "c" + std::to_string(l + 2) + "_w", bn = "c" + std::to_string(l + 2) + "_b";
     const NpzArray* w = need(wn.c_str(), {couts[l], 3, 3, cins[l]});
@@ -738,19 +1071,28 @@ int mg_net_forward_enqueue(modsgpu_ctx* ctx, modsgpu_net net, const uint8_t* d_p
     float* pout = d_out + (size_t)p0 * nw->out_dim;
     int rc = 0;
     if (net == MODSGPU_HARDNET) {
-      MG_PROF2(ctx, "k_conv1<32>", 1, 2.0 * np * 1024 * 9 * 32, (double)np * (1024.0 + 1024.0 * 32 * 2));
-      k_conv1<32><<<np, 256, 0, ctx->stream>>>(pin, np, nw->c1_w, nw->c1_b, nw->act[0], nw->slots[0]);
-      MG_LAUNCHED(ctx);
-      if ((rc = launch_conv<32, 32, 1, 32, 1, OUT_PARITY>(ctx, nw->act[0], nw->slots[0], nw->conv[0], nw->act[1], nw->slots[1], np))) return rc;
+      if (nw->fused12) {
+        if ((rc = launch_conv12<32, 2>(ctx, pin, nw->conv[0], nw->act[1], nw->slots[1], np))) return rc;
+      } else {
+        MG_PROF2(ctx, "k_conv1<32>", 1, 2.0 * np * 1024 * 9 * 32, (double)np * (1024.0 + 1024.0 * 32 * 2));
+        k_conv1<32><<<np, 256, 0, ctx->stream>>>(pin, np, nw->c1_w, nw->c1_b, nw->act[0], nw->slots[0]);
+        MG_LAUNCHED(ctx);
+        if ((rc = launch_conv<32, 32, 1, 32, 1, OUT_PARITY>(ctx, nw->act[0], nw->slots[0], nw->conv[0], nw->act[1], nw->slots[1], np))) return rc;
+      }
       if ((rc = launch_conv<32, 64, 1, 16, 4, OUT_NORMAL>(ctx, nw->act[1], nw->slots[1], nw->conv[1], nw->act[2], nw->slots[2], np))) return rc;
       if ((rc = launch_conv<64, 64, 1, 16, 1, OUT_PARITY>(ctx, nw->act[2], nw->slots[2], nw->conv[2], nw->act[3], nw->slots[3], np))) return rc;
       if ((rc = launch_conv<64, 64, 2, 8, 4, OUT_NORMAL>(ctx, nw->act[3], nw->slots[3], nw->conv[3], nw->act[4], nw->slots[4], np))) return rc;
       if ((rc = launch_conv<128, 64, 2, 8, 1, OUT_GEMM>(ctx, nw->act[4], nw->slots[4], nw->conv[4], act6all, (size_t)m_pad, np, p0))) return rc;
     } else {
-      MG_PROF2(ctx, "k_conv1<16>", 1, 2.0 * np * 1024 * 9 * 16, (double)np * (1024.0 + 1024.0 * 16 * 2));
-      k_conv1<16><<<np, 256, 0, ctx->stream>>>(pin, np, nw->c1_w, nw->c1_b, nw->act[0], nw->slots[0]);
-      MG_LAUNCHED(ctx);
-      if ((rc = launch_conv<16, 16, 1, 32, 1, OUT_PARITY>(ctx, nw->act[0], nw->slots[0], nw->conv[0], nw->act[1], nw->slots[1], np))) return rc;
+      if (nw->fused12) {
+        if ((rc = (net == MODSGPU_AFFNET ? launch_conv12<16, 0>(ctx, pin, nw->conv[0], nw->act[1], nw->slots[1], np)
+                                         : launch_conv12<16, 1>(ctx, pin, nw->conv[0], nw->act[1], nw->slots[1], np)))) return rc;
+      } else {
+        MG_PROF2(ctx, "k_conv1<16>", 1, 2.0 * np * 1024 * 9 * 16, (double)np * (1024.0 + 1024.0 * 16 * 2));
+        k_conv1<16><<<np, 256, 0, ctx->stream>>>(pin, np, nw->c1_w, nw->c1_b, nw->act[0], nw->slots[0]);
+        MG_LAUNCHED(ctx);
+        if ((rc = launch_conv<16, 16, 1, 32, 1, OUT_PARITY>(ctx, nw->act[0], nw->slots[0], nw->conv[0], nw->act[1], nw->slots[1], np))) return rc;
+      }
       if ((rc = launch_conv<16, 32, 1, 16, 4, OUT_NORMAL>(ctx, nw->act[1], nw->slots[1], nw->conv[1], nw->act[2], nw->slots[2], np))) return rc;
       if ((rc = launch_conv<32, 32, 1, 16, 1, OUT_PARITY>(ctx, nw->act[2], nw->slots[2], nw->conv[2], nw->act[3], nw->slots[3], np))) return rc;
       if ((rc = launch_conv<32, 64, 1, 8, 4, OUT_NORMAL>(ctx, nw->act[3], nw->slots[3], nw->conv[3], nw->act[4], nw->slots[4], np))) return rc;

@@ -78,6 +78,7 @@ struct modsgpu_ctx {
   DevBuf io_a, io_b, io_c;            // generic staging for the test-only entry points
   DevBuf smp_regs, smp_meta, smp_taps, smp_scratch, smp_out;
   DevBuf cnn_act0, cnn_act1, cnn_out;
+  DevBuf cnn_stats;                   // normalised patches (fp32) for the fused conv1+conv2 kernel
   DevBuf mt_q, mt_t, mt_d, mt_aux, mt_out;
   DevBuf rs_buf;
   NetWeights* nets[3] = {nullptr, nullptr, nullptr};

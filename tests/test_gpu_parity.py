@@ -2,12 +2,14 @@
 CPU oracle on the same seeded inputs.  Integer / index / byte outputs must be bit-exact; the network
 outputs carry the tolerances stated at the test (fp16 operands, fp32 accumulation)."""
 import os
+import sys
 
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
 GOLD = os.path.join(HERE, "golden")
 
 
@@ -820,3 +822,24 @@ def test_match_pre_extracted_regions(mg, synth_pair, tmp_path):
     assert rf["tentatives"] == ref["tentatives"] and rf["inliers"] >= 0.5 * ref["inliers"]
     r0 = mg.match_features(feats[0][:0], feats[1])
     assert r0["tentatives"] == 0 and r0["inliers"] == 0
+
+
+def test_fused_conv12_experimental_path_parity():
+    """MODSGPU_FUSED_CONV12=1 routes conv1+conv2 through k_conv12 (experimental, opt-in; the flag is read when the weights
+    are loaded).  Same tolerances as the product path, checked in a fresh process."""
+    import subprocess
+    code = ("import os, sys, numpy as np\n"
+            "sys.path.insert(0, %r)\n"
+            "import mods_light_zmq_b200 as M\n"
+            "from tests.test_gpu_parity import _check_nets, GOLD\n"
+            "z = np.load(os.path.join(GOLD, 'cnn_golden.npz'))\n"
+            "mg = M.ModsGpu(0, load_nets=True)\n"
+            "_check_nets(mg, z['patches'], z['affnet'], z['orinet'], z['hardnet'])\n"
+            "rng = np.random.RandomState(5)\n"
+            "p = rng.randint(0, 256, (700, 32, 32)).astype(np.uint8)\n"
+            "a = mg.net_forward_u8(M.HARDNET, p)\n"
+            "assert np.array_equal(a[:300], mg.net_forward_u8(M.HARDNET, p[:300]))\n"
+            "print('fused ok')\n") % ROOT
+    env = dict(os.environ, MODSGPU_FUSED_CONV12="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300, cwd=ROOT)
+    assert r.returncode == 0 and "fused ok" in r.stdout, r.stdout[-500:] + r.stderr[-1500:]

@@ -143,8 +143,12 @@ struct ConvCfg {
   static constexpr int A_BYTES = NPL * TP * 16;
   static constexpr int W_BYTES = 9 * KSTEPS * 2 * COUT_T * 16;
   static constexpr int TMEM_COLS = (2 * COUT_T <= 32) ? 32 : (2 * COUT_T <= 64 ? 64 : (2 * COUT_T <= 128 ? 128 : 256));
-  // A-tile ring: as deep as shared memory allows (small tiles are latency- not bandwidth-limited)
-  static constexpr int NST_FIT = (232448 - W_BYTES - 256) / A_BYTES;
+  // A-tile ring: as deep as shared memory allows (small tiles are latency- not bandwidth-limited).  Layers whose weights
+  // and >= 3 A stages fit in half an SM's shared memory run TWO CTAs per SM: two independent load/MMA/epilogue
+  // pipelines interleave on the tensor pipe and hide each other's per-tile latencies.
+  static constexpr int NST_HALF = (113 * 1024 - W_BYTES - 256) / A_BYTES;
+  static constexpr bool TWO_CTAS = NST_HALF >= 3;
+  static constexpr int NST_FIT = TWO_CTAS ? NST_HALF : (232448 - W_BYTES - 256) / A_BYTES;
   static constexpr int NST = NST_FIT < 2 ? 2 : (NST_FIT > 8 ? 8 : NST_FIT);
   static constexpr int SMEM_BYTES = W_BYTES + NST * A_BYTES + 256;
   static_assert(CIN % 16 == 0 && COUT_T % 16 == 0, "UMMA shape");
@@ -692,8 +696,9 @@ __device__ __forceinline__ void load8(const __half* p, float* f) {
 
 // AffNet: conv 8x8 (64->3, bias) -> tanh -> +1 on outputs 0 and 2 (affnet_server.py:64-66,:80-84)
 // OriNet: conv 8x8 pad 1 (64->2, bias) -> 3x3 map -> tanh -> mean (orinet_server.py:64-70)
-// Weights live in shared memory as [o][e][item] (item = pix*8 + c8) so that the 32 lanes of a warp, which
-// walk consecutive items, read consecutive floats; one warp per patch, persistent over patches.
+// Weights live in shared memory as [o][e/4][item][4] (item = pix*8 + c8, e = channel within the 8-channel plane) so that
+// the 32 lanes of a warp, which walk consecutive items, read consecutive float4s: two conflict-free LDS.128 per
+// 8 FMAs (the first version read one scalar weight per FMA and was LSU-bound); one warp per patch, persistent.
 template <int NOUT, bool ORI>
 __global__ void __launch_bounds__(256)
 k_head_small(const __half* __restrict__ act, size_t slots, const float* __restrict__ w, const float* __restrict__ b,
@@ -701,7 +706,8 @@ k_head_small(const __half* __restrict__ act, size_t slots, const float* __restri
   extern __shared__ float ws[];   // NOUT * 8 * 512
   for (int idx = threadIdx.x; idx < NOUT * 4096; idx += blockDim.x) {
     const int o = idx >> 12, rem = idx & 4095, pix = rem >> 6, c = rem & 63;
-    ws[(o * 8 + (c & 7)) * 512 + pix * 8 + (c >> 3)] = w[idx];
+    const int e = c & 7, item = pix * 8 + (c >> 3);
+    ws[((o * 2 + (e >> 2)) * 512 + item) * 4 + (e & 3)] = w[idx];
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -712,7 +718,7 @@ k_head_small(const __half* __restrict__ act, size_t slots, const float* __restri
     for (int p = 0; p < NPOS; p++)
 #pragma unroll
       for (int o = 0; o < NOUT; o++) acc[p][o] = 0.f;
-#pragma unroll 4
+#pragma unroll 8
     for (int k = 0; k < 16; k++) {
       const int it = lane + 32 * k;
       const int pix = it >> 3, c8 = it & 7, y = pix >> 3, x = pix & 7;
@@ -720,9 +726,14 @@ k_head_small(const __half* __restrict__ act, size_t slots, const float* __restri
       load8(act + ((size_t)c8 * slots + FS + (size_t)patch * 81 + (y + 1) * 9 + x) * 8, a);
       if (!ORI) {
 #pragma unroll
-        for (int o = 0; o < NOUT; o++)
-#pragma unroll
-          for (int e = 0; e < 8; e++) acc[0][o] = fmaf(a[e], ws[(o * 8 + e) * 512 + it], acc[0][o]);
+        for (int o = 0; o < NOUT; o++) {
+          const float4 w0 = *reinterpret_cast<const float4*>(ws + ((o * 2 + 0) * 512 + it) * 4);
+          const float4 w1 = *reinterpret_cast<const float4*>(ws + ((o * 2 + 1) * 512 + it) * 4);
+          float s0 = acc[0][o];
+          s0 = fmaf(a[0], w0.x, s0); s0 = fmaf(a[1], w0.y, s0); s0 = fmaf(a[2], w0.z, s0); s0 = fmaf(a[3], w0.w, s0);
+          s0 = fmaf(a[4], w1.x, s0); s0 = fmaf(a[5], w1.y, s0); s0 = fmaf(a[6], w1.z, s0); s0 = fmaf(a[7], w1.w, s0);
+          acc[0][o] = s0;
+        }
       } else {
 #pragma unroll
         for (int pos = 0; pos < 9; pos++) {
@@ -730,9 +741,14 @@ k_head_small(const __half* __restrict__ act, size_t slots, const float* __restri
           if (ky < 0 || ky > 7 || kx < 0 || kx > 7) continue;
           const int wit = (ky * 8 + kx) * 8 + c8;
 #pragma unroll
-          for (int o = 0; o < NOUT; o++)
-#pragma unroll
-            for (int e = 0; e < 8; e++) acc[pos][o] = fmaf(a[e], ws[(o * 8 + e) * 512 + wit], acc[pos][o]);
+          for (int o = 0; o < NOUT; o++) {
+            const float4 w0 = *reinterpret_cast<const float4*>(ws + ((o * 2 + 0) * 512 + wit) * 4);
+            const float4 w1 = *reinterpret_cast<const float4*>(ws + ((o * 2 + 1) * 512 + wit) * 4);
+            float s0 = acc[pos][o];
+            s0 = fmaf(a[0], w0.x, s0); s0 = fmaf(a[1], w0.y, s0); s0 = fmaf(a[2], w0.z, s0); s0 = fmaf(a[3], w0.w, s0);
+            s0 = fmaf(a[4], w1.x, s0); s0 = fmaf(a[5], w1.y, s0); s0 = fmaf(a[6], w1.z, s0); s0 = fmaf(a[7], w1.w, s0);
+            acc[pos][o] = s0;
+          }
         }
       }
     }
@@ -896,7 +912,8 @@ int launch_conv(modsgpu_ctx* ctx, const __half* in, size_t in_slots, const ConvW
   if (!pname[0]) snprintf(pname, sizeof(pname), "k_conv_umma<%d,%d,S%d,%s>", CIN, Cfg::COUT, S, NGRP == 4 ? "s2" : "s1");
   constexpr int S_IN = NGRP == 4 ? 2 * S : S;   // stride-2 layers read the parity planes of a 2S x 2S map
   MG_PROF2(ctx, pname, 1, 2.0 * np * S * S * 9.0 * CIN * Cfg::COUT, 2.0 * np * ((double)S_IN * S_IN * CIN + (double)S * S * Cfg::COUT));
-  int gx = std::min(ntiles, std::max(1, ctx->num_sms / NSPLIT));
+  static const bool one_cta = [] { const char* e = getenv("MODSGPU_CONV_ONE_CTA"); return e && atoi(e) != 0; }();   // A/B switch
+  int gx = std::min(ntiles, std::max(1, ctx->num_sms * ((Cfg::TWO_CTAS && !one_cta) ? 2 : 1) / NSPLIT));
   dim3 grid(gx, NSPLIT);
   kern<<<grid, 192, Cfg::SMEM_BYTES, ctx->stream>>>(in, in_slots, w.w, w.b, out, out_slots, np, ntiles, patch_base);
   MG_LAUNCHED(ctx);
@@ -1103,7 +1120,7 @@ int mg_net_forward_enqueue(modsgpu_ctx* ctx, modsgpu_net net, const uint8_t* d_p
         MG_CUDA(ctx, cudaFuncSetAttribute(k_head_small<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4096 * 4));
         hattr.set(ctx->device);
       }
-      const int hgrid = std::min(ceil_div(np, 8), 2 * ctx->num_sms);
+      const int hgrid = std::min(ceil_div(np, 8), 4 * ctx->num_sms);   // 24-48 KB of weights per CTA: 4 CTAs (32 warps) per SM
       MG_PROF(ctx, net == MODSGPU_AFFNET ? "k_head_aff" : "k_head_ori", 1, 2.0 * np * (net == MODSGPU_AFFNET ? 12288.0 : 61952.0));
       if (net == MODSGPU_AFFNET)
         k_head_small<3, false><<<hgrid, 256, 3 * 4096 * 4, ctx->stream>>>(nw->act[5], nw->slots[5], nw->head_w32, nw->head_b, pout, np);

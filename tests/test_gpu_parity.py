@@ -831,7 +831,10 @@ def test_fused_conv12_experimental_path_parity():
     code = ("import os, sys, numpy as np\n"
             "sys.path.insert(0, %r)\n"
             "import mods_light_zmq_b200 as M\n"
-            "from tests.test_gpu_parity import _check_nets, GOLD\n"
+            "import importlib.util\n"
+            "spec = importlib.util.spec_from_file_location('tgp', os.path.join(%r, 'tests', 'test_gpu_parity.py'))\n"
+            "tgp = importlib.util.module_from_spec(spec); spec.loader.exec_module(tgp)\n"
+            "_check_nets, GOLD = tgp._check_nets, tgp.GOLD\n"
             "z = np.load(os.path.join(GOLD, 'cnn_golden.npz'))\n"
             "mg = M.ModsGpu(0, load_nets=True)\n"
             "_check_nets(mg, z['patches'], z['affnet'], z['orinet'], z['hardnet'])\n"
@@ -839,7 +842,7 @@ def test_fused_conv12_experimental_path_parity():
             "p = rng.randint(0, 256, (700, 32, 32)).astype(np.uint8)\n"
             "a = mg.net_forward_u8(M.HARDNET, p)\n"
             "assert np.array_equal(a[:300], mg.net_forward_u8(M.HARDNET, p[:300]))\n"
-            "print('fused ok')\n") % ROOT
+            "print('fused ok')\n") % (ROOT, ROOT)
     env = dict(os.environ, MODSGPU_FUSED_CONV12="1")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300, cwd=ROOT)
     assert r.returncode == 0 and "fused ok" in r.stdout, r.stdout[-500:] + r.stderr[-1500:]

@@ -71,7 +71,19 @@ typedef struct {            /* PyramidParams, structures.hpp:114-151 */
   float  threshold;             /* 5.33 ([HessianAffine] threshold in the ini) */
   double edgeEigenValueRatio;   /* 10   */
   int    border;                /* 5    */
+  /* detection mode (structures.hpp:10-14, prepareKeysForExport scale-space-detector.hpp:125-198).  Every mode but
+   * FIXED_TH detects with all thresholds at 0 (pyramid.h:58-59) and truncates the |response|-sorted list:
+   *   RELATIVE_TH keeps |r| > max|r| * rel_threshold;  FIXED_REG_NUMBER keeps reg_number;  RELATIVE_REG_NUMBER keeps
+   *   floor(rel_reg_number * n);  NOT_LESS_THAN_REGIONS keeps max(reg_number, #{|r| > threshold}) (capped at n). */
+  int    detectorMode;          /* MODSGPU_FIXED_TH */
+  float  rel_threshold;         /* -1 */
+  int    reg_number;            /* -1 */
+  float  rel_reg_number;        /* -1 */
 } modsgpu_pyr_params;
+enum { MODSGPU_FIXED_TH = 0, MODSGPU_RELATIVE_TH = 1, MODSGPU_FIXED_REG_NUMBER = 2, MODSGPU_RELATIVE_REG_NUMBER = 3,
+       MODSGPU_NOT_LESS_THAN_REGIONS = 4 };
+/* DetectAffineKeypoints (scale-space-detector.cpp:13-32): reg_number shrinks on strongly tilted / zoomed-out views */
+int  modsgpu_reg_number_for_view(int reg_number, double tilt, double zoom);
 
 typedef struct {            /* AffineKeypoint structures.hpp:185-194 + provenance for parity tests */
   float x, y, s;                /* pyramid.cpp:392-402 */

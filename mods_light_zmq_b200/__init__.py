@@ -31,7 +31,11 @@ NET_DIM = {AFFNET: 3, ORINET: 2, HARDNET: 128}
 
 class PyrParams(C.Structure):
     _fields_ = [("numberOfScales", C.c_int), ("initialSigma", C.c_float), ("threshold", C.c_float),
-                ("edgeEigenValueRatio", C.c_double), ("border", C.c_int)]
+                ("edgeEigenValueRatio", C.c_double), ("border", C.c_int),
+                ("detectorMode", C.c_int), ("rel_threshold", C.c_float), ("reg_number", C.c_int), ("rel_reg_number", C.c_float)]
+
+
+FIXED_TH, RELATIVE_TH, FIXED_REG_NUMBER, RELATIVE_REG_NUMBER, NOT_LESS_THAN_REGIONS = range(5)
 
 
 class AffShapeParams(C.Structure):

@@ -691,6 +691,7 @@ int mg_gaussian_taps(float sigmaf, std::vector<float>& taps) {
 // ------------------------------------------------------------------------------------------
 extern "C" void modsgpu_default_pyr_params(modsgpu_pyr_params* p) {
   p->numberOfScales = 3; p->initialSigma = 1.6f; p->threshold = 5.33f; p->edgeEigenValueRatio = 10.0; p->border = 5;
+  p->detectorMode = MODSGPU_FIXED_TH; p->rel_threshold = -1.f; p->reg_number = -1; p->rel_reg_number = -1.f;
 }
 
 extern "C" int modsgpu_image_from_bgr8(modsgpu_ctx* ctx, const uint8_t* bgr, int w, int h, modsgpu_image** out) {
@@ -846,8 +847,10 @@ int mg_detect_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
 
   // thresholds, pyramid.h:46-66 (DET_HESSIAN, FIXED_TH)
   const double edgeThr = (p->edgeEigenValueRatio + 1.0f) * (p->edgeEigenValueRatio + 1.0f) / p->edgeEigenValueRatio;
-  const float posThr = (float)(0.8 * p->threshold), negThr = -posThr;
-  const float finalThr = p->threshold * p->threshold;
+  // every mode but FIXED_TH keeps all extrema and truncates after the sort (pyramid.h:58-59)
+  const bool fixedTh = p->detectorMode == MODSGPU_FIXED_TH;
+  const float posThr = fixedTh ? (float)(0.8 * p->threshold) : 0.f, negThr = -posThr;
+  const float finalThr = fixedTh ? p->threshold * p->threshold : 0.f;
   const float sigmaStep = std::pow(2.0f, 1.0f / (float)nS);
 
   float pixelDistance = 1.0f;
@@ -959,9 +962,52 @@ int mg_detect_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
   return 0;
 }
 
+// prepareKeysForExport (scale-space-detector.hpp:125-198) on the |response|-descending list: how many keys survive
+static int keys_to_export(const modsgpu_keypoint* k, int n, const modsgpu_pyr_params* p, bool doBaumberg) {
+  if (n <= 0 || p->detectorMode == MODSGPU_FIXED_TH) return n;
+  auto count_above = [&](double thr) {      // lower_bound with responseCompareInvOrder: first key with |r| <= thr
+    int lo = 0, hi = n;
+    while (lo < hi) { const int mid = (lo + hi) / 2; if (std::fabs((double)k[mid].response) > thr) lo = mid + 1; else hi = mid; }
+    return lo;
+  };
+  int keep = n;
+  switch (p->detectorMode) {
+    case MODSGPU_RELATIVE_TH: {
+      // effectiveThreshold is a float member, tempKey.response a double
+      const float eff = (float)(std::fabs((double)k[0].response) * (double)p->rel_threshold);
+      keep = count_above(std::fabs((double)eff));
+      break;
+    }
+    case MODSGPU_FIXED_REG_NUMBER: {
+      int nr = p->reg_number;
+      if (doBaumberg) nr = (int)std::floor(3.0 * (double)nr);
+      if (nr < n && nr >= 0) keep = nr;
+      if (keep > p->reg_number) keep = p->reg_number;       // the closing clause of the function (:194-195)
+      break;
+    }
+    case MODSGPU_RELATIVE_REG_NUMBER:
+      keep = (int)std::floor((double)p->rel_reg_number * (double)n);
+      break;
+    case MODSGPU_NOT_LESS_THAN_REGIONS: {
+      const int fixed = count_above((double)p->threshold);   // NB the un-squared threshold (reference quirk, :174)
+      keep = fixed < p->reg_number ? std::min(p->reg_number, n) : std::min(fixed, n);
+      break;
+    }
+    default: break;
+  }
+  return std::max(0, std::min(keep, n));
+}
+
+extern "C" int modsgpu_reg_number_for_view(int reg_number, double tilt, double zoom) {
+  if (tilt > 2.0 || zoom < 0.5) return (int)std::floor(zoom * (double)reg_number / tilt);
+  return reg_number;
+}
+
 static int detect_impl(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_pyr_params* p,
                        const modsgpu_affshape_params* aff, modsgpu_keypoint** out, float** A, int* n) {
   if (!ctx || !img || !p || !out || !n) return MODSGPU_EINVAL;
+  if (p->detectorMode < MODSGPU_FIXED_TH || p->detectorMode > MODSGPU_NOT_LESS_THAN_REGIONS)
+    MG_FAIL(ctx, MODSGPU_EINVAL, "unknown detectorMode");
   if (mg_begin(ctx)) return MODSGPU_ECUDA;
   int cap = 1 << 16;
   for (;;) {
@@ -983,6 +1029,7 @@ static int detect_impl(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu
         MG_CUDA(ctx, cudaMemcpyAsync(resA, ctx->det_out.as<modsgpu_keypoint>() + cap, 16 * (size_t)kept, cudaMemcpyDeviceToHost, ctx->stream));
     }
     if (mg_end(ctx)) { free(res); free(resA); return MODSGPU_ECUDA; }
+    kept = keys_to_export(res, kept, p, aff != nullptr && aff->doBaumberg);
     *out = res; *n = kept;
     if (A) *A = resA;
     return 0;

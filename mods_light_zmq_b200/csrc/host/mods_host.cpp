@@ -162,7 +162,9 @@ int ImageRepresentation::AddViews(const std::vector<ViewSynthParameters>& views,
     TimeSpent.SynthTime += now_ms() - t0;
     AffineRegionVector one;
     const int kp0 = n_keypoints, af0 = n_affine;
-    rc = DescribeView(view, H, w, h, par, one);
+    DetectPars vpar = par;     // DetectAffineKeypoints shrinks reg_number on tilted / zoomed-out views (scale-space-detector.cpp:19-21)
+    vpar.pyr.reg_number = modsgpu_reg_number_for_view(par.pyr.reg_number, views[v].tilt, views[v].zoom);
+    rc = DescribeView(view, H, w, h, vpar, one);
     modsgpu_image_free(ctx_, view);
     if (rc < 0) return rc;
     n_keypoints += kp0; n_affine += af0;

@@ -209,6 +209,41 @@ def detect_hessian(gray, params=None, cap=200000):
     return out[:n].copy()
 
 
+FIXED_TH, RELATIVE_TH, FIXED_REG_NUMBER, RELATIVE_REG_NUMBER, NOT_LESS_THAN_REGIONS = range(5)
+
+
+def detect_hessian_mode(gray, mode, threshold=5.33, rel_threshold=-1.0, reg_number=-1, rel_reg_number=-1.0, affine=False):
+    """The detection modes of prepareKeysForExport (scale-space-detector.hpp:125-198): every mode but FIXED_TH runs the
+    pyramid with all thresholds at 0 (pyramid.h:58-59) and truncates the |response|-descending key list.  Numpy
+    restatement of the truncation rules on top of the C oracle's detector."""
+    par = default_params()
+    par.threshold = threshold if mode == FIXED_TH else 0.0
+    if affine:
+        kps, A = detect_hessian_affine(gray, par, cap=1 << 20)
+    else:
+        kps, A = detect_hessian(gray, par, cap=1 << 20), None
+    n = len(kps)
+    if n == 0 or mode == FIXED_TH:
+        return (kps, A) if affine else kps
+    mag = np.abs(kps["response"].astype(np.float64))
+    keep = n
+    if mode == RELATIVE_TH:
+        eff = np.float32(mag[0] * np.float64(np.float32(rel_threshold)))       # float member effectiveThreshold (:145)
+        keep = int(np.sum(mag > abs(float(eff))))                             # lower_bound on the sorted list (:149-150)
+    elif mode == FIXED_REG_NUMBER:
+        nr = int(np.floor(3.0 * reg_number)) if affine else reg_number          # doBaumberg triples it (:156-157) ...
+        if 0 <= nr < n:
+            keep = nr
+        keep = min(keep, reg_number)                                            # ... and :194-195 cuts it back
+    elif mode == RELATIVE_REG_NUMBER:
+        keep = int(np.floor(np.float64(np.float32(rel_reg_number)) * n))
+    elif mode == NOT_LESS_THAN_REGIONS:
+        fixed = int(np.sum(mag > float(np.float32(threshold))))                 # un-squared threshold (:174)
+        keep = min(reg_number, n) if fixed < reg_number else min(fixed, n)
+    keep = max(0, min(keep, n))
+    return (kps[:keep], A[:keep]) if affine else kps[:keep]
+
+
 def regions_from_keypoints(kps):
     """synth-detection.hpp:79-112 with doBaumberg=0: A = I, s unchanged (sqrt|det I| = 1)."""
     r = np.zeros(len(kps), REGION_DTYPE)

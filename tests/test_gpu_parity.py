@@ -1,6 +1,7 @@
 """GPU parity tests (-m gpu): every call goes through the C ABI of libmodsgpu.so and is compared with the
 CPU oracle on the same seeded inputs.  Integer / index / byte outputs must be bit-exact; the network
 outputs carry the tolerances stated at the test (fp16 operands, fp32 accumulation)."""
+import ctypes as C
 import os
 import sys
 
@@ -846,3 +847,36 @@ def test_fused_conv12_experimental_path_parity():
     env = dict(os.environ, MODSGPU_FUSED_CONV12="1")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300, cwd=ROOT)
     assert r.returncode == 0 and "fused ok" in r.stdout, r.stdout[-500:] + r.stderr[-1500:]
+
+
+# ------------------------------------------------------------------------------------------ detection modes (a9)
+@pytest.mark.parametrize("mode,kw", [(1, dict(rel_threshold=0.02)), (2, dict(reg_number=500)), (2, dict(reg_number=10 ** 6)),
+                                      (3, dict(rel_reg_number=0.25)), (4, dict(reg_number=900)), (4, dict(reg_number=50))])
+def test_detector_modes_bit_exact(mg, oracle, mode, kw):
+    """RelativeTh / FixedRegNumber / RelativeRegNumber / NotLessThanRegions (prepareKeysForExport,
+    scale-space-detector.hpp:125-198): zero thresholds in the pyramid, then truncation of the sorted list."""
+    import mods_light_zmq_b200 as M
+    from mods_light_zmq_b200 import synth
+    u8 = synth.blob_image(seed=77, w=320, h=240, n_blobs=400)
+    g = _gray(oracle, u8)
+    img = mg.image_from_gray32f(g)
+    p = M.PyrParams()
+    mg.lib.modsgpu_default_pyr_params(C.byref(p))
+    p.detectorMode = mode
+    for k, v in kw.items():
+        setattr(p, k, v)
+    ref = oracle.detect_hessian_mode(g, mode, threshold=p.threshold, **kw)
+    got = mg.detect(img, p)
+    assert len(ref) > 0
+    _assert_kp_equal(got, ref)
+    all_keys = oracle.detect_hessian_mode(g, 3, rel_reg_number=1.0)
+    assert len(all_keys) > len(mg.detect(img))            # zero thresholds keep far more extrema than FixedTh
+    if mode == 2 and kw["reg_number"] == 500:
+        # with Baumberg: 3 x reg_number first, then cut back to reg_number (the reference's closing clause)
+        refa, refA = oracle.detect_hessian_mode(g, mode, affine=True, **kw)
+        gota, gotA = mg.detect_affine(img, p)
+        _assert_kp_equal(gota, refa)
+        assert np.array_equal(gotA, refA) and len(gota) == 500
+    assert mg.lib.modsgpu_reg_number_for_view(1000, C.c_double(4.0), C.c_double(1.0)) == 250
+    assert mg.lib.modsgpu_reg_number_for_view(1000, C.c_double(1.5), C.c_double(0.25)) == 166
+    assert mg.lib.modsgpu_reg_number_for_view(1000, C.c_double(2.0), C.c_double(0.5)) == 1000

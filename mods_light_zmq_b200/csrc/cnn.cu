@@ -43,7 +43,7 @@ struct NetWeights {
   float* c1_w = nullptr; float* c1_b = nullptr;
   ConvW conv[5];                 // conv2..conv6 in UMMA block order
   __half* head_w16 = nullptr;    // HardNet head, UMMA block order
-  float* head_w32 = nullptr;     // AffNet / OriNet head [Cout][8][8][64]
+  float* head_w32 = nullptr;     // AffNet / OriNet head, k_head_small's shared-memory layout
   float* head_b = nullptr;
   int cap = 0;                   // patches per chunk the activation buffers hold
   bool fused12 = false;          // conv1 weights resident in c_conv1[net] on this device -> k_conv12 path
@@ -696,7 +696,7 @@ __device__ __forceinline__ void load8(const __half* p, float* f) {
 
 // AffNet: conv 8x8 (64->3, bias) -> tanh -> +1 on outputs 0 and 2 (affnet_server.py:64-66,:80-84)
 // OriNet: conv 8x8 pad 1 (64->2, bias) -> 3x3 map -> tanh -> mean (orinet_server.py:64-70)
-// Weights live in shared memory as [o][e/4][item][4] (item = pix*8 + c8, e = channel within the 8-channel plane) so that
+// Weights live in shared memory as [o][e/4][item][4] (item = c8*64 + pix, e = channel within the 8-channel plane) so that
 // the 32 lanes of a warp, which walk consecutive items, read consecutive float4s: two conflict-free LDS.128 per
 // 8 FMAs (the first version read one scalar weight per FMA and was LSU-bound); one warp per patch, persistent.
 template <int NOUT, bool ORI>
@@ -704,11 +704,8 @@ __global__ void __launch_bounds__(256)
 k_head_small(const __half* __restrict__ act, size_t slots, const float* __restrict__ w, const float* __restrict__ b,
              float* __restrict__ out, int np) {
   extern __shared__ float ws[];   // NOUT * 8 * 512
-  for (int idx = threadIdx.x; idx < NOUT * 4096; idx += blockDim.x) {
-    const int o = idx >> 12, rem = idx & 4095, pix = rem >> 6, c = rem & 63;
-    const int e = c & 7, item = pix * 8 + (c >> 3);
-    ws[((o * 2 + (e >> 2)) * 512 + item) * 4 + (e & 3)] = w[idx];
-  }
+  // `w` already has the shared-memory layout (modsgpu_load_weights): a straight 16-byte copy
+  for (int i = threadIdx.x; i < NOUT * 1024; i += blockDim.x) reinterpret_cast<float4*>(ws)[i] = __ldg(reinterpret_cast<const float4*>(w) + i);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int patch = blockIdx.x * 8 + warp; patch < np; patch += gridDim.x * 8) {
@@ -721,7 +718,7 @@ k_head_small(const __half* __restrict__ act, size_t slots, const float* __restri
 #pragma unroll 8
     for (int k = 0; k < 16; k++) {
       const int it = lane + 32 * k;
-      const int pix = it >> 3, c8 = it & 7, y = pix >> 3, x = pix & 7;
+      const int c8 = it >> 6, pix = it & 63, y = pix >> 3, x = pix & 7;   // a warp reads 32 consecutive pixels of one plane
       float a[8];
       load8(act + ((size_t)c8 * slots + FS + (size_t)patch * 81 + (y + 1) * 9 + x) * 8, a);
       if (!ORI) {
@@ -739,7 +736,7 @@ k_head_small(const __half* __restrict__ act, size_t slots, const float* __restri
         for (int pos = 0; pos < 9; pos++) {
           const int ky = y - pos / 3 + 1, kx = x - pos % 3 + 1;
           if (ky < 0 || ky > 7 || kx < 0 || kx > 7) continue;
-          const int wit = (ky * 8 + kx) * 8 + c8;
+          const int wit = c8 * 64 + ky * 8 + kx;
 #pragma unroll
           for (int o = 0; o < NOUT; o++) {
             const float4 w0 = *reinterpret_cast<const float4*>(ws + ((o * 2 + 0) * 512 + wit) * 4);
@@ -1044,7 +1041,15 @@ extern "C" int modsgpu_load_weights(modsgpu_ctx* ctx, modsgpu_net net, const cha
           for (int e = 0; e < 8; e++) pk[o++] = __float2half_rn(hw->data[(size_t)n * 8192 + kk * 16 + j * 8 + e]);
     MG_CUDA(ctx, upload(&nw->head_w16, pk.data(), pk.size() * 2));
   } else {
-    MG_CUDA(ctx, upload(&nw->head_w32, hw->data.data(), hw->data.size() * 4));
+    // k_head_small's shared-memory image, prepared once: [o][e/4][item = (c/8)*64 + pix][e%4] with e = c % 8
+    const int nout = nw->out_dim;
+    std::vector<float> img((size_t)nout * 4096);
+    for (int idx = 0; idx < nout * 4096; idx++) {
+      const int o = idx >> 12, rem = idx & 4095, pix = rem >> 6, c = rem & 63;
+      const int e = c & 7, item = (c >> 3) * 64 + pix;
+      img[((size_t)(o * 2 + (e >> 2)) * 512 + item) * 4 + (e & 3)] = hw->data[idx];
+    }
+    MG_CUDA(ctx, upload(&nw->head_w32, img.data(), img.size() * 4));
   }
   // activation buffers, zeroed once: pad slots are never written afterwards
   const int cap = cnn_chunk_cap();

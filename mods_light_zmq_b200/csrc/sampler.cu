@@ -227,12 +227,36 @@ __device__ __forceinline__ void gen_row_starts(const PatchMeta& m, int j, int R,
 }
 
 // lane `sub` of an 8-lane group: sample i0 + sub of a row whose segment starts at coordinate c
+// Branch-free (out-of-image samples read pixel (0,0) and are zeroed by the select) so that the gathers of several
+// unrolled segments can be in flight together: the sampling loops are bound by gather latency, not by issue.
 __device__ __forceinline__ float sample_seg(const float* __restrict__ img, int w, int h, float2 c, float a11, float a21, int sub) {
   float WX = c.x, WY = c.y;
 #pragma unroll
   for (int t = 0; t < SEG - 1; t++)
     if (t < sub) { WX += a11; WY += a21; }
-  return sample_image(img, w, h, WX, WY);
+  const int x = (int)floorf(WX), y = (int)floorf(WY);
+  const bool ok = WX >= 0 && WY >= 0 && x < w - 1 && y < h - 1;
+  const float v = bilinear(img, w, ok ? x : 0, ok ? y : 0, ok ? WX : 0.f, ok ? WY : 0.f);
+  return ok ? v : 0.f;
+}
+
+// one row (or row block) of the first resampling: segments in groups of 4 -- coordinates first, then the 4 x 4 gathers,
+// then the stores (the stores may alias the coordinate table as far as the compiler knows, so the order is spelled out)
+__device__ __forceinline__ void sample_row(const float* __restrict__ img, int w, int h, const float2* cs, int nseg, float a11, float a21,
+                                           int sub, float* row, int R) {
+  for (int s0 = 0; s0 < nseg; s0 += 4) {
+    float2 c[4];
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) c[u] = cs[min(s0 + u, nseg - 1)];
+#pragma unroll
+    for (int u = 0; u < 4; u++) v[u] = sample_seg(img, w, h, c[u], a11, a21, sub);
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = (s0 + u) * SEG + sub;
+      if (s0 + u < nseg && i < R) row[i] = v[u];
+    }
+  }
 }
 
 // Row pass, vector form (x < R & ~3, ks >= 7): s = 0; s = fma(p[t], k[t], s), t = 0..ks-1, for CB adjacent
@@ -328,11 +352,7 @@ k_sample_a(const float* __restrict__ img, int w, int h, const PatchMeta* __restr
     for (int j = g; j < R; j += NT / SEG) {
       float* row = Sp + j * PS + r;
       const float2* cs = C2 + j * nseg;
-      for (int s = 0; s < nseg; s++) {
-        const int i = s * SEG + sub;
-        const float v = sample_seg(img, w, h, cs[s], m.a11, m.a21, sub);
-        if (i < R) row[i] = v;
-      }
+      sample_row(img, w, h, cs, nseg, m.a11, m.a21, sub, row, R);
     }
   }
   __syncthreads();
@@ -470,11 +490,7 @@ k_sample_b(const float* __restrict__ img, int w, int h, const PatchMeta* __restr
       if (g < nrows) {
         float* row = Sb + g * PS + r;
         const float2* cs = C2 + (j0 + g) * nseg;
-        for (int s = 0; s < nseg; s++) {
-          const int i = s * SEG + sub;
-          const float v = sample_seg(img, w, h, cs[s], m.a11, m.a21, sub);
-          if (i < R) row[i] = v;
-        }
+        sample_row(img, w, h, cs, nseg, m.a11, m.a21, sub, row, R);
       }
     }
     __syncthreads();
@@ -583,60 +599,92 @@ __device__ __forceinline__ int needed_pos(float p, int odd, int R) {
   return clampi((int)floorf(p) + odd, 0, R - 1);
 }
 
-constexpr int L1_ROWS = 4, L2_ROWS = 8, L3_OUT_ROWS = 4;
+constexpr int L0_ROWS = 128, L1_ROWS = 16, L2_ROWS = 16, L3_OUT_ROWS = 4;
 
-// phase 1: S[j][i] for L1_ROWS rows of one region
+// per-region scratch (floats): [C: R x nseg float2 row-segment start coordinates | S: R x R | T: R x 2ps]
+__host__ __device__ inline long long large_c_floats(int R) { return 2LL * R * ((R + SEG - 1) / SEG); }
+
+// phase 0: one thread per window row walks the row's float coordinate sequence once (the sequential `WX += a11` of
+// interpolate(), helpers.cpp:551-626, is what makes the samples bit-exact) and keeps every SEG-th coordinate
+__global__ void __launch_bounds__(L0_ROWS)
+k_large_starts(const PatchMeta* __restrict__ metas, int nreg, const int* __restrict__ pre, float* __restrict__ scratch) {
+  const int reg = find_region(pre, nreg, blockIdx.x);
+  const PatchMeta m = metas[reg];
+  const int R = m.R, nseg = (R + SEG - 1) / SEG;
+  const int j = (blockIdx.x - pre[reg]) * L0_ROWS + threadIdx.x;
+  if (j < R) gen_row_starts(m, j, R, nseg, reinterpret_cast<float2*>(scratch + m.scratch_off) + (size_t)j * nseg);
+}
+
+// phase 1: S[j][i] for L1_ROWS rows of one region; an 8-lane group walks one row segment by segment (as class A / B)
 __global__ void __launch_bounds__(128)
 k_large_resample(const float* __restrict__ img, int w, int h, const PatchMeta* __restrict__ metas, int nreg,
                  const int* __restrict__ pre, float* __restrict__ scratch) {
   const int reg = find_region(pre, nreg, blockIdx.x);
   const PatchMeta m = metas[reg];
-  const int R = m.R, half = R / 2;
-  const int row0 = (blockIdx.x - pre[reg]) * L1_ROWS;
-  float* S = scratch + m.scratch_off;
-  const int nchunk = (R + CHUNK - 1) / CHUNK;
-  const int nrows = min(L1_ROWS, R - row0);
-  for (int it = threadIdx.x; it < nrows * nchunk; it += blockDim.x) {
-    const int jr = it / nchunk, q = it - jr * nchunk, j = row0 + jr;
-    float rx = m.x - (float)half * m.a12, ry = m.y - (float)half * m.a22;
-    for (int t = 0; t < j; t++) { rx += m.a12; ry += m.a22; }
-    float WX = rx - (float)half * m.a11, WY = ry - (float)half * m.a21;
-    const int i0 = q * CHUNK;
-    for (int t = 0; t < i0; t++) { WX += m.a11; WY += m.a21; }
-    const int i1 = min(R, i0 + CHUNK);
-    for (int i = i0; i < i1; i++) {
-      S[(size_t)j * R + i] = sample_image(img, w, h, WX, WY);
-      WX += m.a11; WY += m.a21;
-    }
-  }
+  const int R = m.R, nseg = (R + SEG - 1) / SEG;
+  const int j = (blockIdx.x - pre[reg]) * L1_ROWS + (threadIdx.x >> 3), sub = threadIdx.x & 7;
+  if (j >= R) return;
+  const float2* cs = reinterpret_cast<const float2*>(scratch + m.scratch_off) + (size_t)j * nseg;
+  float* row = scratch + m.scratch_off + large_c_floats(R) + (size_t)j * R;
+  sample_row(img, w, h, cs, nseg, m.a11, m.a21, sub, row, R);
 }
 
-// phase 2a: row pass at the 2*ps needed columns for L2_ROWS rows of one region: T[y][ci]
+// phase 2a: row pass at the 2*ps needed columns for L2_ROWS rows of one region: T[y][ci].  Rows are staged in shared
+// memory with their replicated borders, then the register-blocked vector form of class B (a column pair x 2 rows per
+// thread); the few columns in OpenCV's scalar tail go through row_pass_at.
 __global__ void __launch_bounds__(256)
 k_large_rowpass(const PatchMeta* __restrict__ metas, int nreg, const int* __restrict__ pre,
                 const float* __restrict__ taps_all, float* __restrict__ scratch, int ps) {
   extern __shared__ float sm[];
   const int reg = find_region(pre, nreg, blockIdx.x);
   const PatchMeta m = metas[reg];
-  const int R = m.R, ks = m.ks, nc = 2 * ps;
+  const int R = m.R, ks = m.ks, r = ks >> 1, nc = 2 * ps, PS = (R + 2 * r + 2) | 1;
   const int row0 = (blockIdx.x - pre[reg]) * L2_ROWS;
   const int nrows = min(L2_ROWS, R - row0);
-  float* P = sm;              // ps
-  float* kk = P + MAX_PS;     // ks <= 640
-  float* rows = kk + 640;     // nrows x R
-  const float* S = scratch + m.scratch_off;
-  float* T = scratch + m.scratch_off + (size_t)R * R;
-  for (int i = threadIdx.x; i < ks; i += blockDim.x) kk[i] = taps_all[m.tap_off + i];
-  for (int i = threadIdx.x; i < nrows * R; i += blockDim.x) rows[i] = S[(size_t)row0 * R + i];
+  float* P = sm;                                      // ps
+  int* X = reinterpret_cast<int*>(P + MAX_PS);        // ps
+  float* kk = P + 2 * MAX_PS;                         // ks + 1 <= 642
+  float* rows = kk + 642;                             // nrows x PS (padded)
+  const float* S = scratch + m.scratch_off + large_c_floats(R);
+  float* T = scratch + m.scratch_off + large_c_floats(R) + (size_t)R * R;
+  for (int i = threadIdx.x; i < ks + 1; i += blockDim.x) kk[i] = i < ks ? taps_all[m.tap_off + i] : 0.f;
   if (threadIdx.x == 0) {
     float p = (float)(R / 2) - (float)(ps / 2) * m.scale;
-    for (int i = 0; i < ps; i++) { P[i] = p; p += m.scale; }
+    for (int i = 0; i < ps; i++) { P[i] = p; X[i] = (int)floorf(p); p += m.scale; }
+  }
+  for (int jr = threadIdx.x >> 5; jr < nrows; jr += 8) {          // a warp per row: coalesced reads, clamped index = border replication
+    const float* src = S + (size_t)(row0 + jr) * R;
+    float* dst = rows + jr * PS;
+    for (int t = threadIdx.x & 31; t < R + 2 * r + 2; t += 32) dst[t] = src[clampi(t - r, 0, R - 1)];
   }
   __syncthreads();
-  for (int it = threadIdx.x; it < nrows * nc; it += blockDim.x) {
-    const int yr = it / nc, ci = it - yr * nc;
-    const int x = needed_pos(P[ci >> 1], ci & 1, R);
-    T[(size_t)(row0 + yr) * nc + ci] = row_pass_at(rows + yr * R, R, x, kk, ks);
+  const int xv = R & ~3;
+  const int rg = threadIdx.x & 7;
+  for (int pi = threadIdx.x >> 3; pi < ps; pi += 32) {
+    const int x0 = X[pi];
+    int rowi[2] = {rg, rg + 8};
+    if (x0 >= 0 && x0 + 1 < xv && ks >= 7) {
+      const float* rp[2];
+#pragma unroll
+      for (int b = 0; b < 2; b++) rp[b] = rows + min(rowi[b], nrows - 1) * PS + x0;
+      float acc[2][2];
+      rowpass_block<2, 2>(rp, kk, ks, acc);
+#pragma unroll
+      for (int b = 0; b < 2; b++)
+        if (rowi[b] < nrows) {
+          float* t = T + (size_t)(row0 + rowi[b]) * nc + 2 * pi;
+          t[0] = acc[b][0]; t[1] = acc[b][1];
+        }
+    } else {
+#pragma unroll 1
+      for (int b = 0; b < 2; b++)
+        if (rowi[b] < nrows) {
+          const float* row = rows + rowi[b] * PS + r;
+          float* t = T + (size_t)(row0 + rowi[b]) * nc + 2 * pi;
+          t[0] = row_pass_at(row, R, needed_pos(P[pi], 0, R), kk, ks);
+          t[1] = row_pass_at(row, R, needed_pos(P[pi], 1, R), kk, ks);
+        }
+    }
   }
 }
 
@@ -653,7 +701,7 @@ k_large_colpass_final(const PatchMeta* __restrict__ metas, const float* __restri
   float* P = sm;
   float* kk = P + MAX_PS;
   float* B = kk + 640;        // (2*nout) x nc
-  const float* T = scratch + m.scratch_off + (size_t)R * R;
+  const float* T = scratch + m.scratch_off + large_c_floats(R) + (size_t)R * R;
   for (int i = threadIdx.x; i < ks; i += blockDim.x) kk[i] = taps_all[m.tap_off + i];
   if (threadIdx.x == 0) {
     float p = (float)(R / 2) - (float)(ps / 2) * m.scale;
@@ -760,13 +808,16 @@ int mg_sample_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
   long long scratch = 0;
   for (PatchMeta& m : large) {
     m.scratch_off = scratch;
-    scratch += (long long)m.R * m.R + (long long)m.R * 2 * ps;
+    scratch += large_c_floats(m.R) + (long long)m.R * m.R + (long long)m.R * 2 * ps;
+    scratch += scratch & 1;          // the float2 table at the head of the next region stays 8-byte aligned
   }
   // prefix sums of the per-region block counts of the two row-blocked phases
   const int nl = (int)large.size();
-  std::vector<int> pre1(nl + 1, 0), pre2(nl + 1, 0);
-  int maxR = 0;
+  std::vector<int> pre0(nl + 1, 0), pre1(nl + 1, 0), pre2(nl + 1, 0);
+  int maxR = 0, maxPS = 0;
   for (int i = 0; i < nl; i++) {
+    pre0[i + 1] = pre0[i] + ceil_div(large[i].R, L0_ROWS);
+    maxPS = std::max(maxPS, (large[i].R + 2 * (large[i].ks >> 1) + 2) | 1);
     pre1[i + 1] = pre1[i] + ceil_div(large[i].R, L1_ROWS);
     pre2[i + 1] = pre2[i] + ceil_div(large[i].R, L2_ROWS);
     maxR = std::max(maxR, large[i].R);
@@ -774,26 +825,28 @@ int mg_sample_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
   size_t nm = 0, cls_off[NCLS];
   for (int c = 0; c < NCLS; c++) { cls_off[c] = nm; nm += cls[c].size(); }
   const size_t meta_bytes = nm * sizeof(PatchMeta), taps_bytes = taps_all.size() * 4, pre_bytes = (size_t)(nl + 1) * 4;
-  MG_CUDA(ctx, ctx->h_stage2.ensure(meta_bytes + taps_bytes + 2 * pre_bytes + 64));
+  MG_CUDA(ctx, ctx->h_stage2.ensure(meta_bytes + taps_bytes + 3 * pre_bytes + 64));
   uint8_t* hb = ctx->h_stage2.as<uint8_t>();
   for (int c = 0; c < NCLS; c++)
     if (!cls[c].empty()) memcpy(hb + cls_off[c] * sizeof(PatchMeta), cls[c].data(), cls[c].size() * sizeof(PatchMeta));
   if (!taps_all.empty()) memcpy(hb + meta_bytes, taps_all.data(), taps_bytes);
   memcpy(hb + meta_bytes + taps_bytes, pre1.data(), pre_bytes);
   memcpy(hb + meta_bytes + taps_bytes + pre_bytes, pre2.data(), pre_bytes);
-  // one upload: [metas | taps | pre1 | pre2]
-  MG_CUDA(ctx, ctx->smp_meta.ensure(meta_bytes + taps_bytes + 2 * pre_bytes + 64));
+  memcpy(hb + meta_bytes + taps_bytes + 2 * pre_bytes, pre0.data(), pre_bytes);
+  // one upload: [metas | taps | pre1 | pre2 | pre0]
+  MG_CUDA(ctx, ctx->smp_meta.ensure(meta_bytes + taps_bytes + 3 * pre_bytes + 64));
   MG_CUDA(ctx, ctx->smp_scratch.ensure((size_t)scratch * 4 + 16));
-  MG_CUDA(ctx, cudaMemcpyAsync(ctx->smp_meta.p, hb, meta_bytes + taps_bytes + 2 * pre_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  MG_CUDA(ctx, cudaMemcpyAsync(ctx->smp_meta.p, hb, meta_bytes + taps_bytes + 3 * pre_bytes, cudaMemcpyHostToDevice, ctx->stream));
   const PatchMeta* dm = ctx->smp_meta.as<PatchMeta>();
   const float* dtaps = reinterpret_cast<const float*>(ctx->smp_meta.as<uint8_t>() + meta_bytes);
   const int* dpre1 = reinterpret_cast<const int*>(ctx->smp_meta.as<uint8_t>() + meta_bytes + taps_bytes);
   const int* dpre2 = reinterpret_cast<const int*>(ctx->smp_meta.as<uint8_t>() + meta_bytes + taps_bytes + pre_bytes);
+  const int* dpre0 = reinterpret_cast<const int*>(ctx->smp_meta.as<uint8_t>() + meta_bytes + taps_bytes + 2 * pre_bytes);
   static OnceFlags attr_set;
   if (attr_set.need(ctx->device)) {
     MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_small, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SMALL));
     MG_CUDA(ctx, cudaFuncSetAttribute(k_large_rowpass, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (MAX_PS + 640 + L2_ROWS * MAX_R) * 4));
+                                      (2 * MAX_PS + 642 + L2_ROWS * ((MAX_R + 602) | 1)) * 4));
     MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_a, cudaFuncAttributeMaxDynamicSharedMemorySize, a_smem_floats(A2_R, 30) * 4));
     MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_b, cudaFuncAttributeMaxDynamicSharedMemorySize, b_smem_floats(B2_R, 30) * 4));
     attr_set.set(ctx->device);
@@ -827,11 +880,14 @@ int mg_sample_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
   if (nl > 0) {
     const PatchMeta* dl = dm + cls_off[C_LARGE];
     float* scr = ctx->smp_scratch.as<float>();
+    MG_PROF(ctx, "k_large_starts", 2, (double)nl);
+    k_large_starts<<<pre0[nl], L0_ROWS, 0, ctx->stream>>>(dl, nl, dpre0, scr);
+    MG_LAUNCHED(ctx);
     MG_PROF(ctx, "k_large_resample", 0, alg_bytes(large));
     k_large_resample<<<pre1[nl], 128, 0, ctx->stream>>>(img->d, img->w, img->h, dl, nl, dpre1, scr);
     MG_LAUNCHED(ctx);
     MG_PROF(ctx, "k_large_rowpass", 2, (double)nl);
-    k_large_rowpass<<<pre2[nl], 256, (MAX_PS + 640 + L2_ROWS * maxR) * 4, ctx->stream>>>(dl, nl, dpre2, dtaps, scr, ps);
+    k_large_rowpass<<<pre2[nl], 256, (2 * MAX_PS + 642 + L2_ROWS * maxPS) * 4, ctx->stream>>>(dl, nl, dpre2, dtaps, scr, ps);
     MG_LAUNCHED(ctx);
     MG_PROF(ctx, "k_large_colpass_final", 2, (double)nl);
     k_large_colpass_final<<<nl * ceil_div(ps, L3_OUT_ROWS), 256, SMEM_L3, ctx->stream>>>(dl, dtaps, scr, d_out, ps, d_outf);

@@ -55,77 +55,124 @@ namespace {
 
 __host__ __device__ constexpr int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
+// {max(lo,0), max(hi,0)} rounded to nearest-even fp16, lo in the low half: one F2FP with the .relu modifier
+// (same values as __float2half_rn(fmaxf(x, 0.f)) for every finite x)
+__device__ __forceinline__ uint32_t relu_pack_h2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 // =================================================================================================
 // conv1 (+ input normalisation) on CUDA cores
+//
+// Persistent, warp-specialised: CTAs (three per SM, 4 conv warps + 1 prep warp: 15 warps leave 128 registers per thread)
+// walk over patches; warp 4 ("prep") loads the next patch (one 32-pixel row per lane), reduces its mean / unbiased std
+// with shuffles and writes the normalised pixels into the other half of a double-buffered padded tile, while warps 0-3
+// run the FMA chains of the current patch (8 independent chains per thread, taps outermost).  The 72 weights + 8 biases of a
+// thread's 8-channel group are loaded into registers once per CTA.  (The first version ran one CTA per patch: global load
+// -> block reduction -> fp64 section on one thread -> 3 barriers were exposed in front of every patch and the issue slots
+// were 56 % busy, profiles/r01_ncu_full_k_conv1_v5.txt.)
 // =================================================================================================
+constexpr int C1_PW = 40;   // padded row: pixel x lives at column x + 4 (16-byte aligned float4 stores), halo at 3 and 36
 template <int C1>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(160, 3)
 k_conv1(const uint8_t* __restrict__ patches, int np, const float* __restrict__ w, const float* __restrict__ b,
         __half* __restrict__ out, size_t out_slots) {
-  __shared__ float P[34][36];
-  __shared__ float ws[C1 * 9], bs[C1];
-  __shared__ unsigned red[2][8];
-  __shared__ float s_mean, s_inv;
-  const int patch = blockIdx.x, tid = threadIdx.x;
-  const uint8_t* src = patches + (size_t)patch * 1024;
-  for (int i = tid; i < 34 * 36; i += 256) (&P[0][0])[i] = 0.f;
-  for (int i = tid; i < C1 * 9; i += 256) ws[i] = w[i];
+  __shared__ __align__(16) float P[2][34][C1_PW];
+  __shared__ __align__(16) float bs[C1];
+  __shared__ uint64_t bars[4];            // full[2], empty[2]
+  uint64_t* full = bars;
+  uint64_t* empty = bars + 2;
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  for (int i = tid; i < 2 * 34 * C1_PW; i += 160) (&P[0][0][0])[i] = 0.f;
   if (tid < C1) bs[tid] = b[tid];
-  uchar4 px = reinterpret_cast<const uchar4*>(src)[tid];
-  unsigned s1 = px.x + px.y + px.z + px.w;
-  unsigned s2 = px.x * px.x + px.y * px.y + px.z * px.z + px.w * px.w;
-  for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
-  if ((tid & 31) == 0) { red[0][tid >> 5] = s1; red[1][tid >> 5] = s2; }
-  __syncthreads();
   if (tid == 0) {
-    unsigned a = 0, q = 0;
-    for (int i = 0; i < 8; i++) { a += red[0][i]; q += red[1][i]; }
-    // torch.mean / torch.std (unbiased) of the 1024 pixels; (x-mean)/(std+1e-7) (desc_server.py:83-87)
-    double mean = (double)a / 1024.0;
-    double var = ((double)q - (double)a * mean) / 1023.0;
-    if (var < 0) var = 0;
-    s_mean = (float)mean;
-    s_inv = (float)sqrt(var) + 1e-7f;
+    mbar_init(full + 0, 1); mbar_init(full + 1, 1);
+    mbar_init(empty + 0, 4); mbar_init(empty + 1, 4);
+    fence_barrier_init();
   }
   __syncthreads();
-  {
-    const float mean = s_mean, sd = s_inv;
-    int y = tid >> 3, x = (tid & 7) * 4;
-    P[y + 1][x + 1] = ((float)px.x - mean) / sd;
-    P[y + 1][x + 2] = ((float)px.y - mean) / sd;
-    P[y + 1][x + 3] = ((float)px.z - mean) / sd;
-    P[y + 1][x + 4] = ((float)px.w - mean) / sd;
-  }
-  __syncthreads();
-  // each thread keeps the 72 weights + 8 biases of ONE group of 8 output channels in registers and walks
-  // over pixels: 9 shared-memory loads + 72 FMAs per output slot
-  constexpr int C8 = C1 / 8, TPC = 256 / C8;
-  const int c8 = tid / TPC, t0 = tid - c8 * TPC;
-  float wr[8][9], br[8];
+  const int n_my = (np - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 4) {
+    // ---- prep warp: lane = row of the patch
+    const uint4* src = reinterpret_cast<const uint4*>(patches);
+    uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
+    if (n_my > 0) { a0 = __ldg(src + (size_t)blockIdx.x * 64 + lane * 2); a1 = __ldg(src + (size_t)blockIdx.x * 64 + lane * 2 + 1); }
+    for (int it = 0; it < n_my; it++) {
+      uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
+      if (it + 1 < n_my) {
+        const size_t pn = (size_t)blockIdx.x + (size_t)(it + 1) * gridDim.x;
+        n0 = __ldg(src + pn * 64 + lane * 2); n1 = __ldg(src + pn * 64 + lane * 2 + 1);
+      }
+      const uint32_t wd[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      unsigned s1 = 0, s2 = 0;
 #pragma unroll
-  for (int e = 0; e < 8; e++) {
-    br[e] = bs[c8 * 8 + e];
+      for (int k = 0; k < 8; k++)
 #pragma unroll
-    for (int t = 0; t < 9; t++) wr[e][t] = ws[(c8 * 8 + e) * 9 + t];
-  }
-#pragma unroll 2
-  for (int p = t0; p < 1024; p += TPC) {
-    const int y = p >> 5, x = p & 31;
-    float v[9];
+        for (int j = 0; j < 4; j++) { const unsigned v = (wd[k] >> (8 * j)) & 255u; s1 += v; s2 += v * v; }
+      for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+      // torch.mean / torch.std (unbiased) of the 1024 pixels; (x-mean)/(std+1e-7) (desc_server.py:83-87)
+      const double mean_d = (double)s1 / 1024.0;
+      double var = ((double)s2 - (double)s1 * mean_d) / 1023.0;
+      if (var < 0) var = 0;
+      const float mean = (float)mean_d, sd = (float)sqrt(var) + 1e-7f;
+      const int bf = it & 1, ph = (it >> 1) & 1;
+      mbar_wait(empty + bf, ph ^ 1);
+      float* row = &P[bf][lane + 1][4];
 #pragma unroll
-    for (int dy = 0; dy < 3; dy++)
-#pragma unroll
-      for (int dx = 0; dx < 3; dx++) v[dy * 3 + dx] = P[y + dy][x + dx];
-    __align__(16) __half h[8];
-#pragma unroll
-    for (int e = 0; e < 8; e++) {
-      float acc = br[e];
-#pragma unroll
-      for (int t = 0; t < 9; t++) acc = fmaf(wr[e][t], v[t], acc);
-      h[e] = __float2half_rn(fmaxf(acc, 0.f));
+      for (int k = 0; k < 8; k++) {
+        float4 f;
+        f.x = ((float)(wd[k] & 255u) - mean) / sd;
+        f.y = ((float)((wd[k] >> 8) & 255u) - mean) / sd;
+        f.z = ((float)((wd[k] >> 16) & 255u) - mean) / sd;
+        f.w = ((float)(wd[k] >> 24) - mean) / sd;
+        *reinterpret_cast<float4*>(row + 4 * k) = f;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full + bf);
+      a0 = n0; a1 = n1;
     }
-    const size_t slot = (size_t)FS + (size_t)patch * 1089 + (size_t)(y + 1) * 33 + x;
-    *reinterpret_cast<uint4*>(out + ((size_t)c8 * out_slots + slot) * 8) = *reinterpret_cast<const uint4*>(h);
+  } else {
+    // ---- conv warps: each thread keeps the 72 weights + 8 biases of ONE group of 8 output channels in registers and
+    // walks over pixels: 9 shared-memory loads + 72 FMAs per output slot
+    constexpr int C8 = C1 / 8, TPC = 128 / C8;
+    const int c8 = tid / TPC, t0 = tid - c8 * TPC;
+    float wr[8][9];
+#pragma unroll
+    for (int e = 0; e < 8; e++)
+#pragma unroll
+      for (int t = 0; t < 9; t++) wr[e][t] = __ldg(w + (c8 * 8 + e) * 9 + t);
+    for (int it = 0; it < n_my; it++) {
+      const int patch = (int)blockIdx.x + it * (int)gridDim.x;
+      const int bf = it & 1, ph = (it >> 1) & 1;
+      mbar_wait(full + bf, ph);
+      __half* obase = out + ((size_t)c8 * out_slots + (size_t)FS + (size_t)patch * 1089) * 8;
+#pragma unroll 1
+      for (int p = t0; p < 1024; p += TPC) {
+        const int y = p >> 5, x = p & 31;
+        float v[9];
+#pragma unroll
+        for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+          for (int dx = 0; dx < 3; dx++) v[dy * 3 + dx] = P[bf][y + dy][x + dx + 3];
+        const float4 b0 = *reinterpret_cast<const float4*>(bs + c8 * 8), b1 = *reinterpret_cast<const float4*>(bs + c8 * 8 + 4);
+        float acc[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        // every accumulator sees its taps in the order t = 0..8 (the contract with the oracle); the 8 chains are independent
+#pragma unroll
+        for (int t = 0; t < 9; t++)
+#pragma unroll
+          for (int e = 0; e < 8; e++) acc[e] = fmaf(wr[e][t], v[t], acc[e]);
+        uint32_t h[4];
+#pragma unroll
+        for (int e2 = 0; e2 < 4; e2++) h[e2] = relu_pack_h2(acc[2 * e2], acc[2 * e2 + 1]);
+        *reinterpret_cast<uint4*>(obase + (size_t)((y + 1) * 33 + x) * 8) = make_uint4(h[0], h[1], h[2], h[3]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + bf);
+    }
   }
 }
 
@@ -158,10 +205,22 @@ template <int CIN, int COUT_T, int NSPLIT, int S, int NGRP, int OUT_MODE>
 __global__ void __launch_bounds__(192, 1)
 k_conv_umma(const __half* __restrict__ in, size_t in_slots, const __half* __restrict__ wts,
             const float* __restrict__ bias, __half* __restrict__ out, size_t out_slots, int np, int ntiles,
-            int patch_base) {
+            int patch_base, int contig) {
   using Cfg = ConvCfg<CIN, COUT_T, NSPLIT, S, NGRP, OUT_MODE>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* w_s = smem;
+  // M tiles of this CTA.  contig: one balanced run of consecutive tiles (the halo rows a tile shares with its predecessor
+  // were fetched by this very SM one tile earlier); strided: tile = blockIdx.x + i * gridDim.x.  Measured equal on B200
+  // (bench 241.3 vs 241.1 pairs/s; DRAM reads are at the algorithmic size either way: the halo always comes from L2).
+  int tile_first, tile_end, tile_step;
+  if (contig) {
+    const int base = ntiles / (int)gridDim.x, rem = ntiles % (int)gridDim.x, b = (int)blockIdx.x;
+    tile_first = b * base + (b < rem ? b : rem);
+    tile_end = tile_first + base + (b < rem ? 1 : 0);
+    tile_step = 1;
+  } else {
+    tile_first = blockIdx.x; tile_end = ntiles; tile_step = gridDim.x;
+  }
   uint8_t* a_s = smem + Cfg::W_BYTES;
   constexpr int NST = Cfg::NST;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::W_BYTES + NST * Cfg::A_BYTES);
@@ -202,7 +261,7 @@ k_conv_umma(const __half* __restrict__ in, size_t in_slots, const __half* __rest
     }
     __syncwarp();
     int it = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+    for (int tile = tile_first; tile < tile_end; tile += tile_step, it++) {
       const int s = it % NST, ph = (it / NST) & 1;
       mbar_wait(a_empty + s, ph ^ 1);
       if (elect_one()) {
@@ -223,7 +282,7 @@ k_conv_umma(const __half* __restrict__ in, size_t in_slots, const __half* __rest
     const uint64_t a_desc0 = smem_desc(smem_u32(a_s), Cfg::TP * 16, 128);
     const uint64_t b_desc0 = smem_desc(w_addr, COUT_T * 16, 128);
     int it = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+    for (int tile = tile_first; tile < tile_end; tile += tile_step, it++) {
       const int s = it % NST, ph = (it / NST) & 1;
       const int ts = it & 1, tph = (it >> 1) & 1;
       mbar_wait(t_empty + ts, tph ^ 1);
@@ -258,8 +317,11 @@ k_conv_umma(const __half* __restrict__ in, size_t in_slots, const __half* __rest
     // ---- epilogue warps 2..5: TMEM -> bias + ReLU -> fp16 -> next layer's layout
     const int q = warp & 3;               // TMEM lane quarter this warp may touch
     const int m = q * 32 + lane;          // row of the M tile
+    float br[COUT_T];
+#pragma unroll
+    for (int e = 0; e < COUT_T; e++) br[e] = __ldg(bias + nsp * COUT_T + e);
     int it = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+    for (int tile = tile_first; tile < tile_end; tile += tile_step, it++) {
       const int s = it & 1, ph = (it >> 1) & 1;
       const int g = tile * 128 + m;
       const int patch = g / Cfg::PP;
@@ -285,12 +347,12 @@ k_conv_umma(const __half* __restrict__ in, size_t in_slots, const __half* __rest
         float v[16];
         tmem_ld16(taddr + cc * 16, v);
         if (valid) {
-          __align__(16) __half h[16];
+          uint32_t h[8];
 #pragma unroll
-          for (int e = 0; e < 16; e++) h[e] = __float2half_rn(fmaxf(v[e] + __ldg(bias + nsp * COUT_T + cc * 16 + e), 0.f));
+          for (int e = 0; e < 8; e++) h[e] = relu_pack_h2(v[2 * e] + br[cc * 16 + 2 * e], v[2 * e + 1] + br[cc * 16 + 2 * e + 1]);
           __half* o = out + ((size_t)(oplane0 + cc * 2) * out_slots + oslot) * 8;
-          *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(h);
-          *reinterpret_cast<uint4*>(o + out_slots * 8) = *reinterpret_cast<const uint4*>(h + 8);
+          *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(o + out_slots * 8) = make_uint4(h[4], h[5], h[6], h[7]);
         }
       }
       fence_before_sync();
@@ -912,7 +974,8 @@ int launch_conv(modsgpu_ctx* ctx, const __half* in, size_t in_slots, const ConvW
   static const bool one_cta = [] { const char* e = getenv("MODSGPU_CONV_ONE_CTA"); return e && atoi(e) != 0; }();   // A/B switch
   int gx = std::min(ntiles, std::max(1, ctx->num_sms * ((Cfg::TWO_CTAS && !one_cta) ? 2 : 1) / NSPLIT));
   dim3 grid(gx, NSPLIT);
-  kern<<<grid, 192, Cfg::SMEM_BYTES, ctx->stream>>>(in, in_slots, w.w, w.b, out, out_slots, np, ntiles, patch_base);
+  static const int contig = [] { const char* e = getenv("MODSGPU_CONV_STRIDED_TILES"); return (e && atoi(e) != 0) ? 0 : 1; }();   // A/B switch
+  kern<<<grid, 192, Cfg::SMEM_BYTES, ctx->stream>>>(in, in_slots, w.w, w.b, out, out_slots, np, ntiles, patch_base, contig);
   MG_LAUNCHED(ctx);
   return 0;
 }
@@ -1097,7 +1160,7 @@ int mg_net_forward_enqueue(modsgpu_ctx* ctx, modsgpu_net net, const uint8_t* d_p
         if ((rc = launch_conv12<32, 2>(ctx, pin, nw->conv[0], nw->act[1], nw->slots[1], np))) return rc;
       } else {
         MG_PROF2(ctx, "k_conv1<32>", 1, 2.0 * np * 1024 * 9 * 32, (double)np * (1024.0 + 1024.0 * 32 * 2));
-        k_conv1<32><<<np, 256, 0, ctx->stream>>>(pin, np, nw->c1_w, nw->c1_b, nw->act[0], nw->slots[0]);
+        k_conv1<32><<<std::min(np, 3 * ctx->num_sms), 160, 0, ctx->stream>>>(pin, np, nw->c1_w, nw->c1_b, nw->act[0], nw->slots[0]);
         MG_LAUNCHED(ctx);
         if ((rc = launch_conv<32, 32, 1, 32, 1, OUT_PARITY>(ctx, nw->act[0], nw->slots[0], nw->conv[0], nw->act[1], nw->slots[1], np))) return rc;
       }
@@ -1111,7 +1174,7 @@ int mg_net_forward_enqueue(modsgpu_ctx* ctx, modsgpu_net net, const uint8_t* d_p
                                          : launch_conv12<16, 1>(ctx, pin, nw->conv[0], nw->act[1], nw->slots[1], np)))) return rc;
       } else {
         MG_PROF2(ctx, "k_conv1<16>", 1, 2.0 * np * 1024 * 9 * 16, (double)np * (1024.0 + 1024.0 * 16 * 2));
-        k_conv1<16><<<np, 256, 0, ctx->stream>>>(pin, np, nw->c1_w, nw->c1_b, nw->act[0], nw->slots[0]);
+        k_conv1<16><<<std::min(np, 3 * ctx->num_sms), 160, 0, ctx->stream>>>(pin, np, nw->c1_w, nw->c1_b, nw->act[0], nw->slots[0]);
         MG_LAUNCHED(ctx);
         if ((rc = launch_conv<16, 16, 1, 32, 1, OUT_PARITY>(ctx, nw->act[0], nw->slots[0], nw->conv[0], nw->act[1], nw->slots[1], np))) return rc;
       }

@@ -201,7 +201,9 @@ def run_gpu(args, rank, world, local_rank):
     nwk = args.workers
     if nwk <= 0:
         local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
-        nwk = min(16, max(4, (os.cpu_count() or 8) // max(1, local_world)))
+        # host waits sleep (blocking-sync events in libmodsgpu), so the number of pairs in flight need not follow the
+        # core count: 16 contexts per GPU also on the 8-GPU box with its 4 cores per rank
+        nwk = 16
     # one modsgpu_ctx (= one CUDA stream + workspaces) per worker thread, as the C ABI prescribes; pairs are
     # independent, so workers overlap one pair's host-side seams with another pair's kernels
     mgs = [M.ModsGpu(local_rank, load_nets=True) for _ in range(nwk)]
@@ -228,6 +230,7 @@ def run_gpu(args, rank, world, local_rank):
 
     results = np.zeros((max(args.steps, 1), 16 + 4 * CAPACITY), np.float64)
     last = {}
+    host_cpu = {"ms": 0.0}
 
     def step_value(wk, k, store=True):
         mg = mgs[wk]
@@ -280,9 +283,11 @@ def run_gpu(args, rank, world, local_rank):
         ms = C.c_float()
         mgs[0].lib.modsgpu_timer_start(mgs[0].ctx)
         t0 = time.perf_counter()
+        c0 = time.process_time()
         gate.wait()
         for t in ths:
             t.join()
+        host_cpu["ms"] = (time.process_time() - c0) * 1e3
         torch.cuda.synchronize()
         gather_results()
         mgs[0].lib.modsgpu_timer_stop(mgs[0].ctx, C.byref(ms))
@@ -316,6 +321,7 @@ def run_gpu(args, rank, world, local_rank):
     timed(step_e2e, 2 * nwk)
     launches0 = sum(mg.launch_count for mg in mgs)
     dev_ms, wall_ms = timed(step_value, args.steps)
+    host_cpu_ms_per_step = host_cpu["ms"] / max(args.steps, 1)
     launches = sum(mg.launch_count for mg in mgs) - launches0
     e2e_ms, e2e_wall = timed(step_e2e, args.steps)
     clk = clocks.stop() if rank == 0 else None
@@ -424,6 +430,7 @@ def run_gpu(args, rank, world, local_rank):
                     "note": "h2d/d2h count the API-level buffers (two BGR images in, verified correspondences + H out); "
                             "the seam-by-seam host round trips of the reference interface are inside the timed region too"},
             "gpu_launches": launches, "wall_ms_per_step": wall_ms / args.steps,
+            "host_cpu_ms_per_step": host_cpu_ms_per_step, "host_cores": os.cpu_count(),
             "roofline": roofline, "kernels": kernels, "clocks": clk}
     if cpu:
         line["cpu_baseline"] = cpu
@@ -443,9 +450,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workers", type=int, default=int(os.environ.get("MODSGPU_BENCH_WORKERS", "0")),
-                    help="worker threads (one modsgpu_ctx / CUDA stream each) per GPU; 0 = auto: min(16, host cores / ranks "
-                         "on this node), at least 4 (measured on B200 with 16 host cores: 8 -> 216, 12 -> 221, 16 -> 233, "
-                         "24 -> 233, 32 -> 230 pairs/s)")
+                    help="worker threads (one modsgpu_ctx / CUDA stream each) per GPU; 0 = 16 (measured on B200 with 16 "
+                         "host cores: 8 -> 216, 12 -> 221, 16 -> 233, 24 -> 233, 32 -> 230 pairs/s)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

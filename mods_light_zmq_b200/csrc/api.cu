@@ -22,6 +22,12 @@ extern "C" int modsgpu_create(int device, modsgpu_ctx** out) {
     delete ctx;
     return MODSGPU_ECUDA;
   }
+  const char* spin = getenv("MODSGPU_SPIN_SYNC");
+  if (!(spin && atoi(spin) != 0) &&
+      cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess) {
+    delete ctx;
+    return MODSGPU_ECUDA;
+  }
   *out = ctx;
   return 0;
 }
@@ -29,7 +35,7 @@ extern "C" int modsgpu_create(int device, modsgpu_ctx** out) {
 extern "C" void modsgpu_destroy(modsgpu_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  mg_stream_sync(ctx);
   mg_free_nets(ctx);
   DevBuf* bufs[] = {&ctx->det_pyr, &ctx->det_cand, &ctx->det_map, &ctx->det_out, &ctx->det_misc, &ctx->det_aff, &ctx->io_a, &ctx->io_b,
                     &ctx->io_c, &ctx->smp_regs, &ctx->smp_meta, &ctx->smp_taps, &ctx->smp_scratch, &ctx->smp_out,
@@ -38,6 +44,7 @@ extern "C" void modsgpu_destroy(modsgpu_ctx* ctx) {
   for (DevBuf* b : bufs) b->release();
   ctx->h_stage.release();
   ctx->h_stage2.release();
+  ctx->h_out.release();
   for (auto e : ctx->prof.pool) cudaEventDestroy(e);
   for (auto& r : ctx->prof.recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   ctx->l2flush.release();
@@ -46,6 +53,7 @@ extern "C" void modsgpu_destroy(modsgpu_ctx* ctx) {
   if (ctx->tm1) cudaEventDestroy(ctx->tm1);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
+  if (ctx->ev_sync) cudaEventDestroy(ctx->ev_sync);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -76,7 +84,7 @@ void mg_prof_end(modsgpu_ctx* ctx) {
 }
 static void prof_collect(modsgpu_ctx* ctx) {
   Profiler& P = ctx->prof;
-  cudaStreamSynchronize(ctx->stream);
+  mg_stream_sync(ctx);
   for (auto& r : P.recs) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
@@ -116,14 +124,14 @@ extern "C" int modsgpu_timer_start(modsgpu_ctx* ctx) {
   if (!ctx) return MODSGPU_EINVAL;
   MG_CUDA(ctx, cudaSetDevice(ctx->device));
   if (!ctx->tm0) { MG_CUDA(ctx, cudaEventCreate(&ctx->tm0)); MG_CUDA(ctx, cudaEventCreate(&ctx->tm1)); }
-  MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  MG_CUDA(ctx, mg_stream_sync(ctx));
   MG_CUDA(ctx, cudaEventRecord(ctx->tm0, ctx->stream));
   return 0;
 }
 extern "C" int modsgpu_timer_stop(modsgpu_ctx* ctx, float* ms) {
   if (!ctx || !ms || !ctx->tm0) return MODSGPU_EINVAL;
   MG_CUDA(ctx, cudaEventRecord(ctx->tm1, ctx->stream));
-  MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  MG_CUDA(ctx, mg_stream_sync(ctx));
   MG_CUDA(ctx, cudaEventElapsedTime(ms, ctx->tm0, ctx->tm1));
   return 0;
 }

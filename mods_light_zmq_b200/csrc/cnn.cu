@@ -205,7 +205,7 @@ template <int CIN, int COUT_T, int NSPLIT, int S, int NGRP, int OUT_MODE>
 __global__ void __launch_bounds__(192, 1)
 k_conv_umma(const __half* __restrict__ in, size_t in_slots, const __half* __restrict__ wts,
             const float* __restrict__ bias, __half* __restrict__ out, size_t out_slots, int np, int ntiles,
-            int patch_base, int contig) {
+            int patch_base, int contig, int nst) {
   using Cfg = ConvCfg<CIN, COUT_T, NSPLIT, S, NGRP, OUT_MODE>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* w_s = smem;
@@ -222,7 +222,9 @@ k_conv_umma(const __half* __restrict__ in, size_t in_slots, const __half* __rest
     tile_first = blockIdx.x; tile_end = ntiles; tile_step = gridDim.x;
   }
   uint8_t* a_s = smem + Cfg::W_BYTES;
-  constexpr int NST = Cfg::NST;
+  // nst <= Cfg::NST stages of the A ring are in use (the launch sizes the dynamic shared memory for nst: a shallower ring
+  // leaves room for CTAs of other streams' kernels on the same SM)
+  const int NST = nst;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::W_BYTES + NST * Cfg::A_BYTES);
   uint64_t* w_full = bars;                  // weights landed
   uint64_t* a_full = bars + 1;              // [NST]
@@ -260,9 +262,8 @@ k_conv_umma(const __half* __restrict__ in, size_t in_slots, const __half* __rest
       }
     }
     __syncwarp();
-    int it = 0;
-    for (int tile = tile_first; tile < tile_end; tile += tile_step, it++) {
-      const int s = it % NST, ph = (it / NST) & 1;
+    int s = 0, ph = 0;
+    for (int tile = tile_first; tile < tile_end; tile += tile_step) {
       mbar_wait(a_empty + s, ph ^ 1);
       if (elect_one()) {
         mbar_expect_tx(a_full + s, Cfg::A_BYTES);
@@ -273,6 +274,7 @@ k_conv_umma(const __half* __restrict__ in, size_t in_slots, const __half* __rest
           bulk_g2s(dst + pl * Cfg::TP * 16, in + ((size_t)pl * in_slots + slot0) * 8, Cfg::TP * 16, a_full + s);
       }
       __syncwarp();
+      if (++s == NST) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
     // ---- MMA issuer: the warp waits together, one elected lane issues the 9 x KSTEPS MMAs of the tile back to back
@@ -281,9 +283,8 @@ k_conv_umma(const __half* __restrict__ in, size_t in_slots, const __half* __rest
     const uint32_t w_addr = smem_u32(w_s);
     const uint64_t a_desc0 = smem_desc(smem_u32(a_s), Cfg::TP * 16, 128);
     const uint64_t b_desc0 = smem_desc(w_addr, COUT_T * 16, 128);
-    int it = 0;
+    int it = 0, s = 0, ph = 0;
     for (int tile = tile_first; tile < tile_end; tile += tile_step, it++) {
-      const int s = it % NST, ph = (it / NST) & 1;
       const int ts = it & 1, tph = (it >> 1) & 1;
       mbar_wait(t_empty + ts, tph ^ 1);
       mbar_wait(a_full + s, ph);
@@ -312,6 +313,7 @@ k_conv_umma(const __half* __restrict__ in, size_t in_slots, const __half* __rest
         mma_commit(t_full + ts);   // accumulator ready for the epilogue
       }
       __syncwarp();
+      if (++s == NST) { s = 0; ph ^= 1; }
     }
   } else {
     // ---- epilogue warps 2..5: TMEM -> bias + ReLU -> fp16 -> next layer's layout
@@ -975,7 +977,11 @@ int launch_conv(modsgpu_ctx* ctx, const __half* in, size_t in_slots, const ConvW
   int gx = std::min(ntiles, std::max(1, ctx->num_sms * ((Cfg::TWO_CTAS && !one_cta) ? 2 : 1) / NSPLIT));
   dim3 grid(gx, NSPLIT);
   static const int contig = [] { const char* e = getenv("MODSGPU_CONV_STRIDED_TILES"); return (e && atoi(e) != 0) ? 0 : 1; }();   // A/B switch
-  kern<<<grid, 192, Cfg::SMEM_BYTES, ctx->stream>>>(in, in_slots, w.w, w.b, out, out_slots, np, ntiles, patch_base, contig);
+  // depth of the A ring: MODSGPU_CONV_STAGES caps it (default: as deep as the layer's configuration allows)
+  static const int stage_cap = [] { const char* e = getenv("MODSGPU_CONV_STAGES"); return e ? std::max(2, atoi(e)) : 64; }();
+  const int nst = std::min(Cfg::NST, stage_cap);
+  const int smem_bytes = Cfg::W_BYTES + nst * Cfg::A_BYTES + 256;
+  kern<<<grid, 192, smem_bytes, ctx->stream>>>(in, in_slots, w.w, w.b, out, out_slots, np, ntiles, patch_base, contig, nst);
   MG_LAUNCHED(ctx);
   return 0;
 }
@@ -1014,7 +1020,7 @@ int launch_conv12(modsgpu_ctx* ctx, const uint8_t* patches, const ConvW& w2, __h
   if (debug) {      // stall table of CTA 0 (cycles): role loop total, then its wait counters
     long long h[23 * 4];
     MG_CUDA(ctx, cudaMemcpyAsync(h, dbg, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-    MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    MG_CUDA(ctx, mg_stream_sync(ctx));
     const long long n = h[22 * 4] > 0 ? h[22 * 4] : 1;
     fprintf(stderr, "k_conv12<%d> np %d tiles/CTA %lld (cycles per tile: loop, wait0, wait1, store+fence+arrive)\n", C1, np, n);
     for (int w : {0, 3, 4, 5, 11, 13, 21})
@@ -1220,8 +1226,7 @@ extern "C" int modsgpu_net_forward_u8(modsgpu_ctx* ctx, modsgpu_net net, const u
   MG_CUDA(ctx, cudaMemcpyAsync(ctx->smp_out.p, patches, (size_t)n * 1024, cudaMemcpyHostToDevice, ctx->stream));
   int rc = mg_net_forward_enqueue(ctx, net, ctx->smp_out.as<uint8_t>(), n, ctx->cnn_out.as<float>());
   if (rc) return rc;
-  MG_CUDA(ctx, cudaMemcpyAsync(out, ctx->cnn_out.p, (size_t)n * D * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  return mg_end(ctx) ? MODSGPU_ECUDA : 0;
+  return mg_read_back_end(ctx, out, ctx->cnn_out.p, (size_t)n * D * 4);
 }
 
 int mg_sample_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_region* regs, int n,
@@ -1240,8 +1245,7 @@ extern "C" int modsgpu_describe(modsgpu_ctx* ctx, modsgpu_net net, const modsgpu
   if (rc) return rc;
   rc = mg_net_forward_enqueue(ctx, net, ctx->smp_out.as<uint8_t>(), n, ctx->cnn_out.as<float>());
   if (rc) return rc;
-  MG_CUDA(ctx, cudaMemcpyAsync(out, ctx->cnn_out.p, (size_t)n * D * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  return mg_end(ctx) ? MODSGPU_ECUDA : 0;
+  return mg_read_back_end(ctx, out, ctx->cnn_out.p, (size_t)n * D * 4);
 }
 
 // test-only: D[128 x 32] = A[128 x 64] * B[32 x 64]^T through the tcgen05 path; A/B given row-major fp32

@@ -69,6 +69,8 @@ struct modsgpu_ctx {
   int num_sms = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  HostBuf h_out;                   // pinned landing area of result read-backs (mg_read_back)
+  cudaEvent_t ev_sync = nullptr;   // cudaEventBlockingSync: host waits sleep instead of spinning (mg_stream_sync)
   float last_ms = 0.f;
   long long launches = 0;
   std::string err;
@@ -118,6 +120,17 @@ void mg_prof_end(modsgpu_ctx* ctx);
     MG_CUDA(ctx, cudaGetLastError());            \
   } while (0)
 
+// Host wait for the context's stream.  The wait sleeps on a blocking-sync event: a process usually drives several
+// contexts from several threads (one per pair in flight), often more threads than it has cores (4 cores per GPU on the
+// 8-GPU box), and a spinning cudaStreamSynchronize per thread starves the threads that have launches to issue.
+// MODSGPU_SPIN_SYNC=1 restores the spinning wait (lowest latency for a single context).
+static inline cudaError_t mg_stream_sync(modsgpu_ctx* ctx) {
+  if (!ctx->ev_sync) return cudaStreamSynchronize(ctx->stream);
+  cudaError_t e = cudaEventRecord(ctx->ev_sync, ctx->stream);
+  if (e != cudaSuccess) return e;
+  return cudaEventSynchronize(ctx->ev_sync);
+}
+
 static inline int mg_begin(modsgpu_ctx* ctx) {
   MG_CUDA(ctx, cudaSetDevice(ctx->device));
   MG_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
@@ -125,8 +138,19 @@ static inline int mg_begin(modsgpu_ctx* ctx) {
 }
 static inline int mg_end(modsgpu_ctx* ctx) {
   MG_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-  MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  MG_CUDA(ctx, mg_stream_sync(ctx));
   MG_CUDA(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+  return 0;
+}
+
+// Device -> caller's (pageable) buffer at the end of an entry point: land in pinned memory, wait for the stream with the
+// sleeping wait, then memcpy.  (A cudaMemcpyAsync to pageable memory would wait for the preceding kernels inside the
+// driver, spinning on a core.)  Includes mg_end.
+static inline int mg_read_back_end(modsgpu_ctx* ctx, void* dst, const void* d_src, size_t bytes) {
+  MG_CUDA(ctx, ctx->h_out.ensure(bytes));
+  MG_CUDA(ctx, cudaMemcpyAsync(ctx->h_out.p, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (mg_end(ctx)) return MODSGPU_ECUDA;
+  memcpy(dst, ctx->h_out.p, bytes);
   return 0;
 }
 

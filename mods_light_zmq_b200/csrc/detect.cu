@@ -726,7 +726,7 @@ extern "C" int modsgpu_image_from_gray32f(modsgpu_ctx* ctx, const float* gray, i
 extern "C" int modsgpu_image_download(modsgpu_ctx* ctx, const modsgpu_image* img, float* gray) {
   if (!ctx || !img || !gray) return MODSGPU_EINVAL;
   MG_CUDA(ctx, cudaMemcpyAsync(gray, img->d, (size_t)img->w * img->h * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  MG_CUDA(ctx, mg_stream_sync(ctx));
   return 0;
 }
 
@@ -1016,7 +1016,7 @@ static int detect_impl(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu
     MG_CUDA(ctx, ctx->h_stage.ensure(64));
     int* hc = ctx->h_stage.as<int>();
     MG_CUDA(ctx, cudaMemcpyAsync(hc, ctx->det_misc.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    MG_CUDA(ctx, mg_stream_sync(ctx));
     if (hc[0] > cap) { cap = hc[0] + hc[0] / 8; continue; }  // candidate list overflowed: redo with room
     int kept = hc[1];
     modsgpu_keypoint* res = (modsgpu_keypoint*)malloc(sizeof(modsgpu_keypoint) * (size_t)std::max(kept, 1));

@@ -4,6 +4,9 @@
 #include "mods_host.h"
 #include "../npz.h"
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <ctime>
 #include <cmath>
 #include <cstring>
 #include <fstream>
@@ -12,6 +15,16 @@ namespace modsb200 {
 
 static double now_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+// CPU time of the calling thread (MODSGPU_HOST_PROFILE=1: per-stage host cost of a pair, printed on stderr)
+static double cpu_ms() {
+  timespec ts;
+  clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts);
+  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+static bool host_profile() {
+  static const bool on = [] { const char* e = getenv("MODSGPU_HOST_PROFILE"); return e && atoi(e) != 0; }();
+  return on;
 }
 
 // helpers.cpp:524-549.  NB callers pass doubles into the int res_w/res_h (truncation).
@@ -193,7 +206,10 @@ int ImageRepresentation::DescribeView(modsgpu_image* view, const double* H, int 
   // ---- DetectAffineRegions (synth-detection.hpp:79-112) over DetectAffineKeypoints
   modsgpu_keypoint* kps = nullptr;
   int n = 0;
+  const bool hp = host_profile();
+  double hc[5] = {0, 0, 0, 0, 0}, hc0 = hp ? cpu_ms() : 0;
   int rc = modsgpu_detect(ctx_, view, &par.pyr, &kps, &n);
+  if (hp) hc[0] = cpu_ms() - hc0;
   if (rc) return rc;
   n_keypoints = n;
   AffineRegionVector temp_kp1(n);
@@ -211,7 +227,9 @@ int ImageRepresentation::DescribeView(modsgpu_image* view, const double* H, int 
   // ---- AffNet (imagerepresentation.cpp:797-845); the border test is against the VIEW
   to_regions(temp_kp1, regs);
   out.resize((size_t)n * 3 + 1);
+  if (hp) hc0 = cpu_ms();
   rc = modsgpu_describe(ctx_, MODSGPU_AFFNET, view, regs.data(), n, par.mrSize, par.patchSize, out.data());
+  if (hp) hc[1] = cpu_ms() - hc0;
   if (rc) return rc;
   AffineRegionVector temp_kp_aff;
   temp_kp_aff.reserve(n);
@@ -246,7 +264,9 @@ int ImageRepresentation::DescribeView(modsgpu_image* view, const double* H, int 
   const int n2 = (int)kept.size();
   to_regions(kept, regs);
   out.resize((size_t)n2 * 2 + 1);
+  if (hp) hc0 = cpu_ms();
   rc = modsgpu_describe(ctx_, MODSGPU_ORINET, view, regs.data(), n2, par.mrSize, par.patchSize, out.data());
+  if (hp) hc[2] = cpu_ms() - hc0;
   if (rc) return rc;
   AffineRegionVector oriented;
   oriented.reserve(n2);
@@ -281,13 +301,20 @@ int ImageRepresentation::DescribeView(modsgpu_image* view, const double* H, int 
   const int n3 = (int)final_regs.size();
   to_regions(final_regs, regs);
   out.resize((size_t)n3 * 128 + 1);
+  if (hp) hc0 = cpu_ms();
   rc = modsgpu_describe(ctx_, MODSGPU_HARDNET, view, regs.data(), n3, par.mrSize, par.patchSize, out.data());
+  if (hp) hc[3] = cpu_ms() - hc0;
   if (rc) return rc;
-  for (int i = 0; i < n3; i++) {
-    final_regs[i].desc.assign(out.begin() + (size_t)i * 128, out.begin() + (size_t)(i + 1) * 128);
-    final_regs[i].id = i;
+  {
+    out.resize((size_t)n3 * 128);
+    auto blk = std::make_shared<const std::vector<float>>(std::move(out));
+    for (int i = 0; i < n3; i++) {
+      final_regs[i].desc.view(blk, (size_t)i * 128, 128);
+      final_regs[i].id = i;
+    }
   }
   result.swap(final_regs);
+  if (hp) fprintf(stderr, "[modsgpu host]   view: cpu ms in detect %.2f affnet %.2f orinet %.2f hardnet %.2f\n", hc[0], hc[1], hc[2], hc[3]);
   TimeSpent.DescTime += now_ms() - t0;
   return n3;
 }
@@ -436,16 +463,25 @@ int MatchFlannFGINN(modsgpu_ctx* ctx, const AffineRegionVector& list1, const Aff
   const int n1 = (int)list1.size(), n2 = (int)list2.size();
   if (n1 == 0 || n2 == 0) return 0;
   const int dim = (int)list1[0].desc.size();
-  std::vector<float> q((size_t)n1 * dim), t((size_t)n2 * dim);
+  // descriptors of one describe call sit back to back in their block: hand that block over as it is
+  auto flat = [dim](const AffineRegionVector& l, std::vector<float>& tmp) -> const float* {
+    const std::vector<float>* b = l[0].desc.block();
+    bool contiguous = b != nullptr;
+    for (size_t i = 0; contiguous && i < l.size(); i++)
+      contiguous = l[i].desc.block() == b && l[i].desc.size() == (size_t)dim && l[i].desc.offset() == l[0].desc.offset() + i * dim;
+    if (contiguous) return l[0].desc.data();
+    tmp.resize(l.size() * (size_t)dim);
+    for (size_t i = 0; i < l.size(); i++) memcpy(&tmp[i * dim], l[i].desc.data(), dim * sizeof(float));
+    return tmp.data();
+  };
+  std::vector<float> qtmp, ttmp;
+  const float* q = flat(list1, qtmp);
+  const float* t = flat(list2, ttmp);
   std::vector<double> txy((size_t)n2 * 2);
-  for (int i = 0; i < n1; i++) memcpy(&q[(size_t)i * dim], list1[i].desc.data(), dim * sizeof(float));
-  for (int i = 0; i < n2; i++) {
-    memcpy(&t[(size_t)i * dim], list2[i].desc.data(), dim * sizeof(float));
-    txy[2 * i] = list2[i].reproj_kp.x; txy[2 * i + 1] = list2[i].reproj_kp.y;
-  }
+  for (int i = 0; i < n2; i++) { txy[2 * i] = list2[i].reproj_kp.x; txy[2 * i + 1] = list2[i].reproj_kp.y; }
   std::vector<modsgpu_match> m(n1);
   int nm = 0;
-  int rc = modsgpu_match_fginn(ctx, q.data(), n1, t.data(), txy.data(), n2, dim, par.FGINNThreshold, par.contradDist,
+  int rc = modsgpu_match_fginn(ctx, q, n1, t, txy.data(), n2, dim, par.FGINNThreshold, par.contradDist,
                                par.nn, m.data(), &nm, nullptr, nullptr);
   if (rc) return rc;
   corresp.TCList.reserve(nm);
@@ -512,11 +548,9 @@ static int NaiveHCheck(const TentativeCorrespListExt& corresp, const double* H, 
   return corr_numb;
 }
 
-// Htools.c HDsSymMax for one point pair: Hl in the degensac convention (column-major, image 2 -> image 1)
-static double HDsSymMax1(const double* Hl, const double* u) {
-  const double Hm[9] = {Hl[0], Hl[3], Hl[6], Hl[1], Hl[4], Hl[7], Hl[2], Hl[5], Hl[8]};
-  double H1[9];
-  invert3(Hm, H1);
+// Htools.c HDsSymMax for one point pair: Hm = Hl transposed (degensac convention: column-major, image 2 -> image 1),
+// H1 = inv(Hm); both are the same for every pair of a call and are formed once by the caller
+static double HDsSymMax1(const double* Hm, const double* H1, const double* u) {
   const double a = H1[6] * u[0] + H1[7] * u[1] + H1[8];
   const double b = Hm[6] * u[3] + Hm[7] * u[4] + Hm[8];
   double xa = (H1[0] * u[0] + H1[1] * u[1] + H1[2]) / a, ya = (H1[3] * u[0] + H1[4] * u[1] + H1[5]) / a;
@@ -534,6 +568,10 @@ static void H_LAF_check(const std::vector<TentativeCorrespExt>& in, const double
   const double k_sigma = 2 * 3.0 * std::sqrt(3.0);
   res.clear();
   if (!(affineFerror > 0)) { res = in; return; }
+  res.reserve(in.size());
+  const double Hm[9] = {Hl[0], Hl[3], Hl[6], Hl[1], Hl[4], Hl[7], Hl[2], Hl[5], Hl[8]};
+  double H1[9];
+  invert3(Hm, H1);
   for (const auto& c : in) {
     const AffineKeypoint &f = c.first.reproj_kp, &s = c.second.reproj_kp;
     double u[18];
@@ -542,7 +580,7 @@ static void H_LAF_check(const std::vector<TentativeCorrespExt>& in, const double
     u[9] = u[3] + k_sigma * s.a12 * s.s; u[10] = u[4] + k_sigma * s.a22 * s.s; u[11] = 1.0;
     u[12] = u[0] + k_sigma * f.a11 * f.s; u[13] = u[1] + k_sigma * f.a21 * f.s; u[14] = 1.0;
     u[15] = u[3] + k_sigma * s.a11 * s.s; u[16] = u[4] + k_sigma * s.a21 * s.s; u[17] = 1.0;
-    const double sumErr = std::sqrt(HDsSymMax1(Hl, u) + HDsSymMax1(Hl, u + 6) + HDsSymMax1(Hl, u + 12));
+    const double sumErr = std::sqrt(HDsSymMax1(Hm, H1, u) + HDsSymMax1(Hm, H1, u + 6) + HDsSymMax1(Hm, H1, u + 12));
     if (!(sumErr > affineFerror)) res.push_back(c);
   }
 }
@@ -574,6 +612,7 @@ int LORANSACFiltering(modsgpu_ctx* ctx, TentativeCorrespListExt& in_corresp, Ten
   int rc = pars.useF ? modsgpu_ransac_F(ctx, u2.data(), tent_size, &rp, Hloran, inl2.data(), &rr)
                      : modsgpu_ransac_H(ctx, u2.data(), tent_size, &rp, Hloran, inl2.data(), &rr);
   if (rc) return rc;
+  ransac_corresp.TCList.reserve(tent_size);
   for (int i = 0; i < tent_size; i++) {
     in_corresp.TCList[i].isTrue = inl2[i];
     if (inl2[i]) ransac_corresp.TCList.push_back(in_corresp.TCList[i]);
@@ -674,24 +713,37 @@ extern "C" int modsgpu_pair_pipeline_images(modsgpu_ctx* ctx, modsgpu_image* img
   MatchPars mp;
   RANSACPars rp;
   rp.seed = seed;
+  const bool hp = host_profile();
+  double c[6] = {0, 0, 0, 0, 0, 0}, w[6] = {0, 0, 0, 0, 0, 0};
+  auto mark = [&](int i) { if (hp) { c[i] = cpu_ms(); w[i] = now_ms(); } };
+  mark(0);
   ImageRepresentation r1(ctx, img1, false), r2(ctx, img2, false);
   int n1 = r1.SynthDetectDescribeKeypoints(dp);
   if (n1 < 0) return n1;
+  mark(1);
   int n2 = r2.SynthDetectDescribeKeypoints(dp);
   if (n2 < 0) return n2;
+  mark(2);
   res->keypoints[0] = r1.n_keypoints; res->keypoints[1] = r2.n_keypoints;
   res->regions[0] = r1.n_affine; res->regions[1] = r2.n_affine;
   res->descriptors[0] = n1; res->descriptors[1] = n2;
   TentativeCorrespListExt tent, verified;
   int nt = MatchFlannFGINN(ctx, r1.GetAffineRegionVector(), r2.GetAffineRegionVector(), tent, mp);
   if (nt < 0) return nt;
+  mark(3);
   res->tentatives = nt;
   int nu = DuplicateFiltering(ctx, tent, mp.doubleFilteringRadius);
   if (nu < 0) return nu;
+  mark(4);
   res->unique_tentatives = nu;
   int ni = LORANSACFiltering(ctx, tent, verified, res->H, rp);
   if (ni < 0) return ni;
+  mark(5);
   res->inliers = ni;
+  if (hp)
+    fprintf(stderr, "[modsgpu host] cpu ms (wall ms): image1 %.2f (%.2f) image2 %.2f (%.2f) match %.2f (%.2f) dup %.2f (%.2f) ransac %.2f (%.2f)\n",
+            c[1] - c[0], w[1] - w[0], c[2] - c[1], w[2] - w[1], c[3] - c[2], w[3] - w[2], c[4] - c[3], w[4] - w[3],
+            c[5] - c[4], w[5] - w[4]);
   for (int i = 0; i < ni && i < capacity && inlier_xy; i++) {
     const TentativeCorrespExt& c = verified.TCList[i];
     inlier_xy[4 * i + 0] = c.first.reproj_kp.x; inlier_xy[4 * i + 1] = c.first.reproj_kp.y;

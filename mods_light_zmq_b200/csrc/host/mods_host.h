@@ -7,6 +7,7 @@
 //   MatchFlannFGINN       matching.cpp:356-460      DuplicateFiltering  matching.cpp:2615-2679
 //   LORANSACFiltering     matching.cpp:637-823      (H branch: NaiveHCheck :1014-1043, H_LAF_check :250-308)
 #pragma once
+#include <memory>
 #include <string>
 #include <vector>
 #include "../../../include/modsgpu.h"
@@ -19,10 +20,30 @@ struct AffineKeypoint {            // structures.hpp:185-194
   double response = 0;
   int octave_number = 0, sub_type = 0;
 };
+// descriptor.vec of a region.  Regions travel by value through the tentative / filtered / verified lists
+// (TentativeCorrespExt holds two of them), so the vector is a VIEW into a shared block -- the n x 128 read-back of one
+// modsgpu_describe call -- and a copy costs a reference count, not an allocation.
+class DescVec {
+ public:
+  size_t size() const { return n_; }
+  bool empty() const { return n_ == 0; }
+  const float* data() const { return blk_ ? blk_->data() + off_ : nullptr; }
+  float operator[](size_t i) const { return (*blk_)[off_ + i]; }
+  template <class It> void assign(It a, It b) {
+    auto v = std::make_shared<std::vector<float>>(a, b);
+    n_ = v->size(); off_ = 0; blk_ = std::move(v);
+  }
+  void view(const std::shared_ptr<const std::vector<float>>& blk, size_t off, size_t n) { blk_ = blk; off_ = off; n_ = n; }
+  const std::vector<float>* block() const { return blk_.get(); }
+  size_t offset() const { return off_; }
+ private:
+  std::shared_ptr<const std::vector<float>> blk_;
+  size_t off_ = 0, n_ = 0;
+};
 struct AffineRegion {              // structures.hpp:218-229
   int img_id = 0, img_reproj_id = 0, id = 0, parent_id = 0, type = 0;
   AffineKeypoint det_kp, reproj_kp;
-  std::vector<float> desc;         // descriptor.vec
+  DescVec desc;                    // descriptor.vec
 };
 typedef std::vector<AffineRegion> AffineRegionVector;
 

@@ -202,7 +202,7 @@ int mg_ransac_run(modsgpu_ctx* ctx, const double* d_u, int T, const modsgpu_rans
   memset(hs, 0, sizeof(RsState));
   hs->max_sam = p->max_samples;
   MG_CUDA(ctx, cudaMemcpyAsync(st, hs, sizeof(RsState), cudaMemcpyHostToDevice, ctx->stream));
-  MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // hs is reused as the read-back buffer below
+  MG_CUDA(ctx, mg_stream_sync(ctx));   // hs is reused as the read-back buffer below
   int basei = 0, batch = 0;
   for (;;) {
     int B = batch == 0 ? 512 : (batch == 1 ? 1024 : RS_MAX_B);
@@ -219,7 +219,7 @@ int mg_ransac_run(modsgpu_ctx* ctx, const double* d_u, int T, const modsgpu_rans
     k_rs_accept<<<1, 32, 0, ctx->stream>>>(d_u, T, p->th, p->conf, p->do_sym_check, B, st, sh);
     MG_LAUNCHED(ctx);
     MG_CUDA(ctx, cudaMemcpyAsync(hs, st, sizeof(RsState), cudaMemcpyDeviceToHost, ctx->stream));
-    MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    MG_CUDA(ctx, mg_stream_sync(ctx));
     basei += B; batch++;
     if (hs->done) break;
   }
@@ -236,7 +236,7 @@ int mg_ransac_run(modsgpu_ctx* ctx, const double* d_u, int T, const modsgpu_rans
   unsigned char* hinl = reinterpret_cast<unsigned char*>(hs + 1);
   MG_CUDA(ctx, cudaMemcpyAsync(hs, st, sizeof(RsState), cudaMemcpyDeviceToHost, ctx->stream));
   MG_CUDA(ctx, cudaMemcpyAsync(hinl, dinl, T, cudaMemcpyDeviceToHost, ctx->stream));
-  MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  MG_CUDA(ctx, mg_stream_sync(ctx));
   for (int i = 0; i < 9; i++) H[i] = hs->H[i];
   memcpy(inl, hinl, T);
   if (res) { res->n_inliers = hs->I; res->J = hs->J; res->samples = hs->no_sam; res->lo_runs = hs->lo_runs; res->oc_rejects = hs->oc_rejects; res->degen_runs = 0; res->h_inliers = 0; }

@@ -913,7 +913,7 @@ int mg_ransac_F_run(modsgpu_ctx* ctx, const double* d_u, int T, const modsgpu_ra
   memset(hs, 0, sizeof(RfState));
   hs->max_sam = p->max_samples;
   MG_CUDA(ctx, cudaMemcpyAsync(st, hs, sizeof(RfState), cudaMemcpyHostToDevice, ctx->stream));
-  MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  MG_CUDA(ctx, mg_stream_sync(ctx));
   int basei = 0, batch = 0;
   for (;;) {
     int B = batch == 0 ? 512 : (batch == 1 ? 1024 : RS_MAX_B);
@@ -929,7 +929,7 @@ int mg_ransac_F_run(modsgpu_ctx* ctx, const double* d_u, int T, const modsgpu_ra
     k_rf_accept<<<1, 32, 0, ctx->stream>>>(T, p->conf, B, st, sh);
     MG_LAUNCHED(ctx);
     MG_CUDA(ctx, cudaMemcpyAsync(hs, st, sizeof(RfState), cudaMemcpyDeviceToHost, ctx->stream));
-    MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    MG_CUDA(ctx, mg_stream_sync(ctx));
     if (hs->degen_pending) {
       // DEGENSAC: plane homography by an inner H-RANSAC at 16*th, then plane-and-parallax
       DegShare hd;
@@ -942,7 +942,7 @@ int mg_ransac_F_run(modsgpu_ctx* ctx, const double* d_u, int T, const modsgpu_ra
       int pbase = batch * 1000003;
       for (int it = 0; it < 64; it++) {
         MG_CUDA(ctx, cudaMemcpyAsync(&hd, deg, sizeof(DegShare), cudaMemcpyDeviceToHost, ctx->stream));
-        MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        MG_CUDA(ctx, mg_stream_sync(ctx));
         if (!hd.run_pp || hd.done) break;
         MG_PROF(ctx, "k_rfd_pp_hyp", 2, (double)PP_B);
         k_rfd_pp_hyp<<<ceil_div(PP_B, 8), 256, 0, ctx->stream>>>(d_u, T, p->th, p->seed, pbase, PP_B, deg, iscr,
@@ -956,7 +956,7 @@ int mg_ransac_F_run(modsgpu_ctx* ctx, const double* d_u, int T, const modsgpu_ra
       k_rfd_finish<<<1, 32, 0, ctx->stream>>>(d_u, T, p->th, p->conf, st, deg);
       MG_LAUNCHED(ctx);
       MG_CUDA(ctx, cudaMemcpyAsync(hs, st, sizeof(RfState), cudaMemcpyDeviceToHost, ctx->stream));
-      MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      MG_CUDA(ctx, mg_stream_sync(ctx));
     }
     basei += B; batch++;
     if (hs->done) break;
@@ -974,7 +974,7 @@ int mg_ransac_F_run(modsgpu_ctx* ctx, const double* d_u, int T, const modsgpu_ra
   unsigned char* hinl = reinterpret_cast<unsigned char*>(hs + 1);
   MG_CUDA(ctx, cudaMemcpyAsync(hs, st, sizeof(RfState), cudaMemcpyDeviceToHost, ctx->stream));
   MG_CUDA(ctx, cudaMemcpyAsync(hinl, dinl, T, cudaMemcpyDeviceToHost, ctx->stream));
-  MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  MG_CUDA(ctx, mg_stream_sync(ctx));
   const bool have = hs->J > 0;
   int ninl = 0;
   for (int i = 0; i < T; i++) { if (!have) hinl[i] = 0; ninl += hinl[i]; }

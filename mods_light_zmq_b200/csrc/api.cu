@@ -45,6 +45,7 @@ extern "C" void modsgpu_destroy(modsgpu_ctx* ctx) {
   ctx->h_stage.release();
   ctx->h_stage2.release();
   ctx->h_out.release();
+  for (auto& g : ctx->det_graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
   for (auto e : ctx->prof.pool) cudaEventDestroy(e);
   for (auto& r : ctx->prof.recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   ctx->l2flush.release();

@@ -69,6 +69,9 @@ struct modsgpu_ctx {
   int num_sms = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // detector launch sequences captured as CUDA graphs, keyed by everything a launch argument depends on (mg_detect_graph)
+  struct DetGraph { cudaGraphExec_t exec = nullptr; long long launches = 0; int uses = 0; };
+  std::map<std::string, DetGraph> det_graphs;
   HostBuf h_out;                   // pinned landing area of result read-backs (mg_read_back)
   cudaEvent_t ev_sync = nullptr;   // cudaEventBlockingSync: host waits sleep instead of spinning (mg_stream_sync)
   float last_ms = 0.f;

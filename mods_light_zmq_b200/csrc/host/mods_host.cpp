@@ -234,32 +234,40 @@ int ImageRepresentation::DescribeView(modsgpu_image* view, const double* H, int 
   AffineRegionVector temp_kp_aff;
   temp_kp_aff.reserve(n);
   for (int i = 0; i < n; i++) {
-    AffineRegion t = temp_kp1[i];
+    // built in place at the back of the list and popped again when a test rejects it (one copy per region)
+    temp_kp_aff.push_back(temp_kp1[i]);
+    AffineRegion& t = temp_kp_aff.back();
     t.det_kp.a11 = out[3 * i + 0];
     t.det_kp.a12 = 0;
     t.det_kp.a21 = out[3 * i + 1];
     t.det_kp.a22 = out[3 * i + 2];
     rectifyAffineTransformationUpIsUp(t.det_kp.a11, t.det_kp.a12, t.det_kp.a21, t.det_kp.a22);
     float l1 = 1.0f, l2 = 1.0f;
-    if (!getEigenvalues((float)t.det_kp.a11, (float)t.det_kp.a12, (float)t.det_kp.a21, (float)t.det_kp.a22, l1, l2)) continue;
-    if ((l1 / l2 > 6) || (l2 / l1 > 6)) continue;
-    if (interpolateCheckBorders(w, h, (float)t.det_kp.x, (float)t.det_kp.y, (float)t.det_kp.a11, (float)t.det_kp.a12,
-                                (float)t.det_kp.a21, (float)t.det_kp.a22, (int)(par.mrSize * t.det_kp.s),
-                                (int)(par.mrSize * t.det_kp.s)))
-      continue;
-    temp_kp_aff.push_back(t);
+    bool keep = getEigenvalues((float)t.det_kp.a11, (float)t.det_kp.a12, (float)t.det_kp.a21, (float)t.det_kp.a22, l1, l2);
+    keep = keep && !((l1 / l2 > 6) || (l2 / l1 > 6));
+    keep = keep && !interpolateCheckBorders(w, h, (float)t.det_kp.x, (float)t.det_kp.y, (float)t.det_kp.a11, (float)t.det_kp.a12,
+                                            (float)t.det_kp.a21, (float)t.det_kp.a22, (int)(par.mrSize * t.det_kp.s),
+                                            (int)(par.mrSize * t.det_kp.s));
+    if (!keep) temp_kp_aff.pop_back();
   }
   n_affine = (int)temp_kp_aff.size();
   TimeSpent.DetectTime += now_ms() - t0;
   t0 = now_ms();
   // ---- ReprojectRegionsAndRemoveTouchBoundary(dontRemove = true) (synth-detection.cpp:151-190)
-  AffineRegionVector kept;
-  kept.reserve(temp_kp_aff.size());
-  for (auto& r : temp_kp_aff) {
-    r.reproj_kp = r.det_kp;
-    if (!eye) ReprojectByH(r.det_kp, r.reproj_kp, Hinv);
-    if ((r.reproj_kp.x < orig_w) && (r.reproj_kp.y < orig_h) && (r.reproj_kp.x > 0) && (r.reproj_kp.y > 0)) kept.push_back(r);
+  // filtered in place (the survivors keep their order)
+  {
+    size_t nk = 0;
+    for (auto& r : temp_kp_aff) {
+      r.reproj_kp = r.det_kp;
+      if (!eye) ReprojectByH(r.det_kp, r.reproj_kp, Hinv);
+      if ((r.reproj_kp.x < orig_w) && (r.reproj_kp.y < orig_h) && (r.reproj_kp.x > 0) && (r.reproj_kp.y > 0)) {
+        if (&temp_kp_aff[nk] != &r) temp_kp_aff[nk] = r;
+        nk++;
+      }
+    }
+    temp_kp_aff.resize(nk);
   }
+  AffineRegionVector& kept = temp_kp_aff;
   // ---- OriNet (imagerepresentation.cpp:876-899), patches from the view
   const int n2 = (int)kept.size();
   to_regions(kept, regs);
@@ -268,35 +276,38 @@ int ImageRepresentation::DescribeView(modsgpu_image* view, const double* H, int 
   rc = modsgpu_describe(ctx_, MODSGPU_ORINET, view, regs.data(), n2, par.mrSize, par.patchSize, out.data());
   if (hp) hc[2] = cpu_ms() - hc0;
   if (rc) return rc;
-  AffineRegionVector oriented;
-  oriented.reserve(n2);
+  // rotated in place: every new entry is computed from the OLD four entries of the same region
   for (int i = 0; i < n2; i++) {
-    const AffineRegion& c = kept[i];
+    AffineKeypoint& k = kept[i].det_kp;
     double angle = std::atan2((double)out[2 * i + 0], (double)out[2 * i + 1]);
     double ci = std::cos(angle), si = std::sin(angle);
-    AffineRegion t = c;
-    t.det_kp.a11 = c.det_kp.a11 * ci - c.det_kp.a12 * si;
-    t.det_kp.a12 = c.det_kp.a11 * si + c.det_kp.a12 * ci;
-    t.det_kp.a21 = c.det_kp.a21 * ci - c.det_kp.a22 * si;
-    t.det_kp.a22 = c.det_kp.a21 * si + c.det_kp.a22 * ci;
-    oriented.push_back(t);
+    const double a11 = k.a11, a12 = k.a12, a21 = k.a21, a22 = k.a22;
+    k.a11 = a11 * ci - a12 * si;
+    k.a12 = a11 * si + a12 * ci;
+    k.a21 = a21 * ci - a22 * si;
+    k.a22 = a21 * si + a22 * ci;
   }
+  AffineRegionVector& oriented = kept;
   TimeSpent.OrientTime += now_ms() - t0;
   t0 = now_ms();
   // ---- ReprojectRegions (synth-detection.cpp:631-706): centre inside + k_sigma*s frame inside the ORIGINAL image
   const double k_sigma = 2 * 3.0 * std::sqrt(3.0);   // synth-detection.cpp:21
-  AffineRegionVector final_regs;
-  final_regs.reserve(oriented.size());
-  for (auto& r : oriented) {
-    r.reproj_kp = r.det_kp;
-    if (!eye) ReprojectByH(r.det_kp, r.reproj_kp, Hinv);
-    const AffineKeypoint& p = r.reproj_kp;
-    if ((p.x < orig_w) && (p.y < orig_h) && (p.x > 0) && (p.y > 0)) {
-      if (!interpolateCheckBorders(orig_w, orig_h, (float)p.x, (float)p.y, (float)p.a11, (float)p.a12, (float)p.a21, (float)p.a22,
-                                   (int)(k_sigma * p.s), (int)(k_sigma * p.s)))
-        final_regs.push_back(r);
+  {
+    size_t nk = 0;
+    for (auto& r : oriented) {
+      r.reproj_kp = r.det_kp;
+      if (!eye) ReprojectByH(r.det_kp, r.reproj_kp, Hinv);
+      const AffineKeypoint& p = r.reproj_kp;
+      if ((p.x < orig_w) && (p.y < orig_h) && (p.x > 0) && (p.y > 0) &&
+          !interpolateCheckBorders(orig_w, orig_h, (float)p.x, (float)p.y, (float)p.a11, (float)p.a12, (float)p.a21, (float)p.a22,
+                                   (int)(k_sigma * p.s), (int)(k_sigma * p.s))) {
+        if (&oriented[nk] != &r) oriented[nk] = r;
+        nk++;
+      }
     }
+    oriented.resize(nk);
   }
+  AffineRegionVector& final_regs = oriented;
   // ---- HardNet++ (imagerepresentation.cpp:992-1006), patches from the view
   const int n3 = (int)final_regs.size();
   to_regions(final_regs, regs);

@@ -761,10 +761,15 @@ int mg_sample_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
   if (ps < 2 || ps > MAX_PS) MG_FAIL(ctx, MODSGPU_EINVAL, "patchSize out of range");
   if (n <= 0) return 0;
   enum { C_SMALL = 0, C_A1, C_A2, C_B1, C_B2, C_LARGE, NCLS };
-  std::vector<PatchMeta> cls[NCLS];
+  // host scratch is per thread and keeps its capacity: this runs three times per image on the calling thread
+  static thread_local std::vector<PatchMeta> cls[NCLS], sort_tmp;
+  static thread_local std::vector<float> taps_all;
+  static thread_local std::vector<int> tap_off_of, tap_ks_of, r_hist;   // indexed by R0 / R
+  for (int c = 0; c < NCLS; c++) cls[c].clear();
+  taps_all.clear();
+  tap_off_of.assign(MAX_R + 4, -1);
+  tap_ks_of.assign(MAX_R + 4, 0);
   int cls_r[NCLS] = {0, 0, 0, 0, 0, 0};           // max blur radius per class
-  std::map<int, std::pair<int, int>> tap_index;   // R0 -> (offset, ks)
-  std::vector<float> taps_all;
   for (int i = 0; i < n; i++) {
     const modsgpu_region& k = regs[i];
     PatchMeta m;
@@ -780,14 +785,13 @@ int mg_sample_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
     if (m.scale > 0.4) {
       m.R = R0 + 2;
       if (m.R > MAX_R) MG_FAIL(ctx, MODSGPU_EINVAL, "region too large for the sampler (R > 2048)");
-      auto it = tap_index.find(R0);
-      if (it == tap_index.end()) {
+      if (tap_off_of[R0] < 0) {
         std::vector<float> t;
-        int ks = mg_gaussian_taps(1.5f * m.scale, t);
-        it = tap_index.emplace(R0, std::make_pair((int)taps_all.size(), ks)).first;
+        tap_ks_of[R0] = mg_gaussian_taps(1.5f * m.scale, t);
+        tap_off_of[R0] = (int)taps_all.size();
         taps_all.insert(taps_all.end(), t.begin(), t.end());
       }
-      m.tap_off = it->second.first; m.ks = it->second.second;
+      m.tap_off = tap_off_of[R0]; m.ks = tap_ks_of[R0];
       if (m.ks > 600) MG_FAIL(ctx, MODSGPU_EINVAL, "sampler blur too wide");
       const bool blocked = m.ks >= 7 && m.ks <= 60 && ps <= 64;
       if (blocked && m.R <= A1_R) c = C_A1;
@@ -802,8 +806,18 @@ int mg_sample_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
     cls[c].push_back(m);
     cls_r[c] = std::max(cls_r[c], m.ks >> 1);
   }
-  for (int c = C_A1; c <= C_LARGE; c++)
-    std::stable_sort(cls[c].begin(), cls[c].end(), [](const PatchMeta& a, const PatchMeta& b) { return a.R > b.R; });
+  // decreasing R inside a class, region order among equal R (a stable counting sort: R <= MAX_R)
+  for (int c = C_A1; c <= C_LARGE; c++) {
+    std::vector<PatchMeta>& v = cls[c];
+    if (v.size() < 2) continue;
+    r_hist.assign(MAX_R + 2, 0);
+    for (const PatchMeta& m : v) r_hist[m.R]++;
+    int pos = 0;
+    for (int R = MAX_R; R >= 0; R--) { const int cnt = r_hist[R]; r_hist[R] = pos; pos += cnt; }
+    sort_tmp.resize(v.size());
+    for (const PatchMeta& m : v) sort_tmp[r_hist[m.R]++] = m;
+    v.swap(sort_tmp);
+  }
   std::vector<PatchMeta>& large = cls[C_LARGE];
   long long scratch = 0;
   for (PatchMeta& m : large) {

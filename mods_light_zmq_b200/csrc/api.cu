@@ -17,13 +17,15 @@ extern "C" int modsgpu_create(int device, modsgpu_ctx** out) {
   modsgpu_ctx* ctx = new modsgpu_ctx();
   ctx->device = device;
   ctx->num_sms = prop.multiProcessorCount;
+  const char* spin = getenv("MODSGPU_SPIN_SYNC");
+  const bool spinning = spin && atoi(spin) != 0;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+      cudaEventCreate(&ctx->ev0) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev1, spinning ? cudaEventDefault : cudaEventBlockingSync) != cudaSuccess) {
     delete ctx;
     return MODSGPU_ECUDA;
   }
-  const char* spin = getenv("MODSGPU_SPIN_SYNC");
-  if (!(spin && atoi(spin) != 0) &&
+  if (!spinning &&
       cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess) {
     delete ctx;
     return MODSGPU_ECUDA;
@@ -60,7 +62,12 @@ extern "C" void modsgpu_destroy(modsgpu_ctx* ctx) {
 }
 
 extern "C" const char* modsgpu_last_error(const modsgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
-extern "C" float modsgpu_last_device_ms(const modsgpu_ctx* ctx) { return ctx ? ctx->last_ms : 0.f; }
+extern "C" float modsgpu_last_device_ms(const modsgpu_ctx* ctx) {
+  if (!ctx) return 0.f;
+  float ms = ctx->last_ms;
+  if (ms < 0.f && cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) != cudaSuccess) { cudaGetLastError(); ms = 0.f; }
+  return ms;
+}
 extern "C" long long modsgpu_launch_count(const modsgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" void* modsgpu_stream(const modsgpu_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 

@@ -761,10 +761,13 @@ __device__ __forceinline__ void load8(const __half* p, float* f) {
 // AffNet: conv 8x8 (64->3, bias) -> tanh -> +1 on outputs 0 and 2 (affnet_server.py:64-66,:80-84)
 // OriNet: conv 8x8 pad 1 (64->2, bias) -> 3x3 map -> tanh -> mean (orinet_server.py:64-70)
 // Weights live in shared memory as [o][e/4][item][4] (item = c8*64 + pix, e = channel within the 8-channel plane) so that
-// the 32 lanes of a warp, which walk consecutive items, read consecutive float4s: two conflict-free LDS.128 per
-// 8 FMAs (the first version read one scalar weight per FMA and was LSU-bound); one warp per patch, persistent.
-template <int NOUT, bool ORI>
-__global__ void __launch_bounds__(256)
+// the 32 lanes of a warp, which walk consecutive items, read consecutive float4s.  A warp works on HEAD_PB patches at
+// once (OriNet): every pair of weight LDS.128 feeds 8 FMAs of each of the HEAD_PB patches (one patch per warp was bound by the
+// shared-memory loads: 8 TFLOP/s); the accumulation order per (patch, position, output, lane) is unchanged.
+// OriNet: 4 patches per warp, 4 warps per CTA; AffNet (12k MACs per patch, bound by its 8 KB activation read): 1 patch
+// per warp, 8 warps per CTA
+template <int NOUT, bool ORI, int HEAD_PB, int NW>
+__global__ void __launch_bounds__(NW * 32)
 k_head_small(const __half* __restrict__ act, size_t slots, const float* __restrict__ w, const float* __restrict__ b,
              float* __restrict__ out, int np) {
   extern __shared__ float ws[];   // NOUT * 8 * 512
@@ -772,62 +775,66 @@ k_head_small(const __half* __restrict__ act, size_t slots, const float* __restri
   for (int i = threadIdx.x; i < NOUT * 1024; i += blockDim.x) reinterpret_cast<float4*>(ws)[i] = __ldg(reinterpret_cast<const float4*>(w) + i);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int patch = blockIdx.x * 8 + warp; patch < np; patch += gridDim.x * 8) {
-    constexpr int NPOS = ORI ? 9 : 1;
-    float acc[NPOS][NOUT];
+  constexpr int NPOS = ORI ? 9 : 1;
+  for (int p0 = (blockIdx.x * NW + warp) * HEAD_PB; p0 < np; p0 += gridDim.x * NW * HEAD_PB) {
+    float acc[HEAD_PB][NPOS][NOUT];
 #pragma unroll
-    for (int p = 0; p < NPOS; p++)
+    for (int q = 0; q < HEAD_PB; q++)
 #pragma unroll
-      for (int o = 0; o < NOUT; o++) acc[p][o] = 0.f;
-#pragma unroll 8
+      for (int p = 0; p < NPOS; p++)
+#pragma unroll
+        for (int o = 0; o < NOUT; o++) acc[q][p][o] = 0.f;
+#pragma unroll (ORI ? 1 : 8)
     for (int k = 0; k < 16; k++) {
       const int it = lane + 32 * k;
       const int c8 = it >> 6, pix = it & 63, y = pix >> 3, x = pix & 7;   // a warp reads 32 consecutive pixels of one plane
-      float a[8];
-      load8(act + ((size_t)c8 * slots + FS + (size_t)patch * 81 + (y + 1) * 9 + x) * 8, a);
-      if (!ORI) {
+      float a[HEAD_PB][8];
 #pragma unroll
-        for (int o = 0; o < NOUT; o++) {
-          const float4 w0 = *reinterpret_cast<const float4*>(ws + ((o * 2 + 0) * 512 + it) * 4);
-          const float4 w1 = *reinterpret_cast<const float4*>(ws + ((o * 2 + 1) * 512 + it) * 4);
-          float s0 = acc[0][o];
-          s0 = fmaf(a[0], w0.x, s0); s0 = fmaf(a[1], w0.y, s0); s0 = fmaf(a[2], w0.z, s0); s0 = fmaf(a[3], w0.w, s0);
-          s0 = fmaf(a[4], w1.x, s0); s0 = fmaf(a[5], w1.y, s0); s0 = fmaf(a[6], w1.z, s0); s0 = fmaf(a[7], w1.w, s0);
-          acc[0][o] = s0;
-        }
-      } else {
+      for (int q = 0; q < HEAD_PB; q++) {
+        const int patch = min(p0 + q, np - 1);   // the tail group re-reads the last patch; its results are not written
+        load8(act + ((size_t)c8 * slots + FS + (size_t)patch * 81 + (y + 1) * 9 + x) * 8, a[q]);
+      }
 #pragma unroll
-        for (int pos = 0; pos < 9; pos++) {
+      for (int pos = 0; pos < NPOS; pos++) {
+        int wit = it;
+        if (ORI) {
           const int ky = y - pos / 3 + 1, kx = x - pos % 3 + 1;
           if (ky < 0 || ky > 7 || kx < 0 || kx > 7) continue;
-          const int wit = c8 * 64 + ky * 8 + kx;
+          wit = c8 * 64 + ky * 8 + kx;
+        }
 #pragma unroll
-          for (int o = 0; o < NOUT; o++) {
-            const float4 w0 = *reinterpret_cast<const float4*>(ws + ((o * 2 + 0) * 512 + wit) * 4);
-            const float4 w1 = *reinterpret_cast<const float4*>(ws + ((o * 2 + 1) * 512 + wit) * 4);
-            float s0 = acc[pos][o];
-            s0 = fmaf(a[0], w0.x, s0); s0 = fmaf(a[1], w0.y, s0); s0 = fmaf(a[2], w0.z, s0); s0 = fmaf(a[3], w0.w, s0);
-            s0 = fmaf(a[4], w1.x, s0); s0 = fmaf(a[5], w1.y, s0); s0 = fmaf(a[6], w1.z, s0); s0 = fmaf(a[7], w1.w, s0);
-            acc[pos][o] = s0;
+        for (int o = 0; o < NOUT; o++) {
+          const float4 w0 = *reinterpret_cast<const float4*>(ws + ((o * 2 + 0) * 512 + wit) * 4);
+          const float4 w1 = *reinterpret_cast<const float4*>(ws + ((o * 2 + 1) * 512 + wit) * 4);
+#pragma unroll
+          for (int q = 0; q < HEAD_PB; q++) {
+            float s0 = acc[q][pos][o];
+            s0 = fmaf(a[q][0], w0.x, s0); s0 = fmaf(a[q][1], w0.y, s0); s0 = fmaf(a[q][2], w0.z, s0); s0 = fmaf(a[q][3], w0.w, s0);
+            s0 = fmaf(a[q][4], w1.x, s0); s0 = fmaf(a[q][5], w1.y, s0); s0 = fmaf(a[q][6], w1.z, s0); s0 = fmaf(a[q][7], w1.w, s0);
+            acc[q][pos][o] = s0;
           }
         }
       }
     }
-    float res[NOUT];
 #pragma unroll
-    for (int o = 0; o < NOUT; o++) res[o] = 0.f;
+    for (int q = 0; q < HEAD_PB; q++) {
+      float res[NOUT];
 #pragma unroll
-    for (int p = 0; p < NPOS; p++)
+      for (int o = 0; o < NOUT; o++) res[o] = 0.f;
 #pragma unroll
-      for (int o = 0; o < NOUT; o++) res[o] += tanhf(warp_sum(acc[p][o]) + b[o]);
-    if (lane == 0) {
-      if (ORI) {
-        out[patch * 2 + 0] = res[0] / 9.f;
-        out[patch * 2 + 1] = res[1] / 9.f;
-      } else {
-        out[patch * 3 + 0] = res[0] + 1.f;
-        out[patch * 3 + 1] = res[1];
-        out[patch * 3 + 2] = res[NOUT - 1] + 1.f;
+      for (int p = 0; p < NPOS; p++)
+#pragma unroll
+        for (int o = 0; o < NOUT; o++) res[o] += tanhf(warp_sum(acc[q][p][o]) + b[o]);
+      const int patch = p0 + q;
+      if (lane == 0 && patch < np) {
+        if (ORI) {
+          out[patch * 2 + 0] = res[0] / 9.f;
+          out[patch * 2 + 1] = res[1] / 9.f;
+        } else {
+          out[patch * 3 + 0] = res[0] + 1.f;
+          out[patch * 3 + 1] = res[1];
+          out[patch * 3 + 2] = res[NOUT - 1] + 1.f;
+        }
       }
     }
   }
@@ -1190,16 +1197,17 @@ int mg_net_forward_enqueue(modsgpu_ctx* ctx, modsgpu_net net, const uint8_t* d_p
       if ((rc = launch_conv<64, 64, 1, 8, 1, OUT_NORMAL>(ctx, nw->act[4], nw->slots[4], nw->conv[4], nw->act[5], nw->slots[5], np))) return rc;
       static OnceFlags hattr;
       if (hattr.need(ctx->device)) {
-        MG_CUDA(ctx, cudaFuncSetAttribute(k_head_small<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 4096 * 4));
-        MG_CUDA(ctx, cudaFuncSetAttribute(k_head_small<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4096 * 4));
+        MG_CUDA(ctx, cudaFuncSetAttribute(k_head_small<3, false, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 4096 * 4));
+        MG_CUDA(ctx, cudaFuncSetAttribute(k_head_small<2, true, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4096 * 4));
         hattr.set(ctx->device);
       }
-      const int hgrid = std::min(ceil_div(np, 8), 4 * ctx->num_sms);   // 24-48 KB of weights per CTA: 4 CTAs (32 warps) per SM
       MG_PROF(ctx, net == MODSGPU_AFFNET ? "k_head_aff" : "k_head_ori", 1, 2.0 * np * (net == MODSGPU_AFFNET ? 12288.0 : 61952.0));
-      if (net == MODSGPU_AFFNET)
-        k_head_small<3, false><<<hgrid, 256, 3 * 4096 * 4, ctx->stream>>>(nw->act[5], nw->slots[5], nw->head_w32, nw->head_b, pout, np);
-      else
-        k_head_small<2, true><<<hgrid, 256, 2 * 4096 * 4, ctx->stream>>>(nw->act[5], nw->slots[5], nw->head_w32, nw->head_b, pout, np);
+      if (net == MODSGPU_AFFNET)   // 48 KB of weights per CTA: 4 CTAs (32 warps) per SM
+        k_head_small<3, false, 1, 8><<<std::min(ceil_div(np, 8), 4 * ctx->num_sms), 256, 3 * 4096 * 4, ctx->stream>>>(
+            nw->act[5], nw->slots[5], nw->head_w32, nw->head_b, pout, np);
+      else                         // 4 warps x 4 patches per CTA pass, 160 registers: 3 CTAs per SM
+        k_head_small<2, true, 4, 4><<<std::min(ceil_div(np, 16), 3 * ctx->num_sms), 128, 2 * 4096 * 4, ctx->stream>>>(
+            nw->act[5], nw->slots[5], nw->head_w32, nw->head_b, pout, np);
       MG_LAUNCHED(ctx);
     }
   }

@@ -140,9 +140,11 @@ static inline int mg_begin(modsgpu_ctx* ctx) {
   return 0;
 }
 static inline int mg_end(modsgpu_ctx* ctx) {
+  // ev1 is the entry point's end marker AND what the host sleeps on (it carries cudaEventBlockingSync unless
+  // MODSGPU_SPIN_SYNC=1); the elapsed time is formed only when modsgpu_last_device_ms asks for it
   MG_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-  MG_CUDA(ctx, mg_stream_sync(ctx));
-  MG_CUDA(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+  MG_CUDA(ctx, ctx->ev_sync ? cudaEventSynchronize(ctx->ev1) : cudaStreamSynchronize(ctx->stream));
+  ctx->last_ms = -1.f;
   return 0;
 }
 

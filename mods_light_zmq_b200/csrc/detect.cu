@@ -1012,7 +1012,12 @@ static int mg_detect_graph(modsgpu_ctx* ctx, const modsgpu_image* img, const mod
                            const modsgpu_affshape_params* aff) {
   static const bool no_graphs = [] { const char* e = getenv("MODSGPU_NO_GRAPHS"); return e && atoi(e) != 0; }();
   if (no_graphs || aff || ctx->prof.on) return mg_detect_enqueue(ctx, img, p, cap, aff);
-  std::string key(reinterpret_cast<const char*>(p), sizeof(*p));
+  modsgpu_pyr_params pk;                 // field by field into a zeroed copy: the caller's padding bytes are not part of the key
+  memset(&pk, 0, sizeof(pk));
+  pk.numberOfScales = p->numberOfScales; pk.initialSigma = p->initialSigma; pk.threshold = p->threshold;
+  pk.edgeEigenValueRatio = p->edgeEigenValueRatio; pk.border = p->border; pk.detectorMode = p->detectorMode;
+  pk.rel_threshold = p->rel_threshold; pk.reg_number = p->reg_number; pk.rel_reg_number = p->rel_reg_number;
+  std::string key(reinterpret_cast<const char*>(&pk), sizeof(pk));
   const void* ptrs[6] = {img->d, ctx->det_pyr.p, ctx->det_map.p, ctx->det_cand.p, ctx->det_out.p, ctx->det_misc.p};
   const int dims[3] = {img->w, img->h, cap};
   key.append(reinterpret_cast<const char*>(ptrs), sizeof(ptrs));

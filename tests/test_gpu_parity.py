@@ -101,6 +101,39 @@ def test_detect_idempotent_and_flat(mg, oracle):
     assert np.all(np.diff(np.abs(k1["response"])) <= 0)
 
 
+def test_detect_graph_replay_equals_plain_launches(mg, oracle):
+    """The detector's launch sequence is captured into a CUDA graph on a repeated request for the same image buffer
+    (detect.cu:mg_detect_graph): the plain first call, the capturing call and the replays must give the oracle's list,
+    and every call must account for the same number of kernel launches.  A second buffer of another size and a
+    parameter change in between must not hit the first buffer's graph."""
+    from mods_light_zmq_b200 import synth
+    ga = _gray(oracle, synth.blob_image(seed=11, w=320, h=240, n_blobs=260))
+    gb = _gray(oracle, synth.blob_image(seed=12, w=288, h=200, n_blobs=220))
+    ia, ib = mg.image_from_gray32f(ga), mg.image_from_gray32f(gb)
+    ra, rb = oracle.detect_hessian(ga), oracle.detect_hessian(gb)
+    per_call = []
+    for rep in range(5):
+        l0 = mg.launch_count
+        ka = mg.detect(ia)
+        per_call.append(mg.launch_count - l0)
+        kb = mg.detect(ib)
+        for k, r in ((ka, ra), (kb, rb)):
+            assert len(k) == len(r)
+            for f in ("x", "y", "s", "response", "r0", "c0", "level", "octave", "type"):
+                assert np.array_equal(k[f], r[f]), (rep, f)
+    assert len(set(per_call)) == 1 and per_call[0] > 10, per_call
+    # another threshold on the same buffer: its own key, fewer keypoints, again the oracle's list
+    import mods_light_zmq_b200 as M
+    pg = M.PyrParams()
+    mg.lib.modsgpu_default_pyr_params(C.byref(pg))
+    pg.threshold = 9.0
+    po = oracle.default_params()
+    po.threshold = 9.0
+    kt = mg.detect(ia, pg)
+    rt = oracle.detect_hessian(ga, po)
+    assert 0 < len(kt) < len(ra) and len(kt) == len(rt) and np.array_equal(kt["response"], rt["response"])
+
+
 # ------------------------------------------------------------------------------------------ sampler
 def _random_affine_regions(oracle, kps, rng):
     regs = oracle.regions_from_keypoints(kps)

@@ -679,6 +679,44 @@ def test_mods_iterations_on_tilted_pair(mg, oracle):
     assert (d <= 16.0).all()
 
 
+def test_mods_view_sharded_loop_equals_mods_pair(mg):
+    """mods_dist.mods_pair_sharded (config 5 across GPUs: one view per extraction call, rows exchanged, matching on the
+    accumulated lists) must reproduce modsgpu_mods_pair on one context: same region counts per step, same tentatives,
+    same verified set and model.  Two in-process "ranks" dealing the units 0::2 / 1::2 and merging by unit index give
+    the same lists as one rank (the collective itself is covered by the gloo test)."""
+    from mods_light_zmq_b200 import synth, mods_dist as D
+    a = synth.blob_image(seed=91, w=640, h=480, n_blobs=1500)
+    Ht = np.array([[0.34, 0.06, 60.0], [-0.02, 0.97, 10.0], [0.0, 0.0, 1.0]])
+    b = synth.warp_image(a, Ht, noise_seed=5)
+    i1, i2 = mg.image_from_bgr8(synth.gray_to_bgr(a)), mg.image_from_bgr8(synth.gray_to_bgr(b))
+    steps = [dict(tilts=[1.0], phi=360.0), dict(tilts=[1.0, 2.0, 4.0], phi=360.0)]
+    ref = mg.mods_pair(i1, i2, steps, min_matches=100000, seed=3)
+    ev, mt = D.gpu_callables(mg, i1, i2, seed=3)
+    got = D.mods_pair_sharded(ev, mt, steps, min_matches=100000)
+    assert got["steps_done"] == ref["steps_done"] == 2 and got["views"] == 4
+    assert got["regions"] == ref["regions"]
+    res = got["result"]
+    assert res["tentatives"] == ref["tentatives"] and res["unique_tentatives"] == ref["unique_tentatives"]
+    assert res["inliers"] == ref["inliers"] and np.array_equal(res["model"], ref["model"])
+    assert np.array_equal(res["inlier_xy"], ref["inlier_xy"])
+    # the dealing: units of rank 0 and rank 1 extracted separately and merged by unit index
+    hist = []
+    feats = [[], []]
+    for st in steps:
+        views = D.step_views(st, hist)
+        units, _ = D.deal_units(len(views), 0, 1)
+        rows = {}
+        for rank in (0, 1):
+            for (k, j) in D.deal_units(len(views), rank, 2)[1]:
+                rows[units.index((k, j))] = ev(k, views[j])
+        for i, (k, j) in enumerate(units):
+            feats[k].append(rows[i])
+    for k in (0, 1):
+        merged = np.concatenate(feats[k])
+        for f in ("x", "y", "s", "a11", "a12", "a21", "a22", "desc"):
+            assert np.array_equal(merged[f], got["features"][k][f]), f
+
+
 # ------------------------------------------------------------------------------------------ classic stages (rows a18, a19)
 def test_dominant_orientation_bit_exact(mg, oracle, synth_pair):
     """DetectOrientation (synth-detection.cpp:1039-1149) on every keypoint of the 1024x768 image: the same regions are

@@ -118,3 +118,87 @@ def test_pnm_reader_matches_memory(tmp_path):
         f.write(b"P5 13 9 255\n" + g.tobytes())
     a = batch.read_image_bgr(str(p))
     assert a.shape == (9, 13, 3) and np.array_equal(a[:, :, 0], g) and np.array_equal(a[:, :, 2], g)
+
+
+# ------------------------------------------------------------------------------------------ config 5: views across ranks
+MODS_WORKER = r'''
+import os, sys, zlib
+import numpy as np
+sys.path.insert(0, %(root)r)
+import torch.distributed as dist
+import mods_light_zmq_b200 as M
+from mods_light_zmq_b200 import mods_dist as D
+
+def fake_extract_view(k, view):
+    # deterministic function of (image, view) only; some views give no region at all
+    seed = zlib.crc32(np.array([k, view["tilt"], view["phi"], view["zoom"]], np.float64).tobytes()) & 0x7fffffff
+    rng = np.random.RandomState(seed)
+    n = seed %% 6
+    f = np.zeros(n, M.FEATURE_DTYPE)
+    f["x"], f["y"], f["s"] = rng.uniform(1, 60, n), rng.uniform(1, 40, n), rng.uniform(2, 9, n)
+    f["a11"], f["a22"] = 1.0, 1.0
+    f["desc"] = rng.randint(0, 256, (n, 128))
+    return f
+
+calls = []
+def fake_match(f1, f2, fginn):
+    calls.append((len(f1), len(f2)))
+    return dict(inliers=(len(f1) + len(f2)) // int(%(div)d), tentatives=len(f1))
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+d = None
+if world > 1:
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=rank, world_size=world)
+    d = dist
+steps = [dict(tilts=[1.0], phi=360.0), dict(tilts=[1.0, 2.0, 4.0], phi=360.0), dict(tilts=[1.0, 2.0, 4.0, 6.0], phi=120.0)]
+r = D.mods_pair_sharded(fake_extract_view, fake_match, steps, rank, world, d, None, min_matches=%(minm)d)
+crc = [zlib.crc32(f.tobytes()) for f in r["features"]]
+print("RESULT", rank, r["steps_done"], r["views"], r["regions"][0], r["regions"][1], crc[0], crc[1], r["inliers"], len(calls),
+      list(r["features"][0]["view"]) == sorted(r["features"][0]["view"]))
+if d is not None:
+    dist.destroy_process_group()
+'''
+
+
+def _run_mods(tmp, tag, world, port, minm, div=1000):
+    script = tmp / (tag + "_mods_worker.py")
+    script.write_text(MODS_WORKER % {"root": ROOT, "port": port, "minm": minm, "div": div})
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    res = [p.communicate(timeout=240) for p in procs]
+    out = []
+    for p, (o, e) in zip(procs, res):
+        assert p.returncode == 0, e[-2000:]
+        out.append(o.split("RESULT")[1].split())
+    return out
+
+
+def test_mods_views_world2_equals_world1(tmp_path):
+    """The view-sharded MODS loop (mods_dist.py): with two ranks every rank ends with the region lists, in the order, of
+    the one-rank run; only rank 0 matches; all ranks leave the loop at the same step."""
+    one = _run_mods(tmp_path, "m1", 1, 29621, minm=10 ** 9)[0]
+    two = _run_mods(tmp_path, "m2", 2, 29622, minm=10 ** 9)
+    # steps_done, views, regions, checksums of both lists
+    assert one[1] == "3" and int(one[2]) == 1 + 3 + 15    # 1; tilt 2: 1 rotation, tilt 4: 2; Phi 120: 3 + 6 + 9 - the 3 already seen
+    for r in two:
+        assert r[1:8] == one[1:8], (r, one)
+        assert r[-1] == "True"                            # rows of one image stay in view order
+    assert two[0][8] == "3" and two[1][8] == "0"          # matching ran on rank 0 only
+    # early stop is decided on rank 0 and followed by every rank
+    one_s = _run_mods(tmp_path, "m3", 1, 29623, minm=1, div=1)[0]
+    two_s = _run_mods(tmp_path, "m4", 2, 29624, minm=1, div=1)
+    assert one_s[1] == two_s[0][1] == two_s[1][1] and int(one_s[1]) < 3
+    assert two_s[0][7] == two_s[1][7] == one_s[7]        # the broadcast verified count
+
+
+def test_step_views_follow_SetVSPars_history():
+    from mods_light_zmq_b200 import mods_dist as D
+    hist = []
+    n = [len(D.step_views(st, hist)) for st in D.MODS_ZMQ_HESSIAN_STEPS]
+    # [HessianAffine2] Phi 360: 1 + (1 + 2 + 3 + 4) rotations; [HessianAffine3] Phi 120: 3 + 6 + 9 + 12 minus the phi = 0 views
+    assert n == [11, 20], n
+    assert len(hist) == sum(n)
+    units, mine = D.deal_units(5, 1, 3)
+    assert len(units) == 10 and mine == [units[1], units[4], units[7]]

@@ -1030,6 +1030,11 @@ extern "C" int modsgpu_match_features(modsgpu_ctx* ctx, const modsgpu_feature* f
   const int cnt[2] = {n1, n2};
   for (int k = 0; k < 2; k++) {
     l[k].resize((size_t)cnt[k]);
+    // one descriptor block per list, the regions hold views into it (what DescribeView produces)
+    auto blk = std::make_shared<std::vector<float>>((size_t)cnt[k] * desc_dim);
+    for (int i = 0; i < cnt[k]; i++)
+      for (int d = 0; d < desc_dim; d++) (*blk)[(size_t)i * desc_dim + d] = src[k][i].desc[d];
+    const std::shared_ptr<const std::vector<float>> cblk = blk;
     for (int i = 0; i < cnt[k]; i++) {
       const modsgpu_feature& f = src[k][i];
       AffineKeypoint& kp = l[k][i].reproj_kp;
@@ -1037,7 +1042,7 @@ extern "C" int modsgpu_match_features(modsgpu_ctx* ctx, const modsgpu_feature* f
       kp.response = f.response; kp.octave_number = f.octave; kp.sub_type = f.type;
       l[k][i].det_kp = kp;
       l[k][i].id = i; l[k][i].img_id = k; l[k][i].img_reproj_id = f.view; l[k][i].type = f.type;
-      l[k][i].desc.assign(f.desc, f.desc + desc_dim);
+      l[k][i].desc.view(cblk, (size_t)i * desc_dim, (size_t)desc_dim);
     }
   }
   memset(res, 0, sizeof(*res));

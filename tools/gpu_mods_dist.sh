@@ -12,5 +12,7 @@ b = synth.warp_image(a, Ht, noise_seed=5)
 np.save("gpurun_out/mods_a.npy", synth.gray_to_bgr(a)); np.save("gpurun_out/mods_b.npy", synth.gray_to_bgr(b))
 PY
 for n in 1 $N; do
-  /usr/bin/env time -f "N=$n wall %e s" timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29530+n)) -m mods_light_zmq_b200.mods_dist gpurun_out/mods_a.npy gpurun_out/mods_b.npy --min-matches 1000000 --time 2>&1 | grep -E "steps_done|wall|Error|error" | cut -c1-400 | tee gpurun_out/mods_dist_N$n.txt
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29530+n)) -m mods_light_zmq_b200.mods_dist gpurun_out/mods_a.npy gpurun_out/mods_b.npy --min-matches 1000000 --time > gpurun_out/mods_dist_N$n.txt 2> gpurun_out/mods_dist_N$n.err
+  echo "N=$n rc=$?"; grep steps_done gpurun_out/mods_dist_N$n.txt | cut -c1-300 || tail -c 800 gpurun_out/mods_dist_N$n.err
+  [ -s gpurun_out/mods_dist_N$n.txt ] || tail -c 1200 gpurun_out/mods_dist_N$n.err
 done

@@ -3,6 +3,8 @@
 
 void mg_free_nets(modsgpu_ctx* ctx);  // cnn.cu
 
+std::atomic<int> mg_live_contexts{0};
+
 extern "C" const char* modsgpu_version(void) { return "modsgpu 0.1 (sm_100a)"; }
 
 extern "C" int modsgpu_create(int device, modsgpu_ctx** out) {
@@ -30,12 +32,14 @@ extern "C" int modsgpu_create(int device, modsgpu_ctx** out) {
     delete ctx;
     return MODSGPU_ECUDA;
   }
+  mg_live_contexts.fetch_add(1);
   *out = ctx;
   return 0;
 }
 
 extern "C" void modsgpu_destroy(modsgpu_ctx* ctx) {
   if (!ctx) return;
+  mg_live_contexts.fetch_sub(1);
   cudaSetDevice(ctx->device);
   mg_stream_sync(ctx);
   mg_free_nets(ctx);

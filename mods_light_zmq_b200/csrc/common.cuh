@@ -1,6 +1,7 @@
 // common.cuh -- context, workspace buffers and error plumbing shared by the kernels of libmodsgpu.so
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cuda_fp16.h>
 #include <cstdint>
 #include <cstdio>
@@ -127,8 +128,14 @@ void mg_prof_end(modsgpu_ctx* ctx);
 // contexts from several threads (one per pair in flight), often more threads than it has cores (4 cores per GPU on the
 // 8-GPU box), and a spinning cudaStreamSynchronize per thread starves the threads that have launches to issue.
 // MODSGPU_SPIN_SYNC=1 restores the spinning wait (lowest latency for a single context).
+// A process with one or two live contexts keeps the spinning wait (lowest latency: 89 vs 111 ms for the MODS loop of
+// one hard pair); with more contexts than that -- one per pair in flight -- the waits sleep.
+extern std::atomic<int> mg_live_contexts;   // api.cu
+static inline bool mg_sleeping_waits(const modsgpu_ctx* ctx) {
+  return ctx->ev_sync != nullptr && mg_live_contexts.load(std::memory_order_relaxed) > 2;
+}
 static inline cudaError_t mg_stream_sync(modsgpu_ctx* ctx) {
-  if (!ctx->ev_sync) return cudaStreamSynchronize(ctx->stream);
+  if (!mg_sleeping_waits(ctx)) return cudaStreamSynchronize(ctx->stream);
   cudaError_t e = cudaEventRecord(ctx->ev_sync, ctx->stream);
   if (e != cudaSuccess) return e;
   return cudaEventSynchronize(ctx->ev_sync);
@@ -143,7 +150,7 @@ static inline int mg_end(modsgpu_ctx* ctx) {
   // ev1 is the entry point's end marker AND what the host sleeps on (it carries cudaEventBlockingSync unless
   // MODSGPU_SPIN_SYNC=1); the elapsed time is formed only when modsgpu_last_device_ms asks for it
   MG_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-  MG_CUDA(ctx, ctx->ev_sync ? cudaEventSynchronize(ctx->ev1) : cudaStreamSynchronize(ctx->stream));
+  MG_CUDA(ctx, mg_sleeping_waits(ctx) ? cudaEventSynchronize(ctx->ev1) : cudaStreamSynchronize(ctx->stream));
   ctx->last_ms = -1.f;
   return 0;
 }
@@ -163,7 +170,6 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // cudaFuncSetAttribute is per device: a call site keeps one OnceFlags and asks whether this context's device still
 // needs the call.  Contexts of several threads may race here; the attribute call is idempotent, the flag is atomic.
-#include <atomic>
 struct OnceFlags {
   std::atomic<unsigned long long> done{0};
   bool need(int device) {

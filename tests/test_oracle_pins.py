@@ -360,3 +360,14 @@ def test_synthetic_pair_is_deterministic(synth_pair):
     from mods_light_zmq_b200 import synth
     a2 = synth.blob_image()
     assert hashlib.sha1(a.tobytes()).hexdigest() == hashlib.sha1(a2.tobytes()).hexdigest()
+
+
+def test_host_mirror_descvec_semantics(tmp_path):
+    """csrc/host/mods_host.h: AffineRegion::desc keeps the std::vector<float> surface of the reference's descriptor.vec
+    while region copies share one block (tests/cpp/descvec_test.cpp, header only, no GPU)."""
+    import subprocess
+    exe = str(tmp_path / "descvec_test")
+    src = os.path.join(ROOT, "tests", "cpp", "descvec_test.cpp")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), src, "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "descvec ok" in out.stdout, out.stdout + out.stderr

@@ -266,8 +266,31 @@ def oxaff_golden():
     print("oxaff_golden.npz", n)
 
 
+def flann_pins():
+    """The matcher's third-party call: cv::flann::Index with cvflann::LinearIndexParams + knnSearch (matching.cpp:394-415,
+    vector_matcher = linear), taken from the cv2 4.13 wheel's flann_Index(algorithm = FLANN_INDEX_LINEAR).  Byte-valued
+    128-D descriptors with exact duplicates among the train rows and query rows equal to train rows, so that the
+    tie order (equal distances keep train-index order) and zero distances are part of the fixture."""
+    import cv2
+    rng = np.random.RandomState(7)
+    t = rng.randint(0, 256, (700, 128)).astype(np.float32)
+    t[50] = t[10]; t[200] = t[10]; t[699] = t[3]; t[350:360] = t[20]
+    q = rng.randint(0, 256, (90, 128)).astype(np.float32)
+    q[0] = t[10]; q[1] = t[3] + 1; q[2] = t[20]; q[3] = 0; q[4] = 255
+    idx, dist = cv2.flann_Index(t, dict(algorithm=0)).knnSearch(q, 50, params={})
+    # a low-dimensional case with many equal distances (integer lattice points)
+    t2 = np.stack(np.meshgrid(np.arange(12), np.arange(12)), -1).reshape(-1, 2).astype(np.float32)
+    q2 = np.array([[5.5, 5.5], [0, 0], [11, 3], [6, 6]], np.float32)
+    idx2, dist2 = cv2.flann_Index(t2, dict(algorithm=0)).knnSearch(q2, 50, params={})
+    np.savez_compressed(os.path.join(HERE, "flann_pins.npz"), q=q.astype(np.uint8), t=t.astype(np.uint8), idx=idx, dist=dist,
+                        q2=q2, t2=t2, idx2=idx2, dist2=dist2, cv2_version=cv2.__version__)
+    print("flann_pins.npz", idx.shape, idx2.shape)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["cv2", "cnn", "graf", "ransac", "ransacF", "oxaff", "synth"]
+    which = sys.argv[1:] or ["cv2", "cnn", "graf", "ransac", "ransacF", "oxaff", "synth", "flann"]
+    if "flann" in which:
+        flann_pins()
     if "cv2" in which:
         cv2_pins()
     if "cnn" in which:

@@ -371,3 +371,30 @@ def test_host_mirror_descvec_semantics(tmp_path):
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), src, "-o", exe])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
     assert out.returncode == 0 and "descvec ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_oracle_knn_matches_cv2_flann_linear_index():
+    """The matcher's third-party boundary ("parity unpinned at the FLANN boundary"): the oracle's restatement
+    of cvflann::LinearIndex + KNNSimpleResultSet (oracle/mods_oracle.cpp:orc_knn_linear) against cv2 4.13's
+    flann_Index(algorithm = LINEAR).knnSearch -- indices AND float distances, with exact duplicates, zero distances and a
+    lattice case full of equal distances (tests/golden/flann_pins.npz, generated by make_golden.py flann).  The GPU matcher
+    is compared with the same oracle function in test_match_fginn_bit_exact."""
+    from oracle import pyoracle as O
+    z = np.load(os.path.join(GOLD, "flann_pins.npz"))
+    idx, dist = O.knn_linear(z["q"].astype(np.float32), z["t"].astype(np.float32), 50)
+    assert np.array_equal(idx, z["idx"]) and np.array_equal(dist, z["dist"])
+    assert list(idx[0, :3]) == [10, 50, 200] and np.all(dist[0, :3] == 0)      # equal distances keep train-index order
+    idx2, dist2 = O.knn_linear(z["q2"], z["t2"], 50)
+    assert np.array_equal(idx2, z["idx2"]) and np.array_equal(dist2, z["dist2"])
+    try:
+        import cv2
+    except ImportError:
+        return
+    rng = np.random.RandomState(11)                       # live: a fresh case against the installed wheel
+    t = rng.randint(0, 256, (300, 128)).astype(np.float32)
+    t[100:110] = t[5]
+    q = rng.randint(0, 256, (40, 128)).astype(np.float32)
+    q[7] = t[5]
+    ci, cd = cv2.flann_Index(t, dict(algorithm=0)).knnSearch(q, 50, params={})
+    oi, od = O.knn_linear(q, t, 50)
+    assert np.array_equal(ci, oi) and np.array_equal(cd, od)

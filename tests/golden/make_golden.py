@@ -287,8 +287,25 @@ def flann_pins():
     print("flann_pins.npz", idx.shape, idx2.shape)
 
 
+def imencode_pins():
+    """What the daemons receive: DescribeWithZmq PNG-encodes the FLOAT patch column (imagerepresentation.cpp:45);
+    cv::imencode falls back to convertTo(CV_8U) = saturate_cast<uchar>(cvRound(v)): round half to even, clamp to 0..255."""
+    import cv2
+    rng = np.random.RandomState(3)
+    a = rng.uniform(-20, 280, (96, 32)).astype(np.float32)
+    a[0, :8] = [0.5, 1.5, 2.5, 3.5, 254.5, 255.5, -0.5, 127.5]
+    a[1, :4] = [np.float32(2.5) - np.float32(1e-6), np.float32(2.5) + np.float32(1e-6), 255.49999, 256.0]
+    ok, buf = cv2.imencode(".png", a)
+    dec = cv2.imdecode(buf, cv2.IMREAD_UNCHANGED)
+    assert ok and dec.dtype == np.uint8
+    np.savez_compressed(os.path.join(HERE, "imencode_pins.npz"), patches=a, u8=dec, cv2_version=cv2.__version__)
+    print("imencode_pins.npz", dec.shape)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["cv2", "cnn", "graf", "ransac", "ransacF", "oxaff", "synth", "flann"]
+    which = sys.argv[1:] or ["cv2", "cnn", "graf", "ransac", "ransacF", "oxaff", "synth", "flann", "imencode"]
+    if "imencode" in which:
+        imencode_pins()
     if "flann" in which:
         flann_pins()
     if "cv2" in which:

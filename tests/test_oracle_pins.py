@@ -398,3 +398,21 @@ def test_oracle_knn_matches_cv2_flann_linear_index():
     ci, cd = cv2.flann_Index(t, dict(algorithm=0)).knnSearch(q, 50, params={})
     oi, od = O.knn_linear(q, t, 50)
     assert np.array_equal(ci, oi) and np.array_equal(cd, od)
+
+
+def test_oracle_u8_quantisation_matches_cv2_imencode():
+    """DescribeWithZmq hands the daemons a PNG of the float patch column (imagerepresentation.cpp:45): cv::imencode's
+    fallback conversion to 8 bit (round half to even, saturate) against the oracle's quantize_u8, which the sampler
+    kernel's u8 output is compared with bit for bit (tests/golden/imencode_pins.npz; live when the cv2 wheel is there)."""
+    from oracle import pyoracle as O
+    z = np.load(os.path.join(GOLD, "imencode_pins.npz"))
+    assert np.array_equal(O.quantize_u8(z["patches"]), z["u8"])
+    assert list(z["u8"][0, :8]) == [0, 2, 2, 4, 254, 255, 0, 128]
+    try:
+        import cv2
+    except ImportError:
+        return
+    a = np.random.RandomState(5).uniform(-5, 260, (64, 32)).astype(np.float32)
+    a[::7, ::5] = np.floor(a[::7, ::5]) + 0.5
+    ok, buf = cv2.imencode(".png", a)
+    assert ok and np.array_equal(cv2.imdecode(buf, cv2.IMREAD_UNCHANGED), O.quantize_u8(a))

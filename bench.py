@@ -5,9 +5,10 @@ duplicate filter -> LO-RANSAC(H)) on synthetic 1024x768 pairs (~4k keypoints per
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
   N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one image pair through modsgpu_pair_pipeline*.  Pairs are independent, so ranks shard pairs
-(weak scaling: every rank runs K steps on its own pairs); the only collective is one NCCL gather of the
-final correspondences / homographies of all steps, inside the timed region.
+One "step" = one BATCH of PAIRS_PER_STEP (16) independent image pairs through modsgpu_pair_pipeline*; `value`
+counts pairs (steps x 16 x ranks / time).  Pairs are independent, so ranks shard pairs (weak scaling: every
+rank runs K steps on its own pairs); the only collective is one NCCL gather of the final correspondences /
+homographies of all pairs, inside the timed region.
 
 value   whole-job pairs/s with the images already resident in HBM (modsgpu_pair_pipeline_images)
 e2e     the same through the reference-facing call with HOST (pinned) BGR images: H2D of both images and D2H
@@ -15,7 +16,8 @@ e2e     the same through the reference-facing call with HOST (pinned) BGR images
 roofline  dominant kernel by accumulated CUDA-event time over the same K steps (per-launch events recorded
         by the library on its own stream), algorithmic work per launch as defined in DESIGN.md
 cpu_baseline / --impl reference  the CPU path (oracle port of the reference C++ stages, the daemons' torch
-        models on the CPU, the reference's own degensac) on the host cores, on a bounded sample
+        models on the CPU, the reference's own degensac on the pair's own tentatives) on the host cores; every
+        reference step times ONE WHOLE pair of the step's batch (the bounded sample), nothing is extrapolated
 The L2 is flushed (256 MB memset) before every step.
 """
 import argparse
@@ -37,6 +39,7 @@ WORKLOAD = "config3: 1024x768 synthetic pair, Hessian-AffNet-OriNet-HardNet++ + 
 W_IMG, H_IMG = 1024, 768
 N_DISTINCT_PAIRS = 4
 CAPACITY = 2048
+PAIRS_PER_STEP = 16
 
 
 def make_pairs(n, rank):
@@ -93,16 +96,19 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU path
-def cpu_pair(pair, sample_stride, threads):
-    """The reference's CPU path on one pair.  Detection runs on both full images; the per-keypoint stages
-    (sampler + nets) on every `sample_stride`-th keypoint; matching on the sampled descriptors; LO-RANSAC by
-    the reference's degensac.  Returns per-stage seconds and the extrapolated seconds per full pair."""
+def cpu_pair(pair, threads):
+    """The reference's CPU path on ONE WHOLE pair (every keypoint, no sub-sampling): detection + sampler + AffNet +
+    OriNet + HardNet++ per image (the two images concurrently, as mods.cpp:234-251 does with OpenMP tasks), linear
+    FGINN, duplicate filter, and LO-RANSAC(H) by the reference's own degensac (oracle/_ref, exp_ransacHcustom as
+    matching.cpp:731 calls it) on the pair's OWN tentatives.  Returns per-stage seconds, the pair's wall seconds
+    and the counts."""
     import torch
     from oracle import pyoracle as O
     from oracle import cnn_oracle as CN
     torch.set_num_threads(threads)
-    t = {"detect": 0.0, "perkp": 0.0, "match": 0.0, "ransac": 0.0}
+    t = {"detect": 0.0, "perkp": 0.0, "match": 0.0, "dup": 0.0, "ransac": 0.0}
     out = [None, None]
+    t_begin = time.perf_counter()
 
     def one(i):
         bgr = pair[i]
@@ -111,7 +117,7 @@ def cpu_pair(pair, sample_stride, threads):
         h, w = g.shape
         kp = O.detect_hessian(g)
         t1 = time.perf_counter()
-        regs = O.regions_from_keypoints(kp[::sample_stride])
+        regs = O.regions_from_keypoints(kp)
         aff = CN.affnet(O.quantize_u8(O.extract_patches(g, regs)))
         r2, _ = O.affnet_postprocess(regs, aff, w, h)
         ori = CN.orinet(O.quantize_u8(O.extract_patches(g, r2)))
@@ -121,7 +127,6 @@ def cpu_pair(pair, sample_stride, threads):
         t2 = time.perf_counter()
         out[i] = (d, np.c_[r4["x"], r4["y"]], t1 - t0, t2 - t1, len(kp))
 
-    # mods.cpp:234-251: the two images of a pair are processed by two concurrent OpenMP tasks
     ths = [threading.Thread(target=one, args=(i,)) for i in (0, 1)]
     t0 = time.perf_counter()
     for th in ths:
@@ -135,51 +140,53 @@ def cpu_pair(pair, sample_stride, threads):
     t0 = time.perf_counter()
     m = O.match_fginn(out[0][0], out[0][1], out[1][0], out[1][1])
     t["match"] = time.perf_counter() - t0
-    # RANSAC on a tentative set of the size the full pair yields (~250), built from the known homography
-    rng = np.random.RandomState(1)
-    T, n_in = 260, 170
-    H = pair[2]
-    x1 = np.c_[rng.uniform(20, 1000, T), rng.uniform(20, 740, T), np.ones(T)]
-    p = x1 @ H.T
-    x2 = p / p[:, 2:3]
-    x2[:, :2] += rng.normal(0, 0.7, (T, 2))
-    x2[n_in:, :2] = np.c_[rng.uniform(0, 1024, T - n_in), rng.uniform(0, 768, T - n_in)]
     t0 = time.perf_counter()
-    if O.ref_available():
-        O.ref_ransac_H(np.ascontiguousarray(np.c_[x1, x2]), th=16.0)
+    xy1, xy2 = out[0][1][m["qi"]], out[1][1][m["ti"]]
+    keep = O.duplicate_filter(xy1, xy2, m["ratio"], 2.0) if len(m) else np.zeros(0, np.int32)
+    t["dup"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    n_inl = 0
+    if len(keep) >= 8:
+        u = np.ascontiguousarray(np.c_[xy1[keep], np.ones(len(keep)), xy2[keep], np.ones(len(keep))])
+        if not O.ref_available():
+            raise RuntimeError("oracle/_ref/libdegensac_ref.so missing: the CPU arm runs the reference's own degensac")
+        n_inl = int(O.ref_ransac_H(u, th=16.0)["inl"].sum())      # err_threshold 4 px squared, matching.cpp:731
     t["ransac"] = time.perf_counter() - t0
-    s = sample_stride
-    full = t["detect"] + s * t["perkp"] + s * s * t["match"] + t["ransac"]
-    return t, full, len(m)
+    counts = {"keypoints": [out[0][4], out[1][4]], "descriptors": [len(out[0][0]), len(out[1][0])],
+              "tentatives": int(len(m)), "unique_tentatives": int(len(keep)), "inliers": n_inl}
+    return t, time.perf_counter() - t_begin, counts
 
 
 def run_reference(args, rank, world):
+    """The reference arm: the CPU implementation of the path with all host threads; under torchrun rank 0 alone works.
+    Each step times one WHOLE pair (pair k mod 4 of the bench workload) -- the bounded sample of the GPU arm's 16-pair
+    step; value = pairs / measured seconds, no extrapolation."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    pairs = make_pairs(2, 0)
-    # bounded sample per step: every stride-th keypoint, chosen so that K steps end within a few minutes
-    stride = 8 if args.steps <= 24 else (16 if args.steps <= 64 else 32)
-    for _ in range(min(args.warmup, 1)):
-        cpu_pair(pairs[0], stride, threads)
-    secs, parts = [], None
-    t_begin = time.perf_counter()
+    pairs = make_pairs(N_DISTINCT_PAIRS, 0)
+    for k in range(max(min(args.warmup, 2), 1)):
+        cpu_pair(pairs[k % len(pairs)], threads)
+    secs, parts, counts = [], None, None
     for k in range(args.steps):
-        parts, full, _ = cpu_pair(pairs[k % len(pairs)], stride, threads)
-        secs.append(full)
-    wall = time.perf_counter() - t_begin
+        parts, sec, counts = cpu_pair(pairs[k % len(pairs)], threads)
+        secs.append(sec)
     per_pair = float(np.mean(secs))
     value = 1.0 / per_pair
-    sample = ("per step: full Hessian detection of both 1024x768 images + sampler/AffNet/OriNet/HardNet++ on every %d-th "
-              "keypoint + linear FGINN on the sampled descriptors + reference degensac on 260 tentatives; "
-              "pair time = detect + %d*perkp + %d*match + ransac (measured %.2f s of CPU work per step)" %
-              (stride, stride, stride * stride, wall / max(args.steps, 1)))
+    sample = ("each step = ONE whole pair of the 16-pair batch the GPU arm calls a step (full Hessian detection of both "
+              "1024x768 images, every keypoint through sampler + AffNet + OriNet + HardNet++, linear FGINN, duplicate "
+              "filter, the reference's own exp_ransacHcustom on the pair's own tentatives); %d pairs, %.1f s of CPU work, "
+              "pairs/s = pairs / measured seconds" % (len(secs), float(np.sum(secs))))
     line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": per_pair * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": WORKLOAD, "l2": "n/a (CPU)"},
+            "config": {"workload": WORKLOAD, "pairs_per_step": 1, "distinct_pairs": N_DISTINCT_PAIRS, "l2": "n/a (CPU)",
+                       "last_step": counts},
             "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port",
-                             "sample": sample, "stage_seconds_sample": parts},
+                             "sample": sample, "stage_seconds_last_pair": parts,
+                             "note": "kind=port: detector / sampler / matcher are the oracle's C++ restatement, the nets "
+                                     "are the daemons' torch models on the CPU; the LO-RANSAC stage is the reference's own "
+                                     "degensac (oracle/_ref)"},
             "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -228,10 +235,13 @@ def run_gpu(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    results = np.zeros((max(args.steps, 1), 16 + 4 * CAPACITY), np.float64)
+    n_pairs = max(args.steps, 1) * PAIRS_PER_STEP      # pairs of the timed arms (steps x 16 per rank)
+    results = np.zeros((n_pairs, 16 + 4 * CAPACITY), np.float64)
     last = {}
     host_cpu = {"ms": 0.0}
 
+    # k = pair index inside the arm (step = k // PAIRS_PER_STEP); store=False for warm-up / rehearsal passes, whose
+    # pair count is independent of --steps
     def step_value(wk, k, store=True):
         mg = mgs[wk]
         mg.lib.modsgpu_flush_l2(mg.ctx)
@@ -261,8 +271,8 @@ def run_gpu(args, rank, world, local_rank):
         dist.gather(t, lst, dst=0)
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
-        """K steps dealt round-robin to the worker threads; device time = CUDA events on worker 0's stream
+    def timed(fn, steps, store=True):
+        """`steps` PAIRS dealt round-robin to the worker threads; device time = CUDA events on worker 0's stream
         bracketing the whole region (start recorded after all workers are ready, stop after all have joined
         and the gather is done)."""
         errs = []
@@ -272,7 +282,7 @@ def run_gpu(args, rank, world, local_rank):
             try:
                 gate.wait()
                 for k in range(wk, steps, nwk):
-                    fn(wk, k)
+                    fn(wk, k, store)
             except Exception as e:  # noqa: BLE001
                 errs.append(e)
 
@@ -319,19 +329,20 @@ def run_gpu(args, rank, world, local_rank):
         clocks.start()
     # rehearsal of both arms through the same threaded / collective machinery (first use of the NCCL barrier and
     # all-reduce costs hundreds of ms once; it must not land in the first timed arm)
-    timed(step_e2e, 2 * nwk)
-    timed(step_value, 4 * nwk)
+    timed(step_e2e, 2 * nwk, store=False)
+    timed(step_value, 4 * nwk, store=False)
     launches0 = sum(mg.launch_count for mg in mgs)
-    dev_ms, wall_ms = timed(step_value, args.steps)
-    host_cpu_ms_per_step = host_cpu["ms"] / max(args.steps, 1)
+    dev_ms, wall_ms = timed(step_value, n_pairs)
+    host_cpu_ms_per_pair = host_cpu["ms"] / n_pairs
     launches = sum(mg.launch_count for mg in mgs) - launches0
-    e2e_ms, e2e_wall = timed(step_e2e, args.steps)
+    e2e_ms, e2e_wall = timed(step_e2e, n_pairs)
     clk = clocks.stop() if rank == 0 else None
     # ---- per-kernel events over K steps on one worker (separate pass: the timed arms carry no event overhead)
     mg = mgs[0]
     lib, ctx = mg.lib, mg.ctx
     lib.modsgpu_profile_enable(ctx, 1)
-    for k in range(args.steps):
+    n_prof = min(n_pairs, 32)
+    for k in range(n_prof):
         step_value(0, k, False)
     buf = C.create_string_buffer(1 << 16)
     lib.modsgpu_profile_report(ctx, buf, len(buf))
@@ -345,34 +356,35 @@ def run_gpu(args, rank, world, local_rank):
             dist.destroy_process_group()
         return
     lastr = last.get("r")
-    value = world * args.steps / (dev_ms * 1e-3)
-    e2e_value = world * args.steps / (e2e_ms * 1e-3)
+    value = world * n_pairs / (dev_ms * 1e-3)
+    e2e_value = world * n_pairs / (e2e_ms * 1e-3)
     total_kernel_ms = sum(v["ms"] for v in prof.values()) or 1.0
     # "dominant kernel" = the __global__ function (all template instantiations together) with the largest accumulated time
-    # among those with an algorithmic work figure; latency-bound helpers (kind 2) are listed in `kernels` only
+    # among those with an algorithmic work figure; latency-bound helpers (kind 2) are listed in `kernels` only.  The BOUND
+    # of a kernel is the one DESIGN.md section 4 / SURVEY 8(d) assign to it (reported by the library as `kind`: the conv
+    # and distance kernels are tensor-bound and counted in flops against the sustained bf16 peak, the image / patch
+    # kernels are HBM-bound and counted in algorithmic bytes) -- not whichever fraction happens to look larger.
     groups = {}
     for k, v in prof.items():
         if v["kind"] not in ALG:
             continue
-        g = groups.setdefault(k.split("<")[0], {"ms": 0.0, "launches": 0, "flops": 0.0, "bytes": 0.0, "members": []})
+        g = groups.setdefault(k.split("<")[0], {"ms": 0.0, "launches": 0, "flops": 0.0, "bytes": 0.0, "members": [], "kind": v["kind"]})
         g["ms"] += v["ms"]
         g["launches"] += v["launches"]
         g["flops"] += v["work"] if v["kind"] == 1 else 0.0
         g["bytes"] += v["work"] if v["kind"] == 0 else v.get("bytes", 0.0)
         g["members"].append(k)
     top = max(groups, key=lambda k: groups[k]["ms"], default=None)
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+    tc_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    tc_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if "bf16_tflops_sustained" in peaks else "fallback 1400 TFLOP/s"
     roofline = None
     if top:
         g = groups[top]
-        hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        hbm_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
-        tc_peak = peaks.get("bf16_tflops_sustained", 1400.0)
-        tc_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if "bf16_tflops_sustained" in peaks else "fallback 1400 TFLOP/s"
         gbs = g["bytes"] / (g["ms"] * 1e-3) / 1e9
         tfs = g["flops"] / (g["ms"] * 1e-3) / 1e12
-        # the bound is the resource the kernel sits closer to (its layers differ: small-channel layers stream activations,
-        # the wide ones are paced by the MMA pipe); both fractions are reported
-        if g["flops"] > 0 and tfs / tc_peak > gbs / hbm_peak:
+        if g["kind"] == 1:
             bound, achieved, peak, unit, src = "tensor", tfs, tc_peak, "TFLOP/s", tc_src
         else:
             bound, achieved, peak, unit, src = "hbm", gbs, hbm_peak, "GB/s", hbm_src
@@ -392,8 +404,28 @@ def run_gpu(args, rank, world, local_rank):
                     "unit": unit, "frac": achieved / peak, "traffic": traffic, "traffic_of": traffic_of, "peak_source": src,
                     "hbm_gbs": gbs, "hbm_frac": gbs / hbm_peak, "tensor_tflops": tfs, "tensor_frac": tfs / tc_peak,
                     "launches": g["launches"], "avg_us": 1e3 * g["ms"] / max(g["launches"], 1),
-                    "share_of_kernel_time": g["ms"] / total_kernel_ms}
-    kernels = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
+                    "share_of_kernel_time": g["ms"] / total_kernel_ms,
+                    "pairs_profiled": n_prof}
+    # whole-stage figures: the CNN stage in flops over ALL kernels of the nets (conv1, tcgen05 convs, heads),
+    # the detector and the sampler in their algorithmic bytes, each against the measured peak of its bound
+    def stage(prefixes, kind):
+        ms = sum(v["ms"] for k, v in prof.items() if k.startswith(prefixes))
+        if kind == 1:
+            work = sum(v["work"] for k, v in prof.items() if k.startswith(prefixes) and v["kind"] == 1)
+            return {"ms_per_pair": ms / n_prof, "gflop_per_pair": work / n_prof / 1e9,
+                    "tflops": work / (ms * 1e-3) / 1e12 if ms > 0 else None,
+                    "frac_of_tensor_peak": work / (ms * 1e-3) / 1e12 / tc_peak if ms > 0 else None}
+        work = sum((v["work"] if v["kind"] == 0 else v.get("bytes", 0.0)) for k, v in prof.items() if k.startswith(prefixes))
+        return {"ms_per_pair": ms / n_prof, "mb_per_pair": work / n_prof / 1e6,
+                "gbs": work / (ms * 1e-3) / 1e9 if ms > 0 else None,
+                "frac_of_hbm_peak": work / (ms * 1e-3) / 1e9 / hbm_peak if ms > 0 else None}
+    stages = {"cnn": stage(("k_conv", "k_head", "k_trunk", "k_patch_prep"), 1),
+              "detect": stage(("k_gray", "k_blur", "k_response", "k_half", "k_nms", "k_resolve", "k_rank", "k_det", "k_pyr"), 0),
+              "sampler": stage(("k_sample", "k_large"), 0),
+              "match": stage(("k_pack_desc", "k_dist", "k_select", "k_dup"), 1),
+              "ransac": {"ms_per_pair": sum(v["ms"] for k, v in prof.items() if k.startswith(("k_rs", "k_rf"))) / n_prof},
+              "all_kernels_ms_per_pair": total_kernel_ms / n_prof}
+    kernels = {k: {"ms_per_pair": v["ms"] / n_prof, "launches_per_pair": v["launches"] / n_prof,
                    "share": v["ms"] / total_kernel_ms,
                    "achieved": (v["work"] / (v["ms"] * 1e-3) / ALG[v["kind"]][2]) if v["kind"] in ALG and v["ms"] > 0 else None,
                    "unit": ALG[v["kind"]][1] if v["kind"] in ALG else "latency-bound",
@@ -401,20 +433,20 @@ def run_gpu(args, rank, world, local_rank):
                for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        # bounded sample of the same workload: WHOLE pairs (every keypoint, no extrapolation) until >= 12 s of CPU work
-        # have been timed, at most 6 pairs (a pair takes ~4 s on the 16-core box)
+        # bounded sample of the same workload: WHOLE pairs (every keypoint, the pair's own tentatives, no extrapolation)
+        # until >= 12 s of CPU work have been timed, at most 6 pairs (a pair takes ~4 s on the 16-core box)
         threads = os.cpu_count() or 1
-        cpu_pair(pairs[0], 16, threads)          # warm-up (library loads, torch thread pool)
+        cpu_pair(pairs[0], threads)          # warm-up (library loads, torch thread pool)
         t0 = time.perf_counter()
-        fulls, parts = [], None
+        fulls, parts, counts = [], None, None
         while len(fulls) < 6 and (time.perf_counter() - t0 < 12.0 or not fulls):
-            parts, full, _ = cpu_pair(pairs[len(fulls) % len(pairs)], 1, threads)
+            parts, full, counts = cpu_pair(pairs[len(fulls) % len(pairs)], threads)
             fulls.append(full)
         cpu = {"value": 1.0 / float(np.mean(fulls)), "unit": "pairs/s", "cores": threads, "kind": "port",
                "sample": "%d whole pairs of the bench workload (full detection, every keypoint through sampler + AffNet + "
-                         "OriNet + HardNet++, linear FGINN, reference degensac on 260 tentatives); %.1f s of CPU work"
-                         % (len(fulls), time.perf_counter() - t0),
-               "stage_seconds_sample": parts}
+                         "OriNet + HardNet++, linear FGINN, duplicate filter, the reference's own degensac on the pair's own "
+                         "tentatives); %.1f s of CPU work" % (len(fulls), time.perf_counter() - t0),
+               "stage_seconds_last_pair": parts, "last_pair": counts}
     h2d = 2 * W_IMG * H_IMG * 3
     d2h = 4 * 8 * int(lastr["inliers"]) + 9 * 8 + 9 * 4 if lastr else 0
     line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
@@ -422,18 +454,18 @@ def run_gpu(args, rank, world, local_rank):
             "scaling": "weak", "vs_baseline": None,
             "dtype": "f16 (nets: fp16 operands, fp32 accumulate); f32 detector/sampler; f64 RANSAC",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pairs_per_step": 1, "distinct_pairs": N_DISTINCT_PAIRS,
+            "config": {"workload": WORKLOAD, "pairs_per_step": PAIRS_PER_STEP, "distinct_pairs": N_DISTINCT_PAIRS,
                        "workers_per_gpu": nwk,
-                       "l2": "flushed before every step (256 MB memset on the pipeline stream)",
+                       "l2": "flushed before every pair (256 MB memset on the pipeline stream)",
                        "parallelism": ("pairs sharded across %d ranks; one NCCL gather of the verified correspondences" % world) if world > 1 else "single GPU",
-                       "last_step": {k: lastr[k] for k in ("keypoints", "regions", "descriptors", "tentatives", "unique_tentatives", "inliers")} if lastr else None},
-            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / args.steps,
-                    "note": "h2d/d2h count the API-level buffers (two BGR images in, verified correspondences + H out); "
-                            "the seam-by-seam host round trips of the reference interface are inside the timed region too"},
+                       "last_pair": {k: lastr[k] for k in ("keypoints", "regions", "descriptors", "tentatives", "unique_tentatives", "inliers")} if lastr else None},
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d * PAIRS_PER_STEP,
+                    "d2h_bytes_per_step": d2h * PAIRS_PER_STEP, "ms_per_step": e2e_ms / args.steps,
+                    "note": "h2d/d2h count the API-level buffers of the 16 pairs of a step (two BGR images in, verified "
+                            "correspondences + H out per pair)"},
             "gpu_launches": launches, "wall_ms_per_step": wall_ms / args.steps,
-            "host_cpu_ms_per_step": host_cpu_ms_per_step, "host_cores": os.cpu_count(),
-            "roofline": roofline, "kernels": kernels, "clocks": clk}
+            "host_cpu_ms_per_pair": host_cpu_ms_per_pair, "host_cores": os.cpu_count(),
+            "roofline": roofline, "stages": stages, "kernels": kernels, "clocks": clk}
     if cpu:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
@@ -447,8 +479,8 @@ def run_gpu(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=192)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workers", type=int, default=int(os.environ.get("MODSGPU_BENCH_WORKERS", "0")),

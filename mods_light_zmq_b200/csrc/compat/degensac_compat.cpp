@@ -69,6 +69,10 @@ Score exp_ransacHcustom(double* u, int len, double th, double conf, int max_sam,
   Score s = {0, 0};
   if (resids) *resids = (double*)malloc(sizeof(double) * (size_t)(len > 0 ? len : 1));
   if (data_out) data_out[0] = data_out[1] = data_out[2] = 0;
+  // the caller (matching.cpp:694-760) reads H and inl[0..len) unconditionally: every failure leaves an EMPTY result
+  if (H) memset(H, 0, 9 * sizeof(double));
+  if (inl && len > 0) memset(inl, 0, (size_t)len);
+  if (resids && *resids) memset(*resids, 0, sizeof(double) * (size_t)(len > 0 ? len : 1));
   modsgpu_ctx* ctx = ctx_locked();
   if (!ctx || !u || !H || !inl || len <= 0) return s;
   modsgpu_ransac_params p;
@@ -88,11 +92,15 @@ Score exp_ransacHcustom(double* u, int len, double th, double conf, int max_sam,
 int exp_ransacFcustom(double* u, int len, double th, double conf, int max_sam, double* F, unsigned char* inl,
                       int* data_out, int do_lo, unsigned inlLimit, double** resids, double* H_best, int* Ih,
                       exFDsPtr, FDsPtr, int doSymCheck) {
-  (void)do_lo; (void)inlLimit; (void)H_best;
+  (void)do_lo; (void)inlLimit;
   std::lock_guard<std::mutex> lk(g_mu);
   if (resids) *resids = (double*)malloc(sizeof(double) * (size_t)(len > 0 ? len : 1));
   if (data_out) data_out[0] = data_out[1] = 0;
   if (Ih) *Ih = 0;
+  if (F) memset(F, 0, 9 * sizeof(double));
+  if (H_best) memset(H_best, 0, 9 * sizeof(double));
+  if (inl && len > 0) memset(inl, 0, (size_t)len);
+  if (resids && *resids) memset(*resids, 0, sizeof(double) * (size_t)(len > 0 ? len : 1));
   modsgpu_ctx* ctx = ctx_locked();
   if (!ctx || !u || !F || !inl || len <= 0) return 0;
   modsgpu_ransac_params p;

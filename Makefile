@@ -8,7 +8,7 @@ NVFLAGS = $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-ffp-contract=off -I
 # detect.cu / sampler.cu are the bit-exact integer/float paths: no FMA contraction
 EXACT = --fmad=false
 
-OBJS = $(OBJ)/api.o $(OBJ)/detect.o $(OBJ)/sampler.o $(OBJ)/cnn.o $(OBJ)/match.o $(OBJ)/ransac.o $(OBJ)/ransac_f.o $(OBJ)/synth.o $(OBJ)/classic.o $(OBJ)/npz.o $(OBJ)/mods_host.o
+OBJS = $(OBJ)/api.o $(OBJ)/detect.o $(OBJ)/sampler.o $(OBJ)/cnn.o $(OBJ)/match.o $(OBJ)/ransac.o $(OBJ)/ransac_f.o $(OBJ)/synth.o $(OBJ)/classic.o $(OBJ)/chain.o $(OBJ)/npz.o $(OBJ)/mods_host.o
 
 all: $(PKG)/libmodsgpu.so $(PKG)/libmodsgpu_degensac.so oracle
 
@@ -22,6 +22,9 @@ $(OBJ)/ransac.o: $(SRC)/ransac.cu $(SRC)/ransac_common.cuh $(SRC)/ransac_h.cuh $
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVFLAGS) $(EXACT) -c $< -o $@
 $(OBJ)/synth.o: $(SRC)/synth.cu $(SRC)/common.cuh include/modsgpu.h
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) $(EXACT) -c $< -o $@
+$(OBJ)/chain.o: $(SRC)/chain.cu $(SRC)/common.cuh include/modsgpu.h
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVFLAGS) $(EXACT) -c $< -o $@
 $(OBJ)/classic.o: $(SRC)/classic.cu $(SRC)/common.cuh include/modsgpu.h

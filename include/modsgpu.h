@@ -218,6 +218,31 @@ int  modsgpu_ransac_H(modsgpu_ctx* ctx, const double* u, int T, const modsgpu_ra
 int  modsgpu_ransac_F(modsgpu_ctx* ctx, const double* u, int T, const modsgpu_ransac_params* p,
                       double* F, unsigned char* inl, modsgpu_ransac_result* res);
 
+/* ---- one VIEW from pixels to described regions on the device (the per-view body of
+ *      ImageRepresentation::SynthDetectDescribeKeypoints, imagerepresentation.cpp:704-1006: DetectAffineRegions :739,
+ *      DescribeWithZmq(AffNet) + rectify / eigen-ratio / frame tests :797-845, ReprojectRegionsAndRemoveTouchBoundary :868,
+ *      DescribeWithZmq(OriNet) + rotation :876-899, ReprojectRegions :951, DescribeWithZmq(desc) :992-1006).
+ *      Same results as modsgpu_detect + 3 x modsgpu_describe with the host arithmetic in between, but the region list
+ *      never leaves the device between the stages: two host synchronisations per view instead of four, no host-side
+ *      sampler preparation.  H: 9 doubles row-major original -> view (NULL = identity view); orig_w/h: the ORIGINAL image.
+ *      *regions: n rows, *desc: n x 128 floats holding integers 0..255; both malloc()ed, release with modsgpu_free().
+ *      counts (may be NULL): [0] raw keypoints, [1] regions after AffNet's tests, [2] described regions. ------------- */
+typedef struct {
+  modsgpu_region det;       /* det_kp: view coordinates (structures.hpp:218-229)   */
+  modsgpu_region reproj;    /* reproj_kp: original image (ReprojectByH)            */
+  double response;
+  int    octave, type;
+} modsgpu_view_region;
+int  modsgpu_describe_view(modsgpu_ctx* ctx, const modsgpu_image* view, const double* H, int orig_w, int orig_h,
+                           const modsgpu_pyr_params* p, double mrSize, int patchSize, modsgpu_view_region** regions,
+                           float** desc, int* n, int* counts);
+/* test-only: the two device post-processing steps of the chain on caller-supplied net outputs (survivors, order kept) */
+int  modsgpu_debug_affnet_post(modsgpu_ctx* ctx, const modsgpu_view_region* regs, const float* aff, int n, int w, int h,
+                               int orig_w, int orig_h, double mrSize, const double* H, modsgpu_view_region* out,
+                               int* n_affine, int* n_out);
+int  modsgpu_debug_orinet_post(modsgpu_ctx* ctx, const modsgpu_view_region* regs, const float* ori, int n, int orig_w,
+                               int orig_h, const double* H, modsgpu_view_region* out, int* n_out);
+
 /* ---- whole pair (what one iteration of mods.cpp:202-356 does for the deep configuration
  *      config_aff_ori_desc_zeromq.ini + iters_HessianZMQ.ini, vector_matcher = linear):
  *      SynthDetectDescribeKeypoints x 2 -> MatchFlannFGINN -> DuplicateFiltering -> LORANSACFiltering.

@@ -22,6 +22,8 @@ MATCH_DTYPE = np.dtype([("qi", "i4"), ("ti", "i4"), ("tj_bad", "i4"), ("d1", "f4
 FEATURE_DTYPE = np.dtype([("x", "f8"), ("y", "f8"), ("s", "f8"), ("a11", "f8"), ("a12", "f8"), ("a21", "f8"), ("a22", "f8"),
                           ("response", "f8"), ("octave", "i4"), ("type", "i4"), ("view", "i4"), ("_pad", "i4"),
                           ("desc", "f4", (128,))])
+_R7 = [("x", "f8"), ("y", "f8"), ("s", "f8"), ("a11", "f8"), ("a12", "f8"), ("a21", "f8"), ("a22", "f8")]
+VIEW_REGION_DTYPE = np.dtype([("det", _R7), ("reproj", _R7), ("response", "f8"), ("octave", "i4"), ("type", "i4")])
 VIEW_DTYPE = np.dtype([("tilt", "f8"), ("phi", "f8"), ("zoom", "f8"), ("InitSigma", "f8"), ("doBlur", "i4"), ("_pad", "i4")])
 
 AFFNET, ORINET, HARDNET = 0, 1, 2
@@ -325,6 +327,54 @@ class ModsGpu:
         self._check(self.lib.modsgpu_extract_patches_f32(self.ctx, img.handle, _p(regs), len(regs), C.c_double(mr_size),
                                                          patch_size, _p(out)))
         return out[:len(regs)]
+
+    # ---- one view on the device: detect -> AffNet -> OriNet -> HardNet++ with the region list resident (chain.cu)
+    def describe_view(self, img, H=None, orig_w=None, orig_h=None, params=None, mrSize=5.1962, patchSize=32):
+        """modsgpu_describe_view.  Returns (regions [VIEW_REGION_DTYPE], desc [n,128] float32, counts [3])."""
+        p = params or self.default_params()
+        rows, desc, n = C.c_void_p(), C.c_void_p(), C.c_int()
+        counts = (C.c_int * 3)()
+        Hp = None if H is None else _p(np.ascontiguousarray(H, np.float64))
+        self._check(self.lib.modsgpu_describe_view(self.ctx, img.handle, Hp, int(orig_w or img.w), int(orig_h or img.h), C.byref(p),
+                                                   C.c_double(mrSize), int(patchSize), C.byref(rows), C.byref(desc), C.byref(n), counts))
+        try:
+            m = n.value
+            if m == 0:
+                return np.zeros(0, VIEW_REGION_DTYPE), np.zeros((0, 128), np.float32), list(counts)
+            r = np.frombuffer((C.c_char * (m * VIEW_REGION_DTYPE.itemsize)).from_address(rows.value), VIEW_REGION_DTYPE).copy()
+            d = np.frombuffer((C.c_char * (m * 512)).from_address(desc.value), np.float32).reshape(m, 128).copy()
+            return r, d, list(counts)
+        finally:
+            self.lib.modsgpu_free(rows)
+            self.lib.modsgpu_free(desc)
+
+    def default_params(self):
+        p = PyrParams()
+        self.lib.modsgpu_default_pyr_params(C.byref(p))
+        return p
+
+    def debug_affnet_post(self, regs, aff, w, h, orig_w, orig_h, mrSize=5.1962, H=None):
+        """the chain's AffNet post-processing kernel on caller-supplied net outputs: (survivors, n_affine)"""
+        rows = np.zeros(len(regs), VIEW_REGION_DTYPE)
+        for f in REGION_DTYPE.names:
+            rows["det"][f] = regs[f]
+        aff = np.ascontiguousarray(aff, np.float32)
+        out = np.zeros(max(len(regs), 1), VIEW_REGION_DTYPE)
+        na, no = C.c_int(), C.c_int()
+        Hp = None if H is None else _p(np.ascontiguousarray(H, np.float64))
+        self._check(self.lib.modsgpu_debug_affnet_post(self.ctx, _p(rows), _p(aff), len(rows), int(w), int(h), int(orig_w), int(orig_h),
+                                                       C.c_double(mrSize), Hp, _p(out), C.byref(na), C.byref(no)))
+        return out[:no.value].copy(), na.value
+
+    def debug_orinet_post(self, rows, ori, orig_w, orig_h, H=None):
+        rows = np.ascontiguousarray(rows, VIEW_REGION_DTYPE)
+        ori = np.ascontiguousarray(ori, np.float32)
+        out = np.zeros(max(len(rows), 1), VIEW_REGION_DTYPE)
+        no = C.c_int()
+        Hp = None if H is None else _p(np.ascontiguousarray(H, np.float64))
+        self._check(self.lib.modsgpu_debug_orinet_post(self.ctx, _p(rows), _p(ori), len(rows), int(orig_w), int(orig_h), Hp, _p(out),
+                                                       C.byref(no)))
+        return out[:no.value].copy()
 
     # ---- one image -> described regions; OxAff writer (extract_features_batch)
     def extract_features(self, img):

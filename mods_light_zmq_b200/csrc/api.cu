@@ -46,7 +46,7 @@ extern "C" void modsgpu_destroy(modsgpu_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->det_pyr, &ctx->det_cand, &ctx->det_map, &ctx->det_out, &ctx->det_misc, &ctx->det_aff, &ctx->io_a, &ctx->io_b,
                     &ctx->io_c, &ctx->smp_regs, &ctx->smp_meta, &ctx->smp_taps, &ctx->smp_scratch, &ctx->smp_out,
                     &ctx->cnn_act0, &ctx->cnn_act1, &ctx->cnn_out, &ctx->mt_q, &ctx->mt_t, &ctx->mt_d, &ctx->mt_aux,
-                    &ctx->mt_out, &ctx->rs_buf};
+                    &ctx->mt_out, &ctx->rs_buf, &ctx->cnn_stats, &ctx->smp_prof, &ctx->smp_taptab, &ctx->chain_a, &ctx->chain_b, &ctx->chain_misc};
   for (DevBuf* b : bufs) b->release();
   ctx->h_stage.release();
   ctx->h_stage2.release();
@@ -111,7 +111,10 @@ static void prof_collect(modsgpu_ctx* ctx) {
 extern "C" int modsgpu_profile_enable(modsgpu_ctx* ctx, int on) {
   if (!ctx) return MODSGPU_EINVAL;
   prof_collect(ctx);
-  if (on) ctx->prof.agg.clear();
+  if (on) {
+    ctx->prof.agg.clear();
+    if (ctx->smp_prof.p) cudaMemsetAsync(ctx->smp_prof.p, 0, 64, ctx->stream);
+  }
   ctx->prof.on = on != 0;
   return 0;
 }
@@ -119,6 +122,18 @@ extern "C" int modsgpu_profile_enable(modsgpu_ctx* ctx, int on) {
 extern "C" int modsgpu_profile_report(modsgpu_ctx* ctx, char* buf, int cap) {
   if (!ctx) return MODSGPU_EINVAL;
   prof_collect(ctx);
+  if (ctx->smp_prof.p) {     // sampler launches prepared on the device: their algorithmic bytes were summed there (sampler.cu)
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    static const char* names[6] = {"k_sample_small", "k_sample_a<R<=40>", "k_sample_a<R<=65>", "k_sample_b<R<=100>", "k_sample_b<R<=160>",
+                                   "k_large_resample"};
+    if (cudaMemcpy(acc, ctx->smp_prof.p, sizeof(acc), cudaMemcpyDeviceToHost) == cudaSuccess) {
+      for (int c = 0; c < 6; c++) {
+        auto it = ctx->prof.agg.find(names[c]);
+        if (it != ctx->prof.agg.end() && acc[c] > 0) it->second.work += acc[c];
+      }
+      cudaMemset(ctx->smp_prof.p, 0, sizeof(acc));
+    }
+  }
   std::string s = "{";
   bool first = true;
   for (auto& kv : ctx->prof.agg) {

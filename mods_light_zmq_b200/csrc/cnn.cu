@@ -74,11 +74,21 @@ __device__ __forceinline__ uint32_t relu_pack_h2(float lo, float hi) {
 // -> block reduction -> fp64 section on one thread -> 3 barriers were exposed in front of every patch and the issue slots
 // were 56 % busy, profiles/r01_ncu_full_k_conv1_v5.txt.)
 // =================================================================================================
+// Patch count of a launch whose exact size only the device knows (the region lists between the net passes are compacted
+// on the device, csrc/chain.cu): the host passes its upper bound `np`, the kernel clamps it to the live count of this
+// chunk.  cnt_dev == nullptr: np is exact.
+__device__ __forceinline__ int live_patches(int np, const int* __restrict__ cnt_dev, int cnt_base) {
+  if (cnt_dev == nullptr) return np;
+  const int live = *cnt_dev - cnt_base;
+  return live < 0 ? 0 : (live < np ? live : np);
+}
+
 constexpr int C1_PW = 40;   // padded row: pixel x lives at column x + 4 (16-byte aligned float4 stores), halo at 3 and 36
 template <int C1>
 __global__ void __launch_bounds__(160, 3)
 k_conv1(const uint8_t* __restrict__ patches, int np, const float* __restrict__ w, const float* __restrict__ b,
-        __half* __restrict__ out, size_t out_slots) {
+        __half* __restrict__ out, size_t out_slots, const int* __restrict__ cnt_dev, int cnt_base) {
+  np = live_patches(np, cnt_dev, cnt_base);
   __shared__ __align__(16) float P[2][34][C1_PW];
   __shared__ __align__(16) float bs[C1];
   __shared__ uint64_t bars[4];            // full[2], empty[2]
@@ -205,8 +215,12 @@ template <int CIN, int COUT_T, int NSPLIT, int S, int NGRP, int OUT_MODE>
 __global__ void __launch_bounds__(192, 1)
 k_conv_umma(const __half* __restrict__ in, size_t in_slots, const __half* __restrict__ wts,
             const float* __restrict__ bias, __half* __restrict__ out, size_t out_slots, int np, int ntiles,
-            int patch_base, int contig, int nst) {
+            int patch_base, int contig, int nst, const int* __restrict__ cnt_dev, int cnt_base) {
   using Cfg = ConvCfg<CIN, COUT_T, NSPLIT, S, NGRP, OUT_MODE>;
+  if (cnt_dev != nullptr) {
+    np = live_patches(np, cnt_dev, cnt_base);
+    ntiles = (np * Cfg::PP + 127) / 128;
+  }
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* w_s = smem;
   // M tiles of this CTA.  contig: one balanced run of consecutive tiles (the halo rows a tile shares with its predecessor
@@ -647,7 +661,8 @@ constexpr int HG_KSPLIT = 8, HG_NKB = 64;   // 64 K blocks of 128, 8 per CTA
 // part[ks][m*128 + row][128]; k_head_finish adds the partials in a fixed order (deterministic).
 __global__ void __launch_bounds__(192, 1)
 k_head_gemm(const __half* __restrict__ act, size_t slots, const __half* __restrict__ wts,
-            float* __restrict__ part, int m_pad) {
+            float* __restrict__ part, int m_pad, const int* __restrict__ cnt_dev) {
+  if (cnt_dev != nullptr && (int)blockIdx.x * 128 >= *cnt_dev) return;     // whole M tile beyond the live patches
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + HG_STAGES * HG_STAGE_BYTES);
   uint64_t* full = bars;                 // [3]
@@ -721,7 +736,8 @@ k_head_gemm(const __half* __restrict__ act, size_t slots, const __half* __restri
 // one warp per patch: sum of the K-split partials + folded BN bias -> L2Norm (desc_server.py:49-52) ->
 // uint8(clip(210*(d+0.45),0,255)) as float (desc_server.py:42)
 __global__ void k_head_finish(const float* __restrict__ part, int m_pad, const float* __restrict__ bias,
-                              float* __restrict__ out, int np) {
+                              float* __restrict__ out, int np, const int* __restrict__ cnt_dev) {
+  np = live_patches(np, cnt_dev, 0);
   const int patch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (patch >= np) return;
   float4 acc = *reinterpret_cast<const float4*>(bias + lane * 4);
@@ -769,7 +785,9 @@ __device__ __forceinline__ void load8(const __half* p, float* f) {
 template <int NOUT, bool ORI, int HEAD_PB, int NW>
 __global__ void __launch_bounds__(NW * 32)
 k_head_small(const __half* __restrict__ act, size_t slots, const float* __restrict__ w, const float* __restrict__ b,
-             float* __restrict__ out, int np) {
+             float* __restrict__ out, int np, const int* __restrict__ cnt_dev, int cnt_base) {
+  np = live_patches(np, cnt_dev, cnt_base);
+  if (np <= 0) return;
   extern __shared__ float ws[];   // NOUT * 8 * 512
   // `w` already has the shared-memory layout (modsgpu_load_weights): a straight 16-byte copy
   for (int i = threadIdx.x; i < NOUT * 1024; i += blockDim.x) reinterpret_cast<float4*>(ws)[i] = __ldg(reinterpret_cast<const float4*>(w) + i);
@@ -967,7 +985,7 @@ int cnn_chunk_cap() {
 
 template <int CIN, int COUT_T, int NSPLIT, int S, int NGRP, int OUT_MODE>
 int launch_conv(modsgpu_ctx* ctx, const __half* in, size_t in_slots, const ConvW& w, __half* out, size_t out_slots, int np,
-                int patch_base = 0) {
+                int patch_base, const int* cnt_dev) {
   using Cfg = ConvCfg<CIN, COUT_T, NSPLIT, S, NGRP, OUT_MODE>;
   auto kern = k_conv_umma<CIN, COUT_T, NSPLIT, S, NGRP, OUT_MODE>;
   static OnceFlags attr;
@@ -988,7 +1006,8 @@ int launch_conv(modsgpu_ctx* ctx, const __half* in, size_t in_slots, const ConvW
   static const int stage_cap = [] { const char* e = getenv("MODSGPU_CONV_STAGES"); return e ? std::max(2, atoi(e)) : 64; }();
   const int nst = std::min(Cfg::NST, stage_cap);
   const int smem_bytes = Cfg::W_BYTES + nst * Cfg::A_BYTES + 256;
-  kern<<<grid, 192, smem_bytes, ctx->stream>>>(in, in_slots, w.w, w.b, out, out_slots, np, ntiles, patch_base, contig, nst);
+  kern<<<grid, 192, smem_bytes, ctx->stream>>>(in, in_slots, w.w, w.b, out, out_slots, np, ntiles, patch_base, contig, nst,
+                                               cnt_dev, patch_base);
   MG_LAUNCHED(ctx);
   return 0;
 }
@@ -1146,7 +1165,8 @@ extern "C" int modsgpu_load_weights(modsgpu_ctx* ctx, modsgpu_net net, const cha
 }
 
 // Enqueue the forward pass of `net` on n device-resident 32x32 u8 patches; d_out: n x out_dim floats.
-int mg_net_forward_enqueue(modsgpu_ctx* ctx, modsgpu_net net, const uint8_t* d_patches, int n, float* d_out) {
+// cnt_dev (optional, device): the live patch count when n is only the host's upper bound (chain.cu).
+int mg_net_forward_enqueue(modsgpu_ctx* ctx, modsgpu_net net, const uint8_t* d_patches, int n, float* d_out, const int* cnt_dev) {
   NetWeights* nw = ctx->nets[net];
   if (!nw) MG_FAIL(ctx, MODSGPU_ESTATE, "modsgpu_load_weights has not been called for this net");
   // HardNet: conv6 of every chunk lands in one [8192/8 planes][m_pad patches] operand; the 8x8 head then runs
@@ -1173,28 +1193,28 @@ int mg_net_forward_enqueue(modsgpu_ctx* ctx, modsgpu_net net, const uint8_t* d_p
         if ((rc = launch_conv12<32, 2>(ctx, pin, nw->conv[0], nw->act[1], nw->slots[1], np))) return rc;
       } else {
         MG_PROF2(ctx, "k_conv1<32>", 1, 2.0 * np * 1024 * 9 * 32, (double)np * (1024.0 + 1024.0 * 32 * 2));
-        k_conv1<32><<<std::min(np, 3 * ctx->num_sms), 160, 0, ctx->stream>>>(pin, np, nw->c1_w, nw->c1_b, nw->act[0], nw->slots[0]);
+        k_conv1<32><<<std::min(np, 3 * ctx->num_sms), 160, 0, ctx->stream>>>(pin, np, nw->c1_w, nw->c1_b, nw->act[0], nw->slots[0], cnt_dev, p0);
         MG_LAUNCHED(ctx);
-        if ((rc = launch_conv<32, 32, 1, 32, 1, OUT_PARITY>(ctx, nw->act[0], nw->slots[0], nw->conv[0], nw->act[1], nw->slots[1], np))) return rc;
+        if ((rc = launch_conv<32, 32, 1, 32, 1, OUT_PARITY>(ctx, nw->act[0], nw->slots[0], nw->conv[0], nw->act[1], nw->slots[1], np, p0, cnt_dev))) return rc;
       }
-      if ((rc = launch_conv<32, 64, 1, 16, 4, OUT_NORMAL>(ctx, nw->act[1], nw->slots[1], nw->conv[1], nw->act[2], nw->slots[2], np))) return rc;
-      if ((rc = launch_conv<64, 64, 1, 16, 1, OUT_PARITY>(ctx, nw->act[2], nw->slots[2], nw->conv[2], nw->act[3], nw->slots[3], np))) return rc;
-      if ((rc = launch_conv<64, 64, 2, 8, 4, OUT_NORMAL>(ctx, nw->act[3], nw->slots[3], nw->conv[3], nw->act[4], nw->slots[4], np))) return rc;
-      if ((rc = launch_conv<128, 64, 2, 8, 1, OUT_GEMM>(ctx, nw->act[4], nw->slots[4], nw->conv[4], act6all, (size_t)m_pad, np, p0))) return rc;
+      if ((rc = launch_conv<32, 64, 1, 16, 4, OUT_NORMAL>(ctx, nw->act[1], nw->slots[1], nw->conv[1], nw->act[2], nw->slots[2], np, p0, cnt_dev))) return rc;
+      if ((rc = launch_conv<64, 64, 1, 16, 1, OUT_PARITY>(ctx, nw->act[2], nw->slots[2], nw->conv[2], nw->act[3], nw->slots[3], np, p0, cnt_dev))) return rc;
+      if ((rc = launch_conv<64, 64, 2, 8, 4, OUT_NORMAL>(ctx, nw->act[3], nw->slots[3], nw->conv[3], nw->act[4], nw->slots[4], np, p0, cnt_dev))) return rc;
+      if ((rc = launch_conv<128, 64, 2, 8, 1, OUT_GEMM>(ctx, nw->act[4], nw->slots[4], nw->conv[4], act6all, (size_t)m_pad, np, p0, cnt_dev))) return rc;
     } else {
       if (nw->fused12) {
         if ((rc = (net == MODSGPU_AFFNET ? launch_conv12<16, 0>(ctx, pin, nw->conv[0], nw->act[1], nw->slots[1], np)
                                          : launch_conv12<16, 1>(ctx, pin, nw->conv[0], nw->act[1], nw->slots[1], np)))) return rc;
       } else {
         MG_PROF2(ctx, "k_conv1<16>", 1, 2.0 * np * 1024 * 9 * 16, (double)np * (1024.0 + 1024.0 * 16 * 2));
-        k_conv1<16><<<std::min(np, 3 * ctx->num_sms), 160, 0, ctx->stream>>>(pin, np, nw->c1_w, nw->c1_b, nw->act[0], nw->slots[0]);
+        k_conv1<16><<<std::min(np, 3 * ctx->num_sms), 160, 0, ctx->stream>>>(pin, np, nw->c1_w, nw->c1_b, nw->act[0], nw->slots[0], cnt_dev, p0);
         MG_LAUNCHED(ctx);
-        if ((rc = launch_conv<16, 16, 1, 32, 1, OUT_PARITY>(ctx, nw->act[0], nw->slots[0], nw->conv[0], nw->act[1], nw->slots[1], np))) return rc;
+        if ((rc = launch_conv<16, 16, 1, 32, 1, OUT_PARITY>(ctx, nw->act[0], nw->slots[0], nw->conv[0], nw->act[1], nw->slots[1], np, p0, cnt_dev))) return rc;
       }
-      if ((rc = launch_conv<16, 32, 1, 16, 4, OUT_NORMAL>(ctx, nw->act[1], nw->slots[1], nw->conv[1], nw->act[2], nw->slots[2], np))) return rc;
-      if ((rc = launch_conv<32, 32, 1, 16, 1, OUT_PARITY>(ctx, nw->act[2], nw->slots[2], nw->conv[2], nw->act[3], nw->slots[3], np))) return rc;
-      if ((rc = launch_conv<32, 64, 1, 8, 4, OUT_NORMAL>(ctx, nw->act[3], nw->slots[3], nw->conv[3], nw->act[4], nw->slots[4], np))) return rc;
-      if ((rc = launch_conv<64, 64, 1, 8, 1, OUT_NORMAL>(ctx, nw->act[4], nw->slots[4], nw->conv[4], nw->act[5], nw->slots[5], np))) return rc;
+      if ((rc = launch_conv<16, 32, 1, 16, 4, OUT_NORMAL>(ctx, nw->act[1], nw->slots[1], nw->conv[1], nw->act[2], nw->slots[2], np, p0, cnt_dev))) return rc;
+      if ((rc = launch_conv<32, 32, 1, 16, 1, OUT_PARITY>(ctx, nw->act[2], nw->slots[2], nw->conv[2], nw->act[3], nw->slots[3], np, p0, cnt_dev))) return rc;
+      if ((rc = launch_conv<32, 64, 1, 8, 4, OUT_NORMAL>(ctx, nw->act[3], nw->slots[3], nw->conv[3], nw->act[4], nw->slots[4], np, p0, cnt_dev))) return rc;
+      if ((rc = launch_conv<64, 64, 1, 8, 1, OUT_NORMAL>(ctx, nw->act[4], nw->slots[4], nw->conv[4], nw->act[5], nw->slots[5], np, p0, cnt_dev))) return rc;
       static OnceFlags hattr;
       if (hattr.need(ctx->device)) {
         MG_CUDA(ctx, cudaFuncSetAttribute(k_head_small<3, false, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 4096 * 4));
@@ -1204,10 +1224,10 @@ int mg_net_forward_enqueue(modsgpu_ctx* ctx, modsgpu_net net, const uint8_t* d_p
       MG_PROF(ctx, net == MODSGPU_AFFNET ? "k_head_aff" : "k_head_ori", 1, 2.0 * np * (net == MODSGPU_AFFNET ? 12288.0 : 61952.0));
       if (net == MODSGPU_AFFNET)   // 48 KB of weights per CTA: 4 CTAs (32 warps) per SM
         k_head_small<3, false, 1, 8><<<std::min(ceil_div(np, 8), 4 * ctx->num_sms), 256, 3 * 4096 * 4, ctx->stream>>>(
-            nw->act[5], nw->slots[5], nw->head_w32, nw->head_b, pout, np);
+            nw->act[5], nw->slots[5], nw->head_w32, nw->head_b, pout, np, cnt_dev, p0);
       else                         // 4 warps x 4 patches per CTA pass, 160 registers: 3 CTAs per SM
         k_head_small<2, true, 4, 4><<<std::min(ceil_div(np, 16), 3 * ctx->num_sms), 128, 2 * 4096 * 4, ctx->stream>>>(
-            nw->act[5], nw->slots[5], nw->head_w32, nw->head_b, pout, np);
+            nw->act[5], nw->slots[5], nw->head_w32, nw->head_b, pout, np, cnt_dev, p0);
       MG_LAUNCHED(ctx);
     }
   }
@@ -1215,10 +1235,10 @@ int mg_net_forward_enqueue(modsgpu_ctx* ctx, modsgpu_net net, const uint8_t* d_p
     static OnceFlags attr;
     if (attr.need(ctx->device)) { MG_CUDA(ctx, cudaFuncSetAttribute(k_head_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, HG_SMEM)); attr.set(ctx->device); }
     MG_PROF(ctx, "k_head_gemm", 1, 2.0 * n * 8192.0 * 128);
-    k_head_gemm<<<dim3(m_pad / 128, HG_KSPLIT), 192, HG_SMEM, ctx->stream>>>(act6all, (size_t)m_pad, nw->head_w16, part, m_pad);
+    k_head_gemm<<<dim3(m_pad / 128, HG_KSPLIT), 192, HG_SMEM, ctx->stream>>>(act6all, (size_t)m_pad, nw->head_w16, part, m_pad, cnt_dev);
     MG_LAUNCHED(ctx);
     MG_PROF(ctx, "k_head_finish", 0, (double)n * 128 * 4 * (HG_KSPLIT + 1));
-    k_head_finish<<<ceil_div(n, 8), 256, 0, ctx->stream>>>(part, m_pad, nw->head_b, d_out, n);
+    k_head_finish<<<ceil_div(n, 8), 256, 0, ctx->stream>>>(part, m_pad, nw->head_b, d_out, n, cnt_dev);
     MG_LAUNCHED(ctx);
   }
   return 0;
@@ -1232,7 +1252,7 @@ extern "C" int modsgpu_net_forward_u8(modsgpu_ctx* ctx, modsgpu_net net, const u
   MG_CUDA(ctx, ctx->smp_out.ensure((size_t)n * 1024));
   MG_CUDA(ctx, ctx->cnn_out.ensure((size_t)n * D * 4));
   MG_CUDA(ctx, cudaMemcpyAsync(ctx->smp_out.p, patches, (size_t)n * 1024, cudaMemcpyHostToDevice, ctx->stream));
-  int rc = mg_net_forward_enqueue(ctx, net, ctx->smp_out.as<uint8_t>(), n, ctx->cnn_out.as<float>());
+  int rc = mg_net_forward_enqueue(ctx, net, ctx->smp_out.as<uint8_t>(), n, ctx->cnn_out.as<float>(), nullptr);
   if (rc) return rc;
   return mg_read_back_end(ctx, out, ctx->cnn_out.p, (size_t)n * D * 4);
 }
@@ -1251,7 +1271,7 @@ extern "C" int modsgpu_describe(modsgpu_ctx* ctx, modsgpu_net net, const modsgpu
   MG_CUDA(ctx, ctx->cnn_out.ensure((size_t)n * D * 4));
   int rc = mg_sample_enqueue(ctx, img, regs, n, mrSize, patchSize, ctx->smp_out.as<uint8_t>(), nullptr);
   if (rc) return rc;
-  rc = mg_net_forward_enqueue(ctx, net, ctx->smp_out.as<uint8_t>(), n, ctx->cnn_out.as<float>());
+  rc = mg_net_forward_enqueue(ctx, net, ctx->smp_out.as<uint8_t>(), n, ctx->cnn_out.as<float>(), nullptr);
   if (rc) return rc;
   return mg_read_back_end(ctx, out, ctx->cnn_out.p, (size_t)n * D * 4);
 }

@@ -53,6 +53,25 @@ struct modsgpu_image {
 
 struct NetWeights;  // cnn.cu
 
+// One region of a view while it lives on the device between the stages of the per-view chain (chain.cu): the
+// AffineRegion fields the hot path reads (structures.hpp:185-229).  Same bytes as modsgpu_view_region.
+struct DevRegion {
+  modsgpu_region det;      // det_kp, view coordinates
+  modsgpu_region reproj;   // reproj_kp, original image
+  double response;
+  int octave, type;
+};
+static_assert(sizeof(DevRegion) == 128, "DevRegion layout");
+
+// Upper bounds the host needs to size the sampler's launches for ANY subset of a view's keypoints: the window size R of a
+// region depends on its scale only, and the scale never changes between the three sampler passes of a view, so the
+// figures of the first pass (all keypoints) bound the later ones.  Written by k_smp_stats, read back once per view.
+struct SmpStats {
+  int cls_cnt[6], cls_rmax[6], cls_kr[6];
+  int nl, pre0, pre1, pre2, maxPS, maxR, maxks, _pad;
+  long long scratch;
+};
+
 // Optional per-launch CUDA-event timing (bench.py's roofline block).  kind: 0 = HBM-bound (work in bytes),
 // 1 = tensor-bound (work in flops), 2 = latency-bound (work = items).
 struct ProfRec { const char* name; int kind; double work, bytes; cudaEvent_t e0, e1; };
@@ -83,6 +102,9 @@ struct modsgpu_ctx {
   HostBuf h_stage, h_stage2;
   DevBuf io_a, io_b, io_c;            // generic staging for the test-only entry points
   DevBuf smp_regs, smp_meta, smp_taps, smp_scratch, smp_out;
+  DevBuf smp_prof;                    // 6 doubles: algorithmic bytes per sampler class of the device-prepared launches (profiler)
+  DevBuf smp_taptab;                  // Gaussian taps of every even window size (patchSize 32), device-side sampler prep
+  DevBuf chain_a, chain_b, chain_misc;   // region lists (DevRegion) of the per-view chain, counters / stats
   DevBuf cnn_act0, cnn_act1, cnn_out;
   DevBuf cnn_stats;                   // normalised patches (fp32) for the fused conv1+conv2 kernel
   DevBuf mt_q, mt_t, mt_d, mt_aux, mt_out;

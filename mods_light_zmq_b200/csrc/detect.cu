@@ -1060,6 +1060,12 @@ static int mg_detect_graph(modsgpu_ctx* ctx, const modsgpu_image* img, const mod
   return 0;
 }
 
+// the per-view chain (chain.cu) runs the detector without the keypoint read-back
+int mg_detect_device(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_pyr_params* p, int cap) {
+  return mg_detect_graph(ctx, img, p, cap, nullptr);
+}
+int mg_keys_to_export(const modsgpu_keypoint* k, int n, const modsgpu_pyr_params* p) { return keys_to_export(k, n, p, false); }
+
 static int detect_impl(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_pyr_params* p,
                        const modsgpu_affshape_params* aff, modsgpu_keypoint** out, float** A, int* n) {
   if (!ctx || !img || !p || !out || !n) return MODSGPU_EINVAL;

@@ -199,6 +199,40 @@ int ImageRepresentation::DescribeView(modsgpu_image* view, const double* H, int 
   int w, h;
   modsgpu_image_size(view, &w, &h);
   result.clear();
+  // Default route: the whole view on the device (modsgpu_describe_view, csrc/chain.cu) -- same stages, same arithmetic,
+  // two host synchronisations instead of four and no host-side list handling between the nets.  MODSGPU_SEAM_CHAIN=1
+  // keeps the seam-by-seam route below (modsgpu_detect + 3 x modsgpu_describe), which the parity tests compare it with.
+  const char* seam_env = getenv("MODSGPU_SEAM_CHAIN");      // read per view: the parity tests switch routes inside one process
+  const bool seam_chain = seam_env && atoi(seam_env) != 0;
+  if (!seam_chain && par.patchSize == 32) {
+    double t0 = now_ms();
+    modsgpu_view_region* rows = nullptr;
+    float* desc = nullptr;
+    int n = 0, counts[3] = {0, 0, 0};
+    int rc = modsgpu_describe_view(ctx_, view, H, orig_w, orig_h, &par.pyr, par.mrSize, par.patchSize, &rows, &desc, &n, counts);
+    if (rc) return rc;
+    n_keypoints = counts[0];
+    n_affine = counts[1];
+    auto blk = std::make_shared<const std::vector<float>>(desc, desc + (size_t)n * 128);
+    result.resize(n);
+    for (int i = 0; i < n; i++) {
+      AffineRegion& r = result[i];
+      r.id = i; r.parent_id = -1; r.type = 1 /* DET_HESSIAN */;
+      AffineKeypoint& k = r.det_kp;
+      const modsgpu_region& d = rows[i].det;
+      k.x = d.x; k.y = d.y; k.s = d.s; k.a11 = d.a11; k.a12 = d.a12; k.a21 = d.a21; k.a22 = d.a22;
+      k.response = rows[i].response; k.octave_number = rows[i].octave; k.sub_type = rows[i].type;
+      r.reproj_kp = k;
+      const modsgpu_region& q = rows[i].reproj;
+      r.reproj_kp.x = q.x; r.reproj_kp.y = q.y;
+      r.reproj_kp.a11 = q.a11; r.reproj_kp.a12 = q.a12; r.reproj_kp.a21 = q.a21; r.reproj_kp.a22 = q.a22;
+      r.desc.view(blk, (size_t)i * 128, 128);
+    }
+    modsgpu_free(rows);
+    modsgpu_free(desc);
+    TimeSpent.DescTime += now_ms() - t0;
+    return n;
+  }
   double Hinv[9];
   invert3h(H, Hinv);
   const bool eye = HIsEye(H);

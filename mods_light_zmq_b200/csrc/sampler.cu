@@ -90,8 +90,10 @@ __device__ __forceinline__ float row_pass_at(const float* row, int R, int x, con
 // ---- small windows: one CTA per region -----------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 k_sample_small(const float* __restrict__ img, int w, int h, const PatchMeta* __restrict__ metas,
-               const float* __restrict__ taps_all, uint8_t* __restrict__ out, int ps, float* __restrict__ outf) {
+               const float* __restrict__ taps_all, uint8_t* __restrict__ out, int ps, float* __restrict__ outf,
+               const int* __restrict__ cnt) {
   extern __shared__ float sm[];
+  if (cnt != nullptr && (int)blockIdx.x >= *cnt) return;      // grid sized by the host's upper bound (device-side prep)
   const PatchMeta m = metas[blockIdx.x];
   const int tid = threadIdx.x, nth = blockDim.x;
   const int R = m.R;
@@ -326,8 +328,10 @@ __host__ __device__ inline int a_smem_floats(int R, int r) {
 
 __global__ void __launch_bounds__(NT)
 k_sample_a(const float* __restrict__ img, int w, int h, const PatchMeta* __restrict__ metas,
-           const float* __restrict__ taps_all, uint8_t* __restrict__ out, int ps, float* __restrict__ outf) {
+           const float* __restrict__ taps_all, uint8_t* __restrict__ out, int ps, float* __restrict__ outf,
+           const int* __restrict__ cnt) {
   extern __shared__ float sm[];
+  if (cnt != nullptr && (int)blockIdx.x >= *cnt) return;
   const PatchMeta m = metas[blockIdx.x];
   const int tid = threadIdx.x;
   const int R = m.R, ks = m.ks, r = ks >> 1;
@@ -457,9 +461,10 @@ __host__ __device__ inline int b_smem_floats(int R, int r) {
 
 __global__ void __launch_bounds__(NT)
 k_sample_b(const float* __restrict__ img, int w, int h, const PatchMeta* __restrict__ metas,
-           const float* __restrict__ taps_all, uint8_t* __restrict__ out) {
+           const float* __restrict__ taps_all, uint8_t* __restrict__ out, const int* __restrict__ cnt) {
   constexpr int ps = 32;
   extern __shared__ float sm[];
+  if (cnt != nullptr && (int)blockIdx.x >= *cnt) return;
   const PatchMeta m = metas[blockIdx.x];
   const int tid = threadIdx.x;
   const int R = m.R, ks = m.ks, r = ks >> 1;
@@ -607,7 +612,9 @@ __host__ __device__ inline long long large_c_floats(int R) { return 2LL * R * ((
 // phase 0: one thread per window row walks the row's float coordinate sequence once (the sequential `WX += a11` of
 // interpolate(), helpers.cpp:551-626, is what makes the samples bit-exact) and keeps every SEG-th coordinate
 __global__ void __launch_bounds__(L0_ROWS)
-k_large_starts(const PatchMeta* __restrict__ metas, int nreg, const int* __restrict__ pre, float* __restrict__ scratch) {
+k_large_starts(const PatchMeta* __restrict__ metas, int nreg, const int* __restrict__ pre, float* __restrict__ scratch,
+               const int* __restrict__ nreg_dev) {
+  if (nreg_dev != nullptr) { nreg = *nreg_dev; if ((int)blockIdx.x >= pre[nreg]) return; }
   const int reg = find_region(pre, nreg, blockIdx.x);
   const PatchMeta m = metas[reg];
   const int R = m.R, nseg = (R + SEG - 1) / SEG;
@@ -618,7 +625,8 @@ k_large_starts(const PatchMeta* __restrict__ metas, int nreg, const int* __restr
 // phase 1: S[j][i] for L1_ROWS rows of one region; an 8-lane group walks one row segment by segment (as class A / B)
 __global__ void __launch_bounds__(128)
 k_large_resample(const float* __restrict__ img, int w, int h, const PatchMeta* __restrict__ metas, int nreg,
-                 const int* __restrict__ pre, float* __restrict__ scratch) {
+                 const int* __restrict__ pre, float* __restrict__ scratch, const int* __restrict__ nreg_dev) {
+  if (nreg_dev != nullptr) { nreg = *nreg_dev; if ((int)blockIdx.x >= pre[nreg]) return; }
   const int reg = find_region(pre, nreg, blockIdx.x);
   const PatchMeta m = metas[reg];
   const int R = m.R, nseg = (R + SEG - 1) / SEG;
@@ -634,8 +642,9 @@ k_large_resample(const float* __restrict__ img, int w, int h, const PatchMeta* _
 // thread); the few columns in OpenCV's scalar tail go through row_pass_at.
 __global__ void __launch_bounds__(256)
 k_large_rowpass(const PatchMeta* __restrict__ metas, int nreg, const int* __restrict__ pre,
-                const float* __restrict__ taps_all, float* __restrict__ scratch, int ps) {
+                const float* __restrict__ taps_all, float* __restrict__ scratch, int ps, const int* __restrict__ nreg_dev) {
   extern __shared__ float sm[];
+  if (nreg_dev != nullptr) { nreg = *nreg_dev; if ((int)blockIdx.x >= pre[nreg]) return; }
   const int reg = find_region(pre, nreg, blockIdx.x);
   const PatchMeta m = metas[reg];
   const int R = m.R, ks = m.ks, r = ks >> 1, nc = 2 * ps, PS = (R + 2 * r + 2) | 1;
@@ -691,10 +700,12 @@ k_large_rowpass(const PatchMeta* __restrict__ metas, int nreg, const int* __rest
 // phase 2b + 3: column pass at the needed rows of L3_OUT_ROWS output rows, then the final resampling
 __global__ void __launch_bounds__(256)
 k_large_colpass_final(const PatchMeta* __restrict__ metas, const float* __restrict__ taps_all,
-                      const float* __restrict__ scratch, uint8_t* __restrict__ out, int ps, float* __restrict__ outf) {
+                      const float* __restrict__ scratch, uint8_t* __restrict__ out, int ps, float* __restrict__ outf,
+                      const int* __restrict__ nreg_dev) {
   extern __shared__ float sm[];
   const int nblk = (ps + L3_OUT_ROWS - 1) / L3_OUT_ROWS;
   const int reg = blockIdx.x / nblk, j0 = (blockIdx.x - reg * nblk) * L3_OUT_ROWS;
+  if (nreg_dev != nullptr && reg >= *nreg_dev) return;
   const PatchMeta m = metas[reg];
   const int R = m.R, ks = m.ks, nc = 2 * ps, r = ks >> 1;
   const int nout = min(L3_OUT_ROWS, ps - j0);
@@ -873,7 +884,7 @@ int mg_sample_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
   };
   if (!cls[C_SMALL].empty()) {
     MG_PROF(ctx, "k_sample_small", 0, alg_bytes(cls[C_SMALL]));
-    k_sample_small<<<(unsigned)cls[C_SMALL].size(), 128, SMEM_SMALL, ctx->stream>>>(img->d, img->w, img->h, dm, dtaps, d_out, ps, d_outf);
+    k_sample_small<<<(unsigned)cls[C_SMALL].size(), 128, SMEM_SMALL, ctx->stream>>>(img->d, img->w, img->h, dm, dtaps, d_out, ps, d_outf, nullptr);
     MG_LAUNCHED(ctx);
   }
   const int a_maxR[2] = {A1_R, A2_R}, b_maxR[2] = {B1_R, B2_R};
@@ -881,30 +892,321 @@ int mg_sample_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
     if (cls[c].empty()) continue;
     const int smem = a_smem_floats(std::min(a_maxR[c - C_A1], cls[c][0].R), cls_r[c]) * 4;
     MG_PROF(ctx, c == C_A1 ? "k_sample_a<R<=40>" : "k_sample_a<R<=65>", 0, alg_bytes(cls[c]));
-    k_sample_a<<<(unsigned)cls[c].size(), NT, smem, ctx->stream>>>(img->d, img->w, img->h, dm + cls_off[c], dtaps, d_out, ps, d_outf);
+    k_sample_a<<<(unsigned)cls[c].size(), NT, smem, ctx->stream>>>(img->d, img->w, img->h, dm + cls_off[c], dtaps, d_out, ps, d_outf, nullptr);
     MG_LAUNCHED(ctx);
   }
   for (int c = C_B1; c <= C_B2; c++) {
     if (cls[c].empty()) continue;
     const int smem = b_smem_floats(std::min(b_maxR[c - C_B1], cls[c][0].R), cls_r[c]) * 4;
     MG_PROF(ctx, c == C_B1 ? "k_sample_b<R<=100>" : "k_sample_b<R<=160>", 0, alg_bytes(cls[c]));
-    k_sample_b<<<(unsigned)cls[c].size(), NT, smem, ctx->stream>>>(img->d, img->w, img->h, dm + cls_off[c], dtaps, d_out);
+    k_sample_b<<<(unsigned)cls[c].size(), NT, smem, ctx->stream>>>(img->d, img->w, img->h, dm + cls_off[c], dtaps, d_out, nullptr);
     MG_LAUNCHED(ctx);
   }
   if (nl > 0) {
     const PatchMeta* dl = dm + cls_off[C_LARGE];
     float* scr = ctx->smp_scratch.as<float>();
     MG_PROF(ctx, "k_large_starts", 2, (double)nl);
-    k_large_starts<<<pre0[nl], L0_ROWS, 0, ctx->stream>>>(dl, nl, dpre0, scr);
+    k_large_starts<<<pre0[nl], L0_ROWS, 0, ctx->stream>>>(dl, nl, dpre0, scr, nullptr);
     MG_LAUNCHED(ctx);
     MG_PROF(ctx, "k_large_resample", 0, alg_bytes(large));
-    k_large_resample<<<pre1[nl], 128, 0, ctx->stream>>>(img->d, img->w, img->h, dl, nl, dpre1, scr);
+    k_large_resample<<<pre1[nl], 128, 0, ctx->stream>>>(img->d, img->w, img->h, dl, nl, dpre1, scr, nullptr);
     MG_LAUNCHED(ctx);
     MG_PROF(ctx, "k_large_rowpass", 2, (double)nl);
-    k_large_rowpass<<<pre2[nl], 256, (2 * MAX_PS + 642 + L2_ROWS * maxPS) * 4, ctx->stream>>>(dl, nl, dpre2, dtaps, scr, ps);
+    k_large_rowpass<<<pre2[nl], 256, (2 * MAX_PS + 642 + L2_ROWS * maxPS) * 4, ctx->stream>>>(dl, nl, dpre2, dtaps, scr, ps, nullptr);
     MG_LAUNCHED(ctx);
     MG_PROF(ctx, "k_large_colpass_final", 2, (double)nl);
-    k_large_colpass_final<<<nl * ceil_div(ps, L3_OUT_ROWS), 256, SMEM_L3, ctx->stream>>>(dl, dtaps, scr, d_out, ps, d_outf);
+    k_large_colpass_final<<<nl * ceil_div(ps, L3_OUT_ROWS), 256, SMEM_L3, ctx->stream>>>(dl, dtaps, scr, d_out, ps, d_outf, nullptr);
+    MG_LAUNCHED(ctx);
+  }
+  return 0;
+}
+
+// =====================================================================================================================
+// Device-side preparation (the per-view chain, chain.cu): the region list lives on the device and its length is only
+// known there, so classification, the decreasing-R placement inside a class and the work lists of the large-window
+// path are built by one CTA (k_smp_prepare) instead of the host loop of mg_sample_enqueue.  Launch grids are sized by
+// the upper bounds of SmpStats (k_smp_stats over ALL keypoints of the view; later passes see subsets with the same
+// scales); surplus CTAs leave at once.  patchSize 32, u8 output only.  The arithmetic that decides R, the class and
+// the taps is the host path's, term by term.
+// =====================================================================================================================
+namespace {
+
+enum { SC_SMALL = 0, SC_A1, SC_A2, SC_B1, SC_B2, SC_LARGE, SC_N };
+constexpr int DEV_PS = 32;
+constexpr int HB_SMALL = 162;                       // R bins of the five shared-memory classes (R <= 160)
+constexpr int HB_TOTAL = 5 * HB_SMALL + MAX_R + 1;  // + the large class
+
+struct TapTab { const int* off; const int* ks; const float* taps; };
+
+// R, class and taps of one region (mg_sample_enqueue's loop body, ps = 32, u8 output)
+__device__ __forceinline__ void classify_region(const modsgpu_region& k, double mrSize, const TapTab& tt, PatchMeta& m, int& c) {
+  m.x = (float)k.x; m.y = (float)k.y;
+  m.a11 = (float)k.a11; m.a12 = (float)k.a12; m.a21 = (float)k.a21; m.a22 = (float)k.a22;
+  const float mrScale = (float)ceil(k.s * mrSize);
+  int R0 = 2 * int(mrScale);
+  if (R0 > MAX_R - 2) R0 = MAX_R - 2;      // the host refuses such views after the statistics read-back (maxR)
+  if (R0 < 0) R0 = 0;
+  m.scale = float(R0) / float(DEV_PS);
+  m.scratch_off = 0; m.ks = 0; m.tap_off = 0; m.out_index = 0;
+  c = SC_SMALL;
+  if ((double)m.scale > 0.4) {
+    m.R = R0 + 2;
+    m.tap_off = tt.off[R0]; m.ks = tt.ks[R0];
+    const bool blocked = m.ks >= 7 && m.ks <= 60;
+    if (blocked && m.R <= A1_R) c = SC_A1;
+    else if (blocked && m.R <= A2_R) c = SC_A2;
+    else if (blocked && R0 >= 2 * DEV_PS && m.R <= B1_R) c = SC_B1;
+    else if (blocked && R0 >= 2 * DEV_PS && m.R <= B2_R) c = SC_B2;
+    else if (m.R <= SMALL_R && m.ks <= 31) c = SC_SMALL;
+    else c = SC_LARGE;
+  } else {
+    m.R = 0;
+  }
+}
+__device__ __forceinline__ int hist_bin(int c, int R) { return c < SC_LARGE ? c * HB_SMALL + R : 5 * HB_SMALL + R; }
+__host__ __device__ inline long long large_region_floats(int R, int ps) {
+  long long f = large_c_floats(R) + (long long)R * R + (long long)R * 2 * ps;
+  return f + (f & 1);          // the float2 table at the head of the next region stays 8-byte aligned
+}
+
+// statistics of a region list (one CTA): per-class counts / largest window / widest blur, and the block and scratch
+// totals of the large-window path
+__global__ void __launch_bounds__(1024)
+k_smp_stats(const DevRegion* __restrict__ regs, const int* __restrict__ cnt, double mrSize, TapTab tt, SmpStats* __restrict__ out) {
+  __shared__ int s_cnt[SC_N], s_rmax[SC_N], s_kr[SC_N], s_i[8];
+  __shared__ unsigned long long s_scratch;
+  if (threadIdx.x < SC_N) { s_cnt[threadIdx.x] = 0; s_rmax[threadIdx.x] = 0; s_kr[threadIdx.x] = 0; }
+  if (threadIdx.x < 8) s_i[threadIdx.x] = 0;
+  if (threadIdx.x == 0) s_scratch = 0ull;
+  __syncthreads();
+  const int n = *cnt;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    PatchMeta m; int c;
+    classify_region(regs[i].det, mrSize, tt, m, c);
+    atomicAdd(&s_cnt[c], 1);
+    atomicMax(&s_rmax[c], m.R);
+    atomicMax(&s_kr[c], m.ks >> 1);
+    atomicMax(&s_i[5], 2 * int((float)ceil(regs[i].det.s * mrSize)) + 2);     // unclamped R
+    atomicMax(&s_i[6], m.ks);
+    if (c == SC_LARGE) {
+      atomicAdd(&s_i[0], 1);
+      atomicAdd(&s_i[1], (m.R + L0_ROWS - 1) / L0_ROWS);
+      atomicAdd(&s_i[2], (m.R + L1_ROWS - 1) / L1_ROWS);
+      atomicAdd(&s_i[3], (m.R + L2_ROWS - 1) / L2_ROWS);
+      atomicMax(&s_i[4], (m.R + 2 * (m.ks >> 1) + 2) | 1);
+      atomicAdd(&s_scratch, (unsigned long long)large_region_floats(m.R, DEV_PS));
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int c = 0; c < SC_N; c++) { out->cls_cnt[c] = s_cnt[c]; out->cls_rmax[c] = s_rmax[c]; out->cls_kr[c] = s_kr[c]; }
+    out->nl = s_i[0]; out->pre0 = s_i[1]; out->pre1 = s_i[2]; out->pre2 = s_i[3]; out->maxPS = s_i[4];
+    out->maxR = s_i[5]; out->maxks = s_i[6]; out->_pad = 0;
+    out->scratch = (long long)s_scratch;
+  }
+}
+
+struct PrepLayout { int cls_off[SC_N]; int nl_cap; };   // class c's PatchMeta live at metas + cls_off[c] (upper-bound layout)
+
+// One CTA builds the sampler's work lists for the regions [0, *cnt): PatchMeta per region, dealt into the classes'
+// slabs in order of decreasing R (the order inside a class only decides which CTAs start first; equal-R regions may
+// land in any order), the live count of every class, and for the large-window class the scratch offsets and the
+// three block-count prefix arrays.
+__global__ void __launch_bounds__(1024)
+k_smp_prepare(const DevRegion* __restrict__ regs, const int* __restrict__ cnt, double mrSize, TapTab tt, PrepLayout lay,
+              PatchMeta* __restrict__ metas, int2* __restrict__ tmp, int* __restrict__ pre1, int* __restrict__ pre2,
+              int* __restrict__ pre0, int* __restrict__ cls_cnt_out, double* __restrict__ prof_bytes) {
+  __shared__ int hist[HB_TOTAL];
+  __shared__ int s_cls[SC_N];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < HB_TOTAL; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  const int n = *cnt;
+  for (int i = tid; i < n; i += blockDim.x) {
+    PatchMeta m; int c;
+    classify_region(regs[i].det, mrSize, tt, m, c);
+    const int bin = hist_bin(c, m.R);
+    tmp[i] = make_int2(bin, atomicAdd(&hist[bin], 1));
+  }
+  __syncthreads();
+  // warp c turns class c's counts into start positions, walking R downwards (exclusive scan, 32 bins per step)
+  if (warp < SC_N) {
+    const int c = warp, rtop = c < SC_LARGE ? HB_SMALL - 1 : MAX_R;
+    int carry = 0;
+    for (int r0 = rtop; r0 >= 0; r0 -= 32) {
+      const int R = r0 - lane;
+      const int v = R >= 0 ? hist[hist_bin(c, R)] : 0;
+      int incl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+      if (R >= 0) hist[hist_bin(c, R)] = lay.cls_off[c] + carry + incl - v;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) { s_cls[c] = carry; cls_cnt_out[c] = carry; }
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += blockDim.x) {
+    PatchMeta m; int c;
+    classify_region(regs[i].det, mrSize, tt, m, c);
+    m.out_index = i;
+    const int2 t = tmp[i];
+    metas[hist[t.x] + t.y] = m;
+    // profiler only: the algorithmic bytes of this region (R*R*4 read + 32*32 written), per class
+    if (prof_bytes != nullptr) atomicAdd(prof_bytes + c, (double)m.R * m.R * 4.0 + (double)(DEV_PS * DEV_PS));
+  }
+  __syncthreads();
+  // large-window class: scratch offsets and the prefix arrays of the three row-blocked phases (warp 0, 32 regions per step)
+  if (warp == 0) {
+    const int nl = min(s_cls[SC_LARGE], lay.nl_cap);
+    PatchMeta* large = metas + lay.cls_off[SC_LARGE];
+    int c0 = 0, c1 = 0, c2 = 0;
+    long long cs = 0;
+    for (int i0 = 0; i0 < nl; i0 += 32) {
+      const int i = i0 + lane;
+      const int R = i < nl ? large[i].R : 0;
+      int b0 = i < nl ? (R + L0_ROWS - 1) / L0_ROWS : 0, b1 = i < nl ? (R + L1_ROWS - 1) / L1_ROWS : 0, b2 = i < nl ? (R + L2_ROWS - 1) / L2_ROWS : 0;
+      long long sz = i < nl ? large_region_floats(R, DEV_PS) : 0;
+      int i0s = b0, i1s = b1, i2s = b2;
+      long long ss = sz;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t0 = __shfl_up_sync(0xffffffffu, i0s, o), t1 = __shfl_up_sync(0xffffffffu, i1s, o), t2 = __shfl_up_sync(0xffffffffu, i2s, o);
+        const long long ts = __shfl_up_sync(0xffffffffu, ss, o);
+        if (lane >= o) { i0s += t0; i1s += t1; i2s += t2; ss += ts; }
+      }
+      if (i < nl) {
+        pre0[i] = c0 + i0s - b0; pre1[i] = c1 + i1s - b1; pre2[i] = c2 + i2s - b2;
+        large[i].scratch_off = cs + ss - sz;
+      }
+      c0 += __shfl_sync(0xffffffffu, i0s, 31); c1 += __shfl_sync(0xffffffffu, i1s, 31); c2 += __shfl_sync(0xffffffffu, i2s, 31);
+      cs += __shfl_sync(0xffffffffu, ss, 31);
+    }
+    if (lane == 0) { pre0[nl] = c0; pre1[nl] = c1; pre2[nl] = c2; }
+  }
+}
+
+}  // namespace
+
+// The taps of every even window size R0 in [2, MAX_R - 2] for patchSize 32 (sigma = 1.5 * R0 / 32, helpers.cpp:726-731),
+// built once per context: [off: MAX_R ints | ks: MAX_R ints | taps].  ~1.2 MB.
+static int smp_taptab(modsgpu_ctx* ctx, TapTab& tt) {
+  if (!ctx->smp_taptab.p) {
+    std::vector<int> off(MAX_R, 0), ks(MAX_R, 0);
+    std::vector<float> taps, t;
+    for (int R0 = 2; R0 <= MAX_R - 2; R0 += 2) {
+      const float scale = float(R0) / float(DEV_PS);
+      if (!((double)scale > 0.4)) continue;
+      ks[R0] = mg_gaussian_taps(1.5f * scale, t);
+      off[R0] = (int)taps.size();
+      taps.insert(taps.end(), t.begin(), t.end());
+    }
+    const size_t bytes = (size_t)2 * MAX_R * 4 + taps.size() * 4;
+    MG_CUDA(ctx, ctx->smp_taptab.ensure(bytes));
+    std::vector<uint8_t> blob(bytes);
+    memcpy(blob.data(), off.data(), MAX_R * 4);
+    memcpy(blob.data() + MAX_R * 4, ks.data(), MAX_R * 4);
+    memcpy(blob.data() + 2 * MAX_R * 4, taps.data(), taps.size() * 4);
+    MG_CUDA(ctx, cudaMemcpyAsync(ctx->smp_taptab.p, blob.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+    MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));     // `blob` is pageable and dies here
+  }
+  tt.off = ctx->smp_taptab.as<int>();
+  tt.ks = tt.off + MAX_R;
+  tt.taps = reinterpret_cast<const float*>(tt.ks + MAX_R);
+  return 0;
+}
+
+// statistics of the regions [0, *cnt_dev) into *d_stats (device); no host synchronisation
+int mg_sample_stats_enqueue(modsgpu_ctx* ctx, const DevRegion* regs, const int* cnt_dev, double mrSize, SmpStats* d_stats) {
+  TapTab tt;
+  if (int rc = smp_taptab(ctx, tt)) return rc;
+  MG_PROF(ctx, "k_smp_stats", 2, 1.0);
+  k_smp_stats<<<1, 1024, 0, ctx->stream>>>(regs, cnt_dev, mrSize, tt, d_stats);
+  MG_LAUNCHED(ctx);
+  return 0;
+}
+
+// The sampler over a DEVICE region list of *cnt_dev (<= n_ub) regions, 32x32 u8 patches in region order into d_out.
+// `st` = the view's upper bounds (mg_sample_stats_enqueue over a superset of these regions).  No host synchronisation.
+int mg_sample_enqueue_dev(modsgpu_ctx* ctx, const modsgpu_image* img, const DevRegion* regs, const int* cnt_dev, int n_ub,
+                          const SmpStats& st, double mrSize, uint8_t* d_out) {
+  if (n_ub <= 0) return 0;
+  if (st.maxR > MAX_R) MG_FAIL(ctx, MODSGPU_EINVAL, "region too large for the sampler (R > 2048)");
+  if (st.maxks > 600) MG_FAIL(ctx, MODSGPU_EINVAL, "sampler blur too wide");
+  TapTab tt;
+  if (int rc = smp_taptab(ctx, tt)) return rc;
+  const int ps = DEV_PS;
+  PrepLayout lay;
+  size_t nm = 0;
+  for (int c = 0; c < SC_N; c++) { lay.cls_off[c] = (int)nm; nm += (size_t)st.cls_cnt[c]; }
+  lay.nl_cap = st.nl;
+  const int nl = st.nl;
+  const size_t meta_bytes = (nm + 1) * sizeof(PatchMeta), pre_bytes = (size_t)(nl + 1) * 4;
+  MG_CUDA(ctx, ctx->smp_meta.ensure(meta_bytes + 3 * pre_bytes + 64));
+  MG_CUDA(ctx, ctx->smp_regs.ensure((size_t)n_ub * sizeof(int2) + 16));
+  MG_CUDA(ctx, ctx->smp_scratch.ensure((size_t)st.scratch * 4 + 16));
+  PatchMeta* dm = ctx->smp_meta.as<PatchMeta>();
+  int* dpre1 = reinterpret_cast<int*>(ctx->smp_meta.as<uint8_t>() + meta_bytes);
+  int* dpre2 = dpre1 + (nl + 1);
+  int* dpre0 = dpre2 + (nl + 1);
+  int* dcnt = dpre0 + (nl + 1);
+  double* prof_bytes = nullptr;      // device accumulators read by modsgpu_profile_report (api.cu)
+  if (ctx->prof.on) {
+    if (!ctx->smp_prof.p) { MG_CUDA(ctx, ctx->smp_prof.ensure(64)); MG_CUDA(ctx, cudaMemsetAsync(ctx->smp_prof.p, 0, 64, ctx->stream)); }
+    prof_bytes = ctx->smp_prof.as<double>();
+  }
+  MG_PROF(ctx, "k_smp_prepare", 2, (double)n_ub);
+  k_smp_prepare<<<1, 1024, 0, ctx->stream>>>(regs, cnt_dev, mrSize, tt, lay, dm, ctx->smp_regs.as<int2>(), dpre1, dpre2, dpre0, dcnt,
+                                             prof_bytes);
+  MG_LAUNCHED(ctx);
+  static OnceFlags attr_set;
+  if (attr_set.need(ctx->device)) {
+    MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_small, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SMALL));
+    MG_CUDA(ctx, cudaFuncSetAttribute(k_large_rowpass, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (2 * MAX_PS + 642 + L2_ROWS * ((MAX_R + 602) | 1)) * 4));
+    MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_a, cudaFuncAttributeMaxDynamicSharedMemorySize, a_smem_floats(A2_R, 30) * 4));
+    MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_b, cudaFuncAttributeMaxDynamicSharedMemorySize, b_smem_floats(B2_R, 30) * 4));
+    attr_set.set(ctx->device);
+  }
+  // the algorithmic bytes of these launches are only known on the device: k_smp_prepare accumulates them per class and
+  // modsgpu_profile_report adds them to the kernels' records
+  auto alg_bytes = [&](int) { return 0.0; };
+  const float* dtaps = tt.taps;
+  if (st.cls_cnt[SC_SMALL] > 0) {
+    MG_PROF(ctx, "k_sample_small", 0, alg_bytes(SC_SMALL));
+    k_sample_small<<<(unsigned)st.cls_cnt[SC_SMALL], 128, SMEM_SMALL, ctx->stream>>>(img->d, img->w, img->h, dm + lay.cls_off[SC_SMALL], dtaps,
+                                                                                    d_out, ps, nullptr, dcnt + SC_SMALL);
+    MG_LAUNCHED(ctx);
+  }
+  const int a_maxR[2] = {A1_R, A2_R}, b_maxR[2] = {B1_R, B2_R};
+  for (int c = SC_A1; c <= SC_A2; c++) {
+    if (st.cls_cnt[c] <= 0) continue;
+    const int smem = a_smem_floats(std::min(a_maxR[c - SC_A1], st.cls_rmax[c]), st.cls_kr[c]) * 4;
+    MG_PROF(ctx, c == SC_A1 ? "k_sample_a<R<=40>" : "k_sample_a<R<=65>", 0, alg_bytes(c));
+    k_sample_a<<<(unsigned)st.cls_cnt[c], NT, smem, ctx->stream>>>(img->d, img->w, img->h, dm + lay.cls_off[c], dtaps, d_out, ps, nullptr, dcnt + c);
+    MG_LAUNCHED(ctx);
+  }
+  for (int c = SC_B1; c <= SC_B2; c++) {
+    if (st.cls_cnt[c] <= 0) continue;
+    const int smem = b_smem_floats(std::min(b_maxR[c - SC_B1], st.cls_rmax[c]), st.cls_kr[c]) * 4;
+    MG_PROF(ctx, c == SC_B1 ? "k_sample_b<R<=100>" : "k_sample_b<R<=160>", 0, alg_bytes(c));
+    k_sample_b<<<(unsigned)st.cls_cnt[c], NT, smem, ctx->stream>>>(img->d, img->w, img->h, dm + lay.cls_off[c], dtaps, d_out, dcnt + c);
+    MG_LAUNCHED(ctx);
+  }
+  if (nl > 0) {
+    const PatchMeta* dl = dm + lay.cls_off[SC_LARGE];
+    float* scr = ctx->smp_scratch.as<float>();
+    const int* dnl = dcnt + SC_LARGE;
+    MG_PROF(ctx, "k_large_starts", 2, (double)nl);
+    k_large_starts<<<st.pre0, L0_ROWS, 0, ctx->stream>>>(dl, nl, dpre0, scr, dnl);
+    MG_LAUNCHED(ctx);
+    MG_PROF(ctx, "k_large_resample", 0, alg_bytes(SC_LARGE));
+    k_large_resample<<<st.pre1, 128, 0, ctx->stream>>>(img->d, img->w, img->h, dl, nl, dpre1, scr, dnl);
+    MG_LAUNCHED(ctx);
+    MG_PROF(ctx, "k_large_rowpass", 2, (double)nl);
+    k_large_rowpass<<<st.pre2, 256, (2 * MAX_PS + 642 + L2_ROWS * st.maxPS) * 4, ctx->stream>>>(dl, nl, dpre2, dtaps, scr, ps, dnl);
+    MG_LAUNCHED(ctx);
+    MG_PROF(ctx, "k_large_colpass_final", 2, (double)nl);
+    k_large_colpass_final<<<nl * ceil_div(ps, L3_OUT_ROWS), 256, SMEM_L3, ctx->stream>>>(dl, dtaps, scr, d_out, ps, nullptr, dnl);
     MG_LAUNCHED(ctx);
   }
   return 0;

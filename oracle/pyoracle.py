@@ -460,3 +460,61 @@ def classic_regions(gray, mr_size=5.1962):
     r2 = apply_orientations(regs, n_ang, ang)
     r3, _ = reproject_filter(r2, w, h)
     return len(kp), r3, describe_sift(gray, r3, mr_size)
+
+
+# --------------------------------------------------------------------------- reprojection (H != I)
+def reproject_by_H(regions, Hinv):
+    """ReprojectByH (synth-detection.cpp:578-587) on every region: the affine part of Hinv (row-major 3x3, view ->
+    original) applied to the centre and to A; s and the other fields are copied.  numpy evaluates each product and
+    sum as a separate IEEE double operation, left to right, like the reference's expression."""
+    Hm = np.asarray(Hinv, np.float64).ravel()
+    out = regions.copy()
+    x, y = regions["x"], regions["y"]
+    out["x"] = (Hm[0] * x + Hm[1] * y + Hm[2])
+    out["y"] = (Hm[3] * x + Hm[4] * y + Hm[5])
+    out["a11"] = (Hm[0] * regions["a11"] + Hm[1] * regions["a21"])
+    out["a12"] = (Hm[0] * regions["a12"] + Hm[1] * regions["a22"])
+    out["a21"] = (Hm[3] * regions["a11"] + Hm[4] * regions["a21"])
+    out["a22"] = (Hm[3] * regions["a12"] + Hm[4] * regions["a22"])
+    return out
+
+
+def invert3(H):
+    """cofactor inverse, the operation order of the host mirror's invert3h (cv::invert's arithmetic is third-party)"""
+    A = np.asarray(H, np.float64).ravel()
+    c0 = A[4] * A[8] - A[5] * A[7]
+    c1 = A[5] * A[6] - A[3] * A[8]
+    c2 = A[3] * A[7] - A[4] * A[6]
+    det = A[0] * c0 + A[1] * c1 + A[2] * c2
+    i = 1.0 / det
+    return np.array([c0 * i, (A[2] * A[7] - A[1] * A[8]) * i, (A[1] * A[5] - A[2] * A[4]) * i,
+                     c1 * i, (A[0] * A[8] - A[2] * A[6]) * i, (A[2] * A[3] - A[0] * A[5]) * i,
+                     c2 * i, (A[1] * A[6] - A[0] * A[7]) * i, (A[0] * A[4] - A[1] * A[3]) * i])
+
+
+def centre_inside(regions, w, h):
+    """ReprojectRegionsAndRemoveTouchBoundary with dontRemove (synth-detection.cpp:151-190): centre strictly inside"""
+    return (regions["x"] < w) & (regions["y"] < h) & (regions["x"] > 0) & (regions["y"] > 0)
+
+
+def describe_view_chain(gray_view, H, orig_w, orig_h, nets, mrSize=5.1962):
+    """The per-view chain of imagerepresentation.cpp:704-1006 on the CPU: detect -> AffNet + tests -> centre test ->
+    OriNet + rotation -> ReprojectRegions -> HardNet++.  `nets` = (affnet, orinet, hardnet) callables on u8 patches.
+    Returns dict(det, reproj, desc, counts)."""
+    h, w = gray_view.shape
+    eye = H is None
+    Hinv = None if eye else invert3(H)
+    kp = detect_hessian(gray_view)
+    regs = regions_from_keypoints(kp)
+    aff = nets[0](quantize_u8(extract_patches(gray_view, regs, mrSize)))
+    r2, _ = affnet_postprocess(regs, aff, w, h, mrSize)
+    n_affine = len(r2)
+    rp = r2 if eye else reproject_by_H(r2, Hinv)
+    r2 = r2[centre_inside(rp, orig_w, orig_h)]
+    ori = nets[1](quantize_u8(extract_patches(gray_view, r2, mrSize)))
+    r3 = orinet_postprocess(r2, ori)
+    rp = r3 if eye else reproject_by_H(r3, Hinv)
+    _, src = reproject_filter(rp, orig_w, orig_h)
+    r4, rp4 = r3[src], rp[src]
+    d = nets[2](quantize_u8(extract_patches(gray_view, r4, mrSize)))
+    return dict(det=r4, reproj=rp4, desc=d, counts=[len(kp), n_affine, len(r4)], aff=aff, ori=ori)

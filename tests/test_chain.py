@@ -1,0 +1,166 @@
+"""The per-view device chain (modsgpu_describe_view, csrc/chain.cu) against the oracle and against the seam-by-seam
+route.  Decisions (which regions survive, in which order) and descriptors must be identical; the region doubles are
+bit-equal up to the OriNet rotation, whose atan2 / cos / sin come from CUDA's libm instead of glibc (<= 2 ulp each,
+<= 5 ulp in a rotated entry of A)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+F7 = ("x", "y", "s", "a11", "a12", "a21", "a22")
+ULP = 1e-14     # a rotated entry is a11*cos - a12*sin with cos / sin each within 2 ulp of glibc's; the reprojection by
+                # H^-1 of a tilted view (entries up to the tilt) adds products of those with cancellation: <= 45 ulp of max(1, |a|)
+
+
+def _gray(oracle, u8):
+    from mods_light_zmq_b200 import synth
+    return oracle.gray_from_bgr(synth.gray_to_bgr(u8))
+
+
+def _close(a, b, what):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    err = np.abs(a - b)
+    tol = ULP * np.maximum(1.0, np.maximum(np.abs(a), np.abs(b)))
+    assert (err <= tol).all(), (what, float(err.max()))
+
+
+def _view(mg, oracle, u8, tilt, phi, zoom=1.0):
+    """device view + the same view on the CPU (both bit-identical, test_synth_view_bit_exact) + H"""
+    from mods_light_zmq_b200 import synth
+    img = mg.image_from_bgr8(synth.gray_to_bgr(u8))
+    view, H = mg.synth_view(img, tilt, phi, zoom, 0.5)
+    return img, view, np.asarray(H, np.float64).reshape(3, 3), mg.image_download(view)
+
+
+@pytest.mark.parametrize("tilt,phi", [(1.0, 0.0), (2.0, 0.6), (4.0, 2.2)])
+def test_post_kernels_fed_oracle_net_outputs(mg, oracle, tilt, phi):
+    """Rows a14-a16 in isolation: the device post-processing kernels get the ORACLE's net outputs (torch CPU) and must
+    make the oracle's decisions and produce its numbers -- AffNet step bit-equal, OriNet step within 2 ulp."""
+    from mods_light_zmq_b200 import synth
+    from oracle import cnn_oracle as CN
+    u8 = synth.blob_image(seed=77, w=480, h=360, n_blobs=700)
+    img, view, H, gv = _view(mg, oracle, u8, tilt, phi)
+    eye = tilt == 1.0
+    h, w = gv.shape
+    Hinv = None if eye else oracle.invert3(H)
+    kp = oracle.detect_hessian(gv)
+    regs = oracle.regions_from_keypoints(kp)
+    assert len(regs) > 150
+    aff = CN.affnet(oracle.quantize_u8(oracle.extract_patches(gv, regs)))
+    # make sure both kinds of rejection occur in the sample
+    aff[::17, 1] *= 9.0
+    r2, _ = oracle.affnet_postprocess(regs, aff, w, h)
+    rp = r2 if eye else oracle.reproject_by_H(r2, Hinv)
+    keep = oracle.centre_inside(rp, 480, 360)
+    got, n_affine = mg.debug_affnet_post(regs, aff, w, h, 480, 360, H=None if eye else H)
+    assert n_affine == len(r2) and len(got) == int(keep.sum()) and 0 < len(got) < len(regs)
+    for f in F7:
+        assert np.array_equal(got["det"][f], r2[keep][f]), f
+        assert np.array_equal(got["reproj"][f], rp[keep][f]), f
+    # OriNet step on the survivors
+    r2k = r2[keep]
+    ori = CN.orinet(oracle.quantize_u8(oracle.extract_patches(gv, r2k)))
+    r3 = oracle.orinet_postprocess(r2k, ori)
+    rp3 = r3 if eye else oracle.reproject_by_H(r3, Hinv)
+    _, src = oracle.reproject_filter(rp3, 480, 360)
+    got3 = mg.debug_orinet_post(got, ori, 480, 360, H=None if eye else H)
+    assert len(got3) == len(src) and 0 < len(src) < len(r2k)
+    for f in F7:
+        _close(got3["det"][f], r3[src][f], "det." + f)
+        _close(got3["reproj"][f], rp3[src][f], "reproj." + f)
+    view.free(); img.free()
+
+
+@pytest.mark.parametrize("tilt,phi", [(1.0, 0.0), (2.0, 1.1)])
+def test_describe_view_equals_oracle_chain(mg, oracle, tilt, phi):
+    """The whole chain on a small view.  The device nets differ from torch in the last bits (fp16 operands), so the CPU
+    chain is walked with the DEVICE net outputs taken through the seam call modsgpu_describe; lists, order, counts and
+    descriptors must then be identical."""
+    import mods_light_zmq_b200 as M
+    from mods_light_zmq_b200 import synth
+    u8 = synth.blob_image(seed=5, w=400, h=300, n_blobs=500)
+    img, view, H, gv = _view(mg, oracle, u8, tilt, phi)
+    eye = tilt == 1.0
+    h, w = gv.shape
+    Hinv = None if eye else oracle.invert3(H)
+    # CPU chain with the device nets evaluated through the seam call modsgpu_describe
+    kp = oracle.detect_hessian(gv)
+    regs = oracle.regions_from_keypoints(kp)
+    aff = mg.describe(M.AFFNET, view, regs)
+    r2, _ = oracle.affnet_postprocess(regs, aff, w, h)
+    n_affine = len(r2)
+    rp = r2 if eye else oracle.reproject_by_H(r2, Hinv)
+    r2 = r2[oracle.centre_inside(rp, 400, 300)]
+    ori = mg.describe(M.ORINET, view, r2)
+    r3 = oracle.orinet_postprocess(r2, ori)
+    rp3 = r3 if eye else oracle.reproject_by_H(r3, Hinv)
+    _, src = oracle.reproject_filter(rp3, 400, 300)
+    r4, rp4 = r3[src], rp3[src]
+    d = mg.describe(M.HARDNET, view, r4)
+    rows, desc, counts = mg.describe_view(view, None if eye else H, 400, 300)
+    assert counts == [len(kp), n_affine, len(r4)] and len(rows) == len(r4) > 50
+    for f in F7:
+        _close(rows["det"][f], r4[f], "det." + f)
+        _close(rows["reproj"][f], rp4[f], "reproj." + f)
+    assert np.array_equal(desc, d)
+    assert rows["octave"].min() >= 0 and set(np.unique(rows["type"])) <= {0, 1, 2}
+    view.free(); img.free()
+
+
+def _features_equal(a, b):
+    assert len(a) == len(b) and len(a) > 0, (len(a), len(b))
+    for f in F7 + ("response",):
+        _close(a[f], b[f], f)
+    for f in ("octave", "type", "view"):
+        assert np.array_equal(a[f], b[f]), f
+    assert np.array_equal(a["desc"], b["desc"])
+
+
+def test_chain_equals_seam_route_full_size(mg, synth_pair):
+    """config 3's image A (1024x768, ~4.4k keypoints, large-window regions included): the device chain returns what
+    the seam-by-seam route (modsgpu_detect + 3 x modsgpu_describe + host arithmetic) returns, identity view and a
+    tilted / rotated view schedule."""
+    import mods_light_zmq_b200 as M
+    from mods_light_zmq_b200 import synth
+    a, _, _ = synth_pair
+    img = mg.image_from_bgr8(synth.gray_to_bgr(a))
+    views = M.view_schedule([1.0], [1.0, 3.0], 120.0, 0.5)
+    assert len(views) >= 3
+    try:
+        os.environ["MODSGPU_SEAM_CHAIN"] = "1"
+        seam = mg.extract_features(img)
+        seam_v = mg.extract_features_views(img, views)
+    finally:
+        os.environ.pop("MODSGPU_SEAM_CHAIN", None)
+    l0 = mg.launch_count
+    chain = mg.extract_features(img)
+    chain_launches = mg.launch_count - l0
+    chain_v = mg.extract_features_views(img, views)
+    _features_equal(chain, seam)
+    _features_equal(chain_v, seam_v)
+    assert len(chain) > 3000 and chain_launches > 20
+    # twice the same answer (graph replay, recycled workspaces)
+    again = mg.extract_features(img)
+    assert again.tobytes() == chain.tobytes()
+    img.free()
+
+
+def test_chain_other_detector_modes_and_empty(mg):
+    """FixedRegNumber truncates the sorted list before the chain (prepareKeysForExport); a flat image yields nothing."""
+    import mods_light_zmq_b200 as M
+    from mods_light_zmq_b200 import synth
+    u8 = synth.blob_image(seed=9, w=320, h=240, n_blobs=300)
+    img = mg.image_from_bgr8(synth.gray_to_bgr(u8))
+    p = mg.default_params()
+    p.detectorMode = M.FIXED_REG_NUMBER
+    p.reg_number = 60
+    rows, desc, counts = mg.describe_view(img, params=p)
+    assert counts[0] == 60 and len(rows) == counts[2] <= counts[1] <= 60 and len(desc) == len(rows)
+    kp = mg.detect(img, p)
+    assert len(kp) == 60
+    flat = mg.image_from_bgr8(np.full((240, 320, 3), 128, np.uint8))
+    rows, desc, counts = mg.describe_view(flat)
+    assert len(rows) == 0 and counts == [0, 0, 0]
+    flat.free(); img.free()

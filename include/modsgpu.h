@@ -194,7 +194,12 @@ typedef struct {
   int    max_samples;           /* 1e6; matching.cpp:644-645 clamps to 1000 when T <= 20 */
   int    do_sym_check;          /* matching.cpp:652-681 */
   uint64_t seed;                /* the reference seeds with time(NULL), exp_ranH.c:823 */
+  int    error_type;            /* RANSACPars::errorType (matching.cpp:652-681): MODSGPU_ERR_SAMPSON (HDs / FDs),
+                                 * MODSGPU_ERR_SYMM_MAX (HDsSymMax), MODSGPU_ERR_SYMM_SUM (HDsSym).  The F estimator
+                                 * implements Sampson only and returns MODSGPU_EINVAL for the other two. */
+  int    _pad;
 } modsgpu_ransac_params;
+enum { MODSGPU_ERR_SAMPSON = 0, MODSGPU_ERR_SYMM_MAX = 1, MODSGPU_ERR_SYMM_SUM = 2 };   /* RANSAC_error_t, matching.hpp:95 */
 typedef struct {
   int    n_inliers;             /* Score.I */
   double J;                     /* Score.J (MSAC cost) */
@@ -209,6 +214,17 @@ typedef struct {
  * inl: T bytes. */
 int  modsgpu_ransac_H(modsgpu_ctx* ctx, const double* u, int T, const modsgpu_ransac_params* p,
                       double* H, unsigned char* inl, modsgpu_ransac_result* res);
+/* the same, also returning the error of every correspondence under H (the *resids array of exp_ransacHcustom) */
+int  modsgpu_ransac_H_resid(modsgpu_ctx* ctx, const double* u, int T, const modsgpu_ransac_params* p,
+                            double* H, unsigned char* inl, modsgpu_ransac_result* res, double* resid /* T */);
+
+/* the empirical checks LORANSACFiltering applies to degensac's inliers (matching.cpp:764-820): H = inv(Hloran^T),
+ * NaiveHCheck (:1014-1043), H_LAF_check (:250-308, HDsSymMax on the three LAF points, 3*HLAFCoef*err_threshold) or
+ * F_LAF_check (:192-249, FDs, LAFCoef*err_threshold); fewer than 8 survivors empty the list.  Host arithmetic only (no
+ * device, no ctx).  kp1 / kp2: reproj_kp of the n RANSAC inliers; model: the degensac-convention H or F; laf_coef:
+ * HLAFCoef (12) or LAFCoef (2); keep: n bytes; model_out: H row-major image 1 -> 2, or F unchanged. */
+int  modsgpu_empirical_checks(const modsgpu_region* kp1, const modsgpu_region* kp2, int n, const double* model, int use_F,
+                              double err_threshold, double laf_coef, unsigned char* keep, double* model_out, int* n_out);
 
 /* replaces exp_ransacFcustom degensac/exp_ranF.h:71-73 as called from LORANSACFiltering matching.cpp:722
  * (7-point sample, oriented epipolar constraint, Sampson error, MSAC, symmetric check, LO).  F: 9 doubles with

@@ -47,7 +47,10 @@ class AffShapeParams(C.Structure):
 
 class RansacParams(C.Structure):
     _fields_ = [("th", C.c_double), ("conf", C.c_double), ("max_samples", C.c_int), ("do_sym_check", C.c_int),
-                ("seed", C.c_uint64)]
+                ("seed", C.c_uint64), ("error_type", C.c_int), ("_pad", C.c_int)]
+
+
+ERR_SAMPSON, ERR_SYMM_MAX, ERR_SYMM_SUM = 0, 1, 2      # RANSAC_error_t, matching.hpp:95
 
 
 class PairResult(C.Structure):
@@ -293,16 +296,17 @@ class ModsGpu:
                                                       C.byref(n)))
         return order[:n.value].copy()
 
-    def ransac_H(self, u, th=16.0, conf=0.99, max_samples=1000000, sym_check=1, seed=12345):
+    def ransac_H(self, u, th=16.0, conf=0.99, max_samples=1000000, sym_check=1, seed=12345, error_type=0):
         u = np.ascontiguousarray(u, np.float64)
         T = len(u)
-        p = RansacParams(th, conf, 1000 if T <= 20 else max_samples, sym_check, seed)
+        p = RansacParams(th, conf, 1000 if T <= 20 else max_samples, sym_check, seed, error_type, 0)
         H = np.zeros(9, np.float64)
         inl = np.zeros(max(T, 1), np.uint8)
+        resid = np.zeros(max(T, 1), np.float64)
         res = RansacResult()
-        self._check(self.lib.modsgpu_ransac_H(self.ctx, _p(u), T, C.byref(p), _p(H), _p(inl), C.byref(res)))
+        self._check(self.lib.modsgpu_ransac_H_resid(self.ctx, _p(u), T, C.byref(p), _p(H), _p(inl), C.byref(res), _p(resid)))
         return dict(H=H, inl=inl[:T], I=res.n_inliers, J=res.J, samples=res.samples, lo_count=res.lo_runs,
-                    oc_rejects=res.oc_rejects)
+                    oc_rejects=res.oc_rejects, resid=resid[:T])
 
     # ---- classic stages
     def dominant_orientation(self, img, regs, mr_size=5.1962, patch_size=32, max_angles=1, th=0.8):
@@ -438,7 +442,7 @@ class ModsGpu:
         """modsgpu_ransac_F: LO-RANSAC for a fundamental matrix (exp_ransacFcustom, matching.cpp:722)."""
         u = np.ascontiguousarray(u, np.float64)
         T = len(u)
-        p = RansacParams(th, conf, 1000 if T <= 20 else max_samples, sym_check, seed)
+        p = RansacParams(th, conf, 1000 if T <= 20 else max_samples, sym_check, seed, 0, 0)
         F = np.zeros(9, np.float64)
         inl = np.zeros(max(T, 1), np.uint8)
         res = RansacResult()

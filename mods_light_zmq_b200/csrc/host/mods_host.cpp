@@ -653,6 +653,8 @@ int LORANSACFiltering(modsgpu_ctx* ctx, TentativeCorrespListExt& in_corresp, Ten
   rp.max_samples = max_samples;
   rp.do_sym_check = pars.doSymmCheck;
   rp.seed = pars.seed;
+  rp.error_type = pars.errorType;
+  rp._pad = 0;
   modsgpu_ransac_result rr;
   int rc = pars.useF ? modsgpu_ransac_F(ctx, u2.data(), tent_size, &rp, Hloran, inl2.data(), &rr)
                      : modsgpu_ransac_H(ctx, u2.data(), tent_size, &rp, Hloran, inl2.data(), &rr);
@@ -660,9 +662,20 @@ int LORANSACFiltering(modsgpu_ctx* ctx, TentativeCorrespListExt& in_corresp, Ten
   ransac_corresp.TCList.reserve(tent_size);
   for (int i = 0; i < tent_size; i++) {
     in_corresp.TCList[i].isTrue = inl2[i];
-    if (inl2[i]) ransac_corresp.TCList.push_back(in_corresp.TCList[i]);
+    // matching.cpp:738-762: justMarkOutliers keeps every tentative in the list and only flags it
+    if (inl2[i] || pars.justMarkOutliers) ransac_corresp.TCList.push_back(in_corresp.TCList[i]);
   }
-  if (pars.useF) {   // matching.cpp:806-820: F_LAF_check (:192-248) with FDs, then F = Hloran as is
+  return EmpiricalChecks(ransac_corresp, Hloran, pars, H);
+}
+
+// The empirical checks at the end of LORANSACFiltering (matching.cpp:764-820) on the list RANSAC returned:
+//   H: model = inv(Hloran^T) (all-zero inverse -> empty list), NaiveHCheck (:1014-1043: fewer than MIN_POINTS
+//      correspondences within 10 px under H and under H^-1 empty the list), H_LAF_check (:250-308) with HDsSymMax on the
+//      three LAF points at 3 * HLAFCoef * err_threshold, fewer than MIN_POINTS survivors empty the list;
+//   F: F_LAF_check (:192-249) with FDs at LAFCoef * err_threshold, same MIN_POINTS rule; model = Hloran as is.
+int EmpiricalChecks(TentativeCorrespListExt& ransac_corresp, const double* Hloran, const RANSACPars& pars, double* H) {
+  const int MIN_POINTS = 8;   // matching.hpp:27
+  if (pars.useF) {
     std::vector<TentativeCorrespExt> checked;
     const double affineFerror = pars.LAFCoef * pars.err_threshold;
     const double k_sigma = 2 * 3.0 * std::sqrt(3.0);
@@ -744,6 +757,32 @@ int MODSPair(modsgpu_ctx* ctx, modsgpu_image* img1, modsgpu_image* img2, const s
 }
 
 }  // namespace modsb200
+
+// host-only seam of the checks above (no device work, callable without a GPU): kp1 / kp2 = reproj_kp of the n
+// correspondences RANSAC kept; model = the degensac-convention H (column-major, image 2 -> 1) or F; keep[i] = survives.
+extern "C" int modsgpu_empirical_checks(const modsgpu_region* kp1, const modsgpu_region* kp2, int n, const double* model, int use_F,
+                                        double err_threshold, double laf_coef, unsigned char* keep, double* model_out, int* n_out) {
+  using namespace modsb200;
+  if (n < 0 || (n > 0 && (!kp1 || !kp2 || !keep)) || !model || !model_out || !n_out) return MODSGPU_EINVAL;
+  TentativeCorrespListExt list;
+  list.TCList.resize(n);
+  auto put = [](AffineKeypoint& k, const modsgpu_region& r) { k.x = r.x; k.y = r.y; k.s = r.s; k.a11 = r.a11; k.a12 = r.a12; k.a21 = r.a21; k.a22 = r.a22; };
+  for (int i = 0; i < n; i++) {
+    put(list.TCList[i].first.reproj_kp, kp1[i]);
+    put(list.TCList[i].second.reproj_kp, kp2[i]);
+    list.TCList[i].first.id = i;      // carries the input index through the filters
+  }
+  RANSACPars pars;
+  pars.useF = use_F;
+  pars.err_threshold = err_threshold;
+  if (use_F) pars.LAFCoef = laf_coef; else pars.HLAFCoef = laf_coef;
+  for (int i = 0; i < 9; i++) model_out[i] = 0;
+  const int m = EmpiricalChecks(list, model, pars, model_out);
+  memset(keep, 0, (size_t)n);
+  for (const auto& c : list.TCList) keep[c.first.id] = 1;
+  *n_out = m;
+  return 0;
+}
 
 // ------------------------------------------------------------------------------------------------------
 // C entry: the whole pair pipeline (what mods.cpp:202-356 does for one iteration of the deep config)

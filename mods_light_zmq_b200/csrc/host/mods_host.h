@@ -71,6 +71,8 @@ struct RANSACPars {                // matching.hpp:132-164
   int doSymmCheck = 1;
   double HLAFCoef = 12.0;
   double LAFCoef = 2.0;            // F branch (matching.cpp:810)
+  int errorType = 0;               // SAMPSON / SYMM_SUM / SYMM_MAX (matching.hpp:86-90) = MODSGPU_ERR_*
+  int justMarkOutliers = 0;        // matching.cpp:751-762: keep every tentative in the output list, only flag isTrue
   int useF = 0;                    // LORANSACF (mods.cpp:325): exp_ransacFcustom instead of exp_ransacHcustom
   unsigned long long seed = 12345; // the reference seeds with time(NULL) (exp_ranH.c:823)
 };
@@ -151,5 +153,7 @@ int MODSPair(modsgpu_ctx* ctx, modsgpu_image* img1, modsgpu_image* img2, const s
 
 int LORANSACFiltering(modsgpu_ctx* ctx, TentativeCorrespListExt& in_corresp, TentativeCorrespListExt& ransac_corresp,
                       double* H, const RANSACPars& pars);
+// the empirical checks at the end of LORANSACFiltering (matching.cpp:764-820); Hloran = the degensac-convention model
+int EmpiricalChecks(TentativeCorrespListExt& ransac_corresp, const double* Hloran, const RANSACPars& pars, double* H);
 
 }  // namespace modsb200

@@ -988,6 +988,9 @@ int mg_ransac_F_run(modsgpu_ctx* ctx, const double* d_u, int T, const modsgpu_ra
 extern "C" int modsgpu_ransac_F(modsgpu_ctx* ctx, const double* u, int T, const modsgpu_ransac_params* p,
                                 double* F, unsigned char* inl, modsgpu_ransac_result* res) {
   if (!ctx || !p || !F || T < 0 || (T > 0 && (!u || !inl))) return MODSGPU_EINVAL;
+  if (p->error_type != MODSGPU_ERR_SAMPSON)
+    MG_FAIL(ctx, MODSGPU_EINVAL, "modsgpu_ransac_F implements the Sampson error (exFDs / FDs) only; the symmetric epipolar "
+                                 "distance (exFDsSym / FDsSym, Ftools.c:103-124, :177-199) is not built");
   if (mg_begin(ctx)) return MODSGPU_ECUDA;
   if (res) memset(res, 0, sizeof(*res));
   for (int i = 0; i < 9; i++) F[i] = 0;

@@ -518,3 +518,121 @@ def describe_view_chain(gray_view, H, orig_w, orig_h, nets, mrSize=5.1962):
     r4, rp4 = r3[src], rp[src]
     d = nets[2](quantize_u8(extract_patches(gray_view, r4, mrSize)))
     return dict(det=r4, reproj=rp4, desc=d, counts=[len(kp), n_affine, len(r4)], aff=aff, ori=ori)
+
+
+# --------------------------------------------------------------------------- batched LO-RANSAC(H) schedule (ransac_batched.c)
+_rb = None
+
+
+def batched_ransac_H(u, th=16.0, conf=0.99, max_samples=1000000, sym_check=1, seed=12345, error_type=0):
+    """The device's batched LO-RANSAC(H) schedule restated on the CPU (oracle/ransac_batched.c): same counter-based
+    generator, batch sizes and reduction orders -> the device's inlier mask and H, bit for bit."""
+    global _rb
+    if _rb is None:
+        path = os.path.join(HERE, "libransac_batched.so")
+        if not os.path.exists(path):
+            build()
+        _rb = C.CDLL(path)
+    u = np.ascontiguousarray(u, np.float64)
+    T = len(u)
+    if T <= 20:
+        max_samples = 1000  # matching.cpp:644-645
+    H = np.zeros(9, np.float64)
+    inl = np.zeros(max(T, 1), np.uint8)
+    resid = np.zeros(max(T, 1), np.float64)
+    stats = np.zeros(4, np.int32)
+    J = C.c_double()
+    _rb.orb_ransac_H(_p(u), T, C.c_double(th), C.c_double(conf), int(max_samples), int(sym_check), C.c_uint64(seed), int(error_type),
+                     _p(H), _p(inl), _p(stats), C.byref(J), _p(resid))
+    return dict(H=H, inl=inl[:T], I=int(stats[0]), samples=int(stats[1]), lo_count=int(stats[2]), oc_rejects=int(stats[3]),
+                J=J.value, resid=resid[:T])
+
+
+# --------------------------------------------------------------------------- LORANSACFiltering's empirical checks
+K_SIGMA = 2 * 3.0 * np.sqrt(3.0)     # matching.cpp (k_sigma of the LAF points)
+
+
+def laf_points(kp1, kp2):
+    """The 18 doubles per correspondence that H_LAF_check / F_LAF_check build (matching.cpp:209-235 / :265-290): the two
+    centres and the two pairs of LAF points x + k_sigma * (a12, a22) * s and x + k_sigma * (a11, a21) * s."""
+    n = len(kp1)
+    u = np.ones((n, 18), np.float64)
+    u[:, 0], u[:, 1] = kp1["x"], kp1["y"]
+    u[:, 3], u[:, 4] = kp2["x"], kp2["y"]
+    u[:, 6] = u[:, 0] + K_SIGMA * kp1["a12"] * kp1["s"]
+    u[:, 7] = u[:, 1] + K_SIGMA * kp1["a22"] * kp1["s"]
+    u[:, 9] = u[:, 3] + K_SIGMA * kp2["a12"] * kp2["s"]
+    u[:, 10] = u[:, 4] + K_SIGMA * kp2["a22"] * kp2["s"]
+    u[:, 12] = u[:, 0] + K_SIGMA * kp1["a11"] * kp1["s"]
+    u[:, 13] = u[:, 1] + K_SIGMA * kp1["a21"] * kp1["s"]
+    u[:, 15] = u[:, 3] + K_SIGMA * kp2["a11"] * kp2["s"]
+    u[:, 16] = u[:, 4] + K_SIGMA * kp2["a21"] * kp2["s"]
+    return u
+
+
+def ref_H_LAF_check(kp1, kp2, Hloran, thresh):
+    """H_LAF_check (matching.cpp:250-308) with the REFERENCE's own HDsSymMax (oracle/_ref): keep mask."""
+    L = ref()
+    u = laf_points(kp1, kp2)
+    Hl = np.ascontiguousarray(Hloran, np.float64)
+    keep = np.ones(len(u), bool)
+    err = np.zeros(3, np.float64)
+    lin = np.zeros(6 * max(len(u), 1), np.float64)
+    if thresh > 0:
+        for i in range(len(u)):
+            row = np.ascontiguousarray(u[i])
+            L.HDsSymMax(_p(lin), _p(row), _p(Hl), _p(err), 3)
+            keep[i] = not (np.sqrt(err[0] + err[1] + err[2]) > thresh)
+    return keep
+
+
+def ref_F_LAF_check(kp1, kp2, F, thresh):
+    """F_LAF_check (matching.cpp:192-249) with the REFERENCE's own FDs (oracle/_ref): keep mask."""
+    L = ref()
+    u = laf_points(kp1, kp2)
+    Fm = np.ascontiguousarray(F, np.float64)
+    keep = np.ones(len(u), bool)
+    err = np.zeros(3, np.float64)
+    if thresh > 0:
+        for i in range(len(u)):
+            row = np.ascontiguousarray(u[i])
+            L.FDs(_p(row), _p(Fm), _p(err), 3)
+            keep[i] = not (np.sqrt(err[0]) + np.sqrt(err[1]) + np.sqrt(err[2]) > thresh)
+    return keep
+
+
+def naive_H_check(kp1, kp2, H, error=10.0):
+    """NaiveHCheck (matching.cpp:1014-1043): number of correspondences within `error` px under H and under inv(H).
+    cv::invert(DECOMP_LU) is third-party; numpy's LU inverse stands in (the decision margin is pixels, not ulps)."""
+    Hm = np.asarray(H, np.float64).reshape(3, 3)
+    Hi = np.linalg.inv(Hm)
+    x1, y1, x2, y2 = kp1["x"], kp1["y"], kp2["x"], kp2["y"]
+    den = Hm[2, 0] * x1 + Hm[2, 1] * y1 + Hm[2, 2]
+    xa, ya = (Hm[0, 0] * x1 + Hm[0, 1] * y1 + Hm[0, 2]) / den, (Hm[1, 0] * x1 + Hm[1, 1] * y1 + Hm[1, 2]) / den
+    d1 = (x2 - xa) ** 2 + (y2 - ya) ** 2
+    den = Hi[2, 0] * x2 + Hi[2, 1] * y2 + Hi[2, 2]
+    xa, ya = (Hi[0, 0] * x2 + Hi[0, 1] * y2 + Hi[0, 2]) / den, (Hi[1, 0] * x2 + Hi[1, 1] * y2 + Hi[1, 2]) / den
+    d2 = (x1 - xa) ** 2 + (y1 - ya) ** 2
+    return int(((d1 <= error * error) & (d2 <= error * error)).sum())
+
+
+def empirical_checks(kp1, kp2, model, use_F, err_threshold=4.0, laf_coef=None):
+    """The tail of LORANSACFiltering (matching.cpp:764-820) on the RANSAC inliers: returns (keep mask, H or F).
+    H branch: H = inv(Hloran^T); NaiveHCheck < 8 empties the list; H_LAF_check at 3*HLAFCoef*err_threshold; < 8
+    survivors empty the list.  F branch: F_LAF_check at LAFCoef*err_threshold."""
+    n = len(kp1)
+    if use_F:
+        keep = ref_F_LAF_check(kp1, kp2, model, (2.0 if laf_coef is None else laf_coef) * err_threshold)
+        if keep.sum() < 8:
+            keep[:] = False
+        return keep, np.asarray(model, np.float64).copy()
+    Hl = np.asarray(model, np.float64).reshape(3, 3)
+    Hout = np.linalg.inv(Hl.T)
+    keep = np.ones(n, bool)
+    if naive_H_check(kp1, kp2, Hout, 10.0) < 8:
+        keep[:] = False
+    k2 = ref_H_LAF_check(kp1, kp2, model, 3.0 * (12.0 if laf_coef is None else laf_coef) * err_threshold)
+    keep &= k2
+    if keep.sum() < 8:
+        keep[:] = False
+    return keep, Hout.ravel()

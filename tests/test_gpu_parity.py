@@ -500,9 +500,25 @@ def test_degensac_link_compat_shim(mg, oracle):
     S = lib.exp_ransacHcustom(p(u), T, C.c_double(16.0), C.c_double(0.99), 1000000, p(H), p(inl), 4, p(data_out), 1,
                               C.c_uint(0), C.byref(resids), None, None, None, 1)
     assert resids.value
+    res = np.frombuffer((C.c_double * T).from_address(resids.value), np.float64).copy()
     libc.free(resids)
     assert S.I == inl.sum() and inl[:150].mean() > 0.93 and data_out[0] >= 50 and data_out[1] >= 1
     assert np.median(_transfer_err(H, u[:150])) < 2.0
+    assert np.array_equal(res <= 16.0, inl.astype(bool)) and res[:150].max() > 0      # *resids = the errors under H
+    # the error-function pointers select the error type (matching.cpp:652-681): the shim exports the reference's names
+    f = lambda name: C.cast(getattr(lib, name), C.c_void_p)
+    H2, inl2 = np.zeros(9), np.zeros(T, np.uint8)
+    S2 = lib.exp_ransacHcustom(p(u), T, C.c_double(16.0), C.c_double(0.99), 1000000, p(H2), p(inl2), 4, p(data_out), 1,
+                               C.c_uint(0), C.byref(resids), f("HDsSymMax"), f("HDsiSymMax"), f("HDsSymidxMax"), 1)
+    res2 = np.frombuffer((C.c_double * T).from_address(resids.value), np.float64).copy()
+    libc.free(resids)
+    assert S2.I == inl2.sum() and inl2[:150].mean() > 0.9 and not np.array_equal(res, res2)
+    # an error function the library does not know: loud failure, EMPTY result (never a silent Sampson run)
+    H3, inl3 = np.ones(9), np.ones(T, np.uint8)
+    S3 = lib.exp_ransacHcustom(p(u), T, C.c_double(16.0), C.c_double(0.99), 1000000, p(H3), p(inl3), 4, p(data_out), 1,
+                               C.c_uint(0), C.byref(resids), C.cast(libc.free, C.c_void_p), None, None, 1)
+    libc.free(resids)
+    assert S3.I == 0 and not inl3.any() and not H3.any()
     uf, _, mask = synth.two_view_correspondences(5, 300, 150)
     F = np.zeros(9)
     inl = np.zeros(300, np.uint8)

@@ -382,6 +382,311 @@ k_conv_umma(const __half* __restrict__ in, size_t in_slots, const __half* __rest
 }
 
 // =================================================================================================
+// conv2 .. conv4 (C1 = 16: AffNet / OriNet) or conv2 .. conv3 (C1 = 32: HardNet++) in ONE kernel: the activation maps
+// between the fused layers never leave the SM.
+//
+// Unfused, every layer round-trips its map through HBM (HardNet conv2 alone: 64 KB in + 64 KB out per patch) and every
+// launch pays its own prologue, weight load and tail wave.  Here a CTA walks over whole PATCHES:
+//   conv2  (C1 -> C1 @ 32x32)    A operand streamed from conv1's map in HBM through a ring of patch-aligned M tiles
+//                                (128 slots + halo per plane, bulk copies), exactly as k_conv_umma does; the epilogue
+//                                writes bias + ReLU + fp16 into the PARITY planes of a shared-memory map A2
+//   conv3  (C1 -> 2C1, stride 2) A operand = A2 in shared memory (four parity groups, unit-stride tap shifts);
+//                                epilogue -> shared-memory map A3 (C1 = 16) or HBM (C1 = 32, last fused layer)
+//   conv4  (2C1 -> 2C1 @ 16x16)  A operand = A3; epilogue -> HBM in the parity layout conv5 reads          (C1 = 16)
+// Roles as in k_conv_umma: warp 0 bulk-copy producer, warp 1 issues every MMA of every layer, warps 2-5 are the epilogue
+// (TMEM lane quarters).  Accumulators are double buffered in TMEM across ALL tiles of all layers, so the MMAs of tile k+1
+// overlap the epilogue of tile k; only at a layer boundary must the MMA warp wait for the map it is about to read
+// (mbarrier a2_full / a3_full: 4 epilogue warps x tiles arrivals, after a generic->async proxy fence).  The epilogue of a
+// later layer is ordered after the MMAs that read the map it overwrites by the accumulator barriers themselves
+// (tcgen05.commit covers every MMA issued before it), so no "empty" barrier exists for A2 / A3.
+// Arithmetic is the unfused path's, tap by tap and k-step by k-step, with the same fp16 rounding points: outputs are
+// bit-identical to k_conv_umma's (tests/test_gpu_parity.py::test_fused_trunk_bit_identical).
+// =================================================================================================
+template <int C1, int NL>
+struct TrunkCfg {
+  static constexpr int PT1 = 33, PP1 = PT1 * PT1, NT1 = (PP1 + 127) / 128, HALO1 = PT1 + 1, TP1 = 128 + 2 * HALO1;
+  static constexpr int PT2 = 17, PP2 = PT2 * PT2, NT2 = (PP2 + 127) / 128, HALO2 = PT2 + 1;
+  static constexpr int CO0 = C1, CO1 = 2 * C1, CO2 = 2 * C1;                 // output channels of conv2 / conv3 / conv4
+  static constexpr int KS0 = C1 / 16, KS1 = C1 / 16, KS2 = 2 * C1 / 16;      // k-steps (input channels / 16)
+  static constexpr int W0_BYTES = 9 * KS0 * 2 * CO0 * 16, W1_BYTES = 9 * KS1 * 2 * CO1 * 16;
+  static constexpr int W2_BYTES = NL == 3 ? 9 * KS2 * 2 * CO2 * 16 : 0;
+  static constexpr int NPL1 = C1 / 8, A1_BYTES = NPL1 * TP1 * 16;            // one ring stage of conv2's input
+  static constexpr int PS2 = HALO2 + PP2, NPL2 = 4 * (C1 / 8);               // A2: parity planes, plane stride in slots
+  static constexpr int A2_BYTES = NPL2 * PS2 * 16 + (NT2 * 128 - PP2) * 16;  // + the overrun of the last tile's garbage rows
+  static constexpr int PS3 = HALO2 + PP2 + HALO2, NPL3 = 2 * C1 / 8;         // A3: normal planes with both halos
+  static constexpr int A3_BYTES = NL == 3 ? NPL3 * PS3 * 16 + (NT2 * 128 - PP2) * 16 : 0;
+  static constexpr int BIAS_BYTES = (CO0 + CO1 + CO2) * 4;
+  static constexpr int NST = C1 == 16 ? 3 : 4;
+  static constexpr int OFF_W0 = 0, OFF_W1 = OFF_W0 + W0_BYTES, OFF_W2 = OFF_W1 + W1_BYTES, OFF_RING = OFF_W2 + W2_BYTES;
+  static constexpr int OFF_A2 = OFF_RING + NST * A1_BYTES, OFF_A3 = OFF_A2 + A2_BYTES, OFF_BIAS = OFF_A3 + A3_BYTES;
+  static constexpr int OFF_BAR = OFF_BIAS + BIAS_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256;
+  static constexpr int NMAX = 2 * C1;                                        // widest accumulator
+  static constexpr int TMEM_COLS = 2 * NMAX <= 64 ? 64 : 128;
+  static_assert(OFF_RING % 16 == 0 && OFF_A2 % 16 == 0 && OFF_A3 % 16 == 0 && OFF_BAR % 8 == 0, "alignment");
+};
+
+template <int C1, int NL>
+__global__ void __launch_bounds__(192, (C1 == 16 ? 2 : 1))
+k_trunk(const __half* __restrict__ in, size_t in_slots, const __half* __restrict__ w0, const float* __restrict__ b0,
+        const __half* __restrict__ w1, const float* __restrict__ b1, const __half* __restrict__ w2, const float* __restrict__ b2,
+        __half* __restrict__ out, size_t out_slots, int np, const int* __restrict__ cnt_dev, int cnt_base) {
+  using Cfg = TrunkCfg<C1, NL>;
+  np = live_patches(np, cnt_dev, cnt_base);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* ring = smem + Cfg::OFF_RING;
+  uint8_t* a2_s = smem + Cfg::OFF_A2;
+  uint8_t* a3_s = smem + Cfg::OFF_A3;
+  float* bias_s = reinterpret_cast<float*>(smem + Cfg::OFF_BIAS);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* w_full = bars;                      // the three weight blocks landed
+  uint64_t* a_full = bars + 1;                  // [NST] ring stage landed
+  uint64_t* a_empty = a_full + Cfg::NST;        // [NST] MMAs reading the stage retired
+  uint64_t* t_full = a_empty + Cfg::NST;        // [2] accumulator ready
+  uint64_t* t_empty = t_full + 2;               // [2] accumulator drained (4 epilogue warps)
+  uint64_t* a2_full = t_empty + 2;              // conv2's map complete in shared memory (4 warps x NT1 tiles per patch)
+  uint64_t* a3_full = a2_full + 1;              // conv3's map complete (4 warps x NT2 tiles per patch)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a3_full + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  const int n_my = (int)blockIdx.x < np ? (np - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  // the resident maps start as zeros: their pad slots are never written afterwards
+  for (int i = threadIdx.x; i < (Cfg::A2_BYTES + Cfg::A3_BYTES) / 16; i += 192) reinterpret_cast<uint4*>(a2_s)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < Cfg::CO0 + Cfg::CO1 + (NL == 3 ? Cfg::CO2 : 0); i += 192)
+    bias_s[i] = i < Cfg::CO0 ? __ldg(b0 + i) : (i < Cfg::CO0 + Cfg::CO1 ? __ldg(b1 + i - Cfg::CO0) : __ldg(b2 + i - Cfg::CO0 - Cfg::CO1));
+  fence_proxy_async();
+  if (threadIdx.x == 0) {
+    mbar_init(w_full, 1);
+    for (int i = 0; i < Cfg::NST; i++) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); }
+    for (int i = 0; i < 2; i++) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 4); }
+    mbar_init(a2_full, 4 * Cfg::NT1);
+    mbar_init(a3_full, 4 * Cfg::NT2);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---- producer: weights once, then conv2's input tiles of every patch of this CTA (patch-aligned M tiles)
+    if (elect_one()) {
+      mbar_expect_tx(w_full, Cfg::W0_BYTES + Cfg::W1_BYTES + Cfg::W2_BYTES);
+      bulk_g2s(smem + Cfg::OFF_W0, w0, Cfg::W0_BYTES, w_full);
+      for (int off = 0; off < Cfg::W1_BYTES; off += 32768)
+        bulk_g2s(smem + Cfg::OFF_W1 + off, reinterpret_cast<const uint8_t*>(w1) + off, min(32768, Cfg::W1_BYTES - off), w_full);
+      if (NL == 3)
+        for (int off = 0; off < Cfg::W2_BYTES; off += 32768)
+          bulk_g2s(smem + Cfg::OFF_W2 + off, reinterpret_cast<const uint8_t*>(w2) + off, min(32768, Cfg::W2_BYTES - off), w_full);
+    }
+    __syncwarp();
+    int s = 0, ph = 0;
+    for (int it = 0; it < n_my; it++) {
+      const size_t patch = (size_t)blockIdx.x + (size_t)it * gridDim.x;
+      for (int t = 0; t < Cfg::NT1; t++) {
+        mbar_wait(a_empty + s, ph ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(a_full + s, Cfg::A1_BYTES);
+          const size_t slot0 = (size_t)FS + patch * Cfg::PP1 + (size_t)t * 128 - Cfg::HALO1;
+          uint8_t* dst = ring + s * Cfg::A1_BYTES;
+#pragma unroll 1
+          for (int pl = 0; pl < Cfg::NPL1; pl++)
+            bulk_g2s(dst + pl * Cfg::TP1 * 16, in + ((size_t)pl * in_slots + slot0) * 8, Cfg::TP1 * 16, a_full + s);
+        }
+        __syncwarp();
+        if (++s == Cfg::NST) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer: per patch conv2's NT1 tiles from the ring, then conv3's (and conv4's) NT2 tiles from the resident maps
+    constexpr uint32_t idesc0 = instr_desc_f16(Cfg::CO0), idesc1 = instr_desc_f16(Cfg::CO1), idesc2 = instr_desc_f16(Cfg::CO2);
+    mbar_wait(w_full, 0);
+    const uint64_t ring_desc = smem_desc(smem_u32(ring), Cfg::TP1 * 16, 128);
+    const uint64_t a2_desc = smem_desc(smem_u32(a2_s), Cfg::PS2 * 16, 128);
+    const uint64_t a3_desc = smem_desc(smem_u32(a3_s), Cfg::PS3 * 16, 128);
+    const uint64_t w0_desc = smem_desc(smem_u32(smem + Cfg::OFF_W0), Cfg::CO0 * 16, 128);
+    const uint64_t w1_desc = smem_desc(smem_u32(smem + Cfg::OFF_W1), Cfg::CO1 * 16, 128);
+    const uint64_t w2_desc = smem_desc(smem_u32(smem + Cfg::OFF_W2), Cfg::CO2 * 16, 128);
+    int s = 0, ph = 0, tc = 0;      // ring stage / phase, running accumulator-tile counter
+    for (int it = 0; it < n_my; it++) {
+      // conv2
+      for (int t = 0; t < Cfg::NT1; t++, tc++) {
+        const int ts = tc & 1, tph = (tc >> 1) & 1;
+        mbar_wait(t_empty + ts, tph ^ 1);
+        mbar_wait(a_full + s, ph);
+        fence_after_sync();
+        const uint64_t a_tile = ring_desc + (uint64_t)((s * Cfg::A1_BYTES) >> 4);
+        const uint32_t d_tmem = tmem_base + ts * Cfg::NMAX;
+        if (elect_one()) {
+#pragma unroll
+          for (int tap = 0; tap < 9; tap++) {
+            const int shift = (tap / 3 - 1) * Cfg::PT1 + (tap % 3 - 1);
+#pragma unroll
+            for (int ks = 0; ks < Cfg::KS0; ks++)
+              mma_f16(d_tmem, a_tile + (uint64_t)((2 * ks) * Cfg::TP1 + Cfg::HALO1 + shift),
+                      w0_desc + (uint64_t)((tap * Cfg::KS0 + ks) * 2 * Cfg::CO0), idesc0, (tap | ks) != 0);
+          }
+          mma_commit(a_empty + s);
+          mma_commit(t_full + ts);
+        }
+        __syncwarp();
+        if (++s == Cfg::NST) { s = 0; ph ^= 1; }
+      }
+      // conv3 (stride 2): four parity groups of A2
+      mbar_wait(a2_full, it & 1);
+      fence_after_sync();
+      for (int t = 0; t < Cfg::NT2; t++, tc++) {
+        const int ts = tc & 1, tph = (tc >> 1) & 1;
+        mbar_wait(t_empty + ts, tph ^ 1);
+        fence_after_sync();
+        const uint32_t d_tmem = tmem_base + ts * Cfg::NMAX;
+        if (elect_one()) {
+#pragma unroll
+          for (int tap = 0; tap < 9; tap++) {
+            const int dy = tap / 3, dx = tap % 3;
+            const int grp = ((dy == 1) ? 0 : 2) + ((dx == 1) ? 0 : 1);
+            const int shift = ((dy == 0) ? -Cfg::PT2 : 0) + ((dx == 0) ? -1 : 0);
+#pragma unroll
+            for (int ks = 0; ks < Cfg::KS1; ks++)
+              mma_f16(d_tmem, a2_desc + (uint64_t)((grp * (C1 / 8) + 2 * ks) * Cfg::PS2 + Cfg::HALO2 + shift + t * 128),
+                      w1_desc + (uint64_t)((tap * Cfg::KS1 + ks) * 2 * Cfg::CO1), idesc1, (tap | ks) != 0);
+          }
+          mma_commit(t_full + ts);
+        }
+        __syncwarp();
+      }
+      if (NL == 3) {
+        // conv4: A3 with both halos
+        mbar_wait(a3_full, it & 1);
+        fence_after_sync();
+        for (int t = 0; t < Cfg::NT2; t++, tc++) {
+          const int ts = tc & 1, tph = (tc >> 1) & 1;
+          mbar_wait(t_empty + ts, tph ^ 1);
+          fence_after_sync();
+          const uint32_t d_tmem = tmem_base + ts * Cfg::NMAX;
+          if (elect_one()) {
+#pragma unroll
+            for (int tap = 0; tap < 9; tap++) {
+              const int shift = (tap / 3 - 1) * Cfg::PT2 + (tap % 3 - 1);
+#pragma unroll
+              for (int ks = 0; ks < Cfg::KS2; ks++)
+                mma_f16(d_tmem, a3_desc + (uint64_t)((2 * ks) * Cfg::PS3 + Cfg::HALO2 + shift + t * 128),
+                        w2_desc + (uint64_t)((tap * Cfg::KS2 + ks) * 2 * Cfg::CO2), idesc2, (tap | ks) != 0);
+            }
+            mma_commit(t_full + ts);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ---- epilogue warps 2..5: the same tile sequence; TMEM -> bias + ReLU -> fp16 -> the next layer's operand
+    const int q = warp & 3, m = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    int tc = 0;
+    for (int it = 0; it < n_my; it++) {
+      const size_t patch = (size_t)blockIdx.x + (size_t)it * gridDim.x;
+      // conv2 -> A2 (parity planes in shared memory)
+      for (int t = 0; t < Cfg::NT1; t++, tc++) {
+        const int ts = tc & 1, tph = (tc >> 1) & 1;
+        const int idx = t * 128 + m;
+        const int yy = idx / Cfg::PT1, x = idx - yy * Cfg::PT1, y = yy - 1;
+        const bool valid = idx < Cfg::PP1 && yy >= 1 && x < 32;
+        const int oslot = ((y >> 1) + 1) * Cfg::PT2 + (x >> 1);
+        const int oplane0 = (((y & 1) << 1) | (x & 1)) * (Cfg::CO0 / 8);
+        mbar_wait(t_full + ts, tph);
+        fence_after_sync();
+#pragma unroll
+        for (int cc = 0; cc < Cfg::CO0 / 16; cc++) {
+          float v[16];
+          tmem_ld16(lane_base + ts * Cfg::NMAX + cc * 16, v);
+          if (valid) {
+            uint32_t h[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) h[e] = relu_pack_h2(v[2 * e] + bias_s[cc * 16 + 2 * e], v[2 * e + 1] + bias_s[cc * 16 + 2 * e + 1]);
+            uint8_t* o = a2_s + ((size_t)(oplane0 + cc * 2) * Cfg::PS2 + Cfg::HALO2 + oslot) * 16;
+            *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(o + Cfg::PS2 * 16) = make_uint4(h[4], h[5], h[6], h[7]);
+          }
+        }
+        fence_before_sync();
+        fence_proxy_async();          // the stores above are read by tcgen05.mma (async proxy)
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(t_empty + ts); mbar_arrive(a2_full); }
+      }
+      // conv3 -> A3 (shared memory, C1 = 16) or HBM (C1 = 32)
+      for (int t = 0; t < Cfg::NT2; t++, tc++) {
+        const int ts = tc & 1, tph = (tc >> 1) & 1;
+        const int idx = t * 128 + m;
+        const int yy = idx / Cfg::PT2, x = idx - yy * Cfg::PT2;
+        const bool valid = idx < Cfg::PP2 && yy >= 1 && x < 16;
+        mbar_wait(t_full + ts, tph);
+        fence_after_sync();
+#pragma unroll
+        for (int cc = 0; cc < Cfg::CO1 / 16; cc++) {
+          float v[16];
+          tmem_ld16(lane_base + ts * Cfg::NMAX + cc * 16, v);
+          if (valid) {
+            uint32_t h[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++)
+              h[e] = relu_pack_h2(v[2 * e] + bias_s[Cfg::CO0 + cc * 16 + 2 * e], v[2 * e + 1] + bias_s[Cfg::CO0 + cc * 16 + 2 * e + 1]);
+            if (NL == 3) {
+              uint8_t* o = a3_s + ((size_t)(cc * 2) * Cfg::PS3 + Cfg::HALO2 + idx) * 16;
+              *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
+              *reinterpret_cast<uint4*>(o + Cfg::PS3 * 16) = make_uint4(h[4], h[5], h[6], h[7]);
+            } else {
+              __half* o = out + ((size_t)(cc * 2) * out_slots + (size_t)FS + patch * Cfg::PP2 + idx) * 8;
+              *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
+              *reinterpret_cast<uint4*>(o + out_slots * 8) = make_uint4(h[4], h[5], h[6], h[7]);
+            }
+          }
+        }
+        fence_before_sync();
+        if (NL == 3) fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(t_empty + ts); if (NL == 3) mbar_arrive(a3_full); }
+      }
+      if (NL == 3) {
+        // conv4 -> HBM, parity layout of the 8x8 stride-2 layer that follows (k_conv_umma OUT_PARITY with S = 16)
+        for (int t = 0; t < Cfg::NT2; t++, tc++) {
+          const int ts = tc & 1, tph = (tc >> 1) & 1;
+          const int idx = t * 128 + m;
+          const int yy = idx / Cfg::PT2, x = idx - yy * Cfg::PT2, y = yy - 1;
+          const bool valid = idx < Cfg::PP2 && yy >= 1 && x < 16;
+          const size_t oslot = (size_t)FS + patch * 81 + ((y >> 1) + 1) * 9 + (x >> 1);
+          const int oplane0 = (((y & 1) << 1) | (x & 1)) * (Cfg::CO2 / 8);
+          mbar_wait(t_full + ts, tph);
+          fence_after_sync();
+#pragma unroll
+          for (int cc = 0; cc < Cfg::CO2 / 16; cc++) {
+            float v[16];
+            tmem_ld16(lane_base + ts * Cfg::NMAX + cc * 16, v);
+            if (valid) {
+              uint32_t h[8];
+#pragma unroll
+              for (int e = 0; e < 8; e++)
+                h[e] = relu_pack_h2(v[2 * e] + bias_s[Cfg::CO0 + Cfg::CO1 + cc * 16 + 2 * e], v[2 * e + 1] + bias_s[Cfg::CO0 + Cfg::CO1 + cc * 16 + 2 * e + 1]);
+              __half* o = out + ((size_t)(oplane0 + cc * 2) * out_slots + oslot) * 8;
+              *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
+              *reinterpret_cast<uint4*>(o + out_slots * 8) = make_uint4(h[4], h[5], h[6], h[7]);
+            }
+          }
+          fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(t_empty + ts);
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// =================================================================================================
 // conv1 + conv2 fused: the 1 -> C1 first layer never leaves the SM.
 //
 //   loader (1 warp)      : bulk copies of the normalised pixels a tile touches, 8 tiles ahead
@@ -1013,6 +1318,34 @@ int launch_conv(modsgpu_ctx* ctx, const __half* in, size_t in_slots, const ConvW
 }
 
 
+// conv2..conv4 (C1 = 16) / conv2..conv3 (C1 = 32) in one launch (k_trunk).  MODSGPU_NO_FUSED_TRUNK=1 keeps the layer-by-layer
+// path (the parity test runs both and compares them bit for bit).
+bool fused_trunk_enabled() {      // read per call: the parity test switches paths inside one process
+  const char* e = getenv("MODSGPU_NO_FUSED_TRUNK");
+  return !(e && atoi(e) != 0);
+}
+template <int C1, int NL>
+int launch_trunk(modsgpu_ctx* ctx, const __half* in, size_t in_slots, const ConvW* w /* conv2.. */, __half* out, size_t out_slots,
+                 int np, int patch_base, const int* cnt_dev) {
+  using Cfg = TrunkCfg<C1, NL>;
+  auto kern = k_trunk<C1, NL>;
+  static OnceFlags attr;
+  if (attr.need(ctx->device)) {
+    MG_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr.set(ctx->device);
+  }
+  static char pname[64] = {0};
+  if (!pname[0]) snprintf(pname, sizeof(pname), "k_trunk<%d,conv2-%d>", C1, NL + 1);
+  const double macs = 1024.0 * 9 * C1 * C1 + 256.0 * 9 * C1 * 2 * C1 + (NL == 3 ? 256.0 * 9 * 2 * C1 * 2 * C1 : 0.0);
+  // algorithmic bytes: conv1's map in, the last fused layer's map out
+  MG_PROF2(ctx, pname, 1, 2.0 * np * macs, 2.0 * np * (1024.0 * C1 + 256.0 * 2 * C1));
+  const int ctas = ctx->num_sms * (C1 == 16 ? 2 : 1);
+  kern<<<std::min(np, ctas), 192, Cfg::SMEM_BYTES, ctx->stream>>>(in, in_slots, w[0].w, w[0].b, w[1].w, w[1].b, NL == 3 ? w[2].w : nullptr,
+                                                                  NL == 3 ? w[2].b : nullptr, out, out_slots, np, cnt_dev, patch_base);
+  MG_LAUNCHED(ctx);
+  return 0;
+}
+
 // conv1 + conv2 in one launch (k_conv12).  EXPERIMENTAL, opt-in with MODSGPU_FUSED_CONV12=1: parity-green but slower on
 // B200 than k_conv1 + k_conv_umma (profiles/r01_conv12_stalls.txt has the three variants and their stall tables).
 bool fused_conv12_enabled() {
@@ -1195,9 +1528,14 @@ int mg_net_forward_enqueue(modsgpu_ctx* ctx, modsgpu_net net, const uint8_t* d_p
         MG_PROF2(ctx, "k_conv1<32>", 1, 2.0 * np * 1024 * 9 * 32, (double)np * (1024.0 + 1024.0 * 32 * 2));
         k_conv1<32><<<std::min(np, 3 * ctx->num_sms), 160, 0, ctx->stream>>>(pin, np, nw->c1_w, nw->c1_b, nw->act[0], nw->slots[0], cnt_dev, p0);
         MG_LAUNCHED(ctx);
-        if ((rc = launch_conv<32, 32, 1, 32, 1, OUT_PARITY>(ctx, nw->act[0], nw->slots[0], nw->conv[0], nw->act[1], nw->slots[1], np, p0, cnt_dev))) return rc;
+        if (fused_trunk_enabled()) {
+          if ((rc = launch_trunk<32, 2>(ctx, nw->act[0], nw->slots[0], nw->conv, nw->act[2], nw->slots[2], np, p0, cnt_dev))) return rc;
+        } else {
+          if ((rc = launch_conv<32, 32, 1, 32, 1, OUT_PARITY>(ctx, nw->act[0], nw->slots[0], nw->conv[0], nw->act[1], nw->slots[1], np, p0, cnt_dev))) return rc;
+        }
       }
-      if ((rc = launch_conv<32, 64, 1, 16, 4, OUT_NORMAL>(ctx, nw->act[1], nw->slots[1], nw->conv[1], nw->act[2], nw->slots[2], np, p0, cnt_dev))) return rc;
+      if (nw->fused12 || !fused_trunk_enabled())
+        if ((rc = launch_conv<32, 64, 1, 16, 4, OUT_NORMAL>(ctx, nw->act[1], nw->slots[1], nw->conv[1], nw->act[2], nw->slots[2], np, p0, cnt_dev))) return rc;
       if ((rc = launch_conv<64, 64, 1, 16, 1, OUT_PARITY>(ctx, nw->act[2], nw->slots[2], nw->conv[2], nw->act[3], nw->slots[3], np, p0, cnt_dev))) return rc;
       if ((rc = launch_conv<64, 64, 2, 8, 4, OUT_NORMAL>(ctx, nw->act[3], nw->slots[3], nw->conv[3], nw->act[4], nw->slots[4], np, p0, cnt_dev))) return rc;
       if ((rc = launch_conv<128, 64, 2, 8, 1, OUT_GEMM>(ctx, nw->act[4], nw->slots[4], nw->conv[4], act6all, (size_t)m_pad, np, p0, cnt_dev))) return rc;
@@ -1209,10 +1547,16 @@ int mg_net_forward_enqueue(modsgpu_ctx* ctx, modsgpu_net net, const uint8_t* d_p
         MG_PROF2(ctx, "k_conv1<16>", 1, 2.0 * np * 1024 * 9 * 16, (double)np * (1024.0 + 1024.0 * 16 * 2));
         k_conv1<16><<<std::min(np, 3 * ctx->num_sms), 160, 0, ctx->stream>>>(pin, np, nw->c1_w, nw->c1_b, nw->act[0], nw->slots[0], cnt_dev, p0);
         MG_LAUNCHED(ctx);
-        if ((rc = launch_conv<16, 16, 1, 32, 1, OUT_PARITY>(ctx, nw->act[0], nw->slots[0], nw->conv[0], nw->act[1], nw->slots[1], np, p0, cnt_dev))) return rc;
+        if (fused_trunk_enabled()) {
+          if ((rc = launch_trunk<16, 3>(ctx, nw->act[0], nw->slots[0], nw->conv, nw->act[3], nw->slots[3], np, p0, cnt_dev))) return rc;
+        } else {
+          if ((rc = launch_conv<16, 16, 1, 32, 1, OUT_PARITY>(ctx, nw->act[0], nw->slots[0], nw->conv[0], nw->act[1], nw->slots[1], np, p0, cnt_dev))) return rc;
+        }
       }
-      if ((rc = launch_conv<16, 32, 1, 16, 4, OUT_NORMAL>(ctx, nw->act[1], nw->slots[1], nw->conv[1], nw->act[2], nw->slots[2], np, p0, cnt_dev))) return rc;
-      if ((rc = launch_conv<32, 32, 1, 16, 1, OUT_PARITY>(ctx, nw->act[2], nw->slots[2], nw->conv[2], nw->act[3], nw->slots[3], np, p0, cnt_dev))) return rc;
+      if (nw->fused12 || !fused_trunk_enabled()) {
+        if ((rc = launch_conv<16, 32, 1, 16, 4, OUT_NORMAL>(ctx, nw->act[1], nw->slots[1], nw->conv[1], nw->act[2], nw->slots[2], np, p0, cnt_dev))) return rc;
+        if ((rc = launch_conv<32, 32, 1, 16, 1, OUT_PARITY>(ctx, nw->act[2], nw->slots[2], nw->conv[2], nw->act[3], nw->slots[3], np, p0, cnt_dev))) return rc;
+      }
       if ((rc = launch_conv<32, 64, 1, 8, 4, OUT_NORMAL>(ctx, nw->act[3], nw->slots[3], nw->conv[3], nw->act[4], nw->slots[4], np, p0, cnt_dev))) return rc;
       if ((rc = launch_conv<64, 64, 1, 8, 1, OUT_NORMAL>(ctx, nw->act[4], nw->slots[4], nw->conv[4], nw->act[5], nw->slots[5], np, p0, cnt_dev))) return rc;
       static OnceFlags hattr;

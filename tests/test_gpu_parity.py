@@ -531,6 +531,26 @@ def test_degensac_link_compat_shim(mg, oracle):
     assert I == inl.sum() and (inl.astype(bool) & mask).sum() > 0.93 * 150
 
 
+def test_fused_trunk_bit_identical(mg):
+    """k_trunk (conv2..conv4 of AffNet / OriNet, conv2..conv3 of HardNet++ with the maps between them resident in shared
+    memory) performs the layer-by-layer path's arithmetic tap by tap with the same fp16 rounding points: the net outputs
+    must be BIT-identical, for patch counts that end inside a tile, fill several CTAs per SM or leave most CTAs idle."""
+    import mods_light_zmq_b200 as M
+    rng = np.random.RandomState(11)
+    for n in (1, 7, 300, 1500):
+        patches = rng.randint(0, 256, (n, 32, 32)).astype(np.uint8)
+        patches[n // 2] = 128                 # a flat patch (std = 0 -> all-equal normalised input)
+        for net in (M.AFFNET, M.ORINET, M.HARDNET):
+            fused = mg.net_forward_u8(net, patches)
+            try:
+                os.environ["MODSGPU_NO_FUSED_TRUNK"] = "1"
+                plain = mg.net_forward_u8(net, patches)
+            finally:
+                os.environ.pop("MODSGPU_NO_FUSED_TRUNK", None)
+            assert fused.tobytes() == plain.tobytes(), (n, net, float(np.abs(fused - plain).max()))
+            assert np.isfinite(fused).all()
+
+
 # ------------------------------------------------------------------------------------------ whole pair (config 3)
 def test_pair_pipeline_config3(mg, oracle, synth_pair):
     """BASELINE config 3: single 1024x768 pair, Hessian-AffNet-OriNet-HardNet++ + linear FGINN + LO-RANSAC(H),

@@ -281,6 +281,36 @@ int  modsgpu_pair_pipeline_classic_images(modsgpu_ctx* ctx, modsgpu_image* img1,
 /* host BGR images (cv::imread layout): upload + pipeline */
 int  modsgpu_pair_pipeline(modsgpu_ctx* ctx, const uint8_t* bgr1, const uint8_t* bgr2, int w, int h,
                            unsigned long long seed, modsgpu_pair_result* res, double* inlier_xy, int capacity);
+/* ---- the parameter block of the pair-level entry points: what the reference reads from its ini files into
+ *      PyramidParams (structures.hpp:114-151, [HessianAffine]), MatchPars (matching.hpp:97-130, [Matching] + the
+ *      FGINNThreshold of the iters file) and RANSACPars (matching.hpp:132-164, [RANSAC]).  modsgpu_default_pipeline_params
+ *      fills the values of build/config_aff_ori_desc_zeromq.ini + iters_HessianZMQ.ini; the entry points above without a
+ *      parameter block use exactly those. ------------------------------------------------------------------------------ */
+typedef struct {
+  modsgpu_pyr_params pyr;          /* [HessianAffine] */
+  double mrSize;                   /* 5.1962 : patch extent of AffNet / OriNet / descriptor */
+  int    patchSize, _pad0;         /* 32 */
+  /* MatchPars */
+  double fginn_threshold;          /* 0.8  FGINNThreshold (iters file, per descriptor) */
+  double contrad_dist;             /* 10   contradDist */
+  double dup_filter_radius;        /* 2    DuplicateFiltering radius (mods.cpp:283) */
+  int    nn, _pad1;                /* 50   neighbours per query */
+  /* RANSACPars */
+  double err_threshold;            /* 4    pixels (degensac gets its square) */
+  double confidence;               /* 0.99 */
+  double HLAFCoef, LAFCoef;        /* 12, 2 */
+  int    max_samples;              /* 1e6 */
+  int    do_symm_check;            /* 1 */
+  int    error_type;               /* MODSGPU_ERR_SAMPSON */
+  int    just_mark_outliers;       /* 0 */
+  int    use_F, _pad2;             /* 0: LORANSAC (H), 1: LORANSACF */
+  uint64_t seed;                   /* the reference seeds with time(NULL) */
+} modsgpu_pipeline_params;
+void modsgpu_default_pipeline_params(modsgpu_pipeline_params* p);
+/* modsgpu_pair_pipeline_images / modsgpu_mods_pair with every threshold of the run passed by the caller */
+int  modsgpu_pair_pipeline_images_ex(modsgpu_ctx* ctx, modsgpu_image* img1, modsgpu_image* img2, const modsgpu_pipeline_params* p,
+                                     modsgpu_pair_result* res, double* inlier_xy, int capacity);
+
 /* ---- one image -> described regions (what extract_features_batch.cpp:128-139 does per image for the deep
  *      configuration: ImageRepresentation::SynthDetectDescribeKeypoints, identity view) and the OxAff writer
  *      (ImageRepresentation::SaveRegionsMichal text mode -> saveAR_KM_format, imagerepresentation.cpp:113-126,
@@ -334,6 +364,9 @@ typedef struct {
 int  modsgpu_mods_pair(modsgpu_ctx* ctx, modsgpu_image* img1, modsgpu_image* img2, const modsgpu_mods_step* steps,
                        int n_steps, int min_matches, int use_F, unsigned long long seed, modsgpu_mods_result* res,
                        double* inlier_xy, int capacity);
+/* the same with the run's parameter block (detector, matcher and RANSAC settings; p->use_F selects LORANSACF) */
+int  modsgpu_mods_pair_ex(modsgpu_ctx* ctx, modsgpu_image* img1, modsgpu_image* img2, const modsgpu_mods_step* steps, int n_steps,
+                          int min_matches, const modsgpu_pipeline_params* p, modsgpu_mods_result* res, double* inlier_xy, int capacity);
 
 /* ---- pre-extracted regions (`read_pre_extracted`, mods.cpp:216-229): the reference re-loads region files instead of
  *      detecting, then matches them.  Readers (host only, *out malloc()ed -> modsgpu_free):

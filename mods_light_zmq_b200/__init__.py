@@ -58,6 +58,22 @@ class PairResult(C.Structure):
                 ("tentatives", C.c_int), ("unique_tentatives", C.c_int), ("inliers", C.c_int), ("H", C.c_double * 9)]
 
 
+class PipelineParams(C.Structure):
+    """modsgpu_pipeline_params: PyramidParams + MatchPars + RANSACPars of one run"""
+    _fields_ = [("pyr", PyrParams), ("mrSize", C.c_double), ("patchSize", C.c_int), ("_pad0", C.c_int),
+                ("fginn_threshold", C.c_double), ("contrad_dist", C.c_double), ("dup_filter_radius", C.c_double),
+                ("nn", C.c_int), ("_pad1", C.c_int),
+                ("err_threshold", C.c_double), ("confidence", C.c_double), ("HLAFCoef", C.c_double), ("LAFCoef", C.c_double),
+                ("max_samples", C.c_int), ("do_symm_check", C.c_int), ("error_type", C.c_int), ("just_mark_outliers", C.c_int),
+                ("use_F", C.c_int), ("_pad2", C.c_int), ("seed", C.c_uint64)]
+
+
+def default_pipeline_params():
+    p = PipelineParams()
+    load_library().modsgpu_default_pipeline_params(C.byref(p))
+    return p
+
+
 class ModsStep(C.Structure):
     _fields_ = [("scale_set", C.c_double * 8), ("n_scales", C.c_int), ("tilt_set", C.c_double * 8), ("n_tilts", C.c_int),
                 ("phi", C.c_double), ("init_sigma", C.c_double), ("fginn_threshold", C.c_double), ("do_blur", C.c_int),
@@ -516,6 +532,14 @@ def _pair_pipeline_images(self, img1, img2, seed=12345, capacity=4096):
     return _pair_dict(res, xy)
 
 
+def _pair_pipeline_images_ex(self, img1, img2, params, capacity=4096):
+    """modsgpu_pair_pipeline_images_ex: the deep pair pipeline with the run's parameter block"""
+    res = PairResult()
+    xy = np.zeros((capacity, 4), np.float64)
+    self._check(self.lib.modsgpu_pair_pipeline_images_ex(self.ctx, img1.handle, img2.handle, C.byref(params), C.byref(res), _p(xy), capacity))
+    return _pair_dict(res, xy)
+
+
 def _pair_pipeline_classic_images(self, img1, img2, seed=12345, capacity=4096):
     res = PairResult()
     xy = np.zeros((capacity, 4), np.float64)
@@ -536,6 +560,7 @@ def _pair_pipeline(self, bgr1, bgr2, seed=12345, capacity=4096):
 
 ModsGpu.pair_pipeline_images = _pair_pipeline_images
 ModsGpu.pair_pipeline_classic_images = _pair_pipeline_classic_images
+ModsGpu.pair_pipeline_images_ex = _pair_pipeline_images_ex
 ModsGpu.pair_pipeline = _pair_pipeline
 
 

@@ -722,9 +722,13 @@ int EmpiricalChecks(TentativeCorrespListExt& ransac_corresp, const double* Hlora
 // mods.cpp:202-356, HessianAffine steps only (MSER and the other detectors stay on the reference's CPU path)
 int MODSPair(modsgpu_ctx* ctx, modsgpu_image* img1, modsgpu_image* img2, const std::vector<IterationStep>& steps,
              int minMatches, const RANSACPars& rp, MODSResult& res, TentativeCorrespListExt& verified) {
+  return MODSPair(ctx, img1, img2, steps, minMatches, DetectPars(), MatchPars(), rp, res, verified);
+}
+int MODSPair(modsgpu_ctx* ctx, modsgpu_image* img1, modsgpu_image* img2, const std::vector<IterationStep>& steps,
+             int minMatches, const DetectPars& dp, const MatchPars& mp0, const RANSACPars& rp, MODSResult& res,
+             TentativeCorrespListExt& verified) {
   res = MODSResult();
   verified.TCList.clear();
-  DetectPars dp;
   ImageRepresentation r1(ctx, img1, false), r2(ctx, img2, false);
   std::vector<ViewSynthParameters> hist;   // SetVSPars history: a view is synthesised once per run
   int curr_matches = 0;
@@ -739,7 +743,7 @@ int MODSPair(modsgpu_ctx* ctx, modsgpu_image* img1, modsgpu_image* img2, const s
     res.steps_done = (int)step + 1;
     res.views[0] = r1.n_views; res.views[1] = r2.n_views;
     res.regions[0] = (int)r1.GetAffineRegionVector().size(); res.regions[1] = (int)r2.GetAffineRegionVector().size();
-    MatchPars mp;
+    MatchPars mp = mp0;
     mp.FGINNThreshold = st.FGINNThreshold;
     TentativeCorrespListExt tent;
     int nt = MatchFlannFGINN(ctx, r1.GetAffineRegionVector(), r2.GetAffineRegionVector(), tent, mp);
@@ -787,16 +791,44 @@ extern "C" int modsgpu_empirical_checks(const modsgpu_region* kp1, const modsgpu
 // ------------------------------------------------------------------------------------------------------
 // C entry: the whole pair pipeline (what mods.cpp:202-356 does for one iteration of the deep config)
 // ------------------------------------------------------------------------------------------------------
+static void unpack_params(const modsgpu_pipeline_params* p, modsb200::DetectPars& dp, modsb200::MatchPars& mp, modsb200::RANSACPars& rp) {
+  dp.pyr = p->pyr; dp.mrSize = p->mrSize; dp.patchSize = p->patchSize;
+  mp.FGINNThreshold = p->fginn_threshold; mp.contradDist = p->contrad_dist; mp.nn = p->nn; mp.doubleFilteringRadius = p->dup_filter_radius;
+  rp.err_threshold = p->err_threshold; rp.confidence = p->confidence; rp.max_samples = p->max_samples; rp.doSymmCheck = p->do_symm_check;
+  rp.HLAFCoef = p->HLAFCoef; rp.LAFCoef = p->LAFCoef; rp.errorType = p->error_type; rp.justMarkOutliers = p->just_mark_outliers;
+  rp.useF = p->use_F; rp.seed = p->seed;
+}
+extern "C" void modsgpu_default_pipeline_params(modsgpu_pipeline_params* p) {
+  if (!p) return;
+  memset(p, 0, sizeof(*p));
+  const modsb200::DetectPars dp;
+  const modsb200::MatchPars mp;
+  const modsb200::RANSACPars rp;
+  p->pyr = dp.pyr; p->mrSize = dp.mrSize; p->patchSize = dp.patchSize;
+  p->fginn_threshold = mp.FGINNThreshold; p->contrad_dist = mp.contradDist; p->dup_filter_radius = mp.doubleFilteringRadius; p->nn = mp.nn;
+  p->err_threshold = rp.err_threshold; p->confidence = rp.confidence; p->HLAFCoef = rp.HLAFCoef; p->LAFCoef = rp.LAFCoef;
+  p->max_samples = rp.max_samples; p->do_symm_check = rp.doSymmCheck; p->error_type = rp.errorType;
+  p->just_mark_outliers = rp.justMarkOutliers; p->use_F = rp.useF; p->seed = rp.seed;
+}
 extern "C" int modsgpu_pair_pipeline_images(modsgpu_ctx* ctx, modsgpu_image* img1, modsgpu_image* img2,
                                             unsigned long long seed, modsgpu_pair_result* res,
                                             double* inlier_xy /* capacity*4 or NULL */, int capacity) {
+  modsgpu_pipeline_params p;
+  modsgpu_default_pipeline_params(&p);
+  p.seed = seed;
+  return modsgpu_pair_pipeline_images_ex(ctx, img1, img2, &p, res, inlier_xy, capacity);
+}
+extern "C" int modsgpu_pair_pipeline_images_ex(modsgpu_ctx* ctx, modsgpu_image* img1, modsgpu_image* img2,
+                                               const modsgpu_pipeline_params* pp, modsgpu_pair_result* res,
+                                               double* inlier_xy /* capacity*4 or NULL */, int capacity) {
   using namespace modsb200;
-  if (!ctx || !img1 || !img2 || !res) return MODSGPU_EINVAL;
+  if (!ctx || !img1 || !img2 || !res || !pp) return MODSGPU_EINVAL;
+  if (pp->patchSize != 32 || !(pp->err_threshold > 0) || pp->nn < 2 || pp->nn > 50) return MODSGPU_EINVAL;
   memset(res, 0, sizeof(*res));
   DetectPars dp;
   MatchPars mp;
   RANSACPars rp;
-  rp.seed = seed;
+  unpack_params(pp, dp, mp, rp);
   const bool hp = host_profile();
   double c[6] = {0, 0, 0, 0, 0, 0}, w[6] = {0, 0, 0, 0, 0, 0};
   auto mark = [&](int i) { if (hp) { c[i] = cpu_ms(); w[i] = now_ms(); } };
@@ -1147,8 +1179,16 @@ extern "C" int modsgpu_match_features(modsgpu_ctx* ctx, const modsgpu_feature* f
 extern "C" int modsgpu_mods_pair(modsgpu_ctx* ctx, modsgpu_image* img1, modsgpu_image* img2, const modsgpu_mods_step* steps,
                                  int n_steps, int min_matches, int use_F, unsigned long long seed, modsgpu_mods_result* res,
                                  double* inlier_xy, int capacity) {
+  modsgpu_pipeline_params p;
+  modsgpu_default_pipeline_params(&p);
+  p.seed = seed; p.use_F = use_F;
+  return modsgpu_mods_pair_ex(ctx, img1, img2, steps, n_steps, min_matches, &p, res, inlier_xy, capacity);
+}
+extern "C" int modsgpu_mods_pair_ex(modsgpu_ctx* ctx, modsgpu_image* img1, modsgpu_image* img2, const modsgpu_mods_step* steps,
+                                    int n_steps, int min_matches, const modsgpu_pipeline_params* pp, modsgpu_mods_result* res,
+                                    double* inlier_xy, int capacity) {
   using namespace modsb200;
-  if (!ctx || !img1 || !img2 || !res || n_steps < 0 || (n_steps > 0 && !steps)) return MODSGPU_EINVAL;
+  if (!ctx || !img1 || !img2 || !res || !pp || n_steps < 0 || (n_steps > 0 && !steps)) return MODSGPU_EINVAL;
   std::vector<IterationStep> st((size_t)n_steps);
   for (int i = 0; i < n_steps; i++) {
     if (steps[i].n_scales < 0 || steps[i].n_scales > 8 || steps[i].n_tilts < 0 || steps[i].n_tilts > 8) return MODSGPU_EINVAL;
@@ -1157,11 +1197,13 @@ extern "C" int modsgpu_mods_pair(modsgpu_ctx* ctx, modsgpu_image* img1, modsgpu_
     st[i].Phi = steps[i].phi; st[i].initSigma = steps[i].init_sigma; st[i].FGINNThreshold = steps[i].fginn_threshold;
     st[i].doBlur = steps[i].do_blur;
   }
+  DetectPars dp;
+  MatchPars mp;
   RANSACPars rp;
-  rp.seed = seed; rp.useF = use_F;
+  unpack_params(pp, dp, mp, rp);
   MODSResult r;
   TentativeCorrespListExt verified;
-  int rc = MODSPair(ctx, img1, img2, st, min_matches, rp, r, verified);
+  int rc = MODSPair(ctx, img1, img2, st, min_matches, dp, mp, rp, r, verified);
   if (rc) return rc;
   res->steps_done = r.steps_done;
   for (int k = 0; k < 2; k++) { res->views[k] = r.views[k]; res->regions[k] = r.regions[k]; }

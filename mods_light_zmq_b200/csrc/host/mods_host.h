@@ -150,6 +150,9 @@ struct IterationStep { std::vector<double> ScaleSet, TiltSet; double Phi = 360, 
 struct MODSResult { int steps_done = 0, views[2] = {0, 0}, regions[2] = {0, 0}, tentatives = 0, unique_tentatives = 0, inliers = 0; double model[9] = {0}; };
 int MODSPair(modsgpu_ctx* ctx, modsgpu_image* img1, modsgpu_image* img2, const std::vector<IterationStep>& steps,
              int minMatches, const RANSACPars& rp, MODSResult& res, TentativeCorrespListExt& verified);
+int MODSPair(modsgpu_ctx* ctx, modsgpu_image* img1, modsgpu_image* img2, const std::vector<IterationStep>& steps,
+             int minMatches, const DetectPars& dp, const MatchPars& mp, const RANSACPars& rp, MODSResult& res,
+             TentativeCorrespListExt& verified);
 
 int LORANSACFiltering(modsgpu_ctx* ctx, TentativeCorrespListExt& in_corresp, TentativeCorrespListExt& ransac_corresp,
                       double* H, const RANSACPars& pars);

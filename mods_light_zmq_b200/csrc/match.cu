@@ -190,12 +190,22 @@ k_select_fginn(const float* __restrict__ D, int nt, int nt_pad, int nn, const do
         const int ij = (int)(top[j] & 0xffffffffu);
         const float dj = (float)(unsigned)(top[j] >> 32);
         const double ratio = (double)(d0 / dj);
+        const double dx = txy[2 * i0] - txy[2 * ij], dy = txy[2 * i0 + 1] - txy[2 * ij + 1];
+        const bool contradictive = dx * dx + dy * dy > contrDistSq;
+        if (sqminratio >= 1.0) {
+          // matching.cpp:395-428 ("to get all points"): every query yields a correspondence -- with its first
+          // geometrically inconsistent neighbour, or with the last neighbour of the list
+          if (j == nn - 1 || contradictive) {
+            mt.qi = q_base + q; mt.ti = i0; mt.tj_bad = ij; mt.d1 = d0; mt.d2 = dj; mt.ratio = sqrt(ratio);
+            break;
+          }
+          continue;
+        }
         if (ratio <= sqminratio) {
           mt.qi = q_base + q; mt.ti = i0; mt.tj_bad = ij; mt.d1 = d0; mt.d2 = dj; mt.ratio = sqrt(ratio);
           break;
         }
-        const double dx = txy[2 * i0] - txy[2 * ij], dy = txy[2 * i0 + 1] - txy[2 * ij + 1];
-        if (dx * dx + dy * dy > contrDistSq) break;
+        if (contradictive) break;
       }
     }
     matches[q_base + q] = mt;
@@ -316,7 +326,9 @@ k_dup_resolve(const unsigned* __restrict__ conf, const int* __restrict__ rowflag
 // Results: ctx->mt_out holds nq modsgpu_match records (qi = -1 when the query produced no tentative).
 int mg_match_enqueue(modsgpu_ctx* ctx, const float* d_q, int nq, const float* d_t, const double* d_txy, int nt, int dim,
                      double ratio_thr, double contrad_dist, int nn, int* d_knn_idx, float* d_knn_dist) {
-  if (dim % 16 != 0 || dim < 16 || dim > 256) MG_FAIL(ctx, MODSGPU_EINVAL, "descriptor dim must be a multiple of 16, <= 256");
+  // 255^2 * 2 * dim must stay below 2^24: the fp32 epilogue (qn + tn - 2 dot) and the 24-bit radix select are exact
+  // integers only up to dim = 128 (both reference descriptors are 128-d)
+  if (dim % 16 != 0 || dim < 16 || dim > 128) MG_FAIL(ctx, MODSGPU_EINVAL, "descriptor dim must be a multiple of 16, <= 128");
   if (nn < 1 || nn > 64) MG_FAIL(ctx, MODSGPU_EINVAL, "nn must be in [1,64]");
   const int nq_pad = (nq + 127) / 128 * 128, nt_pad = (nt + 127) / 128 * 128, npl = dim / 8;
   // operand planes + norms + flag

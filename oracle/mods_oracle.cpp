@@ -1219,6 +1219,17 @@ extern "C" int orc_match_fginn(const float* q, const double* qxy, int nq, const 
     for (int j = 1; j < nn; j++) {
       if (I[j] < 0) break; /* fewer than nn train points (defined as "stop") */
       double ratio = Dd[0] / Dd[j]; /* float division, widened */
+      if (sqminratio >= 1.0) { /* matching.cpp:395-428: every query yields a correspondence */
+        double dx1 = txy[2 * I[0]] - txy[2 * I[j]], dy1 = txy[2 * I[0] + 1] - txy[2 * I[j] + 1];
+        if ((j == nn - 1) || (dx1 * dx1 + dy1 * dy1 > contrDistSq)) {
+          orc_match mt;
+          mt.qi = i; mt.ti = I[0]; mt.tj_bad = I[j]; mt.d1 = Dd[0]; mt.d2 = Dd[j];
+          mt.ratio = std::sqrt(ratio);
+          out[m++] = mt;
+          break;
+        }
+        continue;
+      }
       if (ratio <= sqminratio) {
         orc_match mt;
         mt.qi = i; mt.ti = I[0]; mt.tj_bad = I[j]; mt.d1 = Dd[0]; mt.d2 = Dd[j];

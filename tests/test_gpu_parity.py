@@ -248,6 +248,13 @@ def test_match_fginn_bit_exact(mg, oracle, nq, nt):
     assert np.array_equal(ki, ridx)
     assert np.array_equal(kd, rdist)
     assert got.tobytes() == ref.tobytes()
+    # FGINNThreshold >= 1 (matching.cpp:395-428, "to get all points"): every query matches -- with its first
+    # geometrically inconsistent neighbour or the last of the 50
+    ref1 = oracle.match_fginn(q, np.zeros((nq, 2)), t, txy, ratio=1.0)
+    got1 = mg.match_fginn(q, t, txy, ratio=1.0)
+    assert got1.tobytes() == ref1.tobytes()
+    if nt >= 50:
+        assert len(got1) == nq and len(got1) > len(got)
 
 
 def test_match_empty_and_bad_input(mg):
@@ -259,6 +266,8 @@ def test_match_empty_and_bad_input(mg):
     bad[0, 0] = 0.5
     with pytest.raises(M.ModsGpuError):
         mg.match_fginn(bad, t, np.zeros((10, 2)))
+    with pytest.raises(M.ModsGpuError):          # 255^2 * 2 * dim must stay an exact fp32 integer: dim <= 128
+        mg.match_fginn(np.zeros((4, 256), np.float32), np.zeros((4, 256), np.float32), np.zeros((4, 2)))
 
 
 def test_duplicate_filter_bit_exact(mg, oracle):
@@ -578,6 +587,42 @@ def test_pair_pipeline_config3(mg, oracle, synth_pair):
     for k in ("keypoints", "regions", "descriptors", "tentatives", "unique_tentatives", "inliers"):
         assert r[k] == r2[k], k
     assert np.array_equal(r["H"], r2["H"])
+
+
+def test_pair_pipeline_parameter_block(mg, synth_pair):
+    """modsgpu_pair_pipeline_images_ex: the defaults reproduce the parameterless entry point bit for bit; every group of
+    the block (detector, matcher, RANSAC) reaches its stage."""
+    import mods_light_zmq_b200 as M
+    from mods_light_zmq_b200 import synth
+    a, b, H = synth_pair
+    i1, i2 = mg.image_from_bgr8(synth.gray_to_bgr(a)), mg.image_from_bgr8(synth.gray_to_bgr(b))
+    base = mg.pair_pipeline_images(i1, i2, seed=5)
+    p = M.default_pipeline_params()
+    assert (p.fginn_threshold, p.contrad_dist, p.nn, p.err_threshold, p.HLAFCoef, p.max_samples) == (0.8, 10.0, 50, 4.0, 12.0, 1000000)
+    p.seed = 5
+    r = mg.pair_pipeline_images_ex(i1, i2, p)
+    for k in ("keypoints", "regions", "descriptors", "tentatives", "unique_tentatives", "inliers"):
+        assert r[k] == base[k], k
+    assert np.array_equal(r["H"], base["H"]) and np.array_equal(r["inlier_xy"], base["inlier_xy"])
+    p.pyr.threshold = 12.0                       # detector block
+    r2 = mg.pair_pipeline_images_ex(i1, i2, p)
+    assert all(x < y for x, y in zip(r2["keypoints"], base["keypoints"]))
+    p = M.default_pipeline_params(); p.seed = 5
+    p.fginn_threshold = 0.6                      # matcher block
+    r3 = mg.pair_pipeline_images_ex(i1, i2, p)
+    assert r3["keypoints"] == base["keypoints"] and r3["tentatives"] < base["tentatives"]
+    p = M.default_pipeline_params(); p.seed = 5
+    p.err_threshold = 1.0                        # RANSAC block: 1 px instead of 4
+    p.error_type = M.ERR_SYMM_MAX
+    r4 = mg.pair_pipeline_images_ex(i1, i2, p)
+    assert r4["tentatives"] == base["tentatives"] and 50 < r4["inliers"] < base["inliers"]
+    p = M.default_pipeline_params(); p.seed = 5
+    p.just_mark_outliers = 1                     # matching.cpp:751-762: the whole list goes on to the LAF check
+    r5 = mg.pair_pipeline_images_ex(i1, i2, p)
+    assert r5["inliers"] >= base["inliers"]
+    p.patchSize = 41
+    with pytest.raises(M.ModsGpuError):
+        mg.pair_pipeline_images_ex(i1, i2, p)
 
 
 # ------------------------------------------------------------------------------------------ batch extraction (config 4)

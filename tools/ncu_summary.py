@@ -63,6 +63,10 @@ def do_full(path):
             if k in hdr:
                 i = hdr.index(k)
                 print("  %-84s %s %s" % (k, r[i], units[i]))
+        # every tensor-pipe counter the capture holds (names differ between ncu versions: sm__pipe_tensor*, sm__inst_executed_pipe_tensor*)
+        for i, k in enumerate(hdr):
+            if "pipe_tensor" in k and k not in KEY and r[i] not in ("", "n/a"):
+                print("  %-84s %s %s" % (k, r[i], units[i]))
 
 
 if __name__ == "__main__":

@@ -385,6 +385,17 @@ int  modsgpu_match_features(modsgpu_ctx* ctx, const modsgpu_feature* f1, int n1,
                             int desc_dim, double fginn_threshold, int use_F, unsigned long long seed,
                             modsgpu_mods_result* res, double* inlier_xy, int capacity);
 
+/* ---- CorrespondenceBank::MatchImgReps (correspondencebank.cpp:234-343) over region lists filed per (detector, descriptor):
+ *      GROUPED -- for every group descriptor the lists of all group detectors are pooled (image 2 = train, image 1 = query)
+ *      and matched once (FGINN, that descriptor's threshold), filed under ("Group", descriptor); SEPARATE -- every separate
+ *      detector x separate descriptor pair is matched on its own.  A descriptor without a threshold (or <= 0) is skipped.
+ *      Name sets / thresholds are comma-separated ("HessianAffine,MSER", "ZMQ=0.8,RootSIFT=0.85").  out: 7 doubles per
+ *      tentative (x1 y1 x2 y2 d1 d2 ratio) in the order of CorrespondenceBank::GetCorresponcesVector("All", "All"). -------- */
+typedef struct { int image /* 1 | 2 */, n; const char* det; const char* desc; const modsgpu_feature* f; } modsgpu_region_list;
+int  modsgpu_match_imgreps(modsgpu_ctx* ctx, const modsgpu_region_list* lists, int n_lists, const char* group_detectors,
+                           const char* group_descriptors, const char* separate_detectors, const char* separate_descriptors,
+                           const char* fginn_thresholds, double* out, int capacity, int* n_out);
+
 /* test-only: one 128x32x64 GEMM through the tcgen05 descriptor conventions of the dense kernels */
 int  modsgpu_debug_umma_probe(modsgpu_ctx* ctx, const float* A, const float* B, float* D, int swap_lbo_sbo);
 /* test / profiling only: cycles per tcgen05.mma (M128 K16) for a given operand-descriptor configuration;

@@ -422,6 +422,23 @@ class ModsGpu:
         finally:
             self.lib.modsgpu_free(out)
 
+    def match_imgreps(self, lists, group_dets=(), group_descs=(), sep_dets=(), sep_descs=(), fginn=None, capacity=1 << 16):
+        """modsgpu_match_imgreps = CorrespondenceBank::MatchImgReps.  lists: [(image 1|2, det, desc, FEATURE_DTYPE array)].
+        Returns an [n, 7] array (x1 y1 x2 y2 d1 d2 ratio)."""
+        class RegionList(C.Structure):
+            _fields_ = [("image", C.c_int), ("n", C.c_int), ("det", C.c_char_p), ("desc", C.c_char_p), ("f", C.c_void_p)]
+        keep = [np.ascontiguousarray(f, FEATURE_DTYPE) for _, _, _, f in lists]
+        arr = (RegionList * max(len(lists), 1))()
+        for a, (img, det, desc, _), f in zip(arr, lists, keep):
+            a.image, a.n, a.det, a.desc, a.f = int(img), len(f), det.encode(), desc.encode(), f.ctypes.data
+        out = np.zeros((capacity, 7), np.float64)
+        n = C.c_int()
+        thr = ",".join("%s=%r" % kv for kv in (fginn or {}).items())
+        self._check(self.lib.modsgpu_match_imgreps(self.ctx, arr, len(lists), ",".join(group_dets).encode(), ",".join(group_descs).encode(),
+                                                   ",".join(sep_dets).encode(), ",".join(sep_descs).encode(), thr.encode(), _p(out), capacity,
+                                                   C.byref(n)))
+        return out[:min(n.value, capacity)].copy()
+
     def mods_pair(self, img1, img2, steps, min_matches=10, use_F=False, seed=12345, capacity=8192):
         """modsgpu_mods_pair.  steps: list of dicts(scales, tilts, phi, init_sigma, fginn) -- one per iteration of an
         iters_*.ini schedule."""

@@ -3,9 +3,9 @@
 // Replaces the per-view body of ImageRepresentation::SynthDetectDescribeKeypoints (imagerepresentation.cpp:704-1006,
 // HessianAffine + AffNet + OriNet + HardNet++):
 //   DetectAffineRegions (:739)                          -> detector graph, keypoints stay in ctx->det_out
-//   DescribeWithZmq(AffNet) + post-processing (:797-845) -> sampler, AffNet, k_chain_affnet_post
+//   DescribeWithZmq(AffNet) + post-processing (:797-845) -> sampler, AffNet, k_chain_affnet_apply + k_chain_compact
 //   ReprojectRegionsAndRemoveTouchBoundary (:868, synth-detection.cpp:151-190, dontRemove)   (same kernel)
-//   DescribeWithZmq(OriNet) + rotation (:876-899)        -> sampler, OriNet, k_chain_orinet_post
+//   DescribeWithZmq(OriNet) + rotation (:876-899)        -> sampler, OriNet, k_chain_orinet_apply + k_chain_compact
 //   ReprojectRegions (:951, synth-detection.cpp:631-706)                                     (same kernel)
 //   DescribeWithZmq(desc) (:992-1006)                    -> sampler, HardNet++
 // The seam-by-seam route (modsgpu_detect + 3 x modsgpu_describe with the host arithmetic of mods_host.cpp in between)
@@ -152,52 +152,60 @@ __global__ void k_chain_init(const modsgpu_keypoint* __restrict__ kp, const int*
   out[i] = r;
 }
 
-// One CTA: thread t owns the contiguous run [t*per, (t+1)*per) so that the survivors keep their order.
-// cnt_out[0] = #keepA (regions after AffNet's own tests, ImageRepresentation::n_affine), cnt_out[1] = #keepB (list length)
-__global__ void __launch_bounds__(1024)
-k_chain_affnet_post(const DevRegion* __restrict__ in, const float* __restrict__ aff, const int* __restrict__ cnt_in,
-                    DevRegion* __restrict__ out, int* __restrict__ cnt_out, int w, int h, int orig_w, int orig_h, double mrSize,
-                    Mat3 Hinv, int eye) {
-  __shared__ int s_total, s_totalA;
-  const int n = *cnt_in;
-  const int per = (n + 1023) / 1024, i0 = threadIdx.x * per, i1 = min(n, i0 + per);
-  int nA = 0, nB = 0;
-  for (int i = i0; i < i1; i++) {
-    DevRegion t; bool ka, kb;
-    affnet_apply(in[i], aff + 3 * (size_t)i, w, h, orig_w, orig_h, mrSize, Hinv, eye, t, ka, kb);
-    nA += ka; nB += kb;
-  }
-  int dummy;
-  block_excl_scan(nA, s_totalA);
-  (void)dummy;
-  int pos = block_excl_scan(nB, s_total);
-  for (int i = i0; i < i1; i++) {
-    DevRegion t; bool ka, kb;
-    affnet_apply(in[i], aff + 3 * (size_t)i, w, h, orig_w, orig_h, mrSize, Hinv, eye, t, ka, kb);
-    if (kb) out[pos++] = t;
-  }
-  if (threadIdx.x == 0) { cnt_out[0] = s_totalA; cnt_out[1] = s_total; }
+// Post-processing of a net's output in two launches: the per-region arithmetic runs on as many CTAs as the list needs
+// (k_chain_*_apply: new row into tmp[i], verdict into flag[i]); one CTA then compacts the survivors in list order
+// (k_chain_compact: thread t owns the contiguous run [t*per, (t+1)*per) of the flags; rows are copied 16 bytes per lane).
+// flag bits: 1 = counted in cnt_out[0] (AffNet: survives AffNet's own tests, ImageRepresentation::n_affine), 2 = kept.
+__global__ void __launch_bounds__(128)
+k_chain_affnet_apply(const DevRegion* __restrict__ in, const float* __restrict__ aff, const int* __restrict__ cnt_in,
+                     DevRegion* __restrict__ tmp, unsigned char* __restrict__ flag, int w, int h, int orig_w, int orig_h, double mrSize,
+                     Mat3 Hinv, int eye) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= *cnt_in) return;
+  DevRegion t; bool ka, kb;
+  affnet_apply(in[i], aff + 3 * (size_t)i, w, h, orig_w, orig_h, mrSize, Hinv, eye, t, ka, kb);
+  tmp[i] = t;
+  flag[i] = (unsigned char)((ka ? 1 : 0) | (kb ? 2 : 0));
 }
-
+__global__ void __launch_bounds__(128)
+k_chain_orinet_apply(const DevRegion* __restrict__ in, const float* __restrict__ ori, const int* __restrict__ cnt_in,
+                     DevRegion* __restrict__ tmp, unsigned char* __restrict__ flag, int orig_w, int orig_h, double k_sigma, Mat3 Hinv, int eye) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= *cnt_in) return;
+  DevRegion t; bool k;
+  orinet_apply(in[i], ori + 2 * (size_t)i, orig_w, orig_h, k_sigma, Hinv, eye, t, k);
+  tmp[i] = t;
+  flag[i] = (unsigned char)(k ? 3 : 0);
+}
+// cnt_out[0] = #(flag & 1), cnt_out[n_cnt - 1] = #(flag & 2) = length of the compacted list (n_cnt = 2: both counters)
 __global__ void __launch_bounds__(1024)
-k_chain_orinet_post(const DevRegion* __restrict__ in, const float* __restrict__ ori, const int* __restrict__ cnt_in,
-                    DevRegion* __restrict__ out, int* __restrict__ cnt_out, int orig_w, int orig_h, double k_sigma, Mat3 Hinv, int eye) {
-  __shared__ int s_total;
+k_chain_compact(const DevRegion* __restrict__ tmp, const unsigned char* __restrict__ flag, const int* __restrict__ cnt_in,
+                DevRegion* __restrict__ out, int* __restrict__ cnt_out, int n_cnt) {
+  __shared__ int s_total, s_totalA;
+  __shared__ int s_src[8192];          // source index of every survivor of the current 8192-row window
   const int n = *cnt_in;
-  const int per = (n + 1023) / 1024, i0 = threadIdx.x * per, i1 = min(n, i0 + per);
-  int nk = 0;
-  for (int i = i0; i < i1; i++) {
-    DevRegion t; bool k;
-    orinet_apply(in[i], ori + 2 * (size_t)i, orig_w, orig_h, k_sigma, Hinv, eye, t, k);
-    nk += k;
+  int done = 0, doneA = 0;
+  for (int base = 0; base < n; base += 8192) {
+    const int m = min(8192, n - base);
+    const int per = (m + 1023) / 1024, i0 = threadIdx.x * per, i1 = min(m, i0 + per);
+    int nA = 0, nB = 0;
+    for (int i = i0; i < i1; i++) { const int f = flag[base + i]; nA += f & 1; nB += (f >> 1) & 1; }
+    block_excl_scan(nA, s_totalA);
+    int pos = block_excl_scan(nB, s_total);
+    for (int i = i0; i < i1; i++) if (flag[base + i] & 2) s_src[pos++] = base + i;
+    __syncthreads();
+    const int kept = s_total;
+    // rows of 128 bytes: 8 lanes x 16 bytes per row, coalesced
+    const uint4* src4 = reinterpret_cast<const uint4*>(tmp);
+    uint4* dst4 = reinterpret_cast<uint4*>(out);
+    for (int it = threadIdx.x; it < kept * 8; it += 1024) {
+      const int k = it >> 3, q = it & 7;
+      dst4[(size_t)(done + k) * 8 + q] = src4[(size_t)s_src[k] * 8 + q];
+    }
+    done += kept; doneA += s_totalA;
+    __syncthreads();
   }
-  int pos = block_excl_scan(nk, s_total);
-  for (int i = i0; i < i1; i++) {
-    DevRegion t; bool k;
-    orinet_apply(in[i], ori + 2 * (size_t)i, orig_w, orig_h, k_sigma, Hinv, eye, t, k);
-    if (k) out[pos++] = t;
-  }
-  if (threadIdx.x == 0) cnt_out[0] = s_total;
+  if (threadIdx.x == 0) { cnt_out[0] = doneA; cnt_out[n_cnt - 1] = done; }
 }
 
 bool invert3h(const double* A, double* R) {
@@ -242,9 +250,16 @@ extern "C" int modsgpu_debug_affnet_post(modsgpu_ctx* ctx, const modsgpu_view_re
   MG_CUDA(ctx, cudaMemcpyAsync(ctx->chain_a.p, regs, (size_t)n * sizeof(DevRegion), cudaMemcpyHostToDevice, ctx->stream));
   MG_CUDA(ctx, cudaMemcpyAsync(ctx->cnn_out.p, aff, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
   MG_CUDA(ctx, cudaMemcpyAsync(cnt, &n, 4, cudaMemcpyHostToDevice, ctx->stream));
-  k_chain_affnet_post<<<1, 1024, 0, ctx->stream>>>(ctx->chain_a.as<DevRegion>(), ctx->cnn_out.as<float>(), cnt, ctx->chain_b.as<DevRegion>(),
-                                                   cnt + 1, w, h, orig_w, orig_h, mrSize, Hinv, eye);
-  MG_LAUNCHED(ctx);
+  MG_CUDA(ctx, ctx->chain_tmp.ensure((size_t)(n + 1) * (sizeof(DevRegion) + 1)));
+  {
+    DevRegion* tmp = ctx->chain_tmp.as<DevRegion>();
+    unsigned char* flag = reinterpret_cast<unsigned char*>(tmp + n + 1);
+    k_chain_affnet_apply<<<ceil_div(std::max(n, 1), 128), 128, 0, ctx->stream>>>(ctx->chain_a.as<DevRegion>(), ctx->cnn_out.as<float>(), cnt, tmp, flag,
+                                                                                 w, h, orig_w, orig_h, mrSize, Hinv, eye);
+    MG_LAUNCHED(ctx);
+    k_chain_compact<<<1, 1024, 0, ctx->stream>>>(tmp, flag, cnt, ctx->chain_b.as<DevRegion>(), cnt + 1, 2);
+    MG_LAUNCHED(ctx);
+  }
   int hc[3] = {0, 0, 0};
   MG_CUDA(ctx, cudaMemcpyAsync(hc, cnt, 12, cudaMemcpyDeviceToHost, ctx->stream));
   MG_CUDA(ctx, mg_stream_sync(ctx));
@@ -269,9 +284,16 @@ extern "C" int modsgpu_debug_orinet_post(modsgpu_ctx* ctx, const modsgpu_view_re
   MG_CUDA(ctx, cudaMemcpyAsync(ctx->chain_a.p, regs, (size_t)n * sizeof(DevRegion), cudaMemcpyHostToDevice, ctx->stream));
   MG_CUDA(ctx, cudaMemcpyAsync(ctx->cnn_out.p, ori, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
   MG_CUDA(ctx, cudaMemcpyAsync(cnt, &n, 4, cudaMemcpyHostToDevice, ctx->stream));
-  k_chain_orinet_post<<<1, 1024, 0, ctx->stream>>>(ctx->chain_a.as<DevRegion>(), ctx->cnn_out.as<float>(), cnt, ctx->chain_b.as<DevRegion>(),
-                                                   cnt + 1, orig_w, orig_h, k_sigma, Hinv, eye);
-  MG_LAUNCHED(ctx);
+  MG_CUDA(ctx, ctx->chain_tmp.ensure((size_t)(n + 1) * (sizeof(DevRegion) + 1)));
+  {
+    DevRegion* tmp = ctx->chain_tmp.as<DevRegion>();
+    unsigned char* flag = reinterpret_cast<unsigned char*>(tmp + n + 1);
+    k_chain_orinet_apply<<<ceil_div(std::max(n, 1), 128), 128, 0, ctx->stream>>>(ctx->chain_a.as<DevRegion>(), ctx->cnn_out.as<float>(), cnt, tmp, flag,
+                                                                                 orig_w, orig_h, k_sigma, Hinv, eye);
+    MG_LAUNCHED(ctx);
+    k_chain_compact<<<1, 1024, 0, ctx->stream>>>(tmp, flag, cnt, ctx->chain_b.as<DevRegion>(), cnt + 1, 1);
+    MG_LAUNCHED(ctx);
+  }
   int hc[2] = {0, 0};
   MG_CUDA(ctx, cudaMemcpyAsync(hc, cnt, 8, cudaMemcpyDeviceToHost, ctx->stream));
   MG_CUDA(ctx, mg_stream_sync(ctx));
@@ -345,14 +367,23 @@ extern "C" int modsgpu_describe_view(modsgpu_ctx* ctx, const modsgpu_image* view
   // ---- AffNet
   if ((rc = mg_sample_enqueue_dev(ctx, view, ra, cnt, n0, st, mrSize, patches))) return rc;
   if ((rc = mg_net_forward_enqueue(ctx, MODSGPU_AFFNET, patches, n0, nout, cnt))) return rc;
-  MG_PROF(ctx, "k_chain_affnet_post", 2, (double)n0);
-  k_chain_affnet_post<<<1, 1024, 0, ctx->stream>>>(ra, nout, cnt, rb, cnt + 1, view->w, view->h, orig_w, orig_h, mrSize, Hinv, eye);
+  MG_CUDA(ctx, ctx->chain_tmp.ensure((size_t)(n0 + 1) * (sizeof(DevRegion) + 1)));
+  DevRegion* tmp = ctx->chain_tmp.as<DevRegion>();
+  unsigned char* flag = reinterpret_cast<unsigned char*>(tmp + n0 + 1);
+  MG_PROF(ctx, "k_chain_affnet_apply", 2, (double)n0);
+  k_chain_affnet_apply<<<ceil_div(n0, 128), 128, 0, ctx->stream>>>(ra, nout, cnt, tmp, flag, view->w, view->h, orig_w, orig_h, mrSize, Hinv, eye);
+  MG_LAUNCHED(ctx);
+  MG_PROF(ctx, "k_chain_compact", 2, (double)n0);
+  k_chain_compact<<<1, 1024, 0, ctx->stream>>>(tmp, flag, cnt, rb, cnt + 1, 2);
   MG_LAUNCHED(ctx);
   // ---- OriNet
   if ((rc = mg_sample_enqueue_dev(ctx, view, rb, cnt + 2, n0, st, mrSize, patches))) return rc;
   if ((rc = mg_net_forward_enqueue(ctx, MODSGPU_ORINET, patches, n0, nout, cnt + 2))) return rc;
-  MG_PROF(ctx, "k_chain_orinet_post", 2, (double)n0);
-  k_chain_orinet_post<<<1, 1024, 0, ctx->stream>>>(rb, nout, cnt + 2, ra, cnt + 3, orig_w, orig_h, k_sigma, Hinv, eye);
+  MG_PROF(ctx, "k_chain_orinet_apply", 2, (double)n0);
+  k_chain_orinet_apply<<<ceil_div(n0, 128), 128, 0, ctx->stream>>>(rb, nout, cnt + 2, tmp, flag, orig_w, orig_h, k_sigma, Hinv, eye);
+  MG_LAUNCHED(ctx);
+  MG_PROF(ctx, "k_chain_compact", 2, (double)n0);
+  k_chain_compact<<<1, 1024, 0, ctx->stream>>>(tmp, flag, cnt + 2, ra, cnt + 3, 1);
   MG_LAUNCHED(ctx);
   // ---- HardNet++
   if ((rc = mg_sample_enqueue_dev(ctx, view, ra, cnt + 3, n0, st, mrSize, patches))) return rc;

@@ -1339,7 +1339,10 @@ int launch_trunk(modsgpu_ctx* ctx, const __half* in, size_t in_slots, const Conv
   const double macs = 1024.0 * 9 * C1 * C1 + 256.0 * 9 * C1 * 2 * C1 + (NL == 3 ? 256.0 * 9 * 2 * C1 * 2 * C1 : 0.0);
   // algorithmic bytes: conv1's map in, the last fused layer's map out
   MG_PROF2(ctx, pname, 1, 2.0 * np * macs, 2.0 * np * (1024.0 * C1 + 256.0 * 2 * C1));
-  const int ctas = ctx->num_sms * (C1 == 16 ? 2 : 1);
+  // MODSGPU_TRUNK_CTAS=1: one CTA per SM for the 16-channel trunk as well (A/B switch: leaves half of the shared memory
+  // to the kernels of other streams)
+  static const int cta_cap = [] { const char* e = getenv("MODSGPU_TRUNK_CTAS"); return e ? std::max(1, atoi(e)) : 2; }();
+  const int ctas = ctx->num_sms * (C1 == 16 ? std::min(2, cta_cap) : 1);
   kern<<<std::min(np, ctas), 192, Cfg::SMEM_BYTES, ctx->stream>>>(in, in_slots, w[0].w, w[0].b, w[1].w, w[1].b, NL == 3 ? w[2].w : nullptr,
                                                                   NL == 3 ? w[2].b : nullptr, out, out_slots, np, cnt_dev, patch_base);
   MG_LAUNCHED(ctx);

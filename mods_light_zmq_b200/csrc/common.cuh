@@ -104,6 +104,7 @@ struct modsgpu_ctx {
   DevBuf smp_regs, smp_meta, smp_taps, smp_scratch, smp_out;
   DevBuf smp_prof;                    // 6 doubles: algorithmic bytes per sampler class of the device-prepared launches (profiler)
   DevBuf smp_taptab;                  // Gaussian taps of every even window size (patchSize 32), device-side sampler prep
+  DevBuf chain_tmp;                   // uncompacted rows + verdict bytes between a net and the compaction
   DevBuf chain_a, chain_b, chain_misc;   // region lists (DevRegion) of the per-view chain, counters / stats
   DevBuf cnn_act0, cnn_act1, cnn_out;
   DevBuf cnn_stats;                   // normalised patches (fp32) for the fused conv1+conv2 kernel

@@ -382,6 +382,7 @@ int ImageRepresentation::SynthDetectDescribeKeypointsClassic(const DetectPars& p
   int w, h;
   modsgpu_image_size(img_, &w, &h);
   regions_.clear();
+  desc_name = "RootSIFT";
   n_views = 1;
   double t0 = now_ms();
   modsgpu_keypoint* kps = nullptr;
@@ -539,6 +540,86 @@ int MatchFlannFGINN(modsgpu_ctx* ctx, const AffineRegionVector& list1, const Aff
     corresp.TCList.push_back(tc);
   }
   return nm;
+}
+
+// ---- keyed region store (imagerepresentation.cpp:600-660) ------------------------------------------------------------
+void ImageRepresentation::AddRegions(const AffineRegionVector& RegionsToAdd, const std::string& det, const std::string& desc) {
+  AffineRegionVector& dst = RegionVectorMap[det][desc];       // appended to an existing list, created otherwise
+  dst.insert(dst.end(), RegionsToAdd.begin(), RegionsToAdd.end());
+}
+AffineRegionVector ImageRepresentation::GetAffineRegionVector(const std::string& desc, const std::string& det) const {
+  AffineRegionVector out;
+  if (det == det_name && desc == desc_name) out = regions_;   // the lists this object extracted itself
+  auto d = RegionVectorMap.find(det);
+  if (d != RegionVectorMap.end()) {
+    auto e = d->second.find(desc);
+    if (e != d->second.end()) out.insert(out.end(), e->second.begin(), e->second.end());
+  }
+  return out;
+}
+
+// ---- CorrespondenceBank (correspondencebank.cpp) ------------------------------------------------------------------------
+void CorrespondenceBank::AddCorrespondences(const TentativeCorrespListExt& CorrsToAdd, const std::string& det, const std::string& desc) {
+  auto& byDet = CorrespondencesMapMap[desc];                  // :174-199
+  auto it = byDet.find(det);
+  if (it != byDet.end()) it->second.TCList.insert(it->second.TCList.end(), CorrsToAdd.TCList.begin(), CorrsToAdd.TCList.end());
+  else byDet[det] = CorrsToAdd;
+}
+void CorrespondenceBank::ClearCorrespondences(const std::string& det, const std::string& desc) {
+  auto d = CorrespondencesMapMap.find(desc);                  // :200-211
+  if (d == CorrespondencesMapMap.end()) return;
+  auto e = d->second.find(det);
+  if (e != d->second.end()) e->second.TCList.clear();
+}
+TentativeCorrespListExt CorrespondenceBank::GetCorresponcesVector(const std::string& desc, const std::string& det) const {
+  TentativeCorrespListExt corrs;                              // :115-172: descriptors, then detectors, in map (= name) order
+  for (const auto& d : CorrespondencesMapMap) {
+    if (desc != "All" && d.first != desc) continue;
+    for (const auto& e : d.second) {
+      if (det != "All" && e.first != det) continue;
+      corrs.TCList.insert(corrs.TCList.end(), e.second.TCList.begin(), e.second.TCList.end());
+    }
+  }
+  return corrs;
+}
+int CorrespondenceBank::GetCorrespondencesNumber(const std::string& desc, const std::string& det) const {
+  return (int)GetCorresponcesVector(desc, det).TCList.size();
+}
+int CorrespondenceBank::MatchImgReps(const ImageRepresentation& imgrep1, const ImageRepresentation& imgrep2, const WhatToMatch& what,
+                                     const MatchPars& par, const std::map<std::string, double>& fginn) {
+  auto threshold = [&](const std::string& desc) { auto it = fginn.find(desc); return it != fginn.end() ? it->second : 0.0; };
+  auto match = [&](const AffineRegionVector& queries, const AffineRegionVector& trains, double thr, TentativeCorrespListExt& out) {
+    if (!(thr > 0)) return 0;                                  // currMatchRatio == 0: this descriptor is not matched (:262-277)
+    MatchPars mp = par;
+    mp.FGINNThreshold = thr;
+    return MatchFlannFGINN(ctx_, queries, trains, out, mp);
+  };
+  // grouped (:246-285): one pooled list per group descriptor
+  for (const std::string& curr_desc : what.group_descriptors) {
+    ClearCorrespondences("Group", curr_desc);
+    AffineRegionVector queries, trains;
+    for (const std::string& curr_det : what.group_detectors) {
+      const AffineRegionVector t = imgrep2.GetAffineRegionVector(curr_desc, curr_det);
+      trains.insert(trains.end(), t.begin(), t.end());
+      const AffineRegionVector q = imgrep1.GetAffineRegionVector(curr_desc, curr_det);
+      queries.insert(queries.end(), q.begin(), q.end());
+    }
+    TentativeCorrespListExt current_tents;
+    const int rc = match(queries, trains, threshold(curr_desc), current_tents);
+    if (rc < 0) return rc;
+    AddCorrespondences(current_tents, "Group", curr_desc);
+  }
+  // separate (:288-340): every separate detector x separate descriptor on its own
+  for (const std::string& curr_det : what.separate_detectors)
+    for (const std::string& curr_desc : what.separate_descriptors) {
+      ClearCorrespondences(curr_det, curr_desc);
+      TentativeCorrespListExt current_tents;
+      const int rc = match(imgrep1.GetAffineRegionVector(curr_desc, curr_det), imgrep2.GetAffineRegionVector(curr_desc, curr_det),
+                           threshold(curr_desc), current_tents);
+      if (rc < 0) return rc;
+      AddCorrespondences(current_tents, curr_det, curr_desc);
+    }
+  return 0;
 }
 
 // matching.cpp:2615-2679, mode bestFGINN (mods.cpp:283)
@@ -785,6 +866,66 @@ extern "C" int modsgpu_empirical_checks(const modsgpu_region* kp1, const modsgpu
   memset(keep, 0, (size_t)n);
   for (const auto& c : list.TCList) keep[c.first.id] = 1;
   *n_out = m;
+  return 0;
+}
+
+// CorrespondenceBank::MatchImgReps over caller-supplied region lists (test / integration seam).  lists: which image (1 or 2),
+// detector and descriptor name each list is filed under.  Name sets and thresholds are comma-separated strings
+// ("HessianAffine,MSER", "ZMQ=0.8,RootSIFT=0.85").  out: 7 doubles per tentative (x1 y1 x2 y2 d1 d2 ratio) in the order of
+// GetCorresponcesVector("All", "All").
+extern "C" int modsgpu_match_imgreps(modsgpu_ctx* ctx, const modsgpu_region_list* lists, int n_lists, const char* group_detectors,
+                                     const char* group_descriptors, const char* separate_detectors, const char* separate_descriptors,
+                                     const char* fginn_thresholds, double* out, int capacity, int* n_out) {
+  using namespace modsb200;
+  if (!ctx || n_lists < 0 || (n_lists > 0 && !lists) || !n_out) return MODSGPU_EINVAL;
+  auto split = [](const char* s) {
+    std::vector<std::string> v;
+    std::string cur;
+    for (const char* p = s ? s : ""; ; p++) {
+      if (*p == ',' || *p == 0) { if (!cur.empty()) v.push_back(cur); cur.clear(); if (!*p) break; }
+      else if (*p != ' ') cur.push_back(*p);
+    }
+    return v;
+  };
+  ImageRepresentation rep1(ctx, nullptr, false), rep2(ctx, nullptr, false);
+  rep1.det_name = rep2.det_name = "";          // nothing extracted by these objects: every list comes from AddRegions
+  for (int l = 0; l < n_lists; l++) {
+    const modsgpu_region_list& L = lists[l];
+    if ((L.image != 1 && L.image != 2) || !L.det || !L.desc || L.n < 0 || (L.n > 0 && !L.f)) return MODSGPU_EINVAL;
+    AffineRegionVector v(L.n);
+    auto blk = std::make_shared<std::vector<float>>((size_t)L.n * 128);
+    for (int i = 0; i < L.n; i++) {
+      AffineKeypoint& k = v[i].reproj_kp;
+      k.x = L.f[i].x; k.y = L.f[i].y; k.s = L.f[i].s; k.a11 = L.f[i].a11; k.a12 = L.f[i].a12; k.a21 = L.f[i].a21; k.a22 = L.f[i].a22;
+      k.response = L.f[i].response; k.octave_number = L.f[i].octave; k.sub_type = L.f[i].type;
+      v[i].det_kp = k; v[i].id = i;
+      memcpy(blk->data() + (size_t)i * 128, L.f[i].desc, 512);
+    }
+    std::shared_ptr<const std::vector<float>> cblk = blk;
+    for (int i = 0; i < L.n; i++) v[i].desc.view(cblk, (size_t)i * 128, 128);
+    (L.image == 1 ? rep1 : rep2).AddRegions(v, L.det, L.desc);
+  }
+  WhatToMatch what;
+  what.group_detectors = split(group_detectors); what.group_descriptors = split(group_descriptors);
+  what.separate_detectors = split(separate_detectors); what.separate_descriptors = split(separate_descriptors);
+  std::map<std::string, double> fginn;
+  for (const std::string& kv : split(fginn_thresholds)) {
+    const size_t eq = kv.find('=');
+    if (eq == std::string::npos) return MODSGPU_EINVAL;
+    fginn[kv.substr(0, eq)] = atof(kv.c_str() + eq + 1);
+  }
+  CorrespondenceBank bank(ctx);
+  MatchPars mp;
+  const int rc = bank.MatchImgReps(rep1, rep2, what, mp, fginn);
+  if (rc) return rc;
+  const TentativeCorrespListExt all = bank.GetCorresponcesVector();
+  *n_out = (int)all.TCList.size();
+  for (int i = 0; i < *n_out && i < capacity && out; i++) {
+    const TentativeCorrespExt& c = all.TCList[i];
+    double* o = out + 7 * (size_t)i;
+    o[0] = c.first.reproj_kp.x; o[1] = c.first.reproj_kp.y; o[2] = c.second.reproj_kp.x; o[3] = c.second.reproj_kp.y;
+    o[4] = c.d1; o[5] = c.d2; o[6] = c.ratio;
+  }
   return 0;
 }
 

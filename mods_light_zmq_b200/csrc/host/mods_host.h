@@ -7,6 +7,7 @@
 //   MatchFlannFGINN       matching.cpp:356-460      DuplicateFiltering  matching.cpp:2615-2679
 //   LORANSACFiltering     matching.cpp:637-823      (H branch: NaiveHCheck :1014-1043, H_LAF_check :250-308)
 #pragma once
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -101,10 +102,23 @@ struct TimeLog {                   // structures.hpp:33-56 (device + host ms per
   double SynthTime = 0, DetectTime = 0, OrientTime = 0, DescTime = 0, MatchingTime = 0, RANSACTime = 0;
 };
 
+typedef std::map<std::string, AffineRegionVector> AffineRegionVectorMap;   // descriptor name -> regions (structures.hpp:231)
+struct WhatToMatch {               // structures.hpp:236-242: which (detector, descriptor) lists one iteration matches
+  std::vector<std::string> group_detectors, group_descriptors, separate_detectors, separate_descriptors;
+};
+
 class ImageRepresentation {
  public:
   ImageRepresentation(modsgpu_ctx* ctx, modsgpu_image* img, bool owns_image);
   ~ImageRepresentation();
+  // the keyed region store of the reference (imagerepresentation.h:64, RegionVectorMap[detector][descriptor]).  The lists
+  // this object extracts itself are kept in regions_ under (det_name, desc_name) = ("HessianAffine", "ZMQ" | "RootSIFT");
+  // AddRegions (imagerepresentation.cpp:637-660) files further lists, e.g. pre-extracted ones, under their own keys.
+  std::map<std::string, AffineRegionVectorMap> RegionVectorMap;
+  std::string det_name = "HessianAffine", desc_name = "ZMQ";
+  void AddRegions(const AffineRegionVector& RegionsToAdd, const std::string& det, const std::string& desc);
+  // imagerepresentation.cpp:600-635 for a named detector (MatchImgReps never asks for "All")
+  AffineRegionVector GetAffineRegionVector(const std::string& desc, const std::string& det) const;
   // returns the number of described regions, < 0 on error (message via modsgpu_last_error)
   int SynthDetectDescribeKeypoints(const DetectPars& par);
   // the same over a list of synthesised views (imagerepresentation.cpp:704-1102): every view is generated on the
@@ -142,6 +156,25 @@ void OxAffEllipse(const AffineKeypoint& k, float& a, float& b, float& c);
 
 int MatchFlannFGINN(modsgpu_ctx* ctx, const AffineRegionVector& list1, const AffineRegionVector& list2,
                     TentativeCorrespListExt& corresp, const MatchPars& par);
+
+// correspondencebank.h / .cpp: tentatives filed per (descriptor, detector | "Group").  MatchImgReps
+// (correspondencebank.cpp:234-343): GROUPED -- for every group descriptor the regions of all group detectors are pooled
+// (image 2 = train, image 1 = query) and matched once; SEPARATE -- every separate detector x separate descriptor is
+// matched on its own.  fginn: FGINNThreshold per descriptor name (iters file); a descriptor without an entry, or with a
+// threshold <= 0, is not matched (correspondencebank.cpp:262-277).
+class CorrespondenceBank {
+ public:
+  explicit CorrespondenceBank(modsgpu_ctx* ctx) : ctx_(ctx) {}
+  int MatchImgReps(const ImageRepresentation& imgrep1, const ImageRepresentation& imgrep2, const WhatToMatch& what,
+                   const MatchPars& par, const std::map<std::string, double>& fginn);
+  TentativeCorrespListExt GetCorresponcesVector(const std::string& desc = "All", const std::string& det = "All") const;
+  int GetCorrespondencesNumber(const std::string& desc = "All", const std::string& det = "All") const;
+  void AddCorrespondences(const TentativeCorrespListExt& CorrsToAdd, const std::string& det, const std::string& desc);
+  void ClearCorrespondences(const std::string& det, const std::string& desc);
+ private:
+  modsgpu_ctx* ctx_;
+  std::map<std::string, std::map<std::string, TentativeCorrespListExt>> CorrespondencesMapMap;   // [descriptor][detector]
+};
 int DuplicateFiltering(modsgpu_ctx* ctx, TentativeCorrespListExt& in_corresp, double r);
 // one MODS run over a schedule of iterations (mods.cpp:202-356 for the HessianAffine steps): every step adds the
 // regions of its new views to both images, matches ALL accumulated regions, filters duplicates and verifies with

@@ -1014,7 +1014,7 @@ struct PrepLayout { int cls_off[SC_N]; int nl_cap; };   // class c's PatchMeta l
 // three block-count prefix arrays.
 __global__ void __launch_bounds__(1024)
 k_smp_prepare(const DevRegion* __restrict__ regs, const int* __restrict__ cnt, double mrSize, TapTab tt, PrepLayout lay,
-              PatchMeta* __restrict__ metas, int2* __restrict__ tmp, int* __restrict__ pre1, int* __restrict__ pre2,
+              PatchMeta* __restrict__ metas, PatchMeta* __restrict__ mtmp, int* __restrict__ pre1, int* __restrict__ pre2,
               int* __restrict__ pre0, int* __restrict__ cls_cnt_out, double* __restrict__ prof_bytes) {
   __shared__ int hist[HB_TOTAL];
   __shared__ int s_cls[SC_N];
@@ -1022,11 +1022,25 @@ k_smp_prepare(const DevRegion* __restrict__ regs, const int* __restrict__ cnt, d
   for (int i = tid; i < HB_TOTAL; i += blockDim.x) hist[i] = 0;
   __syncthreads();
   const int n = *cnt;
-  for (int i = tid; i < n; i += blockDim.x) {
-    PatchMeta m; int c;
-    classify_region(regs[i].det, mrSize, tt, m, c);
-    const int bin = hist_bin(c, m.R);
-    tmp[i] = make_int2(bin, atomicAdd(&hist[bin], 1));
+  // four regions per thread and step: the row loads, then the tap-table look-ups, of the four are in flight together
+  // (one CTA walks the whole list, so the dependent-load latency, not the arithmetic, sets this kernel's time)
+  for (int i0 = tid; i0 < n; i0 += 4 * blockDim.x) {
+    modsgpu_region rg[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) { const int i = i0 + u * blockDim.x; rg[u] = regs[i < n ? i : n - 1].det; }
+    PatchMeta m[4]; int c[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) classify_region(rg[u], mrSize, tt, m[u], c[u]);
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + u * blockDim.x;
+      if (i < n) {
+        const int bin = hist_bin(c[u], m[u].R);
+        m[u].out_index = i;
+        m[u].scratch_off = (long long)bin << 32 | (unsigned)atomicAdd(&hist[bin], 1);     // (bin, rank) ride in the unused field
+        mtmp[i] = m[u];
+      }
+    }
   }
   __syncthreads();
   // warp c turns class c's counts into start positions, walking R downwards (exclusive scan, 32 bins per step)
@@ -1045,14 +1059,35 @@ k_smp_prepare(const DevRegion* __restrict__ regs, const int* __restrict__ cnt, d
     if (lane == 0) { s_cls[c] = carry; cls_cnt_out[c] = carry; }
   }
   __syncthreads();
-  for (int i = tid; i < n; i += blockDim.x) {
-    PatchMeta m; int c;
-    classify_region(regs[i].det, mrSize, tt, m, c);
-    m.out_index = i;
-    const int2 t = tmp[i];
-    metas[hist[t.x] + t.y] = m;
-    // profiler only: the algorithmic bytes of this region (R*R*4 read + 32*32 written), per class
-    if (prof_bytes != nullptr) atomicAdd(prof_bytes + c, (double)m.R * m.R * 4.0 + (double)(DEV_PS * DEV_PS));
+  double pb[SC_N] = {0, 0, 0, 0, 0, 0};
+  for (int i0 = tid; i0 < n; i0 += 4 * blockDim.x) {
+    PatchMeta m[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) { const int i = i0 + u * blockDim.x; m[u] = mtmp[i < n ? i : n - 1]; }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + u * blockDim.x;
+      if (i < n) {
+        const int bin = (int)(m[u].scratch_off >> 32), rank = (int)(m[u].scratch_off & 0xffffffffll);
+        m[u].scratch_off = 0;
+        metas[hist[bin] + rank] = m[u];
+        // profiler only: the algorithmic bytes of this region (R*R*4 read + 32*32 written), per class
+        if (prof_bytes != nullptr) {
+          const int c = bin < 5 * HB_SMALL ? bin / HB_SMALL : SC_LARGE;
+          const double b = (double)m[u].R * m[u].R * 4.0 + (double)(DEV_PS * DEV_PS);
+#pragma unroll
+          for (int k = 0; k < SC_N; k++) pb[k] += c == k ? b : 0.0;
+        }
+      }
+    }
+  }
+  if (prof_bytes != nullptr) {       // one atomic per warp and class (thousands on one address would dominate the kernel)
+#pragma unroll
+    for (int k = 0; k < SC_N; k++) {
+      double v = pb[k];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && v > 0) atomicAdd(prof_bytes + k, v);
+    }
   }
   __syncthreads();
   // large-window class: scratch offsets and the prefix arrays of the three row-blocked phases (warp 0, 32 regions per step)
@@ -1142,7 +1177,7 @@ int mg_sample_enqueue_dev(modsgpu_ctx* ctx, const modsgpu_image* img, const DevR
   const int nl = st.nl;
   const size_t meta_bytes = (nm + 1) * sizeof(PatchMeta), pre_bytes = (size_t)(nl + 1) * 4;
   MG_CUDA(ctx, ctx->smp_meta.ensure(meta_bytes + 3 * pre_bytes + 64));
-  MG_CUDA(ctx, ctx->smp_regs.ensure((size_t)n_ub * sizeof(int2) + 16));
+  MG_CUDA(ctx, ctx->smp_regs.ensure((size_t)(n_ub + 1) * sizeof(PatchMeta) + 16));
   MG_CUDA(ctx, ctx->smp_scratch.ensure((size_t)st.scratch * 4 + 16));
   PatchMeta* dm = ctx->smp_meta.as<PatchMeta>();
   int* dpre1 = reinterpret_cast<int*>(ctx->smp_meta.as<uint8_t>() + meta_bytes);
@@ -1155,7 +1190,7 @@ int mg_sample_enqueue_dev(modsgpu_ctx* ctx, const modsgpu_image* img, const DevR
     prof_bytes = ctx->smp_prof.as<double>();
   }
   MG_PROF(ctx, "k_smp_prepare", 2, (double)n_ub);
-  k_smp_prepare<<<1, 1024, 0, ctx->stream>>>(regs, cnt_dev, mrSize, tt, lay, dm, ctx->smp_regs.as<int2>(), dpre1, dpre2, dpre0, dcnt,
+  k_smp_prepare<<<1, 1024, 0, ctx->stream>>>(regs, cnt_dev, mrSize, tt, lay, dm, ctx->smp_regs.as<PatchMeta>(), dpre1, dpre2, dpre0, dcnt,
                                              prof_bytes);
   MG_LAUNCHED(ctx);
   static OnceFlags attr_set;

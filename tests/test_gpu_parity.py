@@ -560,6 +560,48 @@ def test_fused_trunk_bit_identical(mg):
             assert np.isfinite(fused).all()
 
 
+def test_match_imgreps_grouped_and_separate(mg):
+    """CorrespondenceBank::MatchImgReps (correspondencebank.cpp:234-343, row a20): grouped matching pools the lists of the
+    group detectors per descriptor (queries from image 1, trains from image 2, in detector order) and matches once;
+    separate matching runs per (detector, descriptor); the bank returns descriptors, then detectors, in name order."""
+    import mods_light_zmq_b200 as M
+    def feats(n, seed, twin=None):
+        """random byte descriptors; with `twin`, the first half re-describes twin's regions (small noise): true matches"""
+        r = np.random.RandomState(seed)
+        f = np.zeros(n, M.FEATURE_DTYPE)
+        f["x"], f["y"] = r.uniform(0, 1000, n), r.uniform(0, 700, n)
+        f["s"] = 3.0
+        f["a11"] = f["a22"] = 1.0
+        f["desc"] = r.randint(0, 256, (n, 128))
+        if twin is not None:
+            k = min(n, len(twin)) // 2
+            f["desc"][:k] = np.clip(twin["desc"][:k] + r.randint(-6, 7, (k, 128)), 0, 255)
+            f["x"][:k], f["y"][:k] = twin["x"][:k] + 5.0, twin["y"][:k] - 3.0
+        return f
+    A1, B1, S1 = feats(300, 1), feats(150, 3), feats(200, 5)
+    A2, B2, S2 = feats(320, 2, A1), feats(170, 4, B1), feats(210, 6, S1)
+    lists = [(1, "HessianAffine", "ZMQ", A1), (2, "HessianAffine", "ZMQ", A2), (1, "MSER", "ZMQ", B1), (2, "MSER", "ZMQ", B2),
+             (1, "HessianAffine", "RootSIFT", S1), (2, "HessianAffine", "RootSIFT", S2)]
+
+    def expect(q, t, thr):
+        m = mg.match_fginn(q["desc"], t["desc"], np.c_[t["x"], t["y"]], ratio=thr)
+        return np.c_[q["x"][m["qi"]], q["y"][m["qi"]], t["x"][m["ti"]], t["y"][m["ti"]], m["d1"], m["d2"], m["ratio"]]
+    # grouped: one pooled ZMQ matching over both detectors; RootSIFT has no threshold -> not matched
+    got = mg.match_imgreps(lists, group_dets=("HessianAffine", "MSER"), group_descs=("ZMQ", "RootSIFT"), fginn={"ZMQ": 0.85})
+    ref = expect(np.concatenate([A1, B1]), np.concatenate([A2, B2]), 0.85)
+    assert len(ref) > 50 and np.array_equal(got, ref)
+    # separate: per detector x descriptor; the bank lists RootSIFT before ZMQ (descriptor name order), detectors by name
+    got = mg.match_imgreps(lists, sep_dets=("MSER", "HessianAffine"), sep_descs=("ZMQ", "RootSIFT"), fginn={"ZMQ": 0.85, "RootSIFT": 0.8})
+    ref = np.concatenate([expect(S1, S2, 0.8), expect(A1, A2, 0.85), expect(B1, B2, 0.85)])
+    assert np.array_equal(got, ref)
+    # both at once + a detector nobody extracted
+    got = mg.match_imgreps(lists, group_dets=("HessianAffine",), group_descs=("ZMQ",), sep_dets=("MSER", "SURF"), sep_descs=("ZMQ",),
+                           fginn={"ZMQ": 0.85})
+    ref = np.concatenate([expect(A1, A2, 0.85), expect(B1, B2, 0.85)])       # "Group" < "MSER"
+    assert np.array_equal(got, ref)
+    assert len(mg.match_imgreps(lists, group_dets=("HessianAffine",), group_descs=("ZMQ",), fginn={})) == 0
+
+
 # ------------------------------------------------------------------------------------------ whole pair (config 3)
 def test_pair_pipeline_config3(mg, oracle, synth_pair):
     """BASELINE config 3: single 1024x768 pair, Hessian-AffNet-OriNet-HardNet++ + linear FGINN + LO-RANSAC(H),

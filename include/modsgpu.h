@@ -396,6 +396,12 @@ int  modsgpu_match_imgreps(modsgpu_ctx* ctx, const modsgpu_region_list* lists, i
                            const char* group_descriptors, const char* separate_detectors, const char* separate_descriptors,
                            const char* fginn_thresholds, double* out, int capacity, int* n_out);
 
+/* DuplicateFiltering + LORANSACFiltering (the second half of modsgpu_match_features) on tentatives matched elsewhere, e.g. by
+ * several GPUs that each ran modsgpu_match_fginn on a slice of the query rows (config 5, mods_dist.py).  m in query order. */
+int  modsgpu_verify_matches(modsgpu_ctx* ctx, const modsgpu_feature* f1, int n1, const modsgpu_feature* f2, int n2,
+                            const modsgpu_match* m, int nm, int use_F, unsigned long long seed, modsgpu_mods_result* res,
+                            double* inlier_xy, int capacity);
+
 /* test-only: one 128x32x64 GEMM through the tcgen05 descriptor conventions of the dense kernels */
 int  modsgpu_debug_umma_probe(modsgpu_ctx* ctx, const float* A, const float* B, float* D, int swap_lbo_sbo);
 /* test / profiling only: cycles per tcgen05.mma (M128 K16) for a given operand-descriptor configuration;

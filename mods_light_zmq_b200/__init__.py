@@ -471,6 +471,18 @@ class ModsGpu:
         return dict(regions=list(res.regions), tentatives=res.tentatives, unique_tentatives=res.unique_tentatives,
                     inliers=res.inliers, model=np.array(list(res.model)), inlier_xy=xy[:min(res.inliers, capacity)].copy())
 
+    def verify_matches(self, f1, f2, matches, use_F=False, seed=12345, capacity=8192):
+        """modsgpu_verify_matches: duplicate filter + LO-RANSAC + empirical checks on tentatives matched elsewhere"""
+        f1 = np.ascontiguousarray(f1, FEATURE_DTYPE)
+        f2 = np.ascontiguousarray(f2, FEATURE_DTYPE)
+        matches = np.ascontiguousarray(matches, MATCH_DTYPE)
+        res = ModsResult()
+        xy = np.zeros((capacity, 4), np.float64)
+        self._check(self.lib.modsgpu_verify_matches(self.ctx, _p(f1), len(f1), _p(f2), len(f2), _p(matches), len(matches),
+                                                    int(bool(use_F)), C.c_ulonglong(seed), C.byref(res), _p(xy), capacity))
+        return dict(regions=list(res.regions), tentatives=res.tentatives, unique_tentatives=res.unique_tentatives,
+                    inliers=res.inliers, model=np.array(list(res.model)), inlier_xy=xy[:min(res.inliers, capacity)].copy())
+
     def ransac_F(self, u, th=16.0, conf=0.99, max_samples=1000000, sym_check=1, seed=12345):
         """modsgpu_ransac_F: LO-RANSAC for a fundamental matrix (exp_ransacFcustom, matching.cpp:722)."""
         u = np.ascontiguousarray(u, np.float64)

@@ -78,13 +78,53 @@ def gpu_extractor(device):
 
 
 def extract_features_batch(img_fnames, out_fnames, extractor, rank=0, world=1, dist=None, log=None, fmt=None):
-    """Process this rank's share; returns (on rank 0) the list of region counts per image, -1 for skipped/failed."""
+    """Process this rank's share; returns (on rank 0) the list of region counts per image, -1 for skipped/failed.
+    extractor: one callable, or a list of callables (one modsgpu context each): the rank's images are then dealt to as
+    many threads, so that the host side of one image (read, H2D, file writing) overlaps the kernels of another."""
     import mods_light_zmq_b200 as M
     if len(img_fnames) != len(out_fnames):
         raise ValueError("Length of input and output file lists are not equal %d %d" % (len(img_fnames), len(out_fnames)))
     n = len(img_fnames)
     counts = np.full(n, -2, np.int64)          # -2: not mine
-    for i in shard_indices(n, rank, world):
+    mine = shard_indices(n, rank, world)
+    extractors = list(extractor) if isinstance(extractor, (list, tuple)) else [extractor]
+
+    def work(t):
+        _extract_some(mine[t::len(extractors)], img_fnames, out_fnames, extractors[t], counts, log, fmt)
+    if len(extractors) == 1:
+        work(0)
+    else:
+        import threading
+        errs = []
+
+        def guarded(t):
+            try:
+                work(t)
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+        ths = [threading.Thread(target=guarded, args=(t,)) for t in range(len(extractors))]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+        if errs:
+            raise errs[0]
+    if dist is not None and world > 1:
+        import torch
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        t = torch.from_numpy(counts).to(dev)
+        lst = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
+        dist.gather(t, lst, dst=0)
+        if rank != 0:
+            return None
+        allc = torch.stack(lst).cpu().numpy()
+        counts = allc.max(axis=0)               # every image has exactly one owner (>= -1), the rest say -2
+    return counts.tolist()
+
+
+def _extract_some(indices, img_fnames, out_fnames, extractor, counts, log, fmt):
+    import mods_light_zmq_b200 as M
+    for i in indices:
         out = out_fnames[i]
         if os.path.exists(out) or os.path.exists(out + "ZMQ"):
             counts[i] = -1                      # "exists, skip"
@@ -101,23 +141,20 @@ def extract_features_batch(img_fnames, out_fnames, extractor, rank=0, world=1, d
         counts[i] = len(feats)
         if log:
             log("%d %s %s %d" % (i, img_fnames[i], out, len(feats)))
-    if dist is not None and world > 1:
-        import torch
-        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
-        t = torch.from_numpy(counts).to(dev)
-        lst = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
-        dist.gather(t, lst, dst=0)
-        if rank != 0:
-            return None
-        allc = torch.stack(lst).cpu().numpy()
-        counts = allc.max(axis=0)               # every image has exactly one owner (>= -1), the rest say -2
-    return counts.tolist()
 
 
 def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
+    contexts, quiet = 4, False
+    if "--contexts" in argv:
+        k = argv.index("--contexts")
+        contexts = max(1, int(argv[k + 1]))
+        del argv[k:k + 2]
+    if "--quiet" in argv:
+        argv.remove("--quiet")
+        quiet = True
     if len(argv) < 2:
-        print("Usage: python -m mods_light_zmq_b200.batch imfnames.txt out_keys.txt", file=sys.stderr)
+        print("Usage: python -m mods_light_zmq_b200.batch imfnames.txt out_keys.txt [--contexts K] [--quiet]", file=sys.stderr)
         return 1
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -130,12 +167,30 @@ def main(argv=None):
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    ext = gpu_extractor(local_rank)
-    counts = extract_features_batch(imgs, outs, ext, rank, world, dist, log=lambda s: print(s, flush=True))
-    ext.close()
+    import time
+    exts = [gpu_extractor(local_rank) for _ in range(contexts)]        # K contexts (streams) per GPU
+    # every context runs this rank's first image three times before the clock starts: workspace growth, the detector's
+    # graph capture and the first-use costs of the kernels are not part of the batch's throughput
+    mine0 = shard_indices(len(imgs), rank, world)
+    if mine0:
+        try:
+            warm = read_image_bgr(imgs[mine0[0]])
+            for e in exts:
+                for _ in range(3):
+                    e(warm)
+        except (IOError, OSError, ValueError):
+            pass
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    counts = extract_features_batch(imgs, outs, exts, rank, world, dist, log=None if quiet else (lambda s: print(s, flush=True)))
+    sec = time.perf_counter() - t0
+    for e in exts:
+        e.close()
     if rank == 0:
         done = [c for c in counts if c >= 0]
-        print("images %d, extracted %d, skipped %d, regions %d" % (len(counts), len(done), len(counts) - len(done), sum(done)))
+        print("images %d, extracted %d, skipped %d, regions %d, %.2f s, %.1f images/s on %d rank(s) x %d contexts" %
+              (len(counts), len(done), len(counts) - len(done), sum(done), sec, len(done) / max(sec, 1e-9), world, contexts))
     if dist is not None:
         dist.destroy_process_group()
     return 0

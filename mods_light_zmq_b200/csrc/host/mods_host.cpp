@@ -487,19 +487,51 @@ void OxAffEllipse(const AffineKeypoint& k, float& a, float& b, float& c) {
   a = (float)(m22 * q); b = (float)(-m12 * q); c = (float)(m11 * q);
 }
 
+// operator<<(ostream, float / double) with the default format = printf("%g") (6 significant digits); descriptor entries
+// are small integers almost always, which a table prints without any formatting call.  Byte-identical to the iostream
+// form the reference writes (the writer tests compare with files produced through std::ofstream).
+namespace {
+struct NumText {
+  char txt[256][4];
+  unsigned char len[256];
+  NumText() { for (int i = 0; i < 256; i++) len[i] = (unsigned char)snprintf(txt[i], 4, "%d", i); }
+};
+inline void put_g(std::string& out, double v) {
+  char buf[40];
+  const int n = snprintf(buf, sizeof(buf), "%g", v);
+  out.append(buf, (size_t)n);
+}
+inline void put_desc(std::string& out, float v) {
+  static const NumText T;
+  const int iv = (int)v;
+  if (v >= 0.f && v < 256.f && (float)iv == v) out.append(T.txt[iv], T.len[iv]);
+  else put_g(out, (double)v);
+}
+}  // namespace
+
 int SaveRegionsMichal(const AffineRegionVector& regions, const std::string& fname) {
-  std::ofstream kpfile(fname);
-  if (!kpfile.is_open()) return -1;
-  kpfile << "128" << std::endl;
-  kpfile << regions.size() << std::endl;
+  std::string out;
+  out.reserve(regions.size() * 460 + 64);
+  out += "128\n";
+  out += std::to_string(regions.size());
+  out += "\n";
   for (const AffineRegion& ar : regions) {
     float a, b, c;
     OxAffEllipse(ar.reproj_kp, a, b, c);
-    kpfile << ar.reproj_kp.x << " " << ar.reproj_kp.y << " " << a << " " << b << " " << c << " ";
-    for (size_t i = 0; i < ar.desc.size(); i++) kpfile << ar.desc[i] << " ";
-    kpfile << std::endl;
+    put_g(out, ar.reproj_kp.x); out += ' ';
+    put_g(out, ar.reproj_kp.y); out += ' ';
+    put_g(out, (double)a); out += ' ';
+    put_g(out, (double)b); out += ' ';
+    put_g(out, (double)c); out += ' ';
+    const size_t nd = ar.desc.size();
+    const float* d = ar.desc.data();
+    for (size_t i = 0; i < nd; i++) { put_desc(out, d[i]); out += ' '; }
+    out += '\n';
   }
-  return kpfile.good() ? 0 : -1;
+  FILE* f = fopen(fname.c_str(), "wb");
+  if (!f) return -1;
+  const bool ok = fwrite(out.data(), 1, out.size(), f) == out.size();
+  return (fclose(f) == 0 && ok) ? 0 : -1;
 }
 
 // matching.cpp:356-460 (vector_matcher = linear): list1 = queries (image 1), list2 = train (image 2)
@@ -1127,10 +1159,13 @@ extern "C" int modsgpu_write_oxaff(const char* path, const modsgpu_feature* f, i
   using namespace modsb200;
   if (!path || n < 0 || (n > 0 && !f)) return MODSGPU_EINVAL;
   AffineRegionVector v((size_t)n);
+  auto blk = std::make_shared<std::vector<float>>((size_t)n * 128);
+  for (int i = 0; i < n; i++) memcpy(blk->data() + (size_t)i * 128, f[i].desc, 512);
+  const std::shared_ptr<const std::vector<float>> cblk = blk;
   for (int i = 0; i < n; i++) {
     AffineKeypoint& k = v[i].reproj_kp;
     k.x = f[i].x; k.y = f[i].y; k.s = f[i].s; k.a11 = f[i].a11; k.a12 = f[i].a12; k.a21 = f[i].a21; k.a22 = f[i].a22;
-    v[i].desc.assign(f[i].desc, f[i].desc + 128);
+    v[i].desc.view(cblk, (size_t)i * 128, 128);
   }
   return SaveRegionsMichal(v, path) ? MODSGPU_EIO : 0;
 }
@@ -1265,13 +1300,9 @@ extern "C" int modsgpu_read_regions_text(const char* path, modsgpu_feature** out
 
 // mods.cpp:216-229 (`read_pre_extracted`) + :262-356: two pre-extracted region lists -> FGINN tentatives -> duplicate
 // filter -> LO-RANSAC.  The same three calls MODSPair makes per step.
-extern "C" int modsgpu_match_features(modsgpu_ctx* ctx, const modsgpu_feature* f1, int n1, const modsgpu_feature* f2, int n2,
-                                      int desc_dim, double fginn_threshold, int use_F, unsigned long long seed,
-                                      modsgpu_mods_result* res, double* inlier_xy, int capacity) {
+static void features_to_lists(const modsgpu_feature* f1, int n1, const modsgpu_feature* f2, int n2, int desc_dim,
+                              modsb200::AffineRegionVector (&l)[2]) {
   using namespace modsb200;
-  if (!ctx || !res || n1 < 0 || n2 < 0 || (n1 > 0 && !f1) || (n2 > 0 && !f2) || desc_dim < 1 || desc_dim > 128 || capacity < 0)
-    return MODSGPU_EINVAL;
-  AffineRegionVector l[2];
   const modsgpu_feature* src[2] = {f1, f2};
   const int cnt[2] = {n1, n2};
   for (int k = 0; k < 2; k++) {
@@ -1291,15 +1322,13 @@ extern "C" int modsgpu_match_features(modsgpu_ctx* ctx, const modsgpu_feature* f
       l[k][i].desc.view(cblk, (size_t)i * desc_dim, (size_t)desc_dim);
     }
   }
-  memset(res, 0, sizeof(*res));
-  res->steps_done = 1;
-  res->regions[0] = n1; res->regions[1] = n2;
+}
+// DuplicateFiltering + LORANSACFiltering + result packing shared by modsgpu_match_features / modsgpu_verify_matches
+static int verify_tentatives(modsgpu_ctx* ctx, modsb200::TentativeCorrespListExt& tent, int use_F, unsigned long long seed,
+                             modsgpu_mods_result* res, double* inlier_xy, int capacity) {
+  using namespace modsb200;
   MatchPars mp;
-  mp.FGINNThreshold = fginn_threshold;
-  TentativeCorrespListExt tent, verified;
-  int nt = MatchFlannFGINN(ctx, l[0], l[1], tent, mp);
-  if (nt < 0) return nt;
-  res->tentatives = nt;
+  TentativeCorrespListExt verified;
   int nu = DuplicateFiltering(ctx, tent, mp.doubleFilteringRadius);
   if (nu < 0) return nu;
   res->unique_tentatives = nu;
@@ -1314,6 +1343,60 @@ extern "C" int modsgpu_match_features(modsgpu_ctx* ctx, const modsgpu_feature* f
     inlier_xy[4 * i + 2] = c.second.reproj_kp.x; inlier_xy[4 * i + 3] = c.second.reproj_kp.y;
   }
   return 0;
+}
+extern "C" int modsgpu_match_features(modsgpu_ctx* ctx, const modsgpu_feature* f1, int n1, const modsgpu_feature* f2, int n2,
+                                      int desc_dim, double fginn_threshold, int use_F, unsigned long long seed,
+                                      modsgpu_mods_result* res, double* inlier_xy, int capacity) {
+  using namespace modsb200;
+  if (!ctx || !res || n1 < 0 || n2 < 0 || (n1 > 0 && !f1) || (n2 > 0 && !f2) || desc_dim < 1 || desc_dim > 128 || capacity < 0)
+    return MODSGPU_EINVAL;
+  AffineRegionVector l[2];
+  features_to_lists(f1, n1, f2, n2, desc_dim, l);
+  memset(res, 0, sizeof(*res));
+  res->steps_done = 1;
+  res->regions[0] = n1; res->regions[1] = n2;
+  MatchPars mp;
+  mp.FGINNThreshold = fginn_threshold;
+  TentativeCorrespListExt tent;
+  int nt = MatchFlannFGINN(ctx, l[0], l[1], tent, mp);
+  if (nt < 0) return nt;
+  res->tentatives = nt;
+  return verify_tentatives(ctx, tent, use_F, seed, res, inlier_xy, capacity);
+}
+// The second half of modsgpu_match_features on tentatives matched elsewhere -- e.g. by several GPUs, each running
+// modsgpu_match_fginn on its slice of the query rows (mods_light_zmq_b200/mods_dist.py): m[k].qi / .ti index f1 / f2, the
+// list must be in query order (the order MatchFlannFGINN appends in, matching.cpp:430-455).
+extern "C" int modsgpu_verify_matches(modsgpu_ctx* ctx, const modsgpu_feature* f1, int n1, const modsgpu_feature* f2, int n2,
+                                      const modsgpu_match* m, int nm, int use_F, unsigned long long seed, modsgpu_mods_result* res,
+                                      double* inlier_xy, int capacity) {
+  using namespace modsb200;
+  if (!ctx || !res || n1 < 0 || n2 < 0 || nm < 0 || (n1 > 0 && !f1) || (n2 > 0 && !f2) || (nm > 0 && !m) || capacity < 0) return MODSGPU_EINVAL;
+  memset(res, 0, sizeof(*res));
+  res->steps_done = 1;
+  res->regions[0] = n1; res->regions[1] = n2;
+  // only the matched regions are materialised, and without their descriptors: nothing after the matcher reads them
+  auto region_of = [](const modsgpu_feature& f, int id, int img) {
+    AffineRegion r;
+    AffineKeypoint& kp = r.reproj_kp;
+    kp.x = f.x; kp.y = f.y; kp.s = f.s; kp.a11 = f.a11; kp.a12 = f.a12; kp.a21 = f.a21; kp.a22 = f.a22;
+    kp.response = f.response; kp.octave_number = f.octave; kp.sub_type = f.type;
+    r.det_kp = kp;
+    r.id = id; r.img_id = img; r.img_reproj_id = f.view; r.type = f.type;
+    return r;
+  };
+  TentativeCorrespListExt tent;
+  tent.TCList.reserve(nm);
+  for (int k = 0; k < nm; k++) {
+    if (m[k].qi < 0 || m[k].qi >= n1 || m[k].ti < 0 || m[k].ti >= n2) return MODSGPU_EINVAL;
+    TentativeCorrespExt tc;
+    tc.first = region_of(f1[m[k].qi], m[k].qi, 0);
+    tc.second = region_of(f2[m[k].ti], m[k].ti, 1);
+    tc.secondbad_idx = m[k].tj_bad;
+    tc.d1 = m[k].d1; tc.d2 = m[k].d2; tc.ratio = m[k].ratio;
+    tent.TCList.push_back(tc);
+  }
+  res->tentatives = nm;
+  return verify_tentatives(ctx, tent, use_F, seed, res, inlier_xy, capacity);
 }
 
 // MODS run over an iteration schedule (mods.cpp:202-356, HessianAffine steps)

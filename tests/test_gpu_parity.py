@@ -602,6 +602,23 @@ def test_match_imgreps_grouped_and_separate(mg):
     assert len(mg.match_imgreps(lists, group_dets=("HessianAffine",), group_descs=("ZMQ",), fginn={})) == 0
 
 
+def test_verify_matches_equals_match_features(mg, synth_pair):
+    """The matcher sharded by query rows (config 5): slices of the query list matched separately and concatenated, then
+    modsgpu_verify_matches, give exactly modsgpu_match_features' result."""
+    from mods_light_zmq_b200 import synth, mods_dist as D
+    a, b, _ = synth_pair
+    f1 = mg.extract_features(mg.image_from_bgr8(synth.gray_to_bgr(a)))
+    f2 = mg.extract_features(mg.image_from_bgr8(synth.gray_to_bgr(b)))
+    whole = mg.match_features(f1, f2, seed=3)
+    match_slice, verify = D.gpu_sharded_match_callables(mg, seed=3)
+    rows = np.concatenate([match_slice(f1, f2, *D.query_slice(len(f1), r, 3), 0.8) for r in range(3)])
+    parts = verify(f1, f2, rows)
+    assert parts["tentatives"] == whole["tentatives"] > 1000
+    for k in ("unique_tentatives", "inliers"):
+        assert parts[k] == whole[k], k
+    assert np.array_equal(parts["model"], whole["model"]) and np.array_equal(parts["inlier_xy"], whole["inlier_xy"])
+
+
 # ------------------------------------------------------------------------------------------ whole pair (config 3)
 def test_pair_pipeline_config3(mg, oracle, synth_pair):
     """BASELINE config 3: single 1024x768 pair, Hessian-AffNet-OriNet-HardNet++ + linear FGINN + LO-RANSAC(H),

@@ -193,6 +193,80 @@ def test_mods_views_world2_equals_world1(tmp_path):
     assert two_s[0][7] == two_s[1][7] == one_s[7]        # the broadcast verified count
 
 
+SHARD_MATCH_WORKER = r'''
+import os, sys, zlib
+import numpy as np
+sys.path.insert(0, %(root)r)
+import torch.distributed as dist
+import mods_light_zmq_b200 as M
+from mods_light_zmq_b200 import mods_dist as D
+from oracle import pyoracle as O          # the CPU matcher stands in for modsgpu_match_fginn (tests only)
+
+def fake_extract_view(k, view):
+    seed = zlib.crc32(np.array([k, view["tilt"], view["phi"], view["zoom"]], np.float64).tobytes()) & 0x7fffffff
+    rng = np.random.RandomState(seed)
+    n = 40 + seed %% 30
+    f = np.zeros(n, M.FEATURE_DTYPE)
+    base = np.random.RandomState(7).randint(0, 256, (64, 128))          # shared by both images: true matches exist
+    pick = rng.randint(0, 64, n)
+    f["x"], f["y"], f["s"] = pick * 10.0 + rng.uniform(0, 2, n), pick * 5.0 + rng.uniform(0, 2, n), 3.0
+    f["a11"], f["a22"] = 1.0, 1.0
+    f["desc"] = np.clip(base[pick] + rng.randint(-5, 6, (n, 128)), 0, 255)
+    return f
+
+def match_slice(f1, f2, lo, hi, fginn):
+    m = O.match_fginn(f1["desc"][lo:hi], np.zeros((hi - lo, 2)), f2["desc"], np.c_[f2["x"], f2["y"]], ratio=fginn)
+    m = m.astype(M.MATCH_DTYPE)
+    m["qi"] += lo
+    return m
+
+seen = {}
+def verify(f1, f2, rows):
+    seen["rows"] = rows
+    return dict(inliers=len(rows), tentatives=len(rows))
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+d = None
+if world > 1:
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=rank, world_size=world)
+    d = dist
+steps = [dict(tilts=[1.0, 2.0], phi=360.0)]
+r = D.mods_pair_sharded(fake_extract_view, None, steps, rank, world, d, None, min_matches=10 ** 9, match_slice=match_slice, verify=verify)
+rows = seen.get("rows")
+print("RESULT", rank, r["regions"][0], r["regions"][1], r["inliers"], -1 if rows is None else zlib.crc32(rows.tobytes()),
+      -1 if rows is None else int((np.diff(rows["qi"]) > 0).all()))
+if d is not None:
+    dist.destroy_process_group()
+'''
+
+
+def test_sharded_matcher_world2_equals_world1(tmp_path):
+    """mods_dist.py with the matcher sharded by query rows: the tentative rows rank 0 verifies with two ranks are the
+    one-rank list byte for byte (a query's FGINN result depends on its own row only; slices are concatenated in rank
+    order), and every rank learns the verified count."""
+    def run(tag, world, port):
+        script = tmp_path / (tag + "_worker.py")
+        script.write_text(SHARD_MATCH_WORKER % {"root": ROOT, "port": port})
+        procs = []
+        for r in range(world):
+            env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), OMP_NUM_THREADS="1")
+            procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+        out = []
+        for p in procs:
+            o, e = p.communicate(timeout=240)
+            assert p.returncode == 0, e[-2000:]
+            out.append(o.split("RESULT")[1].split())
+        return out
+    one = run("s1", 1, 29631)[0]
+    two = run("s2", 2, 29632)
+    assert int(one[3]) > 20 and one[5] == "1"                        # tentatives exist, in query order
+    assert two[0][1:5] == one[1:5] and two[0][5] == "1"              # same lists, same tentative rows on rank 0
+    assert two[1][1:4] == one[1:4] and two[1][4] == "-1"             # rank 1 verified nothing but knows the count
+    from mods_light_zmq_b200 import mods_dist as D
+    assert [D.query_slice(10, r, 3) for r in range(3)] == [(0, 4), (4, 7), (7, 10)]
+    assert D.query_slice(0, 1, 2) == (0, 0)
+
+
 def test_step_views_follow_SetVSPars_history():
     from mods_light_zmq_b200 import mods_dist as D
     hist = []

@@ -41,6 +41,7 @@ struct ConvW { __half* w = nullptr; float* b = nullptr; };
 struct NetWeights {
   int net = 0, C1 = 0, out_dim = 0;
   float* c1_w = nullptr; float* c1_b = nullptr;
+  __half* c1_split = nullptr;    // conv1 weights for k_conv1_mma: [4 K-planes][C1][8] fp16, K = wh | wh | wl | 0
   ConvW conv[5];                 // conv2..conv6 in UMMA block order
   __half* head_w16 = nullptr;    // HardNet head, UMMA block order
   float* head_w32 = nullptr;     // AffNet / OriNet head, k_head_small's shared-memory layout
@@ -83,6 +84,7 @@ __device__ __forceinline__ int live_patches(int np, const int* __restrict__ cnt_
   return live < 0 ? 0 : (live < np ? live : np);
 }
 
+constexpr int C1_PW_ = 40;
 constexpr int C1_PW = 40;   // padded row: pixel x lives at column x + 4 (16-byte aligned float4 stores), halo at 3 and 36
 template <int C1>
 __global__ void __launch_bounds__(160, 3)
@@ -184,6 +186,212 @@ k_conv1(const uint8_t* __restrict__ patches, int np, const float* __restrict__ w
       if (lane == 0) mbar_arrive(empty + bf);
     }
   }
+}
+
+// =================================================================================================
+// conv1 (+ input normalisation) on the tensor pipe
+//
+// The first layer has ONE input channel: 9 multiply-adds per output value, 147k (C1 = 16) / 295k (C1 = 32) per patch, which
+// on CUDA cores costs ~7k / ~14k warp instructions per patch (k_conv1, FMA pipe 43 % busy).  As a GEMM it is
+// [1089 slots x K] * [K x C1] with K = 9 taps -- far too thin for fp16 operands to be exact enough on their own, so both
+// operands are split: x = xh + xl, w = wh + wl (fp16 each) and K = 32 carries  xh*wh (9+1) | xl*wh (9+1) | xh*wl (9+1) | 0 (2);
+// the dropped xl*wl term is 2^-22 relative, i.e. the result is fp32-accurate (products of fp16 pairs are exact in the fp32
+// accumulator).  Per 128-slot M tile: 128 worker threads write one im2col row each (9 shared-memory loads, the hi / lo
+// splits, 64 bytes out), one thread of a fifth warp issues TWO tcgen05.mma (K = 2 x 16), and the same 128 workers drain the
+// previous tile's accumulator (bias + ReLU + fp16, conv1's map in the layout conv2 reads).  ~2.2k warp instructions per patch instead of 7-14k; what remains is
+// the map's HBM write.  Results differ from k_conv1's in the last fp32 bits only (same values after the fp16 rounding of
+// the map except where the sum sits on a rounding boundary).  Opt-in: see conv1_mma_enabled() for why it is not the default.
+// =================================================================================================
+template <int C1>
+struct Conv1MmaCfg {
+  static constexpr int PT = 33, PP = PT * PT, NT = (PP + 127) / 128;
+  static constexpr int A_BYTES = 4 * 128 * 16;                 // [4 K-planes][128 rows][8 halves]
+  static constexpr int W_BYTES = 4 * C1 * 16;                  // [4 K-planes][C1 rows][8 halves]
+  // The chain  row stores -> mbarrier -> tcgen05.mma -> commit -> mbarrier -> tcgen05.ld  of ONE tile is ~1 us long however
+  // small the MMA is, so the pipeline has to be deep: TS accumulators in TMEM (a worker drains tile k - (TS - 1) after it
+  // built tile k) and TS + 1 operand stages.  With two accumulators and three stages the kernel was no faster than the
+  // CUDA-core version, whatever the warp roles.
+  static constexpr int TS = C1 == 16 ? 6 : 4, LAG = TS - 1;
+  static constexpr int NSTAGE = TS + 1;
+  static constexpr int TMEM_COLS = 128;          // >= TS * C1, a power of two
+  static constexpr int SMEM_DYN = NSTAGE * A_BYTES;
+};
+
+template <int C1>
+__global__ void __launch_bounds__(160, 3)
+k_conv1_mma(const uint8_t* __restrict__ patches, int np, const __half* __restrict__ wsplit, const float* __restrict__ b,
+            __half* __restrict__ out, size_t out_slots, const int* __restrict__ cnt_dev, int cnt_base) {
+  using Cfg = Conv1MmaCfg<C1>;
+  np = live_patches(np, cnt_dev, cnt_base);
+  extern __shared__ __align__(1024) uint8_t a_s[];            // NSTAGE operand stages
+  __shared__ __align__(128) uint8_t w_s[Cfg::W_BYTES];
+  __shared__ __align__(16) float P[34][C1_PW_];               // normalised patch, pixel (y, x) at P[y + 1][x + 4], zero halo
+  __shared__ __align__(16) float bs[C1];
+  __shared__ unsigned red[2][4];
+  __shared__ uint64_t bars[2 * Cfg::NSTAGE + 2 * Cfg::TS];
+  __shared__ uint32_t tmem_slot;
+  uint64_t* a_full = bars;                    // [NSTAGE] 4 worker warps
+  uint64_t* a_empty = a_full + Cfg::NSTAGE;   // [NSTAGE] MMAs retired
+  uint64_t* t_full = a_empty + Cfg::NSTAGE;   // [TS]
+  uint64_t* t_empty = t_full + Cfg::TS;       // [TS] 4 worker warps
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  for (int i = tid; i < 34 * C1_PW_; i += 160) (&P[0][0])[i] = 0.f;
+  for (int i = tid; i < Cfg::W_BYTES / 16; i += 160) reinterpret_cast<uint4*>(w_s)[i] = __ldg(reinterpret_cast<const uint4*>(wsplit) + i);
+  if (tid < C1) bs[tid] = b[tid];
+  fence_proxy_async();
+  if (tid == 0) {
+    for (int i = 0; i < Cfg::NSTAGE; i++) { mbar_init(a_full + i, 4); mbar_init(a_empty + i, 1); }
+    for (int i = 0; i < Cfg::TS; i++) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 4); }
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc<Cfg::TMEM_COLS>(&tmem_slot);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+  const int n_my = (int)blockIdx.x < np ? (np - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (warp < 4) {
+    // ---- workers (4 warps = the 128 rows of an M tile = the 128 TMEM lanes): per patch the normalisation, then per tile
+    //      build row `tid` of tile k and drain the accumulator of tile k-1 -- no warp sits in a barrier wait while others work
+    //      (a first version with dedicated epilogue warps spent three quarters of its issued instructions spinning)
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    auto drain = [&](int tc) {          // accumulator of running tile tc -> bias + ReLU + fp16 -> HBM
+      const int ts = tc % Cfg::TS, tph = (tc / Cfg::TS) & 1;
+      const size_t patch = (size_t)blockIdx.x + (size_t)(tc / Cfg::NT) * gridDim.x;
+      const int t = tc % Cfg::NT;
+      const int idx = t * 128 + tid;
+      const int yy = idx / Cfg::PT, x = idx - yy * Cfg::PT;
+      const bool valid = idx < Cfg::PP && yy >= 1 && x < 32;
+      mbar_wait(t_full + ts, tph);
+      fence_after_sync();
+#pragma unroll
+      for (int cc = 0; cc < C1 / 16; cc++) {
+        float v[16];
+        tmem_ld16(lane_base + ts * C1 + cc * 16, v);
+        if (valid) {
+          uint32_t h[8];
+#pragma unroll
+          for (int e = 0; e < 8; e++) h[e] = relu_pack_h2(v[2 * e] + bs[cc * 16 + 2 * e], v[2 * e + 1] + bs[cc * 16 + 2 * e + 1]);
+          __half* o = out + ((size_t)(cc * 2) * out_slots + (size_t)FS + patch * Cfg::PP + idx) * 8;
+          *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(o + out_slots * 8) = make_uint4(h[4], h[5], h[6], h[7]);
+        }
+      }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty + ts);
+    };
+    int tc = 0;
+    uint2 px = make_uint2(0, 0);
+    if (n_my > 0) px = __ldg(reinterpret_cast<const uint2*>(patches + (size_t)blockIdx.x * 1024) + tid);
+    for (int it = 0; it < n_my; it++) {
+      const size_t patch = (size_t)blockIdx.x + (size_t)it * gridDim.x;
+      const uint32_t wd[2] = {px.x, px.y};                    // 8 pixels of row tid / 4
+      if (it + 1 < n_my) px = __ldg(reinterpret_cast<const uint2*>(patches + (patch + gridDim.x) * 1024) + tid);   // next patch in flight
+      unsigned s1 = 0, s2 = 0;
+#pragma unroll
+      for (int k = 0; k < 2; k++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) { const unsigned v = (wd[k] >> (8 * j)) & 255u; s1 += v; s2 += v * v; }
+      for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+      // every worker is done with the previous patch's P (and red[]) before either is overwritten
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (lane == 0) { red[0][warp] = s1; red[1][warp] = s2; }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      unsigned t1 = 0, t2 = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) { t1 += red[0][k]; t2 += red[1][k]; }
+      // torch.mean / torch.std (unbiased) of the 1024 pixels; (x-mean)/(std+1e-7) (desc_server.py:83-87), as k_conv1
+      const double mean_d = (double)t1 / 1024.0;
+      double var = ((double)t2 - (double)t1 * mean_d) / 1023.0;
+      if (var < 0) var = 0;
+      const float mean = (float)mean_d, sd = (float)sqrt(var) + 1e-7f;
+      {
+        const int y = tid >> 2, x0 = (tid & 3) * 8;
+        float* row = &P[y + 1][4 + x0];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          float4 f;
+          f.x = ((float)(wd[k] & 255u) - mean) / sd;
+          f.y = ((float)((wd[k] >> 8) & 255u) - mean) / sd;
+          f.z = ((float)((wd[k] >> 16) & 255u) - mean) / sd;
+          f.w = ((float)(wd[k] >> 24) - mean) / sd;
+          *reinterpret_cast<float4*>(row + 4 * k) = f;
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int t = 0; t < Cfg::NT; t++, tc++) {
+        const int idx = t * 128 + tid;
+        const int yy = idx / Cfg::PT, x = idx - yy * Cfg::PT, y = yy - 1;
+        const bool valid = idx < Cfg::PP && yy >= 1 && x < 32;
+        __half2 k2[16];
+        if (valid) {
+          float v[9];
+#pragma unroll
+          for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+            for (int dx = 0; dx < 3; dx++) v[dy * 3 + dx] = P[y + dy][x + dx + 3];
+          // K order (pairs, so that every conversion is a packed F2FP): xh0..7 | xh8 0 | xl0..7 | xl8 0 | xh0..7 | xh8 0 | 0 0
+          __half2 H[5], L[5];
+#pragma unroll
+          for (int k = 0; k < 5; k++) {
+            const float a0 = v[2 * k], a1 = k < 4 ? v[2 * k + 1] : 0.f;
+            H[k] = __floats2half2_rn(a0, a1);
+            const float2 back = __half22float2(H[k]);
+            L[k] = __floats2half2_rn(a0 - back.x, a1 - back.y);
+          }
+#pragma unroll
+          for (int k = 0; k < 5; k++) { k2[k] = H[k]; k2[5 + k] = L[k]; k2[10 + k] = H[k]; }
+          k2[15] = __float2half2_rn(0.f);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 16; k++) k2[k] = __float2half2_rn(0.f);
+        }
+        const int s = tc % Cfg::NSTAGE, ph = (tc / Cfg::NSTAGE) & 1;
+        mbar_wait(a_empty + s, ph ^ 1);
+        uint8_t* dst = a_s + s * Cfg::A_BYTES + tid * 16;
+#pragma unroll
+        for (int pl = 0; pl < 4; pl++)
+          *reinterpret_cast<uint4*>(dst + pl * 2048) = make_uint4(*reinterpret_cast<uint32_t*>(&k2[4 * pl]), *reinterpret_cast<uint32_t*>(&k2[4 * pl + 1]),
+                                                                  *reinterpret_cast<uint32_t*>(&k2[4 * pl + 2]), *reinterpret_cast<uint32_t*>(&k2[4 * pl + 3]));
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_full + s);
+        if (tc >= Cfg::LAG) drain(tc - Cfg::LAG);
+      }
+    }
+    for (int k = tc > Cfg::LAG ? tc - Cfg::LAG : 0; k < tc; k++) drain(k);
+  } else {
+    // ---- MMA issuer: two K = 16 steps per tile
+    constexpr uint32_t idesc = instr_desc_f16(C1);
+    const uint64_t a_desc0 = smem_desc(smem_u32(a_s), 2048, 128);
+    const uint64_t w_desc0 = smem_desc(smem_u32(w_s), C1 * 16, 128);
+    int tc = 0;
+    for (int it = 0; it < n_my; it++)
+#pragma unroll 1
+      for (int t = 0; t < Cfg::NT; t++, tc++) {
+        const int ts = tc % Cfg::TS, tph = (tc / Cfg::TS) & 1;
+        const int s = tc % Cfg::NSTAGE, ph = (tc / Cfg::NSTAGE) & 1;
+        while (!mbar_try_wait(t_empty + ts, tph ^ 1)) __nanosleep(20);
+        while (!mbar_try_wait(a_full + s, ph)) __nanosleep(20);
+        fence_after_sync();
+        const uint64_t a_tile = a_desc0 + (uint64_t)((s * Cfg::A_BYTES) >> 4);
+        const uint32_t d_tmem = tmem_base + ts * C1;
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 2; ks++)
+            mma_f16(d_tmem, a_tile + (uint64_t)(2 * ks * 128), w_desc0 + (uint64_t)(2 * ks * C1), idesc, ks != 0);
+          mma_commit(a_empty + s);
+          mma_commit(t_full + ts);
+        }
+        __syncwarp();
+      }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
 // =================================================================================================
@@ -1320,6 +1528,15 @@ int launch_conv(modsgpu_ctx* ctx, const __half* in, size_t in_slots, const ConvW
 
 // conv2..conv4 (C1 = 16) / conv2..conv3 (C1 = 32) in one launch (k_trunk).  MODSGPU_NO_FUSED_TRUNK=1 keeps the layer-by-layer
 // path (the parity test runs both and compares them bit for bit).
+// k_conv1_mma is OPT-IN (MODSGPU_CONV1_MMA=1, read per call).  Measured on B200 in three shapes (dedicated epilogue warps;
+// workers that build and drain; 4-6 accumulators deep): 0.26 / 0.18 ms per pair for C1 = 16 / 32 against 0.20 / 0.17 ms of
+// k_conv1 -- whatever the structure, because BOTH kernels sit on the same bound: conv1's map is 32 / 64 KB per patch of pure
+// HBM WRITE (1.02 GB per pair), and a write-only stream saturates near 2.5-2.9 TB/s on this part, not at the 6.5 TB/s of
+// the read + write copy peak (ncu: 195 MB written in 78 us, L2 hit rate 7 %).  The FMA kernel stays the product path.
+bool conv1_mma_enabled() {
+  const char* e = getenv("MODSGPU_CONV1_MMA");
+  return e && atoi(e) != 0;
+}
 bool fused_trunk_enabled() {      // read per call: the parity test switches paths inside one process
   const char* e = getenv("MODSGPU_NO_FUSED_TRUNK");
   return !(e && atoi(e) != 0);
@@ -1396,7 +1613,7 @@ int launch_conv12(modsgpu_ctx* ctx, const uint8_t* patches, const ConvW& w2, __h
 
 static void free_net(NetWeights* nw) {
   if (!nw) return;
-  cudaFree(nw->c1_w); cudaFree(nw->c1_b);
+  cudaFree(nw->c1_w); cudaFree(nw->c1_b); cudaFree(nw->c1_split);
   for (auto& c : nw->conv) { cudaFree(c.w); cudaFree(c.b); }
   cudaFree(nw->head_w16); cudaFree(nw->head_w32); cudaFree(nw->head_b);
   for (auto a : nw->act) cudaFree(a);
@@ -1431,6 +1648,23 @@ extern "C" int modsgpu_load_weights(modsgpu_ctx* ctx, modsgpu_net net, const cha
   if (!w1 || !b1) { delete nw; MG_FAIL(ctx, MODSGPU_EIO, "weights: c1_w/c1_b missing or wrong shape"); }
   MG_CUDA(ctx, upload(&nw->c1_w, w1->data.data(), w1->data.size() * 4));
   MG_CUDA(ctx, upload(&nw->c1_b, b1->data.data(), b1->data.size() * 4));
+  {
+    // split conv1 weights for the tensor-pipe kernel: B[k][n] in the K order of the im2col rows (three groups of 10:
+    // taps 0..8 + one zero): k = 0..9 wh (pairs with xh), 10..19 wh (pairs with xl), 20..29 wl (pairs with xh), 30..31 zero
+    std::vector<__half> ws((size_t)4 * C1 * 8);
+    for (int n = 0; n < C1; n++)
+      for (int k = 0; k < 32; k++) {
+        float v = 0.f;
+        const int grp = k / 10, tap = k % 10;
+        if (grp < 3 && tap < 9) {
+          const float w = w1->data[(size_t)n * 9 + tap];
+          const __half wh = __float2half_rn(w);
+          v = grp < 2 ? __half2float(wh) : w - __half2float(wh);
+        }
+        ws[((size_t)(k >> 3) * C1 + n) * 8 + (k & 7)] = __float2half_rn(v);
+      }
+    MG_CUDA(ctx, upload(&nw->c1_split, ws.data(), ws.size() * 2));
+  }
   {
     // k_conv12 reads conv1's weights from the constant bank, one slot per (device, net).  The first context that loads a
     // net on a device claims the slot; a context that loads DIFFERENT weights for it keeps the two-kernel path.
@@ -1529,7 +1763,16 @@ int mg_net_forward_enqueue(modsgpu_ctx* ctx, modsgpu_net net, const uint8_t* d_p
         if ((rc = launch_conv12<32, 2>(ctx, pin, nw->conv[0], nw->act[1], nw->slots[1], np))) return rc;
       } else {
         MG_PROF2(ctx, "k_conv1<32>", 1, 2.0 * np * 1024 * 9 * 32, (double)np * (1024.0 + 1024.0 * 32 * 2));
-        k_conv1<32><<<std::min(np, 3 * ctx->num_sms), 160, 0, ctx->stream>>>(pin, np, nw->c1_w, nw->c1_b, nw->act[0], nw->slots[0], cnt_dev, p0);
+        if (conv1_mma_enabled()) {
+          static OnceFlags c1attr;
+          if (c1attr.need(ctx->device)) {
+            MG_CUDA(ctx, cudaFuncSetAttribute(k_conv1_mma<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv1MmaCfg<32>::SMEM_DYN));
+            c1attr.set(ctx->device);
+          }
+          k_conv1_mma<32><<<std::min(np, 3 * ctx->num_sms), 160, Conv1MmaCfg<32>::SMEM_DYN, ctx->stream>>>(pin, np, nw->c1_split, nw->c1_b, nw->act[0], nw->slots[0], cnt_dev, p0);
+        }
+        else
+          k_conv1<32><<<std::min(np, 3 * ctx->num_sms), 160, 0, ctx->stream>>>(pin, np, nw->c1_w, nw->c1_b, nw->act[0], nw->slots[0], cnt_dev, p0);
         MG_LAUNCHED(ctx);
         if (fused_trunk_enabled()) {
           if ((rc = launch_trunk<32, 2>(ctx, nw->act[0], nw->slots[0], nw->conv, nw->act[2], nw->slots[2], np, p0, cnt_dev))) return rc;
@@ -1548,7 +1791,16 @@ int mg_net_forward_enqueue(modsgpu_ctx* ctx, modsgpu_net net, const uint8_t* d_p
                                          : launch_conv12<16, 1>(ctx, pin, nw->conv[0], nw->act[1], nw->slots[1], np)))) return rc;
       } else {
         MG_PROF2(ctx, "k_conv1<16>", 1, 2.0 * np * 1024 * 9 * 16, (double)np * (1024.0 + 1024.0 * 16 * 2));
-        k_conv1<16><<<std::min(np, 3 * ctx->num_sms), 160, 0, ctx->stream>>>(pin, np, nw->c1_w, nw->c1_b, nw->act[0], nw->slots[0], cnt_dev, p0);
+        if (conv1_mma_enabled()) {
+          static OnceFlags c1attr;
+          if (c1attr.need(ctx->device)) {
+            MG_CUDA(ctx, cudaFuncSetAttribute(k_conv1_mma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv1MmaCfg<16>::SMEM_DYN));
+            c1attr.set(ctx->device);
+          }
+          k_conv1_mma<16><<<std::min(np, 3 * ctx->num_sms), 160, Conv1MmaCfg<16>::SMEM_DYN, ctx->stream>>>(pin, np, nw->c1_split, nw->c1_b, nw->act[0], nw->slots[0], cnt_dev, p0);
+        }
+        else
+          k_conv1<16><<<std::min(np, 3 * ctx->num_sms), 160, 0, ctx->stream>>>(pin, np, nw->c1_w, nw->c1_b, nw->act[0], nw->slots[0], cnt_dev, p0);
         MG_LAUNCHED(ctx);
         if (fused_trunk_enabled()) {
           if ((rc = launch_trunk<16, 3>(ctx, nw->act[0], nw->slots[0], nw->conv, nw->act[3], nw->slots[3], np, p0, cnt_dev))) return rc;

@@ -61,6 +61,9 @@ extern "C" void modsgpu_destroy(modsgpu_ctx* ctx) {
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   if (ctx->ev_sync) cudaEventDestroy(ctx->ev_sync);
+  if (ctx->det_fork_ev) cudaEventDestroy(ctx->det_fork_ev);
+  if (ctx->det_join_ev) cudaEventDestroy(ctx->det_join_ev);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

@@ -88,6 +88,8 @@ struct modsgpu_ctx {
   int device = 0;
   int num_sms = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;          // side stream of the detector's fork (detect.cu); events of the fork / join
+  cudaEvent_t det_fork_ev = nullptr, det_join_ev = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // detector launch sequences captured as CUDA graphs, keyed by everything a launch argument depends on (mg_detect_graph)
   struct DetGraph { cudaGraphExec_t exec = nullptr; long long launches = 0; int uses = 0; };

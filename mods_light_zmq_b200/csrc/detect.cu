@@ -611,28 +611,35 @@ __global__ void k_resolve(const Cand* cands, const int* ncand_p, int cap, const 
   keys[i] = keep ? sort_key(k) : ~0ull;
   if (keep) atomicAdd(nkept, 1);
 }
-__global__ void k_rank_export(const Cand* cands, const int* ncand_p, int cap, const unsigned long long* keys,
-                              modsgpu_keypoint* out, const float* candA, float* outA) {
+// rank of a candidate = number of smaller keys (keys are unique: the low word is the visiting order).  64 candidates per
+// CTA, FOUR lanes per candidate (each compares a quarter of every 256-key tile): the scan over all n keys is the kernel's
+// whole latency and was 57 us per image with one thread per candidate and every CTA of the cap-sized grid walking it.
+__global__ void __launch_bounds__(256)
+k_rank_export(const Cand* cands, const int* ncand_p, int cap, const unsigned long long* keys,
+              modsgpu_keypoint* out, const float* candA, float* outA) {
   __shared__ unsigned long long tile[256];
-  int n = min(*ncand_p, cap);
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned long long mine = i < n ? keys[i] : ~0ull;
+  const int n = min(*ncand_p, cap);
+  if ((int)blockIdx.x * 64 >= n) return;                 // whole CTA beyond the list
+  const int i = blockIdx.x * 64 + (threadIdx.x >> 2), q = threadIdx.x & 3;
+  const unsigned long long mine = i < n ? keys[i] : ~0ull;
   int rank = 0;
   for (int base = 0; base < n; base += 256) {
-    int j = base + threadIdx.x;
-    tile[threadIdx.x] = j < n ? keys[j] : ~0ull;
+    const int j = base + threadIdx.x;
+    tile[threadIdx.x] = j < n ? keys[j] : ~0ull;         // padding keys are never smaller than a live key
     __syncthreads();
-    int lim = min(256, n - base);
-    for (int t = 0; t < lim; t++) rank += tile[t] < mine;
+#pragma unroll 16
+    for (int t = 0; t < 64; t++) rank += tile[4 * t + q] < mine;
     __syncthreads();
   }
-  if (i < n && mine != ~0ull) {
+  rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+  rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+  if (q == 0 && i < n && mine != ~0ull) {
     const Cand& k = cands[i];
     modsgpu_keypoint o;
     o.x = k.x; o.y = k.y; o.s = k.s; o.response = k.response; o.type = k.type; o.octave = k.octave;
     o.level = k.level; o.r0 = k.r0; o.c0 = k.c0; o.r = k.r; o.c = k.c; o.seq = 0;
     out[rank] = o;
-    if (candA) for (int q = 0; q < 4; q++) outA[4 * (size_t)rank + q] = candA[4 * (size_t)i + q];
+    if (candA) for (int e = 0; e < 4; e++) outA[4 * (size_t)rank + e] = candA[4 * (size_t)i + e];
   }
 }
 
@@ -853,6 +860,16 @@ int mg_detect_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
   const float finalThr = fixedTh ? p->threshold * p->threshold : 0.f;
   const float sigmaStep = std::pow(2.0f, 1.0f / (float)nS);
 
+  // fork / join across two streams (MODSGPU_DET_NO_FORK=1 keeps the linear chain; the per-kernel profiler needs it linear too)
+  static const bool no_fork = [] { const char* e = getenv("MODSGPU_DET_NO_FORK"); return e && atoi(e) != 0; }();
+  cudaStream_t const main_stream = ctx->stream;
+  bool fork = !no_fork && !ctx->prof.on && nS + 1 >= 2;
+  if (fork && !ctx->stream2) {
+    if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->det_fork_ev, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->det_join_ev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); fork = false; }
+  }
+  bool side_used = false;
   float pixelDistance = 1.0f;
   unsigned octave_base = 0;
   for (int o = 0; o < nOct; o++) {
@@ -888,8 +905,16 @@ int mg_detect_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
       float sigma = curSigma * std::sqrt(sigmaStep * sigmaStep - 1.0f);
       float s2 = curSigma * sigmaStep;
       float norm = s2 * s2;
+      // The last level of an octave (i = nS + 1) and its non-maximum suppression feed nothing downstream but the candidate
+      // list: they run on the context's side stream while the main stream halves level nS and starts the next octave
+      // (in the captured graph: a fork -- 30 instead of 41 kernels on the critical path of a 1024x768 image).
+      if (fork && i == nS + 1) {
+        MG_CUDA(ctx, cudaEventRecord(ctx->det_fork_ev, main_stream));
+        MG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->det_fork_ev, 0));
+        ctx->stream = ctx->stream2;
+      }
       int rc = launch_blur(ctx, Lv + px * (i - 1), Lv + px * i, Rv + px * i, w, h, sigma, norm * norm);
-      if (rc) return rc;
+      if (rc) { ctx->stream = main_stream; return rc; }
       if (i >= 2) {
         LevelArgs& L = na.lv[na.nlev++];
         L.low = Rv + px * (i - 2); L.cur = Rv + px * (i - 1); L.high = Rv + px * i;
@@ -914,11 +939,21 @@ int mg_detect_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
     if (iw > 0 && ih > 0 && na.nlev > 0) {
       dim3 blk(32, 8), grid(ceil_div(iw, 32), ceil_div(ih, 8), na.nlev);
       MG_PROF(ctx, "k_nms_localize", 0, (double)px * 4.0 * (na.nlev + 2));
-      k_nms_localize<<<grid, blk, 0, ctx->stream>>>(na, map, cands, counters, cap);
-      MG_LAUNCHED(ctx);
+      k_nms_localize<<<grid, blk, 0, ctx->stream>>>(na, map, cands, counters, cap);      // side stream when forked
+      ctx->launches++;
+      if (ctx->prof.open) mg_prof_end(ctx);
+      if (cudaGetLastError() != cudaSuccess) { ctx->stream = main_stream; MG_FAIL(ctx, MODSGPU_ECUDA, "k_nms_localize launch failed"); }
+    }
+    if (fork && ctx->stream != main_stream) {
+      side_used = true;
+      ctx->stream = main_stream;
     }
     octave_base += (unsigned)(px * nS);
     pixelDistance *= 2.0f;
+  }
+  if (side_used) {                        // join: the candidate list is complete once the side stream has drained
+    MG_CUDA(ctx, cudaEventRecord(ctx->det_join_ev, ctx->stream2));
+    MG_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->det_join_ev, 0));
   }
   int nb = ceil_div(cap, 256);
   MG_PROF(ctx, "k_resolve", 2, (double)cap);
@@ -957,7 +992,7 @@ int mg_detect_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
     outA = reinterpret_cast<float*>(ctx->det_out.as<modsgpu_keypoint>() + cap);
   }
   MG_PROF(ctx, "k_rank_export", 2, (double)cap);
-  k_rank_export<<<nb, 256, 0, ctx->stream>>>(cands, counters, cap, keys, ctx->det_out.as<modsgpu_keypoint>(), candA, outA);
+  k_rank_export<<<ceil_div(cap, 64), 256, 0, ctx->stream>>>(cands, counters, cap, keys, ctx->det_out.as<modsgpu_keypoint>(), candA, outA);
   MG_LAUNCHED(ctx);
   return 0;
 }

@@ -421,7 +421,7 @@ def run_gpu(args, rank, world, local_rank):
                 "frac_of_hbm_peak": work / (ms * 1e-3) / 1e9 / hbm_peak if ms > 0 else None}
     stages = {"cnn": stage(("k_conv", "k_head", "k_trunk", "k_patch_prep"), 1),
               "detect": stage(("k_gray", "k_blur", "k_response", "k_half", "k_nms", "k_resolve", "k_rank", "k_det", "k_pyr"), 0),
-              "sampler": stage(("k_sample", "k_large"), 0),
+              "sampler": stage(("k_sample", "k_large", "k_smp"), 0),
               "match": stage(("k_pack_desc", "k_dist", "k_select", "k_dup"), 1),
               "ransac": {"ms_per_pair": sum(v["ms"] for k, v in prof.items() if k.startswith(("k_rs", "k_rf"))) / n_prof},
               "all_kernels_ms_per_pair": total_kernel_ms / n_prof}

@@ -181,6 +181,13 @@ int  modsgpu_match_fginn(modsgpu_ctx* ctx, const float* q, int nq, const float* 
                          int dim, double ratio_thr, double contrad_dist, int nn,
                          modsgpu_match* out, int* nout, int* knn_idx, float* knn_dist);
 
+/* ---- binary descriptors (replaces MatchFLANNDistance matching.cpp:574-633 with binary_matcher = linear): the two nearest
+ *      train descriptors by Hamming distance over bytes = floor(entry); a match when d1 <= max_distance; ratio = d1 / d2
+ *      (tj_bad = the second neighbour).  q: nq x dim, t: nt x dim floats, dim = descriptor length in BYTES (32 for ORB),
+ *      a multiple of 4, <= 128.  Ties keep the lower train index (cvflann LinearIndex order). ------------------------ */
+int  modsgpu_match_hamming(modsgpu_ctx* ctx, const float* q, int nq, const float* t, int nt, int dim, double max_distance,
+                           modsgpu_match* out, int* nout);
+
 /* ---- duplicate filter (replaces DuplicateFiltering matching.cpp:2615-2679, mode bestFGINN;
  *      stable order on ties).  order_out: indices of the survivors in sorted order. ---------- */
 int  modsgpu_duplicate_filter(modsgpu_ctx* ctx, const double* xy1, const double* xy2, const double* ratio,
@@ -225,6 +232,13 @@ int  modsgpu_ransac_H_resid(modsgpu_ctx* ctx, const double* u, int T, const mods
  * HLAFCoef (12) or LAFCoef (2); keep: n bytes; model_out: H row-major image 1 -> 2, or F unchanged. */
 int  modsgpu_empirical_checks(const modsgpu_region* kp1, const modsgpu_region* kp2, int n, const double* model, int use_F,
                               double err_threshold, double laf_coef, unsigned char* keep, double* model_out, int* n_out);
+
+/* verification against a KNOWN homography (replaces HMatrixFiltering matching.cpp:917-1013, ver_type GR_TRUTH of
+ * mods.cpp:292-303): error of every tentative under H (HDs / HDsSymMax / HDsSym by error_type) against err_threshold^2.
+ * The reference packs u = (image 2, image 1) here; H is read in the degensac layout for that order.  Host arithmetic only.
+ * xy1 / xy2: n x 2 doubles; keep: n bytes; H_out (may be NULL): H transposed, as true_corresp.H receives it. */
+int  modsgpu_hmatrix_filter(const double* xy1, const double* xy2, int n, const double* H, int error_type, double err_threshold,
+                            unsigned char* keep, double* H_out, int* n_out);
 
 /* replaces exp_ransacFcustom degensac/exp_ranF.h:71-73 as called from LORANSACFiltering matching.cpp:722
  * (7-point sample, oriented epipolar constraint, Sampson error, MSAC, symmetric check, LO).  F: 9 doubles with

@@ -301,6 +301,17 @@ class ModsGpu:
         m = out[:n.value].copy()
         return (m, ki, kd) if want_knn else m
 
+    def match_hamming(self, q, t, max_distance):
+        """modsgpu_match_hamming = MatchFLANNDistance (binary descriptors as floats holding bytes)"""
+        q = np.ascontiguousarray(q, np.float32)
+        t = np.ascontiguousarray(t, np.float32)
+        nq, nt = len(q), len(t)
+        dim = q.shape[1] if q.ndim == 2 and q.shape[1] else (t.shape[1] if t.ndim == 2 else 32)
+        out = np.zeros(max(nq, 1), MATCH_DTYPE)
+        n = C.c_int()
+        self._check(self.lib.modsgpu_match_hamming(self.ctx, _p(q), nq, _p(t), nt, int(dim), C.c_double(max_distance), _p(out), C.byref(n)))
+        return out[:n.value].copy()
+
     def duplicate_filter(self, xy1, xy2, ratio, r=2.0):
         xy1 = np.ascontiguousarray(xy1, np.float64)
         xy2 = np.ascontiguousarray(xy2, np.float64)

@@ -46,7 +46,7 @@ extern "C" void modsgpu_destroy(modsgpu_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->det_pyr, &ctx->det_cand, &ctx->det_map, &ctx->det_out, &ctx->det_misc, &ctx->det_aff, &ctx->io_a, &ctx->io_b,
                     &ctx->io_c, &ctx->smp_regs, &ctx->smp_meta, &ctx->smp_taps, &ctx->smp_scratch, &ctx->smp_out,
                     &ctx->cnn_act0, &ctx->cnn_act1, &ctx->cnn_out, &ctx->mt_q, &ctx->mt_t, &ctx->mt_d, &ctx->mt_aux,
-                    &ctx->mt_out, &ctx->rs_buf, &ctx->cnn_stats, &ctx->smp_prof, &ctx->smp_taptab, &ctx->chain_a, &ctx->chain_b, &ctx->chain_misc, &ctx->chain_tmp};
+                    &ctx->mt_out, &ctx->rs_buf, &ctx->cnn_stats, &ctx->smp_bins, &ctx->smp_prof, &ctx->smp_taptab, &ctx->chain_a, &ctx->chain_b, &ctx->chain_misc, &ctx->chain_tmp};
   for (DevBuf* b : bufs) b->release();
   ctx->h_stage.release();
   ctx->h_stage2.release();

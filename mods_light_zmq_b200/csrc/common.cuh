@@ -104,6 +104,7 @@ struct modsgpu_ctx {
   HostBuf h_stage, h_stage2;
   DevBuf io_a, io_b, io_c;            // generic staging for the test-only entry points
   DevBuf smp_regs, smp_meta, smp_taps, smp_scratch, smp_out;
+  DevBuf smp_bins;                    // histogram / bin-base scratch of the device-side sampler preparation
   DevBuf smp_prof;                    // 6 doubles: algorithmic bytes per sampler class of the device-prepared launches (profiler)
   DevBuf smp_taptab;                  // Gaussian taps of every even window size (patchSize 32), device-side sampler prep
   DevBuf chain_tmp;                   // uncompacted rows + verdict bytes between a net and the compaction

@@ -832,6 +832,88 @@ int EmpiricalChecks(TentativeCorrespListExt& ransac_corresp, const double* Hlora
   return (int)ransac_corresp.TCList.size();
 }
 
+// Htools.c:138-198 pinvJ + HDs for one correspondence (H in the degensac convention)
+static double HDs1(const double* H, const double* u) {
+  const double x1 = u[0], y1 = u[1], x2 = u[3], y2 = u[4], w2 = u[5];
+  double r1 = 0, r2 = 0;
+  r1 += H[0] * x2; r1 += H[2] * (-x1 * x2); r1 += H[3] * y2; r1 += H[5] * (-x1 * y2); r1 += H[6] * w2; r1 += H[8] * (-x1 * w2);
+  r2 += H[1] * x2; r2 += H[2] * (-y1 * x2); r2 += H[4] * y2; r2 += H[5] * (-y1 * y2); r2 += H[7] * w2; r2 += H[8] * (-y1 * w2);
+  const double a = H[0] - H[2] * x1, b = H[3] - H[5] * x1, c = -H[8] - H[2] * x2 - H[5] * y2;
+  const double d = H[1] - H[2] * y1, e = H[4] - H[5] * y1;
+  const double a2 = a * a, b2 = b * b, c2 = c * c, d2 = d * d, e2 = e * e;
+  const double c2pd2 = c2 + d2, ab = a * b, de = d * e;
+  double pJ[8];
+  pJ[0] = -b * de + a * (c2 + e2); pJ[1] = b * c2pd2 - a * de; pJ[2] = c * (c2pd2 + e2); pJ[3] = -c * (a * d + b * e);
+  pJ[4] = d * (b2 + c2) - ab * e; pJ[5] = -ab * d + e * (a2 + c2); pJ[6] = pJ[3]; pJ[7] = c * (a2 + b2 + c2);
+  const double N = a * pJ[0] + b * pJ[1] + c * pJ[2];
+  double s = 0;
+  for (int j = 0; j < 4; j++) { const double t = (pJ[j] / N) * r1 + (pJ[j + 4] / N) * r2; s += t * t; }
+  return s;
+}
+
+// matching.cpp:917-1013: verification against a KNOWN homography (ver_type GR_TRUTH, mods.cpp:292-303).  NB the
+// reference packs u as (second, first) here -- H is expected in the degensac convention of THAT order -- and hands back
+// the transposed H.  isExtended keeps every tentative and only sets isTrue.
+int HMatrixFiltering(TentativeCorrespListExt& in_corresp, TentativeCorrespListExt& true_corresp, const double* H, int isExtended,
+                     const RANSACPars& pars) {
+  const size_t T = in_corresp.TCList.size();
+  true_corresp.TCList.clear();
+  const float th = (float)(pars.err_threshold * pars.err_threshold);       // float in the reference (:968)
+  double Hm[9] = {H[0], H[3], H[6], H[1], H[4], H[7], H[2], H[5], H[8]}, H1[9];
+  if (pars.errorType != 0) invert3(Hm, H1);
+  int true_size = 0;
+  if (isExtended) true_corresp.TCList = in_corresp.TCList;
+  for (size_t i = 0; i < T; i++) {
+    const TentativeCorrespExt& c = in_corresp.TCList[i];
+    const double u[6] = {c.second.reproj_kp.x, c.second.reproj_kp.y, 1., c.first.reproj_kp.x, c.first.reproj_kp.y, 1.};
+    double d;
+    if (pars.errorType == 0) d = HDs1(H, u);
+    else {
+      // HDsSymMax / HDsSym (Htools.c:201-284): max / sum of the two transfer errors
+      const double a = H1[6] * u[0] + H1[7] * u[1] + H1[8], b = Hm[6] * u[3] + Hm[7] * u[4] + Hm[8];
+      double xa = (H1[0] * u[0] + H1[1] * u[1] + H1[2]) / a, ya = (H1[3] * u[0] + H1[4] * u[1] + H1[5]) / a;
+      double xd = u[3] - xa, yd = u[4] - ya;
+      const double d1 = xd * xd + yd * yd;
+      xa = (Hm[0] * u[3] + Hm[1] * u[4] + Hm[2]) / b; ya = (Hm[3] * u[3] + Hm[4] * u[4] + Hm[5]) / b;
+      xd = u[0] - xa; yd = u[1] - ya;
+      const double d2 = xd * xd + yd * yd;
+      d = pars.errorType == 1 ? (d1 > d2 ? d1 : d2) : d1 + d2;
+    }
+    const int inl = d <= th ? 1 : 0;
+    true_size += inl;
+    if (isExtended) true_corresp.TCList[i].isTrue = inl;
+    else if (inl) true_corresp.TCList.push_back(c);
+  }
+  const double Ht[9] = {H[0], H[3], H[6], H[1], H[4], H[7], H[2], H[5], H[8]};
+  for (int i = 0; i < 9; i++) true_corresp.H[i] = Ht[i];
+  return true_size;
+}
+
+// matching.cpp:574-633 on the device (modsgpu_match_hamming): binary descriptors, 2-NN by Hamming distance
+int MatchFLANNDistance(modsgpu_ctx* ctx, const AffineRegionVector& list1, const AffineRegionVector& list2,
+                       TentativeCorrespListExt& corresp, double matchDistanceThreshold) {
+  corresp.TCList.clear();
+  const int n1 = (int)list1.size(), n2 = (int)list2.size();
+  if (n1 == 0 || n2 == 0) return 0;
+  const int dim = (int)list1[0].desc.size();
+  std::vector<float> q((size_t)n1 * dim), t((size_t)n2 * dim);
+  for (int i = 0; i < n1; i++) memcpy(&q[(size_t)i * dim], list1[i].desc.data(), dim * sizeof(float));
+  for (int i = 0; i < n2; i++) memcpy(&t[(size_t)i * dim], list2[i].desc.data(), dim * sizeof(float));
+  std::vector<modsgpu_match> m(n1);
+  int nm = 0;
+  int rc = modsgpu_match_hamming(ctx, q.data(), n1, t.data(), n2, dim, matchDistanceThreshold, m.data(), &nm);
+  if (rc) return rc;
+  corresp.TCList.reserve(nm);
+  for (int k = 0; k < nm; k++) {
+    TentativeCorrespExt tc;
+    tc.first = list1[m[k].qi];
+    tc.second = list2[m[k].ti];
+    tc.d1 = m[k].d1; tc.d2 = m[k].d2; tc.ratio = m[k].ratio;
+    corresp.TCList.push_back(tc);
+  }
+  return nm;
+}
+
 // mods.cpp:202-356, HessianAffine steps only (MSER and the other detectors stay on the reference's CPU path)
 int MODSPair(modsgpu_ctx* ctx, modsgpu_image* img1, modsgpu_image* img2, const std::vector<IterationStep>& steps,
              int minMatches, const RANSACPars& rp, MODSResult& res, TentativeCorrespListExt& verified) {
@@ -874,6 +956,28 @@ int MODSPair(modsgpu_ctx* ctx, modsgpu_image* img1, modsgpu_image* img2, const s
 }
 
 }  // namespace modsb200
+
+// HMatrixFiltering (matching.cpp:917-1013) on caller-supplied centres: xy1 / xy2 = reproj_kp centres of the n tentatives in
+// image 1 / image 2, H in the convention the reference's caller passes (ground-truth file, degensac layout for u = (image 2,
+// image 1)).  keep[i] = within err_threshold under the selected error; H_out = H transposed (what true_corresp.H receives).
+extern "C" int modsgpu_hmatrix_filter(const double* xy1, const double* xy2, int n, const double* H, int error_type, double err_threshold,
+                                      unsigned char* keep, double* H_out, int* n_out) {
+  using namespace modsb200;
+  if (n < 0 || (n > 0 && (!xy1 || !xy2 || !keep)) || !H || !n_out || error_type < 0 || error_type > 2) return MODSGPU_EINVAL;
+  TentativeCorrespListExt in, out;
+  in.TCList.resize(n);
+  for (int i = 0; i < n; i++) {
+    in.TCList[i].first.reproj_kp.x = xy1[2 * i]; in.TCList[i].first.reproj_kp.y = xy1[2 * i + 1];
+    in.TCList[i].second.reproj_kp.x = xy2[2 * i]; in.TCList[i].second.reproj_kp.y = xy2[2 * i + 1];
+  }
+  RANSACPars pars;
+  pars.errorType = error_type;
+  pars.err_threshold = err_threshold;
+  *n_out = HMatrixFiltering(in, out, H, 1, pars);
+  for (int i = 0; i < n; i++) keep[i] = (unsigned char)out.TCList[i].isTrue;
+  if (H_out) for (int i = 0; i < 9; i++) H_out[i] = out.H[i];
+  return 0;
+}
 
 // host-only seam of the checks above (no device work, callable without a GPU): kp1 / kp2 = reproj_kp of the n
 // correspondences RANSAC kept; model = the degensac-convention H (column-major, image 2 -> 1) or F; keep[i] = survives.

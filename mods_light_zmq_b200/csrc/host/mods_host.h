@@ -189,6 +189,11 @@ int MODSPair(modsgpu_ctx* ctx, modsgpu_image* img1, modsgpu_image* img2, const s
 
 int LORANSACFiltering(modsgpu_ctx* ctx, TentativeCorrespListExt& in_corresp, TentativeCorrespListExt& ransac_corresp,
                       double* H, const RANSACPars& pars);
+// matching.cpp:917-1013 (verification against a known homography) and :574-633 (binary descriptors, Hamming 2-NN)
+int HMatrixFiltering(TentativeCorrespListExt& in_corresp, TentativeCorrespListExt& true_corresp, const double* H, int isExtended,
+                     const RANSACPars& pars);
+int MatchFLANNDistance(modsgpu_ctx* ctx, const AffineRegionVector& list1, const AffineRegionVector& list2,
+                       TentativeCorrespListExt& corresp, double matchDistanceThreshold);
 // the empirical checks at the end of LORANSACFiltering (matching.cpp:764-820); Hloran = the degensac-convention model
 int EmpiricalChecks(TentativeCorrespListExt& ransac_corresp, const double* Hloran, const RANSACPars& pars, double* H);
 

@@ -410,6 +410,87 @@ extern "C" int modsgpu_match_fginn(modsgpu_ctx* ctx, const float* q, int nq, con
   return 0;
 }
 
+// =====================================================================================================================
+// MatchFLANNDistance (matching.cpp:574-633): binary descriptors (bytes = floor of the float entries, :596-608), the 2
+// nearest train descriptors by Hamming distance, a match whenever the nearest is within matchDistanceThreshold; ratio =
+// d1 / d2.  Exact linear search (binary_matcher = linear): ties keep the lower train index first, as cvflann's LinearIndex +
+// KNNSimpleResultSet do for every distance type (the reference's default hierarchical-clustering index is approximate and
+// randomised -- not a parity target, like the kd-tree of the vector matcher).
+// One CTA per query: a thread walks train rows j = tid, tid + 128, ..., keeps its two smallest (distance, index) keys,
+// thread 0 merges the 256 keys.
+// =====================================================================================================================
+namespace {
+__global__ void __launch_bounds__(128)
+k_hamming_2nn(const uint32_t* __restrict__ q, const uint32_t* __restrict__ t, int nt, int words, int max_distance,
+              modsgpu_match* __restrict__ matches) {
+  __shared__ uint32_t qs[32];
+  __shared__ unsigned long long best[256];
+  const int qi = blockIdx.x, tid = threadIdx.x;
+  if (tid < words) qs[tid] = q[(size_t)qi * words + tid];
+  __syncthreads();
+  unsigned long long k1 = ~0ull, k2 = ~0ull;
+  for (int j = tid; j < nt; j += 128) {
+    const uint32_t* row = t + (size_t)j * words;
+    unsigned d = 0;
+    for (int w = 0; w < words; w++) d += __popc(qs[w] ^ row[w]);
+    const unsigned long long key = ((unsigned long long)d << 32) | (unsigned)j;
+    if (key < k1) { k2 = k1; k1 = key; }
+    else if (key < k2) k2 = key;
+  }
+  best[2 * tid] = k1; best[2 * tid + 1] = k2;
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long a = ~0ull, b = ~0ull;
+    for (int i = 0; i < 256; i++) {
+      const unsigned long long key = best[i];
+      if (key < a) { b = a; a = key; }
+      else if (key < b) b = key;
+    }
+    modsgpu_match mt;
+    mt.qi = -1; mt.ti = -1; mt.tj_bad = -1; mt.d1 = 0.f; mt.d2 = 0.f; mt._pad = 0; mt.ratio = 0.0;
+    if (a != ~0ull && (int)(a >> 32) <= max_distance) {
+      mt.qi = qi; mt.ti = (int)(a & 0xffffffffu); mt.d1 = (float)(unsigned)(a >> 32);
+      // with a single train descriptor the reference reads an unset second distance; here d2 = 0 and ratio = inf
+      if (b != ~0ull) { mt.tj_bad = (int)(b & 0xffffffffu); mt.d2 = (float)(unsigned)(b >> 32); }
+      mt.ratio = (double)mt.d1 / (double)mt.d2;
+    }
+    matches[qi] = mt;
+  }
+}
+}  // namespace
+
+extern "C" int modsgpu_match_hamming(modsgpu_ctx* ctx, const float* q, int nq, const float* t, int nt, int dim,
+                                     double max_distance, modsgpu_match* out, int* nout) {
+  if (!ctx || !nout || nq < 0 || nt < 0 || (nq > 0 && (!q || !out)) || (nt > 0 && !t)) return MODSGPU_EINVAL;
+  *nout = 0;
+  if (dim < 4 || dim > 128 || dim % 4) MG_FAIL(ctx, MODSGPU_EINVAL, "binary descriptor length must be a multiple of 4 bytes, <= 128");
+  if (mg_begin(ctx)) return MODSGPU_ECUDA;
+  if (nq == 0 || nt == 0) return mg_end(ctx) ? MODSGPU_ECUDA : 0;
+  // Row[j] = floor(desc.vec[j]) into unsigned char (matching.cpp:596-608)
+  const size_t qb = (size_t)nq * dim, tb = (size_t)nt * dim;
+  MG_CUDA(ctx, ctx->h_stage.ensure(qb + tb + (size_t)nq * sizeof(modsgpu_match) + 64));
+  unsigned char* hq = ctx->h_stage.as<unsigned char>();
+  unsigned char* ht = hq + ((qb + 15) & ~(size_t)15);
+  for (size_t i = 0; i < qb; i++) hq[i] = (unsigned char)floorf(q[i]);
+  for (size_t i = 0; i < tb; i++) ht[i] = (unsigned char)floorf(t[i]);
+  MG_CUDA(ctx, ctx->io_a.ensure(qb + 16));
+  MG_CUDA(ctx, ctx->io_b.ensure(tb + 16));
+  MG_CUDA(ctx, ctx->mt_out.ensure((size_t)nq * sizeof(modsgpu_match)));
+  MG_CUDA(ctx, cudaMemcpyAsync(ctx->io_a.p, hq, qb, cudaMemcpyHostToDevice, ctx->stream));
+  MG_CUDA(ctx, cudaMemcpyAsync(ctx->io_b.p, ht, tb, cudaMemcpyHostToDevice, ctx->stream));
+  MG_PROF(ctx, "k_hamming_2nn", 2, (double)nq * nt);
+  k_hamming_2nn<<<nq, 128, 0, ctx->stream>>>(ctx->io_a.as<uint32_t>(), ctx->io_b.as<uint32_t>(), nt, dim / 4, (int)(float)max_distance,
+                                             ctx->mt_out.as<modsgpu_match>());
+  MG_LAUNCHED(ctx);
+  modsgpu_match* hm = reinterpret_cast<modsgpu_match*>(ht + ((tb + 15) & ~(size_t)15));
+  MG_CUDA(ctx, cudaMemcpyAsync(hm, ctx->mt_out.p, (size_t)nq * sizeof(modsgpu_match), cudaMemcpyDeviceToHost, ctx->stream));
+  if (mg_end(ctx)) return MODSGPU_ECUDA;
+  int m = 0;
+  for (int i = 0; i < nq; i++) if (hm[i].qi >= 0) out[m++] = hm[i];
+  *nout = m;
+  return 0;
+}
+
 extern "C" int modsgpu_duplicate_filter(modsgpu_ctx* ctx, const double* xy1, const double* xy2, const double* ratio,
                                         int T, double r, int* order_out, int* nout) {
   if (!ctx || !nout || T < 0 || (T > 0 && (!xy1 || !xy2 || !ratio || !order_out))) return MODSGPU_EINVAL;

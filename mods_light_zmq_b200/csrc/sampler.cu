@@ -924,7 +924,7 @@ int mg_sample_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
 // =====================================================================================================================
 // Device-side preparation (the per-view chain, chain.cu): the region list lives on the device and its length is only
 // known there, so classification, the decreasing-R placement inside a class and the work lists of the large-window
-// path are built by one CTA (k_smp_prepare) instead of the host loop of mg_sample_enqueue.  Launch grids are sized by
+// path are built on the device (k_smp_classify / k_smp_scan / k_smp_scatter) instead of the host loop of mg_sample_enqueue.  Launch grids are sized by
 // the upper bounds of SmpStats (k_smp_stats over ALL keypoints of the view; later passes see subsets with the same
 // scales); surplus CTAs leave at once.  patchSize 32, u8 output only.  The arithmetic that decides R, the class and
 // the taps is the host path's, term by term.
@@ -1006,117 +1006,134 @@ k_smp_stats(const DevRegion* __restrict__ regs, const int* __restrict__ cnt, dou
   }
 }
 
-struct PrepLayout { int cls_off[SC_N]; int nl_cap; };   // class c's PatchMeta live at metas + cls_off[c] (upper-bound layout)
+struct PrepLayout { int cls_off[SC_N]; int rtop[SC_N]; int nl_cap; };   // class c's PatchMeta live at metas + cls_off[c] (upper-bound layout); rtop: its largest window
 
-// One CTA builds the sampler's work lists for the regions [0, *cnt): PatchMeta per region, dealt into the classes'
-// slabs in order of decreasing R (the order inside a class only decides which CTAs start first; equal-R regions may
-// land in any order), the live count of every class, and for the large-window class the scratch offsets and the
-// three block-count prefix arrays.
-__global__ void __launch_bounds__(1024)
-k_smp_prepare(const DevRegion* __restrict__ regs, const int* __restrict__ cnt, double mrSize, TapTab tt, PrepLayout lay,
-              PatchMeta* __restrict__ metas, PatchMeta* __restrict__ mtmp, int* __restrict__ pre1, int* __restrict__ pre2,
-              int* __restrict__ pre0, int* __restrict__ cls_cnt_out, double* __restrict__ prof_bytes) {
-  __shared__ int hist[HB_TOTAL];
-  __shared__ int s_cls[SC_N];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < HB_TOTAL; i += blockDim.x) hist[i] = 0;
-  __syncthreads();
-  const int n = *cnt;
-  // four regions per thread and step: the row loads, then the tap-table look-ups, of the four are in flight together
-  // (one CTA walks the whole list, so the dependent-load latency, not the arithmetic, sets this kernel's time)
-  for (int i0 = tid; i0 < n; i0 += 4 * blockDim.x) {
-    modsgpu_region rg[4];
+// The sampler's work lists for the regions [0, *cnt) in three small launches (a first version did everything in ONE
+// 1024-thread CTA: 73 us, all of it the 128-byte-stride row reads and scattered 48-byte stores of 4.4k regions through a
+// single SM's load/store path -- 27k warp instructions in 140k cycles):
+//   k_smp_classify  grid-wide, one thread per region: PatchMeta + (class, R) bin, rank inside the bin by a global atomic
+//   k_smp_scan      one CTA: bin counts -> start positions (class slabs in order of decreasing R), live class counts, and
+//                   for the large-window class the per-bin bases of the scratch offsets / block-count prefixes (equal-R
+//                   regions have equal sizes, so a region's values follow from its bin base and its rank)
+//   k_smp_scatter   grid-wide: PatchMeta to its slot; large-window regions also get scratch_off and their pre0/1/2 entries
+// The order inside a class only decides which CTAs start first; equal-R regions may land in any order.
+struct PrepBins {                 // device scratch of the three kernels (ints unless noted)
+  int hist[HB_TOTAL];             // counts (k_smp_classify), zero again after k_smp_scan
+  int start[HB_TOTAL];            // slot of the first region of every bin
+  int lb0[MAX_R + 1], lb1[MAX_R + 1], lb2[MAX_R + 1];   // large class: block-count prefixes at the first region of bin R
+  long long lscr[MAX_R + 1];      //              scratch offset (floats) of the first region of bin R
+  int lpos[MAX_R + 1];            //              index inside the large slab of the first region of bin R
+};
+
+__global__ void __launch_bounds__(256)
+k_smp_classify(const DevRegion* __restrict__ regs, const int* __restrict__ cnt, double mrSize, TapTab tt, PrepBins* __restrict__ B,
+               PatchMeta* __restrict__ mtmp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= *cnt) return;
+  PatchMeta m; int c;
+  classify_region(regs[i].det, mrSize, tt, m, c);
+  const int bin = hist_bin(c, m.R);
+  m.out_index = i;
+  m.scratch_off = (long long)bin << 32 | (unsigned)atomicAdd(&B->hist[bin], 1);     // (bin, rank) ride in the unused field
+  mtmp[i] = m;
+}
+
+__global__ void __launch_bounds__(256)
+k_smp_scan(PrepBins* __restrict__ B, PrepLayout lay, int* __restrict__ pre1, int* __restrict__ pre2, int* __restrict__ pre0,
+           int* __restrict__ cls_cnt_out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp >= SC_N) return;
+  // Warp c turns class c's bin counts into start positions, walking R downwards from the largest window the view can hold
+  // (lay.rtop[c], from the statistics pass).  Lane l owns a STRIP of consecutive bins: it adds its strip up serially, one
+  // warp scan combines the 32 strip totals, then it walks its strip again writing the bases.  (A version that scanned 32
+  // bins per step with shuffles took 63 us: 65 steps x ~150 dependent instructions on one warp.)
+  const int c = warp, rtop = lay.rtop[c];
+  const int L = (rtop + 32) / 32;                       // bins per lane; lane l owns R = rtop - l*L ... rtop - l*L - (L-1)
+  const int rhi = rtop - lane * L;
+  int n = 0, t0 = 0, t1 = 0, t2 = 0;
+  long long ts = 0;
+  for (int k = 0; k < L; k++) {
+    const int R = rhi - k;
+    if (R < 0) break;
+    const int v = B->hist[hist_bin(c, R)];
+    n += v;
+    if (c == SC_LARGE && v) {
+      t0 += v * ((R + L0_ROWS - 1) / L0_ROWS); t1 += v * ((R + L1_ROWS - 1) / L1_ROWS); t2 += v * ((R + L2_ROWS - 1) / L2_ROWS);
+      ts += (long long)v * large_region_floats(R, DEV_PS);
+    }
+  }
+  int ni = n, i0 = t0, i1 = t1, i2 = t2;
+  long long si = ts;
 #pragma unroll
-    for (int u = 0; u < 4; u++) { const int i = i0 + u * blockDim.x; rg[u] = regs[i < n ? i : n - 1].det; }
-    PatchMeta m[4]; int c[4];
-#pragma unroll
-    for (int u = 0; u < 4; u++) classify_region(rg[u], mrSize, tt, m[u], c[u]);
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const int i = i0 + u * blockDim.x;
-      if (i < n) {
-        const int bin = hist_bin(c[u], m[u].R);
-        m[u].out_index = i;
-        m[u].scratch_off = (long long)bin << 32 | (unsigned)atomicAdd(&hist[bin], 1);     // (bin, rank) ride in the unused field
-        mtmp[i] = m[u];
+  for (int o = 1; o < 32; o <<= 1) {
+    const int un = __shfl_up_sync(0xffffffffu, ni, o), u0 = __shfl_up_sync(0xffffffffu, i0, o), u1 = __shfl_up_sync(0xffffffffu, i1, o),
+              u2 = __shfl_up_sync(0xffffffffu, i2, o);
+    const long long us = __shfl_up_sync(0xffffffffu, si, o);
+    if (lane >= o) { ni += un; i0 += u0; i1 += u1; i2 += u2; si += us; }
+  }
+  const int total = __shfl_sync(0xffffffffu, ni, 31), tot0 = __shfl_sync(0xffffffffu, i0, 31), tot1 = __shfl_sync(0xffffffffu, i1, 31),
+            tot2 = __shfl_sync(0xffffffffu, i2, 31);
+  int pos = ni - n, p0 = i0 - t0, p1 = i1 - t1, p2 = i2 - t2;      // exclusive prefixes at the head of this lane's strip
+  long long ps = si - ts;
+  for (int k = 0; k < L; k++) {
+    const int R = rhi - k;
+    if (R < 0) break;
+    const int bin = hist_bin(c, R);
+    const int v = B->hist[bin];
+    B->start[bin] = lay.cls_off[c] + pos;
+    B->hist[bin] = 0;
+    if (c == SC_LARGE) {
+      B->lb0[R] = p0; B->lb1[R] = p1; B->lb2[R] = p2; B->lscr[R] = ps; B->lpos[R] = pos;
+      if (v) {
+        p0 += v * ((R + L0_ROWS - 1) / L0_ROWS); p1 += v * ((R + L1_ROWS - 1) / L1_ROWS); p2 += v * ((R + L2_ROWS - 1) / L2_ROWS);
+        ps += (long long)v * large_region_floats(R, DEV_PS);
       }
     }
+    pos += v;
   }
-  __syncthreads();
-  // warp c turns class c's counts into start positions, walking R downwards (exclusive scan, 32 bins per step)
-  if (warp < SC_N) {
-    const int c = warp, rtop = c < SC_LARGE ? HB_SMALL - 1 : MAX_R;
-    int carry = 0;
-    for (int r0 = rtop; r0 >= 0; r0 -= 32) {
-      const int R = r0 - lane;
-      const int v = R >= 0 ? hist[hist_bin(c, R)] : 0;
-      int incl = v;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-      if (R >= 0) hist[hist_bin(c, R)] = lay.cls_off[c] + carry + incl - v;
-      carry += __shfl_sync(0xffffffffu, incl, 31);
+  if (lane == 0) {
+    cls_cnt_out[c] = total;
+    if (c == SC_LARGE) {
+      const int nl = min(total, lay.nl_cap);
+      pre0[nl] = tot0; pre1[nl] = tot1; pre2[nl] = tot2;
     }
-    if (lane == 0) { s_cls[c] = carry; cls_cnt_out[c] = carry; }
   }
-  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+k_smp_scatter(const PatchMeta* __restrict__ mtmp, const int* __restrict__ cnt, const PrepBins* __restrict__ B, PrepLayout lay,
+              PatchMeta* __restrict__ metas, int* __restrict__ pre1, int* __restrict__ pre2, int* __restrict__ pre0,
+              double* __restrict__ prof_bytes) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool live = i < *cnt;
   double pb[SC_N] = {0, 0, 0, 0, 0, 0};
-  for (int i0 = tid; i0 < n; i0 += 4 * blockDim.x) {
-    PatchMeta m[4];
-#pragma unroll
-    for (int u = 0; u < 4; u++) { const int i = i0 + u * blockDim.x; m[u] = mtmp[i < n ? i : n - 1]; }
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const int i = i0 + u * blockDim.x;
-      if (i < n) {
-        const int bin = (int)(m[u].scratch_off >> 32), rank = (int)(m[u].scratch_off & 0xffffffffll);
-        m[u].scratch_off = 0;
-        metas[hist[bin] + rank] = m[u];
-        // profiler only: the algorithmic bytes of this region (R*R*4 read + 32*32 written), per class
-        if (prof_bytes != nullptr) {
-          const int c = bin < 5 * HB_SMALL ? bin / HB_SMALL : SC_LARGE;
-          const double b = (double)m[u].R * m[u].R * 4.0 + (double)(DEV_PS * DEV_PS);
-#pragma unroll
-          for (int k = 0; k < SC_N; k++) pb[k] += c == k ? b : 0.0;
-        }
+  if (live) {
+    PatchMeta m = mtmp[i];
+    const int bin = (int)(m.scratch_off >> 32), rank = (int)(m.scratch_off & 0xffffffffll);
+    m.scratch_off = 0;
+    const int c = bin < 5 * HB_SMALL ? bin / HB_SMALL : SC_LARGE;
+    if (c == SC_LARGE) {
+      const int R = m.R;
+      const int li = B->lpos[R] + rank;                      // index inside the large slab
+      m.scratch_off = B->lscr[R] + (long long)rank * large_region_floats(R, DEV_PS);
+      if (li < lay.nl_cap) {
+        pre0[li] = B->lb0[R] + rank * ((R + L0_ROWS - 1) / L0_ROWS);
+        pre1[li] = B->lb1[R] + rank * ((R + L1_ROWS - 1) / L1_ROWS);
+        pre2[li] = B->lb2[R] + rank * ((R + L2_ROWS - 1) / L2_ROWS);
       }
     }
+    metas[B->start[bin] + rank] = m;
+    // profiler only: the algorithmic bytes of this region (R*R*4 read + 32*32 written), per class
+    if (prof_bytes != nullptr) pb[c] = (double)m.R * m.R * 4.0 + (double)(DEV_PS * DEV_PS);
   }
-  if (prof_bytes != nullptr) {       // one atomic per warp and class (thousands on one address would dominate the kernel)
+  if (prof_bytes != nullptr) {       // one atomic per warp and class
 #pragma unroll
     for (int k = 0; k < SC_N; k++) {
       double v = pb[k];
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       if (lane == 0 && v > 0) atomicAdd(prof_bytes + k, v);
     }
-  }
-  __syncthreads();
-  // large-window class: scratch offsets and the prefix arrays of the three row-blocked phases (warp 0, 32 regions per step)
-  if (warp == 0) {
-    const int nl = min(s_cls[SC_LARGE], lay.nl_cap);
-    PatchMeta* large = metas + lay.cls_off[SC_LARGE];
-    int c0 = 0, c1 = 0, c2 = 0;
-    long long cs = 0;
-    for (int i0 = 0; i0 < nl; i0 += 32) {
-      const int i = i0 + lane;
-      const int R = i < nl ? large[i].R : 0;
-      int b0 = i < nl ? (R + L0_ROWS - 1) / L0_ROWS : 0, b1 = i < nl ? (R + L1_ROWS - 1) / L1_ROWS : 0, b2 = i < nl ? (R + L2_ROWS - 1) / L2_ROWS : 0;
-      long long sz = i < nl ? large_region_floats(R, DEV_PS) : 0;
-      int i0s = b0, i1s = b1, i2s = b2;
-      long long ss = sz;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t0 = __shfl_up_sync(0xffffffffu, i0s, o), t1 = __shfl_up_sync(0xffffffffu, i1s, o), t2 = __shfl_up_sync(0xffffffffu, i2s, o);
-        const long long ts = __shfl_up_sync(0xffffffffu, ss, o);
-        if (lane >= o) { i0s += t0; i1s += t1; i2s += t2; ss += ts; }
-      }
-      if (i < nl) {
-        pre0[i] = c0 + i0s - b0; pre1[i] = c1 + i1s - b1; pre2[i] = c2 + i2s - b2;
-        large[i].scratch_off = cs + ss - sz;
-      }
-      c0 += __shfl_sync(0xffffffffu, i0s, 31); c1 += __shfl_sync(0xffffffffu, i1s, 31); c2 += __shfl_sync(0xffffffffu, i2s, 31);
-      cs += __shfl_sync(0xffffffffu, ss, 31);
-    }
-    if (lane == 0) { pre0[nl] = c0; pre1[nl] = c1; pre2[nl] = c2; }
   }
 }
 
@@ -1172,7 +1189,10 @@ int mg_sample_enqueue_dev(modsgpu_ctx* ctx, const modsgpu_image* img, const DevR
   const int ps = DEV_PS;
   PrepLayout lay;
   size_t nm = 0;
-  for (int c = 0; c < SC_N; c++) { lay.cls_off[c] = (int)nm; nm += (size_t)st.cls_cnt[c]; }
+  for (int c = 0; c < SC_N; c++) {
+    lay.cls_off[c] = (int)nm; nm += (size_t)st.cls_cnt[c];
+    lay.rtop[c] = std::min(c < SC_LARGE ? HB_SMALL - 1 : MAX_R, std::max(st.cls_rmax[c], 0));     // no region of a subset has a larger window
+  }
   lay.nl_cap = st.nl;
   const int nl = st.nl;
   const size_t meta_bytes = (nm + 1) * sizeof(PatchMeta), pre_bytes = (size_t)(nl + 1) * 4;
@@ -1189,9 +1209,21 @@ int mg_sample_enqueue_dev(modsgpu_ctx* ctx, const modsgpu_image* img, const DevR
     if (!ctx->smp_prof.p) { MG_CUDA(ctx, ctx->smp_prof.ensure(64)); MG_CUDA(ctx, cudaMemsetAsync(ctx->smp_prof.p, 0, 64, ctx->stream)); }
     prof_bytes = ctx->smp_prof.as<double>();
   }
-  MG_PROF(ctx, "k_smp_prepare", 2, (double)n_ub);
-  k_smp_prepare<<<1, 1024, 0, ctx->stream>>>(regs, cnt_dev, mrSize, tt, lay, dm, ctx->smp_regs.as<PatchMeta>(), dpre1, dpre2, dpre0, dcnt,
-                                             prof_bytes);
+  if (!ctx->smp_bins.p) {            // histogram scratch: zero once, k_smp_scan leaves it zero
+    MG_CUDA(ctx, ctx->smp_bins.ensure(sizeof(PrepBins)));
+    MG_CUDA(ctx, cudaMemsetAsync(ctx->smp_bins.p, 0, sizeof(PrepBins), ctx->stream));
+  }
+  PrepBins* bins = ctx->smp_bins.as<PrepBins>();
+  PatchMeta* mtmp = ctx->smp_regs.as<PatchMeta>();
+  const int nblk = ceil_div(n_ub, 256);
+  MG_PROF(ctx, "k_smp_classify", 2, (double)n_ub);
+  k_smp_classify<<<nblk, 256, 0, ctx->stream>>>(regs, cnt_dev, mrSize, tt, bins, mtmp);
+  MG_LAUNCHED(ctx);
+  MG_PROF(ctx, "k_smp_scan", 2, (double)HB_TOTAL);
+  k_smp_scan<<<1, 256, 0, ctx->stream>>>(bins, lay, dpre1, dpre2, dpre0, dcnt);
+  MG_LAUNCHED(ctx);
+  MG_PROF(ctx, "k_smp_scatter", 2, (double)n_ub);
+  k_smp_scatter<<<nblk, 256, 0, ctx->stream>>>(mtmp, cnt_dev, bins, lay, dm, dpre1, dpre2, dpre0, prof_bytes);
   MG_LAUNCHED(ctx);
   static OnceFlags attr_set;
   if (attr_set.need(ctx->device)) {
@@ -1202,7 +1234,7 @@ int mg_sample_enqueue_dev(modsgpu_ctx* ctx, const modsgpu_image* img, const DevR
     MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_b, cudaFuncAttributeMaxDynamicSharedMemorySize, b_smem_floats(B2_R, 30) * 4));
     attr_set.set(ctx->device);
   }
-  // the algorithmic bytes of these launches are only known on the device: k_smp_prepare accumulates them per class and
+  // the algorithmic bytes of these launches are only known on the device: k_smp_scatter accumulates them per class and
   // modsgpu_profile_report adds them to the kernels' records
   auto alg_bytes = [&](int) { return 0.0; };
   const float* dtaps = tt.taps;

@@ -636,3 +636,44 @@ def empirical_checks(kp1, kp2, model, use_F, err_threshold=4.0, laf_coef=None):
     if keep.sum() < 8:
         keep[:] = False
     return keep, Hout.ravel()
+
+
+# --------------------------------------------------------------------------- f4 rows: Hamming matcher, ground-truth H filter
+def match_hamming(q, t, max_distance):
+    """MatchFLANNDistance (matching.cpp:574-633) with an exact linear index: bytes = floor(entry), the two nearest train rows
+    by Hamming distance (ties: lower index first, the LinearIndex / KNNSimpleResultSet order), a match when d1 <= (int)
+    max_distance, ratio = d1 / d2.  Returns MATCH_DTYPE rows in query order."""
+    qb = np.floor(np.asarray(q, np.float32)).astype(np.uint8)
+    tb = np.floor(np.asarray(t, np.float32)).astype(np.uint8)
+    out = []
+    md = int(np.float32(max_distance))
+    for i in range(len(qb)):
+        d = np.unpackbits(qb[i][None, :] ^ tb, axis=1).sum(1).astype(np.int64)
+        order = np.argsort(d, kind="stable")
+        if len(order) and d[order[0]] <= md:
+            d1 = float(d[order[0]])
+            d2 = float(d[order[1]]) if len(order) > 1 else 0.0
+            with np.errstate(divide="ignore", invalid="ignore"):
+                ratio = float(np.float64(d1) / np.float64(d2))
+            out.append((i, int(order[0]), int(order[1]) if len(order) > 1 else -1, d1, d2, 0, ratio))
+    return np.array(out, MATCH_DTYPE) if out else np.zeros(0, MATCH_DTYPE)
+
+
+def ref_hmatrix_filter(xy1, xy2, H, error="sampson", err_threshold=4.0):
+    """HMatrixFiltering (matching.cpp:917-1013) with the REFERENCE's own HDs / HDsSym / HDsSymMax (oracle/_ref): u is packed
+    (image 2, image 1) as the reference does; returns (keep mask, errors)."""
+    L = ref()
+    xy1 = np.asarray(xy1, np.float64)
+    xy2 = np.asarray(xy2, np.float64)
+    T = len(xy1)
+    u = np.ascontiguousarray(np.c_[xy2, np.ones(T), xy1, np.ones(T)])
+    Hm = np.ascontiguousarray(H, np.float64)
+    d = np.zeros(max(T, 1), np.float64)
+    Z = np.zeros(max(T, 1) * 18, np.float64)
+    pidx = np.arange(max(T, 1), dtype=np.int32)
+    fn = {"sampson": L.HDs, "symm_max": L.HDsSymMax, "symm_sum": L.HDsSym}[error]
+    if T:
+        L.lin_hg(_p(u), _p(Z), _p(pidx), T)                   # matching.cpp:969: the linearised rows HDs reads
+        fn(_p(Z), _p(u), _p(Hm), _p(d), T)
+    th = np.float32(err_threshold * err_threshold)           # float th in the reference (:968)
+    return d[:T] <= np.float64(th), d[:T]

@@ -298,6 +298,192 @@ int blur2_smem_bytes(int ks) {
   return (AH * blur2_pitch_a(r) + (AH + 3) * BLUR2_PB + (BT_X + 2) * (BT_Y + 2)) * (int)sizeof(float);
 }
 
+// ---- ksize-specialised version (7 <= ks <= 23: every blur of a pyramid with 2..6 scales per octave) ---------------------
+// Same tile, same arithmetic order, a third of the instructions and a shorter critical path per CTA (the detector is a
+// chain of 19 dependent launches per image, so a CTA's latency IS the detector's latency):
+//   load   every thread issues all of its (AH x AW) / 512 clamped global loads before the first shared-memory store
+//          (the old loop exposed one L2 round trip per iteration)
+//   row    a thread owns CB adjacent outputs of one row and streams the CB + ks - 1 samples once; the loops are fully
+//          unrolled, so the taps are constant-bank operands of the FMAs (no tap loads, no register rotation) and each
+//          chain still accumulates t = 0 .. ks-1 in order.  CB is chosen so that the whole tile is ONE round of 512 threads
+//   column a thread owns 5 vertically adjacent outputs of one column: 5 + 2r loads, symmetric pairs in registers
+//   fused  (a) Hessian response of the blurred tile (as before); (b) optionally the response of the SOURCE tile (first
+//          level of octaves >= 1: replaces k_response); (c) optionally the half-size image of the blurred tile
+//          (pyramid.cpp:476, replaces k_half): two launches fewer per octave on the critical path.
+template <int KS>
+struct B3 {
+  static constexpr int R = KS / 2;
+  static constexpr int AW = BT_X + 2 + 2 * R, AH = BT_Y + 2 + 2 * R;
+  static constexpr int BW = BT_X + 2, CH = BT_Y + 2;
+  static constexpr int pick_cb() {
+    for (int cb = 6; cb <= 12; cb++)
+      if (((BW + cb - 1) / cb) * AH <= BT_NT) return cb;
+    return 0;
+  }
+  static constexpr int CB = pick_cb();
+  static constexpr int NCB = (BW + CB - 1) / CB;
+  static constexpr int PA = (NCB * CB + 2 * R) | 1;     // covers the reads of the last column block
+  static constexpr int PB = (NCB * CB) | 1;
+  static constexpr int NL = (AH * AW + BT_NT - 1) / BT_NT;
+  static constexpr int RBC = 5, NRGC = (CH + RBC - 1) / RBC;
+  static constexpr int SMEM = (AH * PA + (AH + 1) * PB + CH * BW) * (int)sizeof(float);
+  static_assert(CB > 0 && NRGC * BW <= BT_NT, "tile does not fit one round");
+};
+
+template <int KS>
+__global__ void __launch_bounds__(BT_NT)
+k_blur3(const float* __restrict__ src, float* __restrict__ dst, float* __restrict__ resp, int w, int h,
+        const __grid_constant__ Taps taps, float norm2,
+        float* __restrict__ resp_src, float norm2_src, float* __restrict__ half_out, int ow, int oh) {
+  using G = B3<KS>;
+  constexpr int R = G::R, AW = G::AW, AH = G::AH, PA = G::PA, PB = G::PB, BW = G::BW, CH = G::CH, CB = G::CB;
+  extern __shared__ float sm[];
+  float* A = sm;                        // AH x PA   source tile, (R + 1)-px replicated halo
+  float* B = A + AH * PA;               // (AH + 1) x PB   row-filtered
+  float* Cc = B + (AH + 1) * PB;        // CH x BW   blurred tile, 1-px halo (0 outside the image)
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * BT_X, y0 = blockIdx.y * BT_Y;
+  {
+    float v[G::NL];
+#pragma unroll
+    for (int k = 0; k < G::NL; k++) {
+      const int i = tid + k * BT_NT;
+      if (i < AH * AW) {
+        const int ly = i / AW, lx = i - ly * AW;
+        const int gy = clampi(y0 - 1 - R + ly, 0, h - 1), gx = clampi(x0 - 1 - R + lx, 0, w - 1);
+        v[k] = src[(size_t)gy * w + gx];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < G::NL; k++) {
+      const int i = tid + k * BT_NT;
+      if (i < AH * AW) {
+        const int ly = i / AW, lx = i - ly * AW;
+        A[ly * PA + lx] = v[k];
+      }
+    }
+  }
+  __syncthreads();
+  // (b) response of the source image on the inner tile
+  if (resp_src != nullptr) {
+#pragma unroll
+    for (int q = 0; q < BT_X * BT_Y / BT_NT; q++) {
+      const int i = tid + q * BT_NT, ly = i >> 6, lx = i & 63;
+      const int gx = x0 + lx, gy = y0 + ly;
+      if (gx < w && gy < h) {
+        float v = 0.f;
+        if (gx >= 1 && gx < w - 1 && gy >= 1 && gy < h - 1) v = hessian_at(A + (ly + R + 1) * PA + lx + R + 1, PA, norm2_src);
+        resp_src[(size_t)gy * w + gx] = v;
+      }
+    }
+  }
+  // row pass -> B[row][lx], lx = 0..65 <-> gx = x0 - 1 + lx; output lx reads A columns lx .. lx + ks - 1
+  if (tid < G::NCB * AH) {
+    const int cb = tid / AH, row = tid - cb * AH, lx0 = cb * CB, gx0 = x0 - 1 + lx0;
+    const float* p = A + row * PA + lx0;
+    float* b = B + row * PB + lx0;
+    if (min(gx0 + CB - 1, w - 1) < (w & ~3)) {        // every in-image column of the block is in the vector body
+      float acc[CB];
+#pragma unroll
+      for (int c = 0; c < CB; c++) acc[c] = 0.f;
+#pragma unroll
+      for (int j = 0; j < CB + KS - 1; j++) {
+        const float d = p[j];
+#pragma unroll
+        for (int c = 0; c < CB; c++)
+          if (j - c >= 0 && j - c < KS) acc[c] = fmaf(d, taps.k[j - c], acc[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < CB; c++) b[c] = acc[c];
+    } else {
+#pragma unroll 1
+      for (int c = 0; c < CB; c++) {
+        const int gx = gx0 + c;
+        float v = 0.f;
+        if (gx >= 0 && gx < w) v = row_pass(p + c, taps.k, KS, gx < (w & ~3), gx < (w & ~1));
+        b[c] = v;
+      }
+    }
+  }
+  __syncthreads();
+  // column pass -> C and dst
+  if (tid < G::NRGC * BW) {
+    constexpr int RBC = G::RBC;
+    const int rg = tid / BW, lx = tid - rg * BW, ly0 = rg * RBC;
+    const int gx = x0 - 1 + lx;
+    const float* Tc = B + ly0 * PB + lx;               // C row ly <-> B rows ly .. ly + 2R (centre ly + R)
+    float T[RBC + 2 * R], o[RBC];
+#pragma unroll
+    for (int i = 0; i < RBC + 2 * R; i++) T[i] = Tc[i * PB];
+#pragma unroll
+    for (int i = 0; i < RBC; i++) o[i] = T[i + R] * taps.k[R];
+    if (gx < (w & ~7)) {
+#pragma unroll
+      for (int t = 1; t <= R; t++)
+#pragma unroll
+        for (int i = 0; i < RBC; i++) o[i] = fmaf(T[i + R - t] + T[i + R + t], taps.k[R + t], o[i]);
+    } else {
+#pragma unroll
+      for (int t = 1; t <= R; t++)
+#pragma unroll
+        for (int i = 0; i < RBC; i++) o[i] = o[i] + (T[i + R - t] + T[i + R + t]) * taps.k[R + t];
+    }
+#pragma unroll
+    for (int i = 0; i < RBC; i++) {
+      const int ly = ly0 + i, gy = y0 - 1 + ly;
+      if (ly < CH) {
+        float v = 0.f;
+        if (gx >= 0 && gx < w && gy >= 0 && gy < h) {
+          v = o[i];
+          if (lx >= 1 && lx <= BT_X && ly >= 1 && ly <= BT_Y) dst[(size_t)gy * w + gx] = v;
+        }
+        Cc[ly * BW + lx] = v;
+      }
+    }
+  }
+  if (resp == nullptr && half_out == nullptr) return;
+  __syncthreads();
+  // (a) response of the blurred tile: a thread owns 4 vertically adjacent pixels of one column
+  if (resp != nullptr) {
+    const int lx = tid & 63, ly0 = (tid >> 6) * 4;
+    const int gx = x0 + lx;
+    const float* c = Cc + ly0 * BW + lx;                // rows ly0 .. ly0 + 5 of the haloed tile, columns lx .. lx + 2
+    float v[6][3];
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) v[i][j] = c[i * BW + j];
+    if (gx < w) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int gy = y0 + ly0 + i;
+        if (gy >= h) break;
+        float out = 0.f;
+        if (gx >= 1 && gx < w - 1 && gy >= 1 && gy < h - 1) {
+          const float Lxx = (v[i + 1][0] - 2 * v[i + 1][1] + v[i + 1][2]);
+          const float Lyy = (v[i][1] - 2 * v[i + 1][1] + v[i + 2][1]);
+          const float Lxy = (v[i][2] - v[i][0] + v[i + 2][0] - v[i + 2][2]) / 4.0f;
+          out = (Lxx * Lyy - Lxy * Lxy) * norm2;
+        }
+        resp[(size_t)gy * w + gx] = out;
+      }
+    }
+  }
+  // (c) half-size image of the blurred tile: lerp form a + (b - a) * 0.5, x then y (k_half)
+  if (half_out != nullptr) {
+    const int ox = (x0 >> 1) + (tid & 31), oy = (y0 >> 1) + (tid >> 5);
+    if (ox < ow && oy < oh) {
+      const int ya = min(2 * oy, h - 1) - y0 + 1, yb = min(2 * oy + 1, h - 1) - y0 + 1;
+      const int xa = min(2 * ox, w - 1) - x0 + 1, xb = min(2 * ox + 1, w - 1) - x0 + 1;
+      const float a = Cc[ya * BW + xa], b = Cc[ya * BW + xb];
+      const float c = Cc[yb * BW + xa], d = Cc[yb * BW + xb];
+      const float r0 = a + (b - a) * 0.5f;
+      const float r1 = c + (d - c) * 0.5f;
+      half_out[(size_t)oy * ow + ox] = r0 + (r1 - r0) * 0.5f;
+    }
+  }
+}
+
 // Hessian response of an image already in HBM (first level of octaves >= 1).
 __global__ void k_response(const float* __restrict__ src, float* __restrict__ resp, int w, int h, float norm2) {
   int gx = blockIdx.x * blockDim.x + threadIdx.x, gy = blockIdx.y * blockDim.y + threadIdx.y;
@@ -649,7 +835,22 @@ int blur_smem_bytes(int ks) {
   return (AW * AH + (BT_X + 2) * AH + (BT_X + 2) * (BT_Y + 2)) * (int)sizeof(float);
 }
 
-int launch_blur(modsgpu_ctx* ctx, const float* src, float* dst, float* resp, int w, int h, float sigma, float norm2) {
+template <int KS>
+static void launch_blur3(modsgpu_ctx* ctx, dim3 grid, const float* src, float* dst, float* resp, int w, int h, const Taps& taps,
+                         float norm2, float* resp_src, float norm2_src, float* half_out, int ow, int oh) {
+  static OnceFlags attr_set;
+  if (attr_set.need(ctx->device)) {
+    cudaFuncSetAttribute(k_blur3<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, B3<KS>::SMEM);
+    attr_set.set(ctx->device);
+  }
+  k_blur3<KS><<<grid, BT_NT, B3<KS>::SMEM, ctx->stream>>>(src, dst, resp, w, h, taps, norm2, resp_src, norm2_src, half_out, ow, oh);
+}
+
+// `resp_src` (response of the SOURCE image, first level of octaves >= 1) and `half_out` (half-size copy of the blurred
+// image) are fused into the blur when the ksize-specialised kernel applies; *fused tells the caller whether they were.
+int launch_blur(modsgpu_ctx* ctx, const float* src, float* dst, float* resp, int w, int h, float sigma, float norm2,
+                float* resp_src = nullptr, float norm2_src = 0.f, float* half_out = nullptr, int ow = 0, int oh = 0,
+                bool* fused = nullptr) {
   std::vector<float> t;
   int ks = mg_gaussian_taps(sigma, t);
   if (ks > MAX_KS) MG_FAIL(ctx, MODSGPU_EINVAL, "gaussian kernel too wide for the pyramid blur (ksize > 63)");
@@ -663,12 +864,25 @@ int launch_blur(modsgpu_ctx* ctx, const float* src, float* dst, float* resp, int
     MG_CUDA(ctx, cudaFuncSetAttribute(k_blur_resp2, cudaFuncAttributeMaxDynamicSharedMemorySize, blur2_smem_bytes(MAX_KS)));
     attr_set.set(ctx->device);
   }
+  static const bool no_blur3 = [] { const char* e = getenv("MODSGPU_NO_BLUR3"); return e && atoi(e) != 0; }();
   dim3 grid(ceil_div(w, BT_X), ceil_div(h, BT_Y));
-  MG_PROF(ctx, resp ? "k_blur_resp" : "k_blur", 0, (double)w * h * 4.0 * (resp ? 3 : 2));
-  if (ks >= 7)
+  const bool spec = !no_blur3 && ks >= 7 && ks <= 23;
+  if (fused) *fused = spec;
+  double bytes = (double)w * h * 4.0 * (resp ? 3 : 2);
+  if (spec && resp_src) bytes += (double)w * h * 4.0;
+  if (spec && half_out) bytes += (double)ow * oh * 4.0;
+  MG_PROF(ctx, resp ? "k_blur_resp" : "k_blur", 0, bytes);
+  if (spec) {
+#define B3_CASE(K) case K: launch_blur3<K>(ctx, grid, src, dst, resp, w, h, taps, norm2, resp_src, norm2_src, half_out, ow, oh); break;
+    switch (ks) {
+      B3_CASE(7) B3_CASE(9) B3_CASE(11) B3_CASE(13) B3_CASE(15) B3_CASE(17) B3_CASE(19) B3_CASE(21) B3_CASE(23)
+    }
+#undef B3_CASE
+  } else if (ks >= 7) {
     k_blur_resp2<<<grid, BT_NT, blur2_smem_bytes(ks), ctx->stream>>>(src, dst, resp, w, h, taps, norm2);
-  else
+  } else {
     k_blur_resp<<<grid, BT_THREADS, blur_smem_bytes(ks), ctx->stream>>>(src, dst, resp, w, h, taps, norm2);
+  }
   MG_LAUNCHED(ctx);
   return 0;
 }
@@ -891,13 +1105,9 @@ int mg_detect_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
         k_response<<<grid, blk, 0, ctx->stream>>>(Lv, Rv, w, h, norm * norm);
         MG_LAUNCHED(ctx);
       }
-    } else {
-      float norm = curSigma * curSigma;
-      dim3 blk(32, 8), grid(ceil_div(w, 32), ceil_div(h, 8));
-      MG_PROF(ctx, "k_response", 0, (double)px * 8.0);
-      k_response<<<grid, blk, 0, ctx->stream>>>(Lv, Rv, w, h, norm * norm);
-      MG_LAUNCHED(ctx);
     }
+    // first level of octaves >= 1: its response is produced by the blur that reads it (level 1), see launch_blur
+    bool first_resp_pending = o > 0;
     NmsArgs na;
     memset(&na, 0, sizeof(na));
     na.nlev = 0;
@@ -913,15 +1123,30 @@ int mg_detect_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
         MG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->det_fork_ev, 0));
         ctx->stream = ctx->stream2;
       }
-      int rc = launch_blur(ctx, Lv + px * (i - 1), Lv + px * i, Rv + px * i, w, h, sigma, norm * norm);
-      if (rc) { ctx->stream = main_stream; return rc; }
+      const bool want_half = i == nS && o + 1 < nOct;
+      bool fused = false;
+      {
+        const float n0 = p->initialSigma * p->initialSigma;
+        int rc = launch_blur(ctx, Lv + px * (i - 1), Lv + px * i, Rv + px * i, w, h, sigma, norm * norm,
+                             first_resp_pending ? Rv : nullptr, n0 * n0,
+                             want_half ? pyr + oct_off[o + 1] : nullptr, want_half ? ow[o + 1] : 0, want_half ? oh[o + 1] : 0, &fused);
+        if (rc) { ctx->stream = main_stream; return rc; }
+      }
+      if (first_resp_pending && !fused) {
+        const float n0 = p->initialSigma * p->initialSigma;
+        dim3 blk(32, 8), grid(ceil_div(w, 32), ceil_div(h, 8));
+        MG_PROF(ctx, "k_response", 0, (double)px * 8.0);
+        k_response<<<grid, blk, 0, ctx->stream>>>(Lv, Rv, w, h, n0 * n0);
+        MG_LAUNCHED(ctx);
+      }
+      first_resp_pending = false;
       if (i >= 2) {
         LevelArgs& L = na.lv[na.nlev++];
         L.low = Rv + px * (i - 2); L.cur = Rv + px * (i - 1); L.high = Rv + px * i;
         L.blur = Lv + px * (i - 1);
         L.curScale = curSigma; L.level = i - 1;
       }
-      if (i == nS && o + 1 < nOct) {
+      if (want_half && !fused) {
         dim3 blk(32, 8), grid(ceil_div(ow[o + 1], 32), ceil_div(oh[o + 1], 8));
         MG_PROF(ctx, "k_half", 0, (double)ow[o + 1] * oh[o + 1] * 20.0);
         k_half<<<grid, blk, 0, ctx->stream>>>(Lv + px * i, w, h, pyr + oct_off[o + 1], ow[o + 1], oh[o + 1]);

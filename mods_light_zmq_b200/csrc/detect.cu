@@ -637,24 +637,41 @@ __device__ void localize(const NmsArgs& a, const LevelArgs& L, int li, int r, in
 __global__ void k_nms_localize(NmsArgs a, int* map, Cand* cands, int* ncand, int cap) {
   const int li = blockIdx.z;
   const LevelArgs& L = a.lv[li];
-  int c = a.border + blockIdx.x * blockDim.x + threadIdx.x;
-  int r = a.border + blockIdx.y * blockDim.y + threadIdx.y;
+  const int c = a.border + blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = a.border + blockIdx.y * blockDim.y + threadIdx.y;
   if (c >= a.w - a.border || r >= a.h - a.border) return;
   const int w = a.w;
   const float val = L.cur[(size_t)r * w + c];
-  bool pos = val > a.posThr, neg = val < a.negThr;
+  const bool pos = val > a.posThr, neg = val < a.negThr;
   if (!pos && !neg) return;
-  const float* planes[3] = {L.cur, L.low, L.high};
-  bool ok = true;
-  for (int p = 0; p < 3 && ok; p++) {
-    const float* q = planes[p] + (size_t)(r - 1) * w + (c - 1);
-    for (int j = 0; j < 3 && ok; j++)
-      for (int i = 0; i < 3; i++) {
-        float v = q[j * w + i];
-        if (pos ? (v > val) : (v < val)) { ok = false; break; }
-      }
+  // isMax / isMin over the 3 x 3 x 3 neighbourhood.  The tests are order independent (all 26 must pass), so the loads of a
+  // plane are issued together: the early-exit loop of the first version was a chain of up to 27 dependent L2 round trips
+  // per surviving thread and made every launch ~16 us whatever the level's size.
+  {
+    const float* q = L.cur + (size_t)(r - 1) * w + (c - 1);
+    float v[9];
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+      for (int i = 0; i < 3; i++) v[j * 3 + i] = q[j * w + i];
+    bool ok = true;
+#pragma unroll
+    for (int t = 0; t < 9; t++) ok = ok && !(pos ? (v[t] > val) : (v[t] < val));
+    if (!ok) return;
   }
-  if (!ok) return;
+  {
+    const float* ql = L.low + (size_t)(r - 1) * w + (c - 1);
+    const float* qh = L.high + (size_t)(r - 1) * w + (c - 1);
+    float v[18];
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+      for (int i = 0; i < 3; i++) { v[j * 3 + i] = ql[j * w + i]; v[9 + j * 3 + i] = qh[j * w + i]; }
+    bool ok = true;
+#pragma unroll
+    for (int t = 0; t < 18; t++) ok = ok && !(pos ? (v[t] > val) : (v[t] < val));
+    if (!ok) return;
+  }
   localize(a, L, li, r, c, map, cands, ncand, cap);
 }
 

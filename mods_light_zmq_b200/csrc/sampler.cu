@@ -215,50 +215,91 @@ constexpr int NT = 256;
 
 __device__ __forceinline__ int fast_div(int a, float inv_b) { return (int)(((float)a + 0.5f) * inv_b); }
 
-// one thread per row: the float coordinate sequence of interpolate() (helpers.cpp:551-626), every SEG-th kept
-__device__ __forceinline__ void gen_row_starts(const PatchMeta& m, int j, int R, int nseg, float2* __restrict__ dst) {
-  const int half = R / 2;
+// Per-row coordinate table.  One thread per row walks the float coordinate sequence of interpolate() (helpers.cpp:551-626:
+// WX += a11 per sample, sequentially rounded -- that sequence is the contract) and keeps every TS-th coordinate; a lane of
+// the samplers below replays at most TS - 1 additions from the nearest entry.  TS = 4 where the table fits (classes A, B1
+// and the large-window slab), 8 for B2.
+// The walker also decides whether the row is INTERIOR: the sequence is monotone in x and in y (fl(x + a) >= x for a >= 0),
+// so if its first and last sample pass the bounds test of interpolate(), every sample of the row does, and the samplers
+// skip the per-sample test, the selects and the predicate spills that came with them (rows of a warp vote).
+__device__ __forceinline__ bool sample_inside(float WX, float WY, int w, int h) {
+  return WX >= 0 && WY >= 0 && (int)floorf(WX) < w - 1 && (int)floorf(WY) < h - 1;
+}
+template <int TS>
+__device__ __forceinline__ bool gen_row_starts(const PatchMeta& m, int j, int R, int w, int h, float2* __restrict__ dst) {
+  const int half = R / 2, nte = (R + TS - 1) / TS;
   float rx = m.x - (float)half * m.a12, ry = m.y - (float)half * m.a22;
   for (int t = 0; t < j; t++) { rx += m.a12; ry += m.a22; }
   float WX = rx - (float)half * m.a11, WY = ry - (float)half * m.a21;
-  for (int s = 0; s < nseg; s++) {
-    dst[s] = make_float2(WX, WY);
+  bool ok = sample_inside(WX, WY, w, h);
+  for (int e = 0; e < nte - 1; e++) {
+    dst[e] = make_float2(WX, WY);
 #pragma unroll
-    for (int t = 0; t < SEG; t++) { WX += m.a11; WY += m.a21; }
+    for (int t = 0; t < TS; t++) { WX += m.a11; WY += m.a21; }
+  }
+  dst[nte - 1] = make_float2(WX, WY);
+  for (int i = (nte - 1) * TS; i < R - 1; i++) { WX += m.a11; WY += m.a21; }      // on to the row's last sample
+  return ok && sample_inside(WX, WY, w, h);
+}
+
+// one sample: `rep` sequential additions from table entry c, then interpolate()'s bilinear form.
+// INTERIOR: the row passed the walker's test, no bounds handling.  Otherwise branch-free (out-of-image samples read pixel
+// (0,0) and are zeroed by the select) so that the gathers of several unrolled segments can be in flight together.
+template <int TS, bool INTERIOR>
+__device__ __forceinline__ float sample_seg(const float* __restrict__ img, int w, int h, float2 c, float a11, float a21, int rep) {
+  float WX = c.x, WY = c.y;
+#pragma unroll
+  for (int t = 0; t < TS - 1; t++)
+    if (t < rep) { WX += a11; WY += a21; }
+  if (INTERIOR) {
+    const int x = (int)WX, y = (int)WY;                  // both >= 0: truncation is floor
+    const float* p = img + (y * w + x);
+    const float v00 = p[0], v01 = p[1], v10 = p[w], v11 = p[w + 1];
+    const float wx = WX - (float)x;
+    const float I1 = wx * (v01 - v00) + v00;
+    return (WY - (float)y) * (wx * (v11 - v10) + v10 - I1) + I1;
+  } else {
+    const int x = (int)floorf(WX), y = (int)floorf(WY);
+    const bool ok = WX >= 0 && WY >= 0 && x < w - 1 && y < h - 1;
+    const float v = bilinear(img, w, ok ? x : 0, ok ? y : 0, ok ? WX : 0.f, ok ? WY : 0.f);
+    return ok ? v : 0.f;
   }
 }
 
-// lane `sub` of an 8-lane group: sample i0 + sub of a row whose segment starts at coordinate c
-// Branch-free (out-of-image samples read pixel (0,0) and are zeroed by the select) so that the gathers of several
-// unrolled segments can be in flight together: the sampling loops are bound by gather latency, not by issue.
-__device__ __forceinline__ float sample_seg(const float* __restrict__ img, int w, int h, float2 c, float a11, float a21, int sub) {
-  float WX = c.x, WY = c.y;
-#pragma unroll
-  for (int t = 0; t < SEG - 1; t++)
-    if (t < sub) { WX += a11; WY += a21; }
-  const int x = (int)floorf(WX), y = (int)floorf(WY);
-  const bool ok = WX >= 0 && WY >= 0 && x < w - 1 && y < h - 1;
-  const float v = bilinear(img, w, ok ? x : 0, ok ? y : 0, ok ? WX : 0.f, ok ? WY : 0.f);
-  return ok ? v : 0.f;
-}
-
-// one row (or row block) of the first resampling: segments in groups of 4 -- coordinates first, then the 4 x 4 gathers,
-// then the stores (the stores may alias the coordinate table as far as the compiler knows, so the order is spelled out)
-__device__ __forceinline__ void sample_row(const float* __restrict__ img, int w, int h, const float2* cs, int nseg, float a11, float a21,
-                                           int sub, float* row, int R) {
+// one row (or row block) of the first resampling: an 8-lane group walks the row in segments of 8 consecutive samples, four
+// segments per step -- coordinates first, then the 4 x 4 gathers, then the stores (the stores may alias the coordinate
+// table as far as the compiler knows, so the order is spelled out).  Lanes beyond the row's end re-sample the last table
+// entry (a real sample of the row, so the interior path never reads outside the image) and store nothing.
+template <int TS, bool INTERIOR>
+__device__ __forceinline__ void sample_row_impl(const float* __restrict__ img, int w, int h, const float2* cs, int nseg, float a11, float a21,
+                                                int sub, float* row, int R) {
+  const int nte = (R + TS - 1) / TS;
   for (int s0 = 0; s0 < nseg; s0 += 4) {
     float2 c[4];
     float v[4];
-#pragma unroll
-    for (int u = 0; u < 4; u++) c[u] = cs[min(s0 + u, nseg - 1)];
-#pragma unroll
-    for (int u = 0; u < 4; u++) v[u] = sample_seg(img, w, h, c[u], a11, a21, sub);
+    int rep[4];
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       const int i = (s0 + u) * SEG + sub;
-      if (s0 + u < nseg && i < R) row[i] = v[u];
+      const bool live = i < R;
+      c[u] = cs[live ? i / TS : nte - 1];
+      rep[u] = live ? i % TS : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) v[u] = sample_seg<TS, INTERIOR>(img, w, h, c[u], a11, a21, rep[u]);
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = (s0 + u) * SEG + sub;
+      if (i < R) row[i] = v[u];
     }
   }
+}
+// `fast` must be warp uniform (the caller votes over the rows of its warp at a convergent point)
+template <int TS>
+__device__ __forceinline__ void sample_row(const float* __restrict__ img, int w, int h, const float2* cs, int nseg, float a11, float a21,
+                                           int sub, float* row, int R, bool fast) {
+  if (fast) sample_row_impl<TS, true>(img, w, h, cs, nseg, a11, a21, sub, row, R);
+  else sample_row_impl<TS, false>(img, w, h, cs, nseg, a11, a21, sub, row, R);
 }
 
 // Row pass, vector form (x < R & ~3, ks >= 7): s = 0; s = fma(p[t], k[t], s), t = 0..ks-1, for CB adjacent
@@ -321,9 +362,10 @@ __device__ __forceinline__ uint8_t quant_u8(float v) {
 }
 
 // ---- class A: R <= 65, the whole R x R window is filtered ------------------------------------------------
+constexpr int A_TS = 8;      // coordinate table spacing of class A (4 was measured: fewer replay additions, no gain -- the phase is gather-latency bound)
 __host__ __device__ inline int a_smem_floats(int R, int r) {
-  const int nseg = (R + SEG - 1) / SEG, PS = (R + 2 * r + 4) | 1, PT = R | 1;
-  return 64 + 64 + 2 * R * nseg + R * PS + (R + 2 * r + 4) * PT;
+  const int nte = (R + A_TS - 1) / A_TS, PS = (R + 2 * r + 4) | 1, PT = R | 1;
+  return 64 + 64 + 72 + 2 * R * nte + R * PS + (R + 2 * r + 4) * PT;
 }
 
 __global__ void __launch_bounds__(NT)
@@ -335,11 +377,12 @@ k_sample_a(const float* __restrict__ img, int w, int h, const PatchMeta* __restr
   const PatchMeta m = metas[blockIdx.x];
   const int tid = threadIdx.x;
   const int R = m.R, ks = m.ks, r = ks >> 1;
-  const int nseg = (R + SEG - 1) / SEG, PS = (R + 2 * r + 4) | 1, PT = R | 1;
+  const int nseg = (R + SEG - 1) / SEG, nte = (R + A_TS - 1) / A_TS, PS = (R + 2 * r + 4) | 1, PT = R | 1;
   float* P = sm;
   float* kp = P + 64;
-  float2* C2 = reinterpret_cast<float2*>(kp + 64);
-  float* Sp = reinterpret_cast<float*>(C2 + R * nseg);
+  int* rowok = reinterpret_cast<int*>(kp + 64);       // 72: per-row interior flags
+  float2* C2 = reinterpret_cast<float2*>(kp + 64 + 72);
+  float* Sp = reinterpret_cast<float*>(C2 + R * nte);
   float* Tp = Sp + R * PS;
   float* B = Sp;   // R x R, written after the row pass has consumed Sp
 
@@ -348,15 +391,16 @@ k_sample_a(const float* __restrict__ img, int w, int h, const PatchMeta* __restr
     float p = (float)(R / 2) - (float)(ps / 2) * m.scale;
     for (int i = 0; i < ps; i++) { P[i] = p; p += m.scale; }
   }
-  if (tid < R) gen_row_starts(m, tid, R, nseg, C2 + tid * nseg);
+  if (tid < R) rowok[tid] = gen_row_starts<A_TS>(m, tid, R, w, h, C2 + tid * nte);
   __syncthreads();
   // 1. first resampling: an 8-lane group walks one row segment by segment (no index division per sample)
   {
     const int g = tid >> 3, sub = tid & 7;
-    for (int j = g; j < R; j += NT / SEG) {
-      float* row = Sp + j * PS + r;
-      const float2* cs = C2 + j * nseg;
-      sample_row(img, w, h, cs, nseg, m.a11, m.a21, sub, row, R);
+    for (int j0 = 0; j0 < R; j0 += NT / SEG) {
+      const int j = j0 + g;
+      const bool act = j < R;
+      const bool fast = __all_sync(0xffffffffu, act ? rowok[j] != 0 : true);
+      if (act) sample_row<A_TS>(img, w, h, C2 + j * nte, nseg, m.a11, m.a21, sub, Sp + j * PS + r, R, fast);
     }
   }
   __syncthreads();
@@ -451,14 +495,16 @@ k_sample_a(const float* __restrict__ img, int w, int h, const PatchMeta* __restr
 
 // ---- class B: 66 <= R <= 160 (scale >= 2): only the 64 columns / rows the final resampling reads ----------
 constexpr int B_NB = 32;     // rows sampled + row-filtered per iteration
+constexpr int B1_TS = 8;     // coordinate table spacing of class B1 (B2: 8)
 constexpr int B_TP = 65;     // pitch of T (64 needed columns)
-__host__ __device__ inline int b_smem_floats(int R, int r) {
-  const int nseg = (R + SEG - 1) / SEG, PS = (R + 2 * r + 2) | 1;
-  int u = 2 * R * nseg + B_NB * PS;      // C2 + S block, later reused for B (64 x 64)
+__host__ __device__ inline int b_smem_floats(int R, int r, int ts) {
+  const int nte = (R + ts - 1) / ts, PS = (R + 2 * r + 2) | 1;
+  int u = 2 * R * nte + B_NB * PS;      // C2 + S block, later reused for B (64 x 64)
   if (u < 4096) u = 4096;
-  return 64 + 64 + 64 + u + (R + 2 * r + 2) * B_TP;
+  return 64 + 64 + 64 + 160 + u + (R + 2 * r + 2) * B_TP;
 }
 
+template <int TS>
 __global__ void __launch_bounds__(NT)
 k_sample_b(const float* __restrict__ img, int w, int h, const PatchMeta* __restrict__ metas,
            const float* __restrict__ taps_all, uint8_t* __restrict__ out, const int* __restrict__ cnt) {
@@ -468,14 +514,15 @@ k_sample_b(const float* __restrict__ img, int w, int h, const PatchMeta* __restr
   const PatchMeta m = metas[blockIdx.x];
   const int tid = threadIdx.x;
   const int R = m.R, ks = m.ks, r = ks >> 1;
-  const int nseg = (R + SEG - 1) / SEG, PS = (R + 2 * r + 2) | 1;
+  const int nseg = (R + SEG - 1) / SEG, nte = (R + TS - 1) / TS, PS = (R + 2 * r + 2) | 1;
   float* P = sm;
   int* X = reinterpret_cast<int*>(P + 64);
   float* kp = P + 128;
-  float2* C2 = reinterpret_cast<float2*>(kp + 64);
-  float* Sb = reinterpret_cast<float*>(C2 + R * nseg);
+  int* rowok = reinterpret_cast<int*>(kp + 64);     // 160: per-row interior flags
+  float2* C2 = reinterpret_cast<float2*>(kp + 64 + 160);
+  float* Sb = reinterpret_cast<float*>(C2 + R * nte);
   float* B = reinterpret_cast<float*>(C2);          // 64 x 64 once C2 / Sb are dead
-  int un = 2 * R * nseg + B_NB * PS;
+  int un = 2 * R * nte + B_NB * PS;
   if (un < 4096) un = 4096;
   float* Tp = reinterpret_cast<float*>(C2) + un;
 
@@ -484,7 +531,7 @@ k_sample_b(const float* __restrict__ img, int w, int h, const PatchMeta* __restr
     float p = (float)(R / 2) - (float)(ps / 2) * m.scale;
     for (int i = 0; i < ps; i++) { P[i] = p; X[i] = (int)floorf(p); p += m.scale; }
   }
-  if (tid < R) gen_row_starts(m, tid, R, nseg, C2 + tid * nseg);
+  if (tid < R) rowok[tid] = gen_row_starts<TS>(m, tid, R, w, h, C2 + tid * nte);
   __syncthreads();
   const int xv = R & ~3;
   for (int j0 = 0; j0 < R; j0 += B_NB) {
@@ -492,11 +539,9 @@ k_sample_b(const float* __restrict__ img, int w, int h, const PatchMeta* __restr
     // 1. sample nrows rows: group g (8 lanes) walks row j0 + g segment by segment
     {
       const int g = tid >> 3, sub = tid & 7;
-      if (g < nrows) {
-        float* row = Sb + g * PS + r;
-        const float2* cs = C2 + (j0 + g) * nseg;
-        sample_row(img, w, h, cs, nseg, m.a11, m.a21, sub, row, R);
-      }
+      const bool act = g < nrows;
+      const bool fast = __all_sync(0xffffffffu, act ? rowok[j0 + g] != 0 : true);
+      if (act) sample_row<TS>(img, w, h, C2 + (j0 + g) * nte, nseg, m.a11, m.a21, sub, Sb + g * PS + r, R, fast);
     }
     __syncthreads();
     // replicate the borders into the padding (r left, r + 2 right entries per row)
@@ -511,33 +556,30 @@ k_sample_b(const float* __restrict__ img, int w, int h, const PatchMeta* __restr
       }
     }
     __syncthreads();
-    // 2. row pass at the 32 column pairs (x_i, x_i + 1): pair = tid >> 3, rows rg + 8k
+    // 2. row pass at the 32 column pairs (x_i, x_i + 1).  LANE = ROW of the block, a warp owns the pairs w, w + 8, w + 16,
+    //    w + 24: with the odd row pitch every sample load and every T store of a warp is bank-conflict free.  (The first
+    //    mapping -- 4 pairs x 8 rows per warp -- measured 2.2 wavefronts per sample load and 3.8 per store: the row
+    //    pass sits on the shared-memory pipe, so that was most of its time.)
     {
-      const int pi = tid >> 3, rg = tid & 7, x0 = X[pi];
-      int rowi[4];
+      const int wq = tid >> 5, row = tid & 31, rowc = min(row, nrows - 1);
+      const float* rows[4];
+      int x0[4];
 #pragma unroll
-      for (int b = 0; b < 4; b++) rowi[b] = rg + 8 * b;
-      if (x0 + 1 < xv) {
-        const float* rows[4];
+      for (int b = 0; b < 4; b++) { x0[b] = X[wq + 8 * b]; rows[b] = Sb + rowc * PS + x0[b]; }
+      float acc[4][2];
+      rowpass_block<2, 4>(rows, kp, ks, acc);
+      if (row < nrows) {
+        float* t = Tp + (j0 + row + r) * B_TP + 2 * wq;
 #pragma unroll
-        for (int b = 0; b < 4; b++) rows[b] = Sb + min(rowi[b], nrows - 1) * PS + x0;
-        float acc[4][2];
-        rowpass_block<2, 4>(rows, kp, ks, acc);
-#pragma unroll
-        for (int b = 0; b < 4; b++)
-          if (rowi[b] < nrows) {
-            float* t = Tp + (j0 + rowi[b] + r) * B_TP + 2 * pi;
-            t[0] = acc[b][0]; t[1] = acc[b][1];
+        for (int b = 0; b < 4; b++) {
+          if (x0[b] + 1 < xv) {           // warp uniform
+            t[16 * b] = acc[b][0]; t[16 * b + 1] = acc[b][1];
+          } else {                        // OpenCV's scalar tail columns (the last pair at most)
+            const float* rp = Sb + row * PS + r;
+            t[16 * b] = row_pass_at(rp, R, x0[b], kp, ks);
+            t[16 * b + 1] = row_pass_at(rp, R, x0[b] + 1, kp, ks);
           }
-      } else {
-#pragma unroll 1
-        for (int b = 0; b < 4; b++)
-          if (rowi[b] < nrows) {
-            const float* row = Sb + rowi[b] * PS + r;
-            float* t = Tp + (j0 + rowi[b] + r) * B_TP + 2 * pi;
-            t[0] = row_pass_at(row, R, x0, kp, ks);
-            t[1] = row_pass_at(row, R, x0 + 1, kp, ks);
-          }
+        }
       }
     }
     __syncthreads();
@@ -607,19 +649,25 @@ __device__ __forceinline__ int needed_pos(float p, int odd, int R) {
 constexpr int L0_ROWS = 128, L1_ROWS = 16, L2_ROWS = 16, L3_OUT_ROWS = 4;
 
 // per-region scratch (floats): [C: R x nseg float2 row-segment start coordinates | S: R x R | T: R x 2ps]
-__host__ __device__ inline long long large_c_floats(int R) { return 2LL * R * ((R + SEG - 1) / SEG); }
+constexpr int L_TS = 8;      // table spacing of the slab path; every table row carries one extra entry: .x = interior flag
+__host__ __device__ inline int large_row_entries(int R) { return (R + L_TS - 1) / L_TS + 1; }
+__host__ __device__ inline long long large_c_floats(int R) { return 2LL * R * large_row_entries(R); }
 
 // phase 0: one thread per window row walks the row's float coordinate sequence once (the sequential `WX += a11` of
 // interpolate(), helpers.cpp:551-626, is what makes the samples bit-exact) and keeps every SEG-th coordinate
 __global__ void __launch_bounds__(L0_ROWS)
 k_large_starts(const PatchMeta* __restrict__ metas, int nreg, const int* __restrict__ pre, float* __restrict__ scratch,
-               const int* __restrict__ nreg_dev) {
+               const int* __restrict__ nreg_dev, int w, int h) {
   if (nreg_dev != nullptr) { nreg = *nreg_dev; if ((int)blockIdx.x >= pre[nreg]) return; }
   const int reg = find_region(pre, nreg, blockIdx.x);
   const PatchMeta m = metas[reg];
-  const int R = m.R, nseg = (R + SEG - 1) / SEG;
+  const int R = m.R, nent = large_row_entries(R);
   const int j = (blockIdx.x - pre[reg]) * L0_ROWS + threadIdx.x;
-  if (j < R) gen_row_starts(m, j, R, nseg, reinterpret_cast<float2*>(scratch + m.scratch_off) + (size_t)j * nseg);
+  if (j < R) {
+    float2* dst = reinterpret_cast<float2*>(scratch + m.scratch_off) + (size_t)j * nent;
+    const bool ok = gen_row_starts<L_TS>(m, j, R, w, h, dst);
+    dst[nent - 1] = make_float2(ok ? 1.f : 0.f, 0.f);
+  }
 }
 
 // phase 1: S[j][i] for L1_ROWS rows of one region; an 8-lane group walks one row segment by segment (as class A / B)
@@ -629,12 +677,14 @@ k_large_resample(const float* __restrict__ img, int w, int h, const PatchMeta* _
   if (nreg_dev != nullptr) { nreg = *nreg_dev; if ((int)blockIdx.x >= pre[nreg]) return; }
   const int reg = find_region(pre, nreg, blockIdx.x);
   const PatchMeta m = metas[reg];
-  const int R = m.R, nseg = (R + SEG - 1) / SEG;
+  const int R = m.R, nseg = (R + SEG - 1) / SEG, nent = large_row_entries(R);
   const int j = (blockIdx.x - pre[reg]) * L1_ROWS + (threadIdx.x >> 3), sub = threadIdx.x & 7;
-  if (j >= R) return;
-  const float2* cs = reinterpret_cast<const float2*>(scratch + m.scratch_off) + (size_t)j * nseg;
+  const bool act = j < R;
+  const float2* cs = reinterpret_cast<const float2*>(scratch + m.scratch_off) + (size_t)(act ? j : 0) * nent;
+  const bool fast = __all_sync(0xffffffffu, act ? cs[nent - 1].x != 0.f : true);
+  if (!act) return;
   float* row = scratch + m.scratch_off + large_c_floats(R) + (size_t)j * R;
-  sample_row(img, w, h, cs, nseg, m.a11, m.a21, sub, row, R);
+  sample_row<L_TS>(img, w, h, cs, nseg, m.a11, m.a21, sub, row, R, fast);
 }
 
 // phase 2a: row pass at the 2*ps needed columns for L2_ROWS rows of one region: T[y][ci].  Rows are staged in shared
@@ -873,7 +923,8 @@ int mg_sample_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
     MG_CUDA(ctx, cudaFuncSetAttribute(k_large_rowpass, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (2 * MAX_PS + 642 + L2_ROWS * ((MAX_R + 602) | 1)) * 4));
     MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_a, cudaFuncAttributeMaxDynamicSharedMemorySize, a_smem_floats(A2_R, 30) * 4));
-    MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_b, cudaFuncAttributeMaxDynamicSharedMemorySize, b_smem_floats(B2_R, 30) * 4));
+    MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_b<B1_TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, b_smem_floats(B1_R, 30, B1_TS) * 4));
+    MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_b<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, b_smem_floats(B2_R, 30, 8) * 4));
     attr_set.set(ctx->device);
   }
   // algorithmic bytes: R*R*4 read + ps*ps written per region
@@ -897,16 +948,17 @@ int mg_sample_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
   }
   for (int c = C_B1; c <= C_B2; c++) {
     if (cls[c].empty()) continue;
-    const int smem = b_smem_floats(std::min(b_maxR[c - C_B1], cls[c][0].R), cls_r[c]) * 4;
+    const int smem = b_smem_floats(std::min(b_maxR[c - C_B1], cls[c][0].R), cls_r[c], c == C_B1 ? B1_TS : 8) * 4;
     MG_PROF(ctx, c == C_B1 ? "k_sample_b<R<=100>" : "k_sample_b<R<=160>", 0, alg_bytes(cls[c]));
-    k_sample_b<<<(unsigned)cls[c].size(), NT, smem, ctx->stream>>>(img->d, img->w, img->h, dm + cls_off[c], dtaps, d_out, nullptr);
+    if (c == C_B1) k_sample_b<B1_TS><<<(unsigned)cls[c].size(), NT, smem, ctx->stream>>>(img->d, img->w, img->h, dm + cls_off[c], dtaps, d_out, nullptr);
+    else k_sample_b<8><<<(unsigned)cls[c].size(), NT, smem, ctx->stream>>>(img->d, img->w, img->h, dm + cls_off[c], dtaps, d_out, nullptr);
     MG_LAUNCHED(ctx);
   }
   if (nl > 0) {
     const PatchMeta* dl = dm + cls_off[C_LARGE];
     float* scr = ctx->smp_scratch.as<float>();
     MG_PROF(ctx, "k_large_starts", 2, (double)nl);
-    k_large_starts<<<pre0[nl], L0_ROWS, 0, ctx->stream>>>(dl, nl, dpre0, scr, nullptr);
+    k_large_starts<<<pre0[nl], L0_ROWS, 0, ctx->stream>>>(dl, nl, dpre0, scr, nullptr, img->w, img->h);
     MG_LAUNCHED(ctx);
     MG_PROF(ctx, "k_large_resample", 0, alg_bytes(large));
     k_large_resample<<<pre1[nl], 128, 0, ctx->stream>>>(img->d, img->w, img->h, dl, nl, dpre1, scr, nullptr);
@@ -1231,7 +1283,8 @@ int mg_sample_enqueue_dev(modsgpu_ctx* ctx, const modsgpu_image* img, const DevR
     MG_CUDA(ctx, cudaFuncSetAttribute(k_large_rowpass, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (2 * MAX_PS + 642 + L2_ROWS * ((MAX_R + 602) | 1)) * 4));
     MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_a, cudaFuncAttributeMaxDynamicSharedMemorySize, a_smem_floats(A2_R, 30) * 4));
-    MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_b, cudaFuncAttributeMaxDynamicSharedMemorySize, b_smem_floats(B2_R, 30) * 4));
+    MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_b<B1_TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, b_smem_floats(B1_R, 30, B1_TS) * 4));
+    MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_b<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, b_smem_floats(B2_R, 30, 8) * 4));
     attr_set.set(ctx->device);
   }
   // the algorithmic bytes of these launches are only known on the device: k_smp_scatter accumulates them per class and
@@ -1254,9 +1307,10 @@ int mg_sample_enqueue_dev(modsgpu_ctx* ctx, const modsgpu_image* img, const DevR
   }
   for (int c = SC_B1; c <= SC_B2; c++) {
     if (st.cls_cnt[c] <= 0) continue;
-    const int smem = b_smem_floats(std::min(b_maxR[c - SC_B1], st.cls_rmax[c]), st.cls_kr[c]) * 4;
+    const int smem = b_smem_floats(std::min(b_maxR[c - SC_B1], st.cls_rmax[c]), st.cls_kr[c], c == SC_B1 ? B1_TS : 8) * 4;
     MG_PROF(ctx, c == SC_B1 ? "k_sample_b<R<=100>" : "k_sample_b<R<=160>", 0, alg_bytes(c));
-    k_sample_b<<<(unsigned)st.cls_cnt[c], NT, smem, ctx->stream>>>(img->d, img->w, img->h, dm + lay.cls_off[c], dtaps, d_out, dcnt + c);
+    if (c == SC_B1) k_sample_b<B1_TS><<<(unsigned)st.cls_cnt[c], NT, smem, ctx->stream>>>(img->d, img->w, img->h, dm + lay.cls_off[c], dtaps, d_out, dcnt + c);
+    else k_sample_b<8><<<(unsigned)st.cls_cnt[c], NT, smem, ctx->stream>>>(img->d, img->w, img->h, dm + lay.cls_off[c], dtaps, d_out, dcnt + c);
     MG_LAUNCHED(ctx);
   }
   if (nl > 0) {
@@ -1264,7 +1318,7 @@ int mg_sample_enqueue_dev(modsgpu_ctx* ctx, const modsgpu_image* img, const DevR
     float* scr = ctx->smp_scratch.as<float>();
     const int* dnl = dcnt + SC_LARGE;
     MG_PROF(ctx, "k_large_starts", 2, (double)nl);
-    k_large_starts<<<st.pre0, L0_ROWS, 0, ctx->stream>>>(dl, nl, dpre0, scr, dnl);
+    k_large_starts<<<st.pre0, L0_ROWS, 0, ctx->stream>>>(dl, nl, dpre0, scr, dnl, img->w, img->h);
     MG_LAUNCHED(ctx);
     MG_PROF(ctx, "k_large_resample", 0, alg_bytes(SC_LARGE));
     k_large_resample<<<st.pre1, 128, 0, ctx->stream>>>(img->d, img->w, img->h, dl, nl, dpre1, scr, dnl);

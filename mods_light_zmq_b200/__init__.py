@@ -12,6 +12,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmodsgpu.so")
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")     # see modsgpu_create (api.cu)
 WEIGHTS_DIR = os.path.join(os.path.dirname(HERE), "weights")
 
 KP_DTYPE = np.dtype([("x", "f4"), ("y", "f4"), ("s", "f4"), ("response", "f4"), ("type", "i4"), ("octave", "i4"),

@@ -270,36 +270,44 @@ __device__ __forceinline__ float sample_seg(const float* __restrict__ img, int w
 // segments per step -- coordinates first, then the 4 x 4 gathers, then the stores (the stores may alias the coordinate
 // table as far as the compiler knows, so the order is spelled out).  Lanes beyond the row's end re-sample the last table
 // entry (a real sample of the row, so the interior path never reads outside the image) and store nothing.
-template <int TS, bool INTERIOR>
+template <int TS, bool INTERIOR, int UNR>
 __device__ __forceinline__ void sample_row_impl(const float* __restrict__ img, int w, int h, const float2* cs, int nseg, float a11, float a21,
                                                 int sub, float* row, int R) {
   const int nte = (R + TS - 1) / TS;
-  for (int s0 = 0; s0 < nseg; s0 += 4) {
-    float2 c[4];
-    float v[4];
-    int rep[4];
+  float2 c[UNR];
+  int rep[UNR];
+  auto fetch = [&](int s0) {               // table entries of the UNR segments starting at s0
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
+    for (int u = 0; u < UNR; u++) {
       const int i = (s0 + u) * SEG + sub;
       const bool live = i < R;
       c[u] = cs[live ? i / TS : nte - 1];
       rep[u] = live ? i % TS : 0;
     }
+  };
+  // PIPE (slab path, table in global memory): the next step's entries travel while this step's gathers do.  With the table
+  // in shared memory the loop-carried registers cost class B 8 %, so there every step fetches its own entries first.
+  constexpr bool PIPE = UNR == 8;
+  if (PIPE) fetch(0);
+  for (int s0 = 0; s0 < nseg; s0 += UNR) {
+    if (!PIPE) fetch(s0);
+    float v[UNR];
 #pragma unroll
-    for (int u = 0; u < 4; u++) v[u] = sample_seg<TS, INTERIOR>(img, w, h, c[u], a11, a21, rep[u]);
+    for (int u = 0; u < UNR; u++) v[u] = sample_seg<TS, INTERIOR>(img, w, h, c[u], a11, a21, rep[u]);
+    if (PIPE && s0 + UNR < nseg) fetch(s0 + UNR);
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
+    for (int u = 0; u < UNR; u++) {
       const int i = (s0 + u) * SEG + sub;
       if (i < R) row[i] = v[u];
     }
   }
 }
 // `fast` must be warp uniform (the caller votes over the rows of its warp at a convergent point)
-template <int TS>
+template <int TS, int UNR = 4>
 __device__ __forceinline__ void sample_row(const float* __restrict__ img, int w, int h, const float2* cs, int nseg, float a11, float a21,
                                            int sub, float* row, int R, bool fast) {
-  if (fast) sample_row_impl<TS, true>(img, w, h, cs, nseg, a11, a21, sub, row, R);
-  else sample_row_impl<TS, false>(img, w, h, cs, nseg, a11, a21, sub, row, R);
+  if (fast) sample_row_impl<TS, true, UNR>(img, w, h, cs, nseg, a11, a21, sub, row, R);
+  else sample_row_impl<TS, false, 4>(img, w, h, cs, nseg, a11, a21, sub, row, R);
 }
 
 // Row pass, vector form (x < R & ~3, ks >= 7): s = 0; s = fma(p[t], k[t], s), t = 0..ks-1, for CB adjacent
@@ -495,7 +503,6 @@ k_sample_a(const float* __restrict__ img, int w, int h, const PatchMeta* __restr
 
 // ---- class B: 66 <= R <= 160 (scale >= 2): only the 64 columns / rows the final resampling reads ----------
 constexpr int B_NB = 32;     // rows sampled + row-filtered per iteration
-constexpr int B1_TS = 8;     // coordinate table spacing of class B1 (B2: 8)
 constexpr int B_TP = 65;     // pitch of T (64 needed columns)
 __host__ __device__ inline int b_smem_floats(int R, int r, int ts) {
   const int nte = (R + ts - 1) / ts, PS = (R + 2 * r + 2) | 1;
@@ -504,7 +511,7 @@ __host__ __device__ inline int b_smem_floats(int R, int r, int ts) {
   return 64 + 64 + 64 + 160 + u + (R + 2 * r + 2) * B_TP;
 }
 
-template <int TS>
+template <int TS, int UNR>
 __global__ void __launch_bounds__(NT)
 k_sample_b(const float* __restrict__ img, int w, int h, const PatchMeta* __restrict__ metas,
            const float* __restrict__ taps_all, uint8_t* __restrict__ out, const int* __restrict__ cnt) {
@@ -541,7 +548,7 @@ k_sample_b(const float* __restrict__ img, int w, int h, const PatchMeta* __restr
       const int g = tid >> 3, sub = tid & 7;
       const bool act = g < nrows;
       const bool fast = __all_sync(0xffffffffu, act ? rowok[j0 + g] != 0 : true);
-      if (act) sample_row<TS>(img, w, h, C2 + (j0 + g) * nte, nseg, m.a11, m.a21, sub, Sb + g * PS + r, R, fast);
+      if (act) sample_row<TS, UNR>(img, w, h, C2 + (j0 + g) * nte, nseg, m.a11, m.a21, sub, Sb + g * PS + r, R, fast);
     }
     __syncthreads();
     // replicate the borders into the padding (r left, r + 2 right entries per row)
@@ -684,7 +691,7 @@ k_large_resample(const float* __restrict__ img, int w, int h, const PatchMeta* _
   const bool fast = __all_sync(0xffffffffu, act ? cs[nent - 1].x != 0.f : true);
   if (!act) return;
   float* row = scratch + m.scratch_off + large_c_floats(R) + (size_t)j * R;
-  sample_row<L_TS>(img, w, h, cs, nseg, m.a11, m.a21, sub, row, R, fast);
+  sample_row<L_TS, 8>(img, w, h, cs, nseg, m.a11, m.a21, sub, row, R, fast);      // no shared memory here: 8 segments in flight per lane
 }
 
 // phase 2a: row pass at the 2*ps needed columns for L2_ROWS rows of one region: T[y][ci].  Rows are staged in shared
@@ -714,7 +721,17 @@ k_large_rowpass(const PatchMeta* __restrict__ metas, int nreg, const int* __rest
   for (int jr = threadIdx.x >> 5; jr < nrows; jr += 8) {          // a warp per row: coalesced reads, clamped index = border replication
     const float* src = S + (size_t)(row0 + jr) * R;
     float* dst = rows + jr * PS;
-    for (int t = threadIdx.x & 31; t < R + 2 * r + 2; t += 32) dst[t] = src[clampi(t - r, 0, R - 1)];
+    // four loads in flight per lane before the first store (the plain loop was one L2 round trip per iteration: 45 % of
+    // this kernel's stall samples)
+    const int len = R + 2 * r + 2;
+    for (int t0 = threadIdx.x & 31; t0 < len; t0 += 128) {
+      float v[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) v[q] = src[clampi(min(t0 + 32 * q, len - 1) - r, 0, R - 1)];
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        if (t0 + 32 * q < len) dst[t0 + 32 * q] = v[q];
+    }
   }
   __syncthreads();
   const int xv = R & ~3;
@@ -774,12 +791,25 @@ k_large_colpass_final(const PatchMeta* __restrict__ metas, const float* __restri
     const int rl = it / nc, ci = it - rl * nc;
     const int ri = 2 * j0 + rl;
     const int y = needed_pos(P[ri >> 1], ri & 1, R), x = needed_pos(P[ci >> 1], ci & 1, R);
-    auto TY = [&](int yy) { return T[(size_t)clampi(yy, 0, R - 1) * nc + ci]; };
-    float s = TY(y) * kk[r];
-    if (x < wc) {
-      for (int t = 1; t <= r; t++) s = fmaf(TY(y - t) + TY(y + t), kk[r + t], s);
-    } else {
-      for (int t = 1; t <= r; t++) s = s + (TY(y - t) + TY(y + t)) * kk[r + t];
+    // the symmetric pairs T[y - t] + T[y + t] of 8 taps are loaded (16 L2 / L1 reads in flight) before their FMAs: the
+    // one-tap-at-a-time loop was 60 % of this kernel's stall samples
+    const float* Tc = T + ci;
+    float s = Tc[(size_t)y * nc] * kk[r];
+    const bool vec = x < wc;
+    for (int t0 = 1; t0 <= r; t0 += 8) {
+      float lo[8], hi[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const int t = min(t0 + q, r);
+        lo[q] = Tc[(size_t)max(y - t, 0) * nc];
+        hi[q] = Tc[(size_t)min(y + t, R - 1) * nc];
+      }
+#pragma unroll
+      for (int q = 0; q < 8; q++)
+        if (t0 + q <= r) {
+          if (vec) s = fmaf(lo[q] + hi[q], kk[r + t0 + q], s);
+          else s = s + (lo[q] + hi[q]) * kk[r + t0 + q];
+        }
     }
     B[rl * nc + ci] = s;
   }
@@ -816,6 +846,15 @@ constexpr int SMEM_L3 = (MAX_PS + 640 + 2 * L3_OUT_ROWS * 2 * MAX_PS) * 4;
 //   A1 R <= 40, A2 R <= 65 : k_sample_a (whole window filtered)        B1 R <= 100, B2 R <= 160 : k_sample_b
 //   odd cases (direct mode, ks < 7, patchSize != 32 for B) : k_sample_small;  R > 160 : the 3-launch slab path
 constexpr int A1_R = 40, A2_R = 65, B1_R = 100, B2_R = 160;
+static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+// class B1 keeps a coordinate table entry for every 4th sample (3 % faster than 8; 72 KB still gives 3 CTAs per SM), B2 for
+// every 8th (a finer table would drop it to one CTA per SM).  8 instead of 4 segments in flight per lane: measured slower.
+static int smp_b1_ts() { static const int v = env_int("MODSGPU_B1_TS", 4); return v == 8 ? 8 : 4; }
+template <typename... A>
+static void launch_sample_b(bool b1, unsigned grid, int smem, cudaStream_t st, A... a) {
+  if (b1 && smp_b1_ts() == 4) k_sample_b<4, 4><<<grid, NT, smem, st>>>(a...);
+  else k_sample_b<8, 4><<<grid, NT, smem, st>>>(a...);
+}
 
 int mg_sample_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_region* regs, int n,
                       double mrSize, int ps, uint8_t* d_out, float* d_outf) {
@@ -923,8 +962,8 @@ int mg_sample_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
     MG_CUDA(ctx, cudaFuncSetAttribute(k_large_rowpass, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (2 * MAX_PS + 642 + L2_ROWS * ((MAX_R + 602) | 1)) * 4));
     MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_a, cudaFuncAttributeMaxDynamicSharedMemorySize, a_smem_floats(A2_R, 30) * 4));
-    MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_b<B1_TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, b_smem_floats(B1_R, 30, B1_TS) * 4));
-    MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_b<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, b_smem_floats(B2_R, 30, 8) * 4));
+    MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_b<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, b_smem_floats(B1_R, 30, 4) * 4));
+    MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_b<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, b_smem_floats(B2_R, 30, 8) * 4));
     attr_set.set(ctx->device);
   }
   // algorithmic bytes: R*R*4 read + ps*ps written per region
@@ -948,10 +987,9 @@ int mg_sample_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
   }
   for (int c = C_B1; c <= C_B2; c++) {
     if (cls[c].empty()) continue;
-    const int smem = b_smem_floats(std::min(b_maxR[c - C_B1], cls[c][0].R), cls_r[c], c == C_B1 ? B1_TS : 8) * 4;
+    const int smem = b_smem_floats(std::min(b_maxR[c - C_B1], cls[c][0].R), cls_r[c], c == C_B1 ? smp_b1_ts() : 8) * 4;
     MG_PROF(ctx, c == C_B1 ? "k_sample_b<R<=100>" : "k_sample_b<R<=160>", 0, alg_bytes(cls[c]));
-    if (c == C_B1) k_sample_b<B1_TS><<<(unsigned)cls[c].size(), NT, smem, ctx->stream>>>(img->d, img->w, img->h, dm + cls_off[c], dtaps, d_out, nullptr);
-    else k_sample_b<8><<<(unsigned)cls[c].size(), NT, smem, ctx->stream>>>(img->d, img->w, img->h, dm + cls_off[c], dtaps, d_out, nullptr);
+    launch_sample_b(c == C_B1, (unsigned)cls[c].size(), smem, ctx->stream, (const float*)img->d, img->w, img->h, dm + cls_off[c], dtaps, d_out, (const int*)nullptr);
     MG_LAUNCHED(ctx);
   }
   if (nl > 0) {
@@ -1283,8 +1321,8 @@ int mg_sample_enqueue_dev(modsgpu_ctx* ctx, const modsgpu_image* img, const DevR
     MG_CUDA(ctx, cudaFuncSetAttribute(k_large_rowpass, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (2 * MAX_PS + 642 + L2_ROWS * ((MAX_R + 602) | 1)) * 4));
     MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_a, cudaFuncAttributeMaxDynamicSharedMemorySize, a_smem_floats(A2_R, 30) * 4));
-    MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_b<B1_TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, b_smem_floats(B1_R, 30, B1_TS) * 4));
-    MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_b<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, b_smem_floats(B2_R, 30, 8) * 4));
+    MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_b<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, b_smem_floats(B1_R, 30, 4) * 4));
+    MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_b<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, b_smem_floats(B2_R, 30, 8) * 4));
     attr_set.set(ctx->device);
   }
   // the algorithmic bytes of these launches are only known on the device: k_smp_scatter accumulates them per class and
@@ -1307,10 +1345,9 @@ int mg_sample_enqueue_dev(modsgpu_ctx* ctx, const modsgpu_image* img, const DevR
   }
   for (int c = SC_B1; c <= SC_B2; c++) {
     if (st.cls_cnt[c] <= 0) continue;
-    const int smem = b_smem_floats(std::min(b_maxR[c - SC_B1], st.cls_rmax[c]), st.cls_kr[c], c == SC_B1 ? B1_TS : 8) * 4;
+    const int smem = b_smem_floats(std::min(b_maxR[c - SC_B1], st.cls_rmax[c]), st.cls_kr[c], c == SC_B1 ? smp_b1_ts() : 8) * 4;
     MG_PROF(ctx, c == SC_B1 ? "k_sample_b<R<=100>" : "k_sample_b<R<=160>", 0, alg_bytes(c));
-    if (c == SC_B1) k_sample_b<B1_TS><<<(unsigned)st.cls_cnt[c], NT, smem, ctx->stream>>>(img->d, img->w, img->h, dm + lay.cls_off[c], dtaps, d_out, dcnt + c);
-    else k_sample_b<8><<<(unsigned)st.cls_cnt[c], NT, smem, ctx->stream>>>(img->d, img->w, img->h, dm + lay.cls_off[c], dtaps, d_out, dcnt + c);
+    launch_sample_b(c == SC_B1, (unsigned)st.cls_cnt[c], smem, ctx->stream, (const float*)img->d, img->w, img->h, (const PatchMeta*)(dm + lay.cls_off[c]), dtaps, d_out, (const int*)(dcnt + c));
     MG_LAUNCHED(ctx);
   }
   if (nl > 0) {

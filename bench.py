@@ -200,7 +200,32 @@ ALG = {  # kernels whose algorithmic work the library reports in bytes (kind 0) 
     0: ("hbm", "GB/s", 1e9), 1: ("tensor", "TFLOP/s", 1e12)}
 
 
+def pin_to_gpu_numa_node(local_rank):
+    """Keep this rank's threads (and the pinned buffers they first touch) on the NUMA node its GPU hangs off: on the
+    2-socket 8-GPU box unpinned ranks pay cross-socket hops on every driver call.  Silently does nothing when the node is
+    unknown (single-socket boxes report -1)."""
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        bdf = out[-12:] if len(out) >= 12 else out          # 00000000:1B:00.0 -> 0000:1b:00.0
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"numa_node": node, "cpus": len(cpus)}
+    except (OSError, ValueError, subprocess.SubprocessError):
+        pass
+    return None
+
+
 def run_gpu(args, rank, world, local_rank):
+    numa = pin_to_gpu_numa_node(local_rank) if world > 1 and not os.environ.get("MODSGPU_NO_NUMA_PIN") else None
     import torch
     import mods_light_zmq_b200 as M
     dist = None
@@ -242,6 +267,7 @@ def run_gpu(args, rank, world, local_rank):
     results = np.zeros((n_pairs, 16 + 4 * CAPACITY), np.float64)
     last = {}
     host_cpu = {"ms": 0.0}
+    rank_ms = {"last": []}
 
     # k = pair index inside the arm (step = k // PAIRS_PER_STEP); store=False for warm-up / rehearsal passes, whose
     # pair count is independent of --steps
@@ -311,10 +337,13 @@ def run_gpu(args, rank, world, local_rank):
         dev_ms = float(ms.value)
         if os.environ.get("MODSGPU_BENCH_DEBUG"):
             print("[rank %d] %s: dev %.1f ms wall %.1f ms for %d steps" % (rank, fn.__name__, dev_ms, wall_ms, steps), file=sys.stderr, flush=True)
+        rank_ms["last"] = [dev_ms]
         if dist is not None:
             t = torch.tensor([dev_ms, wall_ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dev_ms, wall_ms = float(t[0]), float(t[1])
+            allt = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(allt, t)
+            rank_ms["last"] = [float(x[0]) for x in allt]            # per-rank device time of this arm (max = the reported one)
+            dev_ms, wall_ms = max(float(x[0]) for x in allt), max(float(x[1]) for x in allt)
         return dev_ms, wall_ms
 
     # ---- warm-up (every worker), then the timed arms
@@ -336,6 +365,7 @@ def run_gpu(args, rank, world, local_rank):
     timed(step_value, 4 * nwk, store=False)
     launches0 = sum(mg.launch_count for mg in mgs)
     dev_ms, wall_ms = timed(step_value, n_pairs)
+    value_rank_ms = list(rank_ms["last"])
     host_cpu_ms_per_pair = host_cpu["ms"] / n_pairs
     launches = sum(mg.launch_count for mg in mgs) - launches0
     e2e_ms, e2e_wall = timed(step_e2e, n_pairs)
@@ -358,6 +388,25 @@ def run_gpu(args, rank, world, local_rank):
             dist.barrier()
             dist.destroy_process_group()
         return
+    # ---- one pair alone on the GPU (what a single `mods` process sees): wall clock per pair through the host-facing call on
+    # ONE context, the two images one after the other and side by side (modsgpu_set_pair_overlap, mods.cpp:234-251)
+    single = None
+    if rank == 0:
+        for m in mgs[1:]:            # only one context stays alive: its host waits spin, as in a single-pair process
+            m.close()
+        mgs = mgs[:1]
+        single = {}
+        pa, pb = host[0]
+        for name, on in (("sequential_ms", False), ("overlapped_ms", True)):
+            mgs[0].set_pair_overlap(on)
+            for _ in range(3):
+                mgs[0].pair_pipeline(pa.numpy(), pb.numpy(), seed=1, capacity=CAPACITY)
+            t0 = time.perf_counter()
+            for k in range(8):
+                mgs[0].pair_pipeline(pa.numpy(), pb.numpy(), seed=1000 + k, capacity=CAPACITY)
+            single[name] = (time.perf_counter() - t0) * 1e3 / 8
+        mgs[0].set_pair_overlap(False)
+        single["note"] = "host BGR in, verified correspondences out, one context, 8 pairs back to back, wall clock"
     lastr = last.get("r")
     value = world * n_pairs / (dev_ms * 1e-3)
     e2e_value = world * n_pairs / (e2e_ms * 1e-3)
@@ -468,6 +517,7 @@ def run_gpu(args, rank, world, local_rank):
                             "correspondences + H out per pair)"},
             "gpu_launches": launches, "wall_ms_per_step": wall_ms / args.steps,
             "host_cpu_ms_per_pair": host_cpu_ms_per_pair, "host_cores": os.cpu_count(),
+            "rank_ms": value_rank_ms, "numa_pin": numa, "single_pair": single,
             "roofline": roofline, "stages": stages, "kernels": kernels, "clocks": clk}
     if cpu:
         line["cpu_baseline"] = cpu

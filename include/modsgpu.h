@@ -325,6 +325,16 @@ void modsgpu_default_pipeline_params(modsgpu_pipeline_params* p);
 int  modsgpu_pair_pipeline_images_ex(modsgpu_ctx* ctx, modsgpu_image* img1, modsgpu_image* img2, const modsgpu_pipeline_params* p,
                                      modsgpu_pair_result* res, double* inlier_xy, int capacity);
 
+/* The two images of a pair side by side, as the reference's OpenMP tasks do (mods.cpp:234-251): with pair overlap on, the
+ * pair-level entry points (modsgpu_pair_pipeline*) extract image 2 on a sibling context (same device, own stream and
+ * workspaces, shared nets; created on first use, destroyed with ctx) from a helper thread while the calling thread
+ * extracts image 1.  Results are identical.  Off by default (MODSGPU_PAIR_OVERLAP=1 turns it on for every new context):
+ * it shortens ONE pair (7.2 -> ~5 ms); a process that already keeps the GPU full with many contexts gains nothing. */
+int  modsgpu_set_pair_overlap(modsgpu_ctx* ctx, int on);
+int  modsgpu_get_pair_overlap(const modsgpu_ctx* ctx);
+int  modsgpu_ctx_sibling(modsgpu_ctx* ctx, modsgpu_ctx** sibling);   /* borrowed: never destroy it yourself */
+int  modsgpu_ctx_sibling_join(modsgpu_ctx* ctx);                      /* fold the sibling's launch count / error into ctx */
+
 /* ---- one image -> described regions (what extract_features_batch.cpp:128-139 does per image for the deep
  *      configuration: ImageRepresentation::SynthDetectDescribeKeypoints, identity view) and the OxAff writer
  *      (ImageRepresentation::SaveRegionsMichal text mode -> saveAR_KM_format, imagerepresentation.cpp:113-126,

@@ -599,6 +599,12 @@ def _pair_pipeline(self, bgr1, bgr2, seed=12345, capacity=4096):
     return _pair_dict(res, xy)
 
 
+def _set_pair_overlap(self, on=True):
+    """modsgpu_set_pair_overlap: the two images of a pair side by side (image 2 on a sibling context), mods.cpp:234-251"""
+    self._check(self.lib.modsgpu_set_pair_overlap(self.ctx, 1 if on else 0))
+
+
+ModsGpu.set_pair_overlap = _set_pair_overlap
 ModsGpu.pair_pipeline_images = _pair_pipeline_images
 ModsGpu.pair_pipeline_classic_images = _pair_pipeline_classic_images
 ModsGpu.pair_pipeline_images_ex = _pair_pipeline_images_ex

@@ -37,16 +37,70 @@ extern "C" int modsgpu_create(int device, modsgpu_ctx** out) {
     delete ctx;
     return MODSGPU_ECUDA;
   }
+  {
+    const char* e = getenv("MODSGPU_PAIR_OVERLAP");
+    ctx->pair_overlap = e ? atoi(e) : 0;
+  }
   mg_live_contexts.fetch_add(1);
   *out = ctx;
   return 0;
 }
 
+// ---- two images of a pair side by side ----------------------------------------------------------------------------
+// The reference extracts the two images of a pair concurrently (OpenMP tasks, mods.cpp:234-251).  One context is one
+// stream and one set of workspaces, so the pair-level entry points can borrow a SIBLING context for the second image:
+// same device, own stream / workspaces / detector graphs, the nets shared.  Off by default (with many contexts per GPU
+// the device is already full and the sibling only costs memory); MODSGPU_PAIR_OVERLAP=1 or modsgpu_set_pair_overlap.
+extern "C" int modsgpu_set_pair_overlap(modsgpu_ctx* ctx, int on) {
+  if (!ctx) return MODSGPU_EINVAL;
+  ctx->pair_overlap = on ? 1 : 0;
+  return 0;
+}
+extern "C" int modsgpu_get_pair_overlap(const modsgpu_ctx* ctx) { return ctx ? ctx->pair_overlap : 0; }
+
+// The sibling (created on first use, owned by ctx).  Its stream is ordered after everything enqueued on ctx's stream so
+// far -- images converted on ctx's stream may be read by the sibling straight away.
+extern "C" int modsgpu_ctx_sibling(modsgpu_ctx* ctx, modsgpu_ctx** out) {
+  if (!ctx || !out) return MODSGPU_EINVAL;
+  *out = nullptr;
+  if (ctx->nets_borrowed) MG_FAIL(ctx, MODSGPU_ESTATE, "a sibling context has no sibling of its own");
+  if (!ctx->sibling) {
+    modsgpu_ctx* sib = nullptr;
+    const int rc = modsgpu_create(ctx->device, &sib);
+    if (rc) MG_FAIL(ctx, rc, "sibling context could not be created");
+    sib->nets_borrowed = true;
+    sib->pair_overlap = 0;
+    ctx->sibling = sib;
+    MG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->sib_ev, cudaEventDisableTiming));
+  }
+  for (int i = 0; i < 3; i++) ctx->sibling->nets[i] = ctx->nets[i];
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  MG_CUDA(ctx, cudaEventRecord(ctx->sib_ev, ctx->stream));
+  MG_CUDA(ctx, cudaStreamWaitEvent(ctx->sibling->stream, ctx->sib_ev, 0));
+  *out = ctx->sibling;
+  return 0;
+}
+// after the sibling's work has been collected: its launches count as ctx's, its error (if any) becomes ctx's
+extern "C" int modsgpu_ctx_sibling_join(modsgpu_ctx* ctx) {
+  if (!ctx || !ctx->sibling) return MODSGPU_EINVAL;
+  ctx->launches += ctx->sibling->launches;
+  ctx->sibling->launches = 0;
+  if (!ctx->sibling->err.empty()) { ctx->err = ctx->sibling->err; ctx->sibling->err.clear(); }
+  return 0;
+}
+
 extern "C" void modsgpu_destroy(modsgpu_ctx* ctx) {
   if (!ctx) return;
+  if (ctx->sibling) {
+    for (int i = 0; i < 3; i++) ctx->sibling->nets[i] = nullptr;
+    modsgpu_destroy(ctx->sibling);
+    ctx->sibling = nullptr;
+  }
   mg_live_contexts.fetch_sub(1);
   cudaSetDevice(ctx->device);
   mg_stream_sync(ctx);
+  if (ctx->sib_ev) cudaEventDestroy(ctx->sib_ev);
+  if (ctx->nets_borrowed) for (int i = 0; i < 3; i++) ctx->nets[i] = nullptr;
   mg_free_nets(ctx);
   DevBuf* bufs[] = {&ctx->det_pyr, &ctx->det_cand, &ctx->det_map, &ctx->det_out, &ctx->det_misc, &ctx->det_aff, &ctx->io_a, &ctx->io_b,
                     &ctx->io_c, &ctx->smp_regs, &ctx->smp_meta, &ctx->smp_taps, &ctx->smp_scratch, &ctx->smp_out,

@@ -114,6 +114,12 @@ struct modsgpu_ctx {
   DevBuf mt_q, mt_t, mt_d, mt_aux, mt_out;
   DevBuf rs_buf;
   NetWeights* nets[3] = {nullptr, nullptr, nullptr};
+  // second context of the same device for the second image of a pair (modsgpu_ctx_sibling): own stream and workspaces, the
+  // nets are BORROWED from this context (nets_borrowed: never freed by the sibling)
+  modsgpu_ctx* sibling = nullptr;
+  cudaEvent_t sib_ev = nullptr;
+  bool nets_borrowed = false;
+  int pair_overlap = 0;
   Profiler prof;
   cudaEvent_t tm0 = nullptr, tm1 = nullptr;   // modsgpu_timer_*
   DevBuf l2flush;

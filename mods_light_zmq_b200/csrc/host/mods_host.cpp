@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstring>
 #include <fstream>
+#include <thread>
 
 namespace modsb200 {
 
@@ -1110,12 +1111,30 @@ extern "C" int modsgpu_pair_pipeline_images_ex(modsgpu_ctx* ctx, modsgpu_image* 
   double c[6] = {0, 0, 0, 0, 0, 0}, w[6] = {0, 0, 0, 0, 0, 0};
   auto mark = [&](int i) { if (hp) { c[i] = cpu_ms(); w[i] = now_ms(); } };
   mark(0);
-  ImageRepresentation r1(ctx, img1, false), r2(ctx, img2, false);
-  int n1 = r1.SynthDetectDescribeKeypoints(dp);
-  if (n1 < 0) return n1;
-  mark(1);
-  int n2 = r2.SynthDetectDescribeKeypoints(dp);
-  if (n2 < 0) return n2;
+  // mods.cpp:234-251 extracts the two images as concurrent OpenMP tasks; with pair overlap on, image 2 runs on the
+  // sibling context from a helper thread
+  modsgpu_ctx* sib = nullptr;
+  if (modsgpu_get_pair_overlap(ctx) && !hp) {
+    int rc = modsgpu_ctx_sibling(ctx, &sib);
+    if (rc) return rc;
+  }
+  ImageRepresentation r1(ctx, img1, false), r2(sib ? sib : ctx, img2, false);
+  int n1, n2;
+  if (sib) {
+    n2 = 0;
+    std::thread t2([&] { n2 = r2.SynthDetectDescribeKeypoints(dp); });
+    n1 = r1.SynthDetectDescribeKeypoints(dp);
+    t2.join();
+    modsgpu_ctx_sibling_join(ctx);
+    if (n1 < 0) return n1;
+    if (n2 < 0) return n2;
+  } else {
+    n1 = r1.SynthDetectDescribeKeypoints(dp);
+    if (n1 < 0) return n1;
+    mark(1);
+    n2 = r2.SynthDetectDescribeKeypoints(dp);
+    if (n2 < 0) return n2;
+  }
   mark(2);
   res->keypoints[0] = r1.n_keypoints; res->keypoints[1] = r2.n_keypoints;
   res->regions[0] = r1.n_affine; res->regions[1] = r2.n_affine;

@@ -252,59 +252,105 @@ k_dup_filter(const double* __restrict__ xy1, const double* __restrict__ xy2, con
 // positions a < b, (3) one warp walks the rows that have conflicts in order and clears the later bits.
 // Identical result to the sequential greedy loop: a correspondence dies iff an earlier SURVIVOR conflicts.
 constexpr int DUP_MAX_T = 16384;
-__global__ void k_dup_rank(const double* __restrict__ ratio, int T, int* __restrict__ ord) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= T) return;
-  const double me = fabs(ratio[i]);
+// (1) rank of every correspondence in the order (|ratio| ascending, index ascending) and the coordinates in that order.
+// 64 correspondences per CTA, four lanes each, the keys staged through shared memory in tiles of 256 (one thread per
+// correspondence walking all T keys in global memory was 87 us for T = 3000: a chain of dependent loads).
+__global__ void __launch_bounds__(256)
+k_dup_rank(const double* __restrict__ ratio, const double* __restrict__ xy1, const double* __restrict__ xy2, int T,
+           int* __restrict__ ord, double* __restrict__ sxy) {
+  __shared__ double tile[256];
+  const int i = blockIdx.x * 64 + (threadIdx.x >> 2), q = threadIdx.x & 3;
+  const double me = i < T ? fabs(ratio[i]) : 0.0;
   int rank = 0;
-  for (int j = 0; j < T; j++) { double o = fabs(ratio[j]); rank += (o < me) || (o == me && j < i); }
-  ord[rank] = i;
+  for (int base = 0; base < T; base += 256) {
+    const int j = base + threadIdx.x;
+    tile[threadIdx.x] = j < T ? fabs(ratio[j]) : 0.0;
+    __syncthreads();
+    const int n = min(256, T - base);
+#pragma unroll 16
+    for (int t = 0; t < 64; t++) {
+      const int idx = 4 * t + q;
+      const double o = tile[idx];
+      rank += (idx < n) && ((o < me) || (o == me && base + idx < i));
+    }
+    __syncthreads();
+  }
+  rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+  rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+  if (q == 0 && i < T) {
+    ord[rank] = i;
+    sxy[4 * (size_t)rank + 0] = xy1[2 * i]; sxy[4 * (size_t)rank + 1] = xy1[2 * i + 1];
+    sxy[4 * (size_t)rank + 2] = xy2[2 * i]; sxy[4 * (size_t)rank + 3] = xy2[2 * i + 1];
+  }
 }
-__global__ void k_dup_conflicts(const double* __restrict__ xy1, const double* __restrict__ xy2, const int* __restrict__ ord,
-                                int T, int nwords, double r_sq, unsigned* __restrict__ conf, int* __restrict__ rowflag) {
-  const int a = blockIdx.y, wi = blockIdx.x * blockDim.x + threadIdx.x;
-  if (wi >= nwords) return;
-  unsigned bits = 0;
-  if (wi * 32 + 31 > a) {
-    const int ia = ord[a];
-    const double ax1 = xy1[2 * ia], ay1 = xy1[2 * ia + 1], ax2 = xy2[2 * ia], ay2 = xy2[2 * ia + 1];
-    for (int k = 0; k < 32; k++) {
-      const int b = wi * 32 + k;
-      if (b <= a || b >= T) continue;
-      const int ib = ord[b];
-      double dx = ax1 - xy1[2 * ib], dy = ay1 - xy1[2 * ib + 1];
-      if (dx * dx + dy * dy > r_sq) continue;
-      dx = ax2 - xy2[2 * ib]; dy = ay2 - xy2[2 * ib + 1];
-      if (dx * dx + dy * dy <= r_sq) bits |= 1u << k;
+// (2) conflict bit matrix between sorted positions a < b: a warp forms one 32-bit word with a ballot (lane = b), reading
+// the sorted coordinates coalesced.  Only the words a row's walk reads (w >= a / 32) are written.
+__global__ void __launch_bounds__(256)
+k_dup_conflicts(const double* __restrict__ sxy, int T, int nwords, double r_sq, unsigned* __restrict__ conf, int* __restrict__ rowflag) {
+  const int a = blockIdx.y, wi = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (wi >= nwords || wi < (a >> 5)) return;
+  const int b = wi * 32 + lane;
+  bool hit = false;
+  if (b > a && b < T) {
+    const double ax1 = sxy[4 * (size_t)a], ay1 = sxy[4 * (size_t)a + 1], ax2 = sxy[4 * (size_t)a + 2], ay2 = sxy[4 * (size_t)a + 3];
+    double dx = ax1 - sxy[4 * (size_t)b], dy = ay1 - sxy[4 * (size_t)b + 1];
+    if (!(dx * dx + dy * dy > r_sq)) {
+      dx = ax2 - sxy[4 * (size_t)b + 2]; dy = ay2 - sxy[4 * (size_t)b + 3];
+      hit = dx * dx + dy * dy <= r_sq;
     }
   }
-  conf[(size_t)a * nwords + wi] = bits;
-  if (bits) rowflag[a] = 1;
+  const unsigned bits = __ballot_sync(0xffffffffu, hit);
+  if (lane == 0) {
+    conf[(size_t)a * nwords + wi] = bits;
+    if (bits) rowflag[a] = 1;
+  }
 }
+// (3) one warp walks the rows that have conflicts in order and clears the later bits; a row acts only while it is still
+// alive.  The rows it will need are copied into shared memory by the whole CTA first (as many as fit), so the walk is
+// not one L2 round trip per flagged row.
 __global__ void __launch_bounds__(256)
 k_dup_resolve(const unsigned* __restrict__ conf, const int* __restrict__ rowflag, const int* __restrict__ ord, int T,
-              int nwords, int* __restrict__ out, int* __restrict__ nout) {
+              int nwords, int cap_rows, int* __restrict__ out, int* __restrict__ nout) {
+  extern __shared__ unsigned rows_s[];                 // cap_rows x nwords
   __shared__ unsigned alive[DUP_MAX_T / 32];
   __shared__ unsigned flagged[DUP_MAX_T / 32];
-  // rows that have any conflict, as a bit mask (coalesced pass over rowflag by the whole CTA)
-  for (int w = threadIdx.x; w < nwords; w += blockDim.x) {
-    unsigned f = 0;
-    for (int k = 0; k < 32; k++) { const int a = w * 32 + k; if (a < T && rowflag[a]) f |= 1u << k; }
-    flagged[w] = f;
-    alive[w] = 0xffffffffu;
+  __shared__ unsigned short slot_base[DUP_MAX_T / 32];    // staged rows before word w
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int w = warp; w < nwords; w += 8) {
+    const int a = w * 32 + lane;
+    const unsigned f = __ballot_sync(0xffffffffu, a < T && rowflag[a] != 0);
+    if (lane == 0) { flagged[w] = f; alive[w] = 0xffffffffu; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int w = 0; w < nwords; w++) { slot_base[w] = (unsigned short)min(n, 65535); n += __popc(flagged[w]); }
+  }
+  __syncthreads();
+  for (int w = warp; w < nwords; w += 8) {             // stage the flagged rows (a warp per word of the flag mask)
+    unsigned m = flagged[w];
+    int k = slot_base[w];
+    while (m) {
+      const int bit = __ffs(m) - 1;
+      m &= m - 1;
+      if (k >= cap_rows) break;
+      const unsigned* row = conf + (size_t)(w * 32 + bit) * nwords;
+      for (int x = w + lane; x < nwords; x += 32) rows_s[(size_t)k * nwords + x] = row[x];
+      k++;
+    }
   }
   __syncthreads();
   if (threadIdx.x >= 32) return;
-  const int lane = threadIdx.x;
-  // one warp walks the flagged rows in order; a row acts only while it is still alive
   for (int wa = 0; wa < nwords; wa++) {
     unsigned m = flagged[wa];
+    int k = slot_base[wa];
     while (m) {
       const int bit = __ffs(m) - 1;
       m &= m - 1;
       const int a = wa * 32 + bit;
+      const unsigned* row = k < cap_rows ? rows_s + (size_t)k * nwords : conf + (size_t)a * nwords;
+      k++;
       if (!((alive[wa] >> bit) & 1u)) continue;
-      const unsigned* row = conf + (size_t)a * nwords;
       for (int w = wa + lane; w < nwords; w += 32) alive[w] &= ~row[w];
       __syncwarp();
     }
@@ -517,18 +563,27 @@ extern "C" int modsgpu_duplicate_filter(modsgpu_ctx* ctx, const double* xy1, con
   MG_CUDA(ctx, cudaMemcpyAsync(dr, ratio, rb, cudaMemcpyHostToDevice, ctx->stream));
   if (T <= DUP_MAX_T) {
     const int nwords = (T + 31) / 32;
-    MG_CUDA(ctx, ctx->mt_d.ensure((size_t)T * nwords * 4 + (size_t)T * 4 + 16));
+    MG_CUDA(ctx, ctx->mt_d.ensure((size_t)T * nwords * 4 + (size_t)T * 4 + 16 + (size_t)T * 32));
     unsigned* conf = ctx->mt_d.as<unsigned>();
     int* rowflag = reinterpret_cast<int*>(conf + (size_t)T * nwords);
+    double* sxy = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(ctx->mt_d.p) + (((size_t)T * nwords * 4 + (size_t)T * 4 + 15) & ~(size_t)15));
     MG_CUDA(ctx, cudaMemsetAsync(rowflag, 0, (size_t)T * 4, ctx->stream));
     MG_PROF(ctx, "k_dup_rank", 2, (double)T);
-    k_dup_rank<<<(T + 127) / 128, 128, 0, ctx->stream>>>(dr, T, dord);
+    k_dup_rank<<<(T + 63) / 64, 256, 0, ctx->stream>>>(dr, d1, d2, T, dord, sxy);
     MG_LAUNCHED(ctx);
     MG_PROF(ctx, "k_dup_conflicts", 2, (double)T);
-    k_dup_conflicts<<<dim3((nwords + 63) / 64, T), 64, 0, ctx->stream>>>(d1, d2, dord, T, nwords, r * r, conf, rowflag);
+    k_dup_conflicts<<<dim3((nwords + 7) / 8, T), 256, 0, ctx->stream>>>(sxy, T, nwords, r * r, conf, rowflag);
     MG_LAUNCHED(ctx);
+    // rows of the conflict matrix staged in shared memory: as many as 160 KB hold
+    constexpr int RESOLVE_SMEM = 160 * 1024;
+    static OnceFlags attr_set;
+    if (attr_set.need(ctx->device)) {
+      MG_CUDA(ctx, cudaFuncSetAttribute(k_dup_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, RESOLVE_SMEM));
+      attr_set.set(ctx->device);
+    }
+    const int cap_rows = std::min(T, RESOLVE_SMEM / (nwords * 4));
     MG_PROF(ctx, "k_dup_resolve", 2, (double)T);
-    k_dup_resolve<<<1, 256, 0, ctx->stream>>>(conf, rowflag, dord, T, nwords, dout, ctx->mt_aux.as<int>() + 4);
+    k_dup_resolve<<<1, 256, (size_t)cap_rows * nwords * 4, ctx->stream>>>(conf, rowflag, dord, T, nwords, cap_rows, dout, ctx->mt_aux.as<int>() + 4);
     MG_LAUNCHED(ctx);
   } else {
     MG_PROF(ctx, "k_dup_filter", 2, (double)T);

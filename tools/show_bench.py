@@ -12,5 +12,5 @@ for k, v in d["kernels"].items():
     tot += v.get("ms_per_pair", v.get("ms_per_step"))
 print("sum kernel ms/step %.2f" % tot)
 print("stages", {k: (round(v["ms_per_pair"], 3) if isinstance(v, dict) else round(v, 3)) for k, v in d.get("stages", {}).items()})
-print("host_cpu_ms_per_pair", d.get("host_cpu_ms_per_pair"))
+print("host_cpu_ms_per_pair", d.get("host_cpu_ms_per_pair"), "single_pair", d.get("single_pair"))
 print("roofline", {k: d["roofline"][k] for k in ("kernel", "achieved", "frac", "avg_us")})

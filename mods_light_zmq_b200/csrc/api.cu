@@ -73,8 +73,8 @@ extern "C" int modsgpu_ctx_sibling(modsgpu_ctx* ctx, modsgpu_ctx** out) {
     ctx->sibling = sib;
     MG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->sib_ev, cudaEventDisableTiming));
   }
-  for (int i = 0; i < 3; i++) ctx->sibling->nets[i] = ctx->nets[i];
   MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (int rc = mg_nets_share(ctx->sibling, ctx)) MG_FAIL(ctx, rc, ctx->sibling->err);
   MG_CUDA(ctx, cudaEventRecord(ctx->sib_ev, ctx->stream));
   MG_CUDA(ctx, cudaStreamWaitEvent(ctx->sibling->stream, ctx->sib_ev, 0));
   *out = ctx->sibling;
@@ -92,15 +92,13 @@ extern "C" int modsgpu_ctx_sibling_join(modsgpu_ctx* ctx) {
 extern "C" void modsgpu_destroy(modsgpu_ctx* ctx) {
   if (!ctx) return;
   if (ctx->sibling) {
-    for (int i = 0; i < 3; i++) ctx->sibling->nets[i] = nullptr;
-    modsgpu_destroy(ctx->sibling);
+    modsgpu_destroy(ctx->sibling);      // frees its activation buffers only (the weights are ctx's)
     ctx->sibling = nullptr;
   }
   mg_live_contexts.fetch_sub(1);
   cudaSetDevice(ctx->device);
   mg_stream_sync(ctx);
   if (ctx->sib_ev) cudaEventDestroy(ctx->sib_ev);
-  if (ctx->nets_borrowed) for (int i = 0; i < 3; i++) ctx->nets[i] = nullptr;
   mg_free_nets(ctx);
   DevBuf* bufs[] = {&ctx->det_pyr, &ctx->det_cand, &ctx->det_map, &ctx->det_out, &ctx->det_misc, &ctx->det_aff, &ctx->io_a, &ctx->io_b,
                     &ctx->io_c, &ctx->smp_regs, &ctx->smp_meta, &ctx->smp_taps, &ctx->smp_scratch, &ctx->smp_out,

@@ -50,6 +50,7 @@ struct NetWeights {
   bool fused12 = false;          // conv1 weights resident in c_conv1[net] on this device -> k_conv12 path
   __half* act[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t slots[6] = {0, 0, 0, 0, 0, 0};
+  const NetWeights* origin = nullptr;   // clone of a sibling context: the weights belong to *origin, only act[] is owned
 };
 
 namespace {
@@ -1613,11 +1614,41 @@ int launch_conv12(modsgpu_ctx* ctx, const uint8_t* patches, const ConvW& w2, __h
 
 static void free_net(NetWeights* nw) {
   if (!nw) return;
-  cudaFree(nw->c1_w); cudaFree(nw->c1_b); cudaFree(nw->c1_split);
-  for (auto& c : nw->conv) { cudaFree(c.w); cudaFree(c.b); }
-  cudaFree(nw->head_w16); cudaFree(nw->head_w32); cudaFree(nw->head_b);
+  if (!nw->origin) {
+    cudaFree(nw->c1_w); cudaFree(nw->c1_b); cudaFree(nw->c1_split);
+    for (auto& c : nw->conv) { cudaFree(c.w); cudaFree(c.b); }
+    cudaFree(nw->head_w16); cudaFree(nw->head_w32); cudaFree(nw->head_b);
+  }
   for (auto a : nw->act) cudaFree(a);
   delete nw;
+}
+
+// The nets of a sibling context (modsgpu_ctx_sibling): the weights of `src` shared, the activation buffers its own --
+// the two contexts run their forward passes at the same time.
+int mg_nets_share(modsgpu_ctx* sib, const modsgpu_ctx* src) {
+  for (int i = 0; i < 3; i++) {
+    const NetWeights* o = src->nets[i];
+    NetWeights* c = sib->nets[i];
+    if (c && c->origin == o && o && c->c1_w == o->c1_w) continue;      // still the clone of the loaded weights
+    if (c) { free_net(c); sib->nets[i] = nullptr; }
+    if (!o) continue;
+    c = new NetWeights(*o);
+    c->origin = o;
+    for (int k = 0; k < 6; k++) {
+      c->act[k] = nullptr;
+      if (!o->act[k]) continue;
+      const int C1 = o->C1;
+      const int planes[6] = {C1 / 8, 4 * C1 / 8, 2 * C1 / 8, 4 * 2 * C1 / 8, 4 * C1 / 8, 4 * C1 / 8};
+      const size_t bytes = o->slots[k] * planes[k] * 16;
+      if (cudaMalloc((void**)&c->act[k], bytes) != cudaSuccess || cudaMemset(c->act[k], 0, bytes) != cudaSuccess) {
+        free_net(c);
+        sib->err = "sibling context: activation buffers could not be allocated";
+        return MODSGPU_ECUDA;
+      }
+    }
+    sib->nets[i] = c;
+  }
+  return 0;
 }
 
 void mg_free_nets(modsgpu_ctx* ctx) {

@@ -115,7 +115,7 @@ struct modsgpu_ctx {
   DevBuf rs_buf;
   NetWeights* nets[3] = {nullptr, nullptr, nullptr};
   // second context of the same device for the second image of a pair (modsgpu_ctx_sibling): own stream and workspaces, the
-  // nets are BORROWED from this context (nets_borrowed: never freed by the sibling)
+  // weights of the nets shared with this context (mg_nets_share: the sibling owns only its activation buffers)
   modsgpu_ctx* sibling = nullptr;
   cudaEvent_t sib_ev = nullptr;
   bool nets_borrowed = false;
@@ -128,6 +128,7 @@ struct modsgpu_ctx {
 
 cudaError_t mg_image_alloc(modsgpu_ctx* ctx, size_t bytes, float** out);
 
+int mg_nets_share(modsgpu_ctx* sib, const modsgpu_ctx* src);      // cnn.cu
 void mg_prof_begin(modsgpu_ctx* ctx, const char* name, int kind, double work, double bytes = 0.0);
 void mg_prof_end(modsgpu_ctx* ctx);
 // call right before a kernel launch; MG_LAUNCHED closes the record

@@ -171,15 +171,18 @@ def test_pair_overlap_equals_sequential(mg):
     """modsgpu_set_pair_overlap: image 2 extracted on the sibling context from a helper thread (mods.cpp:234-251 runs the
     two images as concurrent OpenMP tasks) -- counts, H and the verified correspondences equal the one-stream run's."""
     from mods_light_zmq_b200 import synth
-    a, b, _ = synth.image_pair(seed=77, w=640, h=480)
-    A, B = synth.gray_to_bgr(a), synth.gray_to_bgr(b)
-    ref = mg.pair_pipeline(A, B, seed=9)
+    pairs = []
+    for seed, (w, h) in ((77, (640, 480)), (78, (1024, 768))):
+        a, b, _ = synth.image_pair(seed=seed, w=w, h=h)
+        A, B = synth.gray_to_bgr(a), synth.gray_to_bgr(b)
+        pairs.append((A, B, mg.pair_pipeline(A, B, seed=9)))
     mg.set_pair_overlap(True)
     try:
-        for _ in range(2):      # second call: the sibling exists and its detector graph is captured
+        for it in range(6):     # from the second call on the sibling exists and its detector graph is captured
+            A, B, ref = pairs[it % 2]
             got = mg.pair_pipeline(A, B, seed=9)
             for k in ("keypoints", "regions", "descriptors", "tentatives", "unique_tentatives", "inliers"):
-                assert got[k] == ref[k], k
-            assert np.array_equal(got["H"], ref["H"]) and np.array_equal(got["inlier_xy"], ref["inlier_xy"])
+                assert got[k] == ref[k], (it, k, got[k], ref[k])
+            assert np.array_equal(got["H"], ref["H"]) and np.array_equal(got["inlier_xy"], ref["inlier_xy"]), it
     finally:
         mg.set_pair_overlap(False)

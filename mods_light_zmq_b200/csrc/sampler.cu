@@ -376,6 +376,7 @@ __host__ __device__ inline int a_smem_floats(int R, int r) {
   return 64 + 64 + 72 + 2 * R * nte + R * PS + (R + 2 * r + 4) * PT;
 }
 
+template <int NT>
 __global__ void __launch_bounds__(NT)
 k_sample_a(const float* __restrict__ img, int w, int h, const PatchMeta* __restrict__ metas,
            const float* __restrict__ taps_all, uint8_t* __restrict__ out, int ps, float* __restrict__ outf,
@@ -850,6 +851,14 @@ static int env_int(const char* name, int dflt) { const char* e = getenv(name); r
 // class B1 keeps a coordinate table entry for every 4th sample (3 % faster than 8; 72 KB still gives 3 CTAs per SM), B2 for
 // every 8th (a finer table would drop it to one CTA per SM).  8 instead of 4 segments in flight per lane: measured slower.
 static int smp_b1_ts() { static const int v = env_int("MODSGPU_B1_TS", 4); return v == 8 ? 8 : 4; }
+// class A1 (R <= 40) runs 128-thread CTAs: its phases have 100-400 work items, half of a 256-thread CTA sat at the barriers
+static int smp_a1_nt() { static const int v = env_int("MODSGPU_A1_NT", 128); return v == 256 ? 256 : 128; }
+template <typename... A>
+static void launch_sample_a(bool a1, unsigned grid, int smem, cudaStream_t st, A... a) {
+  static const int a2nt = env_int("MODSGPU_A2_NT", 256);
+  if ((a1 && smp_a1_nt() == 128) || (!a1 && a2nt == 128)) k_sample_a<128><<<grid, 128, smem, st>>>(a...);
+  else k_sample_a<256><<<grid, 256, smem, st>>>(a...);
+}
 template <typename... A>
 static void launch_sample_b(bool b1, unsigned grid, int smem, cudaStream_t st, A... a) {
   if (b1 && smp_b1_ts() == 4) k_sample_b<4, 4><<<grid, NT, smem, st>>>(a...);
@@ -961,7 +970,8 @@ int mg_sample_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
     MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_small, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SMALL));
     MG_CUDA(ctx, cudaFuncSetAttribute(k_large_rowpass, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (2 * MAX_PS + 642 + L2_ROWS * ((MAX_R + 602) | 1)) * 4));
-    MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_a, cudaFuncAttributeMaxDynamicSharedMemorySize, a_smem_floats(A2_R, 30) * 4));
+    MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_a<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, a_smem_floats(A2_R, 30) * 4));
+    MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_a<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, a_smem_floats(A2_R, 30) * 4));
     MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_b<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, b_smem_floats(B1_R, 30, 4) * 4));
     MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_b<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, b_smem_floats(B2_R, 30, 8) * 4));
     attr_set.set(ctx->device);
@@ -982,7 +992,7 @@ int mg_sample_enqueue(modsgpu_ctx* ctx, const modsgpu_image* img, const modsgpu_
     if (cls[c].empty()) continue;
     const int smem = a_smem_floats(std::min(a_maxR[c - C_A1], cls[c][0].R), cls_r[c]) * 4;
     MG_PROF(ctx, c == C_A1 ? "k_sample_a<R<=40>" : "k_sample_a<R<=65>", 0, alg_bytes(cls[c]));
-    k_sample_a<<<(unsigned)cls[c].size(), NT, smem, ctx->stream>>>(img->d, img->w, img->h, dm + cls_off[c], dtaps, d_out, ps, d_outf, nullptr);
+    launch_sample_a(c == C_A1, (unsigned)cls[c].size(), smem, ctx->stream, (const float*)img->d, img->w, img->h, dm + cls_off[c], dtaps, d_out, ps, d_outf, (const int*)nullptr);
     MG_LAUNCHED(ctx);
   }
   for (int c = C_B1; c <= C_B2; c++) {
@@ -1320,7 +1330,8 @@ int mg_sample_enqueue_dev(modsgpu_ctx* ctx, const modsgpu_image* img, const DevR
     MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_small, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SMALL));
     MG_CUDA(ctx, cudaFuncSetAttribute(k_large_rowpass, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (2 * MAX_PS + 642 + L2_ROWS * ((MAX_R + 602) | 1)) * 4));
-    MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_a, cudaFuncAttributeMaxDynamicSharedMemorySize, a_smem_floats(A2_R, 30) * 4));
+    MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_a<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, a_smem_floats(A2_R, 30) * 4));
+    MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_a<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, a_smem_floats(A2_R, 30) * 4));
     MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_b<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, b_smem_floats(B1_R, 30, 4) * 4));
     MG_CUDA(ctx, cudaFuncSetAttribute(k_sample_b<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, b_smem_floats(B2_R, 30, 8) * 4));
     attr_set.set(ctx->device);
@@ -1340,7 +1351,7 @@ int mg_sample_enqueue_dev(modsgpu_ctx* ctx, const modsgpu_image* img, const DevR
     if (st.cls_cnt[c] <= 0) continue;
     const int smem = a_smem_floats(std::min(a_maxR[c - SC_A1], st.cls_rmax[c]), st.cls_kr[c]) * 4;
     MG_PROF(ctx, c == SC_A1 ? "k_sample_a<R<=40>" : "k_sample_a<R<=65>", 0, alg_bytes(c));
-    k_sample_a<<<(unsigned)st.cls_cnt[c], NT, smem, ctx->stream>>>(img->d, img->w, img->h, dm + lay.cls_off[c], dtaps, d_out, ps, nullptr, dcnt + c);
+    launch_sample_a(c == SC_A1, (unsigned)st.cls_cnt[c], smem, ctx->stream, (const float*)img->d, img->w, img->h, (const PatchMeta*)(dm + lay.cls_off[c]), dtaps, d_out, ps, (float*)nullptr, (const int*)(dcnt + c));
     MG_LAUNCHED(ctx);
   }
   for (int c = SC_B1; c <= SC_B2; c++) {

@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
 F7 = ("x", "y", "s", "a11", "a12", "a21", "a22")
 ULP = 1e-14     # a rotated entry is a11*cos - a12*sin with cos / sin each within 2 ulp of glibc's; the reprojection by
                 # H^-1 of a tilted view (entries up to the tilt) adds products of those with cancellation: <= 45 ulp of max(1, |a|)
@@ -186,3 +187,24 @@ def test_pair_overlap_equals_sequential(mg):
             assert np.array_equal(got["H"], ref["H"]) and np.array_equal(got["inlier_xy"], ref["inlier_xy"]), it
     finally:
         mg.set_pair_overlap(False)
+
+
+@pytest.mark.gpu
+def test_detector_generic_blur_path_equals_specialised(mg, tmp_path):
+    """The ksize-specialised blur (k_blur3, response of the source tile and half-size image fused in) and the generic route
+    (k_blur_resp2 + k_response + k_half, taken for ksizes outside 7..23; forced here with MODSGPU_NO_BLUR3=1 in a child
+    process -- the switch is read once per process) give byte-equal keypoint lists."""
+    import subprocess
+    import sys
+    from mods_light_zmq_b200 import synth
+    root = os.path.dirname(HERE)
+    a, _, _ = synth.image_pair(seed=5, w=800, h=640)            # 800 -> 400 -> 200 -> 100 -> 50 -> 25: ragged widths too
+    kp = mg.detect(mg.image_from_bgr8(synth.gray_to_bgr(a)))
+    out = str(tmp_path / "kp.npy")
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); import mods_light_zmq_b200 as M; from mods_light_zmq_b200 import synth; "
+            "mg = M.ModsGpu(0, load_nets=False); a, _, _ = synth.image_pair(seed=5, w=800, h=640); "
+            "np.save(%r, mg.detect(mg.image_from_bgr8(synth.gray_to_bgr(a))))" % (root, out))
+    env = dict(os.environ, MODSGPU_NO_BLUR3="1")
+    subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=300)
+    ref = np.load(out)
+    assert len(kp) == len(ref) > 500 and kp.tobytes() == ref.tobytes()

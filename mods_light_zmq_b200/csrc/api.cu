@@ -28,12 +28,15 @@ extern "C" int modsgpu_create(int device, modsgpu_ctx** out) {
   const bool spinning = spin && atoi(spin) != 0;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess ||
-      cudaEventCreateWithFlags(&ctx->ev1, spinning ? cudaEventDefault : cudaEventBlockingSync) != cudaSuccess) {
-    delete ctx;
-    return MODSGPU_ECUDA;
-  }
-  if (!spinning &&
-      cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&ctx->ev1, spinning ? cudaEventDefault : cudaEventBlockingSync) != cudaSuccess ||
+      (!spinning &&
+       cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess)) {
+    // whatever was created so far goes with the context (nothing else holds these handles yet)
+    if (ctx->ev_sync) cudaEventDestroy(ctx->ev_sync);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    cudaGetLastError();
     delete ctx;
     return MODSGPU_ECUDA;
   }

@@ -939,12 +939,16 @@ extern "C" int modsgpu_image_from_bgr8(modsgpu_ctx* ctx, const uint8_t* bgr, int
   MG_CUDA(ctx, ctx->io_a.ensure(n * 3));
   modsgpu_image* img = new modsgpu_image();
   img->w = w; img->h = h;
-  MG_CUDA(ctx, mg_image_alloc(ctx, n * sizeof(float), &img->d));
-  MG_CUDA(ctx, cudaMemcpyAsync(ctx->io_a.p, bgr, n * 3, cudaMemcpyHostToDevice, ctx->stream));
-  MG_PROF(ctx, "k_gray_from_bgr", 0, (double)n * 7.0);
-  k_gray_from_bgr<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->io_a.as<uint8_t>(), img->d, (long)n);
-  MG_LAUNCHED(ctx);
-  if (mg_end(ctx)) return MODSGPU_ECUDA;
+  // every error path below hands the image (and its device buffer, if any) back
+  auto body = [&]() -> int {
+    MG_CUDA(ctx, mg_image_alloc(ctx, n * sizeof(float), &img->d));
+    MG_CUDA(ctx, cudaMemcpyAsync(ctx->io_a.p, bgr, n * 3, cudaMemcpyHostToDevice, ctx->stream));
+    MG_PROF(ctx, "k_gray_from_bgr", 0, (double)n * 7.0);
+    k_gray_from_bgr<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->io_a.as<uint8_t>(), img->d, (long)n);
+    MG_LAUNCHED(ctx);
+    return mg_end(ctx) ? MODSGPU_ECUDA : 0;
+  };
+  if (const int rc = body()) { modsgpu_image_free(ctx, img); return rc; }
   *out = img;
   return 0;
 }
@@ -954,9 +958,12 @@ extern "C" int modsgpu_image_from_gray32f(modsgpu_ctx* ctx, const float* gray, i
   if (mg_begin(ctx)) return MODSGPU_ECUDA;
   modsgpu_image* img = new modsgpu_image();
   img->w = w; img->h = h;
-  MG_CUDA(ctx, mg_image_alloc(ctx, (size_t)w * h * sizeof(float), &img->d));
-  MG_CUDA(ctx, cudaMemcpy2DAsync(img->d, (size_t)w * 4, gray, (size_t)stride * 4, (size_t)w * 4, h, cudaMemcpyHostToDevice, ctx->stream));
-  if (mg_end(ctx)) return MODSGPU_ECUDA;
+  auto body = [&]() -> int {
+    MG_CUDA(ctx, mg_image_alloc(ctx, (size_t)w * h * sizeof(float), &img->d));
+    MG_CUDA(ctx, cudaMemcpy2DAsync(img->d, (size_t)w * 4, gray, (size_t)stride * 4, (size_t)w * 4, h, cudaMemcpyHostToDevice, ctx->stream));
+    return mg_end(ctx) ? MODSGPU_ECUDA : 0;
+  };
+  if (const int rc = body()) { modsgpu_image_free(ctx, img); return rc; }
   *out = img;
   return 0;
 }

@@ -266,6 +266,20 @@ typedef struct {
 int  modsgpu_describe_view(modsgpu_ctx* ctx, const modsgpu_image* view, const double* H, int orig_w, int orig_h,
                            const modsgpu_pyr_params* p, double mrSize, int patchSize, modsgpu_view_region** regions,
                            float** desc, int* n, int* counts);
+
+/* The same with the descriptors left ON THE DEVICE (what a caller that only matches them wants: 0.5 MB instead of 2.7 MB
+ * read back per 4k-keypoint view and nothing uploaded again).  *desc (NULL when the view has no keypoint) is released with
+ * modsgpu_devdesc_free on the context that made it; modsgpu_match_fginn_dev = modsgpu_match_fginn over two such blocks
+ * (any context of the same device); modsgpu_devdesc_download copies the n x 128 floats out (tests). */
+typedef struct modsgpu_devdesc modsgpu_devdesc;
+int  modsgpu_describe_view_dev(modsgpu_ctx* ctx, const modsgpu_image* view, const double* H, int orig_w, int orig_h,
+                               const modsgpu_pyr_params* p, double mrSize, int patchSize, modsgpu_view_region** regions,
+                               modsgpu_devdesc** desc, int* n, int* counts);
+int  modsgpu_devdesc_size(const modsgpu_devdesc* desc);
+int  modsgpu_devdesc_download(modsgpu_ctx* ctx, const modsgpu_devdesc* desc, float* out);
+void modsgpu_devdesc_free(modsgpu_ctx* ctx, modsgpu_devdesc* desc);
+int  modsgpu_match_fginn_dev(modsgpu_ctx* ctx, const modsgpu_devdesc* q, const modsgpu_devdesc* t, const double* txy,
+                             double ratio_thr, double contrad_dist, int nn, modsgpu_match* out, int* nout);
 /* test-only: the two device post-processing steps of the chain on caller-supplied net outputs (survivors, order kept) */
 int  modsgpu_debug_affnet_post(modsgpu_ctx* ctx, const modsgpu_view_region* regs, const float* aff, int n, int w, int h,
                                int orig_w, int orig_h, double mrSize, const double* H, modsgpu_view_region* out,

@@ -116,6 +116,7 @@ extern "C" void modsgpu_destroy(modsgpu_ctx* ctx) {
   for (auto& r : ctx->prof.recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   ctx->l2flush.release();
   for (auto& b : ctx->img_pool) cudaFree(b.first);
+  for (auto& b : ctx->desc_pool) cudaFree(b.first);
   if (ctx->tm0) cudaEventDestroy(ctx->tm0);
   if (ctx->tm1) cudaEventDestroy(ctx->tm1);
   cudaEventDestroy(ctx->ev0);

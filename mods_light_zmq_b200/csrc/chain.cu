@@ -304,15 +304,69 @@ extern "C" int modsgpu_debug_orinet_post(modsgpu_ctx* ctx, const modsgpu_view_re
 
 // The whole view.  *regions (n rows) and *desc (n x 128 floats holding integers 0..255) are malloc()ed -> modsgpu_free.
 // counts: [0] raw keypoints, [1] regions after AffNet's eigen-ratio / frame tests, [2] described regions (= n).
+// Descriptor block left on the device (modsgpu_describe_view_dev): n x dim floats, buffers recycled through the context
+// (cudaFree would synchronise the device).
+struct modsgpu_devdesc { float* d = nullptr; int n = 0, dim = 128; size_t cap = 0; };
+
+static cudaError_t devdesc_alloc(modsgpu_ctx* ctx, size_t bytes, modsgpu_devdesc* dd) {
+  bytes = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);       // 1 MB granules: same-sized views hit the pool
+  for (size_t i = 0; i < ctx->desc_pool.size(); i++)
+    if (ctx->desc_pool[i].second >= bytes && ctx->desc_pool[i].second <= 2 * bytes) {
+      dd->d = ctx->desc_pool[i].first; dd->cap = ctx->desc_pool[i].second;
+      ctx->desc_pool.erase(ctx->desc_pool.begin() + i);
+      return cudaSuccess;
+    }
+  dd->cap = bytes;
+  return cudaMalloc((void**)&dd->d, bytes);
+}
+extern "C" void modsgpu_devdesc_free(modsgpu_ctx* ctx, modsgpu_devdesc* dd) {
+  if (!dd) return;
+  if (dd->d) {
+    if (ctx && ctx->desc_pool.size() < 8) ctx->desc_pool.emplace_back(dd->d, dd->cap);
+    else cudaFree(dd->d);
+  }
+  delete dd;
+}
+extern "C" int modsgpu_devdesc_size(const modsgpu_devdesc* dd) { return dd ? dd->n : 0; }
+const float* mg_devdesc_ptr(const modsgpu_devdesc* dd) { return dd ? dd->d : nullptr; }
+// n x 128 floats to the host (tests; the product path never needs them there)
+extern "C" int modsgpu_devdesc_download(modsgpu_ctx* ctx, const modsgpu_devdesc* dd, float* out) {
+  if (!ctx || !dd || (dd->n > 0 && !out)) return MODSGPU_EINVAL;
+  if (mg_begin(ctx)) return MODSGPU_ECUDA;
+  if (dd->n > 0) MG_CUDA(ctx, cudaMemcpyAsync(out, dd->d, (size_t)dd->n * dd->dim * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  return mg_end(ctx) ? MODSGPU_ECUDA : 0;
+}
+
+static int describe_view_impl(modsgpu_ctx* ctx, const modsgpu_image* view, const double* H, int orig_w, int orig_h,
+                              const modsgpu_pyr_params* p, double mrSize, int patchSize, modsgpu_view_region** regions,
+                              float** desc, modsgpu_devdesc** devdesc, int* n, int* counts);
+
 extern "C" int modsgpu_describe_view(modsgpu_ctx* ctx, const modsgpu_image* view, const double* H, int orig_w, int orig_h,
                                      const modsgpu_pyr_params* p, double mrSize, int patchSize, modsgpu_view_region** regions,
                                      float** desc, int* n, int* counts) {
-  if (!ctx || !view || !p || !regions || !desc || !n) return MODSGPU_EINVAL;
+  if (!desc) return MODSGPU_EINVAL;
+  return describe_view_impl(ctx, view, H, orig_w, orig_h, p, mrSize, patchSize, regions, desc, nullptr, n, counts);
+}
+// The same with the descriptors LEFT ON THE DEVICE (*devdesc -> modsgpu_devdesc_free): what a caller that only matches them
+// (modsgpu_match_fginn_dev) wants -- 0.5 MB instead of 2.7 MB read back per 4k-keypoint view, nothing uploaded again.
+extern "C" int modsgpu_describe_view_dev(modsgpu_ctx* ctx, const modsgpu_image* view, const double* H, int orig_w, int orig_h,
+                                         const modsgpu_pyr_params* p, double mrSize, int patchSize, modsgpu_view_region** regions,
+                                         modsgpu_devdesc** devdesc, int* n, int* counts) {
+  if (!devdesc) return MODSGPU_EINVAL;
+  return describe_view_impl(ctx, view, H, orig_w, orig_h, p, mrSize, patchSize, regions, nullptr, devdesc, n, counts);
+}
+
+static int describe_view_impl(modsgpu_ctx* ctx, const modsgpu_image* view, const double* H, int orig_w, int orig_h,
+                              const modsgpu_pyr_params* p, double mrSize, int patchSize, modsgpu_view_region** regions,
+                              float** desc, modsgpu_devdesc** devdesc, int* n, int* counts) {
+  if (!ctx || !view || !p || !regions || !n) return MODSGPU_EINVAL;
+  if (devdesc) *devdesc = nullptr;
   if (patchSize != 32) MG_FAIL(ctx, MODSGPU_EINVAL, "the networks take 32x32 patches");
   if (p->detectorMode < MODSGPU_FIXED_TH || p->detectorMode > MODSGPU_NOT_LESS_THAN_REGIONS)
     MG_FAIL(ctx, MODSGPU_EINVAL, "unknown detectorMode");
   for (int i = 0; i < 3; i++) if (!ctx->nets[i]) MG_FAIL(ctx, MODSGPU_ESTATE, "modsgpu_load_weights has not been called for every net");
-  *regions = nullptr; *desc = nullptr; *n = 0;
+  *regions = nullptr; *n = 0;
+  if (desc) *desc = nullptr;
   if (counts) counts[0] = counts[1] = counts[2] = 0;
   if (mg_begin(ctx)) return MODSGPU_ECUDA;
   const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
@@ -385,25 +439,38 @@ extern "C" int modsgpu_describe_view(modsgpu_ctx* ctx, const modsgpu_image* view
   MG_PROF(ctx, "k_chain_compact", 2, (double)n0);
   k_chain_compact<<<1, 1024, 0, ctx->stream>>>(tmp, flag, cnt + 2, ra, cnt + 3, 1);
   MG_LAUNCHED(ctx);
-  // ---- HardNet++
-  if ((rc = mg_sample_enqueue_dev(ctx, view, ra, cnt + 3, n0, st, mrSize, patches))) return rc;
-  if ((rc = mg_net_forward_enqueue(ctx, MODSGPU_HARDNET, patches, n0, nout, cnt + 3))) return rc;
+  // ---- HardNet++ (its output lands in the block that stays on the device, if the caller asked for one)
+  modsgpu_devdesc* dd = nullptr;
+  if (devdesc) {
+    dd = new modsgpu_devdesc();
+    if (devdesc_alloc(ctx, (size_t)n0 * 128 * 4 + 16, dd) != cudaSuccess) {
+      cudaGetLastError();
+      delete dd;
+      MG_FAIL(ctx, MODSGPU_ECUDA, "descriptor block could not be allocated");
+    }
+    nout = dd->d;
+  }
+  auto fail = [&](int code) { if (dd) modsgpu_devdesc_free(ctx, dd); return code; };
+  if ((rc = mg_sample_enqueue_dev(ctx, view, ra, cnt + 3, n0, st, mrSize, patches))) return fail(rc);
+  if ((rc = mg_net_forward_enqueue(ctx, MODSGPU_HARDNET, patches, n0, nout, cnt + 3))) return fail(rc);
   // ---- one read-back: counters, region rows, descriptors (sized by the upper bound n0; the live rows are the first n3)
-  const size_t row_bytes = (size_t)n0 * sizeof(DevRegion), desc_bytes = (size_t)n0 * 128 * 4;
-  MG_CUDA(ctx, ctx->h_out.ensure(64 + row_bytes + desc_bytes));
+  const size_t row_bytes = (size_t)n0 * sizeof(DevRegion), desc_bytes = desc ? (size_t)n0 * 128 * 4 : 0;
+  if (cudaSuccess != ctx->h_out.ensure(64 + row_bytes + desc_bytes)) { cudaGetLastError(); ctx->err = "pinned read-back buffer"; return fail(MODSGPU_ECUDA); }
   uint8_t* ho = ctx->h_out.as<uint8_t>();
-  MG_CUDA(ctx, cudaMemcpyAsync(ho, cnt, 16, cudaMemcpyDeviceToHost, ctx->stream));
-  MG_CUDA(ctx, cudaMemcpyAsync(ho + 64, ra, row_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  MG_CUDA(ctx, cudaMemcpyAsync(ho + 64 + row_bytes, nout, desc_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  if (mg_end(ctx)) return MODSGPU_ECUDA;                              // host round trip 2 of 2
+  bool ok = cudaMemcpyAsync(ho, cnt, 16, cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess &&
+            cudaMemcpyAsync(ho + 64, ra, row_bytes, cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess;
+  if (ok && desc) ok = cudaMemcpyAsync(ho + 64 + row_bytes, nout, desc_bytes, cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess;
+  if (!ok) { ctx->err = std::string("describe_view read-back: ") + cudaGetErrorString(cudaGetLastError()); return fail(MODSGPU_ECUDA); }
+  if (mg_end(ctx)) return fail(MODSGPU_ECUDA);                        // host round trip 2 of 2
   const int* fc = reinterpret_cast<const int*>(ho);
   const int n3 = fc[3];
   if (counts) { counts[1] = fc[1]; counts[2] = n3; }
   modsgpu_view_region* r = (modsgpu_view_region*)malloc(sizeof(modsgpu_view_region) * (size_t)std::max(n3, 1));
-  float* d = (float*)malloc(sizeof(float) * 128 * (size_t)std::max(n3, 1));
-  if (!r || !d) { free(r); free(d); MG_FAIL(ctx, MODSGPU_ECUDA, "out of host memory"); }
+  float* d = desc ? (float*)malloc(sizeof(float) * 128 * (size_t)std::max(n3, 1)) : nullptr;
+  if (!r || (desc && !d)) { free(r); free(d); ctx->err = "out of host memory"; return fail(MODSGPU_ECUDA); }
   memcpy(r, ho + 64, (size_t)n3 * sizeof(DevRegion));
-  memcpy(d, ho + 64 + row_bytes, (size_t)n3 * 512);
-  *regions = r; *desc = d; *n = n3;
+  if (desc) { memcpy(d, ho + 64 + row_bytes, (size_t)n3 * 512); *desc = d; }
+  if (dd) { dd->n = n3; *devdesc = dd; }
+  *regions = r; *n = n3;
   return 0;
 }

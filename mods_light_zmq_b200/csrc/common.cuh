@@ -124,11 +124,14 @@ struct modsgpu_ctx {
   cudaEvent_t tm0 = nullptr, tm1 = nullptr;   // modsgpu_timer_*
   DevBuf l2flush;
   std::vector<std::pair<float*, size_t>> img_pool;   // recycled image buffers (cudaFree would sync the device)
+  std::vector<std::pair<float*, size_t>> desc_pool;  // recycled device descriptor blocks (modsgpu_describe_view_dev)
 };
 
 cudaError_t mg_image_alloc(modsgpu_ctx* ctx, size_t bytes, float** out);
 
 int mg_nets_share(modsgpu_ctx* sib, const modsgpu_ctx* src);      // cnn.cu
+struct modsgpu_devdesc;
+const float* mg_devdesc_ptr(const modsgpu_devdesc* dd);            // chain.cu
 void mg_prof_begin(modsgpu_ctx* ctx, const char* name, int kind, double work, double bytes = 0.0);
 void mg_prof_end(modsgpu_ctx* ctx);
 // call right before a kernel launch; MG_LAUNCHED closes the record

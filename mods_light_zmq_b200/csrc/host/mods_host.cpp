@@ -70,6 +70,7 @@ bool getEigenvalues(float a, float b, float c, float d, float& l1, float& l2) {
 ImageRepresentation::ImageRepresentation(modsgpu_ctx* ctx, modsgpu_image* img, bool owns_image)
     : ctx_(ctx), img_(img), owns_(owns_image) {}
 ImageRepresentation::~ImageRepresentation() {
+  if (devdesc_) modsgpu_devdesc_free(ctx_, devdesc_);
   if (owns_ && img_) modsgpu_image_free(ctx_, img_);
 }
 
@@ -210,11 +211,15 @@ int ImageRepresentation::DescribeView(modsgpu_image* view, const double* H, int 
     modsgpu_view_region* rows = nullptr;
     float* desc = nullptr;
     int n = 0, counts[3] = {0, 0, 0};
-    int rc = modsgpu_describe_view(ctx_, view, H, orig_w, orig_h, &par.pyr, par.mrSize, par.patchSize, &rows, &desc, &n, counts);
+    const bool on_device = par.desc_on_device && &result == &regions_;
+    if (devdesc_) { modsgpu_devdesc_free(ctx_, devdesc_); devdesc_ = nullptr; }
+    int rc = on_device ? modsgpu_describe_view_dev(ctx_, view, H, orig_w, orig_h, &par.pyr, par.mrSize, par.patchSize, &rows, &devdesc_, &n, counts)
+                       : modsgpu_describe_view(ctx_, view, H, orig_w, orig_h, &par.pyr, par.mrSize, par.patchSize, &rows, &desc, &n, counts);
     if (rc) return rc;
     n_keypoints = counts[0];
     n_affine = counts[1];
-    auto blk = std::make_shared<const std::vector<float>>(desc, desc + (size_t)n * 128);
+    std::shared_ptr<const std::vector<float>> blk;
+    if (!on_device) blk = std::make_shared<const std::vector<float>>(desc, desc + (size_t)n * 128);
     result.resize(n);
     for (int i = 0; i < n; i++) {
       AffineRegion& r = result[i];
@@ -227,10 +232,10 @@ int ImageRepresentation::DescribeView(modsgpu_image* view, const double* H, int 
       const modsgpu_region& q = rows[i].reproj;
       r.reproj_kp.x = q.x; r.reproj_kp.y = q.y;
       r.reproj_kp.a11 = q.a11; r.reproj_kp.a12 = q.a12; r.reproj_kp.a21 = q.a21; r.reproj_kp.a22 = q.a22;
-      r.desc.view(blk, (size_t)i * 128, 128);
+      if (!on_device) r.desc.view(blk, (size_t)i * 128, 128);
     }
     modsgpu_free(rows);
-    modsgpu_free(desc);
+    if (desc) modsgpu_free(desc);
     TimeSpent.DescTime += now_ms() - t0;
     return n;
   }
@@ -562,6 +567,33 @@ int MatchFlannFGINN(modsgpu_ctx* ctx, const AffineRegionVector& list1, const Aff
   int nm = 0;
   int rc = modsgpu_match_fginn(ctx, q, n1, t, txy.data(), n2, dim, par.FGINNThreshold, par.contradDist,
                                par.nn, m.data(), &nm, nullptr, nullptr);
+  if (rc) return rc;
+  corresp.TCList.reserve(nm);
+  for (int k = 0; k < nm; k++) {
+    TentativeCorrespExt tc;
+    tc.first = list1[m[k].qi];
+    tc.second = list2[m[k].ti];
+    tc.secondbad_idx = m[k].tj_bad;
+    tc.d1 = m[k].d1; tc.d2 = m[k].d2; tc.ratio = m[k].ratio;
+    corresp.TCList.push_back(tc);
+  }
+  return nm;
+}
+
+int MatchFlannFGINNDevice(modsgpu_ctx* ctx, const ImageRepresentation& img1, const ImageRepresentation& img2,
+                          TentativeCorrespListExt& corresp, const MatchPars& par) {
+  corresp.TCList.clear();
+  const AffineRegionVector& list1 = img1.GetAffineRegionVector();
+  const AffineRegionVector& list2 = img2.GetAffineRegionVector();
+  const int n1 = (int)list1.size(), n2 = (int)list2.size();
+  if (n1 == 0 || n2 == 0) return 0;
+  const modsgpu_devdesc *q = img1.device_descriptors(), *t = img2.device_descriptors();
+  if (!q || !t || modsgpu_devdesc_size(q) != n1 || modsgpu_devdesc_size(t) != n2) return MODSGPU_ESTATE;
+  std::vector<double> txy((size_t)n2 * 2);
+  for (int i = 0; i < n2; i++) { txy[2 * i] = list2[i].reproj_kp.x; txy[2 * i + 1] = list2[i].reproj_kp.y; }
+  std::vector<modsgpu_match> m(n1);
+  int nm = 0;
+  int rc = modsgpu_match_fginn_dev(ctx, q, t, txy.data(), par.FGINNThreshold, par.contradDist, par.nn, m.data(), &nm);
   if (rc) return rc;
   corresp.TCList.reserve(nm);
   for (int k = 0; k < nm; k++) {
@@ -1107,6 +1139,13 @@ extern "C" int modsgpu_pair_pipeline_images_ex(modsgpu_ctx* ctx, modsgpu_image* 
   MatchPars mp;
   RANSACPars rp;
   unpack_params(pp, dp, mp, rp);
+  // the pair-level call returns correspondences, never descriptors: they stay on the device between HardNet++ and the
+  // matcher (MODSGPU_HOST_DESC=1, read per call, keeps the host round trip of the seam route -- the tests compare the two)
+  {
+    const char* e = getenv("MODSGPU_HOST_DESC");
+    const char* seam = getenv("MODSGPU_SEAM_CHAIN");
+    dp.desc_on_device = !(e && atoi(e) != 0) && !(seam && atoi(seam) != 0);
+  }
   const bool hp = host_profile();
   double c[6] = {0, 0, 0, 0, 0, 0}, w[6] = {0, 0, 0, 0, 0, 0};
   auto mark = [&](int i) { if (hp) { c[i] = cpu_ms(); w[i] = now_ms(); } };
@@ -1140,7 +1179,8 @@ extern "C" int modsgpu_pair_pipeline_images_ex(modsgpu_ctx* ctx, modsgpu_image* 
   res->regions[0] = r1.n_affine; res->regions[1] = r2.n_affine;
   res->descriptors[0] = n1; res->descriptors[1] = n2;
   TentativeCorrespListExt tent, verified;
-  int nt = MatchFlannFGINN(ctx, r1.GetAffineRegionVector(), r2.GetAffineRegionVector(), tent, mp);
+  int nt = dp.desc_on_device ? MatchFlannFGINNDevice(ctx, r1, r2, tent, mp)
+                             : MatchFlannFGINN(ctx, r1.GetAffineRegionVector(), r2.GetAffineRegionVector(), tent, mp);
   if (nt < 0) return nt;
   mark(3);
   res->tentatives = nt;

@@ -85,6 +85,9 @@ struct DetectPars {
   int oriPatchSize = 32, maxAngles = 1;   // [DominantOrientation]
   double oriThreshold = 0.8;
   int siftPatchSize = 41, photoNorm = 1, rootSift = 1;   // [SIFTDescriptor] + iters_HessianSIFT.ini (RootSIFT)
+  // identity-view extraction only: leave the descriptors on the device (ImageRepresentation::device_descriptors()) instead
+  // of filling AffineRegion::desc -- for callers that only match them (MatchFlannFGINNDevice)
+  bool desc_on_device = false;
   DetectPars() { modsgpu_default_pyr_params(&pyr); modsgpu_default_affshape_params(&aff); }
 };
 
@@ -111,6 +114,8 @@ class ImageRepresentation {
  public:
   ImageRepresentation(modsgpu_ctx* ctx, modsgpu_image* img, bool owns_image);
   ~ImageRepresentation();
+  ImageRepresentation(const ImageRepresentation&) = delete;              // owns device handles
+  ImageRepresentation& operator=(const ImageRepresentation&) = delete;
   // the keyed region store of the reference (imagerepresentation.h:64, RegionVectorMap[detector][descriptor]).  The lists
   // this object extracts itself are kept in regions_ under (det_name, desc_name) = ("HessianAffine", "ZMQ" | "RootSIFT");
   // AddRegions (imagerepresentation.cpp:637-660) files further lists, e.g. pre-extracted ones, under their own keys.
@@ -135,8 +140,11 @@ class ImageRepresentation {
   int SynthDetectDescribeKeypointsClassic(const DetectPars& par);
   int n_keypoints = 0, n_affine = 0;
   TimeLog TimeSpent;
+  // descriptor rows of GetAffineRegionVector() in list order, on the device (DetectPars::desc_on_device); NULL otherwise
+  const modsgpu_devdesc* device_descriptors() const { return devdesc_; }
 
  private:
+  modsgpu_devdesc* devdesc_ = nullptr;
   modsgpu_ctx* ctx_;
   modsgpu_image* img_;
   bool owns_;
@@ -156,6 +164,9 @@ void OxAffEllipse(const AffineKeypoint& k, float& a, float& b, float& c);
 
 int MatchFlannFGINN(modsgpu_ctx* ctx, const AffineRegionVector& list1, const AffineRegionVector& list2,
                     TentativeCorrespListExt& corresp, const MatchPars& par);
+// the same over two images whose descriptors stayed on the device (DetectPars::desc_on_device)
+int MatchFlannFGINNDevice(modsgpu_ctx* ctx, const ImageRepresentation& img1, const ImageRepresentation& img2,
+                          TentativeCorrespListExt& corresp, const MatchPars& par);
 
 // correspondencebank.h / .cpp: tentatives filed per (descriptor, detector | "Group").  MatchImgReps
 // (correspondencebank.cpp:234-343): GROUPED -- for every group descriptor the regions of all group detectors are pooled

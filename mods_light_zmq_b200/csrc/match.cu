@@ -456,6 +456,36 @@ extern "C" int modsgpu_match_fginn(modsgpu_ctx* ctx, const float* q, int nq, con
   return 0;
 }
 
+// MatchFlannFGINN over descriptor blocks that never left the device (modsgpu_describe_view_dev): only the train
+// coordinates go up and the matches come down.  Same kernels, same results as modsgpu_match_fginn.
+extern "C" int modsgpu_devdesc_size(const modsgpu_devdesc* dd);
+extern "C" int modsgpu_match_fginn_dev(modsgpu_ctx* ctx, const modsgpu_devdesc* q, const modsgpu_devdesc* t, const double* txy,
+                                       double ratio_thr, double contrad_dist, int nn, modsgpu_match* out, int* nout) {
+  if (!ctx || !nout) return MODSGPU_EINVAL;
+  *nout = 0;
+  const int nq = modsgpu_devdesc_size(q), nt = modsgpu_devdesc_size(t), dim = 128;
+  if ((nq > 0 && !out) || (nt > 0 && !txy)) return MODSGPU_EINVAL;
+  if (mg_begin(ctx)) return MODSGPU_ECUDA;
+  if (nq == 0 || nt == 0) return mg_end(ctx) ? MODSGPU_ECUDA : 0;
+  const size_t xb = (size_t)nt * 16;
+  MG_CUDA(ctx, ctx->io_c.ensure(xb));
+  MG_CUDA(ctx, cudaMemcpyAsync(ctx->io_c.p, txy, xb, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = mg_match_enqueue(ctx, mg_devdesc_ptr(q), nq, mg_devdesc_ptr(t), ctx->io_c.as<double>(), nt, dim, ratio_thr, contrad_dist, nn,
+                            nullptr, nullptr);
+  if (rc) return rc;
+  MG_CUDA(ctx, ctx->h_stage.ensure((size_t)nq * sizeof(modsgpu_match) + 64));
+  modsgpu_match* hm = ctx->h_stage.as<modsgpu_match>();
+  int* hbad = reinterpret_cast<int*>(hm + nq);
+  MG_CUDA(ctx, cudaMemcpyAsync(hm, ctx->mt_out.p, (size_t)nq * sizeof(modsgpu_match), cudaMemcpyDeviceToHost, ctx->stream));
+  MG_CUDA(ctx, cudaMemcpyAsync(hbad, ctx->mt_aux.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (mg_end(ctx)) return MODSGPU_ECUDA;
+  if (*hbad) MG_FAIL(ctx, MODSGPU_EINVAL, "descriptors must hold integers in [0,255] (HardNet++ bytes / RootSIFT)");
+  int m = 0;
+  for (int i = 0; i < nq; i++) if (hm[i].qi >= 0) out[m++] = hm[i];   // query order, like TCList (matching.cpp:449)
+  *nout = m;
+  return 0;
+}
+
 // =====================================================================================================================
 // MatchFLANNDistance (matching.cpp:574-633): binary descriptors (bytes = floor of the float entries, :596-608), the 2
 // nearest train descriptors by Hamming distance, a match whenever the nearest is within matchDistanceThreshold; ratio =

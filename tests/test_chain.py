@@ -208,3 +208,23 @@ def test_detector_generic_blur_path_equals_specialised(mg, tmp_path):
     subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=300)
     ref = np.load(out)
     assert len(kp) == len(ref) > 500 and kp.tobytes() == ref.tobytes()
+
+
+@pytest.mark.gpu
+def test_pair_pipeline_device_descriptors_equal_host_route(mg):
+    """The pair-level call keeps the HardNet++ descriptors on the device between the net and the matcher
+    (modsgpu_describe_view_dev + modsgpu_match_fginn_dev); MODSGPU_HOST_DESC=1 (read per call) restores the read-back /
+    re-upload of the seam route.  Same tentatives, same verified set, same H."""
+    from mods_light_zmq_b200 import synth
+    a, b, _ = synth.image_pair(seed=31, w=800, h=600)
+    A, B = synth.gray_to_bgr(a), synth.gray_to_bgr(b)
+    dev = mg.pair_pipeline(A, B, seed=4)
+    os.environ["MODSGPU_HOST_DESC"] = "1"
+    try:
+        host = mg.pair_pipeline(A, B, seed=4)
+    finally:
+        del os.environ["MODSGPU_HOST_DESC"]
+    assert dev["tentatives"] > 100
+    for k in ("keypoints", "regions", "descriptors", "tentatives", "unique_tentatives", "inliers"):
+        assert dev[k] == host[k], k
+    assert np.array_equal(dev["H"], host["H"]) and np.array_equal(dev["inlier_xy"], host["inlier_xy"])

@@ -280,6 +280,14 @@ int  modsgpu_devdesc_download(modsgpu_ctx* ctx, const modsgpu_devdesc* desc, flo
 void modsgpu_devdesc_free(modsgpu_ctx* ctx, modsgpu_devdesc* desc);
 int  modsgpu_match_fginn_dev(modsgpu_ctx* ctx, const modsgpu_devdesc* q, const modsgpu_devdesc* t, const double* txy,
                              double ratio_thr, double contrad_dist, int nn, modsgpu_match* out, int* nout);
+/* MatchFlannFGINN + DuplicateFiltering (matching.cpp:356-460, :2615-2679, mode bestFGINN) in ONE call: the tentative list
+ * stays on the device between the two, one read-back.  matches (capacity nq) = the tentatives in query order; order
+ * (capacity nq) = indices into matches of the survivors, in the order DuplicateFiltering returns them.  qxy: nq x 2
+ * doubles (query positions), dup_radius <= 0 disables the filter.  Equal to modsgpu_match_fginn_dev followed by
+ * modsgpu_duplicate_filter; refuses nq > 16384 (use the two calls). */
+int  modsgpu_match_dedup_dev(modsgpu_ctx* ctx, const modsgpu_devdesc* q, const modsgpu_devdesc* t, const double* qxy,
+                             const double* txy, double ratio_thr, double contrad_dist, int nn, double dup_radius,
+                             modsgpu_match* matches, int* n_matches, int* order, int* n_unique);
 /* test-only: the two device post-processing steps of the chain on caller-supplied net outputs (survivors, order kept) */
 int  modsgpu_debug_affnet_post(modsgpu_ctx* ctx, const modsgpu_view_region* regs, const float* aff, int n, int w, int h,
                                int orig_w, int orig_h, double mrSize, const double* H, modsgpu_view_region* out,

@@ -607,6 +607,39 @@ int MatchFlannFGINNDevice(modsgpu_ctx* ctx, const ImageRepresentation& img1, con
   return nm;
 }
 
+int MatchDedupDevice(modsgpu_ctx* ctx, const ImageRepresentation& img1, const ImageRepresentation& img2,
+                     TentativeCorrespListExt& corresp, const MatchPars& par, int* n_tentatives) {
+  corresp.TCList.clear();
+  if (n_tentatives) *n_tentatives = 0;
+  const AffineRegionVector& list1 = img1.GetAffineRegionVector();
+  const AffineRegionVector& list2 = img2.GetAffineRegionVector();
+  const int n1 = (int)list1.size(), n2 = (int)list2.size();
+  if (n1 == 0 || n2 == 0) return 0;
+  const modsgpu_devdesc *q = img1.device_descriptors(), *t = img2.device_descriptors();
+  if (!q || !t || modsgpu_devdesc_size(q) != n1 || modsgpu_devdesc_size(t) != n2) return MODSGPU_ESTATE;
+  std::vector<double> qxy((size_t)n1 * 2), txy((size_t)n2 * 2);
+  for (int i = 0; i < n1; i++) { qxy[2 * i] = list1[i].reproj_kp.x; qxy[2 * i + 1] = list1[i].reproj_kp.y; }
+  for (int i = 0; i < n2; i++) { txy[2 * i] = list2[i].reproj_kp.x; txy[2 * i + 1] = list2[i].reproj_kp.y; }
+  std::vector<modsgpu_match> m(n1);
+  std::vector<int> ord(n1);
+  int nm = 0, nu = 0;
+  int rc = modsgpu_match_dedup_dev(ctx, q, t, qxy.data(), txy.data(), par.FGINNThreshold, par.contradDist, par.nn,
+                                   par.doubleFilteringRadius, m.data(), &nm, ord.data(), &nu);
+  if (rc) return rc;
+  if (n_tentatives) *n_tentatives = nm;
+  corresp.TCList.reserve(nu);
+  for (int k = 0; k < nu; k++) {
+    const modsgpu_match& mk = m[ord[k]];
+    TentativeCorrespExt tc;
+    tc.first = list1[mk.qi];
+    tc.second = list2[mk.ti];
+    tc.secondbad_idx = mk.tj_bad;
+    tc.d1 = mk.d1; tc.d2 = mk.d2; tc.ratio = mk.ratio;
+    corresp.TCList.push_back(tc);
+  }
+  return nu;
+}
+
 // ---- keyed region store (imagerepresentation.cpp:600-660) ------------------------------------------------------------
 void ImageRepresentation::AddRegions(const AffineRegionVector& RegionsToAdd, const std::string& det, const std::string& desc) {
   AffineRegionVector& dst = RegionVectorMap[det][desc];       // appended to an existing list, created otherwise
@@ -1179,13 +1212,25 @@ extern "C" int modsgpu_pair_pipeline_images_ex(modsgpu_ctx* ctx, modsgpu_image* 
   res->regions[0] = r1.n_affine; res->regions[1] = r2.n_affine;
   res->descriptors[0] = n1; res->descriptors[1] = n2;
   TentativeCorrespListExt tent, verified;
-  int nt = dp.desc_on_device ? MatchFlannFGINNDevice(ctx, r1, r2, tent, mp)
-                             : MatchFlannFGINN(ctx, r1.GetAffineRegionVector(), r2.GetAffineRegionVector(), tent, mp);
-  if (nt < 0) return nt;
-  mark(3);
-  res->tentatives = nt;
-  int nu = DuplicateFiltering(ctx, tent, mp.doubleFilteringRadius);
-  if (nu < 0) return nu;
+  int nt, nu;
+  const char* unfused_env = getenv("MODSGPU_UNFUSED_TAIL");      // read per call: the tests compare the two routes
+  const bool fused_tail = dp.desc_on_device && !(unfused_env && atoi(unfused_env) != 0) &&
+                          (int)r1.GetAffineRegionVector().size() <= 16384;
+  if (fused_tail) {
+    // matcher + duplicate filter in one device call: the tentative list stays on the device between them
+    nu = MatchDedupDevice(ctx, r1, r2, tent, mp, &nt);
+    if (nu < 0) return nu;
+    mark(3);
+    res->tentatives = nt;
+  } else {
+    nt = dp.desc_on_device ? MatchFlannFGINNDevice(ctx, r1, r2, tent, mp)
+                           : MatchFlannFGINN(ctx, r1.GetAffineRegionVector(), r2.GetAffineRegionVector(), tent, mp);
+    if (nt < 0) return nt;
+    mark(3);
+    res->tentatives = nt;
+    nu = DuplicateFiltering(ctx, tent, mp.doubleFilteringRadius);
+    if (nu < 0) return nu;
+  }
   mark(4);
   res->unique_tentatives = nu;
   int ni = LORANSACFiltering(ctx, tent, verified, res->H, rp);

@@ -167,6 +167,10 @@ int MatchFlannFGINN(modsgpu_ctx* ctx, const AffineRegionVector& list1, const Aff
 // the same over two images whose descriptors stayed on the device (DetectPars::desc_on_device)
 int MatchFlannFGINNDevice(modsgpu_ctx* ctx, const ImageRepresentation& img1, const ImageRepresentation& img2,
                           TentativeCorrespListExt& corresp, const MatchPars& par);
+// MatchFlannFGINNDevice + DuplicateFiltering in one device call (modsgpu_match_dedup_dev): `corresp` receives the filtered
+// list, *n_tentatives the length before the filter; returns the filtered length
+int MatchDedupDevice(modsgpu_ctx* ctx, const ImageRepresentation& img1, const ImageRepresentation& img2,
+                     TentativeCorrespListExt& corresp, const MatchPars& par, int* n_tentatives);
 
 // correspondencebank.h / .cpp: tentatives filed per (descriptor, detector | "Group").  MatchImgReps
 // (correspondencebank.cpp:234-343): GROUPED -- for every group descriptor the regions of all group detectors are pooled

@@ -257,8 +257,9 @@ constexpr int DUP_MAX_T = 16384;
 // correspondence walking all T keys in global memory was 87 us for T = 3000: a chain of dependent loads).
 __global__ void __launch_bounds__(256)
 k_dup_rank(const double* __restrict__ ratio, const double* __restrict__ xy1, const double* __restrict__ xy2, int T,
-           int* __restrict__ ord, double* __restrict__ sxy) {
+           const int* __restrict__ Tp, int* __restrict__ ord, double* __restrict__ sxy) {
   __shared__ double tile[256];
+  if (Tp != nullptr) { T = *Tp; if ((int)blockIdx.x * 64 >= T) return; }     // T known on the device only: grid sized by its bound
   const int i = blockIdx.x * 64 + (threadIdx.x >> 2), q = threadIdx.x & 3;
   const double me = i < T ? fabs(ratio[i]) : 0.0;
   int rank = 0;
@@ -286,9 +287,12 @@ k_dup_rank(const double* __restrict__ ratio, const double* __restrict__ xy1, con
 // (2) conflict bit matrix between sorted positions a < b: a warp forms one 32-bit word with a ballot (lane = b), reading
 // the sorted coordinates coalesced.  Only the words a row's walk reads (w >= a / 32) are written.
 __global__ void __launch_bounds__(256)
-k_dup_conflicts(const double* __restrict__ sxy, int T, int nwords, double r_sq, unsigned* __restrict__ conf, int* __restrict__ rowflag) {
+k_dup_conflicts(const double* __restrict__ sxy, int T, const int* __restrict__ Tp, int nwords, double r_sq, unsigned* __restrict__ conf,
+                int* __restrict__ rowflag) {
+  // nwords = row pitch of conf (from the bound of T when T lives on the device)
   const int a = blockIdx.y, wi = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (wi >= nwords || wi < (a >> 5)) return;
+  if (Tp != nullptr) T = *Tp;
+  if (a >= T || wi >= (T + 31) / 32 || wi < (a >> 5)) return;
   const int b = wi * 32 + lane;
   bool hit = false;
   if (b > a && b < T) {
@@ -301,7 +305,7 @@ k_dup_conflicts(const double* __restrict__ sxy, int T, int nwords, double r_sq, 
   }
   const unsigned bits = __ballot_sync(0xffffffffu, hit);
   if (lane == 0) {
-    conf[(size_t)a * nwords + wi] = bits;
+    conf[(size_t)a * nwords + wi] = bits;      // nwords = pitch
     if (bits) rowflag[a] = 1;
   }
 }
@@ -310,8 +314,10 @@ k_dup_conflicts(const double* __restrict__ sxy, int T, int nwords, double r_sq, 
 // not one L2 round trip per flagged row.
 __global__ void __launch_bounds__(256)
 k_dup_resolve(const unsigned* __restrict__ conf, const int* __restrict__ rowflag, const int* __restrict__ ord, int T,
-              int nwords, int cap_rows, int* __restrict__ out, int* __restrict__ nout) {
-  extern __shared__ unsigned rows_s[];                 // cap_rows x nwords
+              const int* __restrict__ Tp, int pitch, int cap_rows, int* __restrict__ out, int* __restrict__ nout) {
+  extern __shared__ unsigned rows_s[];                 // cap_rows x pitch
+  if (Tp != nullptr) T = *Tp;
+  const int nwords = (T + 31) / 32;
   __shared__ unsigned alive[DUP_MAX_T / 32];
   __shared__ unsigned flagged[DUP_MAX_T / 32];
   __shared__ unsigned short slot_base[DUP_MAX_T / 32];    // staged rows before word w
@@ -334,8 +340,8 @@ k_dup_resolve(const unsigned* __restrict__ conf, const int* __restrict__ rowflag
       const int bit = __ffs(m) - 1;
       m &= m - 1;
       if (k >= cap_rows) break;
-      const unsigned* row = conf + (size_t)(w * 32 + bit) * nwords;
-      for (int x = w + lane; x < nwords; x += 32) rows_s[(size_t)k * nwords + x] = row[x];
+      const unsigned* row = conf + (size_t)(w * 32 + bit) * pitch;
+      for (int x = w + lane; x < nwords; x += 32) rows_s[(size_t)k * pitch + x] = row[x];
       k++;
     }
   }
@@ -348,7 +354,7 @@ k_dup_resolve(const unsigned* __restrict__ conf, const int* __restrict__ rowflag
       const int bit = __ffs(m) - 1;
       m &= m - 1;
       const int a = wa * 32 + bit;
-      const unsigned* row = k < cap_rows ? rows_s + (size_t)k * nwords : conf + (size_t)a * nwords;
+      const unsigned* row = k < cap_rows ? rows_s + (size_t)k * pitch : conf + (size_t)a * pitch;
       k++;
       if (!((alive[wa] >> bit) & 1u)) continue;
       for (int w = wa + lane; w < nwords; w += 32) alive[w] &= ~row[w];
@@ -364,6 +370,71 @@ k_dup_resolve(const unsigned* __restrict__ conf, const int* __restrict__ rowflag
     m += __popc(mask);
   }
   if (lane == 0) *nout = m;
+}
+
+// Matches in query order without the holes (qi < 0), and what the duplicate filter reads of them: the two positions and
+// the ratio.  One CTA, order preserving (ballot + running base), count left on the device.
+__global__ void __launch_bounds__(1024)
+k_match_compact(const modsgpu_match* __restrict__ m, int nq, const double* __restrict__ qxy, const double* __restrict__ txy,
+                modsgpu_match* __restrict__ mc, double* __restrict__ xy1, double* __restrict__ xy2, double* __restrict__ ratio,
+                int* __restrict__ count) {
+  __shared__ int wsum[32];
+  __shared__ int base_s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) base_s = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < nq; i0 += 1024) {
+    const int i = i0 + threadIdx.x;
+    modsgpu_match r;
+    r.qi = -1;
+    if (i < nq) r = m[i];
+    const bool keep = r.qi >= 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) wsum[warp] = __popc(bal);
+    __syncthreads();
+    int off = base_s;
+    for (int w = 0; w < warp; w++) off += wsum[w];
+    if (keep) {
+      const int k = off + __popc(bal & ((1u << lane) - 1));
+      mc[k] = r;
+      xy1[2 * k] = qxy[2 * r.qi]; xy1[2 * k + 1] = qxy[2 * r.qi + 1];
+      xy2[2 * k] = txy[2 * r.ti]; xy2[2 * k + 1] = txy[2 * r.ti + 1];
+      ratio[k] = r.ratio;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 32; w++) t += wsum[w]; base_s += t; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = base_s;
+}
+
+constexpr int RESOLVE_SMEM = 160 * 1024;   // rows of the conflict matrix staged in shared memory by k_dup_resolve
+
+// the three launches of the parallel duplicate filter over T (host value) or *Tp <= T (device value) correspondences
+static int dup_enqueue(modsgpu_ctx* ctx, const double* d1, const double* d2, const double* dr, int T, const int* Tp, double r,
+                       int* dord, int* dout, int* dnout) {
+  const int nwords = (T + 31) / 32;
+  MG_CUDA(ctx, ctx->mt_d.ensure((size_t)T * nwords * 4 + (size_t)T * 4 + 16 + (size_t)T * 32));
+  unsigned* conf = ctx->mt_d.as<unsigned>();
+  int* rowflag = reinterpret_cast<int*>(conf + (size_t)T * nwords);
+  double* sxy = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(ctx->mt_d.p) + (((size_t)T * nwords * 4 + (size_t)T * 4 + 15) & ~(size_t)15));
+  MG_CUDA(ctx, cudaMemsetAsync(rowflag, 0, (size_t)T * 4, ctx->stream));
+  MG_PROF(ctx, "k_dup_rank", 2, (double)T);
+  k_dup_rank<<<(T + 63) / 64, 256, 0, ctx->stream>>>(dr, d1, d2, T, Tp, dord, sxy);
+  MG_LAUNCHED(ctx);
+  MG_PROF(ctx, "k_dup_conflicts", 2, (double)T);
+  k_dup_conflicts<<<dim3((nwords + 7) / 8, T), 256, 0, ctx->stream>>>(sxy, T, Tp, nwords, r * r, conf, rowflag);
+  MG_LAUNCHED(ctx);
+  static OnceFlags attr_set;
+  if (attr_set.need(ctx->device)) {
+    MG_CUDA(ctx, cudaFuncSetAttribute(k_dup_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, RESOLVE_SMEM));
+    attr_set.set(ctx->device);
+  }
+  const int cap_rows = std::min(T, RESOLVE_SMEM / (nwords * 4));
+  MG_PROF(ctx, "k_dup_resolve", 2, (double)T);
+  k_dup_resolve<<<1, 256, (size_t)cap_rows * nwords * 4, ctx->stream>>>(conf, rowflag, dord, T, Tp, nwords, cap_rows, dout, dnout);
+  MG_LAUNCHED(ctx);
+  return 0;
 }
 
 }  // namespace
@@ -486,6 +557,65 @@ extern "C" int modsgpu_match_fginn_dev(modsgpu_ctx* ctx, const modsgpu_devdesc* 
   return 0;
 }
 
+// MatchFlannFGINN + DuplicateFiltering (matching.cpp:356-460, :2615-2679) in one call over device-resident descriptor
+// blocks: the tentative list never visits the host between the two -- it is compacted on the device (k_match_compact),
+// the duplicate filter reads its positions / ratios there and takes its length from device memory; ONE read-back brings the
+// matches (query order) and the order of the survivors.  Results equal modsgpu_match_fginn_dev + modsgpu_duplicate_filter.
+extern "C" int modsgpu_match_dedup_dev(modsgpu_ctx* ctx, const modsgpu_devdesc* q, const modsgpu_devdesc* t, const double* qxy,
+                                       const double* txy, double ratio_thr, double contrad_dist, int nn, double dup_radius,
+                                       modsgpu_match* matches, int* n_matches, int* order, int* n_unique) {
+  if (!ctx || !n_matches || !n_unique) return MODSGPU_EINVAL;
+  *n_matches = 0; *n_unique = 0;
+  const int nq = modsgpu_devdesc_size(q), nt = modsgpu_devdesc_size(t), dim = 128;
+  if ((nq > 0 && (!matches || !order || !qxy)) || (nt > 0 && !txy)) return MODSGPU_EINVAL;
+  if (nq > DUP_MAX_T) MG_FAIL(ctx, MODSGPU_EINVAL, "too many queries for the fused matcher + duplicate filter (use the two calls)");
+  if (mg_begin(ctx)) return MODSGPU_ECUDA;
+  if (nq == 0 || nt == 0) return mg_end(ctx) ? MODSGPU_ECUDA : 0;
+  const size_t xb = (size_t)nt * 16, qb = (size_t)nq * 16;
+  // io_c: [txy | qxy]; io_a: compact matches | xy1 | xy2 | ratio; io_b: ord | out
+  MG_CUDA(ctx, ctx->io_c.ensure(xb + qb));
+  MG_CUDA(ctx, ctx->io_a.ensure((size_t)nq * (sizeof(modsgpu_match) + 40) + 64));
+  MG_CUDA(ctx, ctx->io_b.ensure((size_t)nq * 8 + 64));
+  double* dtxy = ctx->io_c.as<double>();
+  double* dqxy = dtxy + 2 * (size_t)nt;
+  MG_CUDA(ctx, cudaMemcpyAsync(dtxy, txy, xb, cudaMemcpyHostToDevice, ctx->stream));
+  MG_CUDA(ctx, cudaMemcpyAsync(dqxy, qxy, qb, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = mg_match_enqueue(ctx, mg_devdesc_ptr(q), nq, mg_devdesc_ptr(t), dtxy, nt, dim, ratio_thr, contrad_dist, nn, nullptr, nullptr);
+  if (rc) return rc;
+  modsgpu_match* mc = ctx->io_a.as<modsgpu_match>();
+  double* d1 = reinterpret_cast<double*>(mc + nq);
+  double* d2 = d1 + 2 * (size_t)nq;
+  double* dr = d2 + 2 * (size_t)nq;
+  int* dord = ctx->io_b.as<int>();
+  int* dout = dord + nq;
+  int* aux = ctx->mt_aux.as<int>();          // [0] bad-descriptor flag (matcher), [4] survivors, [5] tentatives
+  MG_PROF(ctx, "k_match_compact", 2, (double)nq);
+  k_match_compact<<<1, 1024, 0, ctx->stream>>>(ctx->mt_out.as<modsgpu_match>(), nq, dqxy, dtxy, mc, d1, d2, dr, aux + 5);
+  MG_LAUNCHED(ctx);
+  const bool dedup = dup_radius > 0;          // matching.cpp:2621-2625: a radius <= 0 disables the filter
+  if (dedup && (rc = dup_enqueue(ctx, d1, d2, dr, nq, aux + 5, dup_radius, dord, dout, aux + 4))) return rc;
+  MG_CUDA(ctx, ctx->h_stage.ensure((size_t)nq * (sizeof(modsgpu_match) + 4) + 64));
+  modsgpu_match* hm = ctx->h_stage.as<modsgpu_match>();
+  int* ho = reinterpret_cast<int*>(hm + nq);
+  int* hcnt = ho + nq;                        // [0] bad flag, [4] survivors, [5] tentatives
+  MG_CUDA(ctx, cudaMemcpyAsync(hm, mc, (size_t)nq * sizeof(modsgpu_match), cudaMemcpyDeviceToHost, ctx->stream));
+  if (dedup) MG_CUDA(ctx, cudaMemcpyAsync(ho, dout, (size_t)nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  MG_CUDA(ctx, cudaMemcpyAsync(hcnt, aux, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  if (mg_end(ctx)) return MODSGPU_ECUDA;
+  if (hcnt[0]) MG_FAIL(ctx, MODSGPU_EINVAL, "descriptors must hold integers in [0,255] (HardNet++ bytes / RootSIFT)");
+  const int T = hcnt[5];
+  memcpy(matches, hm, (size_t)T * sizeof(modsgpu_match));
+  *n_matches = T;
+  if (dedup) {
+    *n_unique = hcnt[4];
+    memcpy(order, ho, (size_t)hcnt[4] * 4);
+  } else {
+    for (int i = 0; i < T; i++) order[i] = i;
+    *n_unique = T;
+  }
+  return 0;
+}
+
 // =====================================================================================================================
 // MatchFLANNDistance (matching.cpp:574-633): binary descriptors (bytes = floor of the float entries, :596-608), the 2
 // nearest train descriptors by Hamming distance, a match whenever the nearest is within matchDistanceThreshold; ratio =
@@ -592,29 +722,7 @@ extern "C" int modsgpu_duplicate_filter(modsgpu_ctx* ctx, const double* xy1, con
   MG_CUDA(ctx, cudaMemcpyAsync(d2, xy2, xb, cudaMemcpyHostToDevice, ctx->stream));
   MG_CUDA(ctx, cudaMemcpyAsync(dr, ratio, rb, cudaMemcpyHostToDevice, ctx->stream));
   if (T <= DUP_MAX_T) {
-    const int nwords = (T + 31) / 32;
-    MG_CUDA(ctx, ctx->mt_d.ensure((size_t)T * nwords * 4 + (size_t)T * 4 + 16 + (size_t)T * 32));
-    unsigned* conf = ctx->mt_d.as<unsigned>();
-    int* rowflag = reinterpret_cast<int*>(conf + (size_t)T * nwords);
-    double* sxy = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(ctx->mt_d.p) + (((size_t)T * nwords * 4 + (size_t)T * 4 + 15) & ~(size_t)15));
-    MG_CUDA(ctx, cudaMemsetAsync(rowflag, 0, (size_t)T * 4, ctx->stream));
-    MG_PROF(ctx, "k_dup_rank", 2, (double)T);
-    k_dup_rank<<<(T + 63) / 64, 256, 0, ctx->stream>>>(dr, d1, d2, T, dord, sxy);
-    MG_LAUNCHED(ctx);
-    MG_PROF(ctx, "k_dup_conflicts", 2, (double)T);
-    k_dup_conflicts<<<dim3((nwords + 7) / 8, T), 256, 0, ctx->stream>>>(sxy, T, nwords, r * r, conf, rowflag);
-    MG_LAUNCHED(ctx);
-    // rows of the conflict matrix staged in shared memory: as many as 160 KB hold
-    constexpr int RESOLVE_SMEM = 160 * 1024;
-    static OnceFlags attr_set;
-    if (attr_set.need(ctx->device)) {
-      MG_CUDA(ctx, cudaFuncSetAttribute(k_dup_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, RESOLVE_SMEM));
-      attr_set.set(ctx->device);
-    }
-    const int cap_rows = std::min(T, RESOLVE_SMEM / (nwords * 4));
-    MG_PROF(ctx, "k_dup_resolve", 2, (double)T);
-    k_dup_resolve<<<1, 256, (size_t)cap_rows * nwords * 4, ctx->stream>>>(conf, rowflag, dord, T, nwords, cap_rows, dout, ctx->mt_aux.as<int>() + 4);
-    MG_LAUNCHED(ctx);
+    if (int rc = dup_enqueue(ctx, d1, d2, dr, T, nullptr, r, dord, dout, ctx->mt_aux.as<int>() + 4)) return rc;
   } else {
     MG_PROF(ctx, "k_dup_filter", 2, (double)T);
     k_dup_filter<<<1, 256, 0, ctx->stream>>>(d1, d2, dr, T, r * r, dord, alive, dout, ctx->mt_aux.as<int>() + 4);

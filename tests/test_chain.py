@@ -218,13 +218,14 @@ def test_pair_pipeline_device_descriptors_equal_host_route(mg):
     from mods_light_zmq_b200 import synth
     a, b, _ = synth.image_pair(seed=31, w=800, h=600)
     A, B = synth.gray_to_bgr(a), synth.gray_to_bgr(b)
-    dev = mg.pair_pipeline(A, B, seed=4)
-    os.environ["MODSGPU_HOST_DESC"] = "1"
-    try:
-        host = mg.pair_pipeline(A, B, seed=4)
-    finally:
-        del os.environ["MODSGPU_HOST_DESC"]
-    assert dev["tentatives"] > 100
-    for k in ("keypoints", "regions", "descriptors", "tentatives", "unique_tentatives", "inliers"):
-        assert dev[k] == host[k], k
-    assert np.array_equal(dev["H"], host["H"]) and np.array_equal(dev["inlier_xy"], host["inlier_xy"])
+    dev = mg.pair_pipeline(A, B, seed=4)           # descriptors on the device, matcher + duplicate filter in one call
+    assert dev["tentatives"] > 100 and dev["unique_tentatives"] < dev["tentatives"]
+    for env in ("MODSGPU_UNFUSED_TAIL", "MODSGPU_HOST_DESC"):      # two device calls; the host round trip of the seam route
+        os.environ[env] = "1"
+        try:
+            other = mg.pair_pipeline(A, B, seed=4)
+        finally:
+            del os.environ[env]
+        for k in ("keypoints", "regions", "descriptors", "tentatives", "unique_tentatives", "inliers"):
+            assert dev[k] == other[k], (env, k)
+        assert np.array_equal(dev["H"], other["H"]) and np.array_equal(dev["inlier_xy"], other["inlier_xy"]), env

@@ -5,6 +5,11 @@
 // keypoint list bit-identical to the CPU oracle (oracle/mods_oracle.cpp), which restates
 // pyramid.cpp:196-529 and the arithmetic order of cv::GaussianBlur / cv::resize.
 //
+// Launch structure per image (nS = 3): per octave three dependent blurs on the main stream (k_blur3<ks>: blur + response of
+// the blurred tile, the first one also the response of its source, the third one also the half-size base of the next
+// octave), the fourth blur and the octave's NMS + localisation on a side stream; k_resolve / k_rank_export at the end.
+// The sequence is captured into one CUDA graph per image buffer (mg_detect_graph).
+//
 // Data layout in HBM: one workspace holds, per octave o (w_o x h_o, dense row-major fp32),
 // five blur levels L[0..4] and five responses R[0..4]; an int32 "octave map" (w_o x h_o)
 // resolves the reference's sequential octaveMap de-duplication (pyramid.cpp:387-391)

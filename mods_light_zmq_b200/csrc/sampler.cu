@@ -197,17 +197,24 @@ k_sample_small(const float* __restrict__ img, int w, int h, const PatchMeta* __r
 // =================================================================================================
 // Register-blocked kernels (the common case: ks >= 7).
 //
-// What bounds the sampler is instruction issue and L1 tag bandwidth, not HBM: the image (3 MB) is L2/L1
-// resident and a region costs R^2 bilinear gathers plus ~18 R^2 (pairs form) / 2 ks R^2 (full form)
-// sequentially ordered FMAs.  Two rules shape the kernels below:
+// What bounds the sampler is not HBM: the image (3 MB) is L2 resident and a region costs R^2 bilinear gathers plus
+// ~18 R^2 (pairs form) / 2 ks R^2 (full form) sequentially ordered FMAs.  Measured (profiles/r02_ncu_hot_k_sample_*.txt):
+// class B issues on two thirds of the cycles, the rest is split between barriers, gather latency, shared-memory latency
+// inside the FMA chains and the sequentially rounded coordinate replay; class A is barrier bound.  Shared-memory bank
+// conflicts matter more than instruction counts (the class B row pass lost 20 % to them).  The rules that shape the kernels:
 //  (1) gathers are issued by 8 lanes walking 8 CONSECUTIVE samples of a row (a warp = 4 such groups, usually
 //      32 consecutive samples): a load touches 2-4 cache lines instead of 32.  The reference accumulates
 //      sample coordinates sequentially in float (WX += a11), so one thread per row first walks its whole row
-//      and records the coordinate of every 8th sample (C2 table); a lane then replays <= 7 additions.
+//      and records the coordinate of every 8th (4th: class B1) sample (C2 table); a lane then replays <= 7 (3) additions.
+//      The same walk proves a row interior (first and last sample inside the image => all of them: the sequence is
+//      monotone), and interior rows are sampled without any bounds handling.
 //  (2) the separable blur is register blocked: a thread owns CB adjacent columns x RB rows, loads one tap and
 //      RB samples per step and issues RB*CB FMAs on them (taps rotate through registers), instead of
 //      two shared-memory loads and a clamp per FMA.  Borders are replicated into padding so the inner loops
 //      have no clamps; zero taps appended to the tap array keep the FMA chains bit-exact (fma(d, 0, s) == s).
+//      Lanes are laid out so that a warp's shared-memory accesses fall into 32 different banks (class B: lane = row of
+//      the block with an odd row pitch).
+//  (3) CTA size follows the work per phase: 128 threads for R <= 40, 256 above.
 // Only the columns/rows the final 32x32 resampling reads are filtered when R >= 66 (pairs x_i, x_i + 1).
 // =================================================================================================
 constexpr int SEG = 8;

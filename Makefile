@@ -10,7 +10,7 @@ EXACT = --fmad=false
 
 OBJS = $(OBJ)/api.o $(OBJ)/detect.o $(OBJ)/sampler.o $(OBJ)/cnn.o $(OBJ)/match.o $(OBJ)/ransac.o $(OBJ)/ransac_f.o $(OBJ)/synth.o $(OBJ)/classic.o $(OBJ)/chain.o $(OBJ)/npz.o $(OBJ)/mods_host.o
 
-all: $(PKG)/libmodsgpu.so $(PKG)/libmodsgpu_degensac.so oracle
+all: $(PKG)/libmodsgpu.so $(PKG)/libmodsgpu_degensac.so oracle example
 
 $(OBJ)/detect.o: $(SRC)/detect.cu $(SRC)/common.cuh include/modsgpu.h
 	@mkdir -p $(OBJ)
@@ -50,11 +50,16 @@ $(PKG)/libmodsgpu.so: $(OBJS)
 $(PKG)/libmodsgpu_degensac.so: $(SRC)/compat/degensac_compat.cpp include/modsgpu.h $(PKG)/libmodsgpu.so
 	g++ -O2 -std=c++17 -fPIC -shared -o $@ $< -L$(PKG) -lmodsgpu -Wl,-rpath,'$$ORIGIN'
 
+# smallest host program over the C ABI (plain C): one pair, PPM / PGM in, correspondences out
+example: examples/mods_pair
+examples/mods_pair: examples/mods_pair.c include/modsgpu.h $(PKG)/libmodsgpu.so
+	gcc -O2 -std=c11 -Wall -Iinclude -o $@ $< -L$(PKG) -lmodsgpu -Wl,-rpath,'$$ORIGIN/../$(PKG)'
+
 oracle:
 	$(MAKE) -C oracle -s all
 
 clean:
-	rm -rf $(OBJ) $(PKG)/libmodsgpu.so $(PKG)/libmodsgpu_degensac.so
+	rm -rf $(OBJ) $(PKG)/libmodsgpu.so $(PKG)/libmodsgpu_degensac.so examples/mods_pair
 	$(MAKE) -C oracle clean
 
-.PHONY: all oracle clean
+.PHONY: all oracle clean example

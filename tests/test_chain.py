@@ -229,3 +229,30 @@ def test_pair_pipeline_device_descriptors_equal_host_route(mg):
         for k in ("keypoints", "regions", "descriptors", "tentatives", "unique_tentatives", "inliers"):
             assert dev[k] == other[k], (env, k)
         assert np.array_equal(dev["H"], other["H"]) and np.array_equal(dev["inlier_xy"], other["inlier_xy"]), env
+
+
+@pytest.mark.gpu
+def test_plain_c_example_equals_binding(mg, tmp_path):
+    """examples/mods_pair.c (plain C11 over include/modsgpu.h, built by `make`): two PGM files in, verified
+    correspondences out -- the same counts, H and correspondences as the ctypes binding gives for the same pair."""
+    import subprocess
+    from mods_light_zmq_b200 import synth
+    root = os.path.dirname(HERE)
+    exe = os.path.join(root, "examples", "mods_pair")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", root, "example"], check=True, timeout=300)
+    a, b, _ = synth.image_pair(seed=12, w=640, h=480)
+    paths = []
+    for name, u8 in (("a.pgm", a), ("b.pgm", b)):
+        p = str(tmp_path / name)
+        with open(p, "wb") as f:
+            f.write(b"P5\n# synthetic\n%d %d\n255\n" % (u8.shape[1], u8.shape[0]))
+            f.write(np.ascontiguousarray(u8, np.uint8).tobytes())
+        paths.append(p)
+    ref = mg.pair_pipeline(synth.gray_to_bgr(a), synth.gray_to_bgr(b), seed=12345)
+    for overlap in ("0", "1"):
+        r = subprocess.run([exe, paths[0], paths[1], os.path.join(root, "weights"), overlap], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        xy = np.array([[float(v) for v in line.split()] for line in r.stdout.splitlines() if line.strip()])
+        assert "verified %d" % ref["inliers"] in r.stderr and "tentatives %d," % ref["tentatives"] in r.stderr, r.stderr
+        assert xy.shape == (ref["inliers"], 4) and np.allclose(xy, ref["inlier_xy"], rtol=0, atol=1e-6)

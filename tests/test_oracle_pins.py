@@ -331,6 +331,24 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), n
 
 
+def test_header_is_plain_c_and_example_refuses_without_gpu(tmp_path):
+    """include/modsgpu.h compiles as C11 (no C++ in the boundary) and the plain-C example program builds against the
+    shipped library; without an sm_100 device it stops at modsgpu_create with a message -- there is no CPU path."""
+    import subprocess
+    import torch
+    exe = str(tmp_path / "mods_pair")
+    pkg = os.path.join(ROOT, "mods_light_zmq_b200")
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"), "-o", exe,
+                    os.path.join(ROOT, "examples", "mods_pair.c"), "-L" + pkg, "-lmodsgpu", "-Wl,-rpath," + pkg], check=True, timeout=120)
+    if torch.cuda.is_available():
+        return
+    pgm = str(tmp_path / "x.pgm")
+    with open(pgm, "wb") as f:
+        f.write(b"P5\n8 8\n255\n" + bytes(64))
+    r = subprocess.run([exe, pgm, pgm, os.path.join(ROOT, "weights")], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "modsgpu_create" in r.stderr and "no CPU path" in r.stderr
+
+
 def test_no_cpu_fallback_without_gpu():
     """Without an sm_100 device the product refuses to run (MODSGPU_ENODEV) instead of falling back."""
     import torch

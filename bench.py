@@ -215,8 +215,10 @@ def pin_to_gpu_numa_node(local_rank):
         for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
             a, _, b = part.partition("-")
             cpus.update(range(int(a), int(b or a) + 1))
-        cpus &= os.sched_getaffinity(0)
-        if cpus:
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        # never shrink the rank to a sliver of the machine (a cgroup may expose only a few CPUs of that node)
+        if len(cpus) >= 4 and 4 * len(cpus) >= len(allowed):
             os.sched_setaffinity(0, cpus)
             return {"numa_node": node, "cpus": len(cpus)}
     except (OSError, ValueError, subprocess.SubprocessError):
